@@ -1,0 +1,335 @@
+/* trb.h — C ABI of the B200-native render path for tray_rust.
+ *
+ * This is the drop-in boundary for ONE path of the reference: the call
+ *     Exec::render(&mut self, scene: &mut Scene, rt: &mut RenderTarget, config: &Config)
+ * (/root/reference/src/exec/mod.rs:41-49; sole implementation
+ * exec::MultiThreaded, src/exec/multithreaded.rs:54-114) and the data it consumes
+ * (Scene, src/scene.rs:93-98) and produces (the RGBW f32 film in the layout of
+ * RenderTarget::get_renderf32, src/film/render_target.rs:243-265).
+ *
+ * Everything here is plain C: POD structs, pointers and sizes. No torch types, no
+ * C++ types, no callbacks into the host. The library owns all device memory behind
+ * the opaque trb_scene handle; host buffers are borrowed for the duration of a call.
+ *
+ * All entry points return trb_status; on failure trb_last_error() (thread-local)
+ * describes why. The conditions the reference panics on (image not a multiple of the
+ * 8x8 block, no lights, empty scene, unknown types) are reported as
+ * TRB_INVALID_ARG / TRB_UNSUPPORTED instead of aborting the process.
+ */
+#ifndef TRB_H
+#define TRB_H
+
+#include <stdint.h>
+#include <stddef.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define TRB_ABI_VERSION 1u
+
+typedef enum trb_status {
+    TRB_OK = 0,
+    TRB_INVALID_ARG = 1, /* what the reference would panic!/assert! on */
+    TRB_CUDA = 2,        /* a CUDA runtime call or kernel failed */
+    TRB_OOM = 3,
+    TRB_UNSUPPORTED = 4, /* valid in the reference, not in this build */
+    TRB_IO = 5,
+    TRB_NO_DEVICE = 6    /* no CUDA device: this library has no CPU fallback */
+} trb_status;
+
+/* ---------------------------------------------------------------------------------
+ * Scene description (source-level, nothing derived: no matrices, no BVH).
+ * It is the FFI-safe flattening of `Scene` + `RenderTarget` construction arguments
+ * (src/scene.rs:93-146). Every array is caller-owned and deep-copied by
+ * trb_scene_create.
+ * ------------------------------------------------------------------------------- */
+
+/* linalg::Keyframe (src/linalg/keyframe.rs:14-21): translation, rotation quaternion
+ * (v.x, v.y, v.z, w), scaling. The reference stores EVERY transform this way (even a
+ * static JSON one, src/linalg/animated_transform.rs:34-37) and recomposes T*R*S per
+ * ray (keyframe.rs:60-63), so the TRS triple — not a matrix — is the ABI. */
+typedef struct trb_keyframe {
+    float translation[3];
+    float rotation[4];
+    float scaling[3];
+} trb_keyframe;
+
+/* bspline::BSpline<Keyframe> (animated_transform.rs:22-37): control points
+ * keyframes[ctrl_first .. ctrl_first+n_ctrl), knots[knot_first .. knot_first+n_knots). */
+typedef struct trb_spline {
+    uint32_t degree;
+    uint32_t n_ctrl;
+    uint32_t ctrl_first;
+    uint32_t n_knots;
+    uint32_t knot_first;
+} trb_spline;
+
+/* film::ColorKeyframe (src/film/animated_color.rs:12-17), sorted by time. */
+typedef struct trb_color_key {
+    float rgba[4];
+    float time;
+} trb_color_key;
+
+enum { /* geometry::Instance / EmitterType (src/geometry/instance.rs:81-84, emitter.rs:74-79) */
+    TRB_INST_RECEIVER = 0,
+    TRB_INST_EMITTER_AREA = 1,
+    TRB_INST_EMITTER_POINT = 2
+};
+enum { /* shapes reachable from scene.rs:513-580 */
+    TRB_SHAPE_NONE = 0,   /* point light */
+    TRB_SHAPE_SPHERE = 1, /* p0 = radius                       (geometry/sphere.rs)    */
+    TRB_SHAPE_DISK = 2,   /* p0 = radius, p1 = inner_radius    (geometry/disk.rs)      */
+    TRB_SHAPE_RECT = 3,   /* p0 = width,  p1 = height; "plane" = 2x2 (scene.rs:527-528) */
+    TRB_SHAPE_MESH = 4    /* mesh = index into meshes          (geometry/mesh.rs)      */
+};
+
+/* One geometry::Instance in JSON object order (group members flattened in place,
+ * scene.rs:496-505). The AnimatedTransform is splines[spline_first .. +n_splines) in
+ * application order (animated_transform.rs:42-54: transform = t_i * transform). */
+typedef struct trb_instance {
+    uint32_t kind;
+    uint32_t shape;
+    float p0, p1;
+    uint32_t mesh;
+    uint32_t material;
+    uint32_t spline_first, n_splines;
+    uint32_t emission_first, n_emission; /* color keys; emitters only */
+} trb_instance;
+
+/* geometry::Mesh buffers as produced by Mesh::load_obj (mesh.rs:49-76): positions and
+ * normals 3 floats per vertex, texcoords 2 floats per vertex, 3 indices per triangle. */
+typedef struct trb_mesh {
+    uint32_t n_verts;
+    uint32_t n_tris;
+    const float* positions;
+    const float* normals;
+    const float* texcoords;
+    const uint32_t* indices;
+} trb_mesh;
+
+enum { /* material types (src/material/), constant textures only (texture/mod.rs) */
+    TRB_MAT_MATTE = 0,          /* c0 = diffuse, roughness (degrees; 0 => Lambertian) */
+    TRB_MAT_PLASTIC = 1,        /* c0 = diffuse, c1 = gloss, roughness                */
+    TRB_MAT_METAL = 2,          /* c0 = refractive_index, c1 = absorption_coefficient, roughness */
+    TRB_MAT_SPECULAR_METAL = 3, /* c0 = refractive_index, c1 = absorption_coefficient */
+    TRB_MAT_GLASS = 4,          /* c0 = reflect, c1 = transmit, eta                   */
+    TRB_MAT_ROUGH_GLASS = 5,    /* c0 = reflect, c1 = transmit, eta, roughness        */
+    TRB_MAT_MERL = 6            /* merl = index into merl_tables                       */
+};
+typedef struct trb_material {
+    uint32_t type;
+    float c0[3];
+    float c1[3];
+    float roughness;
+    float eta;
+    uint32_t merl;
+} trb_material;
+
+#define TRB_MERL_N_THETA_H 90u
+#define TRB_MERL_N_THETA_D 90u
+#define TRB_MERL_N_PHI_D 180u
+#define TRB_MERL_TABLE_FLOATS (90u * 90u * 180u * 3u) /* interleaved RGB f32 as built by material::Merl::load_file (merl.rs:51-84) */
+
+/* film::Camera construction arguments (src/film/camera.rs:64-91). Animated fov
+ * (camera.rs:95-125): fov_ctrl/fov_knots non-empty. */
+typedef struct trb_camera {
+    uint32_t spline_first, n_splines; /* cam_world AnimatedTransform */
+    float fov;                        /* degrees */
+    float shutter_size;               /* default 0.5 (scene.rs:197-200) */
+    uint32_t active_at;
+    uint32_t fov_degree, n_fov_ctrl, fov_ctrl_first, n_fov_knots, fov_knot_first; /* into fov_floats */
+} trb_camera;
+
+enum { TRB_FILTER_MITCHELL_NETRAVALI = 0, TRB_FILTER_GAUSSIAN = 1 };
+typedef struct trb_film {
+    uint32_t width, height;  /* multiples of 8 (block_queue.rs:29-31) and of 2 (render_target.rs:43-45) */
+    uint32_t samples;        /* spp; rounded up to a power of two (ld.rs:22-26) */
+    uint32_t frames, start_frame, end_frame;
+    float scene_time;
+    uint32_t filter_type;
+    float filter_w, filter_h;
+    float filter_b, filter_c; /* Mitchell-Netravali b,c; Gaussian: filter_b = alpha */
+} trb_film;
+
+enum { TRB_INTEGRATOR_PATH = 0 };
+typedef struct trb_integrator {
+    uint32_t type;
+    uint32_t min_depth, max_depth; /* integrator/path.rs:35-43 */
+} trb_integrator;
+
+typedef struct trb_scene_desc {
+    uint32_t abi_version; /* TRB_ABI_VERSION */
+    trb_film film;
+    trb_integrator integrator;
+    uint32_t n_cameras;   const trb_camera* cameras;     /* sorted by active_at (scene.rs:190) */
+    uint32_t n_instances; const trb_instance* instances; /* JSON object order == light order (Q20) */
+    uint32_t n_splines;   const trb_spline* splines;
+    uint32_t n_keyframes; const trb_keyframe* keyframes;
+    uint32_t n_knots;     const float* knots;
+    uint32_t n_color_keys; const trb_color_key* color_keys;
+    uint32_t n_meshes;    const trb_mesh* meshes;
+    uint32_t n_materials; const trb_material* materials;
+    uint32_t n_merl;      const float* const* merl_tables; /* each TRB_MERL_TABLE_FLOATS floats */
+    uint32_t n_fov_floats; const float* fov_floats;
+} trb_scene_desc;
+
+/* ---------------------------------------------------------------------------------
+ * Render configuration = exec::Config (src/exec/mod.rs:17-37) minus paths/threads,
+ * plus what the reference leaves to the OS: the RNG seed (multithreaded.rs:79 seeds
+ * StdRng from the OS; see DESIGN.md "RNG") and a sample sub-range so a frame can be
+ * rendered in additive passes.
+ * ------------------------------------------------------------------------------- */
+enum {
+    TRB_RENDER_STATS = 1u,       /* also count BVH node / triangle / instance tests */
+    TRB_RENDER_NO_UPDATE = 2u    /* skip Scene::update_frame (caller already did it) */
+};
+typedef struct trb_render_cfg {
+    uint32_t spp;           /* Config.spp; 0 = film.samples. Rounded up to pow2 like ld.rs:22-26 */
+    uint32_t sample_first;  /* render sample indices [sample_first, sample_first+sample_count) */
+    uint32_t sample_count;  /* of each pixel's spp; 0 = all */
+    uint32_t block_start;   /* Config.select_blocks.0 (index into the Morton-sorted 8x8 block list) */
+    uint32_t block_count;   /* Config.select_blocks.1; 0 = all blocks (block_queue.rs:39-41) */
+    uint32_t current_frame; /* Config.current_frame */
+    uint32_t seed;
+    uint32_t flags;
+} trb_render_cfg;
+
+typedef struct trb_stats {
+    uint64_t camera_samples;
+    uint64_t rays_primary;      /* multithreaded.rs:97        */
+    uint64_t rays_shadow;       /* light/mod.rs:30-37         */
+    uint64_t rays_mis;          /* integrator/mod.rs:156-157  */
+    uint64_t rays_continuation; /* integrator/path.rs:112     */
+    uint64_t node_tests;        /* BBox::fast_intersect calls (TLAS + BLAS); TRB_RENDER_STATS only */
+    uint64_t tri_tests;         /* intersect_triangle calls;                 TRB_RENDER_STATS only */
+    uint64_t inst_tests;        /* Instance::intersect calls;                TRB_RENDER_STATS only */
+    float kernel_ms;            /* device time of the render kernels of this call (CUDA events) */
+    float update_ms;            /* host time of Scene::update_frame + upload */
+} trb_stats;
+
+/* linalg::Ray without depth/time (src/linalg/ray.rs:9-22): 32 bytes. */
+typedef struct trb_ray {
+    float o[3];
+    float d[3];
+    float min_t, max_t;
+} trb_ray;
+
+/* Result of Scene::intersect (scene.rs:148-150): ray.max_t after traversal, the
+ * instance hit (index into instances) and, for meshes, the triangle index.
+ * inst == TRB_MISS when nothing was hit. 16 bytes. */
+#define TRB_MISS 0xffffffffu
+typedef struct trb_hit {
+    float t;
+    uint32_t inst;
+    uint32_t prim;
+    uint32_t pad;
+} trb_hit;
+
+/* Per camera sample record for parity tests: film position and the clamped radiance
+ * pushed as ImageSample (multithreaded.rs:98-102). */
+typedef struct trb_sample {
+    float x, y;
+    float r, g, b;
+} trb_sample;
+
+/* Flattened BVH node in the reference's order (bvh.rs:248-267): interior: a =
+ * second_child, b = axis (0,1,2); leaf: a = geom_offset, b = 0x80000000 | ngeom. */
+typedef struct trb_bvh_node {
+    float bmin[3];
+    float bmax[3];
+    uint32_t a;
+    uint32_t b;
+} trb_bvh_node;
+#define TRB_BVH_LEAF 0x80000000u
+
+typedef struct trb_scene trb_scene;
+
+/* -- lifecycle -------------------------------------------------------------------- */
+
+/* ≙ the construction half of Scene::load_file (scene.rs:101-146): builds each mesh's
+ * BVH<Triangle> (mesh.rs:44, max_geom 16) and uploads the scene to `device`
+ * (cudaSetDevice ordinal). */
+trb_status trb_scene_create(const trb_scene_desc* desc, int device, trb_scene** out);
+
+/* ≙ Scene::load_file(file) (scene.rs:101): JSON + OBJ + MERL loading, then
+ * trb_scene_create. width/height/spp > 0 override film.width/height/samples (the
+ * BASELINE.json configs do this). */
+trb_status trb_scene_load_json(const char* path, uint32_t width, uint32_t height, uint32_t spp,
+                               int device, trb_scene** out);
+
+void trb_scene_destroy(trb_scene* scene);
+
+/* film dimensions and rounded spp of a scene */
+trb_status trb_scene_info(const trb_scene* scene, uint32_t* width, uint32_t* height, uint32_t* spp,
+                          uint32_t* n_blocks, uint32_t* n_instances, uint32_t* n_lights);
+
+/* ≙ Scene::update_frame(frame, start, end) (scene.rs:152-176): selects the camera,
+ * sets the shutter interval, recomposes instance transforms, rebuilds the
+ * BVH<Instance> (max_geom 4) for the shutter interval and uploads it. */
+trb_status trb_scene_update_frame(trb_scene* scene, uint32_t frame, float start, float end);
+
+/* -- the hot path ------------------------------------------------------------------ */
+
+/* ≙ Exec::render (exec/mod.rs:48; multithreaded.rs:55-70). Renders the selected
+ * blocks/samples on the scene's GPU and ADDS the RGBW film (row-major, width*height*4
+ * floats, layout of get_renderf32 render_target.rs:243-265) into the HOST buffer
+ * `film_rgbw` — additive like film::Image::add_pixels (film/image.rs:21-33).
+ * Includes update_frame unless TRB_RENDER_NO_UPDATE. Blocking. */
+trb_status trb_render(trb_scene* scene, const trb_render_cfg* cfg, float* film_rgbw, trb_stats* stats);
+
+/* Same, but the film is a DEVICE buffer on the scene's GPU (accumulated into), and the
+ * work is enqueued on `cuda_stream` (a cudaStream_t; NULL = default stream) without
+ * host synchronisation. Never calls update_frame. `stats` (may be NULL) is a DEVICE
+ * pointer to a trb_stats the kernels accumulate ray counters into. */
+trb_status trb_render_device(trb_scene* scene, const trb_render_cfg* cfg, float* d_film_rgbw,
+                             trb_stats* d_stats, void* cuda_stream);
+
+/* ≙ Scene::intersect (scene.rs:148-150) for a batch of rays: closest hit through the
+ * two-level BVH in the reference's traversal order. Host buffers. */
+trb_status trb_intersect(trb_scene* scene, size_t n, const trb_ray* rays, trb_hit* hits, trb_stats* stats);
+
+/* Device-buffer variant of trb_intersect, enqueued on cuda_stream. */
+trb_status trb_intersect_device(trb_scene* scene, size_t n, const trb_ray* d_rays, trb_hit* d_hits,
+                                trb_stats* d_stats, void* cuda_stream);
+
+/* ≙ LowDiscrepancy::get_samples + get_samples_1d + Camera::generate_ray
+ * (ld.rs:33-64, camera.rs:150-157) for the selected blocks/samples: writes one ray and
+ * one film position per camera sample, in block-list order, pixel row-major within the
+ * block, sample index minor. Host buffers sized n = blocks*64*sample_count. */
+trb_status trb_camera_rays(trb_scene* scene, const trb_render_cfg* cfg, size_t n, trb_ray* rays, float* xy);
+
+/* Parity/debug variant of trb_render: instead of splatting, writes the clamped
+ * radiance of every camera sample (same order as trb_camera_rays). Host buffer. */
+trb_status trb_render_samples(trb_scene* scene, const trb_render_cfg* cfg, size_t n, trb_sample* samples,
+                              trb_stats* stats);
+
+/* ≙ RenderTarget::get_render (render_target.rs:185-210): rgb/weight, clamp, sRGB,
+ * (c*255) as u8; pixels with weight <= 0 stay 0. Host buffers; runs on the scene's GPU. */
+trb_status trb_film_to_srgb8(trb_scene* scene, const float* film_rgbw, uint8_t* rgb8);
+
+/* -- introspection for parity tests ------------------------------------------------ */
+
+/* The Morton-sorted 8x8 block list (block_queue.rs:28-46) after select_blocks: pairs (bx,by). */
+trb_status trb_block_list(const trb_scene* scene, uint32_t block_start, uint32_t block_count,
+                          uint32_t* n_out, uint32_t* xy_pairs, uint32_t capacity);
+
+/* Flattened BVH in the reference's node order. which = -1: BVH<Instance> (after
+ * update_frame); which >= 0: the BVH<Triangle> of mesh `which`. Pass NULL buffers to
+ * query sizes. `ordered` is bvh.rs `ordered_geom`. */
+trb_status trb_scene_get_bvh(const trb_scene* scene, int which, uint32_t* n_nodes, trb_bvh_node* nodes,
+                             uint32_t* n_ordered, uint32_t* ordered);
+
+/* World transform (mat, inv: 16 floats each, row-major) of instance i after update_frame. */
+trb_status trb_scene_get_transform(const trb_scene* scene, uint32_t inst, float* mat16, float* inv16);
+
+/* The 16x16 filter table (render_target.rs:50-57). */
+trb_status trb_scene_get_filter_table(const trb_scene* scene, float* table256);
+
+const char* trb_last_error(void);
+uint32_t trb_abi_version(void);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* TRB_H */
