@@ -181,8 +181,10 @@ typedef struct trb_scene_desc {
  * rendered in additive passes.
  * ------------------------------------------------------------------------------- */
 enum {
-    TRB_RENDER_STATS = 1u,       /* also count BVH node / triangle / instance tests */
-    TRB_RENDER_NO_UPDATE = 2u    /* skip Scene::update_frame (caller already did it) */
+    TRB_RENDER_STATS = 1u,            /* also count BVH node / triangle / instance tests */
+    TRB_RENDER_NO_UPDATE = 2u,        /* skip Scene::update_frame (caller already did it) */
+    TRB_RENDER_REFERENCE_SHADOW = 4u  /* trace shadow rays as full closest-hit like light/mod.rs:30-37 instead of
+                                         stopping at the first accepted hit (same boolean, fewer tests) */
 };
 typedef struct trb_render_cfg {
     uint32_t spp;           /* Config.spp; 0 = film.samples. Rounded up to pow2 like ld.rs:22-26 */
@@ -325,6 +327,22 @@ trb_status trb_scene_get_transform(const trb_scene* scene, uint32_t inst, float*
 
 /* The 16x16 filter table (render_target.rs:50-57). */
 trb_status trb_scene_get_filter_table(const trb_scene* scene, float* table256);
+
+/* -- host-only helpers (no device needed; used by the CPU test-suite) ---------------- */
+
+/* BVH::new over `n` boxes (6 floats each: min xyz, max xyz) with the reference's SAH
+ * build (bvh.rs:139-267). Pass NULL buffers to query sizes. */
+trb_status trb_host_build_bvh(const float* boxes6, uint32_t n, uint32_t max_geom, uint32_t* n_nodes,
+                              trb_bvh_node* nodes, uint32_t* ordered);
+
+/* Keyframe::transform (keyframe.rs:60-63): T * R * S and its inverse, row-major. */
+trb_status trb_host_keyframe_transform(const trb_keyframe* kf, float* mat16, float* inv16);
+
+/* The JSON loader alone (Scene::load_file up to the flattened description): the result is
+ * owned by the library; release with trb_desc_free. */
+trb_status trb_desc_load_json(const char* path, uint32_t width, uint32_t height, uint32_t spp,
+                              trb_scene_desc** out);
+void trb_desc_free(trb_scene_desc* desc);
 
 const char* trb_last_error(void);
 uint32_t trb_abi_version(void);

@@ -1,0 +1,683 @@
+// trb_api.cu — the C ABI of include/trb.h: scene upload, per-frame update and kernel launches.
+// Everything that touches device memory lives here; there is no CPU rendering path in this library.
+#include <chrono>
+#include <cstdio>
+#include <cstdlib>
+#include <memory>
+#include "trb_host.h"
+#include "trb_kernels.cuh"
+
+using namespace trbh;
+
+namespace {
+
+thread_local std::string g_error;
+trb_status fail(trb_status s, const std::string& msg) { g_error = msg; return s; }
+
+#define CU(call)                                                                                                   \
+    do {                                                                                                           \
+        cudaError_t e_ = (call);                                                                                   \
+        if (e_ != cudaSuccess) return fail(e_ == cudaErrorMemoryAllocation ? TRB_OOM : TRB_CUDA,                   \
+                                           std::string(#call) + ": " + cudaGetErrorString(e_));                    \
+    } while (0)
+
+struct DeviceArena { // owns every cudaMalloc of a scene
+    std::vector<void*> ptrs;
+    ~DeviceArena() { for (void* p : ptrs) cudaFree(p); }
+    template <class T>
+    cudaError_t upload(const T* host, size_t n, T** out) {
+        void* d = nullptr;
+        cudaError_t e = cudaMalloc(&d, std::max<size_t>(1, n) * sizeof(T));
+        if (e != cudaSuccess) return e;
+        ptrs.push_back(d);
+        if (n) e = cudaMemcpy(d, host, n * sizeof(T), cudaMemcpyHostToDevice);
+        *out = static_cast<T*>(d);
+        return e;
+    }
+    template <class T>
+    cudaError_t alloc(size_t n, T** out) {
+        void* d = nullptr;
+        cudaError_t e = cudaMalloc(&d, std::max<size_t>(1, n) * sizeof(T));
+        if (e != cudaSuccess) return e;
+        ptrs.push_back(d);
+        *out = static_cast<T*>(d);
+        return e;
+    }
+};
+
+struct HostMesh {
+    std::vector<float> pos, nrm, uv;
+    std::vector<uint32_t> idx;
+    std::vector<trb_bvh_node> nodes;
+    std::vector<uint32_t> order;
+    Box3 bounds;
+};
+
+uint32_t pow2_ceil(uint32_t v) { uint32_t p = 1; while (p < v) p <<= 1; return p; }
+
+void pack_nodes(const std::vector<trb_bvh_node>& in, std::vector<trb::DNode>& out) {
+    out.resize(in.size());
+    for (size_t i = 0; i < in.size(); ++i) {
+        out[i].lo = make_float4(in[i].bmin[0], in[i].bmin[1], in[i].bmin[2], 0.f);
+        out[i].hi = make_float4(in[i].bmax[0], in[i].bmax[1], in[i].bmax[2], 0.f);
+        std::memcpy(&out[i].lo.w, &in[i].a, 4);
+        std::memcpy(&out[i].hi.w, &in[i].b, 4);
+    }
+}
+
+} // namespace
+
+struct trb_scene {
+    int device = 0;
+    int sm_count = 148;
+    // deep copy of the description
+    trb_film film{};
+    trb_integrator integrator{};
+    std::vector<trb_camera> cameras;
+    std::vector<trb_instance> instances;
+    std::vector<trb_spline> splines;
+    std::vector<trb_keyframe> keyframes;
+    std::vector<float> knots;
+    std::vector<trb_color_key> color_keys;
+    std::vector<trb_material> materials;
+    std::vector<HostMesh> meshes;
+    uint32_t spp_pow2 = 1;
+    // per-frame host state
+    int active_camera = -1;
+    float shutter_open = 0, shutter_close = 0;
+    std::vector<Xf> world; // instance world transforms of the current frame
+    std::vector<trb_bvh_node> tlas_nodes;
+    std::vector<uint32_t> tlas_order;
+    float table[256];
+    // device
+    DeviceArena arena;
+    trb::DScene ds{};
+    trb::DInstance* d_instances = nullptr;
+    trb::DNode* d_tlas = nullptr;
+    uint32_t* d_tlas_order = nullptr;
+    size_t tlas_capacity = 0;
+    uint2* d_blocks = nullptr;
+    size_t blocks_capacity = 0;
+    std::vector<uint32_t> cached_blocks;
+    uint32_t cached_block_start = 0xffffffffu, cached_block_count = 0xffffffffu;
+    uint32_t* d_counter = nullptr;
+    int* d_error = nullptr;
+    trb::DStats* d_stats = nullptr;
+    float4* d_film = nullptr;
+    float* h_film_staging = nullptr; // pinned
+    cudaEvent_t ev0 = nullptr, ev1 = nullptr;
+    bool frame_ready = false;
+    ~trb_scene() {
+        if (h_film_staging) cudaFreeHost(h_film_staging);
+        if (ev0) cudaEventDestroy(ev0);
+        if (ev1) cudaEventDestroy(ev1);
+    }
+};
+
+namespace {
+
+// AnimatedTransform::transform for an instance whose splines all hold one control point
+// (animated_transform.rs:42-54: transform = t_i * transform, starting from the identity).
+bool static_world_xf(const trb_scene& s, uint32_t first, uint32_t n, Xf& out) {
+    Xf acc = xf_identity();
+    for (uint32_t i = first; i < first + n; ++i) {
+        const trb_spline& sp = s.splines[i];
+        if (sp.n_ctrl != 1) return false;
+        acc = xf_compose(keyframe_xf(s.keyframes[sp.ctrl_first]), acc);
+    }
+    out = acc;
+    return true;
+}
+
+Box3 shape_bounds(const trb_scene& s, const trb_instance& in) {
+    Box3 b;
+    switch (in.shape) {
+        case TRB_SHAPE_SPHERE: for (int i = 0; i < 3; ++i) { b.lo[i] = -in.p0; b.hi[i] = in.p0; } break;          // sphere.rs:84-88
+        case TRB_SHAPE_DISK: b.lo[0] = b.lo[1] = -in.p0; b.hi[0] = b.hi[1] = in.p0; b.lo[2] = -0.1f; b.hi[2] = 0.1f; break; // disk.rs:79-81
+        case TRB_SHAPE_RECT: { const float hw = in.p0 / 2.0f, hh = in.p1 / 2.0f; b.lo[0] = -hw; b.lo[1] = -hh; b.hi[0] = hw; b.hi[1] = hh; b.lo[2] = b.hi[2] = 0.0f; break; } // rectangle.rs:67-71
+        case TRB_SHAPE_MESH: b = s.meshes[in.mesh].bounds; break;                                                   // mesh.rs:87-90
+        default: for (int i = 0; i < 3; ++i) b.lo[i] = b.hi[i] = 0.0f;                                            // point light (emitter.rs:152)
+    }
+    return b;
+}
+
+trb_status validate(const trb_scene_desc* d) {
+    if (!d) return fail(TRB_INVALID_ARG, "null scene description");
+    if (d->abi_version != TRB_ABI_VERSION) return fail(TRB_INVALID_ARG, "trb_scene_desc.abi_version mismatch");
+    if (d->film.width == 0 || d->film.height == 0 || d->film.width % 8 || d->film.height % 8)
+        return fail(TRB_INVALID_ARG, "Image not evenly divided by blocks of (8, 8)"); // block_queue.rs:29-31
+    if (d->film.frames == 0) return fail(TRB_INVALID_ARG, "film.frames must be >= 1");
+    if (d->n_instances == 0) return fail(TRB_INVALID_ARG, "Aborting: the scene does not have any objects!"); // scene.rs:134
+    if (d->n_cameras == 0) return fail(TRB_INVALID_ARG, "Error: A camera is required!");
+    if (d->integrator.type != TRB_INTEGRATOR_PATH) return fail(TRB_UNSUPPORTED, "only the pathtracer integrator is implemented");
+    if (!(d->film.filter_w > 0.0f && d->film.filter_h > 0.0f)) return fail(TRB_INVALID_ARG, "filter width/height must be positive");
+    if (floorf(d->film.filter_w / 0.5f) > 8.0f || floorf(d->film.filter_h / 0.5f) > 8.0f) return fail(TRB_UNSUPPORTED, "filter wider than 4 pixels");
+    bool light = false;
+    for (uint32_t i = 0; i < d->n_instances; ++i) {
+        const trb_instance& in = d->instances[i];
+        if (in.kind > TRB_INST_EMITTER_POINT || in.shape > TRB_SHAPE_MESH) return fail(TRB_INVALID_ARG, "unknown instance kind/shape");
+        if (in.kind != TRB_INST_EMITTER_POINT && in.shape == TRB_SHAPE_NONE) return fail(TRB_INVALID_ARG, "instance without geometry");
+        if (in.kind == TRB_INST_EMITTER_AREA && in.shape == TRB_SHAPE_MESH)
+            return fail(TRB_INVALID_ARG, "Geometry of type 'mesh' is not sampleable and can't be used for area light geometry"); // scene.rs:577-579
+        if (in.shape == TRB_SHAPE_MESH && in.mesh >= d->n_meshes) return fail(TRB_INVALID_ARG, "mesh index out of range");
+        if (in.kind != TRB_INST_EMITTER_POINT && in.material >= d->n_materials) return fail(TRB_INVALID_ARG, "material index out of range");
+        if (in.spline_first + in.n_splines > d->n_splines) return fail(TRB_INVALID_ARG, "spline range out of bounds");
+        if (in.kind != TRB_INST_RECEIVER) {
+            light = true;
+            if (in.n_emission == 0 || in.emission_first + in.n_emission > d->n_color_keys) return fail(TRB_INVALID_ARG, "An emission color is required for emitters");
+            if (in.n_emission > 1) return fail(TRB_UNSUPPORTED, "keyframed emission is not implemented (DESIGN.md: next)");
+        }
+        for (uint32_t k = in.spline_first; k < in.spline_first + in.n_splines; ++k)
+            if (d->splines[k].n_ctrl != 1) return fail(TRB_UNSUPPORTED, "animated instance transforms are not implemented (DESIGN.md: next, row N1)");
+    }
+    if (!light) return fail(TRB_INVALID_ARG, "At least one light is required"); // multithreaded.rs:39
+    for (uint32_t i = 0; i < d->n_cameras; ++i) {
+        const trb_camera& c = d->cameras[i];
+        if (c.n_fov_ctrl) return fail(TRB_UNSUPPORTED, "animated fov is not implemented (DESIGN.md: next)");
+        for (uint32_t k = c.spline_first; k < c.spline_first + c.n_splines; ++k)
+            if (k >= d->n_splines || d->splines[k].n_ctrl != 1) return fail(TRB_UNSUPPORTED, "animated camera transforms are not implemented (DESIGN.md: next)");
+    }
+    for (uint32_t i = 0; i < d->n_materials; ++i) {
+        if (d->materials[i].type > TRB_MAT_MERL) return fail(TRB_INVALID_ARG, "unrecognized material type");
+        if (d->materials[i].type == TRB_MAT_MERL && d->materials[i].merl >= d->n_merl) return fail(TRB_INVALID_ARG, "merl table index out of range");
+    }
+    for (uint32_t i = 0; i < d->n_meshes; ++i) {
+        const trb_mesh& m = d->meshes[i];
+        if (m.n_tris == 0 || m.n_verts == 0) return fail(TRB_INVALID_ARG, "empty mesh");
+        if (!m.positions || !m.normals || !m.texcoords || !m.indices) return fail(TRB_INVALID_ARG, "Normals and texture coordinates are required!"); // mesh.rs:57-61
+        for (size_t k = 0; k < 3 * (size_t)m.n_tris; ++k) if (m.indices[k] >= m.n_verts) return fail(TRB_INVALID_ARG, "mesh index out of range");
+    }
+    return TRB_OK;
+}
+
+trb_status ensure_blocks(trb_scene* s, uint32_t start, uint32_t count, uint32_t* n_blocks) {
+    if (s->cached_block_start != start || s->cached_block_count != count) {
+        s->cached_blocks = morton_blocks(s->film.width, s->film.height, start, count);
+        const size_t n = s->cached_blocks.size() / 2;
+        if (n > s->blocks_capacity) {
+            CU(s->arena.alloc(n, &s->d_blocks));
+            s->blocks_capacity = n;
+        }
+        if (n) CU(cudaMemcpy(s->d_blocks, s->cached_blocks.data(), n * sizeof(uint2), cudaMemcpyHostToDevice));
+        s->cached_block_start = start; s->cached_block_count = count;
+    }
+    *n_blocks = (uint32_t)(s->cached_blocks.size() / 2);
+    return TRB_OK;
+}
+
+trb_status resolve_samples(const trb_scene* s, const trb_render_cfg* cfg, uint32_t& spp, uint32_t& first, uint32_t& count) {
+    spp = cfg->spp ? pow2_ceil(cfg->spp) : s->spp_pow2; // ld.rs:22-26
+    first = cfg->sample_first;
+    if (first > spp) return fail(TRB_INVALID_ARG, "sample_first exceeds spp");
+    count = cfg->sample_count ? cfg->sample_count : spp - first;
+    if (first + count > spp) return fail(TRB_INVALID_ARG, "sample range exceeds spp");
+    return TRB_OK;
+}
+
+template <bool STATS, int MODE>
+trb_status launch_render_t(trb_scene* s, const trb::RenderParams& rp, uint32_t flags, cudaStream_t st) {
+    const int T = 9 + 2 * std::max(s->ds.fpw_x, s->ds.fpw_y);
+    const size_t smem = (size_t)T * T * sizeof(float4);
+    int per_sm = 0;
+    CU(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, trb::k_render<STATS, MODE>, trb::RENDER_THREADS, smem));
+    const uint32_t grid = std::max(1u, std::min<uint32_t>(rp.n_blocks, (uint32_t)(std::max(1, per_sm) * s->sm_count)));
+    trb::k_render<STATS, MODE><<<grid, trb::RENDER_THREADS, smem, st>>>(s->ds, rp, flags);
+    CU(cudaGetLastError());
+    return TRB_OK;
+}
+trb_status launch_render(trb_scene* s, const trb::RenderParams& rp, uint32_t flags, int mode, cudaStream_t st) {
+    const bool stats = (flags & TRB_RENDER_STATS) != 0;
+    CU(cudaMemsetAsync(rp.work_counter, 0, sizeof(uint32_t), st));
+    if (mode == 0) return stats ? launch_render_t<true, 0>(s, rp, flags, st) : launch_render_t<false, 0>(s, rp, flags, st);
+    return stats ? launch_render_t<true, 1>(s, rp, flags, st) : launch_render_t<false, 1>(s, rp, flags, st);
+}
+
+void stats_out(const trb::DStats& d, trb_stats* o) {
+    o->camera_samples = d.camera_samples; o->rays_primary = d.rays_primary; o->rays_shadow = d.rays_shadow; o->rays_mis = d.rays_mis;
+    o->rays_continuation = d.rays_continuation; o->node_tests = d.node_tests; o->tri_tests = d.tri_tests; o->inst_tests = d.inst_tests;
+}
+
+trb_status check_error_flag(trb_scene* s) {
+    int e = 0;
+    CU(cudaMemcpy(&e, s->d_error, sizeof e, cudaMemcpyDeviceToHost));
+    if (e) { CU(cudaMemset(s->d_error, 0, sizeof(int))); return fail(TRB_CUDA, "BVH traversal stack overflow (depth > 64; the reference would panic)"); }
+    return TRB_OK;
+}
+
+} // namespace
+
+extern "C" {
+
+const char* trb_last_error(void) { return g_error.c_str(); }
+uint32_t trb_abi_version(void) { return TRB_ABI_VERSION; }
+
+trb_status trb_scene_create(const trb_scene_desc* d, int device, trb_scene** out) {
+    if (!out) return fail(TRB_INVALID_ARG, "null out pointer");
+    *out = nullptr;
+    trb_status v = validate(d);
+    if (v != TRB_OK) return v;
+    int ndev = 0;
+    if (cudaGetDeviceCount(&ndev) != cudaSuccess || ndev == 0) return fail(TRB_NO_DEVICE, "no CUDA device: tray_rust_b200 has no CPU fallback");
+    if (device < 0 || device >= ndev) return fail(TRB_INVALID_ARG, "device ordinal out of range");
+    CU(cudaSetDevice(device));
+    std::unique_ptr<trb_scene> s(new trb_scene);
+    s->device = device;
+    cudaDeviceProp prop;
+    CU(cudaGetDeviceProperties(&prop, device));
+    s->sm_count = prop.multiProcessorCount;
+    s->film = d->film; s->integrator = d->integrator;
+    s->spp_pow2 = pow2_ceil(std::max(1u, d->film.samples));
+    s->cameras.assign(d->cameras, d->cameras + d->n_cameras);
+    s->instances.assign(d->instances, d->instances + d->n_instances);
+    s->splines.assign(d->splines, d->splines + d->n_splines);
+    s->keyframes.assign(d->keyframes, d->keyframes + d->n_keyframes);
+    s->knots.assign(d->knots, d->knots + d->n_knots);
+    s->color_keys.assign(d->color_keys, d->color_keys + d->n_color_keys);
+    s->materials.assign(d->materials, d->materials + d->n_materials);
+
+    // meshes: BVH<Triangle> with max_geom 16 (mesh.rs:44), then leaf-ordered triangle records
+    std::vector<trb::DMesh> dmeshes(d->n_meshes);
+    s->meshes.resize(d->n_meshes);
+    for (uint32_t mi = 0; mi < d->n_meshes; ++mi) {
+        const trb_mesh& m = d->meshes[mi];
+        HostMesh& hm = s->meshes[mi];
+        hm.pos.assign(m.positions, m.positions + 3 * (size_t)m.n_verts);
+        hm.nrm.assign(m.normals, m.normals + 3 * (size_t)m.n_verts);
+        hm.uv.assign(m.texcoords, m.texcoords + 2 * (size_t)m.n_verts);
+        hm.idx.assign(m.indices, m.indices + 3 * (size_t)m.n_tris);
+        std::vector<Box3> tb(m.n_tris);
+        for (uint32_t t = 0; t < m.n_tris; ++t) { // Triangle::bounds (mesh.rs:128-134)
+            Box3 b;
+            const float* pa = &hm.pos[3 * hm.idx[3 * t]];
+            for (int k = 0; k < 3; ++k) b.lo[k] = b.hi[k] = pa[k];
+            box_grow_pt(b, &hm.pos[3 * hm.idx[3 * t + 1]]);
+            box_grow_pt(b, &hm.pos[3 * hm.idx[3 * t + 2]]);
+            tb[t] = b;
+        }
+        BvhBuilder bb;
+        bb.build(tb, 16);
+        hm.nodes = bb.nodes; hm.order = bb.order;
+        for (int k = 0; k < 3; ++k) { hm.bounds.lo[k] = hm.nodes[0].bmin[k]; hm.bounds.hi[k] = hm.nodes[0].bmax[k]; }
+        std::vector<trb::DNode> pn;
+        pack_nodes(hm.nodes, pn);
+        std::vector<trb::DTri> tris(m.n_tris);
+        for (uint32_t slot = 0; slot < m.n_tris; ++slot) {
+            const uint32_t t = hm.order[slot];
+            const float* pa = &hm.pos[3 * hm.idx[3 * t]];
+            const float* pb = &hm.pos[3 * hm.idx[3 * t + 1]];
+            const float* pc = &hm.pos[3 * hm.idx[3 * t + 2]];
+            float tid; std::memcpy(&tid, &t, 4);
+            tris[slot].v0 = make_float4(pa[0], pa[1], pa[2], tid);
+            tris[slot].e0 = make_float4(pb[0] - pa[0], pb[1] - pa[1], pb[2] - pa[2], 0.f);
+            tris[slot].e1 = make_float4(pc[0] - pa[0], pc[1] - pa[1], pc[2] - pa[2], 0.f);
+        }
+        trb::DMesh& dm = dmeshes[mi];
+        float *dp, *dn, *dt; uint32_t* di; trb::DNode* dnodes; trb::DTri* dtris;
+        CU(s->arena.upload(hm.pos.data(), hm.pos.size(), &dp));
+        CU(s->arena.upload(hm.nrm.data(), hm.nrm.size(), &dn));
+        CU(s->arena.upload(hm.uv.data(), hm.uv.size(), &dt));
+        CU(s->arena.upload(hm.idx.data(), hm.idx.size(), &di));
+        CU(s->arena.upload(pn.data(), pn.size(), &dnodes));
+        CU(s->arena.upload(tris.data(), tris.size(), &dtris));
+        dm.positions = dp; dm.normals = dn; dm.texcoords = dt; dm.indices = di; dm.nodes = dnodes; dm.tris = dtris;
+        dm.n_nodes = (uint32_t)pn.size(); dm.n_tris = m.n_tris;
+    }
+    trb::DMesh* d_meshes;
+    CU(s->arena.upload(dmeshes.data(), dmeshes.size(), &d_meshes));
+
+    // materials (precompute what Material::bsdf recomputes per hit from constant textures)
+    std::vector<trb::DMaterial> dmats(d->n_materials);
+    for (uint32_t i = 0; i < d->n_materials; ++i) {
+        const trb_material& m = d->materials[i];
+        trb::DMaterial& o = dmats[i];
+        std::memset(&o, 0, sizeof o);
+        o.type = m.type;
+        for (int k = 0; k < 3; ++k) { o.c0[k] = m.c0[k]; o.c1[k] = m.c1[k]; }
+        o.roughness = m.roughness; o.eta = m.eta;
+        o.width = fmaxf(m.roughness, 0.000001f);         // Beckmann::new (beckmann.rs:19-22)
+        float sigma = kPi / 180.0f * m.roughness;        // OrenNayar::new (oren_nayar.rs:26-34), roughness in degrees
+        sigma *= sigma;
+        o.on_a = 1.0f - 0.5f * sigma / (sigma + 0.33f);
+        o.on_b = 0.45f * sigma / (sigma + 0.09f);
+        o.merl_off = m.type == TRB_MAT_MERL ? m.merl * TRB_MERL_TABLE_FLOATS : 0;
+    }
+    trb::DMaterial* d_mats;
+    CU(s->arena.upload(dmats.data(), dmats.size(), &d_mats));
+    float* d_merl = nullptr;
+    CU(s->arena.alloc((size_t)d->n_merl * TRB_MERL_TABLE_FLOATS, &d_merl));
+    for (uint32_t i = 0; i < d->n_merl; ++i)
+        CU(cudaMemcpy(d_merl + (size_t)i * TRB_MERL_TABLE_FLOATS, d->merl_tables[i], sizeof(float) * TRB_MERL_TABLE_FLOATS, cudaMemcpyHostToDevice));
+
+    std::vector<uint32_t> lights;
+    for (uint32_t i = 0; i < d->n_instances; ++i) if (d->instances[i].kind != TRB_INST_RECEIVER) lights.push_back(i); // multithreaded.rs:33-38
+    uint32_t* d_lights;
+    CU(s->arena.upload(lights.data(), lights.size(), &d_lights));
+
+    filter_table(d->film, s->table);
+    float* d_table;
+    CU(s->arena.upload(s->table, 256, &d_table));
+
+    CU(s->arena.alloc(d->n_instances, &s->d_instances));
+    CU(s->arena.alloc(1, &s->d_counter));
+    CU(s->arena.alloc(1, &s->d_error));
+    CU(cudaMemset(s->d_error, 0, sizeof(int)));
+    CU(s->arena.alloc(1, &s->d_stats));
+    CU(s->arena.alloc((size_t)d->film.width * d->film.height, &s->d_film));
+    CU(cudaMallocHost(&s->h_film_staging, (size_t)d->film.width * d->film.height * 4 * sizeof(float)));
+    CU(cudaEventCreate(&s->ev0));
+    CU(cudaEventCreate(&s->ev1));
+
+    trb::DScene& ds = s->ds;
+    ds.instances = s->d_instances; ds.meshes = d_meshes; ds.materials = d_mats; ds.merl = d_merl; ds.lights = d_lights;
+    ds.n_instances = d->n_instances; ds.n_lights = (uint32_t)lights.size();
+    ds.width = d->film.width; ds.height = d->film.height;
+    ds.min_depth = d->integrator.min_depth; ds.max_depth = d->integrator.max_depth;
+    ds.filter_w = d->film.filter_w; ds.filter_h = d->film.filter_h;
+    ds.filter_inv_w = 1.0f / d->film.filter_w; ds.filter_inv_h = 1.0f / d->film.filter_h;
+    ds.fpw_x = (int)floorf(d->film.filter_w / 0.5f); ds.fpw_y = (int)floorf(d->film.filter_h / 0.5f); // render_target.rs:48-49
+    ds.filter_table = d_table;
+    // Scene::load_file builds the BVH<Instance> for [0, scene_time] (scene.rs:141); the first render rebuilds it
+    *out = s.release();
+    return TRB_OK;
+}
+
+void trb_scene_destroy(trb_scene* s) {
+    if (!s) return;
+    cudaSetDevice(s->device);
+    delete s;
+}
+
+trb_status trb_scene_info(const trb_scene* s, uint32_t* w, uint32_t* h, uint32_t* spp, uint32_t* n_blocks, uint32_t* n_inst, uint32_t* n_lights) {
+    if (!s) return fail(TRB_INVALID_ARG, "null scene");
+    if (w) *w = s->film.width; if (h) *h = s->film.height; if (spp) *spp = s->spp_pow2;
+    if (n_blocks) *n_blocks = (s->film.width / 8) * (s->film.height / 8);
+    if (n_inst) *n_inst = (uint32_t)s->instances.size(); if (n_lights) *n_lights = s->ds.n_lights;
+    return TRB_OK;
+}
+
+trb_status trb_scene_update_frame(trb_scene* s, uint32_t frame, float start, float end) {
+    if (!s) return fail(TRB_INVALID_ARG, "null scene");
+    CU(cudaSetDevice(s->device));
+    // camera selection (scene.rs:153-166)
+    int cam;
+    if (s->active_camera >= 0) {
+        cam = s->active_camera;
+        if (cam != (int)s->cameras.size() - 1 && s->cameras[cam + 1].active_at == frame) cam += 1;
+    } else {
+        int c = 0;
+        for (const trb_camera& x : s->cameras) { if (x.active_at <= frame) c++; else break; }
+        if (c == 0) return fail(TRB_INVALID_ARG, "no camera is active at this frame");
+        cam = c - 1;
+    }
+    s->active_camera = cam;
+    const trb_camera& c = s->cameras[cam];
+    s->shutter_open = start;                                  // camera.rs:127-129
+    s->shutter_close = start + c.shutter_size * (end - start);
+    Mat4 px_to_cam; float scaling[3];
+    camera_setup(c.fov, s->film.width, s->film.height, px_to_cam, scaling);
+    Xf cam_world;
+    if (!static_world_xf(*s, c.spline_first, c.n_splines, cam_world)) return fail(TRB_UNSUPPORTED, "animated camera");
+    std::memcpy(s->ds.cam.px_to_cam, px_to_cam.m, 64);
+    std::memcpy(s->ds.cam.cam_mat, cam_world.fwd.m, 64);
+    std::memcpy(s->ds.cam.scaling, scaling, 12);
+    s->ds.cam.shutter_open = s->shutter_open; s->ds.cam.shutter_close = s->shutter_close;
+
+    // instance transforms + bounds, then BVH<Instance>::rebuild(shutter_open, shutter_close) (scene.rs:175, bvh.rs:61-78)
+    const size_t n = s->instances.size();
+    s->world.resize(n);
+    std::vector<Box3> bounds(n);
+    std::vector<trb::DInstance> di(n);
+    for (size_t i = 0; i < n; ++i) {
+        const trb_instance& in = s->instances[i];
+        if (!static_world_xf(*s, in.spline_first, in.n_splines, s->world[i])) return fail(TRB_UNSUPPORTED, "animated instance");
+        bounds[i] = arvo_bounds(s->world[i].fwd, shape_bounds(*s, in)); // animation_bounds, static branch (animated_transform.rs:59-61)
+        trb::DInstance& o = di[i];
+        std::memset(&o, 0, sizeof o);
+        std::memcpy(o.inv, s->world[i].inv.m, 64);
+        std::memcpy(o.mat, s->world[i].fwd.m, 64);
+        o.kind = in.kind; o.shape = in.shape; o.p0 = in.p0; o.p1 = in.p1; o.mesh = in.mesh; o.material = in.material;
+        if (in.kind != TRB_INST_RECEIVER) for (int k = 0; k < 3; ++k) o.emission[k] = s->color_keys[in.emission_first].rgba[k];
+    }
+    BvhBuilder bb;
+    bb.build(bounds, 4);
+    s->tlas_nodes = bb.nodes; s->tlas_order = bb.order;
+    std::vector<trb::DNode> pn;
+    pack_nodes(s->tlas_nodes, pn);
+    if (pn.size() > s->tlas_capacity) {
+        CU(s->arena.alloc(pn.size(), &s->d_tlas));
+        CU(s->arena.alloc(n, &s->d_tlas_order));
+        s->tlas_capacity = pn.size();
+    }
+    CU(cudaMemcpy(s->d_tlas, pn.data(), pn.size() * sizeof(trb::DNode), cudaMemcpyHostToDevice));
+    CU(cudaMemcpy(s->d_tlas_order, s->tlas_order.data(), n * sizeof(uint32_t), cudaMemcpyHostToDevice));
+    CU(cudaMemcpy(s->d_instances, di.data(), n * sizeof(trb::DInstance), cudaMemcpyHostToDevice));
+    s->ds.tlas = s->d_tlas; s->ds.tlas_order = s->d_tlas_order;
+    s->frame_ready = true;
+    return TRB_OK;
+}
+
+trb_status trb_render_device(trb_scene* s, const trb_render_cfg* cfg, float* d_film, trb_stats* d_stats, void* stream) {
+    if (!s || !cfg || !d_film) return fail(TRB_INVALID_ARG, "null argument");
+    if (!s->frame_ready) return fail(TRB_INVALID_ARG, "Update frame must be called before rendering"); // scene.rs:179
+    CU(cudaSetDevice(s->device));
+    uint32_t spp, first, count, nb;
+    trb_status r = resolve_samples(s, cfg, spp, first, count);
+    if (r != TRB_OK) return r;
+    r = ensure_blocks(s, cfg->block_start, cfg->block_count, &nb);
+    if (r != TRB_OK) return r;
+    if (nb == 0 || count == 0) return TRB_OK; // "Warning: This block queue is empty!" (block_queue.rs:42-44)
+    trb::RenderParams rp{};
+    rp.blocks = s->d_blocks; rp.n_blocks = nb; rp.spp = spp; rp.sample_first = first; rp.sample_count = count; rp.seed = cfg->seed;
+    rp.work_counter = s->d_counter; rp.film = reinterpret_cast<float4*>(d_film); rp.stats = reinterpret_cast<trb::DStats*>(d_stats);
+    rp.error_flag = s->d_error;
+    return launch_render(s, rp, cfg->flags, 0, static_cast<cudaStream_t>(stream));
+}
+
+trb_status trb_render(trb_scene* s, const trb_render_cfg* cfg, float* film, trb_stats* stats) {
+    if (!s || !cfg || !film) return fail(TRB_INVALID_ARG, "null argument");
+    CU(cudaSetDevice(s->device));
+    float update_ms = 0.f;
+    if (!(cfg->flags & TRB_RENDER_NO_UPDATE)) { // Exec::render: scene.update_frame first (multithreaded.rs:57-60)
+        auto t0 = std::chrono::steady_clock::now();
+        const float step = s->film.scene_time / (float)s->film.frames;
+        trb_status r = trb_scene_update_frame(s, cfg->current_frame, (float)cfg->current_frame * step, ((float)cfg->current_frame + 1.0f) * step);
+        if (r != TRB_OK) return r;
+        update_ms = std::chrono::duration<float, std::milli>(std::chrono::steady_clock::now() - t0).count();
+    }
+    const size_t npx = (size_t)s->film.width * s->film.height;
+    CU(cudaMemsetAsync(s->d_film, 0, npx * sizeof(float4), 0));
+    CU(cudaMemsetAsync(s->d_stats, 0, sizeof(trb::DStats), 0));
+    CU(cudaEventRecord(s->ev0, 0));
+    trb_status r = trb_render_device(s, cfg, reinterpret_cast<float*>(s->d_film), reinterpret_cast<trb_stats*>(s->d_stats), nullptr);
+    if (r != TRB_OK) return r;
+    CU(cudaEventRecord(s->ev1, 0));
+    CU(cudaMemcpyAsync(s->h_film_staging, s->d_film, npx * sizeof(float4), cudaMemcpyDeviceToHost, 0));
+    CU(cudaStreamSynchronize(0));
+    r = check_error_flag(s);
+    if (r != TRB_OK) return r;
+    for (size_t i = 0; i < npx * 4; ++i) film[i] += s->h_film_staging[i]; // additive, like film::Image::add_pixels (image.rs:21-33)
+    if (stats) {
+        trb::DStats h;
+        CU(cudaMemcpy(&h, s->d_stats, sizeof h, cudaMemcpyDeviceToHost));
+        std::memset(stats, 0, sizeof *stats);
+        stats_out(h, stats);
+        CU(cudaEventElapsedTime(&stats->kernel_ms, s->ev0, s->ev1));
+        stats->update_ms = update_ms;
+    }
+    return TRB_OK;
+}
+
+trb_status trb_render_samples(trb_scene* s, const trb_render_cfg* cfg, size_t n, trb_sample* samples, trb_stats* stats) {
+    if (!s || !cfg || !samples) return fail(TRB_INVALID_ARG, "null argument");
+    if (!s->frame_ready) return fail(TRB_INVALID_ARG, "Update frame must be called before rendering");
+    CU(cudaSetDevice(s->device));
+    uint32_t spp, first, count, nb;
+    trb_status r = resolve_samples(s, cfg, spp, first, count);
+    if (r != TRB_OK) return r;
+    r = ensure_blocks(s, cfg->block_start, cfg->block_count, &nb);
+    if (r != TRB_OK) return r;
+    if (n != (size_t)nb * 64 * count) return fail(TRB_INVALID_ARG, "sample buffer size must be blocks*64*sample_count");
+    if (n == 0) return TRB_OK;
+    trb_sample* d_out = nullptr;
+    CU(cudaMalloc(&d_out, n * sizeof(trb_sample)));
+    CU(cudaMemsetAsync(s->d_stats, 0, sizeof(trb::DStats), 0));
+    trb::RenderParams rp{};
+    rp.blocks = s->d_blocks; rp.n_blocks = nb; rp.spp = spp; rp.sample_first = first; rp.sample_count = count; rp.seed = cfg->seed;
+    rp.work_counter = s->d_counter; rp.film = nullptr; rp.samples_out = d_out; rp.stats = s->d_stats; rp.error_flag = s->d_error;
+    CU(cudaEventRecord(s->ev0, 0));
+    r = launch_render(s, rp, cfg->flags, 1, 0);
+    if (r != TRB_OK) { cudaFree(d_out); return r; }
+    CU(cudaEventRecord(s->ev1, 0));
+    cudaError_t e = cudaMemcpy(samples, d_out, n * sizeof(trb_sample), cudaMemcpyDeviceToHost);
+    cudaFree(d_out);
+    CU(e);
+    r = check_error_flag(s);
+    if (r != TRB_OK) return r;
+    if (stats) {
+        trb::DStats h;
+        CU(cudaMemcpy(&h, s->d_stats, sizeof h, cudaMemcpyDeviceToHost));
+        std::memset(stats, 0, sizeof *stats);
+        stats_out(h, stats);
+        CU(cudaEventElapsedTime(&stats->kernel_ms, s->ev0, s->ev1));
+    }
+    return TRB_OK;
+}
+
+trb_status trb_camera_rays(trb_scene* s, const trb_render_cfg* cfg, size_t n, trb_ray* rays, float* xy) {
+    if (!s || !cfg || !rays || !xy) return fail(TRB_INVALID_ARG, "null argument");
+    if (!s->frame_ready) return fail(TRB_INVALID_ARG, "Update frame must be called before rendering");
+    CU(cudaSetDevice(s->device));
+    uint32_t spp, first, count, nb;
+    trb_status r = resolve_samples(s, cfg, spp, first, count);
+    if (r != TRB_OK) return r;
+    r = ensure_blocks(s, cfg->block_start, cfg->block_count, &nb);
+    if (r != TRB_OK) return r;
+    if (n != (size_t)nb * 64 * count) return fail(TRB_INVALID_ARG, "ray buffer size must be blocks*64*sample_count");
+    if (n == 0) return TRB_OK;
+    trb_ray* d_rays = nullptr; float* d_xy = nullptr;
+    CU(cudaMalloc(&d_rays, n * sizeof(trb_ray)));
+    cudaError_t e = cudaMalloc(&d_xy, n * 2 * sizeof(float));
+    if (e != cudaSuccess) { cudaFree(d_rays); CU(e); }
+    trb::RenderParams rp{};
+    rp.blocks = s->d_blocks; rp.n_blocks = nb; rp.spp = spp; rp.sample_first = first; rp.sample_count = count; rp.seed = cfg->seed;
+    trb::k_camera_rays<<<(unsigned)std::min<size_t>((n + 255) / 256, 148 * 8), 256>>>(s->ds, rp, d_rays, d_xy);
+    e = cudaGetLastError();
+    if (e == cudaSuccess) e = cudaMemcpy(rays, d_rays, n * sizeof(trb_ray), cudaMemcpyDeviceToHost);
+    if (e == cudaSuccess) e = cudaMemcpy(xy, d_xy, n * 2 * sizeof(float), cudaMemcpyDeviceToHost);
+    cudaFree(d_rays); cudaFree(d_xy);
+    CU(e);
+    return TRB_OK;
+}
+
+trb_status trb_intersect_device(trb_scene* s, size_t n, const trb_ray* d_rays, trb_hit* d_hits, trb_stats* d_stats, void* stream) {
+    if (!s || (n && (!d_rays || !d_hits))) return fail(TRB_INVALID_ARG, "null argument");
+    if (!s->frame_ready) return fail(TRB_INVALID_ARG, "Update frame must be called before intersecting");
+    if (n == 0) return TRB_OK;
+    CU(cudaSetDevice(s->device));
+    const unsigned grid = (unsigned)std::min<size_t>((n + 127) / 128, (size_t)s->sm_count * 16);
+    trb::k_intersect<false><<<grid, 128, 0, static_cast<cudaStream_t>(stream)>>>(s->ds, n, d_rays, d_hits, reinterpret_cast<trb::DStats*>(d_stats), s->d_error);
+    CU(cudaGetLastError());
+    return TRB_OK;
+}
+
+trb_status trb_intersect(trb_scene* s, size_t n, const trb_ray* rays, trb_hit* hits, trb_stats* stats) {
+    if (!s || (n && (!rays || !hits))) return fail(TRB_INVALID_ARG, "null argument");
+    if (!s->frame_ready) return fail(TRB_INVALID_ARG, "Update frame must be called before intersecting");
+    if (n == 0) return TRB_OK;
+    CU(cudaSetDevice(s->device));
+    trb_ray* d_rays = nullptr; trb_hit* d_hits = nullptr;
+    CU(cudaMalloc(&d_rays, n * sizeof(trb_ray)));
+    cudaError_t e = cudaMalloc(&d_hits, n * sizeof(trb_hit));
+    if (e != cudaSuccess) { cudaFree(d_rays); CU(e); }
+    e = cudaMemcpy(d_rays, rays, n * sizeof(trb_ray), cudaMemcpyHostToDevice);
+    if (e == cudaSuccess) e = cudaMemsetAsync(s->d_stats, 0, sizeof(trb::DStats), 0);
+    if (e == cudaSuccess) {
+        cudaEventRecord(s->ev0, 0);
+        const unsigned grid = (unsigned)std::min<size_t>((n + 127) / 128, (size_t)s->sm_count * 16);
+        trb::k_intersect<true><<<grid, 128>>>(s->ds, n, d_rays, d_hits, s->d_stats, s->d_error); // host variant always counts tests
+        cudaEventRecord(s->ev1, 0);
+        e = cudaGetLastError();
+    }
+    if (e == cudaSuccess) e = cudaMemcpy(hits, d_hits, n * sizeof(trb_hit), cudaMemcpyDeviceToHost);
+    cudaFree(d_rays); cudaFree(d_hits);
+    CU(e);
+    trb_status r = check_error_flag(s);
+    if (r != TRB_OK) return r;
+    if (stats) {
+        trb::DStats h;
+        CU(cudaMemcpy(&h, s->d_stats, sizeof h, cudaMemcpyDeviceToHost));
+        std::memset(stats, 0, sizeof *stats);
+        stats_out(h, stats);
+        CU(cudaEventElapsedTime(&stats->kernel_ms, s->ev0, s->ev1));
+    }
+    return TRB_OK;
+}
+
+trb_status trb_film_to_srgb8(trb_scene* s, const float* film, uint8_t* rgb8) {
+    if (!s || !film || !rgb8) return fail(TRB_INVALID_ARG, "null argument");
+    CU(cudaSetDevice(s->device));
+    const size_t npx = (size_t)s->film.width * s->film.height;
+    uint8_t* d_out = nullptr;
+    CU(cudaMalloc(&d_out, npx * 3));
+    cudaError_t e = cudaMemcpy(s->d_film, film, npx * sizeof(float4), cudaMemcpyHostToDevice);
+    if (e == cudaSuccess) {
+        trb::k_srgb8<<<(unsigned)std::min<size_t>((npx + 255) / 256, 148 * 16), 256>>>(npx, s->d_film, d_out);
+        e = cudaGetLastError();
+    }
+    if (e == cudaSuccess) e = cudaMemcpy(rgb8, d_out, npx * 3, cudaMemcpyDeviceToHost);
+    cudaFree(d_out);
+    CU(e);
+    return TRB_OK;
+}
+
+trb_status trb_block_list(const trb_scene* s, uint32_t start, uint32_t count, uint32_t* n_out, uint32_t* xy, uint32_t cap) {
+    if (!s || !n_out) return fail(TRB_INVALID_ARG, "null argument");
+    std::vector<uint32_t> b = morton_blocks(s->film.width, s->film.height, start, count);
+    *n_out = (uint32_t)(b.size() / 2);
+    if (xy) std::memcpy(xy, b.data(), sizeof(uint32_t) * std::min<size_t>(b.size(), 2 * (size_t)cap));
+    return TRB_OK;
+}
+
+trb_status trb_scene_get_bvh(const trb_scene* s, int which, uint32_t* n_nodes, trb_bvh_node* nodes, uint32_t* n_ordered, uint32_t* ordered) {
+    if (!s || !n_nodes || !n_ordered) return fail(TRB_INVALID_ARG, "null argument");
+    const std::vector<trb_bvh_node>* nn; const std::vector<uint32_t>* oo;
+    if (which < 0) { if (!s->frame_ready) return fail(TRB_INVALID_ARG, "update_frame first"); nn = &s->tlas_nodes; oo = &s->tlas_order; }
+    else { if ((size_t)which >= s->meshes.size()) return fail(TRB_INVALID_ARG, "mesh index out of range"); nn = &s->meshes[which].nodes; oo = &s->meshes[which].order; }
+    *n_nodes = (uint32_t)nn->size(); *n_ordered = (uint32_t)oo->size();
+    if (nodes) std::memcpy(nodes, nn->data(), nn->size() * sizeof(trb_bvh_node));
+    if (ordered) std::memcpy(ordered, oo->data(), oo->size() * sizeof(uint32_t));
+    return TRB_OK;
+}
+
+trb_status trb_scene_get_transform(const trb_scene* s, uint32_t inst, float* mat16, float* inv16) {
+    if (!s || !s->frame_ready || inst >= s->world.size()) return fail(TRB_INVALID_ARG, "bad instance / update_frame first");
+    std::memcpy(mat16, s->world[inst].fwd.m, 64); std::memcpy(inv16, s->world[inst].inv.m, 64);
+    return TRB_OK;
+}
+
+trb_status trb_scene_get_filter_table(const trb_scene* s, float* t) {
+    if (!s || !t) return fail(TRB_INVALID_ARG, "null argument");
+    std::memcpy(t, s->table, sizeof s->table);
+    return TRB_OK;
+}
+
+trb_status trb_host_build_bvh(const float* boxes6, uint32_t n, uint32_t max_geom, uint32_t* n_nodes, trb_bvh_node* nodes, uint32_t* ordered) {
+    if (!boxes6 || n == 0 || !n_nodes) return fail(TRB_INVALID_ARG, "empty geometry"); // bvh.rs:35 assert!(!geometry.is_empty())
+    std::vector<Box3> b(n);
+    for (uint32_t i = 0; i < n; ++i) for (int k = 0; k < 3; ++k) { b[i].lo[k] = boxes6[6 * i + k]; b[i].hi[k] = boxes6[6 * i + 3 + k]; }
+    BvhBuilder bb;
+    bb.build(b, max_geom);
+    *n_nodes = (uint32_t)bb.nodes.size();
+    if (nodes) std::memcpy(nodes, bb.nodes.data(), bb.nodes.size() * sizeof(trb_bvh_node));
+    if (ordered) std::memcpy(ordered, bb.order.data(), bb.order.size() * sizeof(uint32_t));
+    return TRB_OK;
+}
+
+trb_status trb_host_keyframe_transform(const trb_keyframe* kf, float* mat16, float* inv16) {
+    if (!kf || !mat16 || !inv16) return fail(TRB_INVALID_ARG, "null argument");
+    const Xf x = keyframe_xf(*kf);
+    std::memcpy(mat16, x.fwd.m, 64); std::memcpy(inv16, x.inv.m, 64);
+    return TRB_OK;
+}
+
+} // extern "C"

@@ -1,0 +1,96 @@
+// trb_device.h — device-resident scene layout (HBM), shared by the host code that fills it and the
+// kernels that read it. See DESIGN.md "Data layout in HBM".
+#pragma once
+#include <cstdint>
+#include <cuda_runtime.h>
+
+namespace trb {
+
+// One BVH node, 32 B, read as two 16-byte vector loads. Topology and order are the reference's
+// (src/geometry/bvh.rs:248-267): node i's first child is i+1.
+//   lo = (bmin.xyz, a)   interior: a = second_child            leaf: a = first primitive slot
+//   hi = (bmax.xyz, b)   interior: b = split axis (0,1,2)      leaf: b = 0x80000000 | count
+struct DNode { float4 lo, hi; };
+constexpr uint32_t LEAF_BIT = 0x80000000u;
+
+// One triangle in LEAF ORDER (slot k of the BLAS == ordered_geom[k]), 48 B = three 16-byte loads:
+// v0 = (pa.xyz, triangle index), e0 = pb-pa, e1 = pc-pa (the same single IEEE subtraction the
+// reference performs per test, mesh.rs:140, hoisted to load time).
+struct DTri { float4 v0, e0, e1; };
+
+struct DMesh {
+    const float* positions; // 3 per vertex
+    const float* normals;   // 3 per vertex
+    const float* texcoords; // 2 per vertex
+    const uint32_t* indices; // 3 per triangle
+    const DNode* nodes;     // BVH<Triangle>, max_geom 16 (mesh.rs:44)
+    const DTri* tris;       // leaf order
+    uint32_t n_nodes, n_tris;
+};
+
+// geometry::Instance with its world transform at the current frame (static instances: recomposed
+// once per update_frame instead of once per ray — bit-identical, DESIGN.md "X1").
+struct DInstance {
+    float inv[16];  // world -> object, row-major 4x4 (last row kept: transform.rs:150-162 divides by w)
+    float mat[16];  // object -> world
+    uint32_t kind, shape;
+    float p0, p1;
+    uint32_t mesh, material;
+    float emission[3];
+    uint32_t pad;
+};
+
+struct DMaterial {
+    uint32_t type;
+    float c0[3], c1[3];
+    float roughness; // as given
+    float width;     // Beckmann::new: max(roughness, 1e-6) (beckmann.rs:19-22)
+    float eta;
+    float on_a, on_b; // OrenNayar::new (oren_nayar.rs:26-34)
+    uint32_t merl_off; // float offset into merl
+    uint32_t pad;
+};
+
+struct DCamera {
+    float px_to_cam[16]; // proj_div_inv * raster_screen (camera.rs:152)
+    float cam_mat[16];   // cam_world at the frame (static camera)
+    float scaling[3];
+    float shutter_open, shutter_close;
+};
+
+struct DStats { // mirrors trb_stats' integer part
+    unsigned long long camera_samples, rays_primary, rays_shadow, rays_mis, rays_continuation, node_tests, tri_tests, inst_tests;
+};
+
+struct DScene {
+    const DNode* tlas;           // BVH<Instance>, max_geom 4 (scene.rs:141)
+    const uint32_t* tlas_order;  // ordered_geom
+    const DInstance* instances;
+    const DMesh* meshes;
+    const DMaterial* materials;
+    const float* merl;
+    const uint32_t* lights;      // instance indices of the emitters, object order
+    uint32_t n_instances, n_lights;
+    uint32_t width, height;
+    uint32_t min_depth, max_depth;
+    DCamera cam;
+    // film filter (render_target.rs:41-75)
+    float filter_w, filter_h, filter_inv_w, filter_inv_h;
+    int fpw_x, fpw_y;
+    const float* filter_table; // 256 floats
+};
+
+struct RenderParams {
+    const uint2* blocks;   // Morton-ordered (bx, by) list after select_blocks
+    uint32_t n_blocks;
+    uint32_t spp;          // pow2
+    uint32_t sample_first, sample_count;
+    uint32_t seed;
+    uint32_t* work_counter;
+    float4* film;          // RGBW, row-major
+    void* samples_out;     // trb_sample*, mode 1
+    DStats* stats;
+    int* error_flag;
+};
+
+} // namespace trb

@@ -1,0 +1,1113 @@
+// trb_kernels.cuh — the render hot path of tray_rust as sm_100a CUDA device code.
+//
+// Path covered (reference file:line in /root/reference):
+//   sampler   src/sampler/ld.rs:33-119           (0,2)-sequence samples per pixel / per path
+//   camera    src/film/camera.rs:150-157          Camera::generate_ray
+//   intersect src/scene.rs:148 -> src/geometry/bvh.rs:81-130 (two levels), bbox.rs:75-104,
+//             mesh.rs:136-198, sphere.rs:33-81, disk.rs:42-76, rectangle.rs:38-64,
+//             receiver.rs:29-43 / emitter.rs:118-137
+//   shading   src/material/*.rs -> src/bxdf/**; src/geometry/emitter.rs:140-204 (Light);
+//             src/integrator/mod.rs:106-169, src/integrator/path.rs:45-119, src/mc.rs
+//   film      src/exec/multithreaded.rs:98-111, src/film/render_target.rs:77-165
+//
+// Arithmetic contract: this TU is compiled with --fmad=false (Rust never contracts a*b+c), IEEE
+// div/sqrt, and evaluates every expression in the reference's order; transcendentals come from
+// trb_detmath.cuh. The result of each camera sample is therefore a pure function of
+// (scene, seed, pixel, sample index) — independent of scheduling.
+#pragma once
+#include "trb_device.h"
+#include "trb_detmath.cuh"
+#include "../../include/trb.h"
+
+namespace trb {
+
+// ------------------------------------------------------------------------------------------
+// small vector helpers (componentwise, no FMA)
+// ------------------------------------------------------------------------------------------
+struct f3 { float x, y, z; };
+__device__ __forceinline__ f3 mk(float x, float y, float z) { f3 r; r.x = x; r.y = y; r.z = z; return r; }
+__device__ __forceinline__ f3 splat(float v) { return mk(v, v, v); }
+__device__ __forceinline__ f3 operator+(f3 a, f3 b) { return mk(a.x + b.x, a.y + b.y, a.z + b.z); }
+__device__ __forceinline__ f3 operator-(f3 a, f3 b) { return mk(a.x - b.x, a.y - b.y, a.z - b.z); }
+__device__ __forceinline__ f3 operator*(f3 a, f3 b) { return mk(a.x * b.x, a.y * b.y, a.z * b.z); }
+__device__ __forceinline__ f3 operator/(f3 a, f3 b) { return mk(a.x / b.x, a.y / b.y, a.z / b.z); }
+__device__ __forceinline__ f3 operator*(f3 a, float s) { return mk(a.x * s, a.y * s, a.z * s); }
+__device__ __forceinline__ f3 operator*(float s, f3 a) { return mk(s * a.x, s * a.y, s * a.z); }
+__device__ __forceinline__ f3 operator/(f3 a, float s) { return mk(a.x / s, a.y / s, a.z / s); }
+__device__ __forceinline__ f3 operator-(f3 a) { return mk(-a.x, -a.y, -a.z); }
+__device__ __forceinline__ float dot3(f3 a, f3 b) { return a.x * b.x + a.y * b.y + a.z * b.z; }
+__device__ __forceinline__ f3 cross3(f3 a, f3 b) { return mk(a.y * b.z - a.z * b.y, a.z * b.x - a.x * b.z, a.x * b.y - a.y * b.x); }
+__device__ __forceinline__ float len2(f3 a) { return a.x * a.x + a.y * a.y + a.z * a.z; }
+__device__ __forceinline__ f3 unit(f3 a) { float l = sqrtf(len2(a)); return mk(a.x / l, a.y / l, a.z / l); } // Vector::normalized: 3 divides
+__device__ __forceinline__ bool black(f3 c) { return c.x == 0.0f && c.y == 0.0f && c.z == 0.0f; }
+__device__ __forceinline__ float clampf(float x, float lo, float hi) { return x < lo ? lo : (x > hi ? hi : x); }
+__device__ __forceinline__ float lerpf(float t, float a, float b) { return a * (1.0f - t) + b * t; }
+__device__ __forceinline__ uint32_t f2u(float f) { return __float2uint_rz(f); } // saturating, NaN -> 0 (Rust `as usize`)
+__device__ __forceinline__ float finf() { return __int_as_float(0x7f800000); }
+
+// Transform application (src/linalg/transform.rs:150-254), m row-major 4x4
+__device__ __forceinline__ f3 xf_point(const float* __restrict__ m, f3 p) {
+    f3 r = mk(m[0] * p.x + m[1] * p.y + m[2] * p.z + m[3], m[4] * p.x + m[5] * p.y + m[6] * p.z + m[7],
+              m[8] * p.x + m[9] * p.y + m[10] * p.z + m[11]);
+    float w = m[12] * p.x + m[13] * p.y + m[14] * p.z + m[15];
+    if (fabsf(w - 1.0f) < TRB_EPS) return r / w; // sic: transform.rs:158-162
+    return r;
+}
+__device__ __forceinline__ f3 xf_vector(const float* __restrict__ m, f3 v) {
+    return mk(m[0] * v.x + m[1] * v.y + m[2] * v.z, m[4] * v.x + m[5] * v.y + m[6] * v.z, m[8] * v.x + m[9] * v.y + m[10] * v.z);
+}
+// normal through the transpose of the OTHER matrix (transform.rs:231-242)
+__device__ __forceinline__ f3 xf_normal_t(const float* __restrict__ m, f3 n) {
+    return mk(m[0] * n.x + m[4] * n.y + m[8] * n.z, m[1] * n.x + m[5] * n.y + m[9] * n.z, m[2] * n.x + m[6] * n.y + m[10] * n.z);
+}
+// linalg::coordinate_system (src/linalg/mod.rs:96-108)
+__device__ __forceinline__ void coord_system(f3 e1, f3& e2, f3& e3) {
+    if (fabsf(e1.x) > fabsf(e1.y)) {
+        float il = 1.0f / sqrtf(e1.x * e1.x + e1.z * e1.z);
+        e2 = mk(-e1.z * il, 0.0f, e1.x * il);
+    } else {
+        float il = 1.0f / sqrtf(e1.y * e1.y + e1.z * e1.z);
+        e2 = mk(0.0f, e1.z * il, -e1.y * il);
+    }
+    e3 = cross3(e1, e2);
+}
+
+struct Ray { f3 o, d; float tmin, tmax; };
+struct HitRec { float t; uint32_t inst, prim; float b1, b2; };
+struct Cnt { uint32_t node, tri, inst; };
+
+// ------------------------------------------------------------------------------------------
+// BBox::fast_intersect (src/geometry/bbox.rs:75-104), compares transcribed literally so the NaN
+// behaviour is the reference's.
+// ------------------------------------------------------------------------------------------
+__device__ __forceinline__ bool box_hit(const float4 lo, const float4 hi, f3 o, f3 inv, bool nx, bool ny, bool nz, float tmin_r, float tmax_r) {
+    float tmin = ((nx ? hi.x : lo.x) - o.x) * inv.x;
+    float tmax = ((nx ? lo.x : hi.x) - o.x) * inv.x;
+    float tymin = ((ny ? hi.y : lo.y) - o.y) * inv.y;
+    float tymax = ((ny ? lo.y : hi.y) - o.y) * inv.y;
+    if (tmin > tymax || tymin > tmax) return false;
+    if (tymin > tmin) tmin = tymin;
+    if (tymax < tmax) tmax = tymax;
+    float tzmin = ((nz ? hi.z : lo.z) - o.z) * inv.z;
+    float tzmax = ((nz ? lo.z : hi.z) - o.z) * inv.z;
+    if (tmin > tzmax || tzmin > tmax) return false;
+    if (tzmin > tmin) tmin = tzmin;
+    if (tzmax < tmax) tmax = tzmax;
+    return tmin < tmax_r && tmax > tmin_r;
+}
+
+// ------------------------------------------------------------------------------------------
+// BVH<Triangle>::intersect (bvh.rs:81-130) + intersect_triangle (mesh.rs:136-170, the accept
+// test only: normals / uv / derivatives are deferred to the final hit).
+// ------------------------------------------------------------------------------------------
+template <bool STATS>
+__device__ __forceinline__ bool blas_trace(const DMesh& m, f3 o, f3 d, float tmin, float& tmax, HitRec& hit, bool any_hit, Cnt& cnt, int* err) {
+    const DNode* __restrict__ nodes = m.nodes;
+    const DTri* __restrict__ tris = m.tris;
+    f3 inv = mk(1.0f / d.x, 1.0f / d.y, 1.0f / d.z);
+    const bool nx = d.x < 0.0f, ny = d.y < 0.0f, nz = d.z < 0.0f;
+    uint32_t stack[64];
+    int sp = 0;
+    uint32_t cur = 0;
+    bool result = false;
+    for (;;) {
+        const float4 lo = __ldg(&nodes[cur].lo), hi = __ldg(&nodes[cur].hi);
+        if (STATS) cnt.node++;
+        if (box_hit(lo, hi, o, inv, nx, ny, nz, tmin, tmax)) {
+            const uint32_t a = __float_as_uint(lo.w), b = __float_as_uint(hi.w);
+            if (b & LEAF_BIT) {
+                const uint32_t n = b & ~LEAF_BIT;
+                for (uint32_t k = a; k < a + n; ++k) {
+                    const float4 v0 = __ldg(&tris[k].v0), q0 = __ldg(&tris[k].e0), q1 = __ldg(&tris[k].e1);
+                    if (STATS) cnt.tri++;
+                    const f3 e0 = mk(q0.x, q0.y, q0.z), e1 = mk(q1.x, q1.y, q1.z);
+                    const f3 s0 = cross3(d, e1);
+                    const float dd = dot3(s0, e0);
+                    if (dd == 0.0f) continue;
+                    const float div = 1.0f / dd;
+                    const f3 dv = o - mk(v0.x, v0.y, v0.z);
+                    const float b1 = dot3(dv, s0) * div;
+                    if (b1 < 0.0f || b1 > 1.0f) continue;
+                    const f3 s1 = cross3(dv, e0);
+                    const float b2 = dot3(d, s1) * div;
+                    if (b2 < 0.0f || b1 + b2 > 1.0f) continue;
+                    const float t = dot3(e1, s1) * div;
+                    if (t < tmin || t > tmax) continue;
+                    tmax = t; // last accepted wins, inclusive compare (Q9)
+                    hit.t = t; hit.prim = __float_as_uint(v0.w); hit.b1 = b1; hit.b2 = b2;
+                    result = true;
+                    if (any_hit) return true;
+                }
+                if (sp == 0) break;
+                cur = stack[--sp];
+            } else {
+                const bool neg = b == 0 ? nx : (b == 1 ? ny : nz);
+                if (sp >= 64) { *err = 1; break; }
+                if (neg) { stack[sp++] = cur + 1; cur = a; }
+                else { stack[sp++] = a; cur = cur + 1; }
+            }
+        } else {
+            if (sp == 0) break;
+            cur = stack[--sp];
+        }
+    }
+    return result;
+}
+
+// solve_quadratic (src/linalg/mod.rs:78-94)
+__device__ __forceinline__ bool solve_quadratic(float a, float b, float c, float& t0, float& t1) {
+    float ds = b * b - 4.0f * a * c;
+    if (ds < 0.0f) return false;
+    float disc = sqrtf(ds);
+    float q = b < 0.0f ? -0.5f * (b - disc) : -0.5f * (b + disc);
+    float x = q / a, y = c / q;
+    if (x > y) { t0 = y; t1 = x; } else { t0 = x; t1 = y; }
+    return true;
+}
+// accept tests of the analytic shapes, object space; return t and shrink tmax
+__device__ __forceinline__ bool sphere_t(float radius, f3 o, f3 d, float tmin, float& tmax) { // sphere.rs:33-55
+    float a = len2(d);
+    float b = 2.0f * dot3(d, o);
+    float c = dot3(o, o) - radius * radius;
+    float t0, t1;
+    if (!solve_quadratic(a, b, c, t0, t1)) return false;
+    if (t0 > tmax || t1 < tmin) return false;
+    float th = t0;
+    if (th < tmin) { th = t1; if (th > tmax) return false; }
+    tmax = th;
+    return true;
+}
+__device__ __forceinline__ bool disk_t(float radius, float inner, f3 o, f3 d, float tmin, float& tmax) { // disk.rs:42-68
+    if (fabsf(d.z) == 0.0f) return false;
+    float t = -o.z / d.z;
+    if (t < tmin || t > tmax) return false;
+    f3 p = o + d * t;
+    float ds = p.x * p.x + p.y * p.y;
+    if (ds > radius * radius || ds < inner * inner) return false;
+    // disk.rs:60-66: phi = atan2(p.y, p.x) (+2pi if negative) can never exceed 2pi in fp32, and a NaN
+    // phi fails both compares, so the test never rejects: omitted (DESIGN.md "dead code").
+    tmax = t;
+    return true;
+}
+__device__ __forceinline__ bool rect_t(float width, float height, f3 o, f3 d, float tmin, float& tmax) { // rectangle.rs:38-51
+    if (fabsf(d.z) < 1e-8f) return false;
+    float t = -o.z / d.z;
+    if (t < tmin || t > tmax) return false;
+    f3 p = o + d * t;
+    float hw = width / 2.0f, hh = height / 2.0f;
+    if (p.x >= -hw && p.x <= hw && p.y >= -hh && p.y <= hh) { tmax = t; return true; }
+    return false;
+}
+
+__device__ __forceinline__ void load_xf(const float* __restrict__ src, float* dst) {
+    const float4* s = reinterpret_cast<const float4*>(src);
+#pragma unroll
+    for (int i = 0; i < 4; ++i) { float4 v = __ldg(s + i); dst[4 * i] = v.x; dst[4 * i + 1] = v.y; dst[4 * i + 2] = v.z; dst[4 * i + 3] = v.w; }
+}
+
+// ------------------------------------------------------------------------------------------
+// Scene::intersect (scene.rs:148-150): BVH<Instance> traversal, Instance::intersect per leaf entry
+// (receiver.rs:29-43 / emitter.rs:118-137). Returns the accept record; differential geometry is
+// computed once for the final hit by surface_at().
+// ------------------------------------------------------------------------------------------
+template <bool STATS>
+__device__ __noinline__ bool scene_trace(const DScene& sc, Ray& ray, HitRec& hit, bool any_hit, Cnt& cnt, int* err) {
+    const DNode* __restrict__ nodes = sc.tlas;
+    const f3 o = ray.o, d = ray.d;
+    const f3 inv = mk(1.0f / d.x, 1.0f / d.y, 1.0f / d.z);
+    const bool nx = d.x < 0.0f, ny = d.y < 0.0f, nz = d.z < 0.0f;
+    uint32_t stack[64];
+    int sp = 0;
+    uint32_t cur = 0;
+    bool result = false;
+    hit.inst = TRB_MISS; hit.prim = 0; hit.b1 = 0.0f; hit.b2 = 0.0f; hit.t = ray.tmax;
+    for (;;) {
+        const float4 lo = __ldg(&nodes[cur].lo), hi = __ldg(&nodes[cur].hi);
+        if (STATS) cnt.node++;
+        if (box_hit(lo, hi, o, inv, nx, ny, nz, ray.tmin, ray.tmax)) {
+            const uint32_t a = __float_as_uint(lo.w), b = __float_as_uint(hi.w);
+            if (b & LEAF_BIT) {
+                const uint32_t n = b & ~LEAF_BIT;
+                for (uint32_t k = a; k < a + n; ++k) {
+                    const uint32_t ii = __ldg(&sc.tlas_order[k]);
+                    const DInstance& in = sc.instances[ii];
+                    if (STATS) cnt.inst++;
+                    const uint32_t kind = __ldg(&in.kind);
+                    if (kind == TRB_INST_EMITTER_POINT) continue; // emitter.rs:119-120
+                    float m[16];
+                    load_xf(in.inv, m);
+                    const f3 lo_ = xf_point(m, o), ld_ = xf_vector(m, d); // inv_mul_ray: direction not renormalised
+                    const uint32_t shape = __ldg(&in.shape);
+                    const float p0 = __ldg(&in.p0), p1 = __ldg(&in.p1);
+                    float tmax = ray.tmax;
+                    bool h;
+                    HitRec local = hit;
+                    if (shape == TRB_SHAPE_MESH) h = blas_trace<STATS>(sc.meshes[__ldg(&in.mesh)], lo_, ld_, ray.tmin, tmax, local, any_hit, cnt, err);
+                    else if (shape == TRB_SHAPE_SPHERE) { h = sphere_t(p0, lo_, ld_, ray.tmin, tmax); local.prim = 0; }
+                    else if (shape == TRB_SHAPE_DISK) { h = disk_t(p0, p1, lo_, ld_, ray.tmin, tmax); local.prim = 0; }
+                    else { h = rect_t(p0, p1, lo_, ld_, ray.tmin, tmax); local.prim = 0; }
+                    if (h) {
+                        ray.tmax = tmax; // receiver.rs:36
+                        hit = local; hit.t = tmax; hit.inst = ii;
+                        result = true;
+                        if (any_hit) return true;
+                    }
+                }
+                if (sp == 0) break;
+                cur = stack[--sp];
+            } else {
+                const bool neg = b == 0 ? nx : (b == 1 ? ny : nz);
+                if (sp >= 64) { *err = 1; break; }
+                if (neg) { stack[sp++] = cur + 1; cur = a; }
+                else { stack[sp++] = a; cur = cur + 1; }
+            }
+        } else {
+            if (sp == 0) break;
+            cur = stack[--sp];
+        }
+    }
+    return result;
+}
+
+// ------------------------------------------------------------------------------------------
+// DifferentialGeometry of the final hit, transformed to world space (receiver.rs:36-41). Only the
+// members the integrator reads: p, n, ng, dp_du (u, v feed constant textures only; dp_dv only feeds n).
+// ------------------------------------------------------------------------------------------
+struct Surf { f3 p, n, ng, dp_du; };
+
+__device__ __forceinline__ void surface_at(const DScene& sc, const Ray& ray, const HitRec& hit, Surf& s) {
+    const DInstance& in = sc.instances[hit.inst];
+    float m[16];
+    load_xf(in.inv, m);
+    const f3 o = xf_point(m, ray.o), d = xf_vector(m, ray.d);
+    const f3 p = o + d * hit.t; // ray.at(t) of the local ray
+    const uint32_t shape = __ldg(&in.shape);
+    f3 n, ng, dp_du;
+    if (shape == TRB_SHAPE_MESH) {
+        const DMesh& me = sc.meshes[__ldg(&in.mesh)];
+        const uint32_t ia = __ldg(&me.indices[3 * hit.prim]), ib = __ldg(&me.indices[3 * hit.prim + 1]), ic = __ldg(&me.indices[3 * hit.prim + 2]);
+        const float* P = me.positions; const float* N = me.normals; const float* T = me.texcoords;
+        const f3 pa = mk(__ldg(P + 3 * ia), __ldg(P + 3 * ia + 1), __ldg(P + 3 * ia + 2));
+        const f3 pb = mk(__ldg(P + 3 * ib), __ldg(P + 3 * ib + 1), __ldg(P + 3 * ib + 2));
+        const f3 pc = mk(__ldg(P + 3 * ic), __ldg(P + 3 * ic + 1), __ldg(P + 3 * ic + 2));
+        const f3 na = mk(__ldg(N + 3 * ia), __ldg(N + 3 * ia + 1), __ldg(N + 3 * ia + 2));
+        const f3 nb = mk(__ldg(N + 3 * ib), __ldg(N + 3 * ib + 1), __ldg(N + 3 * ib + 2));
+        const f3 nc = mk(__ldg(N + 3 * ic), __ldg(N + 3 * ic + 1), __ldg(N + 3 * ic + 2));
+        const float b1 = hit.b1, b2 = hit.b2;
+        const float b0 = 1.0f - b1 - b2;
+        n = unit(unit(b0 * na + b1 * nb + b2 * nc)); // mesh.rs:174 normalises, DifferentialGeometry::with_normal normalises again
+        ng = n;                                      // with_normal: n == ng
+        const float tax = __ldg(T + 2 * ia), tay = __ldg(T + 2 * ia + 1), tbx = __ldg(T + 2 * ib), tby = __ldg(T + 2 * ib + 1);
+        const float tcx = __ldg(T + 2 * ic), tcy = __ldg(T + 2 * ic + 1);
+        const float du0 = tax - tcx, du1 = tbx - tcx, dv0 = tay - tcy, dv1 = tby - tcy; // mesh.rs:182-184
+        const float det = du0 * dv1 - dv0 * du1;
+        if (det == 0.0f) {
+            f3 dp_dv;
+            coord_system(unit(cross3(pc - pa, pb - pa)), dp_du, dp_dv); // cross(e[1], e[0])
+        } else {
+            const float idet = 1.0f / det;
+            const f3 dp0 = pa - pc, dp1 = pb - pc;
+            dp_du = (dv1 * dp0 - dv0 * dp1) * idet;
+        }
+    } else if (shape == TRB_SHAPE_SPHERE) {
+        n = unit(p); ng = n;                                            // sphere.rs:58, with_normal
+        dp_du = mk(-TRB_PI * 2.0f * p.y, TRB_PI * 2.0f * p.x, 0.0f);    // sphere.rs:75
+    } else if (shape == TRB_SHAPE_DISK) {
+        const float radius = __ldg(&in.p0), inner = __ldg(&in.p1);
+        const float hr = sqrtf(p.x * p.x + p.y * p.y);
+        dp_du = mk(-TRB_PI * 2.0f * p.y, TRB_PI * 2.0f * p.x, 0.0f);    // disk.rs:71
+        const f3 dp_dv = ((inner - radius) / hr) * mk(p.x, p.y, 0.0f);  // disk.rs:72
+        n = unit(cross3(dp_du, dp_dv));                                  // DifferentialGeometry::new
+        ng = unit(mk(0.0f, 0.0f, 1.0f));
+    } else {
+        const float hw = __ldg(&in.p0) / 2.0f, hh = __ldg(&in.p1) / 2.0f;
+        dp_du = mk(hw * 2.0f, 0.0f, 0.0f);                               // rectangle.rs:57-58
+        const f3 dp_dv = mk(0.0f, hh * 2.0f, 0.0f);
+        n = unit(cross3(dp_du, dp_dv));
+        ng = unit(mk(0.0f, 0.0f, 1.0f));
+    }
+    float w[16];
+    load_xf(in.mat, w);
+    s.p = xf_point(w, p);
+    s.n = xf_normal_t(m, n);
+    s.ng = xf_normal_t(m, ng);
+    s.dp_du = xf_vector(w, dp_du);
+}
+
+// ------------------------------------------------------------------------------------------
+// mc.rs
+// ------------------------------------------------------------------------------------------
+__device__ __forceinline__ void concentric_disk(float u0, float u1, float& ox, float& oy) { // mc.rs:22-51
+    float s0 = 2.0f * u0 - 1.0f, s1 = 2.0f * u1 - 1.0f;
+    if (s0 == 0.0f && s1 == 0.0f) { ox = s0; oy = s1; return; }
+    float radius, theta;
+    if (s0 >= -s1) {
+        if (s0 > s1) { radius = s0; theta = s1 > 0.0f ? s1 / s0 : 8.0f + s1 / s0; }
+        else { radius = s1; theta = 2.0f - s0 / s1; }
+    } else if (s0 <= s1) { radius = -s0; theta = 4.0f + s1 / s0; }
+    else { radius = -s1; theta = 6.0f - s0 / s1; }
+    theta = theta * TRB_PIO4;
+    float sn, cs;
+    dsincos(theta, sn, cs);
+    ox = radius * cs; oy = radius * sn;
+}
+__device__ __forceinline__ f3 cos_hemisphere(float u0, float u1) { // mc.rs:11-16
+    float dx, dy;
+    concentric_disk(u0, u1, dx, dy);
+    return mk(dx, dy, sqrtf(fmaxf(0.0f, 1.0f - dx * dx - dy * dy)));
+}
+__device__ __forceinline__ float power_heuristic(float pf, float pg) { // mc.rs:56-60 with n_f = n_g = 1
+    float f = 1.0f * pf, g = 1.0f * pg;
+    return (f * f) / (f * f + g * g);
+}
+
+// ------------------------------------------------------------------------------------------
+// BxDFs (src/bxdf/**). Shading-space vectors; colours are rgb (alpha is never observable).
+// ------------------------------------------------------------------------------------------
+enum { BX_REFLECTION = 1, BX_TRANSMISSION = 2, BX_DIFFUSE = 4, BX_GLOSSY = 8, BX_SPECULAR = 16 }; // bxdf/mod.rs:37-41
+constexpr uint32_t BX_ALL = 31, BX_NON_SPECULAR = BX_DIFFUSE | BX_GLOSSY | BX_REFLECTION | BX_TRANSMISSION;
+enum { LK_LAMBERT, LK_OREN_NAYAR, LK_SPEC_REFL, LK_SPEC_TRANS, LK_TS, LK_MT, LK_MERL };
+
+struct Mat { // DMaterial in registers
+    uint32_t type; f3 c0, c1; float roughness, width, eta, on_a, on_b; uint32_t merl_off;
+};
+__device__ __forceinline__ void load_mat(const DMaterial& m, Mat& o) {
+    o.type = __ldg(&m.type);
+    o.c0 = mk(__ldg(&m.c0[0]), __ldg(&m.c0[1]), __ldg(&m.c0[2]));
+    o.c1 = mk(__ldg(&m.c1[0]), __ldg(&m.c1[1]), __ldg(&m.c1[2]));
+    o.roughness = __ldg(&m.roughness); o.width = __ldg(&m.width); o.eta = __ldg(&m.eta);
+    o.on_a = __ldg(&m.on_a); o.on_b = __ldg(&m.on_b); o.merl_off = __ldg(&m.merl_off);
+}
+// The lobes Material::bsdf allocates, in allocation order (material/{matte:52,plastic:59,metal:56,
+// specular_metal:49,glass:51,rough_glass:57,merl:88}.rs). Returns false when lobe `i` does not exist.
+__device__ __forceinline__ bool lobe_of(const Mat& m, int i, int& kind, uint32_t& type, f3& col) {
+    switch (m.type) {
+        case TRB_MAT_MATTE:
+            if (i != 0) return false;
+            kind = m.roughness == 0.0f ? LK_LAMBERT : LK_OREN_NAYAR; type = BX_DIFFUSE | BX_REFLECTION; col = m.c0; return true;
+        case TRB_MAT_PLASTIC: {
+            const bool d = !black(m.c0), g = !black(m.c1);
+            if (i == 0 && d) { kind = LK_LAMBERT; type = BX_DIFFUSE | BX_REFLECTION; col = m.c0; return true; }
+            if (((i == 0 && !d) || (i == 1 && d)) && g) { kind = LK_TS; type = BX_GLOSSY | BX_REFLECTION; col = m.c1; return true; }
+            return false;
+        }
+        case TRB_MAT_METAL:
+            if (i != 0) return false;
+            kind = LK_TS; type = BX_GLOSSY | BX_REFLECTION; col = splat(1.0f); return true;
+        case TRB_MAT_SPECULAR_METAL:
+            if (i != 0) return false;
+            kind = LK_SPEC_REFL; type = BX_SPECULAR | BX_REFLECTION; col = splat(1.0f); return true;
+        case TRB_MAT_GLASS: {
+            const bool r = !black(m.c0), t = !black(m.c1);
+            if (i == 0 && r) { kind = LK_SPEC_REFL; type = BX_SPECULAR | BX_REFLECTION; col = m.c0; return true; }
+            if (((i == 0 && !r) || (i == 1 && r)) && t) { kind = LK_SPEC_TRANS; type = BX_SPECULAR | BX_TRANSMISSION; col = m.c1; return true; }
+            return false;
+        }
+        case TRB_MAT_ROUGH_GLASS: {
+            const bool r = !black(m.c0), t = !black(m.c1);
+            if (i == 0 && r) { kind = LK_TS; type = BX_GLOSSY | BX_REFLECTION; col = m.c0; return true; }
+            if (((i == 0 && !r) || (i == 1 && r)) && t) { kind = LK_MT; type = BX_GLOSSY | BX_TRANSMISSION; col = m.c1; return true; }
+            return false;
+        }
+        default: // TRB_MAT_MERL
+            if (i != 0) return false;
+            kind = LK_MERL; type = BX_GLOSSY | BX_REFLECTION; col = splat(0.0f); return true;
+    }
+}
+__device__ __forceinline__ bool type_matches(uint32_t type, uint32_t flags) { return (type & ~flags) == 0; } // is_subset
+
+// trig helpers (bxdf/mod.rs:125-166)
+__device__ __forceinline__ float sin2_theta(f3 v) { return fmaxf(0.0f, 1.0f - v.z * v.z); }
+__device__ __forceinline__ float sin_theta(f3 v) { return sqrtf(sin2_theta(v)); }
+__device__ __forceinline__ float tan_theta(f3 v) { float s2 = sin2_theta(v); return s2 <= 0.0f ? 0.0f : sqrtf(s2) / v.z; }
+__device__ __forceinline__ float cos_phi(f3 v) { float s = sin_theta(v); return s == 0.0f ? 1.0f : clampf(v.x / s, -1.0f, 1.0f); }
+__device__ __forceinline__ float sin_phi(f3 v) { float s = sin_theta(v); return s == 0.0f ? 0.0f : clampf(v.y / s, -1.0f, 1.0f); }
+__device__ __forceinline__ bool same_hemi(f3 a, f3 b) { return a.z * b.z > 0.0f; }
+
+// fresnel.rs. Conductor for the metals, Dielectric(1, eta) for glass, Dielectric(1, 1.5) for plastic (Q16).
+__device__ __forceinline__ void dielectric_etas(const Mat& m, float& ei, float& et) { ei = 1.0f; et = m.type == TRB_MAT_PLASTIC ? 1.5f : m.eta; }
+__device__ __forceinline__ f3 fresnel(const Mat& m, float cos_i) {
+    if (m.type == TRB_MAT_METAL || m.type == TRB_MAT_SPECULAR_METAL) { // fresnel.rs:19-28
+        const float c = fabsf(cos_i);
+        const f3 eta = m.c0, k = m.c1, one = splat(1.0f);
+        const f3 a = (eta * eta + k * k) * c * c;
+        const f3 r_par = (a - eta * c * 2.0f + one) / (a + eta * c * 2.0f + one);
+        const f3 b = eta * eta + k * k;
+        const f3 cc = splat(c * c);
+        const f3 r_perp = (b - eta * c * 2.0f + cc) / (b + eta * c * 2.0f + cc);
+        return (r_par + r_perp) * 0.5f;
+    }
+    float eta_i, eta_t;
+    dielectric_etas(m, eta_i, eta_t);
+    const float ci = clampf(cos_i, -1.0f, 1.0f); // fresnel.rs:48-66
+    const float ei = ci > 0.0f ? eta_i : eta_t, et = ci > 0.0f ? eta_t : eta_i;
+    const float sin_t = ei / et * sqrtf(fmaxf(0.0f, 1.0f - ci * ci));
+    if (sin_t >= 1.0f) return splat(1.0f);
+    const float ct = sqrtf(fmaxf(0.0f, 1.0f - sin_t * sin_t));
+    const float aci = fabsf(ci);
+    const float r_par = (et * aci - ei * ct) / (et * aci + ei * ct); // fresnel.rs:10-14
+    const float r_perp = (ei * aci - et * ct) / (ei * aci + et * ct);
+    return splat(0.5f * (r_par * r_par + r_perp * r_perp));
+}
+// microfacet/beckmann.rs
+__device__ __forceinline__ float beck_d(float width, f3 wh) { // :26-35
+    const float c2 = wh.z * wh.z;
+    const float tan_sqr = sin2_theta(wh) / c2;
+    if (isinf(tan_sqr)) return 0.0f;
+    const float c4 = c2 * c2;
+    const float w2 = width * width;
+    return dexp(-tan_sqr / w2) / (TRB_PI * w2 * c4);
+}
+__device__ __forceinline__ f3 beck_sample(float width, float u0, float u1) { // :36-46
+    float ls = dlog(1.0f - u0);
+    if (isinf(ls)) ls = 0.0f;
+    const float tan2 = -(width * width) * ls;
+    const float phi = 2.0f * TRB_PI * u1;
+    const float ct = 1.0f / sqrtf(1.0f + tan2);
+    const float st = sqrtf(fmaxf(0.0f, 1.0f - ct * ct));
+    float sn, cs;
+    dsincos(phi, sn, cs);
+    return mk(st * cs, st * sn, ct); // linalg::spherical_dir
+}
+__device__ __forceinline__ float beck_pdf(float width, f3 wh) { return fabsf(wh.z) * beck_d(width, wh); }
+__device__ __forceinline__ float beck_g1(float width, f3 v) { // :56-64
+    const float a = 1.0f / (width * fabsf(tan_theta(v)));
+    if (a < 1.6f) { const float a2 = a * a; return (3.535f * a + 2.181f * a2) / (1.0f + 2.276f * a + 2.577f * a2); }
+    return 1.0f;
+}
+__device__ __forceinline__ bool refract3(f3 w, f3 n, float eta, f3& out) { // linalg/mod.rs:117-127
+    const float c1 = dot3(n, w);
+    const float s1 = fmaxf(0.0f, 1.0f - c1 * c1);
+    const float s2 = eta * eta * s1;
+    if (s2 >= 1.0f) return false;
+    const float c2 = sqrtf(1.0f - s2);
+    out = eta * -w + (eta * c1 - c2) * n;
+    return true;
+}
+// microfacet_transmission.rs helpers
+__device__ __forceinline__ void mt_etas(const Mat& m, f3 wo, float& e0, float& e1) { // :33-39
+    float ei, et;
+    dielectric_etas(m, ei, et);
+    if (wo.z > 0.0f) { e0 = ei; e1 = et; } else { e0 = et; e1 = ei; }
+}
+__device__ __forceinline__ float mt_jacobian(f3 wo, f3 wi, f3 wh, float e0, float e1) { // :40-49
+    const float ih = dot3(wi, wh), oh = dot3(wo, wh);
+    const float s = e1 * ih + e0 * oh;
+    const float denom = s * s;
+    if (denom != 0.0f) return fabsf(e0 * e0 * fabsf(oh) / denom);
+    return 0.0f;
+}
+__device__ __forceinline__ f3 mt_half(f3 wo, f3 wi, float e0, float e1) { return unit(-e1 * wi - e0 * wo); } // :50-52
+
+__device__ __forceinline__ uint32_t merl_index(float val, float mx, uint32_t n) { // bxdf/merl.rs:42-44
+    uint32_t i = f2u(val / mx * (float)n);
+    return i > n - 1 ? n - 1 : i;
+}
+__device__ __noinline__ f3 merl_eval(const float* __restrict__ table, f3 wo, f3 wi_in) { // bxdf/merl.rs:47-82
+    f3 wi = wi_in;
+    f3 wh = wo + wi;
+    if (wh.z < 0.0f) { wi = -wi; wh = -wh; }
+    if (len2(wh) == 0.0f) return splat(0.0f);
+    wh = unit(wh);
+    const float theta_h = dacos(clampf(wh.z, -1.0f, 1.0f));
+    const float cph = cos_phi(wh), sph = sin_phi(wh), cth = wh.z, sth = sin_theta(wh);
+    const f3 whx = mk(cph * cth, sph * cth, -sth), why = mk(-sph, cph, 0.0f);
+    const f3 wd = mk(dot3(wi, whx), dot3(wi, why), dot3(wi, wh));
+    const float theta_d = dacos(clampf(wd.z, -1.0f, 1.0f));
+    float phi_d = datan2(wd.y, wd.x);
+    if (phi_d < 0.0f) phi_d = phi_d + TRB_PI * 2.0f;
+    if (phi_d > TRB_PI) phi_d = phi_d - TRB_PI;
+    const uint32_t ih = merl_index(sqrtf(fmaxf(0.0f, 2.0f * theta_h / TRB_PI)), 1.0f, TRB_MERL_N_THETA_H);
+    const uint32_t id = merl_index(theta_d, TRB_PI / 2.0f, TRB_MERL_N_THETA_D);
+    const uint32_t ip = merl_index(phi_d, TRB_PI, TRB_MERL_N_PHI_D);
+    const uint32_t i = ip + TRB_MERL_N_PHI_D * (id + ih * TRB_MERL_N_THETA_D);
+    return mk(__ldg(table + 3 * i), __ldg(table + 3 * i + 1), __ldg(table + 3 * i + 2));
+}
+
+__device__ f3 lobe_eval(const DScene& sc, const Mat& m, int kind, f3 col, f3 wo, f3 wi) {
+    switch (kind) {
+        case LK_LAMBERT: return col * TRB_INV_PI; // lambertian.rs:32-34
+        case LK_OREN_NAYAR: { // oren_nayar.rs:43-61
+            const float so = sin_theta(wo), si = sin_theta(wi);
+            float max_cos = 0.0f;
+            if (si > 1e-4f && so > 1e-4f) max_cos = fmaxf(0.0f, cos_phi(wi) * cos_phi(wo) + sin_phi(wi) * sin_phi(wo));
+            float sin_alpha, tan_beta;
+            if (fabsf(wi.z) > fabsf(wo.z)) { sin_alpha = so; tan_beta = si / fabsf(wi.z); }
+            else { sin_alpha = si; tan_beta = so / fabsf(wo.z); }
+            return col * TRB_INV_PI * (m.on_a + m.on_b * max_cos * sin_alpha * tan_beta);
+        }
+        case LK_TS: { // torrance_sparrow.rs:40-56
+            const float cto = fabsf(wo.z), cti = fabsf(wi.z);
+            if (cto == 0.0f || cti == 0.0f) return splat(0.0f);
+            f3 wh = wi + wo;
+            if (wh.x == 0.0f && wh.y == 0.0f && wh.z == 0.0f) return splat(0.0f);
+            wh = unit(wh);
+            const float d = beck_d(m.width, wh);
+            const f3 f = fresnel(m, dot3(wi, wh));
+            const float g = beck_g1(m.width, wi) * beck_g1(m.width, wo);
+            return col * f * d * g / (4.0f * cti * cto);
+        }
+        case LK_MT: { // microfacet_transmission.rs:65-82
+            if (same_hemi(wo, wi)) return splat(0.0f);
+            if (wo.z == 0.0f || wi.z == 0.0f) return splat(0.0f);
+            float e0, e1;
+            mt_etas(m, wo, e0, e1);
+            const f3 wh = mt_half(wo, wi, e0, e1);
+            const float d = beck_d(m.width, wh);
+            const f3 f = splat(1.0f) - fresnel(m, dot3(wi, wh));
+            const float g = beck_g1(m.width, wi) * beck_g1(m.width, wo);
+            const float ih = dot3(wi, wh);
+            const float jac = mt_jacobian(wo, wi, wh, e0, e1);
+            return col * (fabsf(ih) / (fabsf(wi.z) * fabsf(wo.z))) * (f * g * d) * jac;
+        }
+        case LK_MERL: return merl_eval(sc.merl + m.merl_off, wo, wi);
+        default: return splat(0.0f); // specular lobes (specular_reflection.rs:38, specular_transmission.rs:38)
+    }
+}
+__device__ float lobe_pdf(const Mat& m, int kind, f3 wo, f3 wi) {
+    switch (kind) {
+        case LK_TS: { // torrance_sparrow.rs:73-81
+            if (!same_hemi(wo, wi)) return 0.0f;
+            const f3 wh = unit(wo + wi);
+            const float jac = 1.0f / (4.0f * fabsf(dot3(wo, wh)));
+            return beck_pdf(m.width, wh) * jac;
+        }
+        case LK_MT: { // microfacet_transmission.rs:100-108
+            if (same_hemi(wo, wi)) return 0.0f;
+            float e0, e1;
+            mt_etas(m, wo, e0, e1);
+            const f3 wh = mt_half(wo, wi, e0, e1);
+            return beck_pdf(m.width, wh) * mt_jacobian(wo, wi, wh, e0, e1);
+        }
+        default: // BxDF::pdf default (bxdf/mod.rs:114-121)
+            return same_hemi(wo, wi) ? fabsf(wi.z) * TRB_INV_PI : 0.0f;
+    }
+}
+__device__ void lobe_sample(const DScene& sc, const Mat& m, int kind, f3 col, f3 wo, float u0, float u1, f3& f, f3& wi, float& pdf) {
+    switch (kind) {
+        case LK_SPEC_REFL: { // specular_reflection.rs:39-50
+            wi = mk(-wo.x, -wo.y, wo.z);
+            if (wi.z != 0.0f) { f = fresnel(m, wo.z) * col / fabsf(wi.z); pdf = 1.0f; }
+            else { f = splat(0.0f); pdf = 0.0f; }
+            return;
+        }
+        case LK_SPEC_TRANS: { // specular_transmission.rs:39-56
+            float eta_i, eta_t;
+            dielectric_etas(m, eta_i, eta_t);
+            const bool entering = wo.z > 0.0f;
+            const float ei = entering ? eta_i : eta_t, et = entering ? eta_t : eta_i;
+            const f3 n = entering ? mk(0.0f, 0.0f, 1.0f) : mk(0.0f, 0.0f, -1.0f);
+            f3 r;
+            if (refract3(wo, n, ei / et, r)) {
+                wi = r;
+                const f3 fr = splat(1.0f) - fresnel(m, wi.z);
+                f = fr * col / fabsf(wi.z); pdf = 1.0f;
+            } else { f = splat(0.0f); wi = splat(0.0f); pdf = 0.0f; }
+            return;
+        }
+        case LK_TS: { // torrance_sparrow.rs:57-72
+            if (wo.z == 0.0f) { f = splat(0.0f); wi = splat(0.0f); pdf = 0.0f; return; }
+            f3 wh = beck_sample(m.width, u0, u1);
+            if (!same_hemi(wo, wh)) wh = -wh;
+            wi = 2.0f * dot3(wo, wh) * wh - wo; // linalg::reflect
+            if (!same_hemi(wo, wi)) { f = splat(0.0f); wi = splat(0.0f); pdf = 0.0f; }
+            else { f = lobe_eval(sc, m, kind, col, wo, wi); pdf = lobe_pdf(m, kind, wo, wi); }
+            return;
+        }
+        case LK_MT: { // microfacet_transmission.rs:83-99
+            f3 wh = beck_sample(m.width, u0, u1);
+            if (!same_hemi(wo, wh)) wh = -wh;
+            float e0, e1;
+            mt_etas(m, wo, e0, e1);
+            f3 r;
+            if (refract3(wo, wh, e0 / e1, r) && !same_hemi(wo, r)) { wi = r; f = lobe_eval(sc, m, kind, col, wo, wi); pdf = lobe_pdf(m, kind, wo, wi); }
+            else { f = splat(0.0f); wi = splat(0.0f); pdf = 0.0f; }
+            return;
+        }
+        default: { // BxDF::sample default (bxdf/mod.rs:102-108): Lambertian, Oren-Nayar, Merl
+            wi = cos_hemisphere(u0, u1);
+            if (wo.z < 0.0f) wi.z *= -1.0f;
+            f = lobe_eval(sc, m, kind, col, wo, wi); pdf = lobe_pdf(m, kind, wo, wi);
+            return;
+        }
+    }
+}
+
+// bxdf::BSDF (bsdf.rs)
+struct Frame { f3 p, n, tan, bitan; };
+__device__ __forceinline__ void make_frame(const Surf& s, Frame& fr) { // bsdf.rs:38-44
+    fr.n = unit(s.n);
+    const f3 bt = unit(s.dp_du);
+    fr.tan = cross3(fr.n, bt);
+    fr.bitan = cross3(fr.tan, fr.n);
+    fr.p = s.p;
+}
+__device__ __forceinline__ f3 to_shading(const Frame& fr, f3 v) { return mk(dot3(v, fr.bitan), dot3(v, fr.tan), dot3(v, fr.n)); }
+__device__ __forceinline__ f3 from_shading(const Frame& fr, f3 v) {
+    return mk(fr.bitan.x * v.x + fr.tan.x * v.y + fr.n.x * v.z, fr.bitan.y * v.x + fr.tan.y * v.y + fr.n.y * v.z,
+              fr.bitan.z * v.x + fr.tan.z * v.y + fr.n.z * v.z);
+}
+__device__ __noinline__ f3 bsdf_eval(const DScene& sc, const Mat& m, const Frame& fr, f3 wo_w, f3 wi_w, uint32_t flags) { // bsdf.rs:66-78
+    const f3 wo = unit(to_shading(fr, wo_w)), wi = unit(to_shading(fr, wi_w));
+    if (wo.z * wi.z > 0.0f) flags &= ~(uint32_t)BX_TRANSMISSION; else flags &= ~(uint32_t)BX_REFLECTION;
+    f3 acc = splat(0.0f);
+#pragma unroll 1
+    for (int i = 0; i < 2; ++i) {
+        int kind; uint32_t type; f3 col;
+        if (lobe_of(m, i, kind, type, col) && type_matches(type, flags)) acc = acc + lobe_eval(sc, m, kind, col, wo, wi);
+    }
+    return acc;
+}
+__device__ __noinline__ float bsdf_pdf(const Mat& m, const Frame& fr, f3 wo_w, f3 wi_w, uint32_t flags) { // bsdf.rs:114-125
+    const f3 wo = unit(to_shading(fr, wo_w)), wi = unit(to_shading(fr, wi_w));
+    float pdf = 0.0f; int n = 0;
+#pragma unroll 1
+    for (int i = 0; i < 2; ++i) {
+        int kind; uint32_t type; f3 col;
+        if (lobe_of(m, i, kind, type, col) && type_matches(type, flags)) { pdf = pdf + lobe_pdf(m, kind, wo, wi); n++; }
+    }
+    return n > 0 ? pdf / (float)n : 0.0f;
+}
+__device__ __noinline__ void bsdf_sample(const DScene& sc, const Mat& m, const Frame& fr, f3 wo_w, uint32_t flags, float u0, float u1, float uc,
+                                         f3& f, f3& wi_w, float& pdf, uint32_t& sampled) { // bsdf.rs:85-112
+    int n_matching = 0;
+    for (int i = 0; i < 2; ++i) { int k; uint32_t t; f3 c; if (lobe_of(m, i, k, t, c) && type_matches(t, flags)) n_matching++; }
+    if (n_matching == 0) { f = splat(0.0f); wi_w = splat(0.0f); pdf = 0.0f; sampled = 0; return; }
+    uint32_t comp = f2u(uc * (float)n_matching);
+    if (comp > (uint32_t)n_matching - 1) comp = n_matching - 1;
+    int kind = 0; uint32_t type = 0; f3 col = splat(0.0f);
+    for (int i = 0, k = 0; i < 2; ++i) {
+        int kk; uint32_t tt; f3 cc;
+        if (lobe_of(m, i, kk, tt, cc) && type_matches(tt, flags)) { if ((uint32_t)k == comp) { kind = kk; type = tt; col = cc; break; } k++; }
+    }
+    const f3 wo = unit(to_shading(fr, wo_w));
+    f3 wi;
+    lobe_sample(sc, m, kind, col, wo, u0, u1, f, wi, pdf);
+    if (len2(wi) == 0.0f) { f = splat(0.0f); wi_w = splat(0.0f); pdf = 0.0f; sampled = 0; return; }
+    wi_w = unit(from_shading(fr, wi));
+    const bool spec = (type & BX_SPECULAR) != 0;
+    if (!spec && n_matching > 1) pdf = bsdf_pdf(m, fr, wo_w, wi_w, flags);
+    if (!spec) f = bsdf_eval(sc, m, fr, wo_w, wi_w, flags);
+    sampled = type;
+}
+
+// ------------------------------------------------------------------------------------------
+// Sampleable shapes (sphere.rs:91-141, disk.rs:84-110, rectangle.rs:74-105), object space
+// ------------------------------------------------------------------------------------------
+__device__ __forceinline__ float shape_area(uint32_t shape, float p0, float p1) {
+    if (shape == TRB_SHAPE_SPHERE) return 4.0f * TRB_PI * p0;          // sic (Q3)
+    if (shape == TRB_SHAPE_DISK) return TRB_PI * (p0 * p0 - p1 * p1);
+    return p0 * p1;
+}
+__device__ __forceinline__ void shape_sample_uniform(uint32_t shape, float p0, float p1, float u0, float u1, f3& p, f3& n) {
+    if (shape == TRB_SHAPE_SPHERE) { // sphere.rs:92-95, mc::uniform_sample_sphere
+        const float z = 1.0f - 2.0f * u0;
+        const float r = sqrtf(fmaxf(0.0f, 1.0f - z * z));
+        const float phi = TRB_PI * 2.0f * u1;
+        float sn, cs;
+        dsincos(phi, sn, cs);
+        p = splat(0.0f) + p0 * mk(cs * r, sn * r, z);
+        n = unit(p);
+    } else if (shape == TRB_SHAPE_DISK) { // disk.rs:85-90 (ignores inner radius, Q4)
+        float dx, dy;
+        concentric_disk(u0, u1, dx, dy);
+        p = mk(dx * p0, dy * p0, 0.0f); n = mk(0.0f, 0.0f, 1.0f);
+    } else { // rectangle.rs:77-80
+        p = mk(u0 * p0 - p0 / 2.0f, u1 * p1 - p1 / 2.0f, 0.0f); n = mk(0.0f, 0.0f, 1.0f);
+    }
+}
+__device__ void shape_sample(uint32_t shape, float p0, float p1, f3 pt, float u0, float u1, f3& p, f3& n) {
+    if (shape != TRB_SHAPE_SPHERE) { shape_sample_uniform(shape, p0, p1, u0, u1, p, n); return; }
+    const float dist_sqr = len2(pt - splat(0.0f)); // sphere.rs:99-124
+    if (dist_sqr - p0 * p0 < 0.0001f) { shape_sample_uniform(shape, p0, p1, u0, u1, p, n); return; }
+    const f3 wz = unit(splat(0.0f) - pt);
+    f3 wx, wy;
+    coord_system(wz, wx, wy);
+    const float ctm = sqrtf(fmaxf(0.0f, 1.0f - p0 * p0 / dist_sqr));
+    const float ct = lerpf(u0, ctm, 1.0f); // mc::uniform_sample_cone_frame (mc.rs:77-83)
+    const float st = sqrtf(1.0f - ct * ct);
+    const float phi = u1 * TRB_PI * 2.0f;
+    float sn, cs;
+    dsincos(phi, sn, cs);
+    const f3 dir = unit(cs * st * wx + sn * st * wy + ct * wz);
+    float tmax = finf();
+    if (sphere_t(p0, pt, dir, 0.0f, tmax)) { p = pt + dir * tmax; n = unit(p); return; } // (dg.p, dg.ng)
+    const float t = dot3(splat(0.0f) - pt, dir);
+    p = pt + dir * t;
+    n = unit(p);
+}
+__device__ float shape_pdf(uint32_t shape, float p0, float p1, f3 pt, f3 wi) {
+    if (shape == TRB_SHAPE_SPHERE) { // sphere.rs:131-140
+        const float dist_sqr = len2(pt - splat(0.0f));
+        if (dist_sqr - p0 * p0 < 0.0001f) return 1.0f / shape_area(shape, p0, p1);
+        const float ctm = sqrtf(fmaxf(0.0f, 1.0f - p0 * p0 / dist_sqr));
+        return 1.0f / (TRB_PI * 2.0f * (1.0f - ctm)); // mc::uniform_cone_pdf
+    }
+    // disk.rs:97-110 / rectangle.rs:91-104: re-intersect from pt along wi on [0.001, inf)
+    float tmax = finf();
+    const bool hit = shape == TRB_SHAPE_DISK ? disk_t(p0, p1, pt, wi, 0.001f, tmax) : rect_t(p0, p1, pt, wi, 0.001f, tmax);
+    if (!hit) return 0.0f;
+    const f3 ph = pt + wi * tmax;
+    f3 n; // d.n of DifferentialGeometry::new = normalize(cross(dp_du, dp_dv))
+    if (shape == TRB_SHAPE_DISK) {
+        const float hr = sqrtf(ph.x * ph.x + ph.y * ph.y);
+        const f3 dp_du = mk(-TRB_PI * 2.0f * ph.y, TRB_PI * 2.0f * ph.x, 0.0f);
+        const f3 dp_dv = ((p1 - p0) / hr) * mk(ph.x, ph.y, 0.0f);
+        n = unit(cross3(dp_du, dp_dv));
+    } else {
+        const float hw = p0 / 2.0f, hh = p1 / 2.0f;
+        n = unit(cross3(mk(hw * 2.0f, 0.0f, 0.0f), mk(0.0f, hh * 2.0f, 0.0f)));
+    }
+    const f3 w = -wi;
+    const float pdf = len2(pt - ph) / (fabsf(dot3(n, w)) * shape_area(shape, p0, p1));
+    return isfinite(pdf) ? pdf : 0.0f;
+}
+
+// ------------------------------------------------------------------------------------------
+// per-thread sampler state: the LowDiscrepancy sampler (ld.rs) on the counter RNG
+// ------------------------------------------------------------------------------------------
+struct PathRng {
+    uint32_t h;   // hash state after (seed, pixel, sample)
+    uint32_t len; // max_depth + 1 (path.rs:48)
+    __device__ __forceinline__ uint32_t draw(uint32_t dim) const { return rng_absorb(h, dim); }
+    __device__ __forceinline__ void two_d(uint32_t b, uint32_t d0, uint32_t d1, uint32_t dp, float& x, float& y) const {
+        const uint32_t i = permute_index(b, len, draw(dp));
+        x = ld_vdc(i, scramble_of(draw(d0)));
+        y = ld_sobol(i, scramble_of(draw(d1)));
+    }
+    __device__ __forceinline__ float one_d(uint32_t b, uint32_t d0, uint32_t dp) const {
+        return ld_vdc(permute_index(b, len, draw(dp)), scramble_of(draw(d0)));
+    }
+};
+
+struct RayCounts { uint32_t primary, shadow, mis, cont; };
+
+// ------------------------------------------------------------------------------------------
+// Integrator::estimate_direct (integrator/mod.rs:122-169) with sample_one_light's light choice
+// already made; Light impl of Emitter (emitter.rs:160-204); OcclusionTester (light/mod.rs:21-37).
+// ------------------------------------------------------------------------------------------
+template <bool STATS>
+__device__ __noinline__ f3 estimate_direct(const DScene& sc, const Mat& m, const Frame& fr, f3 wo, uint32_t li, float l0, float l1, float b0, float b1,
+                                           float bc, bool ref_shadow, RayCounts& rc, Cnt& cnt, int* err) {
+    f3 direct = splat(0.0f);
+    const DInstance& light = sc.instances[li];
+    const uint32_t kind = __ldg(&light.kind), shape = __ldg(&light.shape);
+    const float p0 = __ldg(&light.p0), p1 = __ldg(&light.p1);
+    const f3 emission = mk(__ldg(&light.emission[0]), __ldg(&light.emission[1]), __ldg(&light.emission[2]));
+    const bool delta = kind == TRB_INST_EMITTER_POINT;
+    float linv[16], lmat[16];
+    load_xf(light.inv, linv);
+    load_xf(light.mat, lmat);
+    const f3 p = fr.p;
+    // --- light.sample_incident(&bsdf.p, ...) ---
+    f3 lrad, wi, seg;
+    float pdf_light;
+    if (delta) { // emitter.rs:169-174
+        const f3 pos = xf_point(lmat, splat(0.0f));
+        wi = unit(pos - p);
+        lrad = emission / len2(pos - p);
+        pdf_light = 1.0f;
+        seg = pos - p;
+    } else { // emitter.rs:175-185 (object-space pdf and direction, Q5)
+        const f3 pl = xf_point(linv, p);
+        f3 ps, nl;
+        shape_sample(shape, p0, p1, pl, l0, l1, ps, nl);
+        const f3 wil = unit(ps - pl);
+        pdf_light = shape_pdf(shape, p0, p1, pl, wil);
+        lrad = dot3(-wil, nl) > 0.0f ? emission : splat(0.0f); // Emitter::radiance
+        const f3 pw = xf_point(lmat, ps);
+        wi = xf_vector(lmat, wil);
+        seg = pw - p;
+    }
+    if (pdf_light > 0.0f && !black(lrad)) {
+        Ray sr; sr.o = p; sr.d = seg; sr.tmin = 0.001f; sr.tmax = 0.999f; // OcclusionTester::test_points
+        HitRec sh;
+        rc.shadow++;
+        const bool occluded = scene_trace<STATS>(sc, sr, sh, !ref_shadow, cnt, err);
+        if (!occluded) {
+            const f3 f = bsdf_eval(sc, m, fr, wo, wi, BX_NON_SPECULAR);
+            if (!black(f)) {
+                if (delta) direct = f * lrad * fabsf(dot3(wi, fr.n)) / pdf_light;
+                else {
+                    const float pdf_bsdf = bsdf_pdf(m, fr, wo, wi, BX_NON_SPECULAR);
+                    const float w = power_heuristic(pdf_light, pdf_bsdf);
+                    direct = f * lrad * fabsf(dot3(wi, fr.n)) * w / pdf_light;
+                }
+            }
+        }
+    }
+    if (!delta) { // --- BSDF sampling ---
+        f3 f, wi2; float pdf_bsdf; uint32_t sampled;
+        bsdf_sample(sc, m, fr, wo, BX_NON_SPECULAR, b0, b1, bc, f, wi2, pdf_bsdf, sampled);
+        if (pdf_bsdf > 0.0f && !black(f)) {
+            float w = 1.0f;
+            if (!(sampled & BX_SPECULAR)) { // light.pdf (emitter.rs:193-203)
+                const f3 pl = xf_point(linv, p);
+                const f3 wl = unit(xf_vector(linv, wi2));
+                const float pl_pdf = shape_pdf(shape, p0, p1, pl, wl);
+                if (pl_pdf == 0.0f) return direct; // Q7
+                w = power_heuristic(pdf_bsdf, pl_pdf);
+            }
+            Ray mr; mr.o = p; mr.d = wi2; mr.tmin = 0.001f; mr.tmax = finf();
+            HitRec mh;
+            rc.mis++;
+            f3 lr = splat(0.0f);
+            if (scene_trace<STATS>(sc, mr, mh, false, cnt, err) && mh.inst == li) {
+                // e.radiance(&-w_i, &h.dg.p, &h.dg.ng, time): needs the hit's world geometric normal
+                Surf s;
+                surface_at(sc, mr, mh, s);
+                if (dot3(-wi2, s.ng) > 0.0f) lr = emission;
+            }
+            if (!black(lr)) direct = direct + f * lr * fabsf(dot3(wi2, fr.n)) * w / pdf_bsdf;
+        }
+    }
+    return direct;
+}
+
+// ------------------------------------------------------------------------------------------
+// One camera sample: Camera::generate_ray + Scene::intersect + Path::illumination + clamp
+// (multithreaded.rs:94-102, path.rs:45-119).
+// ------------------------------------------------------------------------------------------
+__device__ __forceinline__ void camera_ray(const DScene& sc, float sx, float sy, float tm, Ray& ray) { // camera.rs:150-157
+    const f3 pc = xf_point(sc.cam.px_to_cam, mk(sx, sy, 0.0f));
+    const f3 pp = mk(sc.cam.scaling[0], sc.cam.scaling[1], sc.cam.scaling[2]) * pc;
+    const f3 d = unit(pp);
+    (void)tm; // static camera: cam_world.transform(frame_time) is time-independent
+    ray.o = xf_point(sc.cam.cam_mat, splat(0.0f));
+    ray.d = xf_vector(sc.cam.cam_mat, d);
+    ray.tmin = 0.0f; ray.tmax = finf();
+}
+
+template <bool STATS>
+__device__ f3 radiance_of_sample(const DScene& sc, Ray ray, uint32_t hpix_sample, bool ref_shadow, RayCounts& rc, Cnt& cnt, int* err) {
+    HitRec hit;
+    rc.primary++;
+    if (!scene_trace<STATS>(sc, ray, hit, false, cnt, err)) return splat(0.0f); // multithreaded.rs:101-102
+    PathRng rng; rng.h = hpix_sample; rng.len = sc.max_depth + 1;
+    f3 illum = splat(0.0f), throughput = splat(1.0f);
+    bool specular_bounce = false;
+    uint32_t bounce = 0;
+    Surf s;
+    surface_at(sc, ray, hit, s);
+    const f3 first_ng = s.ng; // path.rs:73 reads hit.dg of the FIRST hit (Q1)
+    for (;;) {
+        const DInstance& in = sc.instances[hit.inst];
+        if (bounce == 0 || specular_bounce) {
+            if (__ldg(&in.kind) != TRB_INST_RECEIVER) {
+                const f3 w = -ray.d;
+                if (dot3(w, first_ng) > 0.0f) // Emitter::radiance (emitter.rs:140-142)
+                    illum = illum + throughput * mk(__ldg(&in.emission[0]), __ldg(&in.emission[1]), __ldg(&in.emission[2]));
+            }
+        }
+        Mat m;
+        load_mat(sc.materials[__ldg(&in.material)], m);
+        Frame fr;
+        make_frame(s, fr);
+        const f3 wo = -ray.d;
+        float l0, l1, b0, b1, q0, q1;
+        rng.two_d(bounce, S_L0, S_L1, S_L_PERM, l0, l1);
+        rng.two_d(bounce, S_B0, S_B1, S_B_PERM, b0, b1);
+        const float lc = rng.one_d(bounce, S_LC, S_LC_PERM), bc = rng.one_d(bounce, S_BC, S_BC_PERM);
+        uint32_t l = f2u(lc * (float)sc.n_lights); // sample_one_light (integrator/mod.rs:108-110), no xN (Q2)
+        if (l > sc.n_lights - 1) l = sc.n_lights - 1;
+        const f3 li = estimate_direct<STATS>(sc, m, fr, wo, __ldg(&sc.lights[l]), l0, l1, b0, b1, bc, ref_shadow, rc, cnt, err);
+        illum = illum + throughput * li;
+
+        rng.two_d(bounce, S_P0, S_P1, S_P_PERM, q0, q1);
+        const float qc = rng.one_d(bounce, S_PC, S_PC_PERM);
+        f3 f, wi; float pdf; uint32_t sampled;
+        bsdf_sample(sc, m, fr, wo, BX_ALL, q0, q1, qc, f, wi, pdf, sampled);
+        if (black(f) || pdf == 0.0f) break;
+        specular_bounce = (sampled & BX_SPECULAR) != 0;
+        throughput = throughput * f * fabsf(dot3(wi, fr.n)) / pdf;
+        if (bounce > sc.min_depth) { // Russian roulette (path.rs:97-104), probability may exceed 1 (Q8)
+            const float lum = 0.2126f * throughput.x + 0.7152f * throughput.y + 0.0722f * throughput.z;
+            const float cont = fmaxf(0.5f, lum);
+            if (unit_f32(rng.draw(S_RR + bounce)) > cont) break;
+            throughput = throughput / cont;
+        }
+        if (bounce == sc.max_depth) break;
+        ray.o = fr.p; ray.d = unit(wi); ray.tmin = 0.001f; ray.tmax = finf(); // ray.child + min_t
+        rc.cont++;
+        if (!scene_trace<STATS>(sc, ray, hit, false, cnt, err)) break;
+        surface_at(sc, ray, hit, s);
+        bounce += 1;
+    }
+    return illum;
+}
+
+// pixel streams of LowDiscrepancy::get_samples / get_samples_1d (ld.rs:33-64)
+struct PixelStreams { uint32_t scr0, scr1, kpos, scrt, ktime, hpix; };
+__device__ __forceinline__ PixelStreams pixel_streams(uint32_t seed, uint32_t pixel) {
+    PixelStreams p;
+    p.hpix = rng_absorb(rng_seed(seed), pixel);
+    const uint32_t hs = rng_absorb(p.hpix, PIXEL_STREAM);
+    p.scr0 = scramble_of(rng_absorb(hs, PX_POS0));
+    p.scr1 = scramble_of(rng_absorb(hs, PX_POS1));
+    p.kpos = rng_absorb(hs, PX_POS_PERM);
+    p.scrt = scramble_of(rng_absorb(hs, PX_TIME));
+    p.ktime = rng_absorb(hs, PX_TIME_PERM);
+    return p;
+}
+
+__device__ __forceinline__ void flush_stats(DStats* st, const RayCounts& rc, const Cnt& cnt, uint32_t samples, bool with_tests) {
+    // warp-aggregate then one atomic per warp per counter
+    unsigned long long v[8] = {samples, rc.primary, rc.shadow, rc.mis, rc.cont, cnt.node, cnt.tri, cnt.inst};
+    const int n = with_tests ? 8 : 5;
+    for (int i = 0; i < n; ++i) {
+        unsigned long long x = v[i];
+        for (int o = 16; o > 0; o >>= 1) x += __shfl_xor_sync(0xffffffffu, x, o);
+        if ((threadIdx.x & 31) == 0 && x) atomicAdd(&reinterpret_cast<unsigned long long*>(st)[i], x);
+    }
+}
+
+// ------------------------------------------------------------------------------------------
+// k_render — persistent CTAs pull 8x8 blocks from the Morton-ordered queue with one atomic, exactly
+// like the reference's worker threads (block_queue.rs:52-59). 128 threads = 64 pixels x 2 sample
+// lanes; a warp is 32 neighbouring pixels at the same sample index (coherent primaries, and the 9x9
+// film footprints of its lanes never collide at the same loop offset). The block's film footprint
+// (8 + 2*fpw + 1)^2 is accumulated in shared memory and flushed once with global atomics.
+// MODE 0: film; MODE 1: write trb_sample records instead (parity).
+// ------------------------------------------------------------------------------------------
+constexpr int RENDER_THREADS = 128;
+constexpr int MAX_TILE = 25; // fpw <= 8
+
+template <bool STATS, int MODE>
+__global__ void __launch_bounds__(RENDER_THREADS) k_render(const __grid_constant__ DScene sc, const __grid_constant__ RenderParams rp, uint32_t flags) {
+    extern __shared__ float4 tile[];           // T*T RGBW
+    __shared__ float s_table[256];
+    __shared__ uint32_t s_item;
+    const int T = 9 + 2 * max(sc.fpw_x, sc.fpw_y);
+    const bool ref_shadow = (flags & 4u) != 0;
+    for (int i = threadIdx.x; i < 256; i += RENDER_THREADS) s_table[i] = sc.filter_table[i];
+    RayCounts rc = {0, 0, 0, 0};
+    Cnt cnt = {0, 0, 0};
+    uint32_t my_samples = 0;
+    const uint32_t pix = threadIdx.x & 63, lane_s = threadIdx.x >> 6;
+    for (;;) {
+        __syncthreads();
+        if (threadIdx.x == 0) s_item = atomicAdd(rp.work_counter, 1u);
+        if (MODE == 0) for (int i = threadIdx.x; i < T * T; i += RENDER_THREADS) tile[i] = make_float4(0.f, 0.f, 0.f, 0.f);
+        __syncthreads();
+        const uint32_t item = s_item;
+        if (item >= rp.n_blocks) break;
+        const uint2 blk = rp.blocks[item];
+        const uint32_t bx = blk.x * 8, by = blk.y * 8;
+        const uint32_t px = bx + (pix & 7), py = by + (pix >> 3); // row-major inside the block (ld.rs:47-52)
+        const uint32_t pixel = py * sc.width + px;
+        const PixelStreams ps = pixel_streams(rp.seed, pixel);
+        // film range of this block (render_target.rs:79-82)
+        const int x_lo = max((int)bx - sc.fpw_x, 0), x_hi = min((int)bx + 8 + sc.fpw_x, (int)sc.width - 1);
+        const int y_lo = max((int)by - sc.fpw_y, 0), y_hi = min((int)by + 8 + sc.fpw_y, (int)sc.height - 1);
+        const int tx0 = (int)bx - sc.fpw_x, ty0 = (int)by - sc.fpw_y;
+        for (uint32_t si = rp.sample_first + lane_s; si < rp.sample_first + rp.sample_count; si += 2) {
+            const uint32_t ip = permute_index(si, rp.spp, ps.kpos);
+            const float sx = ld_vdc(ip, ps.scr0) + (float)px;
+            const float sy = ld_sobol(ip, ps.scr1) + (float)py;
+            const float tm = ld_vdc(permute_index(si, rp.spp, ps.ktime), ps.scrt);
+            Ray ray;
+            camera_ray(sc, sx, sy, tm, ray);
+            my_samples++;
+            f3 c = radiance_of_sample<STATS>(sc, ray, rng_absorb(ps.hpix, si), ref_shadow, rc, cnt, rp.error_flag);
+            c = mk(clampf(c.x, 0.0f, 1.0f), clampf(c.y, 0.0f, 1.0f), clampf(c.z, 0.0f, 1.0f)); // multithreaded.rs:99 (Q12)
+            if (MODE == 1) {
+                trb_sample* out = reinterpret_cast<trb_sample*>(rp.samples_out) + ((size_t)item * 64 + pix) * rp.sample_count + (si - rp.sample_first);
+                out->x = sx; out->y = sy; out->r = c.x; out->g = c.y; out->b = c.z;
+            } else {
+                // RenderTarget::write per sample (render_target.rs:117-148)
+                const float img_x = sx - 0.5f, img_y = sy - 0.5f;
+                // conservative loop bounds around the footprint |d| * inv_w <= w; the exact test is inside
+                const int ry = (int)ceilf(sc.filter_h / sc.filter_inv_h) + 1, rx = (int)ceilf(sc.filter_w / sc.filter_inv_w) + 1;
+                const int iy0 = max(y_lo, (int)py - ry), iy1 = min(y_hi, (int)py + ry + 1);
+                const int ix0 = max(x_lo, (int)px - rx), ix1 = min(x_hi, (int)px + rx + 1);
+                for (int iy = iy0; iy <= iy1; ++iy) {
+                    const float fy = fabsf((float)iy - img_y) * sc.filter_inv_h;
+                    if (fy > sc.filter_h) continue; // sic: normalised distance vs width (A7)
+                    const uint32_t fyi = min(f2u(fy * 16.0f), 15u);
+                    for (int ix = ix0; ix <= ix1; ++ix) {
+                        const float fx = fabsf((float)ix - img_x) * sc.filter_inv_w;
+                        if (fx > sc.filter_w) continue;
+                        const uint32_t fxi = min(f2u(fx * 16.0f), 15u);
+                        const float wgt = s_table[fyi * 16 + fxi];
+                        float* t = reinterpret_cast<float*>(&tile[(iy - ty0) * T + (ix - tx0)]);
+                        atomicAdd(t + 0, wgt * c.x);
+                        atomicAdd(t + 1, wgt * c.y);
+                        atomicAdd(t + 2, wgt * c.z);
+                        atomicAdd(t + 3, wgt);
+                    }
+                }
+            }
+        }
+        if (MODE == 0) {
+            __syncthreads();
+            for (int i = threadIdx.x; i < T * T; i += RENDER_THREADS) {
+                const int ix = tx0 + i % T, iy = ty0 + i / T;
+                if (ix < x_lo || ix > x_hi || iy < y_lo || iy > y_hi) continue;
+                const float4 v = tile[i];
+                if (v.w == 0.0f && v.x == 0.0f && v.y == 0.0f && v.z == 0.0f) continue;
+                float* dst = reinterpret_cast<float*>(rp.film + (size_t)iy * sc.width + ix);
+                atomicAdd(dst + 0, v.x); atomicAdd(dst + 1, v.y); atomicAdd(dst + 2, v.z); atomicAdd(dst + 3, v.w);
+            }
+        }
+    }
+    if (rp.stats) flush_stats(rp.stats, rc, cnt, my_samples, STATS);
+}
+
+// LowDiscrepancy::get_samples + get_samples_1d + Camera::generate_ray only (parity of S2 / C)
+__global__ void k_camera_rays(const __grid_constant__ DScene sc, const __grid_constant__ RenderParams rp, trb_ray* rays, float* xy) {
+    const size_t n = (size_t)rp.n_blocks * 64 * rp.sample_count;
+    for (size_t i = blockIdx.x * (size_t)blockDim.x + threadIdx.x; i < n; i += (size_t)gridDim.x * blockDim.x) {
+        const uint32_t s = (uint32_t)(i % rp.sample_count), pix = (uint32_t)((i / rp.sample_count) % 64), item = (uint32_t)(i / ((size_t)64 * rp.sample_count));
+        const uint2 blk = rp.blocks[item];
+        const uint32_t px = blk.x * 8 + (pix & 7), py = blk.y * 8 + (pix >> 3);
+        const PixelStreams ps = pixel_streams(rp.seed, py * sc.width + px);
+        const uint32_t si = rp.sample_first + s;
+        const uint32_t ip = permute_index(si, rp.spp, ps.kpos);
+        const float sx = ld_vdc(ip, ps.scr0) + (float)px, sy = ld_sobol(ip, ps.scr1) + (float)py;
+        const float tm = ld_vdc(permute_index(si, rp.spp, ps.ktime), ps.scrt);
+        Ray r;
+        camera_ray(sc, sx, sy, tm, r);
+        rays[i].o[0] = r.o.x; rays[i].o[1] = r.o.y; rays[i].o[2] = r.o.z;
+        rays[i].d[0] = r.d.x; rays[i].d[1] = r.d.y; rays[i].d[2] = r.d.z;
+        rays[i].min_t = r.tmin; rays[i].max_t = r.tmax;
+        xy[2 * i] = sx; xy[2 * i + 1] = sy;
+    }
+}
+
+// Scene::intersect over a ray batch (trb_intersect): one ray per thread, grid-stride.
+template <bool STATS>
+__global__ void __launch_bounds__(128) k_intersect(const __grid_constant__ DScene sc, size_t n, const trb_ray* __restrict__ rays, trb_hit* __restrict__ hits,
+                                                    DStats* stats, int* err) {
+    Cnt cnt = {0, 0, 0};
+    RayCounts rc = {0, 0, 0, 0};
+    for (size_t i = blockIdx.x * (size_t)blockDim.x + threadIdx.x; i < n; i += (size_t)gridDim.x * blockDim.x) {
+        const float4 a = __ldg(reinterpret_cast<const float4*>(rays + i)), b = __ldg(reinterpret_cast<const float4*>(rays + i) + 1);
+        Ray r; r.o = mk(a.x, a.y, a.z); r.d = mk(a.w, b.x, b.y); r.tmin = b.z; r.tmax = b.w;
+        HitRec h;
+        const bool hit = scene_trace<STATS>(sc, r, h, false, cnt, err);
+        rc.primary++;
+        uint4 o; o.x = __float_as_uint(r.tmax); o.y = hit ? h.inst : TRB_MISS; o.z = hit ? h.prim : 0u; o.w = 0u;
+        *reinterpret_cast<uint4*>(hits + i) = o;
+    }
+    if (stats) flush_stats(stats, rc, cnt, 0, STATS);
+}
+
+// RenderTarget::get_render (render_target.rs:185-210) + Colorf::to_srgb (color.rs:59-72)
+__global__ void k_srgb8(size_t n, const float4* __restrict__ film, uint8_t* __restrict__ rgb8) {
+    for (size_t i = blockIdx.x * (size_t)blockDim.x + threadIdx.x; i < n; i += (size_t)gridDim.x * blockDim.x) {
+        const float4 c = film[i];
+        uint8_t o[3] = {0, 0, 0};
+        if (c.w > 0.0f) {
+            const float v[3] = {c.x / c.w, c.y / c.w, c.z / c.w};
+            for (int k = 0; k < 3; ++k) {
+                const float x = clampf(v[k], 0.0f, 1.0f);
+                const float s = x <= 0.0031308f ? 12.92f * x : (1.0f + 0.055f) * dpow(x, 1.0f / 2.4f) - 0.055f;
+                const float q = s * 255.0f;
+                o[k] = (uint8_t)f2u(q > 255.0f ? 255.0f : q);
+            }
+        }
+        rgb8[3 * i] = o[0]; rgb8[3 * i + 1] = o[1]; rgb8[3 * i + 2] = o[2];
+    }
+}
+
+} // namespace trb
