@@ -147,14 +147,24 @@ if __name__ == "__main__":
     ap.add_argument("--big", action="store_true")
     ap.add_argument("--no-parity", action="store_true")
     a = ap.parse_args()
+    import traceback
     if not a.no_parity:
-        compare_scene("zoo", SB.scene_materials_zoo(64, 64, 16, SB.synthetic_merl_table()).finish(), spp_pass=8)
-        compare_scene("smallpt", SB.scene_smallpt_like(64, 64, 16).finish(), spp_pass=4)
-        compare_scene("c4_20k", SB.scene_c4(20000, 128, 72, 8).finish(), spp_pass=2)
-        compare_scene("c3", SB.scene_c3(96, 72, 8, subdiv=4).finish(), spp_pass=2)
-    timing(100000)
-    if a.big:
-        timing(1000000)
+        for tag, mk, sp in [("zoo", lambda: SB.scene_materials_zoo(64, 64, 16, SB.synthetic_merl_table()), 8),
+                            ("smallpt", lambda: SB.scene_smallpt_like(64, 64, 16), 4),
+                            ("c4_20k", lambda: SB.scene_c4(20000, 128, 72, 8), 2),
+                            ("c3", lambda: SB.scene_c3(96, 72, 8, subdiv=4), 2)]:
+            try:
+                compare_scene(tag, mk().finish(), spp_pass=sp)
+            except Exception:
+                traceback.print_exc()
+                report(tag + ":exception", False)
+    try:
+        timing(100000)
+        if a.big:
+            timing(1000000)
+    except Exception:
+        traceback.print_exc()
+        report("timing:exception", False)
     os.makedirs("gpurun_out", exist_ok=True)
     json.dump(RES, open("gpurun_out/gpu_check.json", "w"), indent=1, default=str)
     fails = [k for k, v in RES.items() if v is False]

@@ -249,6 +249,7 @@ trb_status check_error_flag(trb_scene* s) {
 extern "C" {
 
 const char* trb_last_error(void) { return g_error.c_str(); }
+void trb_internal_set_error(const char* msg) { g_error = msg ? msg : ""; } // used by trb_loader.cpp
 uint32_t trb_abi_version(void) { return TRB_ABI_VERSION; }
 
 trb_status trb_scene_create(const trb_scene_desc* d, int device, trb_scene** out) {

@@ -30,15 +30,16 @@ struct DMesh {
 
 // geometry::Instance with its world transform at the current frame (static instances: recomposed
 // once per update_frame instead of once per ray — bit-identical, DESIGN.md "X1").
-struct DInstance {
+struct alignas(16) DInstance { // 176 B: the two matrices are read as 16-byte vectors
     float inv[16];  // world -> object, row-major 4x4 (last row kept: transform.rs:150-162 divides by w)
     float mat[16];  // object -> world
     uint32_t kind, shape;
     float p0, p1;
     uint32_t mesh, material;
     float emission[3];
-    uint32_t pad;
+    uint32_t pad[3];
 };
+static_assert(sizeof(DInstance) == 176, "DInstance must stay 16-byte sized");
 
 struct DMaterial {
     uint32_t type;
