@@ -96,64 +96,6 @@ __device__ __forceinline__ bool box_hit(const float4 lo, const float4 hi, f3 o, 
     return tmin < tmax_r && tmax > tmin_r;
 }
 
-// ------------------------------------------------------------------------------------------
-// BVH<Triangle>::intersect (bvh.rs:81-130) + intersect_triangle (mesh.rs:136-170, the accept
-// test only: normals / uv / derivatives are deferred to the final hit).
-// ------------------------------------------------------------------------------------------
-template <bool STATS>
-__device__ __forceinline__ bool blas_trace(const DMesh& m, f3 o, f3 d, float tmin, float& tmax, HitRec& hit, bool any_hit, Cnt& cnt, int* err) {
-    const DNode* __restrict__ nodes = m.nodes;
-    const DTri* __restrict__ tris = m.tris;
-    f3 inv = mk(1.0f / d.x, 1.0f / d.y, 1.0f / d.z);
-    const bool nx = d.x < 0.0f, ny = d.y < 0.0f, nz = d.z < 0.0f;
-    uint32_t stack[64];
-    int sp = 0;
-    uint32_t cur = 0;
-    bool result = false;
-    for (;;) {
-        const float4 lo = __ldg(&nodes[cur].lo), hi = __ldg(&nodes[cur].hi);
-        if (STATS) cnt.node++;
-        if (box_hit(lo, hi, o, inv, nx, ny, nz, tmin, tmax)) {
-            const uint32_t a = __float_as_uint(lo.w), b = __float_as_uint(hi.w);
-            if (b & LEAF_BIT) {
-                const uint32_t n = b & ~LEAF_BIT;
-                for (uint32_t k = a; k < a + n; ++k) {
-                    const float4 v0 = __ldg(&tris[k].v0), q0 = __ldg(&tris[k].e0), q1 = __ldg(&tris[k].e1);
-                    if (STATS) cnt.tri++;
-                    const f3 e0 = mk(q0.x, q0.y, q0.z), e1 = mk(q1.x, q1.y, q1.z);
-                    const f3 s0 = cross3(d, e1);
-                    const float dd = dot3(s0, e0);
-                    if (dd == 0.0f) continue;
-                    const float div = 1.0f / dd;
-                    const f3 dv = o - mk(v0.x, v0.y, v0.z);
-                    const float b1 = dot3(dv, s0) * div;
-                    if (b1 < 0.0f || b1 > 1.0f) continue;
-                    const f3 s1 = cross3(dv, e0);
-                    const float b2 = dot3(d, s1) * div;
-                    if (b2 < 0.0f || b1 + b2 > 1.0f) continue;
-                    const float t = dot3(e1, s1) * div;
-                    if (t < tmin || t > tmax) continue;
-                    tmax = t; // last accepted wins, inclusive compare (Q9)
-                    hit.t = t; hit.prim = __float_as_uint(v0.w); hit.b1 = b1; hit.b2 = b2;
-                    result = true;
-                    if (any_hit) return true;
-                }
-                if (sp == 0) break;
-                cur = stack[--sp];
-            } else {
-                const bool neg = b == 0 ? nx : (b == 1 ? ny : nz);
-                if (sp >= 64) { *err = 1; break; }
-                if (neg) { stack[sp++] = cur + 1; cur = a; }
-                else { stack[sp++] = a; cur = cur + 1; }
-            }
-        } else {
-            if (sp == 0) break;
-            cur = stack[--sp];
-        }
-    }
-    return result;
-}
-
 // solve_quadratic (src/linalg/mod.rs:78-94)
 __device__ __forceinline__ bool solve_quadratic(float a, float b, float c, float& t0, float& t1) {
     float ds = b * b - 4.0f * a * c;
@@ -206,67 +148,132 @@ __device__ __forceinline__ void load_xf(const float* __restrict__ src, float* ds
 }
 
 // ------------------------------------------------------------------------------------------
-// Scene::intersect (scene.rs:148-150): BVH<Instance> traversal, Instance::intersect per leaf entry
-// (receiver.rs:29-43 / emitter.rs:118-137). Returns the accept record; differential geometry is
-// computed once for the final hit by surface_at().
+// Scene::intersect (scene.rs:148-150) = BVH<Instance>::intersect (bvh.rs:81-130) whose leaf callback
+// is Instance::intersect (receiver.rs:29-43 / emitter.rs:118-137), which for meshes runs
+// BVH<Triangle>::intersect with intersect_triangle (mesh.rs:136-170; only the accept test — normals,
+// uv and derivatives are deferred to the final hit, surface_at()).
+//
+// GPU shape: ONE structured loop for both levels so a warp never serialises on "who is inside a
+// mesh": the stack holds TLAS nodes, pending instances of a TLAS leaf (pushed in reverse so they
+// pop in the reference's order) and, below a mesh's nodes, a RETURN marker that restores the world
+// ray. Visit order, compares and the shrinking max_t are exactly the reference's, so hit indices,
+// t and the test counters are bit-identical to the oracle. No early `return` inside the loop: every
+// divergent branch reconverges at the loop head.
 // ------------------------------------------------------------------------------------------
+constexpr uint32_t ST_SPECIAL = 0x80000000u; // level 0: ST_SPECIAL | slot in tlas_order; level 1: ST_RETURN
+constexpr uint32_t ST_RETURN = 0xfffffffeu;
+constexpr uint32_t ST_DONE = 0xffffffffu;
+constexpr int STACK_DEPTH = 96;
+
 template <bool STATS>
 __device__ __noinline__ bool scene_trace(const DScene& sc, Ray& ray, HitRec& hit, bool any_hit, Cnt& cnt, int* err) {
+    const f3 wo = ray.o, wd = ray.d;
+    const f3 winv = mk(1.0f / wd.x, 1.0f / wd.y, 1.0f / wd.z); // bvh.rs:84
+    f3 o = wo, d = wd, inv = winv;
+    bool nx = d.x < 0.0f, ny = d.y < 0.0f, nz = d.z < 0.0f;   // bvh.rs:85
     const DNode* __restrict__ nodes = sc.tlas;
-    const f3 o = ray.o, d = ray.d;
-    const f3 inv = mk(1.0f / d.x, 1.0f / d.y, 1.0f / d.z);
-    const bool nx = d.x < 0.0f, ny = d.y < 0.0f, nz = d.z < 0.0f;
-    uint32_t stack[64];
+    const DTri* __restrict__ tris = nullptr;
+    uint32_t level_inst = TRB_MISS; // instance whose mesh is being traversed, TRB_MISS at the top level
+    const float tmin = ray.tmin;
+    float tmax = ray.tmax;
+    uint32_t stack[STACK_DEPTH];
     int sp = 0;
     uint32_t cur = 0;
-    bool result = false;
-    hit.inst = TRB_MISS; hit.prim = 0; hit.b1 = 0.0f; hit.b2 = 0.0f; hit.t = ray.tmax;
-    for (;;) {
-        const float4 lo = __ldg(&nodes[cur].lo), hi = __ldg(&nodes[cur].hi);
-        if (STATS) cnt.node++;
-        if (box_hit(lo, hi, o, inv, nx, ny, nz, ray.tmin, ray.tmax)) {
+    bool found = false;
+    hit.inst = TRB_MISS; hit.prim = 0; hit.b1 = 0.0f; hit.b2 = 0.0f;
+    while (cur != ST_DONE) {
+        uint32_t next;
+        if (!(cur & ST_SPECIAL)) {
+            // ---- visit a node of the current level ----
+            const float4 lo = __ldg(&nodes[cur].lo), hi = __ldg(&nodes[cur].hi);
+            if (STATS) cnt.node++;
+            const bool bh = box_hit(lo, hi, o, inv, nx, ny, nz, tmin, tmax);
             const uint32_t a = __float_as_uint(lo.w), b = __float_as_uint(hi.w);
-            if (b & LEAF_BIT) {
-                const uint32_t n = b & ~LEAF_BIT;
-                for (uint32_t k = a; k < a + n; ++k) {
-                    const uint32_t ii = __ldg(&sc.tlas_order[k]);
-                    const DInstance& in = sc.instances[ii];
-                    if (STATS) cnt.inst++;
-                    const uint32_t kind = __ldg(&in.kind);
-                    if (kind == TRB_INST_EMITTER_POINT) continue; // emitter.rs:119-120
-                    float m[16];
-                    load_xf(in.inv, m);
-                    const f3 lo_ = xf_point(m, o), ld_ = xf_vector(m, d); // inv_mul_ray: direction not renormalised
-                    const uint32_t shape = __ldg(&in.shape);
-                    const float p0 = __ldg(&in.p0), p1 = __ldg(&in.p1);
-                    float tmax = ray.tmax;
-                    bool h;
-                    HitRec local = hit;
-                    if (shape == TRB_SHAPE_MESH) h = blas_trace<STATS>(sc.meshes[__ldg(&in.mesh)], lo_, ld_, ray.tmin, tmax, local, any_hit, cnt, err);
-                    else if (shape == TRB_SHAPE_SPHERE) { h = sphere_t(p0, lo_, ld_, ray.tmin, tmax); local.prim = 0; }
-                    else if (shape == TRB_SHAPE_DISK) { h = disk_t(p0, p1, lo_, ld_, ray.tmin, tmax); local.prim = 0; }
-                    else { h = rect_t(p0, p1, lo_, ld_, ray.tmin, tmax); local.prim = 0; }
-                    if (h) {
-                        ray.tmax = tmax; // receiver.rs:36
-                        hit = local; hit.t = tmax; hit.inst = ii;
-                        result = true;
-                        if (any_hit) return true;
+            if (bh && !(b & LEAF_BIT)) {
+                // interior: descend to the near child by the sign of d[axis], push the other (bvh.rs:105-119)
+                const bool neg = b == 0 ? nx : (b == 1 ? ny : nz);
+                if (sp >= STACK_DEPTH - 6) { *err = 1; sp = 0; next = ST_DONE; }
+                else { stack[sp++] = neg ? cur + 1 : a; next = neg ? a : cur + 1; }
+            } else {
+                if (bh) {
+                    const uint32_t n = b & ~LEAF_BIT;
+                    if (level_inst == TRB_MISS) {
+                        for (uint32_t k = a + n; k-- > a;) stack[sp++] = ST_SPECIAL | k; // pops as a, a+1, ...
+                    } else {
+                        for (uint32_t k = a; k < a + n; ++k) {
+                            const float4 v0 = __ldg(&tris[k].v0), q0 = __ldg(&tris[k].e0), q1 = __ldg(&tris[k].e1);
+                            if (STATS) cnt.tri++;
+                            const f3 e0 = mk(q0.x, q0.y, q0.z), e1 = mk(q1.x, q1.y, q1.z);
+                            const f3 s0 = cross3(d, e1);
+                            const float dd = dot3(s0, e0);
+                            const float div = 1.0f / dd;
+                            const f3 dv = o - mk(v0.x, v0.y, v0.z);
+                            const float b1 = dot3(dv, s0) * div;
+                            const f3 s1 = cross3(dv, e0);
+                            const float b2 = dot3(d, s1) * div;
+                            const float t = dot3(e1, s1) * div;
+                            // mesh.rs:142-168: d == 0 -> miss; b1 in [0,1]; b2 >= 0 and b1+b2 <= 1; t in [min_t, max_t]
+                            const bool ok = dd != 0.0f && !(b1 < 0.0f || b1 > 1.0f) && !(b2 < 0.0f || b1 + b2 > 1.0f) && !(t < tmin || t > tmax);
+                            if (ok) { // last accepted wins, inclusive compare (Q9)
+                                tmax = t;
+                                hit.prim = __float_as_uint(v0.w); hit.b1 = b1; hit.b2 = b2; hit.inst = level_inst;
+                                found = true;
+                                if (any_hit) sp = 0;
+                            }
+                        }
                     }
                 }
-                if (sp == 0) break;
-                cur = stack[--sp];
-            } else {
-                const bool neg = b == 0 ? nx : (b == 1 ? ny : nz);
-                if (sp >= 64) { *err = 1; break; }
-                if (neg) { stack[sp++] = cur + 1; cur = a; }
-                else { stack[sp++] = a; cur = cur + 1; }
+                next = sp > 0 ? stack[--sp] : ST_DONE;
             }
+        } else if (cur == ST_RETURN) {
+            // ---- leave the mesh: back to the world ray ----
+            o = wo; d = wd; inv = winv;
+            nx = d.x < 0.0f; ny = d.y < 0.0f; nz = d.z < 0.0f;
+            nodes = sc.tlas; level_inst = TRB_MISS;
+            next = sp > 0 ? stack[--sp] : ST_DONE;
         } else {
-            if (sp == 0) break;
-            cur = stack[--sp];
+            // ---- Instance::intersect for one entry of a TLAS leaf ----
+            const uint32_t ii = __ldg(&sc.tlas_order[cur & ~ST_SPECIAL]);
+            const DInstance& in = sc.instances[ii];
+            if (STATS) cnt.inst++;
+            const uint32_t kind = __ldg(&in.kind), shape = __ldg(&in.shape);
+            next = ST_DONE;
+            bool enter = false;
+            if (kind != TRB_INST_EMITTER_POINT) { // point lights never intersect (emitter.rs:119-120)
+                float m[16];
+                load_xf(in.inv, m);
+                const f3 lo_ = xf_point(m, wo), ld_ = xf_vector(m, wd); // inv_mul_ray: direction not renormalised
+                if (shape == TRB_SHAPE_MESH) {
+                    const DMesh& me = sc.meshes[__ldg(&in.mesh)];
+                    o = lo_; d = ld_;
+                    inv = mk(1.0f / d.x, 1.0f / d.y, 1.0f / d.z);
+                    nx = d.x < 0.0f; ny = d.y < 0.0f; nz = d.z < 0.0f;
+                    nodes = me.nodes; tris = me.tris; level_inst = ii;
+                    stack[sp++] = ST_RETURN;
+                    next = 0; // root of the mesh BVH
+                    enter = true;
+                } else {
+                    const float p0 = __ldg(&in.p0), p1 = __ldg(&in.p1);
+                    float t = tmax;
+                    bool h;
+                    if (shape == TRB_SHAPE_SPHERE) h = sphere_t(p0, lo_, ld_, tmin, t);
+                    else if (shape == TRB_SHAPE_DISK) h = disk_t(p0, p1, lo_, ld_, tmin, t);
+                    else h = rect_t(p0, p1, lo_, ld_, tmin, t);
+                    if (h) {
+                        tmax = t; // receiver.rs:36
+                        hit.inst = ii; hit.prim = 0; hit.b1 = 0.0f; hit.b2 = 0.0f;
+                        found = true;
+                        if (any_hit) sp = 0;
+                    }
+                }
+            }
+            if (!enter) next = sp > 0 ? stack[--sp] : ST_DONE;
         }
+        cur = next;
     }
-    return result;
+    ray.tmax = tmax;
+    hit.t = tmax;
+    return found;
 }
 
 // ------------------------------------------------------------------------------------------
