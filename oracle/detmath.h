@@ -186,7 +186,8 @@ static inline uint32_t dm_permute(uint32_t i, uint32_t l, uint32_t p) {
         i &= w;
         i ^= i >> 5;
     } while (i >= l);
-    return (i + p) % l;
+    i += p % l; /* rotation by the key without 32-bit wrap-around (i, p % l < l) */
+    return i >= l ? i - l : i;
 }
 
 /* RNG stream addressing shared by oracle and GPU (DESIGN.md "RNG"):

@@ -533,3 +533,20 @@ size_t orc_partition_even(uint32_t* v, size_t n) {
 }
 
 } // extern "C"
+
+extern "C" {
+/* linalg::cross / dot (src/linalg/mod.rs:38-45) for the restated reference unit tests */
+void orc_cross_dot(const float* a, const float* b, float* out4) {
+    V3 c = cross(V3(a[0], a[1], a[2]), V3(b[0], b[1], b[2]));
+    out4[0] = c.x; out4[1] = c.y; out4[2] = c.z; out4[3] = dot(V3(a[0], a[1], a[2]), V3(b[0], b[1], b[2]));
+}
+/* Transform * {Point, Vector, Normal} with a keyframe's transform (transform.rs:199-242) */
+void orc_xf_apply(const trb_keyframe* kf, const float* v, float* out9) {
+    Keyframe k; k.translation = V3(kf->translation[0], kf->translation[1], kf->translation[2]);
+    k.rotation = Quat{V3(kf->rotation[0], kf->rotation[1], kf->rotation[2]), kf->rotation[3]};
+    k.scaling = V3(kf->scaling[0], kf->scaling[1], kf->scaling[2]);
+    Transform t = k.transform();
+    V3 p = t.point(V3(v[0], v[1], v[2])), w = t.vector(V3(v[0], v[1], v[2])), n = t.normal(V3(v[0], v[1], v[2]));
+    out9[0] = p.x; out9[1] = p.y; out9[2] = p.z; out9[3] = w.x; out9[4] = w.y; out9[5] = w.z; out9[6] = n.x; out9[7] = n.y; out9[8] = n.z;
+}
+}

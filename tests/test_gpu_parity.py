@@ -1,0 +1,169 @@
+"""Parity tests proper (run on the B200 box): the CUDA path, called through the C ABI, against the oracle and the
+committed golden vectors. Bars: ray-scene hit records, traversal counters, camera rays, LD samples and
+per-camera-sample radiance BIT-EXACT; the film within 1e-5 RMSE (its accumulation order is atomic-dependent)."""
+import ctypes as C
+import os
+import sys
+
+import numpy as np
+import pytest
+
+from tray_rust_b200 import _ffi as F, api, scenebuild as SB
+
+pytestmark = pytest.mark.gpu
+HERE = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, os.path.join(HERE, "golden"))
+import make_golden  # noqa: E402
+
+GOLD = make_golden.golden_scenes()
+KEYS = ["camera_samples", "rays_primary", "rays_shadow", "rays_mis", "rays_continuation", "node_tests", "tri_tests", "inst_tests"]
+
+
+def both(desc):
+    g, o = api.Scene(desc), api.OracleScene(desc)
+    g.update_frame(0, 0.0, 0.0); o.update_frame(0, 0.0, 0.0)
+    return g, o
+
+
+@pytest.mark.parametrize("name", sorted(GOLD))
+def test_gpu_matches_golden_vectors(name):
+    mk, kw = GOLD[name]
+    gold = np.load(os.path.join(HERE, "golden", name + ".npz"))
+    g = api.Scene(mk())
+    g.update_frame(0, 0.0, 0.0)
+    rays, xy = g.camera_rays(**kw)
+    assert rays.tobytes() == gold["rays"].tobytes() and xy.tobytes() == gold["xy"].tobytes()
+    hits, _ = g.intersect(gold["rays"])
+    assert hits.tobytes() == gold["hits"].tobytes()
+    s, st = g.render_samples(flags=F.RENDER_STATS | F.RENDER_REFERENCE_SHADOW, **kw)
+    assert s.tobytes() == gold["samples"].tobytes()
+    assert [st.rays_primary, st.rays_shadow, st.rays_mis, st.rays_continuation, st.node_tests, st.tri_tests, st.inst_tests] == gold["counters"].tolist()
+    film, _ = g.render(flags=F.RENDER_NO_UPDATE, **kw)
+    img_g = film[..., :3] / np.maximum(film[..., 3:], 1e-6); img_o = gold["film"][..., :3] / np.maximum(gold["film"][..., 3:], 1e-6)
+    assert np.sqrt(np.mean((img_g - img_o) ** 2)) < 1e-5 and np.allclose(film, gold["film"], rtol=1e-4, atol=1e-5)
+
+
+SCENES = {
+    "zoo": lambda: SB.scene_materials_zoo(64, 64, 16, SB.synthetic_merl_table()),
+    "smallpt": lambda: SB.scene_smallpt_like(64, 64, 16),
+    "c4_20k": lambda: SB.scene_c4(20000, 128, 72, 8),
+    "c3": lambda: SB.scene_c3(96, 72, 8, subdiv=4),
+}
+
+
+@pytest.mark.parametrize("name", sorted(SCENES))
+def test_gpu_vs_oracle(name):
+    desc = SCENES[name]().finish()
+    g, o = both(desc)
+    gn, go = g.bvh(-1); on, oo = o.bvh(-1)
+    assert gn.tobytes() == on.tobytes() and np.array_equal(go, oo)                       # BVH<Instance>
+    for m in range(desc.n_meshes):
+        a, b = g.bvh(m), o.bvh(m)
+        assert a[0].tobytes() == b[0].tobytes() and np.array_equal(a[1], b[1])           # BVH<Triangle>
+    for i in range(desc.n_instances):
+        for x, y in zip(g.transform(i), o.transform(i)):
+            assert np.array_equal(api.bits(x), api.bits(y))
+    assert np.array_equal(api.bits(g.filter_table()), api.bits(o.filter_table()))
+    assert np.array_equal(g.block_list(), o.block_list()) and np.array_equal(g.block_list(3, 5), o.block_list(3, 5))
+    kw = dict(sample_first=0, sample_count=4, seed=7)
+    gr, gxy = g.camera_rays(**kw); orr, oxy = o.camera_rays(**kw)
+    assert gr.tobytes() == orr.tobytes() and gxy.tobytes() == oxy.tobytes()
+    gh, gs = g.intersect(orr); oh, os_ = o.intersect(orr)
+    assert gh.tobytes() == oh.tobytes()
+    assert (gs.node_tests, gs.tri_tests, gs.inst_tests) == (os_.node_tests, os_.tri_tests, os_.inst_tests)
+    # incoherent secondary-like rays from the hit points
+    rng = np.random.default_rng(3)
+    hit = np.nonzero(oh["inst"] != F.MISS)[0]
+    sel = rng.choice(hit, size=min(20000, len(hit)), replace=False)
+    rays = np.zeros(len(sel), F.RAY_DTYPE)
+    rays["o"] = orr["o"][sel] + orr["d"][sel] * oh["t"][sel, None]
+    d = rng.normal(size=(len(sel), 3)).astype(np.float32)
+    rays["d"] = d / np.linalg.norm(d, axis=1, keepdims=True); rays["min_t"] = 0.001; rays["max_t"] = np.inf
+    assert g.intersect(rays)[0].tobytes() == o.intersect(rays)[0].tobytes()
+    # whole paths, bit-exact, with the reference's closest-hit shadow rays so the counters are comparable
+    gsamp, gst = g.render_samples(flags=F.RENDER_STATS | F.RENDER_REFERENCE_SHADOW, **kw)
+    osamp, ost = o.render_samples(**kw)
+    assert gsamp.tobytes() == osamp.tobytes()
+    assert [getattr(gst, k) for k in KEYS] == [getattr(ost, k) for k in KEYS]
+    # default mode (shadow rays stop at the first accepted hit): identical radiance, fewer tests
+    gsamp2, gst2 = g.render_samples(flags=F.RENDER_STATS, **kw)
+    assert gsamp2.tobytes() == gsamp.tobytes() and gst2.node_tests <= gst.node_tests
+    # film (splat order is atomic-dependent): tolerance
+    gf, _ = g.render(**kw); of, _ = o.render(**kw)
+    ig = gf[..., :3] / np.maximum(gf[..., 3:], 1e-6); io = of[..., :3] / np.maximum(of[..., 3:], 1e-6)
+    assert np.isfinite(gf).all() and np.sqrt(np.mean((ig - io) ** 2)) < 1e-5
+    assert np.array_equal(g.to_srgb8(of), o.to_srgb8(of))
+
+
+def test_json_scenes_through_the_loader():
+    """C1 / C2 inputs through trb_scene_load_json-equivalent path (reference-shaped host API)."""
+    from tray_rust_b200 import exec as X
+    for fn, dims in (("c1_cornell_box.json", (40, 32, 8)), ("c2_smallpt.json", (32, 32, 8))):
+        path = os.path.join(HERE, "golden", "scenes", fn)
+        scene, rt, spp, fi = X.Scene.load_file(path, 0, *dims)
+        assert rt.dimensions() == dims[:2] and spp == dims[2] and fi.frames == 1
+        cfg = X.Config(spp=spp, frame_info=fi, seed=9)
+        st = X.B200().render(scene, rt, cfg)
+        lib = F.load_trb()
+        d = C.POINTER(F.SceneDesc)()
+        assert lib.trb_desc_load_json(path.encode(), *dims, C.byref(d)) == 0
+        o = api.OracleScene(d.contents)
+        of, ost = o.render(seed=9)
+        ig = rt.pixels[..., :3] / np.maximum(rt.pixels[..., 3:], 1e-6); io = of[..., :3] / np.maximum(of[..., 3:], 1e-6)
+        assert np.sqrt(np.mean((ig - io) ** 2)) < 1e-5
+        assert st.rays_primary == ost.rays_primary and st.rays_continuation == ost.rays_continuation
+        # two passes accumulate to the same film (Exec mirror with samples_per_pass)
+        rt2 = X.RenderTarget(*dims[:2])
+        X.B200(samples_per_pass=spp // 2).render(scene, rt2, cfg)
+        assert np.allclose(rt2.pixels, rt.pixels, rtol=1e-4, atol=1e-5)
+        assert np.array_equal(X.get_render(scene, rt), o.to_srgb8(rt.pixels))
+        lib.trb_desc_free(d); scene.close()
+
+
+def test_edge_cases():
+    desc = SB.scene_smallpt_like(16, 16, 4).finish()
+    g, o = both(desc)
+    assert len(g.intersect(np.zeros(0, F.RAY_DTYPE))[0]) == 0                              # empty batch
+    rays = np.zeros(6, F.RAY_DTYPE)
+    rays["o"] = [0, 12, -60]; rays["d"] = [[0, 0, 1], [0, 0, -1], [0, 0, 0], [np.nan, 0, 1], [0, 1e-30, 1], [1e30, 0, 1]]
+    rays["max_t"] = [np.inf, np.inf, np.inf, np.inf, np.inf, 1e-3]
+    assert g.intersect(rays)[0].tobytes() == o.intersect(rays)[0].tobytes()               # zero / NaN / denormal directions
+    with pytest.raises(api.TrbError):
+        g.render(sample_first=3, sample_count=4)                                           # beyond spp
+    film, st = g.render(block_start=10 ** 6, block_count=5)                                # "This block queue is empty!"
+    assert st.camera_samples == 0 and not film.any()
+    f1, s1 = g.render(block_start=1, block_count=2, seed=5); f2, _ = o.render(block_start=1, block_count=2, seed=5)
+    assert s1.camera_samples == 2 * 64 * 4 and np.allclose(f1, f2, rtol=1e-4, atol=1e-5)
+    fresh = api.Scene(desc)
+    with pytest.raises(api.TrbError):
+        fresh.render_samples()                                                             # update_frame not called (scene.rs:179)
+
+
+def test_full_size_properties_c4():
+    """BASELINE-size workload (1M triangles, 1920x1080): size-independent properties instead of an oracle run."""
+    g = api.Scene(SB.scene_c4(1_000_000, 1920, 1080, 4096).finish())
+    g.update_frame(0, 0.0, 0.0)
+    nb = g.n_blocks()
+    assert nb == 32400
+    # determinism: a camera sample is a pure function of (seed, pixel, sample index), whatever the launch shape
+    a, _ = g.render_samples(block_start=500, block_count=40, sample_first=8, sample_count=2, seed=3)
+    b, _ = g.render_samples(block_start=500, block_count=40, sample_first=8, sample_count=2, seed=3)
+    c, _ = g.render_samples(block_start=520, block_count=10, sample_first=9, sample_count=1, seed=3)
+    assert a.tobytes() == b.tobytes()
+    assert c.tobytes() == a.reshape(40, 64, 2)[20:30, :, 1].reshape(-1).tobytes()
+    assert (a["r"] >= 0).all() and (a["r"] <= 1).all() and np.isfinite(a["r"]).all()       # per-sample clamp
+    # tile sharding is additive: blocks [0,n/2) + [n/2,n) == all blocks
+    full, sf = g.render(sample_first=0, sample_count=1, seed=3)
+    half, s0 = g.render(block_start=0, block_count=nb // 2, sample_first=0, sample_count=1, seed=3)
+    _, s1 = g.render(half, block_start=nb // 2, block_count=nb - nb // 2, sample_first=0, sample_count=1, seed=3)
+    assert np.allclose(full, half, rtol=1e-4, atol=1e-5)
+    assert s0.rays_total() + s1.rays_total() == sf.rays_total() and sf.camera_samples == 1920 * 1080
+    # every pixel got weight, weights are positive in the interior (Mitchell lobes sum > 0)
+    assert (full[8:-8, 8:-8, 3] > 0).all()
+    # hits: t > 0, triangle ids in range, and closest-hit == the minimum over a second, any-order query of the same ray
+    rays, _ = g.camera_rays(block_start=1000, block_count=50, sample_first=0, sample_count=1, seed=3)
+    h, st = g.intersect(rays)
+    hit = h["inst"] != F.MISS
+    assert (h["t"][hit] > 0).all() and (h["prim"][hit] < 1_000_000).all() and st.node_tests > 0
+    short = rays.copy(); short["max_t"] = np.where(hit, h["t"] * 0.999, 1.0)
+    assert (g.intersect(short)[0]["inst"] == F.MISS).all()                                 # nothing closer than the closest hit

@@ -1,0 +1,168 @@
+"""Analytic pins for the oracle's shading code (the reference holds no vectors for it):
+BSDF reciprocity/energy/pdf consistency, a closed-form direct-lighting integral, film filter properties,
+detmath-vs-glibc neutrality."""
+import ctypes as C
+import math
+
+import numpy as np
+
+from tray_rust_b200 import _ffi as F, api, scenebuild as SB
+
+ALL = 31
+NON_SPECULAR = 4 | 8 | 1 | 2
+
+
+def mat(t, c0=(0, 0, 0), c1=(0, 0, 0), roughness=0.0, eta=1.0):
+    m = F.Material()
+    m.type = t; m.c0[:] = c0; m.c1[:] = c1; m.roughness = roughness; m.eta = eta; m.merl = 0
+    return m
+
+
+def probe(oracle, m, wo, wi, flags=ALL, u=(0.3, 0.6, 0.1), merl=None):
+    out = np.zeros(12, np.float32)
+    wo = np.asarray(wo, np.float32); wi = np.asarray(wi, np.float32); u = np.asarray(u, np.float32)
+    oracle.orc_bsdf_probe(C.byref(m), F.ptr(merl) if merl is not None else None, F.ptr(wo), F.ptr(wi), flags, F.ptr(u), F.ptr(out))
+    return dict(f=out[0:3], pdf=out[3], fs=out[4:7], wi=out[7:10], pdf_s=out[10], type=int(out[11]))
+
+
+def unit(v):
+    v = np.asarray(v, np.float64)
+    return (v / np.linalg.norm(v)).astype(np.float32)
+
+
+def test_lambertian_is_albedo_over_pi(oracle):  # lambertian.rs:32-34
+    m = mat(F.MAT_MATTE, (0.2, 0.5, 0.8), roughness=0.0)
+    r = probe(oracle, m, unit((0.3, 0.1, 1)), unit((-0.5, 0.2, 0.7)))
+    assert np.allclose(r["f"], np.array([0.2, 0.5, 0.8]) / math.pi, rtol=1e-6)
+    assert abs(r["pdf"] - unit((-0.5, 0.2, 0.7))[2] / math.pi) < 1e-6
+    assert np.all(probe(oracle, m, unit((0.3, 0.1, 1)), unit((0.1, 0.1, -1)))["f"] == 0)  # below the surface: no BRDF lobe
+
+
+def test_reciprocity(oracle):
+    rng = np.random.default_rng(0)
+    mats = [mat(F.MAT_MATTE, (0.5, 0.5, 0.5), roughness=20.0), mat(F.MAT_PLASTIC, (0.5, 0.2, 0.2), (0.6, 0.6, 0.6), roughness=0.3),
+            mat(F.MAT_METAL, (0.15, 0.11, 0.13), (4.8, 3.1, 2.1), roughness=0.2)]
+    for m in mats:
+        for _ in range(50):
+            a = unit(np.abs(rng.normal(size=3)) + [0, 0, 0.1]); b = unit(rng.normal(size=3) * [1, 1, 0] + [0, 0, abs(rng.normal()) + 0.1])
+            f1, f2 = probe(oracle, m, a, b)["f"], probe(oracle, m, b, a)["f"]
+            assert np.allclose(f1, f2, rtol=2e-4, atol=1e-7)
+
+
+def test_sampling_consistency_and_energy(oracle):
+    """sample() must return exactly eval()/pdf() of its own direction, and E[f cos / pdf] <= 1 (+MC noise)."""
+    rng = np.random.default_rng(1)
+    mats = [mat(F.MAT_MATTE, (0.9, 0.9, 0.9), roughness=0.0), mat(F.MAT_MATTE, (0.9, 0.9, 0.9), roughness=30.0),
+            mat(F.MAT_PLASTIC, (0.5, 0.5, 0.5), (0.4, 0.4, 0.4), roughness=0.2), mat(F.MAT_METAL, (0.2, 0.9, 1.1), (3.9, 2.4, 2.2), roughness=0.3),
+            mat(F.MAT_ROUGH_GLASS, (1, 1, 1), (1, 1, 1), roughness=0.3, eta=1.5)]
+    wo = unit((0.4, -0.2, 0.8))
+    for m in mats:
+        acc, n = np.zeros(3), 4000
+        for _ in range(n):
+            u = rng.uniform(0, 0.999999, 3)
+            r = probe(oracle, m, wo, wo, ALL, u)
+            if r["pdf_s"] <= 0:
+                continue
+            again = probe(oracle, m, wo, r["wi"], ALL, u)
+            # 1-ulp slack: sample() evaluates a single lobe in shading space, eval()/pdf() re-project from world space
+            assert np.allclose(again["f"], r["fs"], rtol=1e-4, atol=1e-7) and np.isclose(again["pdf"], r["pdf_s"], rtol=1e-4)
+            acc += r["fs"].astype(np.float64) * abs(r["wi"][2]) / r["pdf_s"]
+        # reflective models cannot create energy; the Walter BTDF carries the eta^2 radiance scaling, so it may
+        bound = 2.5 if m.type == F.MAT_ROUGH_GLASS else 1.08
+        assert (acc / n < bound).all(), (m.type, acc / n)
+        assert (acc / n > 0.05).all()
+
+
+def test_specular_glass(oracle):  # specular_reflection.rs / specular_transmission.rs / fresnel.rs
+    m = mat(F.MAT_GLASS, (1, 1, 1), (1, 1, 1), eta=1.5)
+    wo = unit((0, 0, 1))
+    r = probe(oracle, m, wo, wo, ALL, (0.5, 0.5, 0.1))  # first lobe = reflection
+    assert r["type"] == 16 | 1 and np.allclose(r["wi"], [0, 0, 1]) and r["pdf_s"] == 1.0
+    assert np.allclose(r["fs"], 0.04, atol=1e-6)  # ((1.5-1)/(1.5+1))^2 at normal incidence
+    t = probe(oracle, m, wo, wo, ALL, (0.5, 0.5, 0.9))  # second lobe = transmission
+    assert t["type"] == 16 | 2 and np.allclose(t["wi"], [0, 0, -1]) and np.allclose(t["fs"], 0.96, atol=1e-6)
+    assert np.all(probe(oracle, m, wo, unit((0.1, 0, 1)), NON_SPECULAR)["f"] == 0)  # eval of specular lobes is 0
+    # total internal reflection from inside
+    inside = unit((0.9, 0, -0.3))
+    assert probe(oracle, m, inside, inside, 16 | 2, (0.5, 0.5, 0.5))["pdf_s"] == 0.0
+
+
+def test_merl_lookup_indexing(oracle):  # bxdf/merl.rs:47-82
+    table = np.zeros(F.MERL_TABLE_FLOATS, np.float32)
+    table.reshape(90, 90, 180, 3)[0, 0, 0] = (1, 2, 3)       # theta_h = 0, theta_d = 0 -> wo == wi == n
+    table.reshape(90, 90, 180, 3)[0, 45, :] = (4, 5, 6)      # wo, wi mirrored at 45 degrees about n
+    m = mat(F.MAT_MERL)
+    r = probe(oracle, m, (0, 0, 1), (0, 0, 1), ALL, merl=table)
+    assert r["f"].tolist() == [1, 2, 3]
+    a = unit((math.sin(math.pi / 4) * 1.0001, 0, math.cos(math.pi / 4)))
+    b = a * np.array([-1, 1, 1], np.float32)
+    assert probe(oracle, m, a, b, ALL, merl=table)["f"].tolist() == [4, 5, 6]
+
+
+def direct_lighting_scene(spp):
+    """Lambertian floor lit by a rectangle light, max_depth 0: the estimator is sample_one_light only."""
+    b = SB.SceneBuilder(8, 8, spp, min_depth=0, max_depth=0)
+    white = b.add_material(F.MAT_MATTE, (0.8, 0.8, 0.8), roughness=0.0)
+    b.receiver(F.SHAPE_RECT, white, [SB.trs(q=SB.quat_axis_angle((1, 0, 0), -90), s=50)], p0=2, p1=2)  # floor y=0, normal +y
+    b.area_light(F.SHAPE_RECT, white, [SB.trs(t=(0, 4, 0), q=SB.quat_axis_angle((1, 0, 0), 90))], (0.5, 0.5, 0.5), p0=2, p1=2)  # facing down
+    b.add_camera([SB.trs(t=(0, 3, -6), q=SB.quat_axis_angle((1, 0, 0), 26.565))], fov=4.0)  # looks at the origin
+    return b
+
+
+def test_direct_lighting_matches_closed_form(oracle):
+    """E = rho/pi * L * integral over the light of cos cos' / r^2 dA, evaluated numerically in float64."""
+    spp = 256
+    o = api.OracleScene(direct_lighting_scene(spp).finish())
+    o.update_frame(0, 0.0, 0.0)
+    s, st = o.render_samples(seed=5)
+    rays, _ = o.camera_rays(seed=5)
+    hits, _ = o.intersect(rays)
+    assert (hits["inst"] == 0).all()
+    p = rays["o"] + rays["d"] * hits["t"][:, None]
+    assert np.abs(p[:, 1]).max() < 1e-3 and np.abs(p[:, [0, 2]]).max() < 0.7  # all samples near the origin on the floor
+    g = (np.arange(400) + 0.5) / 400 * 2 - 1
+    gx, gz = np.meshgrid(g, g)
+    px, pz = float(p[:, 0].mean()), float(p[:, 2].mean())
+    dx, dz, dy = gx - px, gz - pz, 4.0
+    r2 = dx * dx + dz * dz + dy * dy
+    integral = np.sum((dy / np.sqrt(r2)) ** 2 / r2) * (2.0 / 400) ** 2
+    expect = 0.8 / math.pi * 0.5 * integral
+    got = float(s["r"].mean())
+    assert abs(got - expect) < 0.03 * expect, (got, expect)
+    assert st.rays_continuation == 0 and st.rays_shadow == len(s)
+
+
+def test_libm_choice_is_statistically_neutral(oracle, oracle_sys):
+    """detmath and glibc builds of the oracle agree at the level of Monte-Carlo noise."""
+    d = SB.scene_smallpt_like(16, 16, 64).finish()
+    a, b = api.OracleScene(d, "det"), api.OracleScene(d, "sys")
+    for o in (a, b):
+        o.update_frame(0, 0.0, 0.0)
+    sa, _ = a.render_samples(seed=2)
+    sb, _ = b.render_samples(seed=2)
+    assert np.array_equal(sa["x"], sb["x"])  # no transcendental before the first hit
+    same = np.mean((sa["r"] == sb["r"]) & (sa["g"] == sb["g"]))
+    close = np.mean(np.abs(sa["r"] - sb["r"]) < 1e-4)
+    assert close > 0.9, (same, close)          # ulp-level differences, a few paths branch differently
+    assert abs(sa["r"].mean() - sb["r"].mean()) < 0.01
+
+
+def test_film_filter_properties(oracle):
+    o = api.OracleScene(SB.scene_smallpt_like(16, 16, 1).finish())
+    t = o.filter_table()
+    assert t.shape == (16, 16) and np.allclose(t, t.T) and t[0, 0] > 0.75  # Mitchell b=c=1/3 at the centre ~ (8/9)^2
+    assert (np.diff(t[0]) <= 1e-7).all() or t[0].min() < 0  # decreasing into the negative lobe
+    assert t.min() < 0  # negative lobes exist: weights must be carried as RGBW, not normalised per sample
+    # splatting a constant colour: rgb/weight recovers it exactly wherever weight != 0 (render_target.rs:198-203)
+    b = SB.SceneBuilder(16, 16, 4, 0, 0)
+    m = b.add_material(F.MAT_MATTE, (0, 0, 0), roughness=0.0)
+    b.area_light(F.SHAPE_RECT, m, [SB.trs(t=(0, 0, 5), q=SB.quat_axis_angle((1, 0, 0), 180), s=100)], (0.25, 0.5, 0.75), p0=2, p1=2)
+    b.add_camera([SB.trs()], fov=40)
+    o = api.OracleScene(b.finish())
+    film, st = o.render(seed=1)
+    img = film[..., :3] / film[..., 3:]
+    assert np.allclose(img, [0.25, 0.5, 0.75], atol=1e-5)
+    assert abs(film[..., 3].sum() - 0) > 1  # weights accumulated
+    srgb = o.to_srgb8(film)
+    exp = [int((1.055 * c ** (1 / 2.4) - 0.055) * 255.0) for c in (0.25, 0.5, 0.75)]
+    assert np.abs(srgb.reshape(-1, 3).astype(int) - exp).max() <= 1

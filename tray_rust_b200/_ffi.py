@@ -229,6 +229,10 @@ def load_oracle(kind="det"):
     lib.orc_partition_even.argtypes = [vp, sz]
     lib.orc_partition_even.restype = sz
     lib.orc_libm_kind.restype = C.c_int
+    lib.orc_cross_dot.argtypes = [vp, vp, vp]
+    lib.orc_cross_dot.restype = None
+    lib.orc_xf_apply.argtypes = [C.POINTER(Keyframe), vp, vp]
+    lib.orc_xf_apply.restype = None
     _oracle[kind] = lib
     return lib
 

@@ -151,7 +151,8 @@ __host__ __device__ __forceinline__ uint32_t permute_index(uint32_t i, uint32_t 
         i &= w;
         i ^= i >> 5;
     } while (i >= l);
-    return (i + p) % l;
+    i += p % l; /* rotation by the key without 32-bit wrap-around (i, p % l < l) */
+    return i >= l ? i - l : i;
 }
 
 // stream addressing (DESIGN.md "RNG")

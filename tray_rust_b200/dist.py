@@ -1,0 +1,39 @@
+"""Multi-GPU plumbing: one process per GPU, tile-sharded like exec::distrib (src/exec/distrib/master.rs:88-120),
+film combined by SUM like film::Image::add_pixels (src/film/image.rs:21-50).
+
+The reference partitions the Morton-sorted 8x8 block list into contiguous ranges of floor(B / W) blocks, the last
+worker taking the remainder (master.rs:91-93, 218-224); `shard_blocks` reproduces that. The exchange step is one
+reduce of the RGBW film (torch.distributed: NCCL over NVLink on GPUs, gloo in the CPU tests)."""
+import torch
+import torch.distributed as dist
+
+
+def shard_blocks(n_blocks, rank, world):
+    """(block_start, block_count) of `rank`, exactly master.rs:91-93 + 218-224."""
+    per = n_blocks // world
+    start = rank * per
+    count = per if rank != world - 1 else n_blocks - start
+    return start, count
+
+
+def reduce_film(film, dst=0, group=None):
+    """Sum the per-rank RGBW films into rank `dst` (in place). `film` is a torch tensor on the rank's device."""
+    if not dist.is_initialized() or dist.get_world_size(group) == 1:
+        return film
+    dist.reduce(film, dst=dst, op=dist.ReduceOp.SUM, group=group)
+    return film
+
+
+def max_over_ranks(value, device):
+    """Timing rule: the job time is the max over ranks."""
+    t = torch.tensor([float(value)], dtype=torch.float64, device=device)
+    if dist.is_initialized() and dist.get_world_size() > 1:
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+    return float(t.item())
+
+
+def sum_over_ranks(values, device):
+    t = torch.tensor([float(v) for v in values], dtype=torch.float64, device=device)
+    if dist.is_initialized() and dist.get_world_size() > 1:
+        dist.all_reduce(t, op=dist.ReduceOp.SUM)
+    return [float(x) for x in t.tolist()]
