@@ -1,0 +1,309 @@
+#!/usr/bin/env python
+"""bench.py — Mrays/s (primary+secondary) of the render hot path on N B200s, with roofline and CPU baseline.
+
+    python bench.py --gpus N --steps K --warmup W            # our arm (one rank per GPU under torchrun for N > 1)
+    python bench.py --impl reference --gpus N --steps K ...  # the CPU arm: the oracle port on the box's host cores
+
+Workload (BASELINE.json configs[3]): synthetic 1M-triangle random mesh inside the Cornell walls,
+1920x1080, one 4096-spp frame rendered in additive passes. One STEP = one pass of `--spp-per-step` samples per pixel
+per GPU over the frame, tile-sharded across ranks exactly like the reference's master/worker mode
+(tray_rust_b200.dist.shard_blocks == master.rs:88-120): at N GPUs a step renders N*spp_per_step samples per pixel,
+each rank its own contiguous range of the Morton block list, followed by one SUM-reduce of the RGBW film (NCCL).
+Per-GPU work is therefore constant in N: "scaling": "weak".
+
+`value`  : rays/s of the whole job with the scene resident in HBM and the film left on the device.
+`e2e`    : the same metric through the reference-facing call trb_render (== Exec::render): per step it runs
+           Scene::update_frame (TLAS rebuild + upload), the kernels, and copies the film back to host memory.
+`roofline`: dominant kernel's algorithmic bytes (48 B/ray + 32 B/node test + 48 B/triangle test + 64 B/instance test,
+           SURVEY §8d; counted by the kernel's own test counters in an untimed replay of the same passes) over its
+           measured duration, against the measured HBM peak in MEASURED_PEAKS.json.
+"""
+import argparse
+import json
+import os
+import subprocess
+import sys
+import threading
+import time
+
+import numpy as np
+
+REPO = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, REPO)
+
+WORKLOAD = "C4 synthetic 1M-triangle random mesh in Cornell walls, 1920x1080, 4096 spp frame in passes (BASELINE configs[3])"
+METRIC = "Mrays/s (primary+secondary)"
+
+
+def parse():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=6)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--tris", type=int, default=1_000_000)
+    ap.add_argument("--width", type=int, default=1920)
+    ap.add_argument("--height", type=int, default=1080)
+    ap.add_argument("--spp", type=int, default=4096)
+    ap.add_argument("--spp-per-step", type=int, default=4)
+    ap.add_argument("--seed", type=int, default=1)
+    ap.add_argument("--cpu-seconds", type=float, default=15.0, help="target CPU time of the bounded cpu_baseline sample")
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    return ap.parse_args()
+
+
+def alg_bytes(rays, node, tri, inst):
+    """32 B ray in + 16 B hit out, 32 B per node box tested, 48 B per triangle tested, 64 B per instance tested."""
+    return 48 * rays + 32 * node + 48 * tri + 64 * inst
+
+
+class ClockSampler:
+    """nvidia-smi clocks / throttle reasons DURING the timed region (B200_PROFILING.md)."""
+    Q = "index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap"
+
+    def __init__(self, index):
+        self.index, self.rows, self.proc = index, [], None
+
+    def start(self):
+        try:
+            self.proc = subprocess.Popen(["nvidia-smi", "--query-gpu=" + self.Q, "--format=csv,noheader,nounits", "-lms", "200", "-i", str(self.index)],
+                                         stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+            threading.Thread(target=self._read, daemon=True).start()
+        except Exception:
+            self.proc = None
+
+    def _read(self):
+        for line in self.proc.stdout:
+            self.rows.append([x.strip() for x in line.split(",")])
+
+    def stop(self):
+        if self.proc:
+            self.proc.terminate()
+        sm = [float(r[1]) for r in self.rows if len(r) >= 8 and r[1].replace(".", "").isdigit()]
+        mx = [float(r[2]) for r in self.rows if len(r) >= 8 and r[2].replace(".", "").isdigit()]
+        reasons = set()
+        for r in self.rows:
+            if len(r) >= 8:
+                for name, v in zip(("hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"), r[4:8]):
+                    if v.lower().startswith("active"):
+                        reasons.add(name)
+        return {"sm_mhz": float(np.median(sm)) if sm else None, "sm_max_mhz": max(mx) if mx else None, "reasons": sorted(reasons), "samples": len(sm)}
+
+
+def build_scene_desc(a):
+    from tray_rust_b200 import scenebuild as SB
+    return SB.scene_c4(a.tris, a.width, a.height, a.spp).finish()
+
+
+def cpu_baseline(a, desc, threads=0):
+    """The oracle port (kind "port": the Rust reference cannot be built here) on the host cores, baseline mode
+    (per-ray transform recomposition like the reference), on a bounded sample of the same workload."""
+    from tray_rust_b200 import api, _ffi as F
+    o = api.OracleScene(desc, "det", baseline=True)
+    o.update_frame(0, 0.0, 0.0)
+    nb = o.n_blocks()
+    rng = np.random.default_rng(0)
+    probe_start = int(rng.integers(0, max(1, nb - 64)))
+    t0 = time.time()
+    _, st = o.render(threads=threads, flags=F.RENDER_NO_UPDATE, block_start=probe_start, block_count=64, sample_first=0, sample_count=1, seed=a.seed)
+    dt = max(time.time() - t0, 1e-3)
+    rate = st.rays_total() / dt
+    # choose a contiguous Morton range in the middle of the image sized for ~cpu_seconds
+    want_rays = rate * a.cpu_seconds
+    per_block = st.rays_total() / 64.0
+    count = int(min(nb, max(64, want_rays / per_block)))
+    start = max(0, nb // 2 - count // 2)
+    t0 = time.time()
+    _, st = o.render(threads=threads, flags=F.RENDER_NO_UPDATE, block_start=start, block_count=count, sample_first=0, sample_count=1, seed=a.seed)
+    dt = time.time() - t0
+    cores = threads if threads > 0 else (os.cpu_count() or 1)
+    out = {"value": st.rays_total() / dt / 1e6, "unit": "Mrays/s", "cores": cores, "kind": "port",
+           "sample": "%d of %d Morton blocks (8x8 px) x 1 spp of the same C4 scene, %.1f s wall, oracle baseline mode, %d threads" % (count, nb, dt, cores),
+           "samples_per_s": st.camera_samples / dt}
+    o.close()
+    return out
+
+
+def run_reference(a):
+    """--impl reference: the CPU implementation of the path (oracle port) with all host threads, bounded steps."""
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return
+    from tray_rust_b200 import api, _ffi as F
+    desc = build_scene_desc(a)
+    o = api.OracleScene(desc, "det", baseline=True)
+    o.update_frame(0, 0.0, 0.0)
+    nb = o.n_blocks()
+    count = min(nb, 1200)  # bounded sample per step: ~0.6 M camera samples -> seconds of CPU work
+    start = nb // 2 - count // 2
+    times, rays, samples = [], 0, 0
+    for it in range(a.warmup + a.steps):
+        t0 = time.time()
+        _, st = o.render(threads=0, flags=F.RENDER_NO_UPDATE, block_start=start, block_count=count, sample_first=it, sample_count=1, seed=a.seed)
+        dt = time.time() - t0
+        if it >= a.warmup:
+            times.append(dt); rays += st.rays_total(); samples += st.camera_samples
+    total = sum(times)
+    v = rays / total / 1e6
+    cores = os.cpu_count() or 1
+    line = {"impl": "reference", "metric": METRIC, "value": v, "unit": "Mrays/s", "n_gpus": a.gpus, "steps": a.steps, "warmup": a.warmup,
+            "ms_per_step": 1e3 * total / a.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+            "config": {"workload": WORKLOAD, "tris": a.tris, "width": a.width, "height": a.height, "spp": a.spp},
+            "samples_per_s": samples / total,
+            "cpu_baseline": {"value": v, "unit": "Mrays/s", "cores": cores, "kind": "port",
+                             "sample": "each step = %d of %d Morton blocks x 1 spp of the C4 scene (oracle port, baseline mode, %d threads); the Rust reference cannot be built here (no cargo/rustc)" % (count, nb, cores)},
+            "e2e": {"value": v, "unit": "Mrays/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}
+    print(json.dumps(line))
+
+
+def run_ours(a):
+    import torch
+    import torch.distributed as dist
+    from tray_rust_b200 import api, _ffi as F
+    from tray_rust_b200.dist import shard_blocks, reduce_film, max_over_ranks, sum_over_ranks
+
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    rank = int(os.environ.get("RANK", "0"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    if not torch.cuda.is_available():
+        raise RuntimeError("bench.py needs a CUDA device: tray_rust_b200 has no CPU fallback")
+    torch.cuda.set_device(local)
+    dev = torch.device("cuda", local)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=dev)
+    lib = F.load_trb()
+
+    desc = build_scene_desc(a)
+    t0 = time.time()
+    g = api.Scene(desc, local)
+    create_s = time.time() - t0
+    g.update_frame(0, 0.0, 0.0)
+    nb = g.n_blocks()
+    bstart, bcount = shard_blocks(nb, rank, world)
+    spp_step = a.spp_per_step * world            # weak scaling: N x the samples per pixel per step, tile-sharded
+    n_total = a.warmup + a.steps
+    assert spp_step * n_total <= g.spp, "not enough spp in the frame for the requested steps"
+
+    film = torch.zeros((a.height, a.width, 4), dtype=torch.float32, device=dev)
+    stats = torch.zeros(10, dtype=torch.int64, device=dev)
+    flush = torch.empty(256 << 20, dtype=torch.uint8, device=dev)   # > 126 MB L2
+    stream = torch.cuda.current_stream().cuda_stream
+
+    def step(i, flags=0, st=stats):
+        flush.fill_(i & 0xFF)                                         # L2 flush between timed iterations
+        g.render_device(film.data_ptr(), st.data_ptr(), stream, spp=a.spp, sample_first=i * spp_step, sample_count=spp_step,
+                        block_start=bstart, block_count=bcount, seed=a.seed, flags=flags)
+        if world > 1:
+            reduce_film(film, dst=0)
+
+    for i in range(a.warmup):
+        step(i)
+    torch.cuda.synchronize()
+    if world > 1:
+        dist.barrier()
+    stats.zero_()
+    clocks = ClockSampler(local)
+    if rank == 0:
+        clocks.start()
+    launches0 = lib.trb_launch_count()
+    ev = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)) for _ in range(a.steps)]
+    kev = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)) for _ in range(a.steps)]
+    e_begin, e_end = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    torch.cuda.synchronize()
+    e_begin.record()
+    for k in range(a.steps):
+        i = a.warmup + k
+        flush.fill_(i & 0xFF)
+        kev[k][0].record()
+        g.render_device(film.data_ptr(), stats.data_ptr(), stream, spp=a.spp, sample_first=i * spp_step, sample_count=spp_step,
+                        block_start=bstart, block_count=bcount, seed=a.seed)
+        kev[k][1].record()
+        if world > 1:
+            reduce_film(film, dst=0)
+    e_end.record()
+    torch.cuda.synchronize()
+    if world > 1:
+        dist.barrier()
+    launches = lib.trb_launch_count() - launches0
+    clk = clocks.stop() if rank == 0 else None
+    total_ms = max_over_ranks(e_begin.elapsed_time(e_end), dev)
+    kernel_ms = [kev[k][0].elapsed_time(kev[k][1]) for k in range(a.steps)]
+    st = stats.cpu().numpy()
+    tot = sum_over_ranks([st[0], st[1], st[2], st[3], st[4]], dev)     # samples, primary, shadow, mis, continuation (all ranks)
+    rays_all = sum(tot[1:5])
+
+    # --- roofline of the dominant kernel: untimed replay of this rank's timed passes with the test counters on
+    cstats = torch.zeros(10, dtype=torch.int64, device=dev)
+    scratch = torch.zeros_like(film)
+    for k in range(a.steps):
+        i = a.warmup + k
+        g.render_device(scratch.data_ptr(), cstats.data_ptr(), stream, spp=a.spp, sample_first=i * spp_step, sample_count=spp_step,
+                        block_start=bstart, block_count=bcount, seed=a.seed, flags=F.RENDER_STATS)
+    torch.cuda.synchronize()
+    cs = cstats.cpu().numpy()
+    rank_rays = int(cs[1:5].sum())
+    bytes_per_launch = alg_bytes(rank_rays, int(cs[5]), int(cs[6]), int(cs[7])) / a.steps
+    del scratch
+
+    # --- e2e: the reference-facing call (host film, update_frame + H2D + kernels + D2H inside the timed region)
+    e2e = None
+    if world == 1:
+        hfilm = np.zeros((a.height, a.width, 4), np.float32)
+        e2e_steps = max(2, min(a.steps, 4))
+        g.render(hfilm, spp=a.spp, sample_first=0, sample_count=spp_step, seed=a.seed)   # warm
+        rays_e, t_e = 0, 0.0
+        for k in range(e2e_steps):
+            t0 = time.perf_counter()
+            _, s_e = g.render(hfilm, spp=a.spp, sample_first=(a.warmup + k) * spp_step, sample_count=spp_step, seed=a.seed)
+            t_e += time.perf_counter() - t0
+            rays_e += s_e.rays_total()
+        n_inst = desc.n_instances
+        h2d = n_inst * 176 + (2 * n_inst) * 32 + n_inst * 4 + 32      # instances + TLAS nodes (<= 2n-1) + order + config
+        e2e = {"value": rays_e / t_e / 1e6, "unit": "Mrays/s", "h2d_bytes_per_step": int(h2d), "d2h_bytes_per_step": int(a.width * a.height * 16 + 80),
+               "ms_per_step": 1e3 * t_e / e2e_steps, "steps": e2e_steps, "api": "trb_render (Exec::render): update_frame + kernels + film D2H"}
+
+    cpu = None
+    if rank == 0 and world == 1 and not a.no_cpu_baseline:
+        cpu = cpu_baseline(a, desc)
+
+    if rank == 0:
+        peaks = {}
+        try:
+            peaks = json.load(open(os.path.join(REPO, "MEASURED_PEAKS.json")))
+        except Exception:
+            pass
+        peak = float(peaks.get("hbm_gbs", 6650.0))
+        avg_kernel_ms = float(np.mean(kernel_ms))
+        achieved = bytes_per_launch / (avg_kernel_ms * 1e-3) / 1e9
+        traffic = None
+        try:
+            traffic = json.load(open(os.path.join(REPO, "profiles", "traffic.json"))).get("dram_bytes_per_launch")
+        except Exception:
+            pass
+        line = {
+            "metric": METRIC, "value": rays_all / (total_ms * 1e-3) / 1e6, "unit": "Mrays/s", "n_gpus": world, "steps": a.steps, "warmup": a.warmup,
+            "ms_per_step": total_ms / a.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+            "config": {"workload": WORKLOAD, "tris": a.tris, "width": a.width, "height": a.height, "spp": a.spp, "spp_per_step": spp_step,
+                       "blocks_per_rank": bcount, "parallelism": "tile-sharded x%d (Morton block ranges) + film SUM-reduce" % world,
+                       "l2": "256 MiB buffer written between timed steps (L2 flush)", "scene_create_s": round(create_s, 2)},
+            "samples_per_s": tot[0] / (total_ms * 1e-3),
+            "rays": {"primary": tot[1], "shadow": tot[2], "mis": tot[3], "continuation": tot[4],
+                     "primary_plus_shadow_mrays_s": (tot[1] + tot[2]) / (total_ms * 1e-3) / 1e6},
+            "roofline": {"bound": "hbm", "kernel": "k_render", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
+                         "peak_source": "MEASURED_PEAKS.json hbm_gbs (measured)" if peaks else "fallback 6650 GB/s",
+                         "traffic": traffic, "algorithmic_bytes_per_launch": bytes_per_launch, "kernel_ms": avg_kernel_ms,
+                         "per_ray": {"node_tests": cs[5] / max(1, rank_rays), "tri_tests": cs[6] / max(1, rank_rays), "inst_tests": cs[7] / max(1, rank_rays)}},
+            "gpu_launches": int(launches), "clocks": clk, "e2e": e2e, "cpu_baseline": cpu,
+        }
+        print(json.dumps(line, default=float))
+    g.close()
+    if world > 1:
+        dist.destroy_process_group()
+
+
+if __name__ == "__main__":
+    args = parse()
+    if args.impl == "reference":
+        run_reference(args)
+    else:
+        run_ours(args)

@@ -344,6 +344,9 @@ trb_status trb_desc_load_json(const char* path, uint32_t width, uint32_t height,
                               trb_scene_desc** out);
 void trb_desc_free(trb_scene_desc* desc);
 
+/* Number of CUDA kernels this library has launched in this process (monotonic). */
+unsigned long long trb_launch_count(void);
+
 const char* trb_last_error(void);
 uint32_t trb_abi_version(void);
 

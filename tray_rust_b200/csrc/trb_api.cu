@@ -12,6 +12,7 @@ using namespace trbh;
 namespace {
 
 thread_local std::string g_error;
+unsigned long long g_launches = 0; // kernels launched by this library (bench.py reports it as gpu_launches)
 trb_status fail(trb_status s, const std::string& msg) { g_error = msg; return s; }
 
 #define CU(call)                                                                                                   \
@@ -222,6 +223,7 @@ trb_status launch_render_t(trb_scene* s, const trb::RenderParams& rp, uint32_t f
     CU(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, trb::k_render<STATS, MODE>, trb::RENDER_THREADS, smem));
     const uint32_t grid = std::max(1u, std::min<uint32_t>(rp.n_blocks, (uint32_t)(std::max(1, per_sm) * s->sm_count)));
     trb::k_render<STATS, MODE><<<grid, trb::RENDER_THREADS, smem, st>>>(s->ds, rp, flags);
+    g_launches++;
     CU(cudaGetLastError());
     return TRB_OK;
 }
@@ -251,6 +253,7 @@ extern "C" {
 const char* trb_last_error(void) { return g_error.c_str(); }
 void trb_internal_set_error(const char* msg) { g_error = msg ? msg : ""; } // used by trb_loader.cpp
 uint32_t trb_abi_version(void) { return TRB_ABI_VERSION; }
+unsigned long long trb_launch_count(void) { return g_launches; }
 
 trb_status trb_scene_create(const trb_scene_desc* d, int device, trb_scene** out) {
     if (!out) return fail(TRB_INVALID_ARG, "null out pointer");
@@ -576,6 +579,7 @@ trb_status trb_intersect_device(trb_scene* s, size_t n, const trb_ray* d_rays, t
     if (n == 0) return TRB_OK;
     CU(cudaSetDevice(s->device));
     const unsigned grid = (unsigned)std::min<size_t>((n + 127) / 128, (size_t)s->sm_count * 16);
+    g_launches++;
     trb::k_intersect<false><<<grid, 128, 0, static_cast<cudaStream_t>(stream)>>>(s->ds, n, d_rays, d_hits, reinterpret_cast<trb::DStats*>(d_stats), s->d_error);
     CU(cudaGetLastError());
     return TRB_OK;
