@@ -183,8 +183,9 @@ typedef struct trb_scene_desc {
 enum {
     TRB_RENDER_STATS = 1u,            /* also count BVH node / triangle / instance tests */
     TRB_RENDER_NO_UPDATE = 2u,        /* skip Scene::update_frame (caller already did it) */
-    TRB_RENDER_REFERENCE_SHADOW = 4u  /* trace shadow rays as full closest-hit like light/mod.rs:30-37 instead of
+    TRB_RENDER_REFERENCE_SHADOW = 4u, /* trace shadow rays as full closest-hit like light/mod.rs:30-37 instead of
                                          stopping at the first accepted hit (same boolean, fewer tests) */
+    TRB_RENDER_MEGAKERNEL = 8u        /* one persistent kernel per pass instead of the wavefront pipeline (same results) */
 };
 typedef struct trb_render_cfg {
     uint32_t spp;           /* Config.spp; 0 = film.samples. Rounded up to pow2 like ld.rs:22-26 */

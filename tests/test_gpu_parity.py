@@ -88,6 +88,9 @@ def test_gpu_vs_oracle(name):
     # default mode (shadow rays stop at the first accepted hit): identical radiance, fewer tests
     gsamp2, gst2 = g.render_samples(flags=F.RENDER_STATS, **kw)
     assert gsamp2.tobytes() == gsamp.tobytes() and gst2.node_tests <= gst.node_tests
+    # the megakernel execution shape agrees bit for bit with the wavefront pipeline, counters included
+    gsamp3, gst3 = g.render_samples(flags=F.RENDER_MEGAKERNEL | F.RENDER_STATS | F.RENDER_REFERENCE_SHADOW, **kw)
+    assert gsamp3.tobytes() == gsamp.tobytes() and [getattr(gst3, k) for k in KEYS] == [getattr(gst, k) for k in KEYS]
     # film (splat order is atomic-dependent): tolerance
     gf, _ = g.render(**kw); of, _ = o.render(**kw)
     ig = gf[..., :3] / np.maximum(gf[..., 3:], 1e-6); io = of[..., :3] / np.maximum(of[..., 3:], 1e-6)

@@ -86,6 +86,9 @@ def compare_scene(tag, desc, spp_pass=4, n_rand=20000, film=True):
     # default (any-hit shadow) mode must give the same radiance
     gsamp2, _ = g.render_samples(flags=0, **kw)
     report(tag + ":anyhit_same_radiance", gsamp2.tobytes() == gsamp.tobytes())
+    # the megakernel execution shape must agree bit for bit, counters included
+    gsamp3, gst3 = g.render_samples(flags=F.RENDER_MEGAKERNEL | F.RENDER_STATS | F.RENDER_REFERENCE_SHADOW, **kw)
+    report(tag + ":megakernel_same", gsamp3.tobytes() == gsamp.tobytes() and all(getattr(gst3, k) == getattr(gst, k) for k in keys))
     if film:
         gf, gs = g.render(flags=0, **kw)
         of, _ = o.render(flags=0, threads=0, **kw)
@@ -101,6 +104,9 @@ def compare_scene(tag, desc, spp_pass=4, n_rand=20000, film=True):
     g.close(); o.close()
 
 
+FLAGS = 0
+
+
 def timing(n_tris):
     import torch
     b = SB.scene_c4(n_tris, 1920, 1080, 4096)
@@ -111,13 +117,13 @@ def timing(n_tris):
     film = torch.zeros((1080, 1920, 4), dtype=torch.float32, device="cuda")
     stats = torch.zeros(10, dtype=torch.int64, device="cuda")
     out = {}
-    for spp_pass in (1, 4):
+    for spp_pass in (1, 4, 8):
         for it in range(3):
             stats.zero_()
             e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
             torch.cuda.synchronize()
             e0.record()
-            g.render_device(film.data_ptr(), stats.data_ptr(), None, sample_first=it * spp_pass, sample_count=spp_pass, seed=1)
+            g.render_device(film.data_ptr(), stats.data_ptr(), None, sample_first=it * spp_pass, sample_count=spp_pass, seed=1, flags=FLAGS)
             e1.record()
             torch.cuda.synchronize()
             ms = e0.elapsed_time(e1)

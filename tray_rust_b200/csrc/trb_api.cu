@@ -108,7 +108,12 @@ struct trb_scene {
     float* h_film_staging = nullptr; // pinned
     cudaEvent_t ev0 = nullptr, ev1 = nullptr;
     bool frame_ready = false;
+    // wavefront path state (grown on demand, owned outside the arena so it can be re-sized)
+    trb::WfState wf{};
+    size_t wf_capacity = 0;
+    std::vector<void*> wf_allocs;
     ~trb_scene() {
+        for (void* p : wf_allocs) cudaFree(p);
         if (h_film_staging) cudaFreeHost(h_film_staging);
         if (ev0) cudaEventDestroy(ev0);
         if (ev1) cudaEventDestroy(ev1);
@@ -227,7 +232,62 @@ trb_status launch_render_t(trb_scene* s, const trb::RenderParams& rp, uint32_t f
     CU(cudaGetLastError());
     return TRB_OK;
 }
+trb_status ensure_wavefront(trb_scene* s, size_t n_paths) {
+    if (n_paths <= s->wf_capacity) return TRB_OK;
+    for (void* p : s->wf_allocs) cudaFree(p);
+    s->wf_allocs.clear(); s->wf_capacity = 0;
+    const size_t cap = n_paths + n_paths / 16 + 1024;
+    auto grab = [&](size_t bytes, void** out) -> cudaError_t {
+        cudaError_t e = cudaMalloc(out, bytes);
+        if (e == cudaSuccess) s->wf_allocs.push_back(*out);
+        return e;
+    };
+    trb::WfState& w = s->wf;
+    float4** f4[] = {&w.org, &w.cont, &w.shadow, &w.mis, &w.a, &w.b, &w.tprev, &w.thr, &w.illum, &w.ng, &w.rad};
+    for (float4** q : f4) CU(grab(cap * sizeof(float4), reinterpret_cast<void**>(q)));
+    CU(grab(cap * sizeof(uint4), reinterpret_cast<void**>(&w.hit)));
+    uint32_t** u1[] = {&w.q_active[0], &w.q_active[1], &w.q_cont, &w.q_shadow, &w.q_mis};
+    for (uint32_t** q : u1) CU(grab(cap * sizeof(uint32_t), reinterpret_cast<void**>(q)));
+    CU(grab(64 * trb::WF_CNT * sizeof(uint32_t), reinterpret_cast<void**>(&w.counters)));
+    s->wf_capacity = cap;
+    return TRB_OK;
+}
+
+// Wavefront pass: generate, then (trace, shade) per bounce round, then the film (DESIGN.md "Execution shape").
+trb_status launch_wavefront(trb_scene* s, const trb::RenderParams& rp, uint32_t flags, int mode, cudaStream_t st) {
+    const size_t n_paths = (size_t)rp.n_blocks * 64 * rp.sample_count;
+    if (n_paths >= (1ull << 31)) return fail(TRB_INVALID_ARG, "pass too large: blocks*64*sample_count must be < 2^31; render in more passes");
+    if (s->integrator.max_depth + 3 > 60) return fail(TRB_UNSUPPORTED, "max_depth > 57");
+    trb_status r = ensure_wavefront(s, n_paths);
+    if (r != TRB_OK) return r;
+    trb::WfState wf = s->wf;
+    wf.n_paths = (uint32_t)n_paths;
+    const bool stats = (flags & TRB_RENDER_STATS) != 0;
+    const uint32_t rounds = s->integrator.max_depth + 2; // bounces 0..max_depth, plus the round that only resolves
+    CU(cudaMemsetAsync(wf.counters, 0, 64 * trb::WF_CNT * sizeof(uint32_t), st));
+    const unsigned gen_grid = (unsigned)std::min<size_t>((n_paths + 255) / 256, (size_t)s->sm_count * 8);
+    trb::k_wf_generate<<<gen_grid, 256, 0, st>>>(s->ds, rp, wf);
+    g_launches++;
+    const unsigned trace_grid = (unsigned)s->sm_count * 12, shade_grid = (unsigned)s->sm_count * 4;
+    for (uint32_t round = 0; round < rounds; ++round) {
+        if (stats) trb::k_wf_trace<true><<<trace_grid, 128, 0, st>>>(s->ds, rp, wf, round, flags);
+        else trb::k_wf_trace<false><<<trace_grid, 128, 0, st>>>(s->ds, rp, wf, round, flags);
+        if (mode == 0) trb::k_wf_shade<0><<<shade_grid, 128, 0, st>>>(s->ds, rp, wf, round);
+        else trb::k_wf_shade<1><<<shade_grid, 128, 0, st>>>(s->ds, rp, wf, round);
+        g_launches += 2;
+    }
+    if (mode == 0) {
+        const int T = 9 + 2 * std::max(s->ds.fpw_x, s->ds.fpw_y);
+        const unsigned film_grid = std::min<unsigned>(rp.n_blocks, (unsigned)s->sm_count * 8);
+        trb::k_wf_film<<<film_grid, trb::RENDER_THREADS, (size_t)T * T * sizeof(float4), st>>>(s->ds, rp, wf);
+        g_launches++;
+    }
+    CU(cudaGetLastError());
+    return TRB_OK;
+}
+
 trb_status launch_render(trb_scene* s, const trb::RenderParams& rp, uint32_t flags, int mode, cudaStream_t st) {
+    if (!(flags & TRB_RENDER_MEGAKERNEL)) return launch_wavefront(s, rp, flags, mode, st);
     const bool stats = (flags & TRB_RENDER_STATS) != 0;
     CU(cudaMemsetAsync(rp.work_counter, 0, sizeof(uint32_t), st));
     if (mode == 0) return stats ? launch_render_t<true, 0>(s, rp, flags, st) : launch_render_t<false, 0>(s, rp, flags, st);

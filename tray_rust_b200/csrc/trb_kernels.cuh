@@ -792,11 +792,22 @@ struct RayCounts { uint32_t primary, shadow, mis, cont; };
 // ------------------------------------------------------------------------------------------
 // Integrator::estimate_direct (integrator/mod.rs:122-169) with sample_one_light's light choice
 // already made; Light impl of Emitter (emitter.rs:160-204); OcclusionTester (light/mod.rs:21-37).
+//
+// Split in two so the two rays it needs can be traced elsewhere (inline in the megakernel, by the
+// trace kernel in the wavefront pipeline) without changing a single operation:
+//   direct_setup   everything up to the two rays: the shadow segment + the light-sample term A it
+//                  enables, the BSDF-sampled MIS ray + the term B it enables
+//   direct_resolve direct = occluded ? 0 : A;  if the MIS ray hit this light facing us: direct += B
 // ------------------------------------------------------------------------------------------
-template <bool STATS>
-__device__ __noinline__ f3 estimate_direct(const DScene& sc, const Mat& m, const Frame& fr, f3 wo, uint32_t li, float l0, float l1, float b0, float b1,
-                                           float bc, bool ref_shadow, RayCounts& rc, Cnt& cnt, int* err) {
-    f3 direct = splat(0.0f);
+struct DirectSetup {
+    f3 a, b;             // contributions enabled by the shadow / MIS ray
+    f3 shadow_d, mis_d;  // shadow segment p -> light sample (t in [0.001, 0.999]); MIS direction (t in [0.001, inf))
+    bool has_shadow, has_mis;
+};
+
+__device__ __noinline__ void direct_setup(const DScene& sc, const Mat& m, const Frame& fr, f3 wo, uint32_t li, float l0, float l1, float b0, float b1,
+                                          float bc, DirectSetup& ds) {
+    ds.a = splat(0.0f); ds.b = splat(0.0f); ds.shadow_d = splat(0.0f); ds.mis_d = splat(0.0f); ds.has_shadow = false; ds.has_mis = false;
     const DInstance& light = sc.instances[li];
     const uint32_t kind = __ldg(&light.kind), shape = __ldg(&light.shape);
     const float p0 = __ldg(&light.p0), p1 = __ldg(&light.p1);
@@ -827,19 +838,15 @@ __device__ __noinline__ f3 estimate_direct(const DScene& sc, const Mat& m, const
         seg = pw - p;
     }
     if (pdf_light > 0.0f && !black(lrad)) {
-        Ray sr; sr.o = p; sr.d = seg; sr.tmin = 0.001f; sr.tmax = 0.999f; // OcclusionTester::test_points
-        HitRec sh;
-        rc.shadow++;
-        const bool occluded = scene_trace<STATS>(sc, sr, sh, !ref_shadow, cnt, err);
-        if (!occluded) {
-            const f3 f = bsdf_eval(sc, m, fr, wo, wi, BX_NON_SPECULAR);
-            if (!black(f)) {
-                if (delta) direct = f * lrad * fabsf(dot3(wi, fr.n)) / pdf_light;
-                else {
-                    const float pdf_bsdf = bsdf_pdf(m, fr, wo, wi, BX_NON_SPECULAR);
-                    const float w = power_heuristic(pdf_light, pdf_bsdf);
-                    direct = f * lrad * fabsf(dot3(wi, fr.n)) * w / pdf_light;
-                }
+        ds.has_shadow = true; ds.shadow_d = seg; // OcclusionTester::test_points: Ray::segment(a, b - a, 0.001, 0.999)
+        // evaluated only when unoccluded in the reference; a pure function of the same inputs, so hoisting it is exact
+        const f3 f = bsdf_eval(sc, m, fr, wo, wi, BX_NON_SPECULAR);
+        if (!black(f)) {
+            if (delta) ds.a = f * lrad * fabsf(dot3(wi, fr.n)) / pdf_light;
+            else {
+                const float pdf_bsdf = bsdf_pdf(m, fr, wo, wi, BX_NON_SPECULAR);
+                const float w = power_heuristic(pdf_light, pdf_bsdf);
+                ds.a = f * lrad * fabsf(dot3(wi, fr.n)) * w / pdf_light;
             }
         }
     }
@@ -848,32 +855,100 @@ __device__ __noinline__ f3 estimate_direct(const DScene& sc, const Mat& m, const
         bsdf_sample(sc, m, fr, wo, BX_NON_SPECULAR, b0, b1, bc, f, wi2, pdf_bsdf, sampled);
         if (pdf_bsdf > 0.0f && !black(f)) {
             float w = 1.0f;
+            bool go = true;
             if (!(sampled & BX_SPECULAR)) { // light.pdf (emitter.rs:193-203)
                 const f3 pl = xf_point(linv, p);
                 const f3 wl = unit(xf_vector(linv, wi2));
                 const float pl_pdf = shape_pdf(shape, p0, p1, pl, wl);
-                if (pl_pdf == 0.0f) return direct; // Q7
-                w = power_heuristic(pdf_bsdf, pl_pdf);
+                if (pl_pdf == 0.0f) go = false; // `return direct_light` (Q7)
+                else w = power_heuristic(pdf_bsdf, pl_pdf);
             }
-            Ray mr; mr.o = p; mr.d = wi2; mr.tmin = 0.001f; mr.tmax = finf();
-            HitRec mh;
-            rc.mis++;
-            f3 lr = splat(0.0f);
-            if (scene_trace<STATS>(sc, mr, mh, false, cnt, err) && mh.inst == li) {
-                // e.radiance(&-w_i, &h.dg.p, &h.dg.ng, time): needs the hit's world geometric normal
-                Surf s;
-                surface_at(sc, mr, mh, s);
-                if (dot3(-wi2, s.ng) > 0.0f) lr = emission;
+            if (go) {
+                ds.has_mis = true; ds.mis_d = wi2; // Ray::segment(p, w_i, 0.001, inf)
+                ds.b = f * emission * fabsf(dot3(wi2, fr.n)) * w / pdf_bsdf; // used iff the ray hits this light from its front
             }
-            if (!black(lr)) direct = direct + f * lr * fabsf(dot3(wi2, fr.n)) * w / pdf_bsdf;
         }
     }
+}
+// Does the MIS ray's hit see the light's emitting side? e.radiance(&-w_i, &h.dg.p, &h.dg.ng) (integrator/mod.rs:156-162)
+__device__ __forceinline__ bool mis_sees_light(const DScene& sc, f3 org, f3 mis_d, uint32_t li, uint32_t hit_inst, float hit_t) {
+    if (hit_inst != li) return false;
+    const DInstance& light = sc.instances[li];
+    if (black(mk(__ldg(&light.emission[0]), __ldg(&light.emission[1]), __ldg(&light.emission[2])))) return false; // `if !li.is_black()`
+    Ray mr; mr.o = org; mr.d = mis_d; mr.tmin = 0.001f; mr.tmax = hit_t;
+    HitRec mh; mh.t = hit_t; mh.inst = hit_inst; mh.prim = 0; mh.b1 = 0.0f; mh.b2 = 0.0f; // area lights are analytic shapes
+    Surf s;
+    surface_at(sc, mr, mh, s);
+    return dot3(-mis_d, s.ng) > 0.0f;
+}
+__device__ __forceinline__ f3 direct_resolve(f3 a, f3 b, bool occluded, bool mis_ok) {
+    f3 direct = occluded ? splat(0.0f) : a;
+    if (mis_ok) direct = direct + b;
     return direct;
 }
 
 // ------------------------------------------------------------------------------------------
-// One camera sample: Camera::generate_ray + Scene::intersect + Path::illumination + clamp
-// (multithreaded.rs:94-102, path.rs:45-119).
+// One bounce of Path::illumination (path.rs:69-111) after the vertex has been found: emission,
+// BSDF, direct-light setup, next direction, Russian roulette. Shared by both execution shapes.
+// ------------------------------------------------------------------------------------------
+struct BounceOut {
+    DirectSetup ds;
+    uint32_t light;      // instance index of the sampled light
+    f3 t_before;         // path_throughput multiplying this bounce's direct light
+    f3 throughput;       // after the BSDF sample (and Russian roulette)
+    f3 next_d;           // ray.child direction
+    f3 org;              // bsdf.p
+    bool specular, terminate; // terminate: no continuation ray (black f / pdf 0 / RR / max depth)
+};
+__device__ __forceinline__ void shade_bounce(const DScene& sc, const Surf& s, uint32_t hit_inst, f3 ray_d, f3 first_ng, uint32_t bounce, bool prev_specular,
+                                             uint32_t hsample, f3 throughput_in, f3& illum, BounceOut& o) {
+    const DInstance& in = sc.instances[hit_inst];
+    if (bounce == 0 || prev_specular) {
+        if (__ldg(&in.kind) != TRB_INST_RECEIVER) {
+            const f3 w = -ray_d;
+            if (dot3(w, first_ng) > 0.0f) // Emitter::radiance with the FIRST hit's normal (path.rs:73, Q1)
+                illum = illum + throughput_in * mk(__ldg(&in.emission[0]), __ldg(&in.emission[1]), __ldg(&in.emission[2]));
+        }
+    }
+    Mat m;
+    load_mat(sc.materials[__ldg(&in.material)], m);
+    Frame fr;
+    make_frame(s, fr);
+    const f3 wo = -ray_d;
+    PathRng rng; rng.h = hsample; rng.len = sc.max_depth + 1;
+    float l0, l1, b0, b1, q0, q1;
+    rng.two_d(bounce, S_L0, S_L1, S_L_PERM, l0, l1);
+    rng.two_d(bounce, S_B0, S_B1, S_B_PERM, b0, b1);
+    const float lc = rng.one_d(bounce, S_LC, S_LC_PERM), bc = rng.one_d(bounce, S_BC, S_BC_PERM);
+    uint32_t l = f2u(lc * (float)sc.n_lights); // sample_one_light (integrator/mod.rs:108-110), no xN (Q2)
+    if (l > sc.n_lights - 1) l = sc.n_lights - 1;
+    o.light = __ldg(&sc.lights[l]);
+    direct_setup(sc, m, fr, wo, o.light, l0, l1, b0, b1, bc, o.ds);
+    o.t_before = throughput_in;
+    o.org = fr.p;
+    rng.two_d(bounce, S_P0, S_P1, S_P_PERM, q0, q1);
+    const float qc = rng.one_d(bounce, S_PC, S_PC_PERM);
+    f3 f, wi; float pdf; uint32_t sampled;
+    bsdf_sample(sc, m, fr, wo, BX_ALL, q0, q1, qc, f, wi, pdf, sampled);
+    o.throughput = throughput_in; o.next_d = splat(0.0f); o.specular = false; o.terminate = true;
+    if (black(f) || pdf == 0.0f) return;
+    o.specular = (sampled & BX_SPECULAR) != 0;
+    f3 t = throughput_in * f * fabsf(dot3(wi, fr.n)) / pdf;
+    if (bounce > sc.min_depth) { // Russian roulette (path.rs:97-104), probability may exceed 1 (Q8)
+        const float lum = 0.2126f * t.x + 0.7152f * t.y + 0.0722f * t.z;
+        const float cont = fmaxf(0.5f, lum);
+        if (unit_f32(rng.draw(S_RR + bounce)) > cont) { o.throughput = t; return; }
+        t = t / cont;
+    }
+    o.throughput = t;
+    if (bounce == sc.max_depth) return;
+    o.next_d = unit(wi); // ray.child(&bsdf.p, &w_i.normalized()), min_t = 0.001
+    o.terminate = false;
+}
+
+// ------------------------------------------------------------------------------------------
+// One camera sample, megakernel shape: Camera::generate_ray + Scene::intersect + Path::illumination
+// (multithreaded.rs:94-102, path.rs:45-119) with the rays traced inline.
 // ------------------------------------------------------------------------------------------
 __device__ __forceinline__ void camera_ray(const DScene& sc, float sx, float sy, float tm, Ray& ray) { // camera.rs:150-157
     const f3 pc = xf_point(sc.cam.px_to_cam, mk(sx, sy, 0.0f));
@@ -890,51 +965,33 @@ __device__ f3 radiance_of_sample(const DScene& sc, Ray ray, uint32_t hpix_sample
     HitRec hit;
     rc.primary++;
     if (!scene_trace<STATS>(sc, ray, hit, false, cnt, err)) return splat(0.0f); // multithreaded.rs:101-102
-    PathRng rng; rng.h = hpix_sample; rng.len = sc.max_depth + 1;
     f3 illum = splat(0.0f), throughput = splat(1.0f);
     bool specular_bounce = false;
     uint32_t bounce = 0;
     Surf s;
     surface_at(sc, ray, hit, s);
-    const f3 first_ng = s.ng; // path.rs:73 reads hit.dg of the FIRST hit (Q1)
+    const f3 first_ng = s.ng;
     for (;;) {
-        const DInstance& in = sc.instances[hit.inst];
-        if (bounce == 0 || specular_bounce) {
-            if (__ldg(&in.kind) != TRB_INST_RECEIVER) {
-                const f3 w = -ray.d;
-                if (dot3(w, first_ng) > 0.0f) // Emitter::radiance (emitter.rs:140-142)
-                    illum = illum + throughput * mk(__ldg(&in.emission[0]), __ldg(&in.emission[1]), __ldg(&in.emission[2]));
-            }
+        BounceOut o;
+        shade_bounce(sc, s, hit.inst, ray.d, first_ng, bounce, specular_bounce, hpix_sample, throughput, illum, o);
+        bool occluded = false, mis_ok = false;
+        if (o.ds.has_shadow) {
+            Ray sr; sr.o = o.org; sr.d = o.ds.shadow_d; sr.tmin = 0.001f; sr.tmax = 0.999f;
+            HitRec sh;
+            rc.shadow++;
+            occluded = scene_trace<STATS>(sc, sr, sh, !ref_shadow, cnt, err);
         }
-        Mat m;
-        load_mat(sc.materials[__ldg(&in.material)], m);
-        Frame fr;
-        make_frame(s, fr);
-        const f3 wo = -ray.d;
-        float l0, l1, b0, b1, q0, q1;
-        rng.two_d(bounce, S_L0, S_L1, S_L_PERM, l0, l1);
-        rng.two_d(bounce, S_B0, S_B1, S_B_PERM, b0, b1);
-        const float lc = rng.one_d(bounce, S_LC, S_LC_PERM), bc = rng.one_d(bounce, S_BC, S_BC_PERM);
-        uint32_t l = f2u(lc * (float)sc.n_lights); // sample_one_light (integrator/mod.rs:108-110), no xN (Q2)
-        if (l > sc.n_lights - 1) l = sc.n_lights - 1;
-        const f3 li = estimate_direct<STATS>(sc, m, fr, wo, __ldg(&sc.lights[l]), l0, l1, b0, b1, bc, ref_shadow, rc, cnt, err);
-        illum = illum + throughput * li;
-
-        rng.two_d(bounce, S_P0, S_P1, S_P_PERM, q0, q1);
-        const float qc = rng.one_d(bounce, S_PC, S_PC_PERM);
-        f3 f, wi; float pdf; uint32_t sampled;
-        bsdf_sample(sc, m, fr, wo, BX_ALL, q0, q1, qc, f, wi, pdf, sampled);
-        if (black(f) || pdf == 0.0f) break;
-        specular_bounce = (sampled & BX_SPECULAR) != 0;
-        throughput = throughput * f * fabsf(dot3(wi, fr.n)) / pdf;
-        if (bounce > sc.min_depth) { // Russian roulette (path.rs:97-104), probability may exceed 1 (Q8)
-            const float lum = 0.2126f * throughput.x + 0.7152f * throughput.y + 0.0722f * throughput.z;
-            const float cont = fmaxf(0.5f, lum);
-            if (unit_f32(rng.draw(S_RR + bounce)) > cont) break;
-            throughput = throughput / cont;
+        if (o.ds.has_mis) {
+            Ray mr; mr.o = o.org; mr.d = o.ds.mis_d; mr.tmin = 0.001f; mr.tmax = finf();
+            HitRec mh;
+            rc.mis++;
+            if (scene_trace<STATS>(sc, mr, mh, false, cnt, err)) mis_ok = mis_sees_light(sc, o.org, o.ds.mis_d, o.light, mh.inst, mh.t);
         }
-        if (bounce == sc.max_depth) break;
-        ray.o = fr.p; ray.d = unit(wi); ray.tmin = 0.001f; ray.tmax = finf(); // ray.child + min_t
+        illum = illum + o.t_before * direct_resolve(o.ds.a, o.ds.b, occluded, mis_ok);
+        throughput = o.throughput;
+        specular_bounce = o.specular;
+        if (o.terminate) break;
+        ray.o = o.org; ray.d = o.next_d; ray.tmin = 0.001f; ray.tmax = finf();
         rc.cont++;
         if (!scene_trace<STATS>(sc, ray, hit, false, cnt, err)) break;
         surface_at(sc, ray, hit, s);
@@ -965,6 +1022,32 @@ __device__ __forceinline__ void flush_stats(DStats* st, const RayCounts& rc, con
         unsigned long long x = v[i];
         for (int o = 16; o > 0; o >>= 1) x += __shfl_xor_sync(0xffffffffu, x, o);
         if ((threadIdx.x & 31) == 0 && x) atomicAdd(&reinterpret_cast<unsigned long long*>(st)[i], x);
+    }
+}
+
+// RenderTarget::write for one sample (render_target.rs:117-148) into the block's shared-memory tile
+__device__ __forceinline__ void splat_sample(const DScene& sc, float4* tile, const float* s_table, int T, int tx0, int ty0, int x_lo, int x_hi, int y_lo,
+                                             int y_hi, uint32_t px, uint32_t py, float sx, float sy, f3 c) {
+    const float img_x = sx - 0.5f, img_y = sy - 0.5f;
+    // conservative loop bounds around the footprint |d| * inv_w <= w; the exact test is inside
+    const int ry = (int)ceilf(sc.filter_h / sc.filter_inv_h) + 1, rx = (int)ceilf(sc.filter_w / sc.filter_inv_w) + 1;
+    const int iy0 = max(y_lo, (int)py - ry), iy1 = min(y_hi, (int)py + ry + 1);
+    const int ix0 = max(x_lo, (int)px - rx), ix1 = min(x_hi, (int)px + rx + 1);
+    for (int iy = iy0; iy <= iy1; ++iy) {
+        const float fy = fabsf((float)iy - img_y) * sc.filter_inv_h;
+        if (fy > sc.filter_h) continue; // sic: normalised distance vs width (A7)
+        const uint32_t fyi = min(f2u(fy * 16.0f), 15u);
+        for (int ix = ix0; ix <= ix1; ++ix) {
+            const float fx = fabsf((float)ix - img_x) * sc.filter_inv_w;
+            if (fx > sc.filter_w) continue;
+            const uint32_t fxi = min(f2u(fx * 16.0f), 15u);
+            const float wgt = s_table[fyi * 16 + fxi];
+            float* t = reinterpret_cast<float*>(&tile[(iy - ty0) * T + (ix - tx0)]);
+            atomicAdd(t + 0, wgt * c.x);
+            atomicAdd(t + 1, wgt * c.y);
+            atomicAdd(t + 2, wgt * c.z);
+            atomicAdd(t + 3, wgt);
+        }
     }
 }
 
@@ -1021,28 +1104,7 @@ __global__ void __launch_bounds__(RENDER_THREADS) k_render(const __grid_constant
                 trb_sample* out = reinterpret_cast<trb_sample*>(rp.samples_out) + ((size_t)item * 64 + pix) * rp.sample_count + (si - rp.sample_first);
                 out->x = sx; out->y = sy; out->r = c.x; out->g = c.y; out->b = c.z;
             } else {
-                // RenderTarget::write per sample (render_target.rs:117-148)
-                const float img_x = sx - 0.5f, img_y = sy - 0.5f;
-                // conservative loop bounds around the footprint |d| * inv_w <= w; the exact test is inside
-                const int ry = (int)ceilf(sc.filter_h / sc.filter_inv_h) + 1, rx = (int)ceilf(sc.filter_w / sc.filter_inv_w) + 1;
-                const int iy0 = max(y_lo, (int)py - ry), iy1 = min(y_hi, (int)py + ry + 1);
-                const int ix0 = max(x_lo, (int)px - rx), ix1 = min(x_hi, (int)px + rx + 1);
-                for (int iy = iy0; iy <= iy1; ++iy) {
-                    const float fy = fabsf((float)iy - img_y) * sc.filter_inv_h;
-                    if (fy > sc.filter_h) continue; // sic: normalised distance vs width (A7)
-                    const uint32_t fyi = min(f2u(fy * 16.0f), 15u);
-                    for (int ix = ix0; ix <= ix1; ++ix) {
-                        const float fx = fabsf((float)ix - img_x) * sc.filter_inv_w;
-                        if (fx > sc.filter_w) continue;
-                        const uint32_t fxi = min(f2u(fx * 16.0f), 15u);
-                        const float wgt = s_table[fyi * 16 + fxi];
-                        float* t = reinterpret_cast<float*>(&tile[(iy - ty0) * T + (ix - tx0)]);
-                        atomicAdd(t + 0, wgt * c.x);
-                        atomicAdd(t + 1, wgt * c.y);
-                        atomicAdd(t + 2, wgt * c.z);
-                        atomicAdd(t + 3, wgt);
-                    }
-                }
+                splat_sample(sc, tile, s_table, T, tx0, ty0, x_lo, x_hi, y_lo, y_hi, px, py, sx, sy, c);
             }
         }
         if (MODE == 0) {
@@ -1058,6 +1120,276 @@ __global__ void __launch_bounds__(RENDER_THREADS) k_render(const __grid_constant
         }
     }
     if (rp.stats) flush_stats(rp.stats, rc, cnt, my_samples, STATS);
+}
+
+// ==========================================================================================
+// Wavefront execution of the same path (DESIGN.md "Execution shape"). A pass of P camera samples
+// lives in HBM as structure-of-arrays path state; per bounce round r:
+//     k_wf_trace(r)  one thread per queued ray (continuation / shadow / MIS), lean registers, persistent
+//                    warps that fetch 32 rays at a time from the round's queues
+//     k_wf_shade(r)  one thread per live path: folds the previous bounce's shadow/MIS results into the
+//                    radiance (direct_resolve), then shades the new vertex (shade_bounce) and queues up to
+//                    three rays that all start at the vertex
+// and finally k_wf_film splats each 8x8 block's samples through shared memory. Every camera sample
+// performs exactly the operations of radiance_of_sample(), so results are bit-identical to the
+// megakernel and to the oracle whatever the scheduling.
+// ==========================================================================================
+struct WfState {
+    float4* org;     // (vertex = origin of this round's rays, flags)
+    float4* cont;    // (continuation / primary direction, hit t)
+    uint4* hit;      // continuation hit: (inst, prim, b1, b2)
+    float4* shadow;  // (shadow segment, occluded flag)
+    float4* mis;     // (MIS direction, hit t)
+    float4* a;       // (light-sample term A, MIS hit instance)
+    float4* b;       // (BSDF-sample term B, sampled light instance)
+    float4* tprev;   // throughput multiplying this bounce's direct light
+    float4* thr;     // path throughput
+    float4* illum;   // radiance so far
+    float4* ng;      // first hit's geometric normal (Q1)
+    float4* rad;     // finished, clamped radiance per sample (film mode)
+    uint32_t* q_active[2];
+    uint32_t* q_cont; uint32_t* q_shadow; uint32_t* q_mis;
+    uint32_t* counters; // per round: WF_CNT words
+    uint32_t n_paths;
+};
+enum { WF_N_ACTIVE = 0, WF_N_CONT = 1, WF_N_SHADOW = 2, WF_N_MIS = 3, WF_TRACE_HEAD = 4, WF_SHADE_HEAD = 5, WF_CNT = 8 };
+enum { WF_F_SPECULAR = 1u, WF_F_TERMINATE = 2u, WF_F_SHADOW = 4u, WF_F_MIS = 8u };
+
+// sample index p -> block item, pixel, sample (the canonical order of trb_camera_rays / trb_render_samples)
+struct SampleId { uint32_t item, pix, si, px, py, pixel; };
+__device__ __forceinline__ SampleId sample_id(const DScene& sc, const RenderParams& rp, uint32_t p) {
+    SampleId id;
+    const uint32_t s = p % rp.sample_count, q = p / rp.sample_count;
+    id.pix = q & 63; id.item = q >> 6; id.si = rp.sample_first + s;
+    const uint2 blk = rp.blocks[id.item];
+    id.px = blk.x * 8 + (id.pix & 7); id.py = blk.y * 8 + (id.pix >> 3);
+    id.pixel = id.py * sc.width + id.px;
+    return id;
+}
+__device__ __forceinline__ void sample_position(const RenderParams& rp, const PixelStreams& ps, const SampleId& id, float& sx, float& sy, float& tm) {
+    const uint32_t ip = permute_index(id.si, rp.spp, ps.kpos);
+    sx = ld_vdc(ip, ps.scr0) + (float)id.px;
+    sy = ld_sobol(ip, ps.scr1) + (float)id.py;
+    tm = ld_vdc(permute_index(id.si, rp.spp, ps.ktime), ps.scrt);
+}
+
+// warp-aggregated append: every lane of the warp must call it
+__device__ __forceinline__ void wf_push(uint32_t* q, uint32_t* counter, bool want, uint32_t value) {
+    const unsigned mask = __ballot_sync(0xffffffffu, want);
+    if (mask == 0) return;
+    const int lane = threadIdx.x & 31, leader = __ffs(mask) - 1;
+    uint32_t base = 0;
+    if (lane == leader) base = atomicAdd(counter, (uint32_t)__popc(mask));
+    base = __shfl_sync(0xffffffffu, base, leader);
+    if (want) q[base + __popc(mask & ((1u << lane) - 1u))] = value;
+}
+
+__global__ void __launch_bounds__(256) k_wf_generate(const __grid_constant__ DScene sc, const __grid_constant__ RenderParams rp, const __grid_constant__ WfState wf) {
+    const uint32_t n = wf.n_paths;
+    for (uint32_t p = blockIdx.x * blockDim.x + threadIdx.x; p < n; p += gridDim.x * blockDim.x) {
+        const SampleId id = sample_id(sc, rp, p);
+        const PixelStreams ps = pixel_streams(rp.seed, id.pixel);
+        float sx, sy, tm;
+        sample_position(rp, ps, id, sx, sy, tm);
+        Ray ray;
+        camera_ray(sc, sx, sy, tm, ray);
+        wf.org[p] = make_float4(ray.o.x, ray.o.y, ray.o.z, __uint_as_float(0u));
+        wf.cont[p] = make_float4(ray.d.x, ray.d.y, ray.d.z, finf());
+        wf.thr[p] = make_float4(1.0f, 1.0f, 1.0f, 0.0f);
+        wf.illum[p] = make_float4(0.0f, 0.0f, 0.0f, 0.0f);
+        wf.q_cont[p] = p;
+    }
+    if (blockIdx.x == 0 && threadIdx.x == 0) {
+        wf.counters[WF_N_ACTIVE] = n; wf.counters[WF_N_CONT] = n;
+        if (rp.stats) { atomicAdd(&rp.stats->camera_samples, (unsigned long long)n); }
+    }
+}
+
+// Trace round r: the rays queued by shade round r-1 (round 0: the primary rays).
+template <bool STATS>
+__global__ void __launch_bounds__(128) k_wf_trace(const __grid_constant__ DScene sc, const __grid_constant__ RenderParams rp, const __grid_constant__ WfState wf,
+                                                   uint32_t round, uint32_t flags) {
+    uint32_t* cnt_r = wf.counters + round * WF_CNT;
+    const uint32_t n_cont = cnt_r[WF_N_CONT], n_shadow = cnt_r[WF_N_SHADOW], n_mis = cnt_r[WF_N_MIS];
+    const uint32_t total = n_cont + n_shadow + n_mis;
+    const bool shadow_any = (flags & 4u) == 0; // TRB_RENDER_REFERENCE_SHADOW clears it
+    const int lane = threadIdx.x & 31;
+    Cnt cnt = {0, 0, 0};
+    for (;;) {
+        uint32_t base = 0;
+        if (lane == 0) base = atomicAdd(&cnt_r[WF_TRACE_HEAD], 32u);
+        base = __shfl_sync(0xffffffffu, base, 0);
+        if (base >= total) break;
+        const uint32_t i = base + lane;
+        if (i < total) {
+            int type; uint32_t p;
+            if (i < n_cont) { type = 0; p = wf.q_cont[i]; }
+            else if (i < n_cont + n_shadow) { type = 1; p = wf.q_shadow[i - n_cont]; }
+            else { type = 2; p = wf.q_mis[i - n_cont - n_shadow]; }
+            const float4 o4 = wf.org[p];
+            const float4 d4 = type == 0 ? wf.cont[p] : (type == 1 ? wf.shadow[p] : wf.mis[p]);
+            Ray ray; ray.o = mk(o4.x, o4.y, o4.z); ray.d = mk(d4.x, d4.y, d4.z);
+            ray.tmin = (type == 0 && round == 0) ? 0.0f : 0.001f;
+            ray.tmax = type == 1 ? 0.999f : finf();
+            HitRec h;
+            const bool hit = scene_trace<STATS>(sc, ray, h, type == 1 && shadow_any, cnt, rp.error_flag);
+            if (type == 0) {
+                wf.cont[p] = make_float4(d4.x, d4.y, d4.z, ray.tmax);
+                wf.hit[p] = make_uint4(hit ? h.inst : TRB_MISS, h.prim, __float_as_uint(h.b1), __float_as_uint(h.b2));
+            } else if (type == 1) {
+                wf.shadow[p] = make_float4(d4.x, d4.y, d4.z, __uint_as_float(hit ? 1u : 0u));
+            } else {
+                wf.mis[p] = make_float4(d4.x, d4.y, d4.z, ray.tmax);
+                float4 a4 = wf.a[p];
+                a4.w = __uint_as_float(hit ? h.inst : TRB_MISS);
+                wf.a[p] = a4;
+            }
+        }
+    }
+    if (rp.stats) {
+        if (STATS) {
+            unsigned long long v[3] = {cnt.node, cnt.tri, cnt.inst};
+            for (int k = 0; k < 3; ++k) {
+                unsigned long long x = v[k];
+                for (int o = 16; o > 0; o >>= 1) x += __shfl_xor_sync(0xffffffffu, x, o);
+                if (lane == 0 && x) atomicAdd(&rp.stats->node_tests + k, x);
+            }
+        }
+        if (blockIdx.x == 0 && threadIdx.x == 0) {
+            atomicAdd(round == 0 ? &rp.stats->rays_primary : &rp.stats->rays_continuation, (unsigned long long)n_cont);
+            atomicAdd(&rp.stats->rays_shadow, (unsigned long long)n_shadow);
+            atomicAdd(&rp.stats->rays_mis, (unsigned long long)n_mis);
+        }
+    }
+}
+
+// Shade round r (== bounce r of every live path). MODE 0: finished samples go to wf.rad; MODE 1: to trb_sample records.
+template <int MODE>
+__global__ void __launch_bounds__(128) k_wf_shade(const __grid_constant__ DScene sc, const __grid_constant__ RenderParams rp, const __grid_constant__ WfState wf,
+                                                   uint32_t round) {
+    uint32_t* cnt_r = wf.counters + round * WF_CNT;
+    uint32_t* cnt_n = wf.counters + (round + 1) * WF_CNT;
+    const uint32_t n = cnt_r[WF_N_ACTIVE];
+    const uint32_t* __restrict__ act = wf.q_active[round & 1];
+    uint32_t* act_next = wf.q_active[(round + 1) & 1];
+    const int lane = threadIdx.x & 31;
+    for (;;) {
+        uint32_t base = 0;
+        if (lane == 0) base = atomicAdd(&cnt_r[WF_SHADE_HEAD], 32u);
+        base = __shfl_sync(0xffffffffu, base, 0);
+        if (base >= n) break;
+        const uint32_t i = base + lane;
+        const bool valid = i < n;
+        uint32_t p = 0;
+        bool push_cont = false, push_shadow = false, push_mis = false, push_active = false;
+        if (valid) {
+            p = round == 0 ? i : act[i];
+            const float4 o4 = wf.org[p];
+            const uint32_t fl = __float_as_uint(o4.w);
+            const f3 org = mk(o4.x, o4.y, o4.z);
+            float4 il4 = wf.illum[p];
+            f3 illum = mk(il4.x, il4.y, il4.z);
+            bool done = false;
+            if (round > 0) { // fold in the direct light of the previous bounce (estimate_direct's two ray results)
+                const float4 a4 = wf.a[p], b4 = wf.b[p], t4 = wf.tprev[p];
+                bool occluded = false, mis_ok = false;
+                if (fl & WF_F_SHADOW) occluded = __float_as_uint(wf.shadow[p].w) != 0u;
+                if (fl & WF_F_MIS) {
+                    const float4 m4 = wf.mis[p];
+                    mis_ok = mis_sees_light(sc, org, mk(m4.x, m4.y, m4.z), __float_as_uint(b4.w), __float_as_uint(a4.w), m4.w);
+                }
+                illum = illum + mk(t4.x, t4.y, t4.z) * direct_resolve(mk(a4.x, a4.y, a4.z), mk(b4.x, b4.y, b4.z), occluded, mis_ok);
+                done = (fl & WF_F_TERMINATE) != 0;
+            }
+            if (!done) {
+                const float4 c4 = wf.cont[p];
+                const uint4 h4 = wf.hit[p];
+                if (h4.x == TRB_MISS) done = true; // primary miss: black sample (multithreaded.rs:101-102); later: `None => break`
+                else {
+                    Ray ray; ray.o = org; ray.d = mk(c4.x, c4.y, c4.z); ray.tmin = 0.0f; ray.tmax = c4.w;
+                    HitRec h; h.t = c4.w; h.inst = h4.x; h.prim = h4.y; h.b1 = __uint_as_float(h4.z); h.b2 = __uint_as_float(h4.w);
+                    Surf s;
+                    surface_at(sc, ray, h, s);
+                    f3 first_ng;
+                    if (round == 0) { first_ng = s.ng; wf.ng[p] = make_float4(s.ng.x, s.ng.y, s.ng.z, 0.0f); }
+                    else { const float4 n4 = wf.ng[p]; first_ng = mk(n4.x, n4.y, n4.z); }
+                    const SampleId id = sample_id(sc, rp, p);
+                    const uint32_t hs = rng_absorb(rng_absorb(rng_seed(rp.seed), id.pixel), id.si);
+                    const float4 th4 = wf.thr[p];
+                    BounceOut o;
+                    shade_bounce(sc, s, h.inst, ray.d, first_ng, round, (fl & WF_F_SPECULAR) != 0, hs, mk(th4.x, th4.y, th4.z), illum, o);
+                    const uint32_t nf = (o.specular ? WF_F_SPECULAR : 0u) | (o.terminate ? WF_F_TERMINATE : 0u) | (o.ds.has_shadow ? WF_F_SHADOW : 0u) |
+                                        (o.ds.has_mis ? WF_F_MIS : 0u);
+                    push_cont = !o.terminate; push_shadow = o.ds.has_shadow; push_mis = o.ds.has_mis;
+                    push_active = push_cont || push_shadow || push_mis;
+                    if (push_active) {
+                        wf.org[p] = make_float4(o.org.x, o.org.y, o.org.z, __uint_as_float(nf));
+                        if (push_cont) wf.cont[p] = make_float4(o.next_d.x, o.next_d.y, o.next_d.z, finf());
+                        if (push_shadow) wf.shadow[p] = make_float4(o.ds.shadow_d.x, o.ds.shadow_d.y, o.ds.shadow_d.z, 0.0f);
+                        if (push_mis) wf.mis[p] = make_float4(o.ds.mis_d.x, o.ds.mis_d.y, o.ds.mis_d.z, finf());
+                        wf.a[p] = make_float4(o.ds.a.x, o.ds.a.y, o.ds.a.z, __uint_as_float(TRB_MISS));
+                        wf.b[p] = make_float4(o.ds.b.x, o.ds.b.y, o.ds.b.z, __uint_as_float(o.light));
+                        wf.tprev[p] = make_float4(o.t_before.x, o.t_before.y, o.t_before.z, 0.0f);
+                        wf.thr[p] = make_float4(o.throughput.x, o.throughput.y, o.throughput.z, 0.0f);
+                        wf.illum[p] = make_float4(illum.x, illum.y, illum.z, 0.0f);
+                    } else done = true; // nothing pending: direct light of this bounce is zero, the path ends here
+                }
+            }
+            if (done) { // per-sample clamp (multithreaded.rs:99, Q12) and hand-over to the film
+                const f3 c = mk(clampf(illum.x, 0.0f, 1.0f), clampf(illum.y, 0.0f, 1.0f), clampf(illum.z, 0.0f, 1.0f));
+                if (MODE == 0) wf.rad[p] = make_float4(c.x, c.y, c.z, 1.0f);
+                else {
+                    const SampleId id = sample_id(sc, rp, p);
+                    const PixelStreams ps = pixel_streams(rp.seed, id.pixel);
+                    float sx, sy, tm;
+                    sample_position(rp, ps, id, sx, sy, tm);
+                    trb_sample* out = reinterpret_cast<trb_sample*>(rp.samples_out) + p;
+                    out->x = sx; out->y = sy; out->r = c.x; out->g = c.y; out->b = c.z;
+                }
+            }
+        }
+        wf_push(wf.q_cont, &cnt_n[WF_N_CONT], push_cont, p);
+        wf_push(wf.q_shadow, &cnt_n[WF_N_SHADOW], push_shadow, p);
+        wf_push(wf.q_mis, &cnt_n[WF_N_MIS], push_mis, p);
+        wf_push(act_next, &cnt_n[WF_N_ACTIVE], push_active, p);
+    }
+}
+
+// RenderTarget::write for a whole pass: one CTA per 8x8 block, footprint accumulated in shared memory.
+__global__ void __launch_bounds__(RENDER_THREADS) k_wf_film(const __grid_constant__ DScene sc, const __grid_constant__ RenderParams rp, const __grid_constant__ WfState wf) {
+    extern __shared__ float4 tile[];
+    __shared__ float s_table[256];
+    const int T = 9 + 2 * max(sc.fpw_x, sc.fpw_y);
+    for (int i = threadIdx.x; i < 256; i += RENDER_THREADS) s_table[i] = sc.filter_table[i];
+    const uint32_t pix = threadIdx.x & 63, lane_s = threadIdx.x >> 6;
+    for (uint32_t item = blockIdx.x; item < rp.n_blocks; item += gridDim.x) {
+        __syncthreads();
+        for (int i = threadIdx.x; i < T * T; i += RENDER_THREADS) tile[i] = make_float4(0.f, 0.f, 0.f, 0.f);
+        __syncthreads();
+        const uint2 blk = rp.blocks[item];
+        const uint32_t bx = blk.x * 8, by = blk.y * 8;
+        SampleId id; id.item = item; id.pix = pix; id.px = bx + (pix & 7); id.py = by + (pix >> 3); id.pixel = id.py * sc.width + id.px;
+        const PixelStreams ps = pixel_streams(rp.seed, id.pixel);
+        const int x_lo = max((int)bx - sc.fpw_x, 0), x_hi = min((int)bx + 8 + sc.fpw_x, (int)sc.width - 1);
+        const int y_lo = max((int)by - sc.fpw_y, 0), y_hi = min((int)by + 8 + sc.fpw_y, (int)sc.height - 1);
+        const int tx0 = (int)bx - sc.fpw_x, ty0 = (int)by - sc.fpw_y;
+        for (uint32_t s = lane_s; s < rp.sample_count; s += 2) {
+            id.si = rp.sample_first + s;
+            float sx, sy, tm;
+            sample_position(rp, ps, id, sx, sy, tm);
+            const float4 c4 = wf.rad[((size_t)item * 64 + pix) * rp.sample_count + s];
+            splat_sample(sc, tile, s_table, T, tx0, ty0, x_lo, x_hi, y_lo, y_hi, id.px, id.py, sx, sy, mk(c4.x, c4.y, c4.z));
+        }
+        __syncthreads();
+        for (int i = threadIdx.x; i < T * T; i += RENDER_THREADS) {
+            const int ix = tx0 + i % T, iy = ty0 + i / T;
+            if (ix < x_lo || ix > x_hi || iy < y_lo || iy > y_hi) continue;
+            const float4 v = tile[i];
+            if (v.w == 0.0f && v.x == 0.0f && v.y == 0.0f && v.z == 0.0f) continue;
+            float* dst = reinterpret_cast<float*>(rp.film + (size_t)iy * sc.width + ix);
+            atomicAdd(dst + 0, v.x); atomicAdd(dst + 1, v.y); atomicAdd(dst + 2, v.z); atomicAdd(dst + 3, v.w);
+        }
+    }
 }
 
 // LowDiscrepancy::get_samples + get_samples_1d + Camera::generate_ray only (parity of S2 / C)
