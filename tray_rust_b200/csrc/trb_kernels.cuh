@@ -165,115 +165,134 @@ constexpr uint32_t ST_RETURN = 0xfffffffeu;
 constexpr uint32_t ST_DONE = 0xffffffffu;
 constexpr int STACK_DEPTH = 96;
 
+// The traversal as an explicit state machine so that a warp can keep all lanes busy: scene_trace()
+// runs it to completion for one ray; the wavefront trace kernel refills finished lanes with new rays.
+struct TraceState {
+    f3 wo, wd, winv;      // world ray and 1/d (bvh.rs:84)
+    f3 o, d, inv;         // ray of the current level (world, or the mesh instance's object space)
+    bool nx, ny, nz;      // d < 0 per axis (bvh.rs:85)
+    const DNode* nodes;
+    const DTri* tris;
+    uint32_t level_inst;  // instance whose mesh is being traversed, TRB_MISS at the top level
+    float tmin, tmax;
+    int sp;
+    uint32_t cur;
+    bool found, any_hit;
+    uint32_t h_inst, h_prim;
+    float h_b1, h_b2;
+};
+__device__ __forceinline__ void trace_init(const DScene& sc, TraceState& t, const Ray& ray, bool any_hit) {
+    t.wo = ray.o; t.wd = ray.d;
+    t.winv = mk(1.0f / ray.d.x, 1.0f / ray.d.y, 1.0f / ray.d.z);
+    t.o = t.wo; t.d = t.wd; t.inv = t.winv;
+    t.nx = t.d.x < 0.0f; t.ny = t.d.y < 0.0f; t.nz = t.d.z < 0.0f;
+    t.nodes = sc.tlas; t.tris = nullptr; t.level_inst = TRB_MISS;
+    t.tmin = ray.tmin; t.tmax = ray.tmax;
+    t.sp = 0; t.cur = 0; t.found = false; t.any_hit = any_hit;
+    t.h_inst = TRB_MISS; t.h_prim = 0; t.h_b1 = 0.0f; t.h_b2 = 0.0f;
+}
+// One transition: visit a node (box test; descend / expand a leaf), leave a mesh, or test one instance.
 template <bool STATS>
-__device__ __noinline__ bool scene_trace(const DScene& sc, Ray& ray, HitRec& hit, bool any_hit, Cnt& cnt, int* err) {
-    const f3 wo = ray.o, wd = ray.d;
-    const f3 winv = mk(1.0f / wd.x, 1.0f / wd.y, 1.0f / wd.z); // bvh.rs:84
-    f3 o = wo, d = wd, inv = winv;
-    bool nx = d.x < 0.0f, ny = d.y < 0.0f, nz = d.z < 0.0f;   // bvh.rs:85
-    const DNode* __restrict__ nodes = sc.tlas;
-    const DTri* __restrict__ tris = nullptr;
-    uint32_t level_inst = TRB_MISS; // instance whose mesh is being traversed, TRB_MISS at the top level
-    const float tmin = ray.tmin;
-    float tmax = ray.tmax;
-    uint32_t stack[STACK_DEPTH];
-    int sp = 0;
-    uint32_t cur = 0;
-    bool found = false;
-    hit.inst = TRB_MISS; hit.prim = 0; hit.b1 = 0.0f; hit.b2 = 0.0f;
-    while (cur != ST_DONE) {
-        uint32_t next;
-        if (!(cur & ST_SPECIAL)) {
-            // ---- visit a node of the current level ----
-            const float4 lo = __ldg(&nodes[cur].lo), hi = __ldg(&nodes[cur].hi);
-            if (STATS) cnt.node++;
-            const bool bh = box_hit(lo, hi, o, inv, nx, ny, nz, tmin, tmax);
-            const uint32_t a = __float_as_uint(lo.w), b = __float_as_uint(hi.w);
-            if (bh && !(b & LEAF_BIT)) {
-                // interior: descend to the near child by the sign of d[axis], push the other (bvh.rs:105-119)
-                const bool neg = b == 0 ? nx : (b == 1 ? ny : nz);
-                if (sp >= STACK_DEPTH - 6) { *err = 1; sp = 0; next = ST_DONE; }
-                else { stack[sp++] = neg ? cur + 1 : a; next = neg ? a : cur + 1; }
-            } else {
-                if (bh) {
-                    const uint32_t n = b & ~LEAF_BIT;
-                    if (level_inst == TRB_MISS) {
-                        for (uint32_t k = a + n; k-- > a;) stack[sp++] = ST_SPECIAL | k; // pops as a, a+1, ...
-                    } else {
-                        for (uint32_t k = a; k < a + n; ++k) {
-                            const float4 v0 = __ldg(&tris[k].v0), q0 = __ldg(&tris[k].e0), q1 = __ldg(&tris[k].e1);
-                            if (STATS) cnt.tri++;
-                            const f3 e0 = mk(q0.x, q0.y, q0.z), e1 = mk(q1.x, q1.y, q1.z);
-                            const f3 s0 = cross3(d, e1);
-                            const float dd = dot3(s0, e0);
-                            const float div = 1.0f / dd;
-                            const f3 dv = o - mk(v0.x, v0.y, v0.z);
-                            const float b1 = dot3(dv, s0) * div;
-                            const f3 s1 = cross3(dv, e0);
-                            const float b2 = dot3(d, s1) * div;
-                            const float t = dot3(e1, s1) * div;
-                            // mesh.rs:142-168: d == 0 -> miss; b1 in [0,1]; b2 >= 0 and b1+b2 <= 1; t in [min_t, max_t]
-                            const bool ok = dd != 0.0f && !(b1 < 0.0f || b1 > 1.0f) && !(b2 < 0.0f || b1 + b2 > 1.0f) && !(t < tmin || t > tmax);
-                            if (ok) { // last accepted wins, inclusive compare (Q9)
-                                tmax = t;
-                                hit.prim = __float_as_uint(v0.w); hit.b1 = b1; hit.b2 = b2; hit.inst = level_inst;
-                                found = true;
-                                if (any_hit) sp = 0;
-                            }
+__device__ __forceinline__ void trace_step(const DScene& sc, TraceState& t, uint32_t* stack, Cnt& cnt, int* err) {
+    const uint32_t cur = t.cur;
+    uint32_t next;
+    if (!(cur & ST_SPECIAL)) {
+        const float4 lo = __ldg(&t.nodes[cur].lo), hi = __ldg(&t.nodes[cur].hi);
+        if (STATS) cnt.node++;
+        const bool bh = box_hit(lo, hi, t.o, t.inv, t.nx, t.ny, t.nz, t.tmin, t.tmax);
+        const uint32_t a = __float_as_uint(lo.w), b = __float_as_uint(hi.w);
+        if (bh && !(b & LEAF_BIT)) {
+            // interior: descend to the near child by the sign of d[axis], push the other (bvh.rs:105-119)
+            const bool neg = b == 0 ? t.nx : (b == 1 ? t.ny : t.nz);
+            if (t.sp >= STACK_DEPTH - 6) { *err = 1; t.sp = 0; next = ST_DONE; }
+            else { stack[t.sp++] = neg ? cur + 1 : a; next = neg ? a : cur + 1; }
+        } else {
+            if (bh) {
+                const uint32_t n = b & ~LEAF_BIT;
+                if (t.level_inst == TRB_MISS) {
+                    for (uint32_t k = a + n; k-- > a;) stack[t.sp++] = ST_SPECIAL | k; // pops as a, a+1, ...
+                } else {
+                    const DTri* __restrict__ tris = t.tris;
+                    for (uint32_t k = a; k < a + n; ++k) {
+                        const float4 v0 = __ldg(&tris[k].v0), q0 = __ldg(&tris[k].e0), q1 = __ldg(&tris[k].e1);
+                        if (STATS) cnt.tri++;
+                        const f3 e0 = mk(q0.x, q0.y, q0.z), e1 = mk(q1.x, q1.y, q1.z);
+                        const f3 s0 = cross3(t.d, e1);
+                        const float dd = dot3(s0, e0);
+                        const float div = 1.0f / dd;
+                        const f3 dv = t.o - mk(v0.x, v0.y, v0.z);
+                        const float b1 = dot3(dv, s0) * div;
+                        const f3 s1 = cross3(dv, e0);
+                        const float b2 = dot3(t.d, s1) * div;
+                        const float tt = dot3(e1, s1) * div;
+                        // mesh.rs:142-168: d == 0 -> miss; b1 in [0,1]; b2 >= 0 and b1+b2 <= 1; t in [min_t, max_t]
+                        const bool ok = dd != 0.0f && !(b1 < 0.0f || b1 > 1.0f) && !(b2 < 0.0f || b1 + b2 > 1.0f) && !(tt < t.tmin || tt > t.tmax);
+                        if (ok) { // last accepted wins, inclusive compare (Q9)
+                            t.tmax = tt;
+                            t.h_prim = __float_as_uint(v0.w); t.h_b1 = b1; t.h_b2 = b2; t.h_inst = t.level_inst;
+                            t.found = true;
+                            if (t.any_hit) t.sp = 0;
                         }
                     }
                 }
-                next = sp > 0 ? stack[--sp] : ST_DONE;
             }
-        } else if (cur == ST_RETURN) {
-            // ---- leave the mesh: back to the world ray ----
-            o = wo; d = wd; inv = winv;
-            nx = d.x < 0.0f; ny = d.y < 0.0f; nz = d.z < 0.0f;
-            nodes = sc.tlas; level_inst = TRB_MISS;
-            next = sp > 0 ? stack[--sp] : ST_DONE;
-        } else {
-            // ---- Instance::intersect for one entry of a TLAS leaf ----
-            const uint32_t ii = __ldg(&sc.tlas_order[cur & ~ST_SPECIAL]);
-            const DInstance& in = sc.instances[ii];
-            if (STATS) cnt.inst++;
-            const uint32_t kind = __ldg(&in.kind), shape = __ldg(&in.shape);
-            next = ST_DONE;
-            bool enter = false;
-            if (kind != TRB_INST_EMITTER_POINT) { // point lights never intersect (emitter.rs:119-120)
-                float m[16];
-                load_xf(in.inv, m);
-                const f3 lo_ = xf_point(m, wo), ld_ = xf_vector(m, wd); // inv_mul_ray: direction not renormalised
-                if (shape == TRB_SHAPE_MESH) {
-                    const DMesh& me = sc.meshes[__ldg(&in.mesh)];
-                    o = lo_; d = ld_;
-                    inv = mk(1.0f / d.x, 1.0f / d.y, 1.0f / d.z);
-                    nx = d.x < 0.0f; ny = d.y < 0.0f; nz = d.z < 0.0f;
-                    nodes = me.nodes; tris = me.tris; level_inst = ii;
-                    stack[sp++] = ST_RETURN;
-                    next = 0; // root of the mesh BVH
-                    enter = true;
-                } else {
-                    const float p0 = __ldg(&in.p0), p1 = __ldg(&in.p1);
-                    float t = tmax;
-                    bool h;
-                    if (shape == TRB_SHAPE_SPHERE) h = sphere_t(p0, lo_, ld_, tmin, t);
-                    else if (shape == TRB_SHAPE_DISK) h = disk_t(p0, p1, lo_, ld_, tmin, t);
-                    else h = rect_t(p0, p1, lo_, ld_, tmin, t);
-                    if (h) {
-                        tmax = t; // receiver.rs:36
-                        hit.inst = ii; hit.prim = 0; hit.b1 = 0.0f; hit.b2 = 0.0f;
-                        found = true;
-                        if (any_hit) sp = 0;
-                    }
+            next = t.sp > 0 ? stack[--t.sp] : ST_DONE;
+        }
+    } else if (cur == ST_RETURN) {
+        t.o = t.wo; t.d = t.wd; t.inv = t.winv;
+        t.nx = t.d.x < 0.0f; t.ny = t.d.y < 0.0f; t.nz = t.d.z < 0.0f;
+        t.nodes = sc.tlas; t.level_inst = TRB_MISS;
+        next = t.sp > 0 ? stack[--t.sp] : ST_DONE;
+    } else {
+        // Instance::intersect for one entry of a TLAS leaf
+        const uint32_t ii = __ldg(&sc.tlas_order[cur & ~ST_SPECIAL]);
+        const DInstance& in = sc.instances[ii];
+        if (STATS) cnt.inst++;
+        const uint32_t kind = __ldg(&in.kind), shape = __ldg(&in.shape);
+        next = ST_DONE;
+        bool enter = false;
+        if (kind != TRB_INST_EMITTER_POINT) { // point lights never intersect (emitter.rs:119-120)
+            float m[16];
+            load_xf(in.inv, m);
+            const f3 lo_ = xf_point(m, t.wo), ld_ = xf_vector(m, t.wd); // inv_mul_ray: direction not renormalised
+            if (shape == TRB_SHAPE_MESH) {
+                const DMesh& me = sc.meshes[__ldg(&in.mesh)];
+                t.o = lo_; t.d = ld_;
+                t.inv = mk(1.0f / ld_.x, 1.0f / ld_.y, 1.0f / ld_.z);
+                t.nx = ld_.x < 0.0f; t.ny = ld_.y < 0.0f; t.nz = ld_.z < 0.0f;
+                t.nodes = me.nodes; t.tris = me.tris; t.level_inst = ii;
+                stack[t.sp++] = ST_RETURN;
+                next = 0; // root of the mesh BVH
+                enter = true;
+            } else {
+                const float p0 = __ldg(&in.p0), p1 = __ldg(&in.p1);
+                float tt = t.tmax;
+                bool h;
+                if (shape == TRB_SHAPE_SPHERE) h = sphere_t(p0, lo_, ld_, t.tmin, tt);
+                else if (shape == TRB_SHAPE_DISK) h = disk_t(p0, p1, lo_, ld_, t.tmin, tt);
+                else h = rect_t(p0, p1, lo_, ld_, t.tmin, tt);
+                if (h) {
+                    t.tmax = tt; // receiver.rs:36
+                    t.h_inst = ii; t.h_prim = 0; t.h_b1 = 0.0f; t.h_b2 = 0.0f;
+                    t.found = true;
+                    if (t.any_hit) t.sp = 0;
                 }
             }
-            if (!enter) next = sp > 0 ? stack[--sp] : ST_DONE;
         }
-        cur = next;
+        if (!enter) next = t.sp > 0 ? stack[--t.sp] : ST_DONE;
     }
-    ray.tmax = tmax;
-    hit.t = tmax;
-    return found;
+    t.cur = next;
+}
+
+template <bool STATS>
+__device__ __noinline__ bool scene_trace(const DScene& sc, Ray& ray, HitRec& hit, bool any_hit, Cnt& cnt, int* err) {
+    TraceState t;
+    uint32_t stack[STACK_DEPTH];
+    trace_init(sc, t, ray, any_hit);
+    while (t.cur != ST_DONE) trace_step<STATS>(sc, t, stack, cnt, err);
+    ray.tmax = t.tmax;
+    hit.t = t.tmax; hit.inst = t.h_inst; hit.prim = t.h_prim; hit.b1 = t.h_b1; hit.b2 = t.h_b2;
+    return t.found;
 }
 
 // ------------------------------------------------------------------------------------------
@@ -1205,7 +1224,12 @@ __global__ void __launch_bounds__(256) k_wf_generate(const __grid_constant__ DSc
     }
 }
 
-// Trace round r: the rays queued by shade round r-1 (round 0: the primary rays).
+// Trace round r: the rays queued by shade round r-1 (round 0: the primary rays). Persistent warps: a lane
+// whose ray has finished writes its result and, once enough lanes of the warp are idle, the idle lanes
+// fetch new rays with one warp-aggregated atomic, so rays of very different lengths (an any-hit shadow
+// ray vs. a continuation ray crossing the whole mesh) do not leave the warp mostly empty.
+constexpr int WF_REFILL_IDLE = 8; // refill when at least this many lanes are idle
+
 template <bool STATS>
 __global__ void __launch_bounds__(128) k_wf_trace(const __grid_constant__ DScene sc, const __grid_constant__ RenderParams rp, const __grid_constant__ WfState wf,
                                                    uint32_t round, uint32_t flags) {
@@ -1214,36 +1238,62 @@ __global__ void __launch_bounds__(128) k_wf_trace(const __grid_constant__ DScene
     const uint32_t total = n_cont + n_shadow + n_mis;
     const bool shadow_any = (flags & 4u) == 0; // TRB_RENDER_REFERENCE_SHADOW clears it
     const int lane = threadIdx.x & 31;
+    const unsigned lt_mask = (1u << lane) - 1u;
     Cnt cnt = {0, 0, 0};
+    TraceState t;
+    uint32_t stack[STACK_DEPTH];
+    t.cur = ST_DONE;
+    bool have = false, exhausted = false;
+    uint32_t p = 0;
+    int type = 0;
     for (;;) {
-        uint32_t base = 0;
-        if (lane == 0) base = atomicAdd(&cnt_r[WF_TRACE_HEAD], 32u);
-        base = __shfl_sync(0xffffffffu, base, 0);
-        if (base >= total) break;
-        const uint32_t i = base + lane;
-        if (i < total) {
-            int type; uint32_t p;
-            if (i < n_cont) { type = 0; p = wf.q_cont[i]; }
-            else if (i < n_cont + n_shadow) { type = 1; p = wf.q_shadow[i - n_cont]; }
-            else { type = 2; p = wf.q_mis[i - n_cont - n_shadow]; }
-            const float4 o4 = wf.org[p];
-            const float4 d4 = type == 0 ? wf.cont[p] : (type == 1 ? wf.shadow[p] : wf.mis[p]);
-            Ray ray; ray.o = mk(o4.x, o4.y, o4.z); ray.d = mk(d4.x, d4.y, d4.z);
-            ray.tmin = (type == 0 && round == 0) ? 0.0f : 0.001f;
-            ray.tmax = type == 1 ? 0.999f : finf();
-            HitRec h;
-            const bool hit = scene_trace<STATS>(sc, ray, h, type == 1 && shadow_any, cnt, rp.error_flag);
+        // ---- retire finished rays ----
+        if (have && t.cur == ST_DONE) {
             if (type == 0) {
-                wf.cont[p] = make_float4(d4.x, d4.y, d4.z, ray.tmax);
-                wf.hit[p] = make_uint4(hit ? h.inst : TRB_MISS, h.prim, __float_as_uint(h.b1), __float_as_uint(h.b2));
+                wf.cont[p] = make_float4(t.wd.x, t.wd.y, t.wd.z, t.tmax);
+                wf.hit[p] = make_uint4(t.found ? t.h_inst : TRB_MISS, t.h_prim, __float_as_uint(t.h_b1), __float_as_uint(t.h_b2));
             } else if (type == 1) {
-                wf.shadow[p] = make_float4(d4.x, d4.y, d4.z, __uint_as_float(hit ? 1u : 0u));
+                wf.shadow[p] = make_float4(t.wd.x, t.wd.y, t.wd.z, __uint_as_float(t.found ? 1u : 0u));
             } else {
-                wf.mis[p] = make_float4(d4.x, d4.y, d4.z, ray.tmax);
+                wf.mis[p] = make_float4(t.wd.x, t.wd.y, t.wd.z, t.tmax);
                 float4 a4 = wf.a[p];
-                a4.w = __uint_as_float(hit ? h.inst : TRB_MISS);
+                a4.w = __uint_as_float(t.found ? t.h_inst : TRB_MISS);
                 wf.a[p] = a4;
             }
+            have = false;
+        }
+        // ---- refill idle lanes ----
+        const unsigned idle = __ballot_sync(0xffffffffu, !have);
+        if (idle != 0 && !exhausted && (__popc(idle) >= WF_REFILL_IDLE || idle == 0xffffffffu)) {
+            const int leader = __ffs(idle) - 1;
+            uint32_t base = 0;
+            if (lane == leader) base = atomicAdd(&cnt_r[WF_TRACE_HEAD], (uint32_t)__popc(idle));
+            base = __shfl_sync(0xffffffffu, base, leader);
+            if (base >= total) exhausted = true;
+            else if (!have) {
+                const uint32_t i = base + __popc(idle & lt_mask);
+                if (i < total) {
+                    if (i < n_cont) { type = 0; p = wf.q_cont[i]; }
+                    else if (i < n_cont + n_shadow) { type = 1; p = wf.q_shadow[i - n_cont]; }
+                    else { type = 2; p = wf.q_mis[i - n_cont - n_shadow]; }
+                    const float4 o4 = wf.org[p];
+                    const float4 d4 = type == 0 ? wf.cont[p] : (type == 1 ? wf.shadow[p] : wf.mis[p]);
+                    Ray ray; ray.o = mk(o4.x, o4.y, o4.z); ray.d = mk(d4.x, d4.y, d4.z);
+                    ray.tmin = (type == 0 && round == 0) ? 0.0f : 0.001f;
+                    ray.tmax = type == 1 ? 0.999f : finf();
+                    trace_init(sc, t, ray, type == 1 && shadow_any);
+                    have = true;
+                }
+            }
+        }
+        const unsigned busy0 = __ballot_sync(0xffffffffu, have);
+        if (busy0 == 0) { if (exhausted) break; else continue; }
+        // ---- traverse until enough lanes have finished ----
+        for (;;) {
+            if (have && t.cur != ST_DONE) trace_step<STATS>(sc, t, stack, cnt, rp.error_flag);
+            const unsigned running = __ballot_sync(0xffffffffu, have && t.cur != ST_DONE);
+            if (running == 0) break;
+            if (!exhausted && 32 - __popc(running) >= WF_REFILL_IDLE) break;
         }
     }
     if (rp.stats) {
