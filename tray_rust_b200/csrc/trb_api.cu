@@ -56,14 +56,36 @@ struct HostMesh {
 
 uint32_t pow2_ceil(uint32_t v) { uint32_t p = 1; while (p < v) p <<= 1; return p; }
 
-void pack_nodes(const std::vector<trb_bvh_node>& in, std::vector<trb::DNode>& out) {
-    out.resize(in.size());
+// Re-layout of the reference-order flat tree into child-pair records (trb_device.h DPair). Pure layout: no box,
+// child order or primitive order changes. Returns false if a leaf does not fit the 25-bit slot / 5-bit count fields.
+float bits_f(uint32_t u) { float f; std::memcpy(&f, &u, 4); return f; }
+bool pack_pairs(const std::vector<trb_bvh_node>& in, std::vector<trb::DPair>& out, trb::DBvh& hdr) {
+    std::vector<uint32_t> rec_of(in.size(), 0);
+    uint32_t n_rec = 0;
+    for (size_t i = 0; i < in.size(); ++i) if (!(in[i].b & TRB_BVH_LEAF)) rec_of[i] = n_rec++;
+    bool ok = n_rec < (1u << 30);
+    auto ref_of = [&](uint32_t i) -> uint32_t {
+        if (in[i].b & TRB_BVH_LEAF) {
+            const uint32_t cnt = in[i].b & ~TRB_BVH_LEAF, first = in[i].a;
+            if (cnt > 31 || first >= (1u << 25)) ok = false;
+            return trb::REF_LEAF | (cnt << 25) | first;
+        }
+        return trb::REF_INTERIOR | rec_of[i];
+    };
+    out.resize(n_rec);
     for (size_t i = 0; i < in.size(); ++i) {
-        out[i].lo = make_float4(in[i].bmin[0], in[i].bmin[1], in[i].bmin[2], 0.f);
-        out[i].hi = make_float4(in[i].bmax[0], in[i].bmax[1], in[i].bmax[2], 0.f);
-        std::memcpy(&out[i].lo.w, &in[i].a, 4);
-        std::memcpy(&out[i].hi.w, &in[i].b, 4);
+        if (in[i].b & TRB_BVH_LEAF) continue;
+        const trb_bvh_node& l = in[i + 1];
+        const trb_bvh_node& r = in[in[i].a];
+        trb::DPair& p = out[rec_of[i]];
+        p.l_lo = make_float4(l.bmin[0], l.bmin[1], l.bmin[2], bits_f(ref_of((uint32_t)i + 1)));
+        p.l_hi = make_float4(l.bmax[0], l.bmax[1], l.bmax[2], bits_f(ref_of(in[i].a)));
+        p.r_lo = make_float4(r.bmin[0], r.bmin[1], r.bmin[2], bits_f(in[i].b));
+        p.r_hi = make_float4(r.bmax[0], r.bmax[1], r.bmax[2], 0.f);
     }
+    hdr.root_lo = make_float4(in[0].bmin[0], in[0].bmin[1], in[0].bmin[2], bits_f(ref_of(0)));
+    hdr.root_hi = make_float4(in[0].bmax[0], in[0].bmax[1], in[0].bmax[2], 0.f);
+    return ok;
 }
 
 } // namespace
@@ -94,7 +116,8 @@ struct trb_scene {
     DeviceArena arena;
     trb::DScene ds{};
     trb::DInstance* d_instances = nullptr;
-    trb::DNode* d_tlas = nullptr;
+    trb::DPair* d_tlas = nullptr;
+    trb::DBvh* d_tlas_hdr = nullptr;
     uint32_t* d_tlas_order = nullptr;
     size_t tlas_capacity = 0;
     uint2* d_blocks = nullptr;
@@ -270,8 +293,14 @@ trb_status launch_wavefront(trb_scene* s, const trb::RenderParams& rp, uint32_t 
     g_launches++;
     const unsigned trace_grid = (unsigned)s->sm_count * 12, shade_grid = (unsigned)s->sm_count * 4;
     for (uint32_t round = 0; round < rounds; ++round) {
-        if (stats) trb::k_wf_trace<true><<<trace_grid, 128, 0, st>>>(s->ds, rp, wf, round, flags);
-        else trb::k_wf_trace<false><<<trace_grid, 128, 0, st>>>(s->ds, rp, wf, round, flags);
+        static const int refill = getenv("TRB_REFILL") ? atoi(getenv("TRB_REFILL")) : 8;
+        static const int occ = getenv("TRB_TRACE_OCC") ? atoi(getenv("TRB_TRACE_OCC")) : 6;
+        static const unsigned tg = getenv("TRB_TRACE_GRID") ? (unsigned)atoi(getenv("TRB_TRACE_GRID")) : 12u;
+        const unsigned tgrid = (unsigned)s->sm_count * tg;
+        if (stats) trb::k_wf_trace<true, 4><<<tgrid, 128, 0, st>>>(s->ds, rp, wf, round, flags, refill);
+        else if (occ >= 8) trb::k_wf_trace<false, 8><<<tgrid, 128, 0, st>>>(s->ds, rp, wf, round, flags, refill);
+        else if (occ >= 6) trb::k_wf_trace<false, 6><<<tgrid, 128, 0, st>>>(s->ds, rp, wf, round, flags, refill);
+        else trb::k_wf_trace<false, 4><<<tgrid, 128, 0, st>>>(s->ds, rp, wf, round, flags, refill);
         if (mode == 0) trb::k_wf_shade<0><<<shade_grid, 128, 0, st>>>(s->ds, rp, wf, round);
         else trb::k_wf_shade<1><<<shade_grid, 128, 0, st>>>(s->ds, rp, wf, round);
         g_launches += 2;
@@ -362,8 +391,9 @@ trb_status trb_scene_create(const trb_scene_desc* d, int device, trb_scene** out
         bb.build(tb, 16);
         hm.nodes = bb.nodes; hm.order = bb.order;
         for (int k = 0; k < 3; ++k) { hm.bounds.lo[k] = hm.nodes[0].bmin[k]; hm.bounds.hi[k] = hm.nodes[0].bmax[k]; }
-        std::vector<trb::DNode> pn;
-        pack_nodes(hm.nodes, pn);
+        std::vector<trb::DPair> pn;
+        trb::DBvh hdr{};
+        if (!pack_pairs(hm.nodes, pn, hdr)) return fail(TRB_UNSUPPORTED, "mesh too large for the leaf encoding (2^25 triangles)");
         std::vector<trb::DTri> tris(m.n_tris);
         for (uint32_t slot = 0; slot < m.n_tris; ++slot) {
             const uint32_t t = hm.order[slot];
@@ -376,15 +406,16 @@ trb_status trb_scene_create(const trb_scene_desc* d, int device, trb_scene** out
             tris[slot].e1 = make_float4(pc[0] - pa[0], pc[1] - pa[1], pc[2] - pa[2], 0.f);
         }
         trb::DMesh& dm = dmeshes[mi];
-        float *dp, *dn, *dt; uint32_t* di; trb::DNode* dnodes; trb::DTri* dtris;
+        float *dp, *dn, *dt; uint32_t* di; trb::DPair* dnodes; trb::DTri* dtris;
         CU(s->arena.upload(hm.pos.data(), hm.pos.size(), &dp));
         CU(s->arena.upload(hm.nrm.data(), hm.nrm.size(), &dn));
         CU(s->arena.upload(hm.uv.data(), hm.uv.size(), &dt));
         CU(s->arena.upload(hm.idx.data(), hm.idx.size(), &di));
         CU(s->arena.upload(pn.data(), pn.size(), &dnodes));
         CU(s->arena.upload(tris.data(), tris.size(), &dtris));
-        dm.positions = dp; dm.normals = dn; dm.texcoords = dt; dm.indices = di; dm.nodes = dnodes; dm.tris = dtris;
-        dm.n_nodes = (uint32_t)pn.size(); dm.n_tris = m.n_tris;
+        hdr.pairs = dnodes;
+        dm.positions = dp; dm.normals = dn; dm.texcoords = dt; dm.indices = di; dm.bvh = hdr; dm.tris = dtris;
+        dm.n_nodes = (uint32_t)hm.nodes.size(); dm.n_tris = m.n_tris;
     }
     trb::DMesh* d_meshes;
     CU(s->arena.upload(dmeshes.data(), dmeshes.size(), &d_meshes));
@@ -505,17 +536,21 @@ trb_status trb_scene_update_frame(trb_scene* s, uint32_t frame, float start, flo
     BvhBuilder bb;
     bb.build(bounds, 4);
     s->tlas_nodes = bb.nodes; s->tlas_order = bb.order;
-    std::vector<trb::DNode> pn;
-    pack_nodes(s->tlas_nodes, pn);
-    if (pn.size() > s->tlas_capacity) {
-        CU(s->arena.alloc(pn.size(), &s->d_tlas));
+    std::vector<trb::DPair> pn;
+    trb::DBvh hdr{};
+    if (!pack_pairs(s->tlas_nodes, pn, hdr)) return fail(TRB_UNSUPPORTED, "too many instances for the leaf encoding");
+    if (pn.size() + 1 > s->tlas_capacity) {
+        CU(s->arena.alloc(pn.size() + 1, &s->d_tlas));
         CU(s->arena.alloc(n, &s->d_tlas_order));
-        s->tlas_capacity = pn.size();
+        s->tlas_capacity = pn.size() + 1;
     }
-    CU(cudaMemcpy(s->d_tlas, pn.data(), pn.size() * sizeof(trb::DNode), cudaMemcpyHostToDevice));
+    if (!pn.empty()) CU(cudaMemcpy(s->d_tlas, pn.data(), pn.size() * sizeof(trb::DPair), cudaMemcpyHostToDevice));
     CU(cudaMemcpy(s->d_tlas_order, s->tlas_order.data(), n * sizeof(uint32_t), cudaMemcpyHostToDevice));
     CU(cudaMemcpy(s->d_instances, di.data(), n * sizeof(trb::DInstance), cudaMemcpyHostToDevice));
-    s->ds.tlas = s->d_tlas; s->ds.tlas_order = s->d_tlas_order;
+    hdr.pairs = s->d_tlas;
+    if (!s->d_tlas_hdr) CU(s->arena.alloc(1, &s->d_tlas_hdr));
+    CU(cudaMemcpy(s->d_tlas_hdr, &hdr, sizeof hdr, cudaMemcpyHostToDevice));
+    s->ds.tlas = s->d_tlas_hdr; s->ds.tlas_order = s->d_tlas_order;
     s->frame_ready = true;
     return TRB_OK;
 }

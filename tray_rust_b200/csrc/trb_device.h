@@ -13,6 +13,24 @@ namespace trb {
 struct DNode { float4 lo, hi; };
 constexpr uint32_t LEAF_BIT = 0x80000000u;
 
+// Traversal layout: one 64-byte record per INTERIOR node of the reference tree holding BOTH children's
+// boxes, so one fetch (four 16-byte loads, two 32-byte sectors) feeds two box tests and the dependent-load
+// chain per ray is half as long. Topology, child order and every compare are unchanged (DESIGN.md
+// "Node layout"). A child reference is 2 tag bits + 30 payload bits:
+//   REF_INTERIOR | record index        REF_LEAF | count << 25 | first primitive slot
+struct DPair {
+    float4 l_lo; // left  (= first child, index+1) min, w = left reference
+    float4 l_hi; // left  max,                       w = right reference
+    float4 r_lo; // right (= second_child) min,      w = split axis of this node
+    float4 r_hi; // right max
+};
+constexpr uint32_t REF_TAG = 0xc0000000u, REF_INTERIOR = 0x00000000u, REF_LEAF = 0x40000000u;
+struct DBvh {
+    const DPair* pairs;
+    float4 root_lo; // root box min, w = root reference
+    float4 root_hi;
+};
+
 // One triangle in LEAF ORDER (slot k of the BLAS == ordered_geom[k]), 48 B = three 16-byte loads:
 // v0 = (pa.xyz, triangle index), e0 = pb-pa, e1 = pc-pa (the same single IEEE subtraction the
 // reference performs per test, mesh.rs:140, hoisted to load time).
@@ -23,7 +41,7 @@ struct DMesh {
     const float* normals;   // 3 per vertex
     const float* texcoords; // 2 per vertex
     const uint32_t* indices; // 3 per triangle
-    const DNode* nodes;     // BVH<Triangle>, max_geom 16 (mesh.rs:44)
+    DBvh bvh;               // BVH<Triangle>, max_geom 16 (mesh.rs:44)
     const DTri* tris;       // leaf order
     uint32_t n_nodes, n_tris;
 };
@@ -64,7 +82,7 @@ struct DStats { // mirrors trb_stats' integer part
 };
 
 struct DScene {
-    const DNode* tlas;           // BVH<Instance>, max_geom 4 (scene.rs:141)
+    const DBvh* tlas;            // BVH<Instance>, max_geom 4 (scene.rs:141); header in global memory like the meshes'
     const uint32_t* tlas_order;  // ordered_geom
     const DInstance* instances;
     const DMesh* meshes;

@@ -80,7 +80,8 @@ struct Cnt { uint32_t node, tri, inst; };
 // BBox::fast_intersect (src/geometry/bbox.rs:75-104), compares transcribed literally so the NaN
 // behaviour is the reference's.
 // ------------------------------------------------------------------------------------------
-__device__ __forceinline__ bool box_hit(const float4 lo, const float4 hi, f3 o, f3 inv, bool nx, bool ny, bool nz, float tmin_r, float tmax_r) {
+__device__ __forceinline__ bool box_hit(const float4 lo, const float4 hi, f3 o, f3 inv, bool nx, bool ny, bool nz, float tmin_r, float tmax_r, float& t_entry) {
+    t_entry = 0.0f;
     float tmin = ((nx ? hi.x : lo.x) - o.x) * inv.x;
     float tmax = ((nx ? lo.x : hi.x) - o.x) * inv.x;
     float tymin = ((ny ? hi.y : lo.y) - o.y) * inv.y;
@@ -93,6 +94,7 @@ __device__ __forceinline__ bool box_hit(const float4 lo, const float4 hi, f3 o, 
     if (tmin > tzmax || tzmin > tmax) return false;
     if (tzmin > tmin) tmin = tzmin;
     if (tzmax < tmax) tmax = tzmax;
+    t_entry = tmin; // the only quantity a later, smaller max_t can still reject: `tmin < r.max_t` (bbox.rs:103)
     return tmin < tmax_r && tmax > tmin_r;
 }
 
@@ -160,8 +162,11 @@ __device__ __forceinline__ void load_xf(const float* __restrict__ src, float* ds
 // t and the test counters are bit-identical to the oracle. No early `return` inside the loop: every
 // divergent branch reconverges at the loop head.
 // ------------------------------------------------------------------------------------------
-constexpr uint32_t ST_SPECIAL = 0x80000000u; // level 0: ST_SPECIAL | slot in tlas_order; level 1: ST_RETURN
-constexpr uint32_t ST_RETURN = 0xfffffffeu;
+// `cur` / stack references: 2 tag bits + payload
+//   00 interior record | 01 leaf (count << 25 | first slot) | 10 pending instance (slot in tlas_order) | 11 control
+constexpr uint32_t ST_INSTANCE = 0x80000000u;
+constexpr uint32_t ST_ROOT = 0xfffffffdu;   // test the current level's root box, then go to its reference
+constexpr uint32_t ST_RETURN = 0xfffffffeu; // leave the mesh: restore the world ray
 constexpr uint32_t ST_DONE = 0xffffffffu;
 constexpr int STACK_DEPTH = 96;
 
@@ -171,7 +176,7 @@ struct TraceState {
     f3 wo, wd, winv;      // world ray and 1/d (bvh.rs:84)
     f3 o, d, inv;         // ray of the current level (world, or the mesh instance's object space)
     bool nx, ny, nz;      // d < 0 per axis (bvh.rs:85)
-    const DNode* nodes;
+    const DBvh* bvh;      // current level
     const DTri* tris;
     uint32_t level_inst;  // instance whose mesh is being traversed, TRB_MISS at the top level
     float tmin, tmax;
@@ -186,66 +191,91 @@ __device__ __forceinline__ void trace_init(const DScene& sc, TraceState& t, cons
     t.winv = mk(1.0f / ray.d.x, 1.0f / ray.d.y, 1.0f / ray.d.z);
     t.o = t.wo; t.d = t.wd; t.inv = t.winv;
     t.nx = t.d.x < 0.0f; t.ny = t.d.y < 0.0f; t.nz = t.d.z < 0.0f;
-    t.nodes = sc.tlas; t.tris = nullptr; t.level_inst = TRB_MISS;
+    t.bvh = sc.tlas; t.tris = nullptr; t.level_inst = TRB_MISS;
     t.tmin = ray.tmin; t.tmax = ray.tmax;
-    t.sp = 0; t.cur = 0; t.found = false; t.any_hit = any_hit;
+    t.sp = 0; t.cur = ST_ROOT; t.found = false; t.any_hit = any_hit;
     t.h_inst = TRB_MISS; t.h_prim = 0; t.h_b1 = 0.0f; t.h_b2 = 0.0f;
 }
-// One transition: visit a node (box test; descend / expand a leaf), leave a mesh, or test one instance.
+// Pop the next reference. A node entry carries the entry distance of its box, computed when its parent was
+// visited; the reference tests that box only now, against the current (smaller) max_t: `tmin < r.max_t`.
+__device__ __forceinline__ uint32_t trace_pop(TraceState& t, const unsigned long long* stack) {
+    while (t.sp > 0) {
+        const unsigned long long e = stack[--t.sp];
+        const uint32_t ref = (uint32_t)e;
+        if (ref & ST_INSTANCE) return ref; // pending instances and control entries are never culled
+        if (__uint_as_float((uint32_t)(e >> 32)) < t.tmax) return ref;
+    }
+    return ST_DONE;
+}
+// One transition: visit an interior node (two box tests), a leaf, the root, a pending instance, or leave a mesh.
 template <bool STATS>
-__device__ __forceinline__ void trace_step(const DScene& sc, TraceState& t, uint32_t* stack, Cnt& cnt, int* err) {
+__device__ __forceinline__ void trace_step(const DScene& sc, TraceState& t, unsigned long long* stack, Cnt& cnt, int* err) {
     const uint32_t cur = t.cur;
+    const uint32_t tag = cur & REF_TAG;
     uint32_t next;
-    if (!(cur & ST_SPECIAL)) {
-        const float4 lo = __ldg(&t.nodes[cur].lo), hi = __ldg(&t.nodes[cur].hi);
-        if (STATS) cnt.node++;
-        const bool bh = box_hit(lo, hi, t.o, t.inv, t.nx, t.ny, t.nz, t.tmin, t.tmax);
-        const uint32_t a = __float_as_uint(lo.w), b = __float_as_uint(hi.w);
-        if (bh && !(b & LEAF_BIT)) {
-            // interior: descend to the near child by the sign of d[axis], push the other (bvh.rs:105-119)
-            const bool neg = b == 0 ? t.nx : (b == 1 ? t.ny : t.nz);
-            if (t.sp >= STACK_DEPTH - 6) { *err = 1; t.sp = 0; next = ST_DONE; }
-            else { stack[t.sp++] = neg ? cur + 1 : a; next = neg ? a : cur + 1; }
+    if (tag == REF_INTERIOR) {
+        const DPair* __restrict__ rec = t.bvh->pairs + cur;
+        const float4 l_lo = __ldg(&rec->l_lo), l_hi = __ldg(&rec->l_hi), r_lo = __ldg(&rec->r_lo), r_hi = __ldg(&rec->r_hi);
+        if (STATS) cnt.node += 2; // the reference tests the near child now and the far child when it pops it
+        float tl, tr;
+        const bool hl = box_hit(l_lo, l_hi, t.o, t.inv, t.nx, t.ny, t.nz, t.tmin, t.tmax, tl);
+        const bool hr = box_hit(r_lo, r_hi, t.o, t.inv, t.nx, t.ny, t.nz, t.tmin, t.tmax, tr);
+        const uint32_t axis = __float_as_uint(r_lo.w);
+        const bool neg = axis == 0 ? t.nx : (axis == 1 ? t.ny : t.nz); // near child = second_child iff d[axis] < 0 (bvh.rs:111-117)
+        const uint32_t ref_l = __float_as_uint(l_lo.w), ref_r = __float_as_uint(l_hi.w);
+        const bool h_near = neg ? hr : hl, h_far = neg ? hl : hr;
+        const uint32_t ref_near = neg ? ref_r : ref_l, ref_far = neg ? ref_l : ref_r;
+        const float t_far = neg ? tl : tr;
+        if (h_near) {
+            next = ref_near;
+            if (h_far) {
+                if (t.sp >= STACK_DEPTH - 6) { *err = 1; t.sp = 0; next = ST_DONE; }
+                else stack[t.sp++] = ((unsigned long long)__float_as_uint(t_far) << 32) | ref_far;
+            }
+        } else if (h_far) next = ref_far; // nothing was tested in between, so max_t is unchanged: same outcome as pop + test
+        else next = trace_pop(t, stack);
+    } else if (tag == REF_LEAF) {
+        const uint32_t a = cur & 0x01ffffffu, n = (cur >> 25) & 31u;
+        if (t.level_inst == TRB_MISS) {
+            for (uint32_t k = a + n; k-- > a;) stack[t.sp++] = ST_INSTANCE | k; // pops as a, a+1, ... (bvh.rs:95-98)
         } else {
-            if (bh) {
-                const uint32_t n = b & ~LEAF_BIT;
-                if (t.level_inst == TRB_MISS) {
-                    for (uint32_t k = a + n; k-- > a;) stack[t.sp++] = ST_SPECIAL | k; // pops as a, a+1, ...
-                } else {
-                    const DTri* __restrict__ tris = t.tris;
-                    for (uint32_t k = a; k < a + n; ++k) {
-                        const float4 v0 = __ldg(&tris[k].v0), q0 = __ldg(&tris[k].e0), q1 = __ldg(&tris[k].e1);
-                        if (STATS) cnt.tri++;
-                        const f3 e0 = mk(q0.x, q0.y, q0.z), e1 = mk(q1.x, q1.y, q1.z);
-                        const f3 s0 = cross3(t.d, e1);
-                        const float dd = dot3(s0, e0);
-                        const float div = 1.0f / dd;
-                        const f3 dv = t.o - mk(v0.x, v0.y, v0.z);
-                        const float b1 = dot3(dv, s0) * div;
-                        const f3 s1 = cross3(dv, e0);
-                        const float b2 = dot3(t.d, s1) * div;
-                        const float tt = dot3(e1, s1) * div;
-                        // mesh.rs:142-168: d == 0 -> miss; b1 in [0,1]; b2 >= 0 and b1+b2 <= 1; t in [min_t, max_t]
-                        const bool ok = dd != 0.0f && !(b1 < 0.0f || b1 > 1.0f) && !(b2 < 0.0f || b1 + b2 > 1.0f) && !(tt < t.tmin || tt > t.tmax);
-                        if (ok) { // last accepted wins, inclusive compare (Q9)
-                            t.tmax = tt;
-                            t.h_prim = __float_as_uint(v0.w); t.h_b1 = b1; t.h_b2 = b2; t.h_inst = t.level_inst;
-                            t.found = true;
-                            if (t.any_hit) t.sp = 0;
-                        }
-                    }
+            const DTri* __restrict__ tris = t.tris;
+            for (uint32_t k = a; k < a + n; ++k) {
+                const float4 v0 = __ldg(&tris[k].v0), q0 = __ldg(&tris[k].e0), q1 = __ldg(&tris[k].e1);
+                if (STATS) cnt.tri++;
+                const f3 e0 = mk(q0.x, q0.y, q0.z), e1 = mk(q1.x, q1.y, q1.z);
+                const f3 s0 = cross3(t.d, e1);
+                const float dd = dot3(s0, e0);
+                const float div = 1.0f / dd;
+                const f3 dv = t.o - mk(v0.x, v0.y, v0.z);
+                const float b1 = dot3(dv, s0) * div;
+                const f3 s1 = cross3(dv, e0);
+                const float b2 = dot3(t.d, s1) * div;
+                const float tt = dot3(e1, s1) * div;
+                // mesh.rs:142-168: d == 0 -> miss; b1 in [0,1]; b2 >= 0 and b1+b2 <= 1; t in [min_t, max_t]
+                const bool ok = dd != 0.0f && !(b1 < 0.0f || b1 > 1.0f) && !(b2 < 0.0f || b1 + b2 > 1.0f) && !(tt < t.tmin || tt > t.tmax);
+                if (ok) { // last accepted wins, inclusive compare (Q9)
+                    t.tmax = tt;
+                    t.h_prim = __float_as_uint(v0.w); t.h_b1 = b1; t.h_b2 = b2; t.h_inst = t.level_inst;
+                    t.found = true;
+                    if (t.any_hit) t.sp = 0;
                 }
             }
-            next = t.sp > 0 ? stack[--t.sp] : ST_DONE;
         }
+        next = trace_pop(t, stack);
+    } else if (cur == ST_ROOT) {
+        const float4 lo = __ldg(&t.bvh->root_lo), hi = __ldg(&t.bvh->root_hi);
+        if (STATS) cnt.node++;
+        float te;
+        next = box_hit(lo, hi, t.o, t.inv, t.nx, t.ny, t.nz, t.tmin, t.tmax, te) ? __float_as_uint(lo.w) : trace_pop(t, stack);
     } else if (cur == ST_RETURN) {
         t.o = t.wo; t.d = t.wd; t.inv = t.winv;
         t.nx = t.d.x < 0.0f; t.ny = t.d.y < 0.0f; t.nz = t.d.z < 0.0f;
-        t.nodes = sc.tlas; t.level_inst = TRB_MISS;
-        next = t.sp > 0 ? stack[--t.sp] : ST_DONE;
+        t.bvh = sc.tlas; t.level_inst = TRB_MISS;
+        next = trace_pop(t, stack);
     } else {
         // Instance::intersect for one entry of a TLAS leaf
-        const uint32_t ii = __ldg(&sc.tlas_order[cur & ~ST_SPECIAL]);
+        const uint32_t ii = __ldg(&sc.tlas_order[cur & ~REF_TAG]);
         const DInstance& in = sc.instances[ii];
         if (STATS) cnt.inst++;
         const uint32_t kind = __ldg(&in.kind), shape = __ldg(&in.shape);
@@ -260,9 +290,9 @@ __device__ __forceinline__ void trace_step(const DScene& sc, TraceState& t, uint
                 t.o = lo_; t.d = ld_;
                 t.inv = mk(1.0f / ld_.x, 1.0f / ld_.y, 1.0f / ld_.z);
                 t.nx = ld_.x < 0.0f; t.ny = ld_.y < 0.0f; t.nz = ld_.z < 0.0f;
-                t.nodes = me.nodes; t.tris = me.tris; t.level_inst = ii;
+                t.bvh = &me.bvh; t.tris = me.tris; t.level_inst = ii;
                 stack[t.sp++] = ST_RETURN;
-                next = 0; // root of the mesh BVH
+                next = ST_ROOT; // BVH<Triangle>::intersect starts by testing its root box
                 enter = true;
             } else {
                 const float p0 = __ldg(&in.p0), p1 = __ldg(&in.p1);
@@ -279,7 +309,7 @@ __device__ __forceinline__ void trace_step(const DScene& sc, TraceState& t, uint
                 }
             }
         }
-        if (!enter) next = t.sp > 0 ? stack[--t.sp] : ST_DONE;
+        if (!enter) next = trace_pop(t, stack);
     }
     t.cur = next;
 }
@@ -287,7 +317,7 @@ __device__ __forceinline__ void trace_step(const DScene& sc, TraceState& t, uint
 template <bool STATS>
 __device__ __noinline__ bool scene_trace(const DScene& sc, Ray& ray, HitRec& hit, bool any_hit, Cnt& cnt, int* err) {
     TraceState t;
-    uint32_t stack[STACK_DEPTH];
+    unsigned long long stack[STACK_DEPTH];
     trace_init(sc, t, ray, any_hit);
     while (t.cur != ST_DONE) trace_step<STATS>(sc, t, stack, cnt, err);
     ray.tmax = t.tmax;
@@ -1228,11 +1258,9 @@ __global__ void __launch_bounds__(256) k_wf_generate(const __grid_constant__ DSc
 // whose ray has finished writes its result and, once enough lanes of the warp are idle, the idle lanes
 // fetch new rays with one warp-aggregated atomic, so rays of very different lengths (an any-hit shadow
 // ray vs. a continuation ray crossing the whole mesh) do not leave the warp mostly empty.
-constexpr int WF_REFILL_IDLE = 8; // refill when at least this many lanes are idle
-
-template <bool STATS>
-__global__ void __launch_bounds__(128) k_wf_trace(const __grid_constant__ DScene sc, const __grid_constant__ RenderParams rp, const __grid_constant__ WfState wf,
-                                                   uint32_t round, uint32_t flags) {
+template <bool STATS, int MINB>
+__global__ void __launch_bounds__(128, MINB) k_wf_trace(const __grid_constant__ DScene sc, const __grid_constant__ RenderParams rp, const __grid_constant__ WfState wf,
+                                                         uint32_t round, uint32_t flags, int WF_REFILL_IDLE) {
     uint32_t* cnt_r = wf.counters + round * WF_CNT;
     const uint32_t n_cont = cnt_r[WF_N_CONT], n_shadow = cnt_r[WF_N_SHADOW], n_mis = cnt_r[WF_N_MIS];
     const uint32_t total = n_cont + n_shadow + n_mis;
@@ -1241,7 +1269,7 @@ __global__ void __launch_bounds__(128) k_wf_trace(const __grid_constant__ DScene
     const unsigned lt_mask = (1u << lane) - 1u;
     Cnt cnt = {0, 0, 0};
     TraceState t;
-    uint32_t stack[STACK_DEPTH];
+    unsigned long long stack[STACK_DEPTH];
     t.cur = ST_DONE;
     bool have = false, exhausted = false;
     uint32_t p = 0;
