@@ -550,7 +550,7 @@ trb_status trb_scene_update_frame(trb_scene* s, uint32_t frame, float start, flo
     hdr.pairs = s->d_tlas;
     if (!s->d_tlas_hdr) CU(s->arena.alloc(1, &s->d_tlas_hdr));
     CU(cudaMemcpy(s->d_tlas_hdr, &hdr, sizeof hdr, cudaMemcpyHostToDevice));
-    s->ds.tlas = s->d_tlas_hdr; s->ds.tlas_order = s->d_tlas_order;
+    s->ds.tlas = s->d_tlas_hdr; s->ds.tlas_pairs = s->d_tlas; s->ds.tlas_order = s->d_tlas_order;
     s->frame_ready = true;
     return TRB_OK;
 }

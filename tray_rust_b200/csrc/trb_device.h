@@ -83,6 +83,7 @@ struct DStats { // mirrors trb_stats' integer part
 
 struct DScene {
     const DBvh* tlas;            // BVH<Instance>, max_geom 4 (scene.rs:141); header in global memory like the meshes'
+    const DPair* tlas_pairs;     // == tlas->pairs
     const uint32_t* tlas_order;  // ordered_geom
     const DInstance* instances;
     const DMesh* meshes;

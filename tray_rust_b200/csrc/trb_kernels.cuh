@@ -176,7 +176,8 @@ struct TraceState {
     f3 wo, wd, winv;      // world ray and 1/d (bvh.rs:84)
     f3 o, d, inv;         // ray of the current level (world, or the mesh instance's object space)
     bool nx, ny, nz;      // d < 0 per axis (bvh.rs:85)
-    const DBvh* bvh;      // current level
+    const DBvh* bvh;      // current level (root box + reference)
+    const DPair* pairs;   // current level's records, kept in registers: no pointer chase per step
     const DTri* tris;
     uint32_t level_inst;  // instance whose mesh is being traversed, TRB_MISS at the top level
     float tmin, tmax;
@@ -191,16 +192,34 @@ __device__ __forceinline__ void trace_init(const DScene& sc, TraceState& t, cons
     t.winv = mk(1.0f / ray.d.x, 1.0f / ray.d.y, 1.0f / ray.d.z);
     t.o = t.wo; t.d = t.wd; t.inv = t.winv;
     t.nx = t.d.x < 0.0f; t.ny = t.d.y < 0.0f; t.nz = t.d.z < 0.0f;
-    t.bvh = sc.tlas; t.tris = nullptr; t.level_inst = TRB_MISS;
+    t.bvh = sc.tlas; t.pairs = sc.tlas_pairs; t.tris = nullptr; t.level_inst = TRB_MISS;
     t.tmin = ray.tmin; t.tmax = ray.tmax;
     t.sp = 0; t.cur = ST_ROOT; t.found = false; t.any_hit = any_hit;
     t.h_inst = TRB_MISS; t.h_prim = 0; t.h_b1 = 0.0f; t.h_b2 = 0.0f;
 }
+// Traversal stack storage. LocalStack: per-thread local memory. HybridStack: the 16 hottest entries live in shared
+// memory ([entry][thread], conflict-free 8-byte accesses), deeper entries spill to local memory — pops no longer
+// compete with node fetches for L1 (the trace kernel's second most frequent stall was the local-memory pop).
+struct LocalStack {
+    unsigned long long* s;
+    __device__ __forceinline__ void put(int i, unsigned long long v) const { s[i] = v; }
+    __device__ __forceinline__ unsigned long long get(int i) const { return s[i]; }
+};
+constexpr int SMEM_STACK = 16;
+struct HybridStack {
+    unsigned long long* sm; // &smem[0][threadIdx.x], stride = blockDim.x
+    unsigned long long* lo;
+    int stride;
+    __device__ __forceinline__ void put(int i, unsigned long long v) const { if (i < SMEM_STACK) sm[i * stride] = v; else lo[i - SMEM_STACK] = v; }
+    __device__ __forceinline__ unsigned long long get(int i) const { return i < SMEM_STACK ? sm[i * stride] : lo[i - SMEM_STACK]; }
+};
+
 // Pop the next reference. A node entry carries the entry distance of its box, computed when its parent was
 // visited; the reference tests that box only now, against the current (smaller) max_t: `tmin < r.max_t`.
-__device__ __forceinline__ uint32_t trace_pop(TraceState& t, const unsigned long long* stack) {
+template <class Stack>
+__device__ __forceinline__ uint32_t trace_pop(TraceState& t, const Stack& stack) {
     while (t.sp > 0) {
-        const unsigned long long e = stack[--t.sp];
+        const unsigned long long e = stack.get(--t.sp);
         const uint32_t ref = (uint32_t)e;
         if (ref & ST_INSTANCE) return ref; // pending instances and control entries are never culled
         if (__uint_as_float((uint32_t)(e >> 32)) < t.tmax) return ref;
@@ -208,13 +227,13 @@ __device__ __forceinline__ uint32_t trace_pop(TraceState& t, const unsigned long
     return ST_DONE;
 }
 // One transition: visit an interior node (two box tests), a leaf, the root, a pending instance, or leave a mesh.
-template <bool STATS>
-__device__ __forceinline__ void trace_step(const DScene& sc, TraceState& t, unsigned long long* stack, Cnt& cnt, int* err) {
+template <bool STATS, class Stack>
+__device__ __forceinline__ void trace_step(const DScene& sc, TraceState& t, const Stack& stack, Cnt& cnt, int* err) {
     const uint32_t cur = t.cur;
     const uint32_t tag = cur & REF_TAG;
     uint32_t next;
     if (tag == REF_INTERIOR) {
-        const DPair* __restrict__ rec = t.bvh->pairs + cur;
+        const DPair* __restrict__ rec = t.pairs + cur;
         const float4 l_lo = __ldg(&rec->l_lo), l_hi = __ldg(&rec->l_hi), r_lo = __ldg(&rec->r_lo), r_hi = __ldg(&rec->r_hi);
         if (STATS) cnt.node += 2; // the reference tests the near child now and the far child when it pops it
         float tl, tr;
@@ -230,14 +249,14 @@ __device__ __forceinline__ void trace_step(const DScene& sc, TraceState& t, unsi
             next = ref_near;
             if (h_far) {
                 if (t.sp >= STACK_DEPTH - 6) { *err = 1; t.sp = 0; next = ST_DONE; }
-                else stack[t.sp++] = ((unsigned long long)__float_as_uint(t_far) << 32) | ref_far;
+                else stack.put(t.sp++, ((unsigned long long)__float_as_uint(t_far) << 32) | ref_far);
             }
         } else if (h_far) next = ref_far; // nothing was tested in between, so max_t is unchanged: same outcome as pop + test
         else next = trace_pop(t, stack);
     } else if (tag == REF_LEAF) {
         const uint32_t a = cur & 0x01ffffffu, n = (cur >> 25) & 31u;
         if (t.level_inst == TRB_MISS) {
-            for (uint32_t k = a + n; k-- > a;) stack[t.sp++] = ST_INSTANCE | k; // pops as a, a+1, ... (bvh.rs:95-98)
+            for (uint32_t k = a + n; k-- > a;) stack.put(t.sp++, ST_INSTANCE | k); // pops as a, a+1, ... (bvh.rs:95-98)
         } else {
             const DTri* __restrict__ tris = t.tris;
             for (uint32_t k = a; k < a + n; ++k) {
@@ -271,7 +290,7 @@ __device__ __forceinline__ void trace_step(const DScene& sc, TraceState& t, unsi
     } else if (cur == ST_RETURN) {
         t.o = t.wo; t.d = t.wd; t.inv = t.winv;
         t.nx = t.d.x < 0.0f; t.ny = t.d.y < 0.0f; t.nz = t.d.z < 0.0f;
-        t.bvh = sc.tlas; t.level_inst = TRB_MISS;
+        t.bvh = sc.tlas; t.pairs = sc.tlas_pairs; t.level_inst = TRB_MISS;
         next = trace_pop(t, stack);
     } else {
         // Instance::intersect for one entry of a TLAS leaf
@@ -290,8 +309,8 @@ __device__ __forceinline__ void trace_step(const DScene& sc, TraceState& t, unsi
                 t.o = lo_; t.d = ld_;
                 t.inv = mk(1.0f / ld_.x, 1.0f / ld_.y, 1.0f / ld_.z);
                 t.nx = ld_.x < 0.0f; t.ny = ld_.y < 0.0f; t.nz = ld_.z < 0.0f;
-                t.bvh = &me.bvh; t.tris = me.tris; t.level_inst = ii;
-                stack[t.sp++] = ST_RETURN;
+                t.bvh = &me.bvh; t.pairs = me.bvh.pairs; t.tris = me.tris; t.level_inst = ii;
+                stack.put(t.sp++, ST_RETURN);
                 next = ST_ROOT; // BVH<Triangle>::intersect starts by testing its root box
                 enter = true;
             } else {
@@ -317,7 +336,8 @@ __device__ __forceinline__ void trace_step(const DScene& sc, TraceState& t, unsi
 template <bool STATS>
 __device__ __noinline__ bool scene_trace(const DScene& sc, Ray& ray, HitRec& hit, bool any_hit, Cnt& cnt, int* err) {
     TraceState t;
-    unsigned long long stack[STACK_DEPTH];
+    unsigned long long stack_mem[STACK_DEPTH];
+    const LocalStack stack{stack_mem};
     trace_init(sc, t, ray, any_hit);
     while (t.cur != ST_DONE) trace_step<STATS>(sc, t, stack, cnt, err);
     ray.tmax = t.tmax;
@@ -1269,7 +1289,9 @@ __global__ void __launch_bounds__(128, MINB) k_wf_trace(const __grid_constant__ 
     const unsigned lt_mask = (1u << lane) - 1u;
     Cnt cnt = {0, 0, 0};
     TraceState t;
-    unsigned long long stack[STACK_DEPTH];
+    __shared__ unsigned long long s_stack[SMEM_STACK * 128];
+    unsigned long long stack_lo[STACK_DEPTH - SMEM_STACK];
+    const HybridStack stack{s_stack + threadIdx.x, stack_lo, 128};
     t.cur = ST_DONE;
     bool have = false, exhausted = false;
     uint32_t p = 0;
@@ -1278,15 +1300,15 @@ __global__ void __launch_bounds__(128, MINB) k_wf_trace(const __grid_constant__ 
         // ---- retire finished rays ----
         if (have && t.cur == ST_DONE) {
             if (type == 0) {
-                wf.cont[p] = make_float4(t.wd.x, t.wd.y, t.wd.z, t.tmax);
-                wf.hit[p] = make_uint4(t.found ? t.h_inst : TRB_MISS, t.h_prim, __float_as_uint(t.h_b1), __float_as_uint(t.h_b2));
+                __stcs(&wf.cont[p], make_float4(t.wd.x, t.wd.y, t.wd.z, t.tmax));
+                __stcs(&wf.hit[p], make_uint4(t.found ? t.h_inst : TRB_MISS, t.h_prim, __float_as_uint(t.h_b1), __float_as_uint(t.h_b2)));
             } else if (type == 1) {
-                wf.shadow[p] = make_float4(t.wd.x, t.wd.y, t.wd.z, __uint_as_float(t.found ? 1u : 0u));
+                __stcs(&wf.shadow[p], make_float4(t.wd.x, t.wd.y, t.wd.z, __uint_as_float(t.found ? 1u : 0u)));
             } else {
-                wf.mis[p] = make_float4(t.wd.x, t.wd.y, t.wd.z, t.tmax);
-                float4 a4 = wf.a[p];
+                __stcs(&wf.mis[p], make_float4(t.wd.x, t.wd.y, t.wd.z, t.tmax));
+                float4 a4 = __ldcs(&wf.a[p]);
                 a4.w = __uint_as_float(t.found ? t.h_inst : TRB_MISS);
-                wf.a[p] = a4;
+                __stcs(&wf.a[p], a4);
             }
             have = false;
         }
@@ -1304,8 +1326,8 @@ __global__ void __launch_bounds__(128, MINB) k_wf_trace(const __grid_constant__ 
                     if (i < n_cont) { type = 0; p = wf.q_cont[i]; }
                     else if (i < n_cont + n_shadow) { type = 1; p = wf.q_shadow[i - n_cont]; }
                     else { type = 2; p = wf.q_mis[i - n_cont - n_shadow]; }
-                    const float4 o4 = wf.org[p];
-                    const float4 d4 = type == 0 ? wf.cont[p] : (type == 1 ? wf.shadow[p] : wf.mis[p]);
+                    const float4 o4 = __ldcs(&wf.org[p]);
+                    const float4 d4 = __ldcs(type == 0 ? &wf.cont[p] : (type == 1 ? &wf.shadow[p] : &wf.mis[p])); // streamed: keep L2 for the BVH
                     Ray ray; ray.o = mk(o4.x, o4.y, o4.z); ray.d = mk(d4.x, d4.y, d4.z);
                     ray.tmin = (type == 0 && round == 0) ? 0.0f : 0.001f;
                     ray.tmax = type == 1 ? 0.999f : finf();
