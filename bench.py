@@ -216,7 +216,7 @@ def run_ours(a):
         flush.fill_(i & 0xFF)
         kev[k][0].record()
         g.render_device(film.data_ptr(), stats.data_ptr(), stream, spp=a.spp, sample_first=i * spp_step, sample_count=spp_step,
-                        block_start=bstart, block_count=bcount, seed=a.seed)
+                        block_start=bstart, block_count=bcount, seed=a.seed, flags=F.RENDER_TIME_TRACE)
         kev[k][1].record()
         if world > 1:
             reduce_film(film, dst=0)
@@ -225,6 +225,7 @@ def run_ours(a):
     if world > 1:
         dist.barrier()
     launches = lib.trb_launch_count() - launches0
+    trace_ms, trace_launches = g.trace_time()      # CUDA events around every k_wf_trace launch of the timed steps
     clk = clocks.stop() if rank == 0 else None
     total_ms = max_over_ranks(e_begin.elapsed_time(e_end), dev)
     kernel_ms = [kev[k][0].elapsed_time(kev[k][1]) for k in range(a.steps)]
@@ -242,8 +243,32 @@ def run_ours(a):
     torch.cuda.synchronize()
     cs = cstats.cpu().numpy()
     rank_rays = int(cs[1:5].sum())
-    bytes_per_launch = alg_bytes(rank_rays, int(cs[5]), int(cs[6]), int(cs[7])) / a.steps
+    bytes_total = alg_bytes(rank_rays, int(cs[5]), int(cs[6]), int(cs[7]))
     del scratch
+
+    # --- primary + shadow rays only (the north-star target is quoted on them): the same scene with max_depth 0,
+    #     i.e. one primary and one shadow ray per camera sample; secondary measurement, device-resident like `value`
+    direct = None
+    if world == 1:
+        from tray_rust_b200 import scenebuild as SB
+        b0 = SB.scene_c4(a.tris, a.width, a.height, a.spp)
+        b0.integrator = (0, 0, 0)
+        g0 = api.Scene(b0.finish(), local)
+        g0.update_frame(0, 0.0, 0.0)
+        dstats = torch.zeros(10, dtype=torch.int64, device=dev)
+        for i in range(2):
+            g0.render_device(film.data_ptr(), dstats.data_ptr(), stream, spp=a.spp, sample_first=i * spp_step, sample_count=spp_step, seed=a.seed)
+        torch.cuda.synchronize(); dstats.zero_()
+        d0, d1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        d0.record()
+        for i in range(2, 2 + a.steps):
+            g0.render_device(film.data_ptr(), dstats.data_ptr(), stream, spp=a.spp, sample_first=i * spp_step, sample_count=spp_step, seed=a.seed)
+        d1.record(); torch.cuda.synchronize()
+        ds = dstats.cpu().numpy()
+        dms = d0.elapsed_time(d1)
+        direct = {"mrays_s": float(ds[1:5].sum()) / dms / 1e3, "msamples_s": float(ds[0]) / dms / 1e3, "primary": int(ds[1]), "shadow": int(ds[2]),
+                  "ms_per_step": dms / a.steps, "note": "same C4 scene, pathtracer max_depth 0: one primary + one (any-hit) shadow ray per camera sample"}
+        g0.close()
 
     # --- e2e: the reference-facing call (host film, update_frame + H2D + kernels + D2H inside the timed region)
     e2e = None
@@ -274,7 +299,9 @@ def run_ours(a):
             pass
         peak = float(peaks.get("hbm_gbs", 6650.0))
         avg_kernel_ms = float(np.mean(kernel_ms))
-        achieved = bytes_per_launch / (avg_kernel_ms * 1e-3) / 1e9
+        trace_launches = max(1, trace_launches)
+        bytes_per_launch = bytes_total / trace_launches
+        achieved = bytes_total / (trace_ms * 1e-3) / 1e9        # == bytes per launch / average launch duration
         traffic = None
         try:
             traffic = json.load(open(os.path.join(REPO, "profiles", "traffic.json"))).get("dram_bytes_per_launch")
@@ -289,10 +316,13 @@ def run_ours(a):
             "samples_per_s": tot[0] / (total_ms * 1e-3),
             "rays": {"primary": tot[1], "shadow": tot[2], "mis": tot[3], "continuation": tot[4],
                      "primary_plus_shadow_mrays_s": (tot[1] + tot[2]) / (total_ms * 1e-3) / 1e6},
-            "roofline": {"bound": "hbm", "kernel": "k_render", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
+            "roofline": {"bound": "hbm", "kernel": "k_wf_trace", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
                          "peak_source": "MEASURED_PEAKS.json hbm_gbs (measured)" if peaks else "fallback 6650 GB/s",
-                         "traffic": traffic, "algorithmic_bytes_per_launch": bytes_per_launch, "kernel_ms": avg_kernel_ms,
+                         "traffic": traffic, "algorithmic_bytes_per_launch": bytes_per_launch, "launches": trace_launches,
+                         "avg_launch_ms": trace_ms / trace_launches, "share_of_step": trace_ms / (avg_kernel_ms * a.steps),
+                         "step_kernels_ms": avg_kernel_ms,
                          "per_ray": {"node_tests": cs[5] / max(1, rank_rays), "tri_tests": cs[6] / max(1, rank_rays), "inst_tests": cs[7] / max(1, rank_rays)}},
+            "primary_shadow_only": direct,
             "gpu_launches": int(launches), "clocks": clk, "e2e": e2e, "cpu_baseline": cpu,
         }
         print(json.dumps(line, default=float))

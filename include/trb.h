@@ -185,7 +185,8 @@ enum {
     TRB_RENDER_NO_UPDATE = 2u,        /* skip Scene::update_frame (caller already did it) */
     TRB_RENDER_REFERENCE_SHADOW = 4u, /* trace shadow rays as full closest-hit like light/mod.rs:30-37 instead of
                                          stopping at the first accepted hit (same boolean, fewer tests) */
-    TRB_RENDER_MEGAKERNEL = 8u        /* one persistent kernel per pass instead of the wavefront pipeline (same results) */
+    TRB_RENDER_MEGAKERNEL = 8u,       /* one persistent kernel per pass instead of the wavefront pipeline (same results) */
+    TRB_RENDER_TIME_TRACE = 16u       /* bracket every trace-kernel launch with CUDA events (read with trb_scene_trace_time) */
 };
 typedef struct trb_render_cfg {
     uint32_t spp;           /* Config.spp; 0 = film.samples. Rounded up to pow2 like ld.rs:22-26 */
@@ -344,6 +345,10 @@ trb_status trb_host_keyframe_transform(const trb_keyframe* kf, float* mat16, flo
 trb_status trb_desc_load_json(const char* path, uint32_t width, uint32_t height, uint32_t spp,
                               trb_scene_desc** out);
 void trb_desc_free(trb_scene_desc* desc);
+
+/* Device time spent in the dominant kernel (k_wf_trace) by launches made with TRB_RENDER_TIME_TRACE since the last
+ * call, measured with CUDA events on the launching stream; synchronises those events. */
+trb_status trb_scene_trace_time(trb_scene* scene, float* total_ms, uint32_t* n_launches);
 
 /* Number of CUDA kernels this library has launched in this process (monotonic). */
 unsigned long long trb_launch_count(void);

@@ -139,3 +139,18 @@ def test_loader_rejects_bad_json(tmp_path, trb):
                  ' "filter": {"type": "box", "width": 1, "height": 1}}}')
     assert trb.trb_desc_load_json(str(p).encode(), 0, 0, 0, C.byref(d)) == F.TRB_INVALID_ARG
     assert b"Unrecognized filter type" in trb.trb_last_error()
+
+
+def test_cpp_host_mirror_compiles_and_reports_no_device(tmp_path):
+    """include/tray_exec.hpp (the C++ mirror of Exec / Scene / RenderTarget / Config) builds against libtrb.so; without a
+    GPU the example must fail loudly with a status, never render on the host."""
+    import subprocess, torch
+    exe = str(tmp_path / "render_cornell")
+    lib = os.path.join(REPO, "tray_rust_b200", "lib")
+    subprocess.run(["g++", "-std=c++17", "-I" + os.path.join(REPO, "include"), os.path.join(REPO, "examples", "render_cornell.cpp"),
+                    "-L" + lib, "-ltrb", "-Wl,-rpath," + lib, "-o", exe], check=True)
+    r = subprocess.run([exe, os.path.join(SCENES, "c1_cornell_box.json"), "32", "32", "2"], capture_output=True, text=True, cwd=str(tmp_path))
+    if torch.cuda.is_available():
+        assert r.returncode == 0 and "rendering took" in r.stdout
+    else:
+        assert r.returncode == 1 and "status" in r.stderr

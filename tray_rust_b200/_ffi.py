@@ -20,7 +20,7 @@ INST_RECEIVER, INST_EMITTER_AREA, INST_EMITTER_POINT = 0, 1, 2
 SHAPE_NONE, SHAPE_SPHERE, SHAPE_DISK, SHAPE_RECT, SHAPE_MESH = 0, 1, 2, 3, 4
 MAT_MATTE, MAT_PLASTIC, MAT_METAL, MAT_SPECULAR_METAL, MAT_GLASS, MAT_ROUGH_GLASS, MAT_MERL = range(7)
 FILTER_MITCHELL_NETRAVALI, FILTER_GAUSSIAN = 0, 1
-RENDER_STATS, RENDER_NO_UPDATE, RENDER_REFERENCE_SHADOW, RENDER_MEGAKERNEL = 1, 2, 4, 8
+RENDER_STATS, RENDER_NO_UPDATE, RENDER_REFERENCE_SHADOW, RENDER_MEGAKERNEL, RENDER_TIME_TRACE = 1, 2, 4, 8, 16
 MISS = 0xFFFFFFFF
 BVH_LEAF = 0x80000000
 MERL_TABLE_FLOATS = 90 * 90 * 180 * 3
@@ -130,7 +130,7 @@ TRB_SYMBOLS = [
     "trb_render", "trb_render_device", "trb_intersect", "trb_intersect_device", "trb_camera_rays",
     "trb_render_samples", "trb_film_to_srgb8", "trb_block_list", "trb_scene_get_bvh", "trb_scene_get_transform",
     "trb_scene_get_filter_table", "trb_last_error", "trb_abi_version", "trb_desc_load_json", "trb_desc_free",
-    "trb_host_build_bvh", "trb_host_keyframe_transform", "trb_launch_count",
+    "trb_host_build_bvh", "trb_host_keyframe_transform", "trb_launch_count", "trb_scene_trace_time",
 ]
 
 _trb = None
@@ -177,6 +177,7 @@ def load_trb():
     lib.trb_host_build_bvh.argtypes = [vp, u32, u32, C.POINTER(u32), vp, vp]
     lib.trb_host_keyframe_transform.argtypes = [C.POINTER(Keyframe), vp, vp]
     lib.trb_launch_count.restype = C.c_uint64
+    lib.trb_scene_trace_time.argtypes = [vp, C.POINTER(f32), C.POINTER(u32)]
     _trb = lib
     return lib
 

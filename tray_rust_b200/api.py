@@ -112,6 +112,12 @@ class Scene(_Base):
         cfg = _cfg(**kw)
         self._check(self._lib.trb_render_device(self._h, C.byref(cfg), d_film_ptr, d_stats_ptr, stream))
 
+    def trace_time(self):
+        """(total ms, launches) of the trace kernel for launches made with RENDER_TIME_TRACE since the last call."""
+        ms, n = F.f32(), F.u32()
+        self._check(self._lib.trb_scene_trace_time(self._h, C.byref(ms), C.byref(n)))
+        return ms.value, n.value
+
     def render_samples(self, **kw):
         cfg = _cfg(**kw)
         n = self._n_samples(cfg)

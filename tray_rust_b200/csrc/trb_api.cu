@@ -135,8 +135,12 @@ struct trb_scene {
     trb::WfState wf{};
     size_t wf_capacity = 0;
     std::vector<void*> wf_allocs;
+    std::vector<std::pair<cudaEvent_t, cudaEvent_t>> trace_events; // TRB_RENDER_TIME_TRACE
+    std::vector<std::pair<cudaEvent_t, cudaEvent_t>> event_pool;
     ~trb_scene() {
         for (void* p : wf_allocs) cudaFree(p);
+        for (auto& e : trace_events) { cudaEventDestroy(e.first); cudaEventDestroy(e.second); }
+        for (auto& e : event_pool) { cudaEventDestroy(e.first); cudaEventDestroy(e.second); }
         if (h_film_staging) cudaFreeHost(h_film_staging);
         if (ev0) cudaEventDestroy(ev0);
         if (ev1) cudaEventDestroy(ev1);
@@ -297,10 +301,17 @@ trb_status launch_wavefront(trb_scene* s, const trb::RenderParams& rp, uint32_t 
         static const int occ = getenv("TRB_TRACE_OCC") ? atoi(getenv("TRB_TRACE_OCC")) : 6;
         static const unsigned tg = getenv("TRB_TRACE_GRID") ? (unsigned)atoi(getenv("TRB_TRACE_GRID")) : 12u;
         const unsigned tgrid = (unsigned)s->sm_count * tg;
+        std::pair<cudaEvent_t, cudaEvent_t> ev{nullptr, nullptr};
+        if (flags & TRB_RENDER_TIME_TRACE) {
+            if (!s->event_pool.empty()) { ev = s->event_pool.back(); s->event_pool.pop_back(); }
+            else { CU(cudaEventCreate(&ev.first)); CU(cudaEventCreate(&ev.second)); }
+            CU(cudaEventRecord(ev.first, st));
+        }
         if (stats) trb::k_wf_trace<true, 4><<<tgrid, 128, 0, st>>>(s->ds, rp, wf, round, flags, refill);
         else if (occ >= 8) trb::k_wf_trace<false, 8><<<tgrid, 128, 0, st>>>(s->ds, rp, wf, round, flags, refill);
         else if (occ >= 6) trb::k_wf_trace<false, 6><<<tgrid, 128, 0, st>>>(s->ds, rp, wf, round, flags, refill);
         else trb::k_wf_trace<false, 4><<<tgrid, 128, 0, st>>>(s->ds, rp, wf, round, flags, refill);
+        if (ev.first) { CU(cudaEventRecord(ev.second, st)); s->trace_events.push_back(ev); }
         if (mode == 0) trb::k_wf_shade<0><<<shade_grid, 128, 0, st>>>(s->ds, rp, wf, round);
         else trb::k_wf_shade<1><<<shade_grid, 128, 0, st>>>(s->ds, rp, wf, round);
         g_launches += 2;
@@ -343,6 +354,22 @@ const char* trb_last_error(void) { return g_error.c_str(); }
 void trb_internal_set_error(const char* msg) { g_error = msg ? msg : ""; } // used by trb_loader.cpp
 uint32_t trb_abi_version(void) { return TRB_ABI_VERSION; }
 unsigned long long trb_launch_count(void) { return g_launches; }
+
+trb_status trb_scene_trace_time(trb_scene* s, float* total_ms, uint32_t* n_launches) {
+    if (!s || !total_ms || !n_launches) return fail(TRB_INVALID_ARG, "null argument");
+    CU(cudaSetDevice(s->device));
+    float total = 0.f;
+    for (auto& e : s->trace_events) {
+        CU(cudaEventSynchronize(e.second));
+        float ms = 0.f;
+        CU(cudaEventElapsedTime(&ms, e.first, e.second));
+        total += ms;
+        s->event_pool.push_back(e);
+    }
+    *total_ms = total; *n_launches = (uint32_t)s->trace_events.size();
+    s->trace_events.clear();
+    return TRB_OK;
+}
 
 trb_status trb_scene_create(const trb_scene_desc* d, int device, trb_scene** out) {
     if (!out) return fail(TRB_INVALID_ARG, "null out pointer");
