@@ -90,15 +90,24 @@ class ClockSampler:
         return {"sm_mhz": float(np.median(sm)) if sm else None, "sm_max_mhz": max(mx) if mx else None, "reasons": sorted(reasons), "samples": len(sm)}
 
 
+def host_threads():
+    """All host cores this process may use (torchrun exports OMP_NUM_THREADS=1, so the count is passed explicitly)."""
+    try:
+        return len(os.sched_getaffinity(0))
+    except Exception:
+        return os.cpu_count() or 1
+
+
 def build_scene_desc(a):
     from tray_rust_b200 import scenebuild as SB
     return SB.scene_c4(a.tris, a.width, a.height, a.spp).finish()
 
 
-def cpu_baseline(a, desc, threads=0):
+def cpu_baseline(a, desc, threads=None):
     """The oracle port (kind "port": the Rust reference cannot be built here) on the host cores, baseline mode
     (per-ray transform recomposition like the reference), on a bounded sample of the same workload."""
     from tray_rust_b200 import api, _ffi as F
+    threads = threads or host_threads()
     o = api.OracleScene(desc, "det", baseline=True)
     o.update_frame(0, 0.0, 0.0)
     nb = o.n_blocks()
@@ -116,7 +125,7 @@ def cpu_baseline(a, desc, threads=0):
     t0 = time.time()
     _, st = o.render(threads=threads, flags=F.RENDER_NO_UPDATE, block_start=start, block_count=count, sample_first=0, sample_count=1, seed=a.seed)
     dt = time.time() - t0
-    cores = threads if threads > 0 else (os.cpu_count() or 1)
+    cores = threads
     out = {"value": st.rays_total() / dt / 1e6, "unit": "Mrays/s", "cores": cores, "kind": "port",
            "sample": "%d of %d Morton blocks (8x8 px) x 1 spp of the same C4 scene, %.1f s wall, oracle baseline mode, %d threads" % (count, nb, dt, cores),
            "samples_per_s": st.camera_samples / dt}
@@ -134,18 +143,18 @@ def run_reference(a):
     o = api.OracleScene(desc, "det", baseline=True)
     o.update_frame(0, 0.0, 0.0)
     nb = o.n_blocks()
-    count = min(nb, 1200)  # bounded sample per step: ~0.6 M camera samples -> seconds of CPU work
+    cores = host_threads()
+    count = min(nb, 75 * cores)  # bounded sample per step, a few seconds of CPU work on every core
     start = nb // 2 - count // 2
     times, rays, samples = [], 0, 0
     for it in range(a.warmup + a.steps):
         t0 = time.time()
-        _, st = o.render(threads=0, flags=F.RENDER_NO_UPDATE, block_start=start, block_count=count, sample_first=it, sample_count=1, seed=a.seed)
+        _, st = o.render(threads=cores, flags=F.RENDER_NO_UPDATE, block_start=start, block_count=count, sample_first=it, sample_count=1, seed=a.seed)
         dt = time.time() - t0
         if it >= a.warmup:
             times.append(dt); rays += st.rays_total(); samples += st.camera_samples
     total = sum(times)
     v = rays / total / 1e6
-    cores = os.cpu_count() or 1
     line = {"impl": "reference", "metric": METRIC, "value": v, "unit": "Mrays/s", "n_gpus": a.gpus, "steps": a.steps, "warmup": a.warmup,
             "ms_per_step": 1e3 * total / a.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
             "config": {"workload": WORKLOAD, "tris": a.tris, "width": a.width, "height": a.height, "spp": a.spp},
