@@ -298,7 +298,7 @@ trb_status launch_wavefront(trb_scene* s, const trb::RenderParams& rp, uint32_t 
     const unsigned trace_grid = (unsigned)s->sm_count * 12, shade_grid = (unsigned)s->sm_count * 4;
     for (uint32_t round = 0; round < rounds; ++round) {
         static const int refill = getenv("TRB_REFILL") ? atoi(getenv("TRB_REFILL")) : 8;
-        static const int occ = getenv("TRB_TRACE_OCC") ? atoi(getenv("TRB_TRACE_OCC")) : 6;
+        static const int occ = getenv("TRB_TRACE_OCC") ? atoi(getenv("TRB_TRACE_OCC")) : 7;
         static const unsigned tg = getenv("TRB_TRACE_GRID") ? (unsigned)atoi(getenv("TRB_TRACE_GRID")) : 12u;
         const unsigned tgrid = (unsigned)s->sm_count * tg;
         std::pair<cudaEvent_t, cudaEvent_t> ev{nullptr, nullptr};
@@ -307,10 +307,13 @@ trb_status launch_wavefront(trb_scene* s, const trb::RenderParams& rp, uint32_t 
             else { CU(cudaEventCreate(&ev.first)); CU(cudaEventCreate(&ev.second)); }
             CU(cudaEventRecord(ev.first, st));
         }
-        if (stats) trb::k_wf_trace<true, 4><<<tgrid, 128, 0, st>>>(s->ds, rp, wf, round, flags, refill);
-        else if (occ >= 8) trb::k_wf_trace<false, 8><<<tgrid, 128, 0, st>>>(s->ds, rp, wf, round, flags, refill);
-        else if (occ >= 6) trb::k_wf_trace<false, 6><<<tgrid, 128, 0, st>>>(s->ds, rp, wf, round, flags, refill);
-        else trb::k_wf_trace<false, 4><<<tgrid, 128, 0, st>>>(s->ds, rp, wf, round, flags, refill);
+        static const int sst = getenv("TRB_SMEM_STACK") ? atoi(getenv("TRB_SMEM_STACK")) : 16;
+#define TRB_TRACE_LAUNCH(ST, MB, SS) trb::k_wf_trace<ST, MB, SS><<<tgrid, 128, 0, st>>>(s->ds, rp, wf, round, flags, refill)
+        if (stats) TRB_TRACE_LAUNCH(true, 4, 16);
+        else if (occ >= 8) { if (sst <= 8) TRB_TRACE_LAUNCH(false, 8, 8); else if (sst <= 12) TRB_TRACE_LAUNCH(false, 8, 12); else TRB_TRACE_LAUNCH(false, 8, 16); }
+        else if (occ >= 7) { if (sst <= 8) TRB_TRACE_LAUNCH(false, 7, 8); else if (sst <= 12) TRB_TRACE_LAUNCH(false, 7, 12); else TRB_TRACE_LAUNCH(false, 7, 16); }
+        else { if (sst <= 8) TRB_TRACE_LAUNCH(false, 6, 8); else if (sst <= 12) TRB_TRACE_LAUNCH(false, 6, 12); else TRB_TRACE_LAUNCH(false, 6, 16); }
+#undef TRB_TRACE_LAUNCH
         if (ev.first) { CU(cudaEventRecord(ev.second, st)); s->trace_events.push_back(ev); }
         if (mode == 0) trb::k_wf_shade<0><<<shade_grid, 128, 0, st>>>(s->ds, rp, wf, round);
         else trb::k_wf_shade<1><<<shade_grid, 128, 0, st>>>(s->ds, rp, wf, round);
