@@ -205,7 +205,7 @@ struct LocalStack {
     __device__ __forceinline__ void put(int i, unsigned long long v) const { s[i] = v; }
     __device__ __forceinline__ unsigned long long get(int i) const { return s[i]; }
 };
-constexpr int SMEM_STACK = 16;
+template <int SMEM_STACK>
 struct HybridStack {
     unsigned long long* sm; // &smem[0][threadIdx.x], stride = blockDim.x
     unsigned long long* lo;
@@ -1278,7 +1278,7 @@ __global__ void __launch_bounds__(256) k_wf_generate(const __grid_constant__ DSc
 // whose ray has finished writes its result and, once enough lanes of the warp are idle, the idle lanes
 // fetch new rays with one warp-aggregated atomic, so rays of very different lengths (an any-hit shadow
 // ray vs. a continuation ray crossing the whole mesh) do not leave the warp mostly empty.
-template <bool STATS, int MINB>
+template <bool STATS, int MINB, int SMEM_STACK>
 __global__ void __launch_bounds__(128, MINB) k_wf_trace(const __grid_constant__ DScene sc, const __grid_constant__ RenderParams rp, const __grid_constant__ WfState wf,
                                                          uint32_t round, uint32_t flags, int WF_REFILL_IDLE) {
     uint32_t* cnt_r = wf.counters + round * WF_CNT;
@@ -1291,7 +1291,7 @@ __global__ void __launch_bounds__(128, MINB) k_wf_trace(const __grid_constant__ 
     TraceState t;
     __shared__ unsigned long long s_stack[SMEM_STACK * 128];
     unsigned long long stack_lo[STACK_DEPTH - SMEM_STACK];
-    const HybridStack stack{s_stack + threadIdx.x, stack_lo, 128};
+    const HybridStack<SMEM_STACK> stack{s_stack + threadIdx.x, stack_lo, 128};
     t.cur = ST_DONE;
     bool have = false, exhausted = false;
     uint32_t p = 0;
