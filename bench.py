@@ -225,7 +225,7 @@ def run_ours(a):
         flush.fill_(i & 0xFF)
         kev[k][0].record()
         g.render_device(film.data_ptr(), stats.data_ptr(), stream, spp=a.spp, sample_first=i * spp_step, sample_count=spp_step,
-                        block_start=bstart, block_count=bcount, seed=a.seed, flags=F.RENDER_TIME_TRACE)
+                        block_start=bstart, block_count=bcount, seed=a.seed)
         kev[k][1].record()
         if world > 1:
             reduce_film(film, dst=0)
@@ -234,7 +234,6 @@ def run_ours(a):
     if world > 1:
         dist.barrier()
     launches = lib.trb_launch_count() - launches0
-    trace_ms, trace_launches = g.trace_time()      # CUDA events around every k_wf_trace launch of the timed steps
     clk = clocks.stop() if rank == 0 else None
     total_ms = max_over_ranks(e_begin.elapsed_time(e_end), dev)
     kernel_ms = [kev[k][0].elapsed_time(kev[k][1]) for k in range(a.steps)]
@@ -242,9 +241,18 @@ def run_ours(a):
     tot = sum_over_ranks([st[0], st[1], st[2], st[3], st[4]], dev)     # samples, primary, shadow, mis, continuation (all ranks)
     rays_all = sum(tot[1:5])
 
-    # --- roofline of the dominant kernel: untimed replay of this rank's timed passes with the test counters on
+    # --- roofline of the dominant kernel (k_wf_trace), from two untimed replays of this rank's timed passes:
+    #     (1) CUDA events around every trace launch -> its duration; (2) the test counters on -> its algorithmic bytes
     cstats = torch.zeros(10, dtype=torch.int64, device=dev)
     scratch = torch.zeros_like(film)
+    for k in range(a.steps):
+        i = a.warmup + k
+        flush.fill_(i & 0xFF)
+        g.render_device(scratch.data_ptr(), cstats.data_ptr(), stream, spp=a.spp, sample_first=i * spp_step, sample_count=spp_step,
+                        block_start=bstart, block_count=bcount, seed=a.seed, flags=F.RENDER_TIME_TRACE)
+    torch.cuda.synchronize()
+    trace_ms, trace_launches = g.trace_time()
+    cstats.zero_()
     for k in range(a.steps):
         i = a.warmup + k
         g.render_device(scratch.data_ptr(), cstats.data_ptr(), stream, spp=a.spp, sample_first=i * spp_step, sample_count=spp_step,
@@ -328,7 +336,7 @@ def run_ours(a):
             "roofline": {"bound": "hbm", "kernel": "k_wf_trace", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
                          "peak_source": "MEASURED_PEAKS.json hbm_gbs (measured)" if peaks else "fallback 6650 GB/s",
                          "traffic": traffic, "algorithmic_bytes_per_launch": bytes_per_launch, "launches": trace_launches,
-                         "avg_launch_ms": trace_ms / trace_launches, "share_of_step": trace_ms / (avg_kernel_ms * a.steps),
+                         "avg_launch_ms": trace_ms / trace_launches, "trace_ms_per_step": trace_ms / a.steps,
                          "step_kernels_ms": avg_kernel_ms,
                          "per_ray": {"node_tests": cs[5] / max(1, rank_rays), "tri_tests": cs[6] / max(1, rank_rays), "inst_tests": cs[7] / max(1, rank_rays)}},
             "primary_shadow_only": direct,
