@@ -287,11 +287,13 @@ def run_ours(a):
                   "ms_per_step": dms / a.steps, "note": "same C4 scene, pathtracer max_depth 0: one primary + one (any-hit) shadow ray per camera sample"}
         g0.close()
 
-    # --- e2e: the reference-facing call (host film, update_frame + H2D + kernels + D2H inside the timed region)
-    e2e = None
+    # --- e2e: through the public API with host buffers; per step: Scene::update_frame (TLAS rebuild + H2D upload),
+    #     the kernels, the film reduce (N > 1) and the film D2H copy, all inside the timed region
+    n_inst = desc.n_instances
+    h2d = n_inst * 176 + (2 * n_inst) * 64 + n_inst * 4 + 32 + 32   # instances + TLAS records (<= 2n) + order + header + config
+    e2e_steps = max(2, min(a.steps, 4))
     if world == 1:
         hfilm = np.zeros((a.height, a.width, 4), np.float32)
-        e2e_steps = max(2, min(a.steps, 4))
         g.render(hfilm, spp=a.spp, sample_first=0, sample_count=spp_step, seed=a.seed)   # warm
         rays_e, t_e = 0, 0.0
         for k in range(e2e_steps):
@@ -299,10 +301,27 @@ def run_ours(a):
             _, s_e = g.render(hfilm, spp=a.spp, sample_first=(a.warmup + k) * spp_step, sample_count=spp_step, seed=a.seed)
             t_e += time.perf_counter() - t0
             rays_e += s_e.rays_total()
-        n_inst = desc.n_instances
-        h2d = n_inst * 176 + (2 * n_inst) * 32 + n_inst * 4 + 32      # instances + TLAS nodes (<= 2n-1) + order + config
-        e2e = {"value": rays_e / t_e / 1e6, "unit": "Mrays/s", "h2d_bytes_per_step": int(h2d), "d2h_bytes_per_step": int(a.width * a.height * 16 + 80),
-               "ms_per_step": 1e3 * t_e / e2e_steps, "steps": e2e_steps, "api": "trb_render (Exec::render): update_frame + kernels + film D2H"}
+        api_name = "trb_render (Exec::render): update_frame + kernels + film D2H"
+    else:
+        pinned = torch.empty((a.height, a.width, 4), dtype=torch.float32, pin_memory=True) if rank == 0 else None
+        estats = torch.zeros(10, dtype=torch.int64, device=dev)
+        dist.barrier(); torch.cuda.synchronize()
+        t0 = time.perf_counter()
+        for k in range(e2e_steps):
+            film.zero_()
+            g.update_frame(0, 0.0, 0.0)
+            g.render_device(film.data_ptr(), estats.data_ptr(), stream, spp=a.spp, sample_first=(a.warmup + k) * spp_step, sample_count=spp_step,
+                            block_start=bstart, block_count=bcount, seed=a.seed)
+            reduce_film(film, dst=0)
+            if rank == 0:
+                pinned.copy_(film, non_blocking=True)
+            torch.cuda.synchronize()
+        dist.barrier()
+        t_e = max_over_ranks(time.perf_counter() - t0, dev)
+        rays_e = sum(sum_over_ranks(estats.cpu().numpy()[1:5].tolist(), dev))
+        api_name = "per rank: trb_scene_update_frame + trb_render_device on its tile shard, NCCL film reduce, rank-0 film D2H"
+    e2e = {"value": rays_e / t_e / 1e6, "unit": "Mrays/s", "h2d_bytes_per_step": int(h2d), "d2h_bytes_per_step": int(a.width * a.height * 16 + 80),
+           "ms_per_step": 1e3 * t_e / e2e_steps, "steps": e2e_steps, "api": api_name}
 
     cpu = None
     if rank == 0 and world == 1 and not a.no_cpu_baseline:
