@@ -169,7 +169,7 @@ def run_ours(a):
     import torch
     import torch.distributed as dist
     from tray_rust_b200 import api, _ffi as F
-    from tray_rust_b200.dist import shard_blocks, reduce_film, max_over_ranks, sum_over_ranks
+    from tray_rust_b200.dist import shard_interleaved, reduce_film, max_over_ranks, sum_over_ranks
 
     world = int(os.environ.get("WORLD_SIZE", "1"))
     rank = int(os.environ.get("RANK", "0"))
@@ -179,6 +179,8 @@ def run_ours(a):
     torch.cuda.set_device(local)
     dev = torch.device("cuda", local)
     if world > 1:
+        if os.environ.get("NCCL_DEBUG", "VERSION").upper() == "VERSION":
+            os.environ["NCCL_DEBUG"] = "WARN"      # keep stdout to the one JSON line
         dist.init_process_group("nccl", device_id=dev)
     lib = F.load_trb()
 
@@ -188,7 +190,8 @@ def run_ours(a):
     create_s = time.time() - t0
     g.update_frame(0, 0.0, 0.0)
     nb = g.n_blocks()
-    bstart, bcount = shard_blocks(nb, rank, world)
+    shard = shard_interleaved(rank, world, chunk=32)   # contiguous ranges (master.rs) leave the ranks unevenly loaded
+    bstart, bcount = 0, 0
     spp_step = a.spp_per_step * world            # weak scaling: N x the samples per pixel per step, tile-sharded
     n_total = a.warmup + a.steps
     assert spp_step * n_total <= g.spp, "not enough spp in the frame for the requested steps"
@@ -201,7 +204,7 @@ def run_ours(a):
     def step(i, flags=0, st=stats):
         flush.fill_(i & 0xFF)                                         # L2 flush between timed iterations
         g.render_device(film.data_ptr(), st.data_ptr(), stream, spp=a.spp, sample_first=i * spp_step, sample_count=spp_step,
-                        block_start=bstart, block_count=bcount, seed=a.seed, flags=flags)
+                        block_start=bstart, block_count=bcount, seed=a.seed, **shard, flags=flags)
         if world > 1:
             reduce_film(film, dst=0)
 
@@ -225,7 +228,7 @@ def run_ours(a):
         flush.fill_(i & 0xFF)
         kev[k][0].record()
         g.render_device(film.data_ptr(), stats.data_ptr(), stream, spp=a.spp, sample_first=i * spp_step, sample_count=spp_step,
-                        block_start=bstart, block_count=bcount, seed=a.seed)
+                        block_start=bstart, block_count=bcount, seed=a.seed, **shard)
         kev[k][1].record()
         if world > 1:
             reduce_film(film, dst=0)
@@ -249,14 +252,14 @@ def run_ours(a):
         i = a.warmup + k
         flush.fill_(i & 0xFF)
         g.render_device(scratch.data_ptr(), cstats.data_ptr(), stream, spp=a.spp, sample_first=i * spp_step, sample_count=spp_step,
-                        block_start=bstart, block_count=bcount, seed=a.seed, flags=F.RENDER_TIME_TRACE)
+                        block_start=bstart, block_count=bcount, seed=a.seed, **shard, flags=F.RENDER_TIME_TRACE)
     torch.cuda.synchronize()
     trace_ms, trace_launches = g.trace_time()
     cstats.zero_()
     for k in range(a.steps):
         i = a.warmup + k
         g.render_device(scratch.data_ptr(), cstats.data_ptr(), stream, spp=a.spp, sample_first=i * spp_step, sample_count=spp_step,
-                        block_start=bstart, block_count=bcount, seed=a.seed, flags=F.RENDER_STATS)
+                        block_start=bstart, block_count=bcount, seed=a.seed, **shard, flags=F.RENDER_STATS)
     torch.cuda.synchronize()
     cs = cstats.cpu().numpy()
     rank_rays = int(cs[1:5].sum())
@@ -311,7 +314,7 @@ def run_ours(a):
             film.zero_()
             g.update_frame(0, 0.0, 0.0)
             g.render_device(film.data_ptr(), estats.data_ptr(), stream, spp=a.spp, sample_first=(a.warmup + k) * spp_step, sample_count=spp_step,
-                            block_start=bstart, block_count=bcount, seed=a.seed)
+                            block_start=bstart, block_count=bcount, seed=a.seed, **shard)
             reduce_film(film, dst=0)
             if rank == 0:
                 pinned.copy_(film, non_blocking=True)
@@ -347,7 +350,7 @@ def run_ours(a):
             "metric": METRIC, "value": rays_all / (total_ms * 1e-3) / 1e6, "unit": "Mrays/s", "n_gpus": world, "steps": a.steps, "warmup": a.warmup,
             "ms_per_step": total_ms / a.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
             "config": {"workload": WORKLOAD, "tris": a.tris, "width": a.width, "height": a.height, "spp": a.spp, "spp_per_step": spp_step,
-                       "blocks_per_rank": bcount, "parallelism": "tile-sharded x%d (Morton block ranges) + film SUM-reduce" % world,
+                       "blocks_per_rank": nb // world, "parallelism": "tile-sharded x%d (interleaved 32-block chunks of the Morton block list) + film SUM-reduce" % world,
                        "l2": "256 MiB buffer written between timed steps (L2 flush)", "scene_create_s": round(create_s, 2)},
             "samples_per_s": tot[0] / (total_ms * 1e-3),
             "rays": {"primary": tot[1], "shadow": tot[2], "mis": tot[3], "continuation": tot[4],

@@ -26,7 +26,7 @@
 extern "C" {
 #endif
 
-#define TRB_ABI_VERSION 1u
+#define TRB_ABI_VERSION 2u
 
 typedef enum trb_status {
     TRB_OK = 0,
@@ -197,6 +197,10 @@ typedef struct trb_render_cfg {
     uint32_t current_frame; /* Config.current_frame */
     uint32_t seed;
     uint32_t flags;
+    /* Optional interleaved sharding of the selected block list for multi-GPU load balance: keep block j (index in the
+     * list after select_blocks) iff (j / shard_chunk) % shard_count == shard_index. shard_count <= 1 disables it. The
+     * reference shards by contiguous ranges only (master.rs:91-93); the union and the summed film are the same. */
+    uint32_t shard_index, shard_count, shard_chunk;
 } trb_render_cfg;
 
 typedef struct trb_stats {

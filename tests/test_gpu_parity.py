@@ -161,6 +161,13 @@ def test_full_size_properties_c4():
     _, s1 = g.render(half, block_start=nb // 2, block_count=nb - nb // 2, sample_first=0, sample_count=1, seed=3)
     assert np.allclose(full, half, rtol=1e-4, atol=1e-5)
     assert s0.rays_total() + s1.rays_total() == sf.rays_total() and sf.camera_samples == 1920 * 1080
+    # interleaved sharding (dist.shard_interleaved): the union of the 3 shards is the whole block list, films add up
+    from tray_rust_b200.dist import shard_interleaved
+    acc = np.zeros_like(full); rays_sh = 0
+    for r in range(3):
+        _, ss = g.render(acc, sample_first=0, sample_count=1, seed=3, **shard_interleaved(r, 3, chunk=32))
+        rays_sh += ss.rays_total()
+    assert rays_sh == sf.rays_total() and np.allclose(full, acc, rtol=1e-4, atol=1e-5)
     # every pixel got weight, weights are positive in the interior (Mitchell lobes sum > 0)
     assert (full[8:-8, 8:-8, 3] > 0).all()
     # hits: t > 0, triangle ids in range, and closest-hit == the minimum over a second, any-order query of the same ray

@@ -14,7 +14,7 @@ import os
 _HERE = os.path.dirname(os.path.abspath(__file__))
 REPO = os.path.dirname(_HERE)
 
-TRB_ABI_VERSION = 1
+TRB_ABI_VERSION = 2
 TRB_OK, TRB_INVALID_ARG, TRB_CUDA, TRB_OOM, TRB_UNSUPPORTED, TRB_IO, TRB_NO_DEVICE = range(7)
 INST_RECEIVER, INST_EMITTER_AREA, INST_EMITTER_POINT = 0, 1, 2
 SHAPE_NONE, SHAPE_SPHERE, SHAPE_DISK, SHAPE_RECT, SHAPE_MESH = 0, 1, 2, 3, 4
@@ -86,7 +86,8 @@ class SceneDesc(C.Structure):
 
 class RenderCfg(C.Structure):
     _fields_ = [("spp", u32), ("sample_first", u32), ("sample_count", u32), ("block_start", u32),
-                ("block_count", u32), ("current_frame", u32), ("seed", u32), ("flags", u32)]
+                ("block_count", u32), ("current_frame", u32), ("seed", u32), ("flags", u32),
+                ("shard_index", u32), ("shard_count", u32), ("shard_chunk", u32)]
 
 
 class Stats(C.Structure):

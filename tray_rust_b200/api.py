@@ -20,8 +20,10 @@ class TrbError(RuntimeError):
         self.status = status
 
 
-def _cfg(spp=0, sample_first=0, sample_count=0, block_start=0, block_count=0, current_frame=0, seed=1, flags=0):
-    return F.RenderCfg(spp, sample_first, sample_count, block_start, block_count, current_frame, seed, flags)
+def _cfg(spp=0, sample_first=0, sample_count=0, block_start=0, block_count=0, current_frame=0, seed=1, flags=0,
+         shard_index=0, shard_count=0, shard_chunk=0):
+    return F.RenderCfg(spp, sample_first, sample_count, block_start, block_count, current_frame, seed, flags,
+                       shard_index, shard_count, shard_chunk)
 
 
 class _Base:
@@ -29,6 +31,9 @@ class _Base:
 
     def _n_samples(self, cfg):
         nb = self.n_blocks(cfg.block_start, cfg.block_count)
+        if cfg.shard_count > 1:
+            ch = max(1, cfg.shard_chunk)
+            nb = sum(1 for j in range(nb) if (j // ch) % cfg.shard_count == cfg.shard_index)
         spp = self.spp if cfg.spp == 0 else 1 << (max(1, cfg.spp) - 1).bit_length()
         cnt = cfg.sample_count if cfg.sample_count else spp - cfg.sample_first
         return nb * 64 * cnt

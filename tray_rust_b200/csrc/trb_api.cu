@@ -123,7 +123,7 @@ struct trb_scene {
     uint2* d_blocks = nullptr;
     size_t blocks_capacity = 0;
     std::vector<uint32_t> cached_blocks;
-    uint32_t cached_block_start = 0xffffffffu, cached_block_count = 0xffffffffu;
+    uint32_t cached_block_start = 0xffffffffu, cached_block_count = 0xffffffffu, cached_shard[3] = {0, 0, 0};
     uint32_t* d_counter = nullptr;
     int* d_error = nullptr;
     trb::DStats* d_stats = nullptr;
@@ -223,9 +223,13 @@ trb_status validate(const trb_scene_desc* d) {
     return TRB_OK;
 }
 
-trb_status ensure_blocks(trb_scene* s, uint32_t start, uint32_t count, uint32_t* n_blocks) {
-    if (s->cached_block_start != start || s->cached_block_count != count) {
-        s->cached_blocks = morton_blocks(s->film.width, s->film.height, start, count);
+trb_status ensure_blocks(trb_scene* s, const trb_render_cfg* cfg, uint32_t* n_blocks) {
+    const uint32_t start = cfg->block_start, count = cfg->block_count;
+    if (cfg->shard_count > 1 && cfg->shard_index >= cfg->shard_count) return fail(TRB_INVALID_ARG, "shard_index must be < shard_count");
+    if (s->cached_block_start != start || s->cached_block_count != count || s->cached_shard[0] != cfg->shard_index ||
+        s->cached_shard[1] != cfg->shard_count || s->cached_shard[2] != cfg->shard_chunk) {
+        s->cached_blocks = morton_blocks(s->film.width, s->film.height, start, count, cfg->shard_index, cfg->shard_count, cfg->shard_chunk);
+        s->cached_shard[0] = cfg->shard_index; s->cached_shard[1] = cfg->shard_count; s->cached_shard[2] = cfg->shard_chunk;
         const size_t n = s->cached_blocks.size() / 2;
         if (n > s->blocks_capacity) {
             CU(s->arena.alloc(n, &s->d_blocks));
@@ -592,7 +596,7 @@ trb_status trb_render_device(trb_scene* s, const trb_render_cfg* cfg, float* d_f
     uint32_t spp, first, count, nb;
     trb_status r = resolve_samples(s, cfg, spp, first, count);
     if (r != TRB_OK) return r;
-    r = ensure_blocks(s, cfg->block_start, cfg->block_count, &nb);
+    r = ensure_blocks(s, cfg, &nb);
     if (r != TRB_OK) return r;
     if (nb == 0 || count == 0) return TRB_OK; // "Warning: This block queue is empty!" (block_queue.rs:42-44)
     trb::RenderParams rp{};
@@ -643,7 +647,7 @@ trb_status trb_render_samples(trb_scene* s, const trb_render_cfg* cfg, size_t n,
     uint32_t spp, first, count, nb;
     trb_status r = resolve_samples(s, cfg, spp, first, count);
     if (r != TRB_OK) return r;
-    r = ensure_blocks(s, cfg->block_start, cfg->block_count, &nb);
+    r = ensure_blocks(s, cfg, &nb);
     if (r != TRB_OK) return r;
     if (n != (size_t)nb * 64 * count) return fail(TRB_INVALID_ARG, "sample buffer size must be blocks*64*sample_count");
     if (n == 0) return TRB_OK;
@@ -679,7 +683,7 @@ trb_status trb_camera_rays(trb_scene* s, const trb_render_cfg* cfg, size_t n, tr
     uint32_t spp, first, count, nb;
     trb_status r = resolve_samples(s, cfg, spp, first, count);
     if (r != TRB_OK) return r;
-    r = ensure_blocks(s, cfg->block_start, cfg->block_count, &nb);
+    r = ensure_blocks(s, cfg, &nb);
     if (r != TRB_OK) return r;
     if (n != (size_t)nb * 64 * count) return fail(TRB_INVALID_ARG, "ray buffer size must be blocks*64*sample_count");
     if (n == 0) return TRB_OK;

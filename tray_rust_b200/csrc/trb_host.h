@@ -278,7 +278,8 @@ inline uint32_t spread_bits(uint32_t x) {
     x &= 0x0000ffffu; x = (x ^ (x << 8)) & 0x00ff00ffu; x = (x ^ (x << 4)) & 0x0f0f0f0fu; x = (x ^ (x << 2)) & 0x33333333u;
     return (x ^ (x << 1)) & 0x55555555u;
 }
-inline std::vector<uint32_t> morton_blocks(uint32_t w, uint32_t h, uint32_t start, uint32_t count) {
+inline std::vector<uint32_t> morton_blocks(uint32_t w, uint32_t h, uint32_t start, uint32_t count, uint32_t shard_index = 0,
+                                           uint32_t shard_count = 0, uint32_t shard_chunk = 0) {
     const uint32_t nbx = w / 8, nby = h / 8;
     std::vector<std::pair<uint32_t, uint32_t>> keyed(nbx * nby); // (morton, linear)
     for (uint32_t i = 0; i < nbx * nby; ++i) keyed[i] = {(spread_bits(i / nbx) << 1) + spread_bits(i % nbx), i};
@@ -286,7 +287,11 @@ inline std::vector<uint32_t> morton_blocks(uint32_t w, uint32_t h, uint32_t star
     std::vector<uint32_t> out;
     size_t b0 = 0, b1 = keyed.size();
     if (count > 0) { b0 = std::min<size_t>(start, keyed.size()); b1 = std::min<size_t>(keyed.size(), (size_t)start + count); }
-    for (size_t i = b0; i < b1; ++i) { out.push_back(keyed[i].second % nbx); out.push_back(keyed[i].second / nbx); }
+    const uint32_t chunk = shard_chunk ? shard_chunk : 1;
+    for (size_t i = b0; i < b1; ++i) {
+        if (shard_count > 1 && ((i - b0) / chunk) % shard_count != shard_index) continue; // interleaved multi-GPU sharding
+        out.push_back(keyed[i].second % nbx); out.push_back(keyed[i].second / nbx);
+    }
     return out;
 }
 

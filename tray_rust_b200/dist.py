@@ -16,6 +16,13 @@ def shard_blocks(n_blocks, rank, world):
     return start, count
 
 
+def shard_interleaved(rank, world, chunk=32):
+    """Load-balanced alternative: rank r takes every world-th chunk of `chunk` consecutive blocks of the Morton list
+    (render-cfg fields shard_index / shard_count / shard_chunk). Same union, same summed film; image regions of very
+    different cost (e.g. rays that leave the scene) are spread over all ranks instead of landing on one."""
+    return dict(shard_index=rank, shard_count=world, shard_chunk=chunk) if world > 1 else {}
+
+
 def reduce_film(film, dst=0, group=None):
     """Sum the per-rank RGBW films into rank `dst` (in place). `film` is a torch tensor on the rank's device."""
     if not dist.is_initialized() or dist.get_world_size(group) == 1:
