@@ -178,9 +178,11 @@ def run_ours(a):
         raise RuntimeError("bench.py needs a CUDA device: tray_rust_b200 has no CPU fallback")
     torch.cuda.set_device(local)
     dev = torch.device("cuda", local)
+    # stdout carries exactly one JSON line: anything a library prints to fd 1 (e.g. NCCL's version banner) goes to stderr
+    sys.stdout.flush()
+    json_out = os.fdopen(os.dup(1), "w")
+    os.dup2(2, 1)
     if world > 1:
-        if os.environ.get("NCCL_DEBUG", "VERSION").upper() == "VERSION":
-            os.environ["NCCL_DEBUG"] = "WARN"      # keep stdout to the one JSON line
         dist.init_process_group("nccl", device_id=dev)
     lib = F.load_trb()
 
@@ -364,7 +366,8 @@ def run_ours(a):
             "primary_shadow_only": direct,
             "gpu_launches": int(launches), "clocks": clk, "e2e": e2e, "cpu_baseline": cpu,
         }
-        print(json.dumps(line, default=float))
+        json_out.write(json.dumps(line, default=float) + "\n")
+        json_out.flush()
     g.close()
     if world > 1:
         dist.destroy_process_group()
