@@ -344,6 +344,14 @@ trb_status trb_host_build_bvh(const float* boxes6, uint32_t n, uint32_t max_geom
 /* Keyframe::transform (keyframe.rs:60-63): T * R * S and its inverse, row-major. */
 trb_status trb_host_keyframe_transform(const trb_keyframe* kf, float* mat16, float* inv16);
 
+/* AnimatedTransform::transform(time) (animated_transform.rs:40-56) of the transform stack
+ * desc->splines[first .. first+count): the same code the device runs per ray for keyframed
+ * instances, compiled for the host. AnimatedColor::color(time) (animated_color.rs:52-78) of
+ * desc->color_keys[first .. first+count) likewise. */
+trb_status trb_host_animated_transform(const trb_scene_desc* desc, uint32_t first, uint32_t count, float time,
+                                       float* mat16, float* inv16);
+trb_status trb_host_animated_color(const trb_scene_desc* desc, uint32_t first, uint32_t count, float time, float* rgb3);
+
 /* The JSON loader alone (Scene::load_file up to the flattened description): the result is
  * owned by the library; release with trb_desc_free. */
 trb_status trb_desc_load_json(const char* path, uint32_t width, uint32_t height, uint32_t spp,

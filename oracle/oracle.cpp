@@ -350,12 +350,14 @@ int orc_scene_get_filter_table(const orc_scene* s, float* t) { memcpy(t, s->rt.t
 /* Scene::intersect over a batch (scene.rs:148-150) */
 int orc_intersect(orc_scene* s, size_t n, const trb_ray* rays, trb_hit* hits, trb_stats* stats) {
     Counters total;
+    /* batch rays carry no time: they are traced at the frame's shutter-open time */
+    const float t0 = s->active_camera >= 0 ? s->cameras[s->active_camera].shutter_open : 0.0f;
 #pragma omp parallel
     {
         Counters cnt;
 #pragma omp for schedule(dynamic, 1024)
         for (long i = 0; i < (long)n; ++i) {
-            Ray r = Ray::segment(V3(rays[i].o[0], rays[i].o[1], rays[i].o[2]), V3(rays[i].d[0], rays[i].d[1], rays[i].d[2]), rays[i].min_t, rays[i].max_t, 0.0f);
+            Ray r = Ray::segment(V3(rays[i].o[0], rays[i].o[1], rays[i].o[2]), V3(rays[i].d[0], rays[i].d[1], rays[i].d[2]), rays[i].min_t, rays[i].max_t, t0);
             Hit h;
             bool hit = s->geom.intersect(r, h, cnt);
             hits[i].t = r.max_t; hits[i].inst = hit ? h.inst : TRB_MISS; hits[i].prim = hit ? h.prim : 0; hits[i].pad = 0;

@@ -149,19 +149,6 @@ struct trb_scene {
 
 namespace {
 
-// AnimatedTransform::transform for an instance whose splines all hold one control point
-// (animated_transform.rs:42-54: transform = t_i * transform, starting from the identity).
-bool static_world_xf(const trb_scene& s, uint32_t first, uint32_t n, Xf& out) {
-    Xf acc = xf_identity();
-    for (uint32_t i = first; i < first + n; ++i) {
-        const trb_spline& sp = s.splines[i];
-        if (sp.n_ctrl != 1) return false;
-        acc = xf_compose(keyframe_xf(s.keyframes[sp.ctrl_first]), acc);
-    }
-    out = acc;
-    return true;
-}
-
 Box3 shape_bounds(const trb_scene& s, const trb_instance& in) {
     Box3 b;
     switch (in.shape) {
@@ -198,17 +185,22 @@ trb_status validate(const trb_scene_desc* d) {
         if (in.kind != TRB_INST_RECEIVER) {
             light = true;
             if (in.n_emission == 0 || in.emission_first + in.n_emission > d->n_color_keys) return fail(TRB_INVALID_ARG, "An emission color is required for emitters");
-            if (in.n_emission > 1) return fail(TRB_UNSUPPORTED, "keyframed emission is not implemented (DESIGN.md: next)");
         }
-        for (uint32_t k = in.spline_first; k < in.spline_first + in.n_splines; ++k)
-            if (d->splines[k].n_ctrl != 1) return fail(TRB_UNSUPPORTED, "animated instance transforms are not implemented (DESIGN.md: next, row N1)");
+    }
+    for (uint32_t k = 0; k < d->n_splines; ++k) { // BSpline::new's invariants (bspline.rs:37-45) + the device evaluator's degree cap
+        const trb_spline& sp = d->splines[k];
+        if (sp.n_ctrl == 0 || sp.ctrl_first + sp.n_ctrl > d->n_keyframes) return fail(TRB_INVALID_ARG, "spline control points out of bounds");
+        if (sp.n_ctrl > 1) {
+            if (sp.knot_first + sp.n_knots > d->n_knots) return fail(TRB_INVALID_ARG, "spline knots out of bounds");
+            if (sp.n_knots != sp.n_ctrl + sp.degree + 1) return fail(TRB_INVALID_ARG, "Invalid B-spline: knots.len() != control_points.len() + degree + 1");
+            if (sp.degree > (uint32_t)trbh::kMaxSplineDegree) return fail(TRB_UNSUPPORTED, "B-spline degree above 5");
+        }
     }
     if (!light) return fail(TRB_INVALID_ARG, "At least one light is required"); // multithreaded.rs:39
     for (uint32_t i = 0; i < d->n_cameras; ++i) {
         const trb_camera& c = d->cameras[i];
         if (c.n_fov_ctrl) return fail(TRB_UNSUPPORTED, "animated fov is not implemented (DESIGN.md: next)");
-        for (uint32_t k = c.spline_first; k < c.spline_first + c.n_splines; ++k)
-            if (k >= d->n_splines || d->splines[k].n_ctrl != 1) return fail(TRB_UNSUPPORTED, "animated camera transforms are not implemented (DESIGN.md: next)");
+        if (c.spline_first + c.n_splines > d->n_splines) return fail(TRB_INVALID_ARG, "camera spline range out of bounds");
     }
     for (uint32_t i = 0; i < d->n_materials; ++i) {
         if (d->materials[i].type > TRB_MAT_MERL) return fail(TRB_INVALID_ARG, "unrecognized material type");
@@ -505,6 +497,14 @@ trb_status trb_scene_create(const trb_scene_desc* d, int device, trb_scene** out
     ds.filter_inv_w = 1.0f / d->film.filter_w; ds.filter_inv_h = 1.0f / d->film.filter_h;
     ds.fpw_x = (int)floorf(d->film.filter_w / 0.5f); ds.fpw_y = (int)floorf(d->film.filter_h / 0.5f); // render_target.rs:48-49
     ds.filter_table = d_table;
+    { // animation tables (evaluated per ray for keyframed instances / camera / emission)
+        trb_spline* d_sp = nullptr; trb_keyframe* d_kf = nullptr; float* d_kn = nullptr; trb_color_key* d_ck = nullptr;
+        if (!s->splines.empty()) CU(s->arena.upload(s->splines.data(), s->splines.size(), &d_sp));
+        if (!s->keyframes.empty()) CU(s->arena.upload(s->keyframes.data(), s->keyframes.size(), &d_kf));
+        if (!s->knots.empty()) CU(s->arena.upload(s->knots.data(), s->knots.size(), &d_kn));
+        if (!s->color_keys.empty()) CU(s->arena.upload(s->color_keys.data(), s->color_keys.size(), &d_ck));
+        ds.splines = d_sp; ds.keyframes = d_kf; ds.knots = d_kn; ds.color_keys = d_ck; ds.has_anim = 0;
+    }
     // Scene::load_file builds the BVH<Instance> for [0, scene_time] (scene.rs:141); the first render rebuilds it
     *out = s.release();
     return TRB_OK;
@@ -544,8 +544,11 @@ trb_status trb_scene_update_frame(trb_scene* s, uint32_t frame, float start, flo
     s->shutter_close = start + c.shutter_size * (end - start);
     Mat4 px_to_cam; float scaling[3];
     camera_setup(c.fov, s->film.width, s->film.height, px_to_cam, scaling);
-    Xf cam_world;
-    if (!static_world_xf(*s, c.spline_first, c.n_splines, cam_world)) return fail(TRB_UNSUPPORTED, "animated camera");
+    // cam_world.transform(frame_time): a keyframed camera is evaluated per ray on the device (camera.rs:156)
+    const bool cam_static = trbh::xf_is_static(s->splines.data(), c.spline_first, c.n_splines);
+    const Xf cam_world = trbh::animated_xf(s->splines.data(), c.spline_first, c.n_splines, s->keyframes.data(), s->knots.data(), s->shutter_open);
+    s->ds.cam.animated = cam_static ? 0u : 1u; s->ds.cam.spline_first = c.spline_first; s->ds.cam.n_splines = c.n_splines;
+    bool any_anim = !cam_static;
     std::memcpy(s->ds.cam.px_to_cam, px_to_cam.m, 64);
     std::memcpy(s->ds.cam.cam_mat, cam_world.fwd.m, 64);
     std::memcpy(s->ds.cam.scaling, scaling, 12);
@@ -558,15 +561,35 @@ trb_status trb_scene_update_frame(trb_scene* s, uint32_t frame, float start, flo
     std::vector<trb::DInstance> di(n);
     for (size_t i = 0; i < n; ++i) {
         const trb_instance& in = s->instances[i];
-        if (!static_world_xf(*s, in.spline_first, in.n_splines, s->world[i])) return fail(TRB_UNSUPPORTED, "animated instance");
-        bounds[i] = arvo_bounds(s->world[i].fwd, shape_bounds(*s, in)); // animation_bounds, static branch (animated_transform.rs:59-61)
+        // world[i] = transform(shutter_open): exact for static instances; keyframed ones are re-evaluated per ray on the device
+        s->world[i] = trbh::animated_xf(s->splines.data(), in.spline_first, in.n_splines, s->keyframes.data(), s->knots.data(), s->shutter_open);
+        const Box3 local = shape_bounds(*s, in);
+        if (!trbh::xf_is_animated(s->splines.data(), in.spline_first, in.n_splines)) { // animation_bounds (animated_transform.rs:57-70, Q22)
+            bounds[i] = arvo_bounds(s->world[i].fwd, local);
+        } else {
+            Box3 acc = box_empty();
+            for (int k = 0; k < 128; ++k) {
+                const float u = (float)k / 127.0f;
+                const float time = s->shutter_open * (1.0f - u) + s->shutter_close * u; // linalg::lerp
+                const Xf x = trbh::animated_xf(s->splines.data(), in.spline_first, in.n_splines, s->keyframes.data(), s->knots.data(), time);
+                box_grow(acc, arvo_bounds(x.fwd, local));
+            }
+            bounds[i] = acc;
+        }
         trb::DInstance& o = di[i];
         std::memset(&o, 0, sizeof o);
         std::memcpy(o.inv, s->world[i].inv.m, 64);
         std::memcpy(o.mat, s->world[i].fwd.m, 64);
         o.kind = in.kind; o.shape = in.shape; o.p0 = in.p0; o.p1 = in.p1; o.mesh = in.mesh; o.material = in.material;
-        if (in.kind != TRB_INST_RECEIVER) for (int k = 0; k < 3; ++k) o.emission[k] = s->color_keys[in.emission_first].rgba[k];
+        if (!trbh::xf_is_static(s->splines.data(), in.spline_first, in.n_splines)) {
+            o.flags |= trb::DI_ANIM_XF; o.spline_first = in.spline_first; o.n_splines = in.n_splines; any_anim = true;
+        }
+        if (in.kind != TRB_INST_RECEIVER) {
+            for (int k = 0; k < 3; ++k) o.emission[k] = s->color_keys[in.emission_first].rgba[k];
+            if (in.n_emission > 1) { o.flags |= trb::DI_ANIM_EMISSION; o.emission_first = in.emission_first; o.n_emission = in.n_emission; any_anim = true; }
+        }
     }
+    s->ds.has_anim = any_anim ? 1u : 0u;
     BvhBuilder bb;
     bb.build(bounds, 4);
     s->tlas_nodes = bb.nodes; s->tlas_order = bb.order;
@@ -811,6 +834,23 @@ trb_status trb_host_keyframe_transform(const trb_keyframe* kf, float* mat16, flo
     if (!kf || !mat16 || !inv16) return fail(TRB_INVALID_ARG, "null argument");
     const Xf x = keyframe_xf(*kf);
     std::memcpy(mat16, x.fwd.m, 64); std::memcpy(inv16, x.inv.m, 64);
+    return TRB_OK;
+}
+
+trb_status trb_host_animated_transform(const trb_scene_desc* d, uint32_t first, uint32_t count, float time, float* mat16, float* inv16) {
+    if (!d || !mat16 || !inv16) return fail(TRB_INVALID_ARG, "null argument");
+    const trb_status r = validate(d);
+    if (r != TRB_OK) return r;
+    if (first + count > d->n_splines) return fail(TRB_INVALID_ARG, "spline range out of bounds");
+    const Xf x = trbh::animated_xf(d->splines, first, count, d->keyframes, d->knots, time);
+    std::memcpy(mat16, x.fwd.m, 64); std::memcpy(inv16, x.inv.m, 64);
+    return TRB_OK;
+}
+
+trb_status trb_host_animated_color(const trb_scene_desc* d, uint32_t first, uint32_t count, float time, float* rgb3) {
+    if (!d || !rgb3) return fail(TRB_INVALID_ARG, "null argument");
+    if (count == 0 || first + count > d->n_color_keys) return fail(TRB_INVALID_ARG, "colour key range out of bounds");
+    trbh::animated_color(d->color_keys, first, count, time, rgb3);
     return TRB_OK;
 }
 

@@ -9,7 +9,9 @@
 // (Cephes single-precision kernels) instead, which makes every camera sample reproducible on any
 // IEEE machine. Written for sm_100a; nothing here is shared with oracle/.
 #pragma once
+#include <cmath>
 #include <cstdint>
+#include <cstring>
 #include <cuda_runtime.h>
 
 namespace trb {
@@ -20,10 +22,18 @@ namespace trb {
 #define TRB_INV_PI 0.318309886183790671f
 #define TRB_EPS 1.1920929e-7f
 
+#define TRB_DM __host__ __device__ __forceinline__
+TRB_DM float bits_f32(uint32_t u) {
+#ifdef __CUDA_ARCH__
+    return __uint_as_float(u);
+#else
+    float f; memcpy(&f, &u, 4); return f;
+#endif
+}
 __device__ __forceinline__ float pow2i(int k) { return __uint_as_float((uint32_t)(k + 127) << 23); }
 
 // Cody-Waite reduction to [-pi/4, pi/4]; quadrant in q. |x| <= 1e5.
-__device__ __forceinline__ float reduce_pio2(float x, int& q) {
+TRB_DM float reduce_pio2(float x, int& q) {
     float kf = rintf(x * 0.636619772367581343f);
     q = (int)kf;
     float r = x - kf * 1.5703125f;
@@ -31,16 +41,16 @@ __device__ __forceinline__ float reduce_pio2(float x, int& q) {
     r = r - kf * 7.54978995489188216e-8f;
     return r;
 }
-__device__ __forceinline__ float sin_kernel(float r) {
+TRB_DM float sin_kernel(float r) {
     float z = r * r;
     return r + r * z * (-1.6666654611e-1f + z * (8.3321608736e-3f + z * -1.9515295891e-4f));
 }
-__device__ __forceinline__ float cos_kernel(float r) {
+TRB_DM float cos_kernel(float r) {
     float z = r * r;
     return 1.0f - 0.5f * z + z * z * (4.166664568298827e-2f + z * (-1.388731625493765e-3f + z * 2.443315711809948e-5f));
 }
 // sin and cos of the same angle share the reduction
-__device__ __forceinline__ void dsincos(float x, float& s, float& c) {
+TRB_DM void dsincos(float x, float& s, float& c) {
     if (!(fabsf(x) <= 1.0e5f)) { s = x - x; c = x - x; return; }
     int q;
     float r = reduce_pio2(x, q);
@@ -52,15 +62,15 @@ __device__ __forceinline__ void dsincos(float x, float& s, float& c) {
         default: s = -ck; c = sk; break;
     }
 }
-__device__ __forceinline__ float dsin(float x) { float s, c; dsincos(x, s, c); return s; }
-__device__ __forceinline__ float dcos(float x) { float s, c; dsincos(x, s, c); return c; }
+TRB_DM float dsin(float x) { float s, c; dsincos(x, s, c); return s; }
+TRB_DM float dcos(float x) { float s, c; dsincos(x, s, c); return c; }
 
-__device__ __forceinline__ float asin_kernel(float z) {
+TRB_DM float asin_kernel(float z) {
     float z2 = z * z;
     float p = ((((4.2163199048e-2f * z2 + 2.4181311049e-2f) * z2 + 4.5470025998e-2f) * z2 + 7.4953002686e-2f) * z2 + 1.6666752422e-1f);
     return z + z * z2 * p;
 }
-__device__ __forceinline__ float dacos(float x) {
+TRB_DM float dacos(float x) {
     if (x != x) return x;
     if (x >= 1.0f) return 0.0f;
     if (x <= -1.0f) return TRB_PI;

@@ -3,6 +3,7 @@
 #pragma once
 #include <cstdint>
 #include <cuda_runtime.h>
+#include "../../include/trb.h"
 
 namespace trb {
 
@@ -54,10 +55,14 @@ struct alignas(16) DInstance { // 176 B: the two matrices are read as 16-byte ve
     uint32_t kind, shape;
     float p0, p1;
     uint32_t mesh, material;
-    float emission[3];
-    uint32_t pad[3];
+    float emission[3];       // static emission (one colour key)
+    uint32_t flags;          // DI_ANIM_XF: transform depends on ray time; DI_ANIM_EMISSION: keyframed emission
+    uint32_t spline_first, n_splines;     // AnimatedTransform (into DScene::splines) when DI_ANIM_XF
+    uint32_t emission_first, n_emission;  // colour keys (into DScene::color_keys) when DI_ANIM_EMISSION
+    uint32_t pad[2];
 };
-static_assert(sizeof(DInstance) == 176, "DInstance must stay 16-byte sized");
+constexpr uint32_t DI_ANIM_XF = 1u, DI_ANIM_EMISSION = 2u;
+static_assert(sizeof(DInstance) == 192, "DInstance must stay 16-byte sized");
 
 struct DMaterial {
     uint32_t type;
@@ -75,6 +80,7 @@ struct DCamera {
     float cam_mat[16];   // cam_world at the frame (static camera)
     float scaling[3];
     float shutter_open, shutter_close;
+    uint32_t animated, spline_first, n_splines; // keyframed cam_world: evaluated at each ray's time (camera.rs:156)
 };
 
 struct DStats { // mirrors trb_stats' integer part
@@ -98,6 +104,12 @@ struct DScene {
     float filter_w, filter_h, filter_inv_w, filter_inv_h;
     int fpw_x, fpw_y;
     const float* filter_table; // 256 floats
+    // animation: the AnimatedTransform / AnimatedColor tables of the scene description, evaluated per ray
+    const trb_spline* splines;
+    const trb_keyframe* keyframes;
+    const float* knots;
+    const trb_color_key* color_keys;
+    uint32_t has_anim; // any instance / camera / emission depends on time
 };
 
 struct RenderParams {

@@ -21,6 +21,14 @@
 #include <vector>
 #include "../../include/trb.h"
 
+// Functions marked TRB_HD are shared by the host (per-frame preparation, TLAS bounds) and the device (per-ray
+// evaluation of animated transforms); both compilers evaluate them without FMA contraction, so the bits agree.
+#ifdef __CUDACC__
+#define TRB_HD __host__ __device__
+#else
+#define TRB_HD
+#endif
+
 namespace trbh {
 
 constexpr float kPi = 3.14159265358979323846f;
@@ -28,8 +36,8 @@ constexpr float kEps = 1.1920929e-7f;
 
 struct Mat4 { float m[16]; };
 
-inline Mat4 mat_identity() { Mat4 r; std::memset(r.m, 0, sizeof r.m); r.m[0] = r.m[5] = r.m[10] = r.m[15] = 1.0f; return r; }
-inline Mat4 mat_mul(const Mat4& a, const Mat4& b) { // matrix4.rs:232-247
+TRB_HD inline Mat4 mat_identity() { Mat4 r; for (int i = 0; i < 16; ++i) r.m[i] = 0.0f; r.m[0] = r.m[5] = r.m[10] = r.m[15] = 1.0f; return r; }
+TRB_HD inline Mat4 mat_mul(const Mat4& a, const Mat4& b) { // matrix4.rs:232-247
     Mat4 r;
     for (int i = 0; i < 4; ++i)
         for (int j = 0; j < 4; ++j)
@@ -37,9 +45,9 @@ inline Mat4 mat_mul(const Mat4& a, const Mat4& b) { // matrix4.rs:232-247
     return r;
 }
 // 3x3 sub-determinant helper: returns x*y*z with the reference's left-to-right product order
-inline float p3(float x, float y, float z) { return x * y * z; }
+TRB_HD inline float p3(float x, float y, float z) { return x * y * z; }
 // Matrix4::inverse (matrix4.rs:48-172): cofactor expansion, each cofactor a 6-term signed sum in the source order.
-inline Mat4 mat_inverse(const Mat4& s) {
+TRB_HD inline Mat4 mat_inverse(const Mat4& s) {
     const float* a = s.m;
     Mat4 out;
     float* v = out.m;
@@ -67,24 +75,24 @@ inline Mat4 mat_inverse(const Mat4& s) {
 
 // Transform {mat, inv} (transform.rs:10-15)
 struct Xf { Mat4 fwd, inv; };
-inline Xf xf_identity() { return Xf{mat_identity(), mat_identity()}; }
-inline Xf xf_compose(const Xf& l, const Xf& r) { return Xf{mat_mul(l.fwd, r.fwd), mat_mul(r.inv, l.inv)}; } // transform.rs:191-197
-inline Xf xf_translate(const float t[3]) {
+TRB_HD inline Xf xf_identity() { return Xf{mat_identity(), mat_identity()}; }
+TRB_HD inline Xf xf_compose(const Xf& l, const Xf& r) { return Xf{mat_mul(l.fwd, r.fwd), mat_mul(r.inv, l.inv)}; } // transform.rs:191-197
+TRB_HD inline Xf xf_translate(const float t[3]) {
     Xf x = xf_identity();
     for (int i = 0; i < 3; ++i) { x.fwd.m[4 * i + 3] = t[i]; x.inv.m[4 * i + 3] = -t[i]; }
     return x;
 }
-inline Xf xf_scale(const float s[3]) {
+TRB_HD inline Xf xf_scale(const float s[3]) {
     Xf x = xf_identity();
     for (int i = 0; i < 3; ++i) { x.fwd.m[5 * i] = s[i]; x.inv.m[5 * i] = 1.0f / s[i]; }
     return x;
 }
-inline Xf xf_from_mat(const Mat4& m) { return Xf{m, mat_inverse(m)}; }
-inline Xf xf_inverse(const Xf& x) { return Xf{x.inv, x.fwd}; }
+TRB_HD inline Xf xf_from_mat(const Mat4& m) { return Xf{m, mat_inverse(m)}; }
+TRB_HD inline Xf xf_inverse(const Xf& x) { return Xf{x.inv, x.fwd}; }
 
 // Quaternion::to_matrix (quaternion.rs:65-84): the rotation matrix of (x,y,z,w). The source writes the
 // transposed literal and transposes it; element (r,c) below is the source literal's (c,r).
-inline Mat4 quat_matrix(const float q[4]) {
+TRB_HD inline Mat4 quat_matrix(const float q[4]) {
     const float x = q[0], y = q[1], z = q[2], w = q[3];
     Mat4 r = mat_identity();
     r.m[0] = 1.0f - 2.0f * (y * y + z * z); r.m[1] = 2.0f * (x * y - z * w);        r.m[2] = 2.0f * (x * z + y * w);
@@ -93,7 +101,7 @@ inline Mat4 quat_matrix(const float q[4]) {
     return r;
 }
 // Keyframe::transform (keyframe.rs:60-63): (translate * from_mat(rot)) * scale
-inline Xf keyframe_xf(const trb_keyframe& k) {
+TRB_HD inline Xf keyframe_xf(const trb_keyframe& k) {
     return xf_compose(xf_compose(xf_translate(k.translation), xf_from_mat(quat_matrix(k.rotation))), xf_scale(k.scaling));
 }
 

@@ -17,6 +17,7 @@
 #pragma once
 #include "trb_device.h"
 #include "trb_detmath.cuh"
+#include "trb_anim.h"
 #include "../../include/trb.h"
 
 namespace trb {
@@ -149,6 +150,30 @@ __device__ __forceinline__ void load_xf(const float* __restrict__ src, float* ds
     for (int i = 0; i < 4; ++i) { float4 v = __ldg(s + i); dst[4 * i] = v.x; dst[4 * i + 1] = v.y; dst[4 * i + 2] = v.z; dst[4 * i + 3] = v.w; }
 }
 
+// AnimatedTransform::transform(ray.time) of a keyframed instance: the reference recomposes it per ray per instance
+// (receiver.rs:30, emitter.rs:122,176,197); static instances use the matrices prepared by update_frame.
+__device__ __noinline__ void eval_anim_xf(const DScene& sc, uint32_t first, uint32_t n, float time, float* inv16, float* mat16) {
+    const trbh::Xf x = trbh::animated_xf(sc.splines, first, n, sc.keyframes, sc.knots, time);
+#pragma unroll
+    for (int i = 0; i < 16; ++i) { inv16[i] = x.inv.m[i]; if (mat16) mat16[i] = x.fwd.m[i]; }
+}
+__device__ __forceinline__ void instance_inv(const DScene& sc, const DInstance& in, float time, float* inv16) {
+    if (sc.has_anim && (__ldg(&in.flags) & DI_ANIM_XF)) eval_anim_xf(sc, __ldg(&in.spline_first), __ldg(&in.n_splines), time, inv16, nullptr);
+    else load_xf(in.inv, inv16);
+}
+__device__ __forceinline__ void instance_inv_mat(const DScene& sc, const DInstance& in, float time, float* inv16, float* mat16) {
+    if (sc.has_anim && (__ldg(&in.flags) & DI_ANIM_XF)) eval_anim_xf(sc, __ldg(&in.spline_first), __ldg(&in.n_splines), time, inv16, mat16);
+    else { load_xf(in.inv, inv16); load_xf(in.mat, mat16); }
+}
+// AnimatedColor::color(time) of an emitter (animated_color.rs:52-78)
+__device__ __forceinline__ void emission_at(const DScene& sc, const DInstance& in, float time, float& r, float& g, float& b) {
+    if (sc.has_anim && (__ldg(&in.flags) & DI_ANIM_EMISSION)) {
+        float c[3];
+        trbh::animated_color(sc.color_keys, __ldg(&in.emission_first), __ldg(&in.n_emission), time, c);
+        r = c[0]; g = c[1]; b = c[2];
+    } else { r = __ldg(&in.emission[0]); g = __ldg(&in.emission[1]); b = __ldg(&in.emission[2]); }
+}
+
 // ------------------------------------------------------------------------------------------
 // Scene::intersect (scene.rs:148-150) = BVH<Instance>::intersect (bvh.rs:81-130) whose leaf callback
 // is Instance::intersect (receiver.rs:29-43 / emitter.rs:118-137), which for meshes runs
@@ -181,13 +206,15 @@ struct TraceState {
     const DTri* tris;
     uint32_t level_inst;  // instance whose mesh is being traversed, TRB_MISS at the top level
     float tmin, tmax;
+    float time;           // ray.time (only read for keyframed instances)
     int sp;
     uint32_t cur;
     bool found, any_hit;
     uint32_t h_inst, h_prim;
     float h_b1, h_b2;
 };
-__device__ __forceinline__ void trace_init(const DScene& sc, TraceState& t, const Ray& ray, bool any_hit) {
+__device__ __forceinline__ void trace_init(const DScene& sc, TraceState& t, const Ray& ray, bool any_hit, float time) {
+    t.time = time;
     t.wo = ray.o; t.wd = ray.d;
     t.winv = mk(1.0f / ray.d.x, 1.0f / ray.d.y, 1.0f / ray.d.z);
     t.o = t.wo; t.d = t.wd; t.inv = t.winv;
@@ -302,7 +329,7 @@ __device__ __forceinline__ void trace_step(const DScene& sc, TraceState& t, cons
         bool enter = false;
         if (kind != TRB_INST_EMITTER_POINT) { // point lights never intersect (emitter.rs:119-120)
             float m[16];
-            load_xf(in.inv, m);
+            instance_inv(sc, in, t.time, m);
             const f3 lo_ = xf_point(m, t.wo), ld_ = xf_vector(m, t.wd); // inv_mul_ray: direction not renormalised
             if (shape == TRB_SHAPE_MESH) {
                 const DMesh& me = sc.meshes[__ldg(&in.mesh)];
@@ -334,11 +361,11 @@ __device__ __forceinline__ void trace_step(const DScene& sc, TraceState& t, cons
 }
 
 template <bool STATS>
-__device__ __noinline__ bool scene_trace(const DScene& sc, Ray& ray, HitRec& hit, bool any_hit, Cnt& cnt, int* err) {
+__device__ __noinline__ bool scene_trace(const DScene& sc, Ray& ray, HitRec& hit, bool any_hit, Cnt& cnt, int* err, float time) {
     TraceState t;
     unsigned long long stack_mem[STACK_DEPTH];
     const LocalStack stack{stack_mem};
-    trace_init(sc, t, ray, any_hit);
+    trace_init(sc, t, ray, any_hit, time);
     while (t.cur != ST_DONE) trace_step<STATS>(sc, t, stack, cnt, err);
     ray.tmax = t.tmax;
     hit.t = t.tmax; hit.inst = t.h_inst; hit.prim = t.h_prim; hit.b1 = t.h_b1; hit.b2 = t.h_b2;
@@ -351,10 +378,10 @@ __device__ __noinline__ bool scene_trace(const DScene& sc, Ray& ray, HitRec& hit
 // ------------------------------------------------------------------------------------------
 struct Surf { f3 p, n, ng, dp_du; };
 
-__device__ __forceinline__ void surface_at(const DScene& sc, const Ray& ray, const HitRec& hit, Surf& s) {
+__device__ __forceinline__ void surface_at(const DScene& sc, const Ray& ray, const HitRec& hit, Surf& s, float time) {
     const DInstance& in = sc.instances[hit.inst];
-    float m[16];
-    load_xf(in.inv, m);
+    float m[16], w[16];
+    instance_inv_mat(sc, in, time, m, w);
     const f3 o = xf_point(m, ray.o), d = xf_vector(m, ray.d);
     const f3 p = o + d * hit.t; // ray.at(t) of the local ray
     const uint32_t shape = __ldg(&in.shape);
@@ -402,8 +429,6 @@ __device__ __forceinline__ void surface_at(const DScene& sc, const Ray& ray, con
         n = unit(cross3(dp_du, dp_dv));
         ng = unit(mk(0.0f, 0.0f, 1.0f));
     }
-    float w[16];
-    load_xf(in.mat, w);
     s.p = xf_point(w, p);
     s.n = xf_normal_t(m, n);
     s.ng = xf_normal_t(m, ng);
@@ -875,16 +900,16 @@ struct DirectSetup {
 };
 
 __device__ __noinline__ void direct_setup(const DScene& sc, const Mat& m, const Frame& fr, f3 wo, uint32_t li, float l0, float l1, float b0, float b1,
-                                          float bc, DirectSetup& ds) {
+                                          float bc, float time, DirectSetup& ds) {
     ds.a = splat(0.0f); ds.b = splat(0.0f); ds.shadow_d = splat(0.0f); ds.mis_d = splat(0.0f); ds.has_shadow = false; ds.has_mis = false;
     const DInstance& light = sc.instances[li];
     const uint32_t kind = __ldg(&light.kind), shape = __ldg(&light.shape);
     const float p0 = __ldg(&light.p0), p1 = __ldg(&light.p1);
-    const f3 emission = mk(__ldg(&light.emission[0]), __ldg(&light.emission[1]), __ldg(&light.emission[2]));
+    f3 emission;
+    emission_at(sc, light, time, emission.x, emission.y, emission.z); // self.emission.color(time)
     const bool delta = kind == TRB_INST_EMITTER_POINT;
     float linv[16], lmat[16];
-    load_xf(light.inv, linv);
-    load_xf(light.mat, lmat);
+    instance_inv_mat(sc, light, time, linv, lmat); // self.transform.transform(time)
     const f3 p = fr.p;
     // --- light.sample_incident(&bsdf.p, ...) ---
     f3 lrad, wi, seg;
@@ -940,14 +965,16 @@ __device__ __noinline__ void direct_setup(const DScene& sc, const Mat& m, const 
     }
 }
 // Does the MIS ray's hit see the light's emitting side? e.radiance(&-w_i, &h.dg.p, &h.dg.ng) (integrator/mod.rs:156-162)
-__device__ __forceinline__ bool mis_sees_light(const DScene& sc, f3 org, f3 mis_d, uint32_t li, uint32_t hit_inst, float hit_t) {
+__device__ __forceinline__ bool mis_sees_light(const DScene& sc, f3 org, f3 mis_d, uint32_t li, uint32_t hit_inst, float hit_t, float time) {
     if (hit_inst != li) return false;
     const DInstance& light = sc.instances[li];
-    if (black(mk(__ldg(&light.emission[0]), __ldg(&light.emission[1]), __ldg(&light.emission[2])))) return false; // `if !li.is_black()`
+    f3 le;
+    emission_at(sc, light, time, le.x, le.y, le.z);
+    if (black(le)) return false; // `if !li.is_black()`
     Ray mr; mr.o = org; mr.d = mis_d; mr.tmin = 0.001f; mr.tmax = hit_t;
     HitRec mh; mh.t = hit_t; mh.inst = hit_inst; mh.prim = 0; mh.b1 = 0.0f; mh.b2 = 0.0f; // area lights are analytic shapes
     Surf s;
-    surface_at(sc, mr, mh, s);
+    surface_at(sc, mr, mh, s, time);
     return dot3(-mis_d, s.ng) > 0.0f;
 }
 __device__ __forceinline__ f3 direct_resolve(f3 a, f3 b, bool occluded, bool mis_ok) {
@@ -970,13 +997,16 @@ struct BounceOut {
     bool specular, terminate; // terminate: no continuation ray (black f / pdf 0 / RR / max depth)
 };
 __device__ __forceinline__ void shade_bounce(const DScene& sc, const Surf& s, uint32_t hit_inst, f3 ray_d, f3 first_ng, uint32_t bounce, bool prev_specular,
-                                             uint32_t hsample, f3 throughput_in, f3& illum, BounceOut& o) {
+                                             uint32_t hsample, f3 throughput_in, float time, f3& illum, BounceOut& o) {
     const DInstance& in = sc.instances[hit_inst];
     if (bounce == 0 || prev_specular) {
         if (__ldg(&in.kind) != TRB_INST_RECEIVER) {
             const f3 w = -ray_d;
-            if (dot3(w, first_ng) > 0.0f) // Emitter::radiance with the FIRST hit's normal (path.rs:73, Q1)
-                illum = illum + throughput_in * mk(__ldg(&in.emission[0]), __ldg(&in.emission[1]), __ldg(&in.emission[2]));
+            if (dot3(w, first_ng) > 0.0f) { // Emitter::radiance with the FIRST hit's normal (path.rs:73, Q1)
+                f3 le;
+                emission_at(sc, in, time, le.x, le.y, le.z);
+                illum = illum + throughput_in * le;
+            }
         }
     }
     Mat m;
@@ -992,7 +1022,7 @@ __device__ __forceinline__ void shade_bounce(const DScene& sc, const Surf& s, ui
     uint32_t l = f2u(lc * (float)sc.n_lights); // sample_one_light (integrator/mod.rs:108-110), no xN (Q2)
     if (l > sc.n_lights - 1) l = sc.n_lights - 1;
     o.light = __ldg(&sc.lights[l]);
-    direct_setup(sc, m, fr, wo, o.light, l0, l1, b0, b1, bc, o.ds);
+    direct_setup(sc, m, fr, wo, o.light, l0, l1, b0, b1, bc, time, o.ds);
     o.t_before = throughput_in;
     o.org = fr.p;
     rng.two_d(bounce, S_P0, S_P1, S_P_PERM, q0, q1);
@@ -1019,42 +1049,51 @@ __device__ __forceinline__ void shade_bounce(const DScene& sc, const Surf& s, ui
 // One camera sample, megakernel shape: Camera::generate_ray + Scene::intersect + Path::illumination
 // (multithreaded.rs:94-102, path.rs:45-119) with the rays traced inline.
 // ------------------------------------------------------------------------------------------
-__device__ __forceinline__ void camera_ray(const DScene& sc, float sx, float sy, float tm, Ray& ray) { // camera.rs:150-157
+// Returns the ray's time: frame_time = (shutter_close - shutter_open) * time + shutter_open.
+__device__ __forceinline__ float camera_ray(const DScene& sc, float sx, float sy, float tm, Ray& ray) { // camera.rs:150-157
     const f3 pc = xf_point(sc.cam.px_to_cam, mk(sx, sy, 0.0f));
     const f3 pp = mk(sc.cam.scaling[0], sc.cam.scaling[1], sc.cam.scaling[2]) * pc;
     const f3 d = unit(pp);
-    (void)tm; // static camera: cam_world.transform(frame_time) is time-independent
-    ray.o = xf_point(sc.cam.cam_mat, splat(0.0f));
-    ray.d = xf_vector(sc.cam.cam_mat, d);
+    const float frame_time = (sc.cam.shutter_close - sc.cam.shutter_open) * tm + sc.cam.shutter_open;
+    if (sc.cam.animated) { // keyframed camera: cam_world.transform(frame_time) per ray
+        float inv[16], mat[16];
+        eval_anim_xf(sc, sc.cam.spline_first, sc.cam.n_splines, frame_time, inv, mat);
+        ray.o = xf_point(mat, splat(0.0f));
+        ray.d = xf_vector(mat, d);
+    } else {
+        ray.o = xf_point(sc.cam.cam_mat, splat(0.0f));
+        ray.d = xf_vector(sc.cam.cam_mat, d);
+    }
     ray.tmin = 0.0f; ray.tmax = finf();
+    return frame_time;
 }
 
 template <bool STATS>
-__device__ f3 radiance_of_sample(const DScene& sc, Ray ray, uint32_t hpix_sample, bool ref_shadow, RayCounts& rc, Cnt& cnt, int* err) {
+__device__ f3 radiance_of_sample(const DScene& sc, Ray ray, float time, uint32_t hpix_sample, bool ref_shadow, RayCounts& rc, Cnt& cnt, int* err) {
     HitRec hit;
     rc.primary++;
-    if (!scene_trace<STATS>(sc, ray, hit, false, cnt, err)) return splat(0.0f); // multithreaded.rs:101-102
+    if (!scene_trace<STATS>(sc, ray, hit, false, cnt, err, time)) return splat(0.0f); // multithreaded.rs:101-102
     f3 illum = splat(0.0f), throughput = splat(1.0f);
     bool specular_bounce = false;
     uint32_t bounce = 0;
     Surf s;
-    surface_at(sc, ray, hit, s);
+    surface_at(sc, ray, hit, s, time);
     const f3 first_ng = s.ng;
     for (;;) {
         BounceOut o;
-        shade_bounce(sc, s, hit.inst, ray.d, first_ng, bounce, specular_bounce, hpix_sample, throughput, illum, o);
+        shade_bounce(sc, s, hit.inst, ray.d, first_ng, bounce, specular_bounce, hpix_sample, throughput, time, illum, o);
         bool occluded = false, mis_ok = false;
         if (o.ds.has_shadow) {
             Ray sr; sr.o = o.org; sr.d = o.ds.shadow_d; sr.tmin = 0.001f; sr.tmax = 0.999f;
             HitRec sh;
             rc.shadow++;
-            occluded = scene_trace<STATS>(sc, sr, sh, !ref_shadow, cnt, err);
+            occluded = scene_trace<STATS>(sc, sr, sh, !ref_shadow, cnt, err, time);
         }
         if (o.ds.has_mis) {
             Ray mr; mr.o = o.org; mr.d = o.ds.mis_d; mr.tmin = 0.001f; mr.tmax = finf();
             HitRec mh;
             rc.mis++;
-            if (scene_trace<STATS>(sc, mr, mh, false, cnt, err)) mis_ok = mis_sees_light(sc, o.org, o.ds.mis_d, o.light, mh.inst, mh.t);
+            if (scene_trace<STATS>(sc, mr, mh, false, cnt, err, time)) mis_ok = mis_sees_light(sc, o.org, o.ds.mis_d, o.light, mh.inst, mh.t, time);
         }
         illum = illum + o.t_before * direct_resolve(o.ds.a, o.ds.b, occluded, mis_ok);
         throughput = o.throughput;
@@ -1062,8 +1101,8 @@ __device__ f3 radiance_of_sample(const DScene& sc, Ray ray, uint32_t hpix_sample
         if (o.terminate) break;
         ray.o = o.org; ray.d = o.next_d; ray.tmin = 0.001f; ray.tmax = finf();
         rc.cont++;
-        if (!scene_trace<STATS>(sc, ray, hit, false, cnt, err)) break;
-        surface_at(sc, ray, hit, s);
+        if (!scene_trace<STATS>(sc, ray, hit, false, cnt, err, time)) break;
+        surface_at(sc, ray, hit, s, time);
         bounce += 1;
     }
     return illum;
@@ -1165,9 +1204,9 @@ __global__ void __launch_bounds__(RENDER_THREADS) k_render(const __grid_constant
             const float sy = ld_sobol(ip, ps.scr1) + (float)py;
             const float tm = ld_vdc(permute_index(si, rp.spp, ps.ktime), ps.scrt);
             Ray ray;
-            camera_ray(sc, sx, sy, tm, ray);
+            const float time = camera_ray(sc, sx, sy, tm, ray);
             my_samples++;
-            f3 c = radiance_of_sample<STATS>(sc, ray, rng_absorb(ps.hpix, si), ref_shadow, rc, cnt, rp.error_flag);
+            f3 c = radiance_of_sample<STATS>(sc, ray, time, rng_absorb(ps.hpix, si), ref_shadow, rc, cnt, rp.error_flag);
             c = mk(clampf(c.x, 0.0f, 1.0f), clampf(c.y, 0.0f, 1.0f), clampf(c.z, 0.0f, 1.0f)); // multithreaded.rs:99 (Q12)
             if (MODE == 1) {
                 trb_sample* out = reinterpret_cast<trb_sample*>(rp.samples_out) + ((size_t)item * 64 + pix) * rp.sample_count + (si - rp.sample_first);
@@ -1261,10 +1300,10 @@ __global__ void __launch_bounds__(256) k_wf_generate(const __grid_constant__ DSc
         float sx, sy, tm;
         sample_position(rp, ps, id, sx, sy, tm);
         Ray ray;
-        camera_ray(sc, sx, sy, tm, ray);
+        const float time = camera_ray(sc, sx, sy, tm, ray);
         wf.org[p] = make_float4(ray.o.x, ray.o.y, ray.o.z, __uint_as_float(0u));
         wf.cont[p] = make_float4(ray.d.x, ray.d.y, ray.d.z, finf());
-        wf.thr[p] = make_float4(1.0f, 1.0f, 1.0f, 0.0f);
+        wf.thr[p] = make_float4(1.0f, 1.0f, 1.0f, time); // .w: the path's ray.time (every child ray inherits it)
         wf.illum[p] = make_float4(0.0f, 0.0f, 0.0f, 0.0f);
         wf.q_cont[p] = p;
     }
@@ -1331,7 +1370,7 @@ __global__ void __launch_bounds__(128, MINB) k_wf_trace(const __grid_constant__ 
                     Ray ray; ray.o = mk(o4.x, o4.y, o4.z); ray.d = mk(d4.x, d4.y, d4.z);
                     ray.tmin = (type == 0 && round == 0) ? 0.0f : 0.001f;
                     ray.tmax = type == 1 ? 0.999f : finf();
-                    trace_init(sc, t, ray, type == 1 && shadow_any);
+                    trace_init(sc, t, ray, type == 1 && shadow_any, sc.has_anim ? __ldg(&wf.thr[p].w) : 0.0f);
                     have = true;
                 }
             }
@@ -1390,13 +1429,15 @@ __global__ void __launch_bounds__(128) k_wf_shade(const __grid_constant__ DScene
             float4 il4 = wf.illum[p];
             f3 illum = mk(il4.x, il4.y, il4.z);
             bool done = false;
+            const float4 th4 = wf.thr[p];
+            const float time = th4.w;
             if (round > 0) { // fold in the direct light of the previous bounce (estimate_direct's two ray results)
                 const float4 a4 = wf.a[p], b4 = wf.b[p], t4 = wf.tprev[p];
                 bool occluded = false, mis_ok = false;
                 if (fl & WF_F_SHADOW) occluded = __float_as_uint(wf.shadow[p].w) != 0u;
                 if (fl & WF_F_MIS) {
                     const float4 m4 = wf.mis[p];
-                    mis_ok = mis_sees_light(sc, org, mk(m4.x, m4.y, m4.z), __float_as_uint(b4.w), __float_as_uint(a4.w), m4.w);
+                    mis_ok = mis_sees_light(sc, org, mk(m4.x, m4.y, m4.z), __float_as_uint(b4.w), __float_as_uint(a4.w), m4.w, time);
                 }
                 illum = illum + mk(t4.x, t4.y, t4.z) * direct_resolve(mk(a4.x, a4.y, a4.z), mk(b4.x, b4.y, b4.z), occluded, mis_ok);
                 done = (fl & WF_F_TERMINATE) != 0;
@@ -1409,15 +1450,14 @@ __global__ void __launch_bounds__(128) k_wf_shade(const __grid_constant__ DScene
                     Ray ray; ray.o = org; ray.d = mk(c4.x, c4.y, c4.z); ray.tmin = 0.0f; ray.tmax = c4.w;
                     HitRec h; h.t = c4.w; h.inst = h4.x; h.prim = h4.y; h.b1 = __uint_as_float(h4.z); h.b2 = __uint_as_float(h4.w);
                     Surf s;
-                    surface_at(sc, ray, h, s);
+                    surface_at(sc, ray, h, s, time);
                     f3 first_ng;
                     if (round == 0) { first_ng = s.ng; wf.ng[p] = make_float4(s.ng.x, s.ng.y, s.ng.z, 0.0f); }
                     else { const float4 n4 = wf.ng[p]; first_ng = mk(n4.x, n4.y, n4.z); }
                     const SampleId id = sample_id(sc, rp, p);
                     const uint32_t hs = rng_absorb(rng_absorb(rng_seed(rp.seed), id.pixel), id.si);
-                    const float4 th4 = wf.thr[p];
                     BounceOut o;
-                    shade_bounce(sc, s, h.inst, ray.d, first_ng, round, (fl & WF_F_SPECULAR) != 0, hs, mk(th4.x, th4.y, th4.z), illum, o);
+                    shade_bounce(sc, s, h.inst, ray.d, first_ng, round, (fl & WF_F_SPECULAR) != 0, hs, mk(th4.x, th4.y, th4.z), time, illum, o);
                     const uint32_t nf = (o.specular ? WF_F_SPECULAR : 0u) | (o.terminate ? WF_F_TERMINATE : 0u) | (o.ds.has_shadow ? WF_F_SHADOW : 0u) |
                                         (o.ds.has_mis ? WF_F_MIS : 0u);
                     push_cont = !o.terminate; push_shadow = o.ds.has_shadow; push_mis = o.ds.has_mis;
@@ -1430,7 +1470,7 @@ __global__ void __launch_bounds__(128) k_wf_shade(const __grid_constant__ DScene
                         wf.a[p] = make_float4(o.ds.a.x, o.ds.a.y, o.ds.a.z, __uint_as_float(TRB_MISS));
                         wf.b[p] = make_float4(o.ds.b.x, o.ds.b.y, o.ds.b.z, __uint_as_float(o.light));
                         wf.tprev[p] = make_float4(o.t_before.x, o.t_before.y, o.t_before.z, 0.0f);
-                        wf.thr[p] = make_float4(o.throughput.x, o.throughput.y, o.throughput.z, 0.0f);
+                        wf.thr[p] = make_float4(o.throughput.x, o.throughput.y, o.throughput.z, time);
                         wf.illum[p] = make_float4(illum.x, illum.y, illum.z, 0.0f);
                     } else done = true; // nothing pending: direct light of this bounce is zero, the path ends here
                 }
@@ -1523,7 +1563,7 @@ __global__ void __launch_bounds__(128) k_intersect(const __grid_constant__ DScen
         const float4 a = __ldg(reinterpret_cast<const float4*>(rays + i)), b = __ldg(reinterpret_cast<const float4*>(rays + i) + 1);
         Ray r; r.o = mk(a.x, a.y, a.z); r.d = mk(a.w, b.x, b.y); r.tmin = b.z; r.tmax = b.w;
         HitRec h;
-        const bool hit = scene_trace<STATS>(sc, r, h, false, cnt, err);
+        const bool hit = scene_trace<STATS>(sc, r, h, false, cnt, err, sc.cam.shutter_open); // batch rays carry no time: the frame's shutter-open time
         rc.primary++;
         uint4 o; o.x = __float_as_uint(r.tmax); o.y = hit ? h.inst : TRB_MISS; o.z = hit ? h.prim : 0u; o.w = 0u;
         *reinterpret_cast<uint4*>(hits + i) = o;

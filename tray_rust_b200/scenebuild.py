@@ -27,6 +27,29 @@ def trs(t=(0, 0, 0), q=(0, 0, 0, 1), s=(1, 1, 1)):
     return (tuple(float(x) for x in t), tuple(float(x) for x in q), tuple(float(x) for x in s))
 
 
+class Anim:
+    """One animated level of a transform stack: B-spline over TRS control points
+    (AnimatedTransform::with_keyframes, animated_transform.rs:22-33)."""
+
+    def __init__(self, keys, knots=None, degree=3):
+        keys = [list(k) for k in keys]
+        for i in range(1, len(keys)):  # with_keyframes keeps successive quaternions in one hemisphere
+            a, b = np.asarray(keys[i - 1][1], np.float32), np.asarray(keys[i][1], np.float32)
+            if float(np.dot(a, b)) < 0.0:
+                keys[i][1] = tuple(-float(x) for x in keys[i][1])
+        self.keys = [tuple(k) for k in keys]
+        self.degree = degree
+        self.knots = list(knots) if knots is not None else clamped_knots(len(keys), degree)
+
+
+def clamped_knots(n_ctrl, degree, t0=0.0, t1=1.0):
+    """Clamped uniform knot vector over [t0, t1] (n_ctrl + degree + 1 knots)."""
+    inner = n_ctrl - degree - 1
+    assert inner >= 0, "need at least degree + 1 control points"
+    mid = [t0 + (t1 - t0) * (i + 1) / (inner + 1) for i in range(inner)]
+    return [t0] * (degree + 1) + mid + [t1] * (degree + 1)
+
+
 class SceneBuilder:
     def __init__(self, width=64, height=64, spp=4, min_depth=4, max_depth=8):
         self.film = dict(width=width, height=height, samples=spp, frames=1, start_frame=0, end_frame=0, scene_time=0.0,
@@ -41,7 +64,14 @@ class SceneBuilder:
     def _add_xf(self, levels):
         """levels: list of TRS triples, applied first-to-last (animated_transform.rs:42-54)."""
         first = len(self.splines)
-        for (t, q, s) in levels:
+        for lv in levels:
+            if isinstance(lv, Anim):
+                assert len(lv.knots) == len(lv.keys) + lv.degree + 1
+                self.splines.append((lv.degree, len(lv.keys), len(self.keyframes), len(lv.knots), len(self.knots)))
+                self.keyframes += lv.keys
+                self.knots += [float(k) for k in lv.knots]
+                continue
+            (t, q, s) = lv
             self.splines.append((0, 1, len(self.keyframes), 2, len(self.knots)))
             self.keyframes.append((t, q, s))
             self.knots += [0.0, 1.0]  # AnimatedTransform::unanimated (animated_transform.rs:34-37)
@@ -70,14 +100,19 @@ class SceneBuilder:
         sf, ns = self._add_xf(xf)
         ef, ne = 0, 0
         if emission is not None:
-            ef, ne = len(self.color_keys), 1
-            e = list(emission)
-            if len(e) == 4:  # load_color: rgb scaled by the 4th component (scene.rs:713-716)
-                e = [np.float32(e[0]) * np.float32(e[3]), np.float32(e[1]) * np.float32(e[3]), np.float32(e[2]) * np.float32(e[3]),
-                     np.float32(e[3])]
-            else:
-                e = e + [1.0]
-            self.color_keys.append((tuple(float(x) for x in e), 0.0))
+            # a plain colour, or [(colour, time), ...] for AnimatedColor keyframes (scene.rs:729-747), times ascending
+            keyed = isinstance(emission, list) and len(emission) > 0 and isinstance(emission[0], (tuple, list)) and len(emission[0]) == 2 \
+                and isinstance(emission[0][0], (tuple, list))
+            keys = emission if keyed else [(emission, 0.0)]
+            ef, ne = len(self.color_keys), len(keys)
+            for col, tm in keys:
+                e = list(col)
+                if len(e) == 4:  # load_color: rgb scaled by the 4th component (scene.rs:713-716)
+                    e = [np.float32(e[0]) * np.float32(e[3]), np.float32(e[1]) * np.float32(e[3]), np.float32(e[2]) * np.float32(e[3]),
+                         np.float32(e[3])]
+                else:
+                    e = e + [1.0]
+                self.color_keys.append((tuple(float(x) for x in e), float(tm)))
         self.instances.append((kind, shape, float(p0), float(p1), mesh, material, sf, ns, ef, ne))
         return len(self.instances) - 1
 
@@ -280,6 +315,38 @@ def scene_smallpt_like(width=512, height=512, spp=1024):
     b.receiver(F.SHAPE_SPHERE, glass, [trs(t=(6, 5, -2), s=5)], p0=1.0)
     b.area_light(F.SHAPE_SPHERE, white, [trs(t=(0, 22, 0))], (0.780131, 0.780409, 0.775833, 60), p0=1.0)
     b.add_camera([trs(t=(0, 12, -60))], fov=30.0)
+    return b
+
+
+def scene_animated(width=64, height=64, spp=8, frames=4, scene_time=1.0):
+    """Small keyframed scene (the tr15 feature set): B-spline animated receivers (one- and two-level
+    stacks), a moving area light with keyframed emission, a moving point light and a keyframed camera."""
+    b = SceneBuilder(width, height, spp, 2, 6)
+    b.film.update(frames=frames, start_frame=0, end_frame=frames - 1, scene_time=scene_time)
+    mats = cornell_walls(b)
+    plastic = b.add_material(F.MAT_PLASTIC, (0.2, 0.6, 0.9), (0.7, 0.7, 0.7), roughness=0.2)
+    metal = b.add_material(F.MAT_METAL, (0.155265, 0.116723, 0.138381), (4.82835, 3.12225, 2.14696), roughness=0.3)
+    glass = b.add_material(F.MAT_GLASS, (1, 1, 1), (1, 1, 1), eta=1.5)
+    # a sphere flying along a cubic spline while spinning and pulsing
+    fly = Anim([trs(t=(-9, 3, 6), s=2.0), trs(t=(-3, 9, 2), q=quat_axis_angle((0, 1, 0), 80), s=3.0),
+                trs(t=(4, 5, -2), q=quat_axis_angle((0, 1, 0), 160), s=2.5), trs(t=(9, 8, 4), q=quat_axis_angle((1, 1, 0), 200), s=2.0),
+                trs(t=(6, 3, 8), q=quat_axis_angle((1, 0, 0), 270), s=3.0)], degree=3)
+    b.receiver(F.SHAPE_SPHERE, plastic, [fly], p0=1.0)
+    # a mesh spinning about its own axis (animated inner level) inside a static placement (two-level stack, Q22: bounds are NOT sampled)
+    m = b.add_mesh(*icosphere_mesh(2, 1.0, 0.1, 0x5EED))
+    spin = Anim([trs(q=quat_axis_angle((0, 1, 0), a)) for a in (0, 90, 170, 250)], degree=2)
+    b.receiver(F.SHAPE_MESH, metal, [spin, trs(t=(0, 4, 0), s=3.0)], mesh=m)
+    # a glass sphere on a linear (degree-1) path placed through a static outer level
+    b.receiver(F.SHAPE_SPHERE, glass, [trs(s=2.0), Anim([trs(t=(-6, 12, -4)), trs(t=(6, 14, -6))], degree=1)], p0=1.0)
+    # moving area light with keyframed emission; static panel light; moving point light
+    slide = Anim([trs(t=(-6, 23.5, 0), q=quat_axis_angle((1, 0, 0), 90)), trs(t=(0, 22, 4), q=quat_axis_angle((1, 0, 0), 100)),
+                  trs(t=(6, 23.5, 0), q=quat_axis_angle((1, 0, 0), 80))], degree=2)
+    b.area_light(F.SHAPE_DISK, mats["white"], [slide], [((1.0, 0.6, 0.3, 30), 0.0), ((0.3, 1.0, 0.4, 60), 0.4), ((0.4, 0.5, 1.0, 20), 0.9)],
+                 p0=3.0, p1=0.0)
+    b.area_light(F.SHAPE_RECT, mats["white"], [trs(t=(0, 23.9, 8), q=quat_axis_angle((1, 0, 0), 90))], (1, 1, 1, 8), p0=6.0, p1=4.0)
+    b.point_light([Anim([trs(t=(-10, 15, -12)), trs(t=(10, 18, -10))], degree=1)], [((1, 1, 1, 120), 0.2), ((1, 0.5, 0.5, 60), 0.8)])
+    b.add_camera([Anim([trs(t=(-3, 12, -60)), trs(t=(0, 13, -58), q=quat_axis_angle((0, 1, 0), 3)), trs(t=(4, 12, -60), q=quat_axis_angle((0, 1, 0), -4))],
+                       degree=2)], fov=30.0, shutter_size=0.5)
     return b
 
 
