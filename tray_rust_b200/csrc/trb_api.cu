@@ -243,14 +243,14 @@ trb_status resolve_samples(const trb_scene* s, const trb_render_cfg* cfg, uint32
     return TRB_OK;
 }
 
-template <bool STATS, int MODE>
+template <bool STATS, int MODE, bool ANIM>
 trb_status launch_render_t(trb_scene* s, const trb::RenderParams& rp, uint32_t flags, cudaStream_t st) {
     const int T = 9 + 2 * std::max(s->ds.fpw_x, s->ds.fpw_y);
     const size_t smem = (size_t)T * T * sizeof(float4);
     int per_sm = 0;
-    CU(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, trb::k_render<STATS, MODE>, trb::RENDER_THREADS, smem));
+    CU(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, trb::k_render<STATS, MODE, ANIM>, trb::RENDER_THREADS, smem));
     const uint32_t grid = std::max(1u, std::min<uint32_t>(rp.n_blocks, (uint32_t)(std::max(1, per_sm) * s->sm_count)));
-    trb::k_render<STATS, MODE><<<grid, trb::RENDER_THREADS, smem, st>>>(s->ds, rp, flags);
+    trb::k_render<STATS, MODE, ANIM><<<grid, trb::RENDER_THREADS, smem, st>>>(s->ds, rp, flags);
     g_launches++;
     CU(cudaGetLastError());
     return TRB_OK;
@@ -289,11 +289,13 @@ trb_status launch_wavefront(trb_scene* s, const trb::RenderParams& rp, uint32_t 
     const uint32_t rounds = s->integrator.max_depth + 2; // bounces 0..max_depth, plus the round that only resolves
     CU(cudaMemsetAsync(wf.counters, 0, 64 * trb::WF_CNT * sizeof(uint32_t), st));
     const unsigned gen_grid = (unsigned)std::min<size_t>((n_paths + 255) / 256, (size_t)s->sm_count * 8);
-    trb::k_wf_generate<<<gen_grid, 256, 0, st>>>(s->ds, rp, wf);
+    const bool anim = s->ds.has_anim != 0; // static scenes run kernels with no animation code in them at all
+    if (anim) trb::k_wf_generate<true><<<gen_grid, 256, 0, st>>>(s->ds, rp, wf);
+    else trb::k_wf_generate<false><<<gen_grid, 256, 0, st>>>(s->ds, rp, wf);
     g_launches++;
     const unsigned trace_grid = (unsigned)s->sm_count * 12, shade_grid = (unsigned)s->sm_count * 4;
     for (uint32_t round = 0; round < rounds; ++round) {
-        static const int refill = getenv("TRB_REFILL") ? atoi(getenv("TRB_REFILL")) : 8;
+        const int refill = getenv("TRB_REFILL") ? atoi(getenv("TRB_REFILL")) : 8;
         static const int occ = getenv("TRB_TRACE_OCC") ? atoi(getenv("TRB_TRACE_OCC")) : 7;
         static const unsigned tg = getenv("TRB_TRACE_GRID") ? (unsigned)atoi(getenv("TRB_TRACE_GRID")) : 12u;
         const unsigned tgrid = (unsigned)s->sm_count * tg;
@@ -304,15 +306,24 @@ trb_status launch_wavefront(trb_scene* s, const trb::RenderParams& rp, uint32_t 
             CU(cudaEventRecord(ev.first, st));
         }
         static const int sst = getenv("TRB_SMEM_STACK") ? atoi(getenv("TRB_SMEM_STACK")) : 16;
-#define TRB_TRACE_LAUNCH(ST, MB, SS) trb::k_wf_trace<ST, MB, SS><<<tgrid, 128, 0, st>>>(s->ds, rp, wf, round, flags, refill)
-        if (stats) TRB_TRACE_LAUNCH(true, 4, 16);
-        else if (occ >= 8) { if (sst <= 8) TRB_TRACE_LAUNCH(false, 8, 8); else if (sst <= 12) TRB_TRACE_LAUNCH(false, 8, 12); else TRB_TRACE_LAUNCH(false, 8, 16); }
-        else if (occ >= 7) { if (sst <= 8) TRB_TRACE_LAUNCH(false, 7, 8); else if (sst <= 12) TRB_TRACE_LAUNCH(false, 7, 12); else TRB_TRACE_LAUNCH(false, 7, 16); }
-        else { if (sst <= 8) TRB_TRACE_LAUNCH(false, 6, 8); else if (sst <= 12) TRB_TRACE_LAUNCH(false, 6, 12); else TRB_TRACE_LAUNCH(false, 6, 16); }
+        // TRB_TRACE_SCHED: 0 = flat state machine; else the phase thresholds A | B << 8 | C << 16 (see k_wf_trace)
+        const uint32_t sched = getenv("TRB_TRACE_SCHED") ? (uint32_t)strtoul(getenv("TRB_TRACE_SCHED"), nullptr, 0) : (12u | 8u << 8 | 8u << 16); // read per launch: tools/sched_sweep.py
+#define TRB_TRACE_LAUNCH(ST, MB, SS, AN, PH) trb::k_wf_trace<ST, MB, SS, AN, PH><<<tgrid, 128, 0, st>>>(s->ds, rp, wf, round, flags, refill, sched)
+        if (anim) { if (stats) TRB_TRACE_LAUNCH(true, 4, 16, true, true); else TRB_TRACE_LAUNCH(false, 7, 16, true, true); }
+        else if (stats) { if (sched) TRB_TRACE_LAUNCH(true, 4, 16, false, true); else TRB_TRACE_LAUNCH(true, 4, 16, false, false); }
+        else if (sched == 0) { if (occ >= 8) TRB_TRACE_LAUNCH(false, 8, 16, false, false); else if (occ >= 7) TRB_TRACE_LAUNCH(false, 7, 16, false, false); else TRB_TRACE_LAUNCH(false, 6, 16, false, false); }
+        else if (occ >= 8) TRB_TRACE_LAUNCH(false, 8, 16, false, true);
+        else if (occ >= 7) { if (sst <= 8) TRB_TRACE_LAUNCH(false, 7, 8, false, true); else TRB_TRACE_LAUNCH(false, 7, 16, false, true); }
+        else TRB_TRACE_LAUNCH(false, 6, 16, false, true);
 #undef TRB_TRACE_LAUNCH
         if (ev.first) { CU(cudaEventRecord(ev.second, st)); s->trace_events.push_back(ev); }
-        if (mode == 0) trb::k_wf_shade<0><<<shade_grid, 128, 0, st>>>(s->ds, rp, wf, round);
-        else trb::k_wf_shade<1><<<shade_grid, 128, 0, st>>>(s->ds, rp, wf, round);
+        if (anim) {
+            if (mode == 0) trb::k_wf_shade<0, true><<<shade_grid, 128, 0, st>>>(s->ds, rp, wf, round);
+            else trb::k_wf_shade<1, true><<<shade_grid, 128, 0, st>>>(s->ds, rp, wf, round);
+        } else {
+            if (mode == 0) trb::k_wf_shade<0, false><<<shade_grid, 128, 0, st>>>(s->ds, rp, wf, round);
+            else trb::k_wf_shade<1, false><<<shade_grid, 128, 0, st>>>(s->ds, rp, wf, round);
+        }
         g_launches += 2;
     }
     if (mode == 0) {
@@ -329,8 +340,12 @@ trb_status launch_render(trb_scene* s, const trb::RenderParams& rp, uint32_t fla
     if (!(flags & TRB_RENDER_MEGAKERNEL)) return launch_wavefront(s, rp, flags, mode, st);
     const bool stats = (flags & TRB_RENDER_STATS) != 0;
     CU(cudaMemsetAsync(rp.work_counter, 0, sizeof(uint32_t), st));
-    if (mode == 0) return stats ? launch_render_t<true, 0>(s, rp, flags, st) : launch_render_t<false, 0>(s, rp, flags, st);
-    return stats ? launch_render_t<true, 1>(s, rp, flags, st) : launch_render_t<false, 1>(s, rp, flags, st);
+    if (s->ds.has_anim) {
+        if (mode == 0) return stats ? launch_render_t<true, 0, true>(s, rp, flags, st) : launch_render_t<false, 0, true>(s, rp, flags, st);
+        return stats ? launch_render_t<true, 1, true>(s, rp, flags, st) : launch_render_t<false, 1, true>(s, rp, flags, st);
+    }
+    if (mode == 0) return stats ? launch_render_t<true, 0, false>(s, rp, flags, st) : launch_render_t<false, 0, false>(s, rp, flags, st);
+    return stats ? launch_render_t<true, 1, false>(s, rp, flags, st) : launch_render_t<false, 1, false>(s, rp, flags, st);
 }
 
 void stats_out(const trb::DStats& d, trb_stats* o) {
@@ -716,7 +731,8 @@ trb_status trb_camera_rays(trb_scene* s, const trb_render_cfg* cfg, size_t n, tr
     if (e != cudaSuccess) { cudaFree(d_rays); CU(e); }
     trb::RenderParams rp{};
     rp.blocks = s->d_blocks; rp.n_blocks = nb; rp.spp = spp; rp.sample_first = first; rp.sample_count = count; rp.seed = cfg->seed;
-    trb::k_camera_rays<<<(unsigned)std::min<size_t>((n + 255) / 256, 148 * 8), 256>>>(s->ds, rp, d_rays, d_xy);
+    if (s->ds.has_anim) trb::k_camera_rays<true><<<(unsigned)std::min<size_t>((n + 255) / 256, 148 * 8), 256>>>(s->ds, rp, d_rays, d_xy);
+    else trb::k_camera_rays<false><<<(unsigned)std::min<size_t>((n + 255) / 256, 148 * 8), 256>>>(s->ds, rp, d_rays, d_xy);
     e = cudaGetLastError();
     if (e == cudaSuccess) e = cudaMemcpy(rays, d_rays, n * sizeof(trb_ray), cudaMemcpyDeviceToHost);
     if (e == cudaSuccess) e = cudaMemcpy(xy, d_xy, n * 2 * sizeof(float), cudaMemcpyDeviceToHost);
@@ -732,7 +748,8 @@ trb_status trb_intersect_device(trb_scene* s, size_t n, const trb_ray* d_rays, t
     CU(cudaSetDevice(s->device));
     const unsigned grid = (unsigned)std::min<size_t>((n + 127) / 128, (size_t)s->sm_count * 16);
     g_launches++;
-    trb::k_intersect<false><<<grid, 128, 0, static_cast<cudaStream_t>(stream)>>>(s->ds, n, d_rays, d_hits, reinterpret_cast<trb::DStats*>(d_stats), s->d_error);
+    if (s->ds.has_anim) trb::k_intersect<false, true><<<grid, 128, 0, static_cast<cudaStream_t>(stream)>>>(s->ds, n, d_rays, d_hits, reinterpret_cast<trb::DStats*>(d_stats), s->d_error);
+    else trb::k_intersect<false, false><<<grid, 128, 0, static_cast<cudaStream_t>(stream)>>>(s->ds, n, d_rays, d_hits, reinterpret_cast<trb::DStats*>(d_stats), s->d_error);
     CU(cudaGetLastError());
     return TRB_OK;
 }
@@ -751,7 +768,8 @@ trb_status trb_intersect(trb_scene* s, size_t n, const trb_ray* rays, trb_hit* h
     if (e == cudaSuccess) {
         cudaEventRecord(s->ev0, 0);
         const unsigned grid = (unsigned)std::min<size_t>((n + 127) / 128, (size_t)s->sm_count * 16);
-        trb::k_intersect<true><<<grid, 128>>>(s->ds, n, d_rays, d_hits, s->d_stats, s->d_error); // host variant always counts tests
+        if (s->ds.has_anim) trb::k_intersect<true, true><<<grid, 128>>>(s->ds, n, d_rays, d_hits, s->d_stats, s->d_error);
+        else trb::k_intersect<true, false><<<grid, 128>>>(s->ds, n, d_rays, d_hits, s->d_stats, s->d_error); // host variant always counts tests
         cudaEventRecord(s->ev1, 0);
         e = cudaGetLastError();
     }

@@ -157,17 +157,20 @@ __device__ __noinline__ void eval_anim_xf(const DScene& sc, uint32_t first, uint
 #pragma unroll
     for (int i = 0; i < 16; ++i) { inv16[i] = x.inv.m[i]; if (mat16) mat16[i] = x.fwd.m[i]; }
 }
+template <bool ANIM>
 __device__ __forceinline__ void instance_inv(const DScene& sc, const DInstance& in, float time, float* inv16) {
-    if (sc.has_anim && (__ldg(&in.flags) & DI_ANIM_XF)) eval_anim_xf(sc, __ldg(&in.spline_first), __ldg(&in.n_splines), time, inv16, nullptr);
+    if (ANIM && (__ldg(&in.flags) & DI_ANIM_XF)) eval_anim_xf(sc, __ldg(&in.spline_first), __ldg(&in.n_splines), time, inv16, nullptr);
     else load_xf(in.inv, inv16);
 }
+template <bool ANIM>
 __device__ __forceinline__ void instance_inv_mat(const DScene& sc, const DInstance& in, float time, float* inv16, float* mat16) {
-    if (sc.has_anim && (__ldg(&in.flags) & DI_ANIM_XF)) eval_anim_xf(sc, __ldg(&in.spline_first), __ldg(&in.n_splines), time, inv16, mat16);
+    if (ANIM && (__ldg(&in.flags) & DI_ANIM_XF)) eval_anim_xf(sc, __ldg(&in.spline_first), __ldg(&in.n_splines), time, inv16, mat16);
     else { load_xf(in.inv, inv16); load_xf(in.mat, mat16); }
 }
 // AnimatedColor::color(time) of an emitter (animated_color.rs:52-78)
+template <bool ANIM>
 __device__ __forceinline__ void emission_at(const DScene& sc, const DInstance& in, float time, float& r, float& g, float& b) {
-    if (sc.has_anim && (__ldg(&in.flags) & DI_ANIM_EMISSION)) {
+    if (ANIM && (__ldg(&in.flags) & DI_ANIM_EMISSION)) {
         float c[3];
         trbh::animated_color(sc.color_keys, __ldg(&in.emission_first), __ldg(&in.n_emission), time, c);
         r = c[0]; g = c[1]; b = c[2];
@@ -254,7 +257,7 @@ __device__ __forceinline__ uint32_t trace_pop(TraceState& t, const Stack& stack)
     return ST_DONE;
 }
 // One transition: visit an interior node (two box tests), a leaf, the root, a pending instance, or leave a mesh.
-template <bool STATS, class Stack>
+template <bool STATS, bool ANIM, class Stack>
 __device__ __forceinline__ void trace_step(const DScene& sc, TraceState& t, const Stack& stack, Cnt& cnt, int* err) {
     const uint32_t cur = t.cur;
     const uint32_t tag = cur & REF_TAG;
@@ -329,7 +332,7 @@ __device__ __forceinline__ void trace_step(const DScene& sc, TraceState& t, cons
         bool enter = false;
         if (kind != TRB_INST_EMITTER_POINT) { // point lights never intersect (emitter.rs:119-120)
             float m[16];
-            instance_inv(sc, in, t.time, m);
+            instance_inv<ANIM>(sc, in, t.time, m);
             const f3 lo_ = xf_point(m, t.wo), ld_ = xf_vector(m, t.wd); // inv_mul_ray: direction not renormalised
             if (shape == TRB_SHAPE_MESH) {
                 const DMesh& me = sc.meshes[__ldg(&in.mesh)];
@@ -360,13 +363,147 @@ __device__ __forceinline__ void trace_step(const DScene& sc, TraceState& t, cons
     t.cur = next;
 }
 
+// ------------------------------------------------------------------------------------------
+// The same state machine cut into three kinds of micro-step so that a warp can run them in PHASES
+// (k_wf_trace, PHASED): per ray the sequence of operations — and therefore hits, t and the test
+// counters — is exactly trace_step's; only *when* a lane takes its next micro-step changes.
+//   class A  node work: one child-pair visit, or pop attempts            (~64 per ray on C4)
+//   class B  one triangle of a mesh leaf                                  (~4.5 per ray)
+//   class C  everything else: level root box, TLAS leaf, instance entry, mesh return (~6 per ray)
+// In the flat loop a warp executes A, B and C code every iteration with whatever lanes are in that
+// state: ncu showed the triangle code running with 2.2 of 32 lanes and the pop loop with 4.
+// ------------------------------------------------------------------------------------------
+constexpr uint32_t ST_POP = 0xfffffffcu; // control: take the next reference off the stack
+__device__ __forceinline__ int trace_class(const TraceState& t) {
+    const uint32_t cur = t.cur;
+    if (cur == ST_DONE) return 0;
+    const uint32_t tag = cur & REF_TAG;
+    if (tag == REF_INTERIOR || cur == ST_POP) return 1;
+    if (tag == REF_LEAF && t.level_inst != TRB_MISS) return 2;
+    return 3;
+}
+template <bool STATS, class Stack>
+__device__ __forceinline__ void step_nodes(TraceState& t, const Stack& stack, Cnt& cnt, int* err) {
+    uint32_t cur = t.cur;
+    if (cur != ST_POP) {
+        const DPair* __restrict__ rec = t.pairs + cur;
+        const float4 l_lo = __ldg(&rec->l_lo), l_hi = __ldg(&rec->l_hi), r_lo = __ldg(&rec->r_lo), r_hi = __ldg(&rec->r_hi);
+        if (STATS) cnt.node += 2;
+        float tl, tr;
+        const bool hl = box_hit(l_lo, l_hi, t.o, t.inv, t.nx, t.ny, t.nz, t.tmin, t.tmax, tl);
+        const bool hr = box_hit(r_lo, r_hi, t.o, t.inv, t.nx, t.ny, t.nz, t.tmin, t.tmax, tr);
+        const uint32_t axis = __float_as_uint(r_lo.w);
+        const bool neg = axis == 0 ? t.nx : (axis == 1 ? t.ny : t.nz);
+        const uint32_t ref_l = __float_as_uint(l_lo.w), ref_r = __float_as_uint(l_hi.w);
+        const bool h_near = neg ? hr : hl, h_far = neg ? hl : hr;
+        const uint32_t ref_near = neg ? ref_r : ref_l, ref_far = neg ? ref_l : ref_r;
+        const float t_far = neg ? tl : tr;
+        cur = h_near ? ref_near : (h_far ? ref_far : ST_POP);
+        if (h_near && h_far) {
+            if (t.sp >= STACK_DEPTH - 6) { *err = 1; t.sp = 0; cur = ST_DONE; }
+            else stack.put(t.sp++, ((unsigned long long)__float_as_uint(t_far) << 32) | ref_far);
+        }
+    }
+#pragma unroll
+    for (int k = 0; k < 2; ++k) { // bounded: a lane with a long run of culled entries comes back next iteration
+        if (cur == ST_POP) {
+            if (t.sp == 0) cur = ST_DONE;
+            else {
+                const unsigned long long e = stack.get(--t.sp);
+                const uint32_t ref = (uint32_t)e;
+                if ((ref & ST_INSTANCE) || __uint_as_float((uint32_t)(e >> 32)) < t.tmax) cur = ref;
+            }
+        }
+    }
+    t.cur = cur;
+}
 template <bool STATS>
+__device__ __forceinline__ void step_triangle(TraceState& t, Cnt& cnt) {
+    const uint32_t cur = t.cur;
+    const uint32_t a = cur & 0x01ffffffu, n = (cur >> 25) & 31u;
+    uint32_t next = n > 1 ? (REF_LEAF | ((n - 1) << 25) | (a + 1)) : ST_POP;
+    if (n != 0) {
+        const DTri* __restrict__ tri = t.tris + a;
+        const float4 v0 = __ldg(&tri->v0), q0 = __ldg(&tri->e0), q1 = __ldg(&tri->e1);
+        if (STATS) cnt.tri++;
+        const f3 e0 = mk(q0.x, q0.y, q0.z), e1 = mk(q1.x, q1.y, q1.z);
+        const f3 s0 = cross3(t.d, e1);
+        const float dd = dot3(s0, e0);
+        const float div = 1.0f / dd;
+        const f3 dv = t.o - mk(v0.x, v0.y, v0.z);
+        const float b1 = dot3(dv, s0) * div;
+        const f3 s1 = cross3(dv, e0);
+        const float b2 = dot3(t.d, s1) * div;
+        const float tt = dot3(e1, s1) * div;
+        const bool ok = dd != 0.0f && !(b1 < 0.0f || b1 > 1.0f) && !(b2 < 0.0f || b1 + b2 > 1.0f) && !(tt < t.tmin || tt > t.tmax);
+        if (ok) {
+            t.tmax = tt;
+            t.h_prim = __float_as_uint(v0.w); t.h_b1 = b1; t.h_b2 = b2; t.h_inst = t.level_inst;
+            t.found = true;
+            if (t.any_hit) { t.sp = 0; next = ST_DONE; } // occlusion only: any accepted hit answers the query
+        }
+    }
+    t.cur = next;
+}
+template <bool STATS, bool ANIM, class Stack>
+__device__ __forceinline__ void step_other(const DScene& sc, TraceState& t, const Stack& stack, Cnt& cnt) {
+    const uint32_t cur = t.cur;
+    uint32_t next = ST_POP;
+    if ((cur & REF_TAG) == REF_LEAF) { // TLAS leaf: its instances pop in the reference's order (bvh.rs:95-98)
+        const uint32_t a = cur & 0x01ffffffu, n = (cur >> 25) & 31u;
+        for (uint32_t k = a + n; k-- > a;) stack.put(t.sp++, ST_INSTANCE | k);
+    } else if (cur == ST_ROOT) {
+        const float4 lo = __ldg(&t.bvh->root_lo), hi = __ldg(&t.bvh->root_hi);
+        if (STATS) cnt.node++;
+        float te;
+        if (box_hit(lo, hi, t.o, t.inv, t.nx, t.ny, t.nz, t.tmin, t.tmax, te)) next = __float_as_uint(lo.w);
+    } else if (cur == ST_RETURN) {
+        t.o = t.wo; t.d = t.wd; t.inv = t.winv;
+        t.nx = t.d.x < 0.0f; t.ny = t.d.y < 0.0f; t.nz = t.d.z < 0.0f;
+        t.bvh = sc.tlas; t.pairs = sc.tlas_pairs; t.level_inst = TRB_MISS;
+    } else { // Instance::intersect for one entry of a TLAS leaf
+        const uint32_t ii = __ldg(&sc.tlas_order[cur & ~REF_TAG]);
+        const DInstance& in = sc.instances[ii];
+        if (STATS) cnt.inst++;
+        const uint32_t kind = __ldg(&in.kind), shape = __ldg(&in.shape);
+        if (kind != TRB_INST_EMITTER_POINT) {
+            float m[16];
+            instance_inv<ANIM>(sc, in, t.time, m);
+            const f3 lo_ = xf_point(m, t.wo), ld_ = xf_vector(m, t.wd);
+            if (shape == TRB_SHAPE_MESH) {
+                const DMesh& me = sc.meshes[__ldg(&in.mesh)];
+                t.o = lo_; t.d = ld_;
+                t.inv = mk(1.0f / ld_.x, 1.0f / ld_.y, 1.0f / ld_.z);
+                t.nx = ld_.x < 0.0f; t.ny = ld_.y < 0.0f; t.nz = ld_.z < 0.0f;
+                t.bvh = &me.bvh; t.pairs = me.bvh.pairs; t.tris = me.tris; t.level_inst = ii;
+                stack.put(t.sp++, ST_RETURN);
+                next = ST_ROOT;
+            } else {
+                const float p0 = __ldg(&in.p0), p1 = __ldg(&in.p1);
+                float tt = t.tmax;
+                bool h;
+                if (shape == TRB_SHAPE_SPHERE) h = sphere_t(p0, lo_, ld_, t.tmin, tt);
+                else if (shape == TRB_SHAPE_DISK) h = disk_t(p0, p1, lo_, ld_, t.tmin, tt);
+                else h = rect_t(p0, p1, lo_, ld_, t.tmin, tt);
+                if (h) {
+                    t.tmax = tt;
+                    t.h_inst = ii; t.h_prim = 0; t.h_b1 = 0.0f; t.h_b2 = 0.0f;
+                    t.found = true;
+                    if (t.any_hit) { t.sp = 0; next = ST_DONE; }
+                }
+            }
+        }
+    }
+    t.cur = next;
+}
+
+template <bool STATS, bool ANIM>
 __device__ __noinline__ bool scene_trace(const DScene& sc, Ray& ray, HitRec& hit, bool any_hit, Cnt& cnt, int* err, float time) {
     TraceState t;
     unsigned long long stack_mem[STACK_DEPTH];
     const LocalStack stack{stack_mem};
     trace_init(sc, t, ray, any_hit, time);
-    while (t.cur != ST_DONE) trace_step<STATS>(sc, t, stack, cnt, err);
+    while (t.cur != ST_DONE) trace_step<STATS, ANIM>(sc, t, stack, cnt, err);
     ray.tmax = t.tmax;
     hit.t = t.tmax; hit.inst = t.h_inst; hit.prim = t.h_prim; hit.b1 = t.h_b1; hit.b2 = t.h_b2;
     return t.found;
@@ -378,10 +515,11 @@ __device__ __noinline__ bool scene_trace(const DScene& sc, Ray& ray, HitRec& hit
 // ------------------------------------------------------------------------------------------
 struct Surf { f3 p, n, ng, dp_du; };
 
+template <bool ANIM>
 __device__ __forceinline__ void surface_at(const DScene& sc, const Ray& ray, const HitRec& hit, Surf& s, float time) {
     const DInstance& in = sc.instances[hit.inst];
     float m[16], w[16];
-    instance_inv_mat(sc, in, time, m, w);
+    instance_inv_mat<ANIM>(sc, in, time, m, w);
     const f3 o = xf_point(m, ray.o), d = xf_vector(m, ray.d);
     const f3 p = o + d * hit.t; // ray.at(t) of the local ray
     const uint32_t shape = __ldg(&in.shape);
@@ -899,6 +1037,7 @@ struct DirectSetup {
     bool has_shadow, has_mis;
 };
 
+template <bool ANIM>
 __device__ __noinline__ void direct_setup(const DScene& sc, const Mat& m, const Frame& fr, f3 wo, uint32_t li, float l0, float l1, float b0, float b1,
                                           float bc, float time, DirectSetup& ds) {
     ds.a = splat(0.0f); ds.b = splat(0.0f); ds.shadow_d = splat(0.0f); ds.mis_d = splat(0.0f); ds.has_shadow = false; ds.has_mis = false;
@@ -906,10 +1045,10 @@ __device__ __noinline__ void direct_setup(const DScene& sc, const Mat& m, const 
     const uint32_t kind = __ldg(&light.kind), shape = __ldg(&light.shape);
     const float p0 = __ldg(&light.p0), p1 = __ldg(&light.p1);
     f3 emission;
-    emission_at(sc, light, time, emission.x, emission.y, emission.z); // self.emission.color(time)
+    emission_at<ANIM>(sc, light, time, emission.x, emission.y, emission.z); // self.emission.color(time)
     const bool delta = kind == TRB_INST_EMITTER_POINT;
     float linv[16], lmat[16];
-    instance_inv_mat(sc, light, time, linv, lmat); // self.transform.transform(time)
+    instance_inv_mat<ANIM>(sc, light, time, linv, lmat); // self.transform.transform(time)
     const f3 p = fr.p;
     // --- light.sample_incident(&bsdf.p, ...) ---
     f3 lrad, wi, seg;
@@ -965,16 +1104,17 @@ __device__ __noinline__ void direct_setup(const DScene& sc, const Mat& m, const 
     }
 }
 // Does the MIS ray's hit see the light's emitting side? e.radiance(&-w_i, &h.dg.p, &h.dg.ng) (integrator/mod.rs:156-162)
+template <bool ANIM>
 __device__ __forceinline__ bool mis_sees_light(const DScene& sc, f3 org, f3 mis_d, uint32_t li, uint32_t hit_inst, float hit_t, float time) {
     if (hit_inst != li) return false;
     const DInstance& light = sc.instances[li];
     f3 le;
-    emission_at(sc, light, time, le.x, le.y, le.z);
+    emission_at<ANIM>(sc, light, time, le.x, le.y, le.z);
     if (black(le)) return false; // `if !li.is_black()`
     Ray mr; mr.o = org; mr.d = mis_d; mr.tmin = 0.001f; mr.tmax = hit_t;
     HitRec mh; mh.t = hit_t; mh.inst = hit_inst; mh.prim = 0; mh.b1 = 0.0f; mh.b2 = 0.0f; // area lights are analytic shapes
     Surf s;
-    surface_at(sc, mr, mh, s, time);
+    surface_at<ANIM>(sc, mr, mh, s, time);
     return dot3(-mis_d, s.ng) > 0.0f;
 }
 __device__ __forceinline__ f3 direct_resolve(f3 a, f3 b, bool occluded, bool mis_ok) {
@@ -996,6 +1136,7 @@ struct BounceOut {
     f3 org;              // bsdf.p
     bool specular, terminate; // terminate: no continuation ray (black f / pdf 0 / RR / max depth)
 };
+template <bool ANIM>
 __device__ __forceinline__ void shade_bounce(const DScene& sc, const Surf& s, uint32_t hit_inst, f3 ray_d, f3 first_ng, uint32_t bounce, bool prev_specular,
                                              uint32_t hsample, f3 throughput_in, float time, f3& illum, BounceOut& o) {
     const DInstance& in = sc.instances[hit_inst];
@@ -1004,7 +1145,7 @@ __device__ __forceinline__ void shade_bounce(const DScene& sc, const Surf& s, ui
             const f3 w = -ray_d;
             if (dot3(w, first_ng) > 0.0f) { // Emitter::radiance with the FIRST hit's normal (path.rs:73, Q1)
                 f3 le;
-                emission_at(sc, in, time, le.x, le.y, le.z);
+                emission_at<ANIM>(sc, in, time, le.x, le.y, le.z);
                 illum = illum + throughput_in * le;
             }
         }
@@ -1022,7 +1163,7 @@ __device__ __forceinline__ void shade_bounce(const DScene& sc, const Surf& s, ui
     uint32_t l = f2u(lc * (float)sc.n_lights); // sample_one_light (integrator/mod.rs:108-110), no xN (Q2)
     if (l > sc.n_lights - 1) l = sc.n_lights - 1;
     o.light = __ldg(&sc.lights[l]);
-    direct_setup(sc, m, fr, wo, o.light, l0, l1, b0, b1, bc, time, o.ds);
+    direct_setup<ANIM>(sc, m, fr, wo, o.light, l0, l1, b0, b1, bc, time, o.ds);
     o.t_before = throughput_in;
     o.org = fr.p;
     rng.two_d(bounce, S_P0, S_P1, S_P_PERM, q0, q1);
@@ -1050,12 +1191,13 @@ __device__ __forceinline__ void shade_bounce(const DScene& sc, const Surf& s, ui
 // (multithreaded.rs:94-102, path.rs:45-119) with the rays traced inline.
 // ------------------------------------------------------------------------------------------
 // Returns the ray's time: frame_time = (shutter_close - shutter_open) * time + shutter_open.
+template <bool ANIM>
 __device__ __forceinline__ float camera_ray(const DScene& sc, float sx, float sy, float tm, Ray& ray) { // camera.rs:150-157
     const f3 pc = xf_point(sc.cam.px_to_cam, mk(sx, sy, 0.0f));
     const f3 pp = mk(sc.cam.scaling[0], sc.cam.scaling[1], sc.cam.scaling[2]) * pc;
     const f3 d = unit(pp);
     const float frame_time = (sc.cam.shutter_close - sc.cam.shutter_open) * tm + sc.cam.shutter_open;
-    if (sc.cam.animated) { // keyframed camera: cam_world.transform(frame_time) per ray
+    if (ANIM && sc.cam.animated) { // keyframed camera: cam_world.transform(frame_time) per ray
         float inv[16], mat[16];
         eval_anim_xf(sc, sc.cam.spline_first, sc.cam.n_splines, frame_time, inv, mat);
         ray.o = xf_point(mat, splat(0.0f));
@@ -1068,32 +1210,32 @@ __device__ __forceinline__ float camera_ray(const DScene& sc, float sx, float sy
     return frame_time;
 }
 
-template <bool STATS>
+template <bool STATS, bool ANIM>
 __device__ f3 radiance_of_sample(const DScene& sc, Ray ray, float time, uint32_t hpix_sample, bool ref_shadow, RayCounts& rc, Cnt& cnt, int* err) {
     HitRec hit;
     rc.primary++;
-    if (!scene_trace<STATS>(sc, ray, hit, false, cnt, err, time)) return splat(0.0f); // multithreaded.rs:101-102
+    if (!scene_trace<STATS, ANIM>(sc, ray, hit, false, cnt, err, time)) return splat(0.0f); // multithreaded.rs:101-102
     f3 illum = splat(0.0f), throughput = splat(1.0f);
     bool specular_bounce = false;
     uint32_t bounce = 0;
     Surf s;
-    surface_at(sc, ray, hit, s, time);
+    surface_at<ANIM>(sc, ray, hit, s, time);
     const f3 first_ng = s.ng;
     for (;;) {
         BounceOut o;
-        shade_bounce(sc, s, hit.inst, ray.d, first_ng, bounce, specular_bounce, hpix_sample, throughput, time, illum, o);
+        shade_bounce<ANIM>(sc, s, hit.inst, ray.d, first_ng, bounce, specular_bounce, hpix_sample, throughput, time, illum, o);
         bool occluded = false, mis_ok = false;
         if (o.ds.has_shadow) {
             Ray sr; sr.o = o.org; sr.d = o.ds.shadow_d; sr.tmin = 0.001f; sr.tmax = 0.999f;
             HitRec sh;
             rc.shadow++;
-            occluded = scene_trace<STATS>(sc, sr, sh, !ref_shadow, cnt, err, time);
+            occluded = scene_trace<STATS, ANIM>(sc, sr, sh, !ref_shadow, cnt, err, time);
         }
         if (o.ds.has_mis) {
             Ray mr; mr.o = o.org; mr.d = o.ds.mis_d; mr.tmin = 0.001f; mr.tmax = finf();
             HitRec mh;
             rc.mis++;
-            if (scene_trace<STATS>(sc, mr, mh, false, cnt, err, time)) mis_ok = mis_sees_light(sc, o.org, o.ds.mis_d, o.light, mh.inst, mh.t, time);
+            if (scene_trace<STATS, ANIM>(sc, mr, mh, false, cnt, err, time)) mis_ok = mis_sees_light<ANIM>(sc, o.org, o.ds.mis_d, o.light, mh.inst, mh.t, time);
         }
         illum = illum + o.t_before * direct_resolve(o.ds.a, o.ds.b, occluded, mis_ok);
         throughput = o.throughput;
@@ -1101,8 +1243,8 @@ __device__ f3 radiance_of_sample(const DScene& sc, Ray ray, float time, uint32_t
         if (o.terminate) break;
         ray.o = o.org; ray.d = o.next_d; ray.tmin = 0.001f; ray.tmax = finf();
         rc.cont++;
-        if (!scene_trace<STATS>(sc, ray, hit, false, cnt, err, time)) break;
-        surface_at(sc, ray, hit, s, time);
+        if (!scene_trace<STATS, ANIM>(sc, ray, hit, false, cnt, err, time)) break;
+        surface_at<ANIM>(sc, ray, hit, s, time);
         bounce += 1;
     }
     return illum;
@@ -1170,7 +1312,7 @@ __device__ __forceinline__ void splat_sample(const DScene& sc, float4* tile, con
 constexpr int RENDER_THREADS = 128;
 constexpr int MAX_TILE = 25; // fpw <= 8
 
-template <bool STATS, int MODE>
+template <bool STATS, int MODE, bool ANIM>
 __global__ void __launch_bounds__(RENDER_THREADS) k_render(const __grid_constant__ DScene sc, const __grid_constant__ RenderParams rp, uint32_t flags) {
     extern __shared__ float4 tile[];           // T*T RGBW
     __shared__ float s_table[256];
@@ -1204,9 +1346,9 @@ __global__ void __launch_bounds__(RENDER_THREADS) k_render(const __grid_constant
             const float sy = ld_sobol(ip, ps.scr1) + (float)py;
             const float tm = ld_vdc(permute_index(si, rp.spp, ps.ktime), ps.scrt);
             Ray ray;
-            const float time = camera_ray(sc, sx, sy, tm, ray);
+            const float time = camera_ray<ANIM>(sc, sx, sy, tm, ray);
             my_samples++;
-            f3 c = radiance_of_sample<STATS>(sc, ray, time, rng_absorb(ps.hpix, si), ref_shadow, rc, cnt, rp.error_flag);
+            f3 c = radiance_of_sample<STATS, ANIM>(sc, ray, time, rng_absorb(ps.hpix, si), ref_shadow, rc, cnt, rp.error_flag);
             c = mk(clampf(c.x, 0.0f, 1.0f), clampf(c.y, 0.0f, 1.0f), clampf(c.z, 0.0f, 1.0f)); // multithreaded.rs:99 (Q12)
             if (MODE == 1) {
                 trb_sample* out = reinterpret_cast<trb_sample*>(rp.samples_out) + ((size_t)item * 64 + pix) * rp.sample_count + (si - rp.sample_first);
@@ -1292,6 +1434,7 @@ __device__ __forceinline__ void wf_push(uint32_t* q, uint32_t* counter, bool wan
     if (want) q[base + __popc(mask & ((1u << lane) - 1u))] = value;
 }
 
+template <bool ANIM>
 __global__ void __launch_bounds__(256) k_wf_generate(const __grid_constant__ DScene sc, const __grid_constant__ RenderParams rp, const __grid_constant__ WfState wf) {
     const uint32_t n = wf.n_paths;
     for (uint32_t p = blockIdx.x * blockDim.x + threadIdx.x; p < n; p += gridDim.x * blockDim.x) {
@@ -1300,7 +1443,7 @@ __global__ void __launch_bounds__(256) k_wf_generate(const __grid_constant__ DSc
         float sx, sy, tm;
         sample_position(rp, ps, id, sx, sy, tm);
         Ray ray;
-        const float time = camera_ray(sc, sx, sy, tm, ray);
+        const float time = camera_ray<ANIM>(sc, sx, sy, tm, ray);
         wf.org[p] = make_float4(ray.o.x, ray.o.y, ray.o.z, __uint_as_float(0u));
         wf.cont[p] = make_float4(ray.d.x, ray.d.y, ray.d.z, finf());
         wf.thr[p] = make_float4(1.0f, 1.0f, 1.0f, time); // .w: the path's ray.time (every child ray inherits it)
@@ -1317,9 +1460,13 @@ __global__ void __launch_bounds__(256) k_wf_generate(const __grid_constant__ DSc
 // whose ray has finished writes its result and, once enough lanes of the warp are idle, the idle lanes
 // fetch new rays with one warp-aggregated atomic, so rays of very different lengths (an any-hit shadow
 // ray vs. a continuation ray crossing the whole mesh) do not leave the warp mostly empty.
-template <bool STATS, int MINB, int SMEM_STACK>
+//
+// PHASED: each iteration the warp runs only the micro-step classes (A nodes / B triangle / C other) that enough of its
+// lanes are waiting for (thresholds in `sched`: A | B << 8 | C << 16; if no class reaches its threshold, the fullest one
+// runs), so triangle tests and instance entries execute with many lanes instead of the two or three that happen to be there.
+template <bool STATS, int MINB, int SMEM_STACK, bool ANIM, bool PHASED>
 __global__ void __launch_bounds__(128, MINB) k_wf_trace(const __grid_constant__ DScene sc, const __grid_constant__ RenderParams rp, const __grid_constant__ WfState wf,
-                                                         uint32_t round, uint32_t flags, int WF_REFILL_IDLE) {
+                                                         uint32_t round, uint32_t flags, int WF_REFILL_IDLE, uint32_t sched) {
     uint32_t* cnt_r = wf.counters + round * WF_CNT;
     const uint32_t n_cont = cnt_r[WF_N_CONT], n_shadow = cnt_r[WF_N_SHADOW], n_mis = cnt_r[WF_N_MIS];
     const uint32_t total = n_cont + n_shadow + n_mis;
@@ -1370,7 +1517,7 @@ __global__ void __launch_bounds__(128, MINB) k_wf_trace(const __grid_constant__ 
                     Ray ray; ray.o = mk(o4.x, o4.y, o4.z); ray.d = mk(d4.x, d4.y, d4.z);
                     ray.tmin = (type == 0 && round == 0) ? 0.0f : 0.001f;
                     ray.tmax = type == 1 ? 0.999f : finf();
-                    trace_init(sc, t, ray, type == 1 && shadow_any, sc.has_anim ? __ldg(&wf.thr[p].w) : 0.0f);
+                    trace_init(sc, t, ray, type == 1 && shadow_any, ANIM ? __ldg(&wf.thr[p].w) : 0.0f);
                     have = true;
                 }
             }
@@ -1378,11 +1525,29 @@ __global__ void __launch_bounds__(128, MINB) k_wf_trace(const __grid_constant__ 
         const unsigned busy0 = __ballot_sync(0xffffffffu, have);
         if (busy0 == 0) { if (exhausted) break; else continue; }
         // ---- traverse until enough lanes have finished ----
-        for (;;) {
-            if (have && t.cur != ST_DONE) trace_step<STATS>(sc, t, stack, cnt, rp.error_flag);
-            const unsigned running = __ballot_sync(0xffffffffu, have && t.cur != ST_DONE);
-            if (running == 0) break;
-            if (!exhausted && 32 - __popc(running) >= WF_REFILL_IDLE) break;
+        if (PHASED) {
+            const int thr_a = (int)(sched & 255u), thr_b = (int)((sched >> 8) & 255u), thr_c = (int)((sched >> 16) & 255u);
+            for (;;) {
+                const int cls = have ? trace_class(t) : 0;
+                const unsigned m_a = __ballot_sync(0xffffffffu, cls == 1), m_b = __ballot_sync(0xffffffffu, cls == 2), m_c = __ballot_sync(0xffffffffu, cls == 3);
+                const int n_a = __popc(m_a), n_b = __popc(m_b), n_c = __popc(m_c);
+                if ((m_a | m_b | m_c) == 0) break;
+                if (!exhausted && 32 - (n_a + n_b + n_c) >= WF_REFILL_IDLE) break;
+                bool do_a = n_a >= thr_a, do_b = n_b >= thr_b, do_c = n_c >= thr_c;
+                if (!(do_a || do_b || do_c)) { // nobody reached a quorum: run the fullest class
+                    if (n_a >= n_b && n_a >= n_c) do_a = true; else if (n_b >= n_c) do_b = true; else do_c = true;
+                }
+                if (do_c && cls == 3) step_other<STATS, ANIM>(sc, t, stack, cnt);
+                if (do_b && cls == 2) step_triangle<STATS>(t, cnt);
+                if (do_a && cls == 1) step_nodes<STATS>(t, stack, cnt, rp.error_flag);
+            }
+        } else {
+            for (;;) {
+                if (have && t.cur != ST_DONE) trace_step<STATS, ANIM>(sc, t, stack, cnt, rp.error_flag);
+                const unsigned running = __ballot_sync(0xffffffffu, have && t.cur != ST_DONE);
+                if (running == 0) break;
+                if (!exhausted && 32 - __popc(running) >= WF_REFILL_IDLE) break;
+            }
         }
     }
     if (rp.stats) {
@@ -1403,7 +1568,7 @@ __global__ void __launch_bounds__(128, MINB) k_wf_trace(const __grid_constant__ 
 }
 
 // Shade round r (== bounce r of every live path). MODE 0: finished samples go to wf.rad; MODE 1: to trb_sample records.
-template <int MODE>
+template <int MODE, bool ANIM>
 __global__ void __launch_bounds__(128) k_wf_shade(const __grid_constant__ DScene sc, const __grid_constant__ RenderParams rp, const __grid_constant__ WfState wf,
                                                    uint32_t round) {
     uint32_t* cnt_r = wf.counters + round * WF_CNT;
@@ -1437,7 +1602,7 @@ __global__ void __launch_bounds__(128) k_wf_shade(const __grid_constant__ DScene
                 if (fl & WF_F_SHADOW) occluded = __float_as_uint(wf.shadow[p].w) != 0u;
                 if (fl & WF_F_MIS) {
                     const float4 m4 = wf.mis[p];
-                    mis_ok = mis_sees_light(sc, org, mk(m4.x, m4.y, m4.z), __float_as_uint(b4.w), __float_as_uint(a4.w), m4.w, time);
+                    mis_ok = mis_sees_light<ANIM>(sc, org, mk(m4.x, m4.y, m4.z), __float_as_uint(b4.w), __float_as_uint(a4.w), m4.w, time);
                 }
                 illum = illum + mk(t4.x, t4.y, t4.z) * direct_resolve(mk(a4.x, a4.y, a4.z), mk(b4.x, b4.y, b4.z), occluded, mis_ok);
                 done = (fl & WF_F_TERMINATE) != 0;
@@ -1450,14 +1615,14 @@ __global__ void __launch_bounds__(128) k_wf_shade(const __grid_constant__ DScene
                     Ray ray; ray.o = org; ray.d = mk(c4.x, c4.y, c4.z); ray.tmin = 0.0f; ray.tmax = c4.w;
                     HitRec h; h.t = c4.w; h.inst = h4.x; h.prim = h4.y; h.b1 = __uint_as_float(h4.z); h.b2 = __uint_as_float(h4.w);
                     Surf s;
-                    surface_at(sc, ray, h, s, time);
+                    surface_at<ANIM>(sc, ray, h, s, time);
                     f3 first_ng;
                     if (round == 0) { first_ng = s.ng; wf.ng[p] = make_float4(s.ng.x, s.ng.y, s.ng.z, 0.0f); }
                     else { const float4 n4 = wf.ng[p]; first_ng = mk(n4.x, n4.y, n4.z); }
                     const SampleId id = sample_id(sc, rp, p);
                     const uint32_t hs = rng_absorb(rng_absorb(rng_seed(rp.seed), id.pixel), id.si);
                     BounceOut o;
-                    shade_bounce(sc, s, h.inst, ray.d, first_ng, round, (fl & WF_F_SPECULAR) != 0, hs, mk(th4.x, th4.y, th4.z), time, illum, o);
+                    shade_bounce<ANIM>(sc, s, h.inst, ray.d, first_ng, round, (fl & WF_F_SPECULAR) != 0, hs, mk(th4.x, th4.y, th4.z), time, illum, o);
                     const uint32_t nf = (o.specular ? WF_F_SPECULAR : 0u) | (o.terminate ? WF_F_TERMINATE : 0u) | (o.ds.has_shadow ? WF_F_SHADOW : 0u) |
                                         (o.ds.has_mis ? WF_F_MIS : 0u);
                     push_cont = !o.terminate; push_shadow = o.ds.has_shadow; push_mis = o.ds.has_mis;
@@ -1533,6 +1698,7 @@ __global__ void __launch_bounds__(RENDER_THREADS) k_wf_film(const __grid_constan
 }
 
 // LowDiscrepancy::get_samples + get_samples_1d + Camera::generate_ray only (parity of S2 / C)
+template <bool ANIM>
 __global__ void k_camera_rays(const __grid_constant__ DScene sc, const __grid_constant__ RenderParams rp, trb_ray* rays, float* xy) {
     const size_t n = (size_t)rp.n_blocks * 64 * rp.sample_count;
     for (size_t i = blockIdx.x * (size_t)blockDim.x + threadIdx.x; i < n; i += (size_t)gridDim.x * blockDim.x) {
@@ -1545,7 +1711,7 @@ __global__ void k_camera_rays(const __grid_constant__ DScene sc, const __grid_co
         const float sx = ld_vdc(ip, ps.scr0) + (float)px, sy = ld_sobol(ip, ps.scr1) + (float)py;
         const float tm = ld_vdc(permute_index(si, rp.spp, ps.ktime), ps.scrt);
         Ray r;
-        camera_ray(sc, sx, sy, tm, r);
+        camera_ray<ANIM>(sc, sx, sy, tm, r);
         rays[i].o[0] = r.o.x; rays[i].o[1] = r.o.y; rays[i].o[2] = r.o.z;
         rays[i].d[0] = r.d.x; rays[i].d[1] = r.d.y; rays[i].d[2] = r.d.z;
         rays[i].min_t = r.tmin; rays[i].max_t = r.tmax;
@@ -1554,7 +1720,7 @@ __global__ void k_camera_rays(const __grid_constant__ DScene sc, const __grid_co
 }
 
 // Scene::intersect over a ray batch (trb_intersect): one ray per thread, grid-stride.
-template <bool STATS>
+template <bool STATS, bool ANIM>
 __global__ void __launch_bounds__(128) k_intersect(const __grid_constant__ DScene sc, size_t n, const trb_ray* __restrict__ rays, trb_hit* __restrict__ hits,
                                                     DStats* stats, int* err) {
     Cnt cnt = {0, 0, 0};
@@ -1563,7 +1729,7 @@ __global__ void __launch_bounds__(128) k_intersect(const __grid_constant__ DScen
         const float4 a = __ldg(reinterpret_cast<const float4*>(rays + i)), b = __ldg(reinterpret_cast<const float4*>(rays + i) + 1);
         Ray r; r.o = mk(a.x, a.y, a.z); r.d = mk(a.w, b.x, b.y); r.tmin = b.z; r.tmax = b.w;
         HitRec h;
-        const bool hit = scene_trace<STATS>(sc, r, h, false, cnt, err, sc.cam.shutter_open); // batch rays carry no time: the frame's shutter-open time
+        const bool hit = scene_trace<STATS, ANIM>(sc, r, h, false, cnt, err, sc.cam.shutter_open); // batch rays carry no time: the frame's shutter-open time
         rc.primary++;
         uint4 o; o.x = __float_as_uint(r.tmax); o.y = hit ? h.inst : TRB_MISS; o.z = hit ? h.prim : 0u; o.w = 0u;
         *reinterpret_cast<uint4*>(hits + i) = o;
