@@ -344,6 +344,12 @@ trb_status trb_host_build_bvh(const float* boxes6, uint32_t n, uint32_t max_geom
 /* Keyframe::transform (keyframe.rs:60-63): T * R * S and its inverse, row-major. */
 trb_status trb_host_keyframe_transform(const trb_keyframe* kf, float* mat16, float* inv16);
 
+/* Self-check of the two-level node records the trace kernel walks (csrc/trb_device.h DQuad): for every ray
+ * with a finite 1/d, a literal BVH::intersect walk (bvh.rs:81-130) over `nodes` and a walk through the packed
+ * records must visit the same leaves in the same order. Host only. */
+trb_status trb_host_quad_check(const trb_bvh_node* nodes, uint32_t n_nodes, const trb_ray* rays, uint32_t n_rays,
+                               uint32_t* mismatches, uint64_t* leaf_visits, uint64_t* quad_visits);
+
 /* AnimatedTransform::transform(time) (animated_transform.rs:40-56) of the transform stack
  * desc->splines[first .. first+count): the same code the device runs per ray for keyframed
  * instances, compiled for the host. AnimatedColor::color(time) (animated_color.rs:52-78) of

@@ -26,9 +26,11 @@ def scene(depth0):
     return g
 
 
-def measure(g, sched, refill=8, flags=0):
+def measure(g, sched, refill=8, flags=0, quads=1, occ=7):
     os.environ["TRB_TRACE_SCHED"] = str(sched)
     os.environ["TRB_REFILL"] = str(refill)
+    os.environ["TRB_TRACE_QUADS"] = str(quads)
+    os.environ["TRB_TRACE_OCC"] = str(occ)
     g.render_device(film.data_ptr(), stats.data_ptr(), None, spp=4096, sample_first=0, sample_count=SPP_STEP, seed=1, flags=flags)
     torch.cuda.synchronize(); stats.zero_()
     ms = 0.0
@@ -43,16 +45,19 @@ def measure(g, sched, refill=8, flags=0):
     return float(s[1:5].sum()) / ms / 1e3, ms / STEPS
 
 
-def sched(a, b, c):
-    return a | b << 8 | c << 16
+def sched(a, b, c, pf=0):
+    return a | b << 8 | c << 16 | pf << 24
 
 
-CASES = [("flat", 0, 8)] + [("A%d B%d C%d r%d" % (a, b, c, r), sched(a, b, c), r)
-                             for (a, b, c, r) in [(12, 8, 8, 8), (16, 8, 8, 8), (8, 8, 8, 8), (12, 4, 4, 8), (12, 12, 12, 8), (12, 16, 8, 8), (16, 16, 16, 8),
-                                                  (33, 33, 33, 8), (20, 12, 8, 8), (12, 8, 8, 4), (12, 8, 8, 12), (12, 8, 8, 16), (1, 8, 8, 8), (1, 12, 12, 8)]]
+# (name, sched word, refill, quads, occ)
+CASES = [("flat pairs", 0, 8, 0, 7), ("phased pairs", sched(12, 4, 4), 8, 0, 7), ("phased pairs +pf", sched(12, 4, 4, 1), 8, 0, 7)]
+for occ in (7, 6, 8):
+    for (a, b, c) in [(12, 4, 4), (12, 8, 8), (1, 4, 4), (8, 4, 4)]:
+        CASES.append(("quads A%d B%d C%d occ%d" % (a, b, c, occ), sched(a, b, c), 8, 1, occ))
+CASES += [("quads +pf occ7", sched(12, 4, 4, 1), 8, 1, 7), ("quads r4", sched(12, 4, 4), 4, 1, 7), ("quads r12", sched(12, 4, 4), 12, 1, 7)]
 if __name__ == "__main__":
     full, direct = scene(False), scene(True)
-    for name, sc, r in CASES:
-        v, ms = measure(full, sc, r)
-        v0, ms0 = measure(direct, sc, r)
-        print("%-18s full path %7.1f Mrays/s (%6.1f ms/step)   primary+shadow %7.1f Mrays/s (%5.1f ms/step)" % (name, v, ms, v0, ms0), flush=True)
+    for name, sc, r, q, occ in CASES:
+        v, ms = measure(full, sc, r, quads=q, occ=occ)
+        v0, ms0 = measure(direct, sc, r, quads=q, occ=occ)
+        print("%-24s full path %7.1f Mrays/s (%6.1f ms/step)   primary+shadow %7.1f Mrays/s (%5.1f ms/step)" % (name, v, ms, v0, ms0), flush=True)

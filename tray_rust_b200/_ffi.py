@@ -131,7 +131,7 @@ TRB_SYMBOLS = [
     "trb_render", "trb_render_device", "trb_intersect", "trb_intersect_device", "trb_camera_rays",
     "trb_render_samples", "trb_film_to_srgb8", "trb_block_list", "trb_scene_get_bvh", "trb_scene_get_transform",
     "trb_scene_get_filter_table", "trb_last_error", "trb_abi_version", "trb_desc_load_json", "trb_desc_free",
-    "trb_host_build_bvh", "trb_host_keyframe_transform", "trb_host_animated_transform", "trb_host_animated_color", "trb_launch_count", "trb_scene_trace_time",
+    "trb_host_build_bvh", "trb_host_keyframe_transform", "trb_host_animated_transform", "trb_host_animated_color", "trb_host_quad_check", "trb_launch_count", "trb_scene_trace_time",
 ]
 
 _trb = None
@@ -179,6 +179,7 @@ def load_trb():
     lib.trb_host_keyframe_transform.argtypes = [C.POINTER(Keyframe), vp, vp]
     lib.trb_host_animated_transform.argtypes = [C.POINTER(SceneDesc), u32, u32, f32, vp, vp]
     lib.trb_host_animated_color.argtypes = [C.POINTER(SceneDesc), u32, u32, f32, vp]
+    lib.trb_host_quad_check.argtypes = [vp, u32, vp, u32, C.POINTER(u32), C.POINTER(C.c_uint64), C.POINTER(C.c_uint64)]
     lib.trb_launch_count.restype = C.c_uint64
     lib.trb_scene_trace_time.argtypes = [vp, C.POINTER(f32), C.POINTER(u32)]
     _trb = lib

@@ -59,6 +59,7 @@ uint32_t pow2_ceil(uint32_t v) { uint32_t p = 1; while (p < v) p <<= 1; return p
 // Re-layout of the reference-order flat tree into child-pair records (trb_device.h DPair). Pure layout: no box,
 // child order or primitive order changes. Returns false if a leaf does not fit the 25-bit slot / 5-bit count fields.
 float bits_f(uint32_t u) { float f; std::memcpy(&f, &u, 4); return f; }
+constexpr uint32_t QUAD_EMPTY_HOST = 0xffffffffu;
 bool pack_pairs(const std::vector<trb_bvh_node>& in, std::vector<trb::DPair>& out, trb::DBvh& hdr) {
     std::vector<uint32_t> rec_of(in.size(), 0);
     uint32_t n_rec = 0;
@@ -85,6 +86,65 @@ bool pack_pairs(const std::vector<trb_bvh_node>& in, std::vector<trb::DPair>& ou
     }
     hdr.root_lo = make_float4(in[0].bmin[0], in[0].bmin[1], in[0].bmin[2], bits_f(ref_of(0)));
     hdr.root_hi = make_float4(in[0].bmax[0], in[0].bmax[1], in[0].bmax[2], 0.f);
+    return ok;
+}
+
+// Collapse pairs of levels of the reference-order tree into DQuad records (trb_device.h). Layout only: boxes, child
+// order and primitive order are the reference's. A child whose box is not inside its parent's (cannot happen for boxes
+// built as unions, checked anyway) is kept as a one-slot half so the containment argument never has to be trusted.
+// Returns the root reference in DQuad index space.
+bool pack_quads(const std::vector<trb_bvh_node>& in, std::vector<trb::DQuad>& out, uint32_t& root_ref) {
+    out.clear();
+    bool ok = true;
+    auto is_leaf = [&](uint32_t i) { return (in[i].b & TRB_BVH_LEAF) != 0; };
+    auto leaf_ref = [&](uint32_t i) -> uint32_t {
+        const uint32_t cnt = in[i].b & ~TRB_BVH_LEAF, first = in[i].a;
+        if (cnt > 31 || first >= (1u << 25)) ok = false;
+        return trb::REF_LEAF | (cnt << 25) | first;
+    };
+    auto inside = [&](uint32_t c, uint32_t p) {
+        for (int k = 0; k < 3; ++k) if (!(in[c].bmin[k] >= in[p].bmin[k] && in[c].bmax[k] <= in[p].bmax[k])) return false;
+        return true;
+    };
+    if (in.empty()) { root_ref = QUAD_EMPTY_HOST; return true; }
+    if (is_leaf(0)) { root_ref = leaf_ref(0); return ok; }
+    // quad roots in depth-first order (a record is followed by the records below its first slots: locality for near-first descent)
+    std::vector<uint32_t> quad_of(in.size(), 0xffffffffu), order, todo{0};
+    while (!todo.empty()) {
+        const uint32_t p = todo.back(); todo.pop_back();
+        quad_of[p] = (uint32_t)order.size(); order.push_back(p);
+        uint32_t kids[4]; int nk = 0;
+        for (uint32_t c : {p + 1, in[p].a}) {
+            if (is_leaf(c)) continue;
+            const uint32_t g0 = c + 1, g1 = in[c].a;
+            if (inside(g0, c) && inside(g1, c)) { if (!is_leaf(g0)) kids[nk++] = g0; if (!is_leaf(g1)) kids[nk++] = g1; }
+            else kids[nk++] = c;
+        }
+        for (int k = nk; k-- > 0;) todo.push_back(kids[k]);
+    }
+    if (order.size() >= (1u << 30)) return false;
+    out.resize(order.size());
+    auto slot = [&](trb::DQuad& q, int k, uint32_t node, bool empty) {
+        if (empty) { q.q[2 * k] = make_float4(0.f, 0.f, 0.f, bits_f(0xffffffffu)); q.q[2 * k + 1] = make_float4(0.f, 0.f, 0.f, 0.f); return; }
+        const uint32_t ref = is_leaf(node) ? leaf_ref(node) : (trb::REF_INTERIOR | quad_of[node]);
+        q.q[2 * k] = make_float4(in[node].bmin[0], in[node].bmin[1], in[node].bmin[2], bits_f(ref));
+        q.q[2 * k + 1] = make_float4(in[node].bmax[0], in[node].bmax[1], in[node].bmax[2], 0.f);
+    };
+    for (size_t qi = 0; qi < order.size(); ++qi) {
+        const uint32_t p = order[qi];
+        trb::DQuad& q = out[qi];
+        uint32_t axes[2] = {0, 0};
+        int h = 0;
+        for (uint32_t c : {p + 1, in[p].a}) {
+            bool split = false;
+            if (!is_leaf(c)) { const uint32_t g0 = c + 1, g1 = in[c].a; split = inside(g0, c) && inside(g1, c); }
+            if (split) { slot(q, 2 * h, c + 1, false); slot(q, 2 * h + 1, in[c].a, false); axes[h] = in[c].b & 3u; }
+            else { slot(q, 2 * h, c, false); slot(q, 2 * h + 1, 0, true); }
+            ++h;
+        }
+        q.q[1].w = bits_f((in[p].b & 3u) | axes[0] << 2 | axes[1] << 4);
+    }
+    root_ref = trb::REF_INTERIOR | quad_of[0];
     return ok;
 }
 
@@ -117,6 +177,7 @@ struct trb_scene {
     trb::DScene ds{};
     trb::DInstance* d_instances = nullptr;
     trb::DPair* d_tlas = nullptr;
+    trb::DQuad* d_tlas_quads = nullptr;
     trb::DBvh* d_tlas_hdr = nullptr;
     uint32_t* d_tlas_order = nullptr;
     size_t tlas_capacity = 0;
@@ -296,8 +357,8 @@ trb_status launch_wavefront(trb_scene* s, const trb::RenderParams& rp, uint32_t 
     const unsigned trace_grid = (unsigned)s->sm_count * 12, shade_grid = (unsigned)s->sm_count * 4;
     for (uint32_t round = 0; round < rounds; ++round) {
         const int refill = getenv("TRB_REFILL") ? atoi(getenv("TRB_REFILL")) : 8;
-        static const int occ = getenv("TRB_TRACE_OCC") ? atoi(getenv("TRB_TRACE_OCC")) : 7;
-        static const unsigned tg = getenv("TRB_TRACE_GRID") ? (unsigned)atoi(getenv("TRB_TRACE_GRID")) : 12u;
+        const int occ = getenv("TRB_TRACE_OCC") ? atoi(getenv("TRB_TRACE_OCC")) : 7;
+        const unsigned tg = getenv("TRB_TRACE_GRID") ? (unsigned)atoi(getenv("TRB_TRACE_GRID")) : 12u;
         const unsigned tgrid = (unsigned)s->sm_count * tg;
         std::pair<cudaEvent_t, cudaEvent_t> ev{nullptr, nullptr};
         if (flags & TRB_RENDER_TIME_TRACE) {
@@ -308,13 +369,16 @@ trb_status launch_wavefront(trb_scene* s, const trb::RenderParams& rp, uint32_t 
         static const int sst = getenv("TRB_SMEM_STACK") ? atoi(getenv("TRB_SMEM_STACK")) : 16;
         // TRB_TRACE_SCHED: 0 = flat state machine; else the phase thresholds A | B << 8 | C << 16 (see k_wf_trace)
         const uint32_t sched = getenv("TRB_TRACE_SCHED") ? (uint32_t)strtoul(getenv("TRB_TRACE_SCHED"), nullptr, 0) : (12u | 8u << 8 | 8u << 16); // read per launch: tools/sched_sweep.py
-#define TRB_TRACE_LAUNCH(ST, MB, SS, AN, PH) trb::k_wf_trace<ST, MB, SS, AN, PH><<<tgrid, 128, 0, st>>>(s->ds, rp, wf, round, flags, refill, sched)
-        if (anim) { if (stats) TRB_TRACE_LAUNCH(true, 4, 16, true, true); else TRB_TRACE_LAUNCH(false, 7, 16, true, true); }
-        else if (stats) { if (sched) TRB_TRACE_LAUNCH(true, 4, 16, false, true); else TRB_TRACE_LAUNCH(true, 4, 16, false, false); }
-        else if (sched == 0) { if (occ >= 8) TRB_TRACE_LAUNCH(false, 8, 16, false, false); else if (occ >= 7) TRB_TRACE_LAUNCH(false, 7, 16, false, false); else TRB_TRACE_LAUNCH(false, 6, 16, false, false); }
-        else if (occ >= 8) TRB_TRACE_LAUNCH(false, 8, 16, false, true);
-        else if (occ >= 7) { if (sst <= 8) TRB_TRACE_LAUNCH(false, 7, 8, false, true); else TRB_TRACE_LAUNCH(false, 7, 16, false, true); }
-        else TRB_TRACE_LAUNCH(false, 6, 16, false, true);
+        // TRB_TRACE_QUADS=0: child-pair records only (the STATS variants always use them: their counters are the reference's)
+        const bool quads = !(getenv("TRB_TRACE_QUADS") && atoi(getenv("TRB_TRACE_QUADS")) == 0);
+#define TRB_TRACE_LAUNCH(ST, MB, SS, AN, PH, QD) trb::k_wf_trace<ST, MB, SS, AN, PH, QD><<<tgrid, 128, 0, st>>>(s->ds, rp, wf, round, flags, refill, sched)
+        if (anim) { if (stats) TRB_TRACE_LAUNCH(true, 4, 16, true, true, false); else TRB_TRACE_LAUNCH(false, 7, 16, true, true, true); }
+        else if (stats) { if (sched) TRB_TRACE_LAUNCH(true, 4, 16, false, true, false); else TRB_TRACE_LAUNCH(true, 4, 16, false, false, false); }
+        else if (sched == 0) { if (occ >= 8) TRB_TRACE_LAUNCH(false, 8, 16, false, false, false); else if (occ >= 7) TRB_TRACE_LAUNCH(false, 7, 16, false, false, false); else TRB_TRACE_LAUNCH(false, 6, 16, false, false, false); }
+        else if (!quads) { if (occ >= 8) TRB_TRACE_LAUNCH(false, 8, 16, false, true, false); else if (occ >= 7) TRB_TRACE_LAUNCH(false, 7, 16, false, true, false); else TRB_TRACE_LAUNCH(false, 6, 16, false, true, false); }
+        else if (occ >= 8) TRB_TRACE_LAUNCH(false, 8, 16, false, true, true);
+        else if (occ >= 7) { if (sst <= 8) TRB_TRACE_LAUNCH(false, 7, 8, false, true, true); else TRB_TRACE_LAUNCH(false, 7, 16, false, true, true); }
+        else TRB_TRACE_LAUNCH(false, 6, 16, false, true, true);
 #undef TRB_TRACE_LAUNCH
         if (ev.first) { CU(cudaEventRecord(ev.second, st)); s->trace_events.push_back(ev); }
         if (anim) {
@@ -446,6 +510,13 @@ trb_status trb_scene_create(const trb_scene_desc* d, int device, trb_scene** out
             tris[slot].e0 = make_float4(pb[0] - pa[0], pb[1] - pa[1], pb[2] - pa[2], 0.f);
             tris[slot].e1 = make_float4(pc[0] - pa[0], pc[1] - pa[1], pc[2] - pa[2], 0.f);
         }
+        std::vector<trb::DQuad> qn;
+        uint32_t qroot = 0;
+        if (!pack_quads(hm.nodes, qn, qroot)) return fail(TRB_UNSUPPORTED, "mesh too large for the leaf encoding (2^25 triangles)");
+        hdr.root_hi.w = bits_f(qroot);
+        trb::DQuad* dquads;
+        CU(s->arena.upload(qn.data(), qn.size(), &dquads));
+        hdr.quads = dquads;
         trb::DMesh& dm = dmeshes[mi];
         float *dp, *dn, *dt; uint32_t* di; trb::DPair* dnodes; trb::DTri* dtris;
         CU(s->arena.upload(hm.pos.data(), hm.pos.size(), &dp));
@@ -611,7 +682,12 @@ trb_status trb_scene_update_frame(trb_scene* s, uint32_t frame, float start, flo
     std::vector<trb::DPair> pn;
     trb::DBvh hdr{};
     if (!pack_pairs(s->tlas_nodes, pn, hdr)) return fail(TRB_UNSUPPORTED, "too many instances for the leaf encoding");
+    std::vector<trb::DQuad> qn;
+    uint32_t qroot = 0;
+    if (!pack_quads(s->tlas_nodes, qn, qroot)) return fail(TRB_UNSUPPORTED, "too many instances for the leaf encoding");
+    hdr.root_hi.w = bits_f(qroot);
     if (pn.size() + 1 > s->tlas_capacity) {
+        CU(s->arena.alloc(pn.size() + 1, &s->d_tlas_quads)); // a tree has fewer quad records than pair records
         CU(s->arena.alloc(pn.size() + 1, &s->d_tlas));
         CU(s->arena.alloc(n, &s->d_tlas_order));
         s->tlas_capacity = pn.size() + 1;
@@ -619,10 +695,11 @@ trb_status trb_scene_update_frame(trb_scene* s, uint32_t frame, float start, flo
     if (!pn.empty()) CU(cudaMemcpy(s->d_tlas, pn.data(), pn.size() * sizeof(trb::DPair), cudaMemcpyHostToDevice));
     CU(cudaMemcpy(s->d_tlas_order, s->tlas_order.data(), n * sizeof(uint32_t), cudaMemcpyHostToDevice));
     CU(cudaMemcpy(s->d_instances, di.data(), n * sizeof(trb::DInstance), cudaMemcpyHostToDevice));
-    hdr.pairs = s->d_tlas;
+    if (!qn.empty()) CU(cudaMemcpy(s->d_tlas_quads, qn.data(), qn.size() * sizeof(trb::DQuad), cudaMemcpyHostToDevice));
+    hdr.pairs = s->d_tlas; hdr.quads = s->d_tlas_quads;
     if (!s->d_tlas_hdr) CU(s->arena.alloc(1, &s->d_tlas_hdr));
     CU(cudaMemcpy(s->d_tlas_hdr, &hdr, sizeof hdr, cudaMemcpyHostToDevice));
-    s->ds.tlas = s->d_tlas_hdr; s->ds.tlas_pairs = s->d_tlas; s->ds.tlas_order = s->d_tlas_order;
+    s->ds.tlas = s->d_tlas_hdr; s->ds.tlas_pairs = s->d_tlas; s->ds.tlas_quads = s->d_tlas_quads; s->ds.tlas_order = s->d_tlas_order;
     s->frame_ready = true;
     return TRB_OK;
 }
@@ -852,6 +929,91 @@ trb_status trb_host_keyframe_transform(const trb_keyframe* kf, float* mat16, flo
     if (!kf || !mat16 || !inv16) return fail(TRB_INVALID_ARG, "null argument");
     const Xf x = keyframe_xf(*kf);
     std::memcpy(mat16, x.fwd.m, 64); std::memcpy(inv16, x.inv.m, 64);
+    return TRB_OK;
+}
+
+// Layout check without a GPU: every ray is traversed (a) literally like bvh.rs:81-130 over the reference-order nodes and
+// (b) through the DQuad records with quad_visit — the function the trace kernel runs — and the two must visit the same
+// leaves in the same order with the same max_t history. Leaves "hit" pseudo-randomly (a hash of leaf and ray decides a
+// distance) so that max_t shrinks during the walk. Returns the number of rays whose walks differ.
+trb_status trb_host_quad_check(const trb_bvh_node* nodes, uint32_t n_nodes, const trb_ray* rays, uint32_t n_rays, uint32_t* mismatches,
+                               uint64_t* leaf_visits, uint64_t* quad_visits) {
+    if (!nodes || !rays || !mismatches || n_nodes == 0) return fail(TRB_INVALID_ARG, "null argument");
+    const std::vector<trb_bvh_node> in(nodes, nodes + n_nodes);
+    std::vector<trb::DQuad> quads;
+    uint32_t qroot = 0;
+    if (!pack_quads(in, quads, qroot)) return fail(TRB_UNSUPPORTED, "leaf encoding");
+    uint32_t bad = 0; uint64_t nl = 0, nq = 0;
+    auto leaf_hit = [](uint32_t first, uint32_t ray, float tmin, float& tmax) {
+        uint32_t h = (first * 0x9E3779B1u) ^ (ray * 0x85EBCA77u); h ^= h >> 15; h *= 0x2C1B3C6Du; h ^= h >> 12;
+        if ((h & 3u) == 0) { const float tc = tmin + (float)(h >> 8) * (1.0f / 16777216.0f) * 40.0f; if (tc >= tmin && tc <= tmax) tmax = tc; }
+    };
+    for (uint32_t ri = 0; ri < n_rays; ++ri) {
+        const trb_ray& r = rays[ri];
+        const trb::f3 o = trb::mk(r.o[0], r.o[1], r.o[2]);
+        const trb::f3 inv = trb::mk(1.0f / r.d[0], 1.0f / r.d[1], 1.0f / r.d[2]);
+        const bool nx = r.d[0] < 0.0f, ny = r.d[1] < 0.0f, nz = r.d[2] < 0.0f;
+        const bool neg[3] = {nx, ny, nz};
+        if (!(std::isfinite(inv.x) && std::isfinite(inv.y) && std::isfinite(inv.z))) continue; // these rays take the DPair path
+        // (a) the reference loop
+        std::vector<uint32_t> seq_a, seq_b;
+        float tmax_a = r.max_t, tmax_b = r.max_t;
+        {
+            uint32_t stack[64]; int sp = 0; uint32_t cur = 0;
+            for (;;) {
+                const trb_bvh_node& n = in[cur];
+                float te;
+                const float4 lo = make_float4(n.bmin[0], n.bmin[1], n.bmin[2], 0.f), hi = make_float4(n.bmax[0], n.bmax[1], n.bmax[2], 0.f);
+                if (trb::box_hit(lo, hi, o, inv, nx, ny, nz, r.min_t, tmax_a, te)) {
+                    if (n.b & TRB_BVH_LEAF) {
+                        seq_a.push_back(n.a); leaf_hit(n.a, ri, r.min_t, tmax_a);
+                        if (sp == 0) break;
+                        cur = stack[--sp];
+                    } else {
+                        if (neg[n.b & 3u]) { stack[sp++] = cur + 1; cur = n.a; } else { stack[sp++] = n.a; cur += 1; }
+                    }
+                } else { if (sp == 0) break; cur = stack[--sp]; }
+            }
+        }
+        // (b) root box, then DQuad records with a stack of (entry distance, reference)
+        {
+            const trb_bvh_node& n = in[0];
+            float te;
+            const float4 lo = make_float4(n.bmin[0], n.bmin[1], n.bmin[2], 0.f), hi = make_float4(n.bmax[0], n.bmax[1], n.bmax[2], 0.f);
+            std::vector<unsigned long long> stack;
+            uint32_t cur = trb::box_hit(lo, hi, o, inv, nx, ny, nz, r.min_t, tmax_b, te) ? qroot : 0xffffffffu;
+            for (;;) {
+                if (cur == 0xffffffffu) { // pop
+                    bool got = false;
+                    while (!stack.empty()) {
+                        const unsigned long long e = stack.back(); stack.pop_back();
+                        float tent; const uint32_t tb = (uint32_t)(e >> 32); std::memcpy(&tent, &tb, 4);
+                        if (tent < tmax_b) { cur = (uint32_t)e; got = true; break; }
+                    }
+                    if (!got) break;
+                }
+                if ((cur & trb::REF_TAG) == trb::REF_LEAF) {
+                    const uint32_t first = cur & 0x01ffffffu;
+                    seq_b.push_back(first); leaf_hit(first, ri, r.min_t, tmax_b);
+                    cur = 0xffffffffu;
+                } else {
+                    const float4* q = quads[cur].q;
+                    trb::QuadOut qo;
+                    trb::quad_visit(q[0], q[1], q[2], q[3], q[4], q[5], q[6], q[7], o, inv, nx, ny, nz, r.min_t, tmax_b, qo);
+                    ++nq;
+                    if (qo.p0) stack.push_back(qo.e0);
+                    if (qo.p1) stack.push_back(qo.e1);
+                    if (qo.p2) stack.push_back(qo.e2);
+                    cur = qo.next;
+                }
+            }
+        }
+        nl += seq_a.size();
+        if (seq_a != seq_b || std::memcmp(&tmax_a, &tmax_b, 4) != 0) ++bad;
+    }
+    *mismatches = bad;
+    if (leaf_visits) *leaf_visits = nl;
+    if (quad_visits) *quad_visits = nq;
     return TRB_OK;
 }
 

@@ -26,11 +26,27 @@ struct DPair {
     float4 r_hi; // right max
 };
 constexpr uint32_t REF_TAG = 0xc0000000u, REF_INTERIOR = 0x00000000u, REF_LEAF = 0x40000000u;
+
+// Two levels of the reference tree in one 128-byte record: for an interior node P with children L (= first
+// child) and R (= second_child), the four slots hold the boxes of L's children and R's children (a child that is
+// a leaf occupies one slot with its own box; the other slot of that half is empty). A visit tests four boxes from one
+// fetch, so the dependent-load chain per ray is half as long again. The boxes of L and R themselves are not tested:
+// a child's box lies inside its parent's, and for a ray with finite 1/d every compare of BBox::fast_intersect is
+// monotone in the box, so "grandchild hit" implies "child hit" at the same max_t (rays with a zero direction
+// component use the DPair path). Visit ORDER is the reference's: near half first (P's axis), near slot first
+// inside each half (that child's axis); entries are re-tested against the shrunken max_t when popped.
+//   slot k: q[2k] = (lo.xyz, ref_k), q[2k+1] = (hi.xyz, -)   slots 0,1 = L's half, 2,3 = R's half
+//   q[1].w = axis(P) | axis(L) << 2 | axis(R) << 4          ref = QUAD_EMPTY: unused slot
+struct DQuad { float4 q[8]; };
+constexpr uint32_t QUAD_EMPTY = 0xffffffffu;
+
 struct DBvh {
     const DPair* pairs;
-    float4 root_lo; // root box min, w = root reference
-    float4 root_hi;
+    const DQuad* quads;
+    float4 root_lo; // root box min, w = root reference (DPair index space)
+    float4 root_hi; // root box max, w = root reference (DQuad index space)
 };
+static_assert(sizeof(DBvh) == 48, "DBvh layout");
 
 // One triangle in LEAF ORDER (slot k of the BLAS == ordered_geom[k]), 48 B = three 16-byte loads:
 // v0 = (pa.xyz, triangle index), e0 = pb-pa, e1 = pc-pa (the same single IEEE subtraction the
@@ -90,6 +106,7 @@ struct DStats { // mirrors trb_stats' integer part
 struct DScene {
     const DBvh* tlas;            // BVH<Instance>, max_geom 4 (scene.rs:141); header in global memory like the meshes'
     const DPair* tlas_pairs;     // == tlas->pairs
+    const DQuad* tlas_quads;     // == tlas->quads
     const uint32_t* tlas_order;  // ordered_geom
     const DInstance* instances;
     const DMesh* meshes;

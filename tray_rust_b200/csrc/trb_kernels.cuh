@@ -26,7 +26,7 @@ namespace trb {
 // small vector helpers (componentwise, no FMA)
 // ------------------------------------------------------------------------------------------
 struct f3 { float x, y, z; };
-__device__ __forceinline__ f3 mk(float x, float y, float z) { f3 r; r.x = x; r.y = y; r.z = z; return r; }
+TRB_HD __forceinline__ f3 mk(float x, float y, float z) { f3 r; r.x = x; r.y = y; r.z = z; return r; }
 __device__ __forceinline__ f3 splat(float v) { return mk(v, v, v); }
 __device__ __forceinline__ f3 operator+(f3 a, f3 b) { return mk(a.x + b.x, a.y + b.y, a.z + b.z); }
 __device__ __forceinline__ f3 operator-(f3 a, f3 b) { return mk(a.x - b.x, a.y - b.y, a.z - b.z); }
@@ -81,7 +81,7 @@ struct Cnt { uint32_t node, tri, inst; };
 // BBox::fast_intersect (src/geometry/bbox.rs:75-104), compares transcribed literally so the NaN
 // behaviour is the reference's.
 // ------------------------------------------------------------------------------------------
-__device__ __forceinline__ bool box_hit(const float4 lo, const float4 hi, f3 o, f3 inv, bool nx, bool ny, bool nz, float tmin_r, float tmax_r, float& t_entry) {
+TRB_HD __forceinline__ bool box_hit(const float4 lo, const float4 hi, f3 o, f3 inv, bool nx, bool ny, bool nz, float tmin_r, float tmax_r, float& t_entry) {
     t_entry = 0.0f;
     float tmin = ((nx ? hi.x : lo.x) - o.x) * inv.x;
     float tmax = ((nx ? lo.x : hi.x) - o.x) * inv.x;
@@ -97,6 +97,43 @@ __device__ __forceinline__ bool box_hit(const float4 lo, const float4 hi, f3 o, 
     if (tzmax < tmax) tmax = tzmax;
     t_entry = tmin; // the only quantity a later, smaller max_t can still reject: `tmin < r.max_t` (bbox.rs:103)
     return tmin < tmax_r && tmax > tmin_r;
+}
+
+
+// One visit of a DQuad record (trb_device.h): four box tests, then the reference's visit order. `next` is the first
+// slot hit in that order (QUAD_EMPTY if none); the other hit slots come back farthest-first in e[0..2] so that the
+// caller pushes them in this order and they pop nearest-first. Each entry = entry distance << 32 | reference.
+// Host+device: trb_host_quad_check runs this very function against a literal bvh.rs:81-130 traversal.
+TRB_HD __forceinline__ uint32_t f32_bits(float f) {
+#ifdef __CUDA_ARCH__
+    return __float_as_uint(f);
+#else
+    uint32_t u; memcpy(&u, &f, 4); return u;
+#endif
+}
+struct QuadOut { uint32_t next; unsigned long long e0, e1, e2; bool p0, p1, p2; };
+TRB_HD __forceinline__ void quad_visit(const float4 q0, const float4 q1, const float4 q2, const float4 q3, const float4 q4, const float4 q5, const float4 q6,
+                                       const float4 q7, f3 o, f3 inv, bool nx, bool ny, bool nz, float tmin, float tmax, QuadOut& out) {
+    const uint32_t r0 = f32_bits(q0.w), r1 = f32_bits(q2.w), r2 = f32_bits(q4.w), r3 = f32_bits(q6.w), meta = f32_bits(q1.w);
+    float t0, t1, t2, t3;
+    const bool h0 = box_hit(q0, q1, o, inv, nx, ny, nz, tmin, tmax, t0) && r0 != QUAD_EMPTY;
+    const bool h1 = box_hit(q2, q3, o, inv, nx, ny, nz, tmin, tmax, t1) && r1 != QUAD_EMPTY;
+    const bool h2 = box_hit(q4, q5, o, inv, nx, ny, nz, tmin, tmax, t2) && r2 != QUAD_EMPTY;
+    const bool h3 = box_hit(q6, q7, o, inv, nx, ny, nz, tmin, tmax, t3) && r3 != QUAD_EMPTY;
+    const uint32_t ap = meta & 3u, al = (meta >> 2) & 3u, ar = (meta >> 4) & 3u;
+    const bool negp = ap == 0 ? nx : (ap == 1 ? ny : nz), negl = al == 0 ? nx : (al == 1 ? ny : nz), negr = ar == 0 ? nx : (ar == 1 ? ny : nz);
+    // each half in its own near-first order (an empty slot never hits, so its position does not matter)
+    const bool hla = negl ? h1 : h0, hlb = negl ? h0 : h1, hra = negr ? h3 : h2, hrb = negr ? h2 : h3;
+    const uint32_t rla = negl ? r1 : r0, rlb = negl ? r0 : r1, rra = negr ? r3 : r2, rrb = negr ? r2 : r3;
+    const float tla = negl ? t1 : t0, tlb = negl ? t0 : t1, tra = negr ? t3 : t2, trb_ = negr ? t2 : t3;
+    // halves in P's near-first order
+    const bool a0 = negp ? hra : hla, a1 = negp ? hrb : hlb, a2 = negp ? hla : hra, a3 = negp ? hlb : hrb;
+    const uint32_t s0 = negp ? rra : rla, s1 = negp ? rrb : rlb, s2 = negp ? rla : rra, s3 = negp ? rlb : rrb;
+    const float u1 = negp ? trb_ : tlb, u2 = negp ? tla : tra, u3 = negp ? tlb : trb_;
+    out.next = a0 ? s0 : (a1 ? s1 : (a2 ? s2 : (a3 ? s3 : QUAD_EMPTY)));
+    out.p0 = a3 && (a0 || a1 || a2); out.e0 = ((unsigned long long)f32_bits(u3) << 32) | s3;
+    out.p1 = a2 && (a0 || a1);       out.e1 = ((unsigned long long)f32_bits(u2) << 32) | s2;
+    out.p2 = a1 && a0;               out.e2 = ((unsigned long long)f32_bits(u1) << 32) | s1;
 }
 
 // solve_quadratic (src/linalg/mod.rs:78-94)
@@ -205,7 +242,9 @@ struct TraceState {
     f3 o, d, inv;         // ray of the current level (world, or the mesh instance's object space)
     bool nx, ny, nz;      // d < 0 per axis (bvh.rs:85)
     const DBvh* bvh;      // current level (root box + reference)
-    const DPair* pairs;   // current level's records, kept in registers: no pointer chase per step
+    const DPair* pairs;   // current level's records, kept in registers: no pointer chase per step (DQuad records when `quad`)
+    bool quad;            // this level is traversed through the DQuad records (finite 1/d only, see trb_device.h)
+    bool quads_ok;        // the kernel variant may use DQuad records at all
     const DTri* tris;
     uint32_t level_inst;  // instance whose mesh is being traversed, TRB_MISS at the top level
     float tmin, tmax;
@@ -216,13 +255,20 @@ struct TraceState {
     uint32_t h_inst, h_prim;
     float h_b1, h_b2;
 };
-__device__ __forceinline__ void trace_init(const DScene& sc, TraceState& t, const Ray& ray, bool any_hit, float time) {
-    t.time = time;
+__device__ __forceinline__ bool finite3(f3 v) { return fabsf(v.x) < finf() && fabsf(v.y) < finf() && fabsf(v.z) < finf(); }
+__device__ __forceinline__ void trace_level(TraceState& t, const DBvh* bvh, const DPair* pairs, const DQuad* quads) {
+    t.bvh = bvh;
+    t.quad = t.quads_ok && finite3(t.inv);
+    t.pairs = t.quad ? reinterpret_cast<const DPair*>(quads) : pairs;
+}
+__device__ __forceinline__ void trace_init(const DScene& sc, TraceState& t, const Ray& ray, bool any_hit, float time, bool quads_ok = false) {
+    t.time = time; t.quads_ok = quads_ok;
     t.wo = ray.o; t.wd = ray.d;
     t.winv = mk(1.0f / ray.d.x, 1.0f / ray.d.y, 1.0f / ray.d.z);
     t.o = t.wo; t.d = t.wd; t.inv = t.winv;
     t.nx = t.d.x < 0.0f; t.ny = t.d.y < 0.0f; t.nz = t.d.z < 0.0f;
-    t.bvh = sc.tlas; t.pairs = sc.tlas_pairs; t.tris = nullptr; t.level_inst = TRB_MISS;
+    trace_level(t, sc.tlas, sc.tlas_pairs, sc.tlas_quads);
+    t.tris = nullptr; t.level_inst = TRB_MISS;
     t.tmin = ray.tmin; t.tmax = ray.tmax;
     t.sp = 0; t.cur = ST_ROOT; t.found = false; t.any_hit = any_hit;
     t.h_inst = TRB_MISS; t.h_prim = 0; t.h_b1 = 0.0f; t.h_b2 = 0.0f;
@@ -382,10 +428,33 @@ __device__ __forceinline__ int trace_class(const TraceState& t) {
     if (tag == REF_LEAF && t.level_inst != TRB_MISS) return 2;
     return 3;
 }
-template <bool STATS, class Stack>
-__device__ __forceinline__ void step_nodes(TraceState& t, const Stack& stack, Cnt& cnt, int* err) {
+__device__ __forceinline__ void prefetch_l1(const void* p) { asm volatile("prefetch.global.L1 [%0];" ::"l"(p)); }
+template <bool STATS, bool QUADS, class Stack>
+__device__ __forceinline__ void step_nodes(TraceState& t, const Stack& stack, Cnt& cnt, int* err, bool prefetch) {
     uint32_t cur = t.cur;
-    if (cur != ST_POP) {
+    if (QUADS && cur != ST_POP && t.quad) {
+        const float4* __restrict__ rec = reinterpret_cast<const DQuad*>(t.pairs)[cur].q;
+        const float4 q0 = __ldg(rec), q1 = __ldg(rec + 1), q2 = __ldg(rec + 2), q3 = __ldg(rec + 3), q4 = __ldg(rec + 4), q5 = __ldg(rec + 5),
+                     q6 = __ldg(rec + 6), q7 = __ldg(rec + 7);
+        QuadOut qo;
+        quad_visit(q0, q1, q2, q3, q4, q5, q6, q7, t.o, t.inv, t.nx, t.ny, t.nz, t.tmin, t.tmax, qo);
+        cur = qo.next == QUAD_EMPTY ? ST_POP : qo.next;
+        if (qo.p2) { // at least one more slot was hit
+            if (t.sp >= STACK_DEPTH - 6) { *err = 1; t.sp = 0; cur = ST_DONE; }
+            else {
+                if (qo.p0) stack.put(t.sp++, qo.e0);
+                if (qo.p1) stack.put(t.sp++, qo.e1);
+                stack.put(t.sp++, qo.e2);
+                if (prefetch && ((uint32_t)qo.e2 & REF_TAG) == REF_INTERIOR) prefetch_l1(reinterpret_cast<const DQuad*>(t.pairs) + (uint32_t)qo.e2);
+            }
+        } else if (qo.p0 || qo.p1) {
+            if (t.sp >= STACK_DEPTH - 6) { *err = 1; t.sp = 0; cur = ST_DONE; }
+            else {
+                if (qo.p0) stack.put(t.sp++, qo.e0);
+                if (qo.p1) stack.put(t.sp++, qo.e1);
+            }
+        }
+    } else if (cur != ST_POP) {
         const DPair* __restrict__ rec = t.pairs + cur;
         const float4 l_lo = __ldg(&rec->l_lo), l_hi = __ldg(&rec->l_hi), r_lo = __ldg(&rec->r_lo), r_hi = __ldg(&rec->r_hi);
         if (STATS) cnt.node += 2;
@@ -401,7 +470,10 @@ __device__ __forceinline__ void step_nodes(TraceState& t, const Stack& stack, Cn
         cur = h_near ? ref_near : (h_far ? ref_far : ST_POP);
         if (h_near && h_far) {
             if (t.sp >= STACK_DEPTH - 6) { *err = 1; t.sp = 0; cur = ST_DONE; }
-            else stack.put(t.sp++, ((unsigned long long)__float_as_uint(t_far) << 32) | ref_far);
+            else {
+                stack.put(t.sp++, ((unsigned long long)__float_as_uint(t_far) << 32) | ref_far);
+                if (prefetch && (ref_far & REF_TAG) == REF_INTERIOR) prefetch_l1(t.pairs + ref_far);
+            }
         }
     }
 #pragma unroll
@@ -456,11 +528,12 @@ __device__ __forceinline__ void step_other(const DScene& sc, TraceState& t, cons
         const float4 lo = __ldg(&t.bvh->root_lo), hi = __ldg(&t.bvh->root_hi);
         if (STATS) cnt.node++;
         float te;
-        if (box_hit(lo, hi, t.o, t.inv, t.nx, t.ny, t.nz, t.tmin, t.tmax, te)) next = __float_as_uint(lo.w);
+        if (box_hit(lo, hi, t.o, t.inv, t.nx, t.ny, t.nz, t.tmin, t.tmax, te)) next = __float_as_uint(t.quad ? hi.w : lo.w);
     } else if (cur == ST_RETURN) {
         t.o = t.wo; t.d = t.wd; t.inv = t.winv;
         t.nx = t.d.x < 0.0f; t.ny = t.d.y < 0.0f; t.nz = t.d.z < 0.0f;
-        t.bvh = sc.tlas; t.pairs = sc.tlas_pairs; t.level_inst = TRB_MISS;
+        trace_level(t, sc.tlas, sc.tlas_pairs, sc.tlas_quads);
+        t.level_inst = TRB_MISS;
     } else { // Instance::intersect for one entry of a TLAS leaf
         const uint32_t ii = __ldg(&sc.tlas_order[cur & ~REF_TAG]);
         const DInstance& in = sc.instances[ii];
@@ -475,7 +548,8 @@ __device__ __forceinline__ void step_other(const DScene& sc, TraceState& t, cons
                 t.o = lo_; t.d = ld_;
                 t.inv = mk(1.0f / ld_.x, 1.0f / ld_.y, 1.0f / ld_.z);
                 t.nx = ld_.x < 0.0f; t.ny = ld_.y < 0.0f; t.nz = ld_.z < 0.0f;
-                t.bvh = &me.bvh; t.pairs = me.bvh.pairs; t.tris = me.tris; t.level_inst = ii;
+                trace_level(t, &me.bvh, me.bvh.pairs, me.bvh.quads);
+                t.tris = me.tris; t.level_inst = ii;
                 stack.put(t.sp++, ST_RETURN);
                 next = ST_ROOT;
             } else {
@@ -1464,7 +1538,7 @@ __global__ void __launch_bounds__(256) k_wf_generate(const __grid_constant__ DSc
 // PHASED: each iteration the warp runs only the micro-step classes (A nodes / B triangle / C other) that enough of its
 // lanes are waiting for (thresholds in `sched`: A | B << 8 | C << 16; if no class reaches its threshold, the fullest one
 // runs), so triangle tests and instance entries execute with many lanes instead of the two or three that happen to be there.
-template <bool STATS, int MINB, int SMEM_STACK, bool ANIM, bool PHASED>
+template <bool STATS, int MINB, int SMEM_STACK, bool ANIM, bool PHASED, bool QUADS>
 __global__ void __launch_bounds__(128, MINB) k_wf_trace(const __grid_constant__ DScene sc, const __grid_constant__ RenderParams rp, const __grid_constant__ WfState wf,
                                                          uint32_t round, uint32_t flags, int WF_REFILL_IDLE, uint32_t sched) {
     uint32_t* cnt_r = wf.counters + round * WF_CNT;
@@ -1517,7 +1591,7 @@ __global__ void __launch_bounds__(128, MINB) k_wf_trace(const __grid_constant__ 
                     Ray ray; ray.o = mk(o4.x, o4.y, o4.z); ray.d = mk(d4.x, d4.y, d4.z);
                     ray.tmin = (type == 0 && round == 0) ? 0.0f : 0.001f;
                     ray.tmax = type == 1 ? 0.999f : finf();
-                    trace_init(sc, t, ray, type == 1 && shadow_any, ANIM ? __ldg(&wf.thr[p].w) : 0.0f);
+                    trace_init(sc, t, ray, type == 1 && shadow_any, ANIM ? __ldg(&wf.thr[p].w) : 0.0f, QUADS && PHASED);
                     have = true;
                 }
             }
@@ -1527,6 +1601,7 @@ __global__ void __launch_bounds__(128, MINB) k_wf_trace(const __grid_constant__ 
         // ---- traverse until enough lanes have finished ----
         if (PHASED) {
             const int thr_a = (int)(sched & 255u), thr_b = (int)((sched >> 8) & 255u), thr_c = (int)((sched >> 16) & 255u);
+            const bool prefetch = (sched >> 24) & 1u; // experiment: warm L1 with the record of the entry just pushed
             for (;;) {
                 const int cls = have ? trace_class(t) : 0;
                 const unsigned m_a = __ballot_sync(0xffffffffu, cls == 1), m_b = __ballot_sync(0xffffffffu, cls == 2), m_c = __ballot_sync(0xffffffffu, cls == 3);
@@ -1539,7 +1614,7 @@ __global__ void __launch_bounds__(128, MINB) k_wf_trace(const __grid_constant__ 
                 }
                 if (do_c && cls == 3) step_other<STATS, ANIM>(sc, t, stack, cnt);
                 if (do_b && cls == 2) step_triangle<STATS>(t, cnt);
-                if (do_a && cls == 1) step_nodes<STATS>(t, stack, cnt, rp.error_flag);
+                if (do_a && cls == 1) step_nodes<STATS, QUADS>(t, stack, cnt, rp.error_flag, prefetch);
             }
         } else {
             for (;;) {
