@@ -509,6 +509,7 @@ trb_status trb_scene_create(const trb_scene_desc* d, int device, trb_scene** out
             tris[slot].v0 = make_float4(pa[0], pa[1], pa[2], tid);
             tris[slot].e0 = make_float4(pb[0] - pa[0], pb[1] - pa[1], pb[2] - pa[2], 0.f);
             tris[slot].e1 = make_float4(pc[0] - pa[0], pc[1] - pa[1], pc[2] - pa[2], 0.f);
+            tris[slot].pad = make_float4(0.f, 0.f, 0.f, 0.f);
         }
         std::vector<trb::DQuad> qn;
         uint32_t qroot = 0;

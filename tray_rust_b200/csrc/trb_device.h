@@ -48,10 +48,12 @@ struct DBvh {
 };
 static_assert(sizeof(DBvh) == 48, "DBvh layout");
 
-// One triangle in LEAF ORDER (slot k of the BLAS == ordered_geom[k]), 48 B = three 16-byte loads:
+// One triangle in LEAF ORDER (slot k of the BLAS == ordered_geom[k]), padded to 64 B so that it is two aligned
+// 32-byte loads (one L1TEX tag lookup each) and never straddles a 128-byte line:
 // v0 = (pa.xyz, triangle index), e0 = pb-pa, e1 = pc-pa (the same single IEEE subtraction the
 // reference performs per test, mesh.rs:140, hoisted to load time).
-struct DTri { float4 v0, e0, e1; };
+struct alignas(64) DTri { float4 v0, e0, e1, pad; };
+static_assert(sizeof(DTri) == 64, "DTri layout");
 
 struct DMesh {
     const float* positions; // 3 per vertex

@@ -73,6 +73,17 @@ __device__ __forceinline__ void coord_system(f3 e1, f3& e2, f3& e3) {
     e3 = cross3(e1, e2);
 }
 
+// 256-bit read-only global load (LDG.E.256, sm_100): the trace kernel is bound by L1TEX wavefronts — every lane reads a
+// different node record, so each load instruction costs one tag lookup per lane; 32-byte loads halve the lookups per record.
+__device__ __forceinline__ void ldg256(const void* p, float4& a, float4& b) {
+    float x0, x1, x2, x3, x4, x5, x6, x7;
+    asm volatile("ld.global.nc.v8.f32 {%0,%1,%2,%3,%4,%5,%6,%7}, [%8];"
+                 : "=f"(x0), "=f"(x1), "=f"(x2), "=f"(x3), "=f"(x4), "=f"(x5), "=f"(x6), "=f"(x7)
+                 : "l"(p));
+    a = make_float4(x0, x1, x2, x3);
+    b = make_float4(x4, x5, x6, x7);
+}
+
 struct Ray { f3 o, d; float tmin, tmax; };
 struct HitRec { float t; uint32_t inst, prim; float b1, b2; };
 struct Cnt { uint32_t node, tri, inst; };
@@ -434,8 +445,8 @@ __device__ __forceinline__ void step_nodes(TraceState& t, const Stack& stack, Cn
     uint32_t cur = t.cur;
     if (QUADS && cur != ST_POP && t.quad) {
         const float4* __restrict__ rec = reinterpret_cast<const DQuad*>(t.pairs)[cur].q;
-        const float4 q0 = __ldg(rec), q1 = __ldg(rec + 1), q2 = __ldg(rec + 2), q3 = __ldg(rec + 3), q4 = __ldg(rec + 4), q5 = __ldg(rec + 5),
-                     q6 = __ldg(rec + 6), q7 = __ldg(rec + 7);
+        float4 q0, q1, q2, q3, q4, q5, q6, q7;
+        ldg256(rec, q0, q1); ldg256(rec + 2, q2, q3); ldg256(rec + 4, q4, q5); ldg256(rec + 6, q6, q7);
         QuadOut qo;
         quad_visit(q0, q1, q2, q3, q4, q5, q6, q7, t.o, t.inv, t.nx, t.ny, t.nz, t.tmin, t.tmax, qo);
         cur = qo.next == QUAD_EMPTY ? ST_POP : qo.next;
@@ -456,7 +467,9 @@ __device__ __forceinline__ void step_nodes(TraceState& t, const Stack& stack, Cn
         }
     } else if (cur != ST_POP) {
         const DPair* __restrict__ rec = t.pairs + cur;
-        const float4 l_lo = __ldg(&rec->l_lo), l_hi = __ldg(&rec->l_hi), r_lo = __ldg(&rec->r_lo), r_hi = __ldg(&rec->r_hi);
+        float4 l_lo, l_hi, r_lo, r_hi;
+        ldg256(&rec->l_lo, l_lo, l_hi);
+        ldg256(&rec->r_lo, r_lo, r_hi);
         if (STATS) cnt.node += 2;
         float tl, tr;
         const bool hl = box_hit(l_lo, l_hi, t.o, t.inv, t.nx, t.ny, t.nz, t.tmin, t.tmax, tl);
@@ -496,7 +509,9 @@ __device__ __forceinline__ void step_triangle(TraceState& t, Cnt& cnt) {
     uint32_t next = n > 1 ? (REF_LEAF | ((n - 1) << 25) | (a + 1)) : ST_POP;
     if (n != 0) {
         const DTri* __restrict__ tri = t.tris + a;
-        const float4 v0 = __ldg(&tri->v0), q0 = __ldg(&tri->e0), q1 = __ldg(&tri->e1);
+        float4 v0, q0, q1, qpad;
+        ldg256(&tri->v0, v0, q0);
+        ldg256(&tri->e1, q1, qpad);
         if (STATS) cnt.tri++;
         const f3 e0 = mk(q0.x, q0.y, q0.z), e1 = mk(q1.x, q1.y, q1.z);
         const f3 s0 = cross3(t.d, e1);
