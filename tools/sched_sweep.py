@@ -45,16 +45,16 @@ def measure(g, sched, refill=8, flags=0, quads=1, occ=7):
     return float(s[1:5].sum()) / ms / 1e3, ms / STEPS
 
 
-def sched(a, b, c, pf=0):
-    return a | b << 8 | c << 16 | pf << 24
+def sched(quorum, burst):
+    return quorum | burst << 8
 
 
 # (name, sched word, refill, quads, occ)
-CASES = [("flat pairs", 0, 8, 0, 7), ("phased pairs", sched(12, 4, 4), 8, 0, 7), ("phased pairs +pf", sched(12, 4, 4, 1), 8, 0, 7)]
-for occ in (7, 6, 8):
-    for (a, b, c) in [(12, 4, 4), (12, 8, 8), (1, 4, 4), (8, 4, 4)]:
-        CASES.append(("quads A%d B%d C%d occ%d" % (a, b, c, occ), sched(a, b, c), 8, 1, occ))
-CASES += [("quads +pf occ7", sched(12, 4, 4, 1), 8, 1, 7), ("quads r4", sched(12, 4, 4), 4, 1, 7), ("quads r12", sched(12, 4, 4), 12, 1, 7)]
+CASES = [("flat pairs", 0, 8, 0, 7)]
+for q, b in [(4, 1), (4, 2), (4, 3), (4, 4), (8, 2), (2, 2), (6, 2), (12, 2), (8, 4), (4, 8)]:
+    CASES.append(("pairs quorum%d burst%d" % (q, b), sched(q, b), 8, 0, 7))
+CASES += [("quads q4 b1", sched(4, 1), 8, 1, 7), ("quads q4 b2", sched(4, 2), 8, 1, 7), ("pairs q4 b2 r6", sched(4, 2), 6, 0, 7), ("pairs q4 b2 r12", sched(4, 2), 12, 0, 7),
+          ("pairs q4 b2 occ6", sched(4, 2), 8, 0, 6), ("pairs q4 b2 occ8", sched(4, 2), 8, 0, 8)]
 if __name__ == "__main__":
     full, direct = scene(False), scene(True)
     for name, sc, r, q, occ in CASES:

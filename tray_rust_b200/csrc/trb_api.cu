@@ -367,10 +367,10 @@ trb_status launch_wavefront(trb_scene* s, const trb::RenderParams& rp, uint32_t 
             CU(cudaEventRecord(ev.first, st));
         }
         static const int sst = getenv("TRB_SMEM_STACK") ? atoi(getenv("TRB_SMEM_STACK")) : 16;
-        // TRB_TRACE_SCHED: 0 = flat state machine; else the phase thresholds A | B << 8 | C << 16 (see k_wf_trace)
-        const uint32_t sched = getenv("TRB_TRACE_SCHED") ? (uint32_t)strtoul(getenv("TRB_TRACE_SCHED"), nullptr, 0) : (12u | 8u << 8 | 8u << 16); // read per launch: tools/sched_sweep.py
-        // TRB_TRACE_QUADS=0: child-pair records only (the STATS variants always use them: their counters are the reference's)
-        const bool quads = !(getenv("TRB_TRACE_QUADS") && atoi(getenv("TRB_TRACE_QUADS")) == 0);
+        // TRB_TRACE_SCHED: 0 = flat state machine; else quorum | burst << 8 (see k_wf_trace)
+        const uint32_t sched = getenv("TRB_TRACE_SCHED") ? (uint32_t)strtoul(getenv("TRB_TRACE_SCHED"), nullptr, 0) : (4u | 2u << 8); // read per launch: tools/sched_sweep.py
+        // TRB_TRACE_QUADS=1: two-level DQuad records instead of child-pair records (never in the STATS variants: their counters are the reference's)
+        const bool quads = getenv("TRB_TRACE_QUADS") && atoi(getenv("TRB_TRACE_QUADS")) != 0; // measured 3-6 % slower than pairs on C4: off by default
 #define TRB_TRACE_LAUNCH(ST, MB, SS, AN, PH, QD) trb::k_wf_trace<ST, MB, SS, AN, PH, QD><<<tgrid, 128, 0, st>>>(s->ds, rp, wf, round, flags, refill, sched)
         if (anim) { if (stats) TRB_TRACE_LAUNCH(true, 4, 16, true, true, false); else TRB_TRACE_LAUNCH(false, 7, 16, true, true, true); }
         else if (stats) { if (sched) TRB_TRACE_LAUNCH(true, 4, 16, false, true, false); else TRB_TRACE_LAUNCH(true, 4, 16, false, false, false); }

@@ -431,6 +431,7 @@ __device__ __forceinline__ void trace_step(const DScene& sc, TraceState& t, cons
 // state: ncu showed the triangle code running with 2.2 of 32 lanes and the pop loop with 4.
 // ------------------------------------------------------------------------------------------
 constexpr uint32_t ST_POP = 0xfffffffcu; // control: take the next reference off the stack
+__device__ __forceinline__ bool trace_is_node(uint32_t cur) { return (cur & REF_TAG) == REF_INTERIOR || cur == ST_POP; }
 __device__ __forceinline__ int trace_class(const TraceState& t) {
     const uint32_t cur = t.cur;
     if (cur == ST_DONE) return 0;
@@ -439,9 +440,8 @@ __device__ __forceinline__ int trace_class(const TraceState& t) {
     if (tag == REF_LEAF && t.level_inst != TRB_MISS) return 2;
     return 3;
 }
-__device__ __forceinline__ void prefetch_l1(const void* p) { asm volatile("prefetch.global.L1 [%0];" ::"l"(p)); }
 template <bool STATS, bool QUADS, class Stack>
-__device__ __forceinline__ void step_nodes(TraceState& t, const Stack& stack, Cnt& cnt, int* err, bool prefetch) {
+__device__ __forceinline__ void step_nodes(TraceState& t, const Stack& stack, Cnt& cnt, int* err) {
     uint32_t cur = t.cur;
     if (QUADS && cur != ST_POP && t.quad) {
         const float4* __restrict__ rec = reinterpret_cast<const DQuad*>(t.pairs)[cur].q;
@@ -456,7 +456,6 @@ __device__ __forceinline__ void step_nodes(TraceState& t, const Stack& stack, Cn
                 if (qo.p0) stack.put(t.sp++, qo.e0);
                 if (qo.p1) stack.put(t.sp++, qo.e1);
                 stack.put(t.sp++, qo.e2);
-                if (prefetch && ((uint32_t)qo.e2 & REF_TAG) == REF_INTERIOR) prefetch_l1(reinterpret_cast<const DQuad*>(t.pairs) + (uint32_t)qo.e2);
             }
         } else if (qo.p0 || qo.p1) {
             if (t.sp >= STACK_DEPTH - 6) { *err = 1; t.sp = 0; cur = ST_DONE; }
@@ -483,10 +482,7 @@ __device__ __forceinline__ void step_nodes(TraceState& t, const Stack& stack, Cn
         cur = h_near ? ref_near : (h_far ? ref_far : ST_POP);
         if (h_near && h_far) {
             if (t.sp >= STACK_DEPTH - 6) { *err = 1; t.sp = 0; cur = ST_DONE; }
-            else {
-                stack.put(t.sp++, ((unsigned long long)__float_as_uint(t_far) << 32) | ref_far);
-                if (prefetch && (ref_far & REF_TAG) == REF_INTERIOR) prefetch_l1(t.pairs + ref_far);
-            }
+            else stack.put(t.sp++, ((unsigned long long)__float_as_uint(t_far) << 32) | ref_far);
         }
     }
 #pragma unroll
@@ -1550,9 +1546,10 @@ __global__ void __launch_bounds__(256) k_wf_generate(const __grid_constant__ DSc
 // fetch new rays with one warp-aggregated atomic, so rays of very different lengths (an any-hit shadow
 // ray vs. a continuation ray crossing the whole mesh) do not leave the warp mostly empty.
 //
-// PHASED: each iteration the warp runs only the micro-step classes (A nodes / B triangle / C other) that enough of its
-// lanes are waiting for (thresholds in `sched`: A | B << 8 | C << 16; if no class reaches its threshold, the fullest one
-// runs), so triangle tests and instance entries execute with many lanes instead of the two or three that happen to be there.
+// PHASED: the warp alternates bursts of node micro-steps with one non-node micro-step (triangle / root / instance /
+// return) that runs only once enough lanes are waiting for one (or no lane has node work left), so triangle tests and
+// instance entries execute with several lanes instead of the two that happen to be there, and the scheduling
+// ballots are paid once per burst.
 template <bool STATS, int MINB, int SMEM_STACK, bool ANIM, bool PHASED, bool QUADS>
 __global__ void __launch_bounds__(128, MINB) k_wf_trace(const __grid_constant__ DScene sc, const __grid_constant__ RenderParams rp, const __grid_constant__ WfState wf,
                                                          uint32_t round, uint32_t flags, int WF_REFILL_IDLE, uint32_t sched) {
@@ -1615,21 +1612,22 @@ __global__ void __launch_bounds__(128, MINB) k_wf_trace(const __grid_constant__ 
         if (busy0 == 0) { if (exhausted) break; else continue; }
         // ---- traverse until enough lanes have finished ----
         if (PHASED) {
-            const int thr_a = (int)(sched & 255u), thr_b = (int)((sched >> 8) & 255u), thr_c = (int)((sched >> 16) & 255u);
-            const bool prefetch = (sched >> 24) & 1u; // experiment: warm L1 with the record of the entry just pushed
+            // `sched`: bits 0-7 quorum of lanes waiting for a non-node micro-step (triangle / root / instance / return),
+            //          bits 8-15 node micro-steps per scheduling decision. An idle lane has cur == ST_DONE.
+            const int thr_o = (int)(sched & 255u), burst = (int)((sched >> 8) & 255u);
             for (;;) {
-                const int cls = have ? trace_class(t) : 0;
-                const unsigned m_a = __ballot_sync(0xffffffffu, cls == 1), m_b = __ballot_sync(0xffffffffu, cls == 2), m_c = __ballot_sync(0xffffffffu, cls == 3);
-                const int n_a = __popc(m_a), n_b = __popc(m_b), n_c = __popc(m_c);
-                if ((m_a | m_b | m_c) == 0) break;
-                if (!exhausted && 32 - (n_a + n_b + n_c) >= WF_REFILL_IDLE) break;
-                bool do_a = n_a >= thr_a, do_b = n_b >= thr_b, do_c = n_c >= thr_c;
-                if (!(do_a || do_b || do_c)) { // nobody reached a quorum: run the fullest class
-                    if (n_a >= n_b && n_a >= n_c) do_a = true; else if (n_b >= n_c) do_b = true; else do_c = true;
+                for (int k = 0; k < burst; ++k)
+                    if (trace_is_node(t.cur)) step_nodes<STATS, QUADS>(t, stack, cnt, rp.error_flag);
+                const bool is_a = trace_is_node(t.cur), is_o = !is_a && t.cur != ST_DONE;
+                const unsigned m_a = __ballot_sync(0xffffffffu, is_a), m_o = __ballot_sync(0xffffffffu, is_o);
+                if ((m_a | m_o) == 0) break;
+                if (!exhausted && 32 - __popc(m_a | m_o) >= WF_REFILL_IDLE) break;
+                if (m_o != 0 && (m_a == 0 || __popc(m_o) >= thr_o)) {
+                    if (is_o) {
+                        if ((t.cur & REF_TAG) == REF_LEAF && t.level_inst != TRB_MISS) step_triangle<STATS>(t, cnt);
+                        else step_other<STATS, ANIM>(sc, t, stack, cnt);
+                    }
                 }
-                if (do_c && cls == 3) step_other<STATS, ANIM>(sc, t, stack, cnt);
-                if (do_b && cls == 2) step_triangle<STATS>(t, cnt);
-                if (do_a && cls == 1) step_nodes<STATS, QUADS>(t, stack, cnt, rp.error_flag, prefetch);
             }
         } else {
             for (;;) {
