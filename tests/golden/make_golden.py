@@ -31,13 +31,34 @@ def golden_scenes():
         d = C.POINTER(F.SceneDesc)()
         assert lib.trb_desc_load_json(os.path.join(HERE, "scenes", "c2_smallpt.json").encode(), 16, 16, 4, C.byref(d)) == 0
         return d.contents
-    return {"zoo": (zoo, dict(seed=11)), "c4_5k": (c4, dict(seed=12)), "c1_cornell": (cornell, dict(seed=13)), "c2_smallpt": (smallpt, dict(seed=14))}
+    def anim():
+        return SB.scene_animated(24, 16, 4, frames=4, scene_time=1.0).finish()
+
+    def tr15_like():
+        import make_scenes
+        merl = os.path.join(HERE, "scenes", "merl", "synthetic.binary")
+        if not os.path.exists(merl):
+            make_scenes.write_synthetic_merl(merl)
+        lib = F.load_trb()
+        d = C.POINTER(F.SceneDesc)()
+        assert lib.trb_desc_load_json(os.path.join(HERE, "scenes", "c5_tr15_like.json").encode(), 24, 16, 4, C.byref(d)) == 0
+        return d.contents
+    return {"zoo": (zoo, dict(seed=11)), "c4_5k": (c4, dict(seed=12)), "c1_cornell": (cornell, dict(seed=13)), "c2_smallpt": (smallpt, dict(seed=14)),
+            "anim_f2": (anim, dict(seed=15)), "c5_tr15_like_f12": (tr15_like, dict(seed=16))}
+
+
+# Scene::update_frame arguments (frame, start, end) the vectors were made with; (0, 0, 0) unless listed
+FRAMES = {"anim_f2": (2, 0.5, 0.75), "c5_tr15_like_f12": (12, 6.0, 6.5)}
+
+
+def frame_of(name):
+    return FRAMES.get(name, (0, 0.0, 0.0))
 
 
 if __name__ == "__main__":
     for name, (mk, kw) in golden_scenes().items():
         o = api.OracleScene(mk())
-        o.update_frame(0, 0.0, 0.0)
+        o.update_frame(*frame_of(name))
         rays, xy = o.camera_rays(**kw)
         hits, hst = o.intersect(rays)
         samples, st = o.render_samples(**kw)

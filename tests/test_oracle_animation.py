@@ -165,3 +165,56 @@ def test_product_host_animated_color(trb):
     assert np.array_equal(col(2.0), (0, 0, 5))                                               # after the last key: last colour
     assert np.allclose(col(0.5), (5, 10, 0), atol=1e-5)                                      # lerp between the bracketing keys
     assert np.allclose(col(0.825), (0, 10, 2.5), atol=1e-4)
+
+
+def _tr15_like_desc(trb, w=48, h=32, spp=2):
+    import ctypes as C
+    import os
+    import sys
+    here = os.path.dirname(os.path.abspath(__file__))
+    sys.path.insert(0, os.path.join(here, "golden"))
+    import make_scenes
+    merl = os.path.join(here, "golden", "scenes", "merl", "synthetic.binary")
+    if not os.path.exists(merl):
+        make_scenes.write_synthetic_merl(merl)
+    d = C.POINTER(F.SceneDesc)()
+    assert trb.trb_desc_load_json(os.path.join(here, "golden", "scenes", "c5_tr15_like.json").encode(), w, h, spp, C.byref(d)) == 0, trb.trb_last_error()
+    return d
+
+
+def test_tr15_like_json_through_the_loader(trb):
+    """scene.rs:832-850 load_keyframes: control_points / knots / default degree 3; emission keyframes (scene.rs:722-747);
+    a group's keyframes stack above its children's (scene.rs:600-640)."""
+    d = _tr15_like_desc(trb)
+    desc = d.contents
+    assert (desc.film.frames, desc.film.scene_time, desc.integrator.min_depth, desc.integrator.max_depth) == (50, 25.0, 5, 10)
+    assert desc.n_cameras == 1 and desc.n_instances == 12 and desc.n_merl == 1 and desc.n_meshes == 1
+    cam = desc.cameras[0]
+    assert cam.n_splines == 1 and desc.splines[cam.spline_first].n_ctrl == 7 and desc.splines[cam.spline_first].degree == 3
+    # walls: object transform (static) below the group's 4-point cubic with repeated knots
+    w0 = desc.instances[0]
+    assert w0.n_splines == 2
+    s0, s1 = desc.splines[w0.spline_first], desc.splines[w0.spline_first + 1]
+    assert (s0.n_ctrl, s1.n_ctrl, s1.degree, s1.n_knots) == (1, 4, 3, 8)
+    assert [desc.knots[s1.knot_first + k] for k in range(8)] == [2.5] * 4 + [6.0] * 4
+    lights = [desc.instances[i] for i in range(desc.n_instances) if desc.instances[i].kind != F.INST_RECEIVER]
+    assert sorted(l.n_emission for l in lights) == [1, 2, 4]
+    big = [l for l in lights if l.n_emission == 4][0]
+    ck = [desc.color_keys[big.emission_first + k] for k in range(4)]
+    assert [k.time for k in ck] == [0.0, 3.5, 5.0, 7.0] and ck[0].rgba[0] == 0.0 and abs(ck[2].rgba[0] - 110.0) < 1e-4  # rgb * 4th component
+    o = api.OracleScene(desc)
+    step = desc.film.scene_time / desc.film.frames
+    means = []
+    for fr in (0, 9, 14, 30):
+        o.update_frame(fr, fr * step, (fr + 1) * step)
+        s, st = o.render_samples(seed=3)
+        assert np.isfinite(s["r"]).all()
+        means.append(float(s["r"].mean()))
+    assert means[0] > 0.003            # the static panel light
+    assert means[2] > 1.5 * means[0]   # the keyed disk light has ramped up by t = 7
+    # the walls sit still until t = 2.5, then sink (group keyframes): instance 0's transform
+    o.update_frame(0, 0.0, 0.5); y0 = o.transform(0)[0][1, 3]
+    o.update_frame(4, 2.0, 2.5); y1 = o.transform(0)[0][1, 3]
+    o.update_frame(20, 10.0, 10.5); y2 = o.transform(0)[0][1, 3]
+    assert y0 == y1 == 12.0 and y2 == 10.0
+    trb.trb_desc_free(d)

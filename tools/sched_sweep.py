@@ -26,7 +26,8 @@ def scene(depth0):
     return g
 
 
-def measure(g, sched, refill=8, flags=0, quads=1, occ=7):
+def measure(g, sched, refill=8, flags=0, quads=1, occ=7, shade_occ=4):
+    os.environ["TRB_SHADE_OCC"] = str(shade_occ)
     os.environ["TRB_TRACE_SCHED"] = str(sched)
     os.environ["TRB_REFILL"] = str(refill)
     os.environ["TRB_TRACE_QUADS"] = str(quads)
@@ -49,15 +50,12 @@ def sched(quorum, burst):
     return quorum | burst << 8
 
 
-# (name, sched word, refill, quads, occ)
-CASES = [("flat pairs", 0, 8, 0, 7)]
-for q, b in [(4, 1), (4, 2), (4, 3), (4, 4), (8, 2), (2, 2), (6, 2), (12, 2), (8, 4), (4, 8)]:
-    CASES.append(("pairs quorum%d burst%d" % (q, b), sched(q, b), 8, 0, 7))
-CASES += [("quads q4 b1", sched(4, 1), 8, 1, 7), ("quads q4 b2", sched(4, 2), 8, 1, 7), ("pairs q4 b2 r6", sched(4, 2), 6, 0, 7), ("pairs q4 b2 r12", sched(4, 2), 12, 0, 7),
-          ("pairs q4 b2 occ6", sched(4, 2), 8, 0, 6), ("pairs q4 b2 occ8", sched(4, 2), 8, 0, 8)]
+# (name, sched word, refill, quads, trace occ, shade occ)
+CASES = [("flat pairs", 0, 8, 0, 7, 4), ("q6 b2 (default)", sched(6, 2), 8, 0, 7, 4), ("q6 b2 shade occ5", sched(6, 2), 8, 0, 7, 5), ("q6 b2 shade occ6", sched(6, 2), 8, 0, 7, 6),
+         ("q6 b3", sched(6, 3), 8, 0, 7, 4), ("q6 b2 trace occ8", sched(6, 2), 8, 0, 8, 4), ("q6 b2 occ8 shade5", sched(6, 2), 8, 0, 8, 5)]
 if __name__ == "__main__":
     full, direct = scene(False), scene(True)
-    for name, sc, r, q, occ in CASES:
-        v, ms = measure(full, sc, r, quads=q, occ=occ)
-        v0, ms0 = measure(direct, sc, r, quads=q, occ=occ)
+    for name, sc, r, q, occ, so in CASES:
+        v, ms = measure(full, sc, r, quads=q, occ=occ, shade_occ=so)
+        v0, ms0 = measure(direct, sc, r, quads=q, occ=occ, shade_occ=so)
         print("%-24s full path %7.1f Mrays/s (%6.1f ms/step)   primary+shadow %7.1f Mrays/s (%5.1f ms/step)" % (name, v, ms, v0, ms0), flush=True)

@@ -368,7 +368,7 @@ trb_status launch_wavefront(trb_scene* s, const trb::RenderParams& rp, uint32_t 
         }
         static const int sst = getenv("TRB_SMEM_STACK") ? atoi(getenv("TRB_SMEM_STACK")) : 16;
         // TRB_TRACE_SCHED: 0 = flat state machine; else quorum | burst << 8 (see k_wf_trace)
-        const uint32_t sched = getenv("TRB_TRACE_SCHED") ? (uint32_t)strtoul(getenv("TRB_TRACE_SCHED"), nullptr, 0) : (4u | 2u << 8); // read per launch: tools/sched_sweep.py
+        const uint32_t sched = getenv("TRB_TRACE_SCHED") ? (uint32_t)strtoul(getenv("TRB_TRACE_SCHED"), nullptr, 0) : (6u | 2u << 8); // read per launch: tools/sched_sweep.py
         // TRB_TRACE_QUADS=1: two-level DQuad records instead of child-pair records (never in the STATS variants: their counters are the reference's)
         const bool quads = getenv("TRB_TRACE_QUADS") && atoi(getenv("TRB_TRACE_QUADS")) != 0; // measured 3-6 % slower than pairs on C4: off by default
 #define TRB_TRACE_LAUNCH(ST, MB, SS, AN, PH, QD) trb::k_wf_trace<ST, MB, SS, AN, PH, QD><<<tgrid, 128, 0, st>>>(s->ds, rp, wf, round, flags, refill, sched)
@@ -381,13 +381,15 @@ trb_status launch_wavefront(trb_scene* s, const trb::RenderParams& rp, uint32_t 
         else TRB_TRACE_LAUNCH(false, 6, 16, false, true, true);
 #undef TRB_TRACE_LAUNCH
         if (ev.first) { CU(cudaEventRecord(ev.second, st)); s->trace_events.push_back(ev); }
+        const int shade_occ = getenv("TRB_SHADE_OCC") ? atoi(getenv("TRB_SHADE_OCC")) : 4;
         if (anim) {
-            if (mode == 0) trb::k_wf_shade<0, true><<<shade_grid, 128, 0, st>>>(s->ds, rp, wf, round);
-            else trb::k_wf_shade<1, true><<<shade_grid, 128, 0, st>>>(s->ds, rp, wf, round);
-        } else {
-            if (mode == 0) trb::k_wf_shade<0, false><<<shade_grid, 128, 0, st>>>(s->ds, rp, wf, round);
-            else trb::k_wf_shade<1, false><<<shade_grid, 128, 0, st>>>(s->ds, rp, wf, round);
-        }
+            if (mode == 0) trb::k_wf_shade<0, true, 3><<<shade_grid, 128, 0, st>>>(s->ds, rp, wf, round);
+            else trb::k_wf_shade<1, true, 3><<<shade_grid, 128, 0, st>>>(s->ds, rp, wf, round);
+        } else if (mode == 0) {
+            if (shade_occ >= 6) trb::k_wf_shade<0, false, 6><<<(unsigned)s->sm_count * 6, 128, 0, st>>>(s->ds, rp, wf, round);
+            else if (shade_occ == 5) trb::k_wf_shade<0, false, 5><<<(unsigned)s->sm_count * 5, 128, 0, st>>>(s->ds, rp, wf, round);
+            else trb::k_wf_shade<0, false, 4><<<shade_grid, 128, 0, st>>>(s->ds, rp, wf, round);
+        } else trb::k_wf_shade<1, false, 4><<<shade_grid, 128, 0, st>>>(s->ds, rp, wf, round);
         g_launches += 2;
     }
     if (mode == 0) {

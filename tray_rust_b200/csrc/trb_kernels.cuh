@@ -1656,8 +1656,8 @@ __global__ void __launch_bounds__(128, MINB) k_wf_trace(const __grid_constant__ 
 }
 
 // Shade round r (== bounce r of every live path). MODE 0: finished samples go to wf.rad; MODE 1: to trb_sample records.
-template <int MODE, bool ANIM>
-__global__ void __launch_bounds__(128) k_wf_shade(const __grid_constant__ DScene sc, const __grid_constant__ RenderParams rp, const __grid_constant__ WfState wf,
+template <int MODE, bool ANIM, int MINB>
+__global__ void __launch_bounds__(128, MINB) k_wf_shade(const __grid_constant__ DScene sc, const __grid_constant__ RenderParams rp, const __grid_constant__ WfState wf,
                                                    uint32_t round) {
     uint32_t* cnt_r = wf.counters + round * WF_CNT;
     uint32_t* cnt_n = wf.counters + (round + 1) * WF_CNT;
