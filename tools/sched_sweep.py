@@ -26,8 +26,8 @@ def scene(depth0):
     return g
 
 
-def measure(g, sched, refill=8, flags=0, quads=1, occ=7, shade_occ=4):
-    os.environ["TRB_SHADE_OCC"] = str(shade_occ)
+def measure(g, sched, refill=8, flags=0, quads=1, occ=7, sst=16):
+    os.environ["TRB_SMEM_STACK"] = str(sst)
     os.environ["TRB_TRACE_SCHED"] = str(sched)
     os.environ["TRB_REFILL"] = str(refill)
     os.environ["TRB_TRACE_QUADS"] = str(quads)
@@ -50,12 +50,13 @@ def sched(quorum, burst):
     return quorum | burst << 8
 
 
-# (name, sched word, refill, quads, trace occ, shade occ)
-CASES = [("flat pairs", 0, 8, 0, 7, 4), ("q6 b2 (default)", sched(6, 2), 8, 0, 7, 4), ("q6 b2 shade occ5", sched(6, 2), 8, 0, 7, 5), ("q6 b2 shade occ6", sched(6, 2), 8, 0, 7, 6),
-         ("q6 b3", sched(6, 3), 8, 0, 7, 4), ("q6 b2 trace occ8", sched(6, 2), 8, 0, 8, 4), ("q6 b2 occ8 shade5", sched(6, 2), 8, 0, 8, 5)]
+# (name, sched word, refill, quads, trace occ, smem stack entries)
+CASES = [("flat pairs", 0, 8, 0, 7, 16), ("q6 b2 (default)", sched(6, 2), 8, 0, 7, 16), ("q6 b2 sst8", sched(6, 2), 8, 0, 7, 8), ("q6 b2 sst12", sched(6, 2), 8, 0, 7, 12),
+         ("q6 b2 sst20", sched(6, 2), 8, 0, 7, 20), ("q6 b3", sched(6, 3), 8, 0, 7, 16), ("q8 b2", sched(8, 2), 8, 0, 7, 16), ("q6 b2 occ8", sched(6, 2), 8, 0, 8, 16),
+         ("q6 b2 occ6", sched(6, 2), 8, 0, 6, 16), ("quads q6 b1", sched(6, 1), 8, 1, 7, 16)]
 if __name__ == "__main__":
     full, direct = scene(False), scene(True)
-    for name, sc, r, q, occ, so in CASES:
-        v, ms = measure(full, sc, r, quads=q, occ=occ, shade_occ=so)
-        v0, ms0 = measure(direct, sc, r, quads=q, occ=occ, shade_occ=so)
+    for name, sc, r, q, occ, sst in CASES:
+        v, ms = measure(full, sc, r, quads=q, occ=occ, sst=sst)
+        v0, ms0 = measure(direct, sc, r, quads=q, occ=occ, sst=sst)
         print("%-24s full path %7.1f Mrays/s (%6.1f ms/step)   primary+shadow %7.1f Mrays/s (%5.1f ms/step)" % (name, v, ms, v0, ms0), flush=True)

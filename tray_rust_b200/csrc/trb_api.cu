@@ -354,7 +354,7 @@ trb_status launch_wavefront(trb_scene* s, const trb::RenderParams& rp, uint32_t 
     if (anim) trb::k_wf_generate<true><<<gen_grid, 256, 0, st>>>(s->ds, rp, wf);
     else trb::k_wf_generate<false><<<gen_grid, 256, 0, st>>>(s->ds, rp, wf);
     g_launches++;
-    const unsigned trace_grid = (unsigned)s->sm_count * 12, shade_grid = (unsigned)s->sm_count * 4;
+    const unsigned shade_grid = (unsigned)s->sm_count * 4;
     for (uint32_t round = 0; round < rounds; ++round) {
         const int refill = getenv("TRB_REFILL") ? atoi(getenv("TRB_REFILL")) : 8;
         const int occ = getenv("TRB_TRACE_OCC") ? atoi(getenv("TRB_TRACE_OCC")) : 7;
@@ -366,30 +366,30 @@ trb_status launch_wavefront(trb_scene* s, const trb::RenderParams& rp, uint32_t 
             else { CU(cudaEventCreate(&ev.first)); CU(cudaEventCreate(&ev.second)); }
             CU(cudaEventRecord(ev.first, st));
         }
-        static const int sst = getenv("TRB_SMEM_STACK") ? atoi(getenv("TRB_SMEM_STACK")) : 16;
+        const int sst = getenv("TRB_SMEM_STACK") ? atoi(getenv("TRB_SMEM_STACK")) : 16;
         // TRB_TRACE_SCHED: 0 = flat state machine; else quorum | burst << 8 (see k_wf_trace)
         const uint32_t sched = getenv("TRB_TRACE_SCHED") ? (uint32_t)strtoul(getenv("TRB_TRACE_SCHED"), nullptr, 0) : (6u | 2u << 8); // read per launch: tools/sched_sweep.py
         // TRB_TRACE_QUADS=1: two-level DQuad records instead of child-pair records (never in the STATS variants: their counters are the reference's)
         const bool quads = getenv("TRB_TRACE_QUADS") && atoi(getenv("TRB_TRACE_QUADS")) != 0; // measured 3-6 % slower than pairs on C4: off by default
 #define TRB_TRACE_LAUNCH(ST, MB, SS, AN, PH, QD) trb::k_wf_trace<ST, MB, SS, AN, PH, QD><<<tgrid, 128, 0, st>>>(s->ds, rp, wf, round, flags, refill, sched)
-        if (anim) { if (stats) TRB_TRACE_LAUNCH(true, 4, 16, true, true, false); else TRB_TRACE_LAUNCH(false, 7, 16, true, true, true); }
+        if (anim) { if (stats) TRB_TRACE_LAUNCH(true, 4, 16, true, true, false); else TRB_TRACE_LAUNCH(false, 7, 16, true, true, false); }
         else if (stats) { if (sched) TRB_TRACE_LAUNCH(true, 4, 16, false, true, false); else TRB_TRACE_LAUNCH(true, 4, 16, false, false, false); }
         else if (sched == 0) { if (occ >= 8) TRB_TRACE_LAUNCH(false, 8, 16, false, false, false); else if (occ >= 7) TRB_TRACE_LAUNCH(false, 7, 16, false, false, false); else TRB_TRACE_LAUNCH(false, 6, 16, false, false, false); }
-        else if (!quads) { if (occ >= 8) TRB_TRACE_LAUNCH(false, 8, 16, false, true, false); else if (occ >= 7) TRB_TRACE_LAUNCH(false, 7, 16, false, true, false); else TRB_TRACE_LAUNCH(false, 6, 16, false, true, false); }
-        else if (occ >= 8) TRB_TRACE_LAUNCH(false, 8, 16, false, true, true);
-        else if (occ >= 7) { if (sst <= 8) TRB_TRACE_LAUNCH(false, 7, 8, false, true, true); else TRB_TRACE_LAUNCH(false, 7, 16, false, true, true); }
-        else TRB_TRACE_LAUNCH(false, 6, 16, false, true, true);
+        else if (quads) TRB_TRACE_LAUNCH(false, 7, 16, false, true, true);
+        else if (occ >= 8) TRB_TRACE_LAUNCH(false, 8, 16, false, true, false);
+        else if (occ <= 6) TRB_TRACE_LAUNCH(false, 6, 16, false, true, false);
+        else if (sst <= 8) TRB_TRACE_LAUNCH(false, 7, 8, false, true, false);
+        else if (sst <= 12) TRB_TRACE_LAUNCH(false, 7, 12, false, true, false);
+        else if (sst <= 16) TRB_TRACE_LAUNCH(false, 7, 16, false, true, false);
+        else TRB_TRACE_LAUNCH(false, 7, 20, false, true, false);
 #undef TRB_TRACE_LAUNCH
         if (ev.first) { CU(cudaEventRecord(ev.second, st)); s->trace_events.push_back(ev); }
-        const int shade_occ = getenv("TRB_SHADE_OCC") ? atoi(getenv("TRB_SHADE_OCC")) : 4;
+        // (occupancy 5 / 6 variants of the shade kernel were measured 1-2 % slower: spills outweigh the extra warps)
         if (anim) {
             if (mode == 0) trb::k_wf_shade<0, true, 3><<<shade_grid, 128, 0, st>>>(s->ds, rp, wf, round);
             else trb::k_wf_shade<1, true, 3><<<shade_grid, 128, 0, st>>>(s->ds, rp, wf, round);
-        } else if (mode == 0) {
-            if (shade_occ >= 6) trb::k_wf_shade<0, false, 6><<<(unsigned)s->sm_count * 6, 128, 0, st>>>(s->ds, rp, wf, round);
-            else if (shade_occ == 5) trb::k_wf_shade<0, false, 5><<<(unsigned)s->sm_count * 5, 128, 0, st>>>(s->ds, rp, wf, round);
-            else trb::k_wf_shade<0, false, 4><<<shade_grid, 128, 0, st>>>(s->ds, rp, wf, round);
-        } else trb::k_wf_shade<1, false, 4><<<shade_grid, 128, 0, st>>>(s->ds, rp, wf, round);
+        } else if (mode == 0) trb::k_wf_shade<0, false, 4><<<shade_grid, 128, 0, st>>>(s->ds, rp, wf, round);
+        else trb::k_wf_shade<1, false, 4><<<shade_grid, 128, 0, st>>>(s->ds, rp, wf, round);
         g_launches += 2;
     }
     if (mode == 0) {

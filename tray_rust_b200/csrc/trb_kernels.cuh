@@ -93,23 +93,24 @@ struct Cnt { uint32_t node, tri, inst; };
 // behaviour is the reference's.
 // ------------------------------------------------------------------------------------------
 TRB_HD __forceinline__ bool box_hit(const float4 lo, const float4 hi, f3 o, f3 inv, bool nx, bool ny, bool nz, float tmin_r, float tmax_r, float& t_entry) {
-    t_entry = 0.0f;
+    // Branch-free form of the reference's early returns: every statement below is the reference's, in its order; the two
+    // `return false` become flags, which cannot change the outcome (after either the result is false whatever follows)
+    // and saves the divergent branches + reconvergence the warp would execute anyway for the lanes that go on.
     float tmin = ((nx ? hi.x : lo.x) - o.x) * inv.x;
     float tmax = ((nx ? lo.x : hi.x) - o.x) * inv.x;
-    float tymin = ((ny ? hi.y : lo.y) - o.y) * inv.y;
-    float tymax = ((ny ? lo.y : hi.y) - o.y) * inv.y;
-    if (tmin > tymax || tymin > tmax) return false;
+    const float tymin = ((ny ? hi.y : lo.y) - o.y) * inv.y;
+    const float tymax = ((ny ? lo.y : hi.y) - o.y) * inv.y;
+    const bool miss_xy = tmin > tymax || tymin > tmax; // bbox.rs:87-89 `return false`
     if (tymin > tmin) tmin = tymin;
     if (tymax < tmax) tmax = tymax;
-    float tzmin = ((nz ? hi.z : lo.z) - o.z) * inv.z;
-    float tzmax = ((nz ? lo.z : hi.z) - o.z) * inv.z;
-    if (tmin > tzmax || tzmin > tmax) return false;
+    const float tzmin = ((nz ? hi.z : lo.z) - o.z) * inv.z;
+    const float tzmax = ((nz ? lo.z : hi.z) - o.z) * inv.z;
+    const bool miss_z = tmin > tzmax || tzmin > tmax;  // bbox.rs:96-98 `return false`
     if (tzmin > tmin) tmin = tzmin;
     if (tzmax < tmax) tmax = tzmax;
     t_entry = tmin; // the only quantity a later, smaller max_t can still reject: `tmin < r.max_t` (bbox.rs:103)
-    return tmin < tmax_r && tmax > tmin_r;
+    return !miss_xy && !miss_z && tmin < tmax_r && tmax > tmin_r;
 }
-
 
 // One visit of a DQuad record (trb_device.h): four box tests, then the reference's visit order. `next` is the first
 // slot hit in that order (QUAD_EMPTY if none); the other hit slots come back farthest-first in e[0..2] so that the
@@ -294,11 +295,10 @@ struct LocalStack {
 };
 template <int SMEM_STACK>
 struct HybridStack {
-    unsigned long long* sm; // &smem[0][threadIdx.x], stride = blockDim.x
+    unsigned long long* sm; // &smem[0][threadIdx.x], stride = blockDim.x = 128
     unsigned long long* lo;
-    int stride;
-    __device__ __forceinline__ void put(int i, unsigned long long v) const { if (i < SMEM_STACK) sm[i * stride] = v; else lo[i - SMEM_STACK] = v; }
-    __device__ __forceinline__ unsigned long long get(int i) const { return i < SMEM_STACK ? sm[i * stride] : lo[i - SMEM_STACK]; }
+    __device__ __forceinline__ void put(int i, unsigned long long v) const { if (i < SMEM_STACK) sm[i * 128] = v; else lo[i - SMEM_STACK] = v; }
+    __device__ __forceinline__ unsigned long long get(int i) const { return i < SMEM_STACK ? sm[i * 128] : lo[i - SMEM_STACK]; }
 };
 
 // Pop the next reference. A node entry carries the entry distance of its box, computed when its parent was
@@ -1563,7 +1563,7 @@ __global__ void __launch_bounds__(128, MINB) k_wf_trace(const __grid_constant__ 
     TraceState t;
     __shared__ unsigned long long s_stack[SMEM_STACK * 128];
     unsigned long long stack_lo[STACK_DEPTH - SMEM_STACK];
-    const HybridStack<SMEM_STACK> stack{s_stack + threadIdx.x, stack_lo, 128};
+    const HybridStack<SMEM_STACK> stack{s_stack + threadIdx.x, stack_lo};
     t.cur = ST_DONE;
     bool have = false, exhausted = false;
     uint32_t p = 0;
