@@ -252,7 +252,7 @@ constexpr int STACK_DEPTH = 96;
 struct TraceState {
     f3 wo, wd, winv;      // world ray and 1/d (bvh.rs:84)
     f3 o, d, inv;         // ray of the current level (world, or the mesh instance's object space)
-    bool nx, ny, nz;      // d < 0 per axis (bvh.rs:85)
+    uint32_t neg;         // bit k: d[k] < 0 (bvh.rs:85)
     const DBvh* bvh;      // current level (root box + reference)
     const DPair* pairs;   // current level's records, kept in registers: no pointer chase per step (DQuad records when `quad`)
     bool quad;            // this level is traversed through the DQuad records (finite 1/d only, see trb_device.h)
@@ -267,6 +267,7 @@ struct TraceState {
     uint32_t h_inst, h_prim;
     float h_b1, h_b2;
 };
+__device__ __forceinline__ uint32_t neg_mask(f3 d) { return (d.x < 0.0f ? 1u : 0u) | (d.y < 0.0f ? 2u : 0u) | (d.z < 0.0f ? 4u : 0u); }
 __device__ __forceinline__ bool finite3(f3 v) { return fabsf(v.x) < finf() && fabsf(v.y) < finf() && fabsf(v.z) < finf(); }
 __device__ __forceinline__ void trace_level(TraceState& t, const DBvh* bvh, const DPair* pairs, const DQuad* quads) {
     t.bvh = bvh;
@@ -278,7 +279,7 @@ __device__ __forceinline__ void trace_init(const DScene& sc, TraceState& t, cons
     t.wo = ray.o; t.wd = ray.d;
     t.winv = mk(1.0f / ray.d.x, 1.0f / ray.d.y, 1.0f / ray.d.z);
     t.o = t.wo; t.d = t.wd; t.inv = t.winv;
-    t.nx = t.d.x < 0.0f; t.ny = t.d.y < 0.0f; t.nz = t.d.z < 0.0f;
+    t.neg = neg_mask(t.d);
     trace_level(t, sc.tlas, sc.tlas_pairs, sc.tlas_quads);
     t.tris = nullptr; t.level_inst = TRB_MISS;
     t.tmin = ray.tmin; t.tmax = ray.tmax;
@@ -324,10 +325,10 @@ __device__ __forceinline__ void trace_step(const DScene& sc, TraceState& t, cons
         const float4 l_lo = __ldg(&rec->l_lo), l_hi = __ldg(&rec->l_hi), r_lo = __ldg(&rec->r_lo), r_hi = __ldg(&rec->r_hi);
         if (STATS) cnt.node += 2; // the reference tests the near child now and the far child when it pops it
         float tl, tr;
-        const bool hl = box_hit(l_lo, l_hi, t.o, t.inv, t.nx, t.ny, t.nz, t.tmin, t.tmax, tl);
-        const bool hr = box_hit(r_lo, r_hi, t.o, t.inv, t.nx, t.ny, t.nz, t.tmin, t.tmax, tr);
+        const bool hl = box_hit(l_lo, l_hi, t.o, t.inv, (t.neg & 1u) != 0, (t.neg & 2u) != 0, (t.neg & 4u) != 0, t.tmin, t.tmax, tl);
+        const bool hr = box_hit(r_lo, r_hi, t.o, t.inv, (t.neg & 1u) != 0, (t.neg & 2u) != 0, (t.neg & 4u) != 0, t.tmin, t.tmax, tr);
         const uint32_t axis = __float_as_uint(r_lo.w);
-        const bool neg = axis == 0 ? t.nx : (axis == 1 ? t.ny : t.nz); // near child = second_child iff d[axis] < 0 (bvh.rs:111-117)
+        const bool neg = ((t.neg >> axis) & 1u) != 0; // near child = second_child iff d[axis] < 0 (bvh.rs:111-117)
         const uint32_t ref_l = __float_as_uint(l_lo.w), ref_r = __float_as_uint(l_hi.w);
         const bool h_near = neg ? hr : hl, h_far = neg ? hl : hr;
         const uint32_t ref_near = neg ? ref_r : ref_l, ref_far = neg ? ref_l : ref_r;
@@ -373,10 +374,10 @@ __device__ __forceinline__ void trace_step(const DScene& sc, TraceState& t, cons
         const float4 lo = __ldg(&t.bvh->root_lo), hi = __ldg(&t.bvh->root_hi);
         if (STATS) cnt.node++;
         float te;
-        next = box_hit(lo, hi, t.o, t.inv, t.nx, t.ny, t.nz, t.tmin, t.tmax, te) ? __float_as_uint(lo.w) : trace_pop(t, stack);
+        next = box_hit(lo, hi, t.o, t.inv, (t.neg & 1u) != 0, (t.neg & 2u) != 0, (t.neg & 4u) != 0, t.tmin, t.tmax, te) ? __float_as_uint(lo.w) : trace_pop(t, stack);
     } else if (cur == ST_RETURN) {
         t.o = t.wo; t.d = t.wd; t.inv = t.winv;
-        t.nx = t.d.x < 0.0f; t.ny = t.d.y < 0.0f; t.nz = t.d.z < 0.0f;
+        t.neg = neg_mask(t.d);
         t.bvh = sc.tlas; t.pairs = sc.tlas_pairs; t.level_inst = TRB_MISS;
         next = trace_pop(t, stack);
     } else {
@@ -395,7 +396,7 @@ __device__ __forceinline__ void trace_step(const DScene& sc, TraceState& t, cons
                 const DMesh& me = sc.meshes[__ldg(&in.mesh)];
                 t.o = lo_; t.d = ld_;
                 t.inv = mk(1.0f / ld_.x, 1.0f / ld_.y, 1.0f / ld_.z);
-                t.nx = ld_.x < 0.0f; t.ny = ld_.y < 0.0f; t.nz = ld_.z < 0.0f;
+                t.neg = neg_mask(ld_);
                 t.bvh = &me.bvh; t.pairs = me.bvh.pairs; t.tris = me.tris; t.level_inst = ii;
                 stack.put(t.sp++, ST_RETURN);
                 next = ST_ROOT; // BVH<Triangle>::intersect starts by testing its root box
@@ -448,7 +449,7 @@ __device__ __forceinline__ void step_nodes(TraceState& t, const Stack& stack, Cn
         float4 q0, q1, q2, q3, q4, q5, q6, q7;
         ldg256(rec, q0, q1); ldg256(rec + 2, q2, q3); ldg256(rec + 4, q4, q5); ldg256(rec + 6, q6, q7);
         QuadOut qo;
-        quad_visit(q0, q1, q2, q3, q4, q5, q6, q7, t.o, t.inv, t.nx, t.ny, t.nz, t.tmin, t.tmax, qo);
+        quad_visit(q0, q1, q2, q3, q4, q5, q6, q7, t.o, t.inv, (t.neg & 1u) != 0, (t.neg & 2u) != 0, (t.neg & 4u) != 0, t.tmin, t.tmax, qo);
         cur = qo.next == QUAD_EMPTY ? ST_POP : qo.next;
         if (qo.p2) { // at least one more slot was hit
             if (t.sp >= STACK_DEPTH - 6) { *err = 1; t.sp = 0; cur = ST_DONE; }
@@ -471,18 +472,18 @@ __device__ __forceinline__ void step_nodes(TraceState& t, const Stack& stack, Cn
         ldg256(&rec->r_lo, r_lo, r_hi);
         if (STATS) cnt.node += 2;
         float tl, tr;
-        const bool hl = box_hit(l_lo, l_hi, t.o, t.inv, t.nx, t.ny, t.nz, t.tmin, t.tmax, tl);
-        const bool hr = box_hit(r_lo, r_hi, t.o, t.inv, t.nx, t.ny, t.nz, t.tmin, t.tmax, tr);
+        const bool hl = box_hit(l_lo, l_hi, t.o, t.inv, (t.neg & 1u) != 0, (t.neg & 2u) != 0, (t.neg & 4u) != 0, t.tmin, t.tmax, tl);
+        const bool hr = box_hit(r_lo, r_hi, t.o, t.inv, (t.neg & 1u) != 0, (t.neg & 2u) != 0, (t.neg & 4u) != 0, t.tmin, t.tmax, tr);
         const uint32_t axis = __float_as_uint(r_lo.w);
-        const bool neg = axis == 0 ? t.nx : (axis == 1 ? t.ny : t.nz);
+        const bool neg = ((t.neg >> axis) & 1u) != 0; // near child = second_child iff d[axis] < 0 (bvh.rs:111-117)
         const uint32_t ref_l = __float_as_uint(l_lo.w), ref_r = __float_as_uint(l_hi.w);
-        const bool h_near = neg ? hr : hl, h_far = neg ? hl : hr;
-        const uint32_t ref_near = neg ? ref_r : ref_l, ref_far = neg ? ref_l : ref_r;
-        const float t_far = neg ? tl : tr;
-        cur = h_near ? ref_near : (h_far ? ref_far : ST_POP);
-        if (h_near && h_far) {
+        const bool both = hl && hr;
+        // both hit: the near child now, the far one on the stack; one hit: that child (nothing is tested in between, so
+        // max_t is unchanged and the far child's deferred test has the same outcome); none: pop
+        cur = both ? (neg ? ref_r : ref_l) : (hl ? ref_l : (hr ? ref_r : ST_POP));
+        if (both) {
             if (t.sp >= STACK_DEPTH - 6) { *err = 1; t.sp = 0; cur = ST_DONE; }
-            else stack.put(t.sp++, ((unsigned long long)__float_as_uint(t_far) << 32) | ref_far);
+            else stack.put(t.sp++, ((unsigned long long)__float_as_uint(neg ? tl : tr) << 32) | (neg ? ref_l : ref_r));
         }
     }
 #pragma unroll
@@ -539,10 +540,10 @@ __device__ __forceinline__ void step_other(const DScene& sc, TraceState& t, cons
         const float4 lo = __ldg(&t.bvh->root_lo), hi = __ldg(&t.bvh->root_hi);
         if (STATS) cnt.node++;
         float te;
-        if (box_hit(lo, hi, t.o, t.inv, t.nx, t.ny, t.nz, t.tmin, t.tmax, te)) next = __float_as_uint(t.quad ? hi.w : lo.w);
+        if (box_hit(lo, hi, t.o, t.inv, (t.neg & 1u) != 0, (t.neg & 2u) != 0, (t.neg & 4u) != 0, t.tmin, t.tmax, te)) next = __float_as_uint(t.quad ? hi.w : lo.w);
     } else if (cur == ST_RETURN) {
         t.o = t.wo; t.d = t.wd; t.inv = t.winv;
-        t.nx = t.d.x < 0.0f; t.ny = t.d.y < 0.0f; t.nz = t.d.z < 0.0f;
+        t.neg = neg_mask(t.d);
         trace_level(t, sc.tlas, sc.tlas_pairs, sc.tlas_quads);
         t.level_inst = TRB_MISS;
     } else { // Instance::intersect for one entry of a TLAS leaf
@@ -558,7 +559,7 @@ __device__ __forceinline__ void step_other(const DScene& sc, TraceState& t, cons
                 const DMesh& me = sc.meshes[__ldg(&in.mesh)];
                 t.o = lo_; t.d = ld_;
                 t.inv = mk(1.0f / ld_.x, 1.0f / ld_.y, 1.0f / ld_.z);
-                t.nx = ld_.x < 0.0f; t.ny = ld_.y < 0.0f; t.nz = ld_.z < 0.0f;
+                t.neg = neg_mask(ld_);
                 trace_level(t, &me.bvh, me.bvh.pairs, me.bvh.quads);
                 t.tris = me.tris; t.level_inst = ii;
                 stack.put(t.sp++, ST_RETURN);
