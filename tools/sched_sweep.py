@@ -51,9 +51,8 @@ def sched(quorum, burst):
 
 
 # (name, sched word, refill, quads, trace occ, smem stack entries)
-CASES = [("flat pairs", 0, 8, 0, 7, 16), ("q6 b2 (default)", sched(6, 2), 8, 0, 7, 16), ("q6 b2 sst8", sched(6, 2), 8, 0, 7, 8), ("q6 b2 sst12", sched(6, 2), 8, 0, 7, 12),
-         ("q6 b2 sst20", sched(6, 2), 8, 0, 7, 20), ("q6 b3", sched(6, 3), 8, 0, 7, 16), ("q8 b2", sched(8, 2), 8, 0, 7, 16), ("q6 b2 occ8", sched(6, 2), 8, 0, 8, 16),
-         ("q6 b2 occ6", sched(6, 2), 8, 0, 6, 16), ("quads q6 b1", sched(6, 1), 8, 1, 7, 16)]
+CASES = [("flat pairs", 0, 8, 0, 7, 16), ("quorum 6 (default)", 6, 8, 0, 7, 16), ("quorum 4", 4, 8, 0, 7, 16), ("quorum 8", 8, 8, 0, 7, 16), ("quorum 6 sst12", 6, 8, 0, 7, 12),
+         ("quorum 6 occ8", 6, 8, 0, 8, 16), ("quorum 6 refill 6", 6, 6, 0, 7, 16), ("quorum 6 refill 10", 6, 10, 0, 7, 16), ("quads quorum 6", 6, 8, 1, 7, 16)]
 if __name__ == "__main__":
     full, direct = scene(False), scene(True)
     for name, sc, r, q, occ, sst in CASES:

@@ -367,8 +367,8 @@ trb_status launch_wavefront(trb_scene* s, const trb::RenderParams& rp, uint32_t 
             CU(cudaEventRecord(ev.first, st));
         }
         const int sst = getenv("TRB_SMEM_STACK") ? atoi(getenv("TRB_SMEM_STACK")) : 16;
-        // TRB_TRACE_SCHED: 0 = flat state machine; else quorum | burst << 8 (see k_wf_trace)
-        const uint32_t sched = getenv("TRB_TRACE_SCHED") ? (uint32_t)strtoul(getenv("TRB_TRACE_SCHED"), nullptr, 0) : (6u | 2u << 8); // read per launch: tools/sched_sweep.py
+        // TRB_TRACE_SCHED: 0 = flat state machine; else the quorum of the phased loop (see k_wf_trace)
+        const uint32_t sched = getenv("TRB_TRACE_SCHED") ? (uint32_t)strtoul(getenv("TRB_TRACE_SCHED"), nullptr, 0) : 6u; // read per launch: tools/sched_sweep.py
         // TRB_TRACE_QUADS=1: two-level DQuad records instead of child-pair records (never in the STATS variants: their counters are the reference's)
         const bool quads = getenv("TRB_TRACE_QUADS") && atoi(getenv("TRB_TRACE_QUADS")) != 0; // measured 3-6 % slower than pairs on C4: off by default
 #define TRB_TRACE_LAUNCH(ST, MB, SS, AN, PH, QD) trb::k_wf_trace<ST, MB, SS, AN, PH, QD><<<tgrid, 128, 0, st>>>(s->ds, rp, wf, round, flags, refill, sched)

@@ -432,6 +432,7 @@ __device__ __forceinline__ void trace_step(const DScene& sc, TraceState& t, cons
 // state: ncu showed the triangle code running with 2.2 of 32 lanes and the pop loop with 4.
 // ------------------------------------------------------------------------------------------
 constexpr uint32_t ST_POP = 0xfffffffcu; // control: take the next reference off the stack
+constexpr int WF_BURST = 3;
 __device__ __forceinline__ bool trace_is_node(uint32_t cur) { return (cur & REF_TAG) == REF_INTERIOR || cur == ST_POP; }
 __device__ __forceinline__ int trace_class(const TraceState& t) {
     const uint32_t cur = t.cur;
@@ -488,13 +489,10 @@ __device__ __forceinline__ void step_nodes(TraceState& t, const Stack& stack, Cn
     }
 #pragma unroll
     for (int k = 0; k < 2; ++k) { // bounded: a lane with a long run of culled entries comes back next iteration
-        if (cur == ST_POP) {
-            if (t.sp == 0) cur = ST_DONE;
-            else {
-                const unsigned long long e = stack.get(--t.sp);
-                const uint32_t ref = (uint32_t)e;
-                if ((ref & ST_INSTANCE) || __uint_as_float((uint32_t)(e >> 32)) < t.tmax) cur = ref;
-            }
+        if (cur == ST_POP) { // entry 0 of a PHASED kernel's stack is a ST_DONE sentinel (never culled): no empty-stack test
+            const unsigned long long e = stack.get(--t.sp);
+            const uint32_t ref = (uint32_t)e;
+            if ((ref & ST_INSTANCE) || __uint_as_float((uint32_t)(e >> 32)) < t.tmax) cur = ref;
         }
     }
     t.cur = cur;
@@ -1605,6 +1603,7 @@ __global__ void __launch_bounds__(128, MINB) k_wf_trace(const __grid_constant__ 
                     ray.tmin = (type == 0 && round == 0) ? 0.0f : 0.001f;
                     ray.tmax = type == 1 ? 0.999f : finf();
                     trace_init(sc, t, ray, type == 1 && shadow_any, ANIM ? __ldg(&wf.thr[p].w) : 0.0f, QUADS && PHASED);
+                    if (PHASED) { stack.put(0, (unsigned long long)ST_DONE); t.sp = 1; } // bottom sentinel: popping it ends the ray
                     have = true;
                 }
             }
@@ -1613,11 +1612,12 @@ __global__ void __launch_bounds__(128, MINB) k_wf_trace(const __grid_constant__ 
         if (busy0 == 0) { if (exhausted) break; else continue; }
         // ---- traverse until enough lanes have finished ----
         if (PHASED) {
-            // `sched`: bits 0-7 quorum of lanes waiting for a non-node micro-step (triangle / root / instance / return),
-            //          bits 8-15 node micro-steps per scheduling decision. An idle lane has cur == ST_DONE.
-            const int thr_o = (int)(sched & 255u), burst = (int)((sched >> 8) & 255u);
+            // `sched`: quorum of lanes waiting for a non-node micro-step (triangle / root / instance / return); WF_BURST node
+            // micro-steps per scheduling decision (2-3 measured best). An idle lane has cur == ST_DONE.
+            const int thr_o = (int)(sched & 255u);
             for (;;) {
-                for (int k = 0; k < burst; ++k)
+#pragma unroll
+                for (int k = 0; k < WF_BURST; ++k)
                     if (trace_is_node(t.cur)) step_nodes<STATS, QUADS>(t, stack, cnt, rp.error_flag);
                 const bool is_a = trace_is_node(t.cur), is_o = !is_a && t.cur != ST_DONE;
                 const unsigned m_a = __ballot_sync(0xffffffffu, is_a), m_o = __ballot_sync(0xffffffffu, is_o);
