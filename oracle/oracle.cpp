@@ -130,6 +130,10 @@ struct Camera {
     AnimatedTransform cam_world;
     Transform raster_screen, proj_div_inv, px_to_cam;
     float shutter_open = 0, shutter_close = 0, shutter_size = 0.5f, fov = 30;
+    /* CameraFov::Animated(BSpline<f32>) (camera.rs:23-30,95-125) */
+    bool fov_animated = false;
+    uint32_t fov_degree = 0;
+    std::vector<float> fovs, fov_knots;
     V3 scaling;
     uint32_t active_at = 0;
     void init(float fov_, uint32_t w, uint32_t h) { /* camera.rs:64-91 */
@@ -151,9 +155,37 @@ struct Camera {
         float tan_fov = tanf(to_radians(fov) / 2.0f);
         scaling = V3(tan_fov, tan_fov, 1.0f);
     }
+    /* bspline 0.2.2 BSpline<f32>::point: de Boor with Interpolate for f32 = a * (1 - t) + b * t */
+    float fov_spline_point(float t) const {
+        size_t n = fov_knots.size(), degree = fov_degree;
+        size_t ub = n;
+        for (size_t i = 0; i < n; ++i) if (fov_knots[i] > t) { ub = i; break; }
+        size_t i0;
+        if (ub == n) i0 = n - degree - 1;
+        else if (ub == 0) i0 = degree;
+        else if (ub >= n - degree - 1) i0 = n - degree - 1;
+        else i0 = ub;
+        std::vector<float> tmp(degree + 1);
+        for (size_t j = 0; j <= degree; ++j) tmp[j] = fovs[j + i0 - degree - 1];
+        for (size_t lvl = 0; lvl < degree; ++lvl) {
+            size_t k = lvl + 1;
+            for (size_t j = 0; j < degree - lvl; ++j) {
+                size_t i = j + k + i0 - degree;
+                float alpha = (t - fov_knots[i - 1]) / (fov_knots[i + degree - k] - fov_knots[i - 1]);
+                tmp[j] = tmp[j] * (1.0f - alpha) + tmp[j + 1] * alpha;
+            }
+        }
+        return tmp[0];
+    }
     void update_frame(float start, float end) { /* camera.rs:127-144 */
         shutter_open = start;
         shutter_close = start + shutter_size * (end - start);
+        if (fov_animated) { /* the spline is sampled once per frame, at the clamped mid-frame time (camera.rs:134-141) */
+            float lo = fov_knots[fov_degree], hi = fov_knots[fov_knots.size() - 1 - fov_degree];
+            float t = (start + end) / 2.0f;
+            t = t < lo ? lo : (t > hi ? hi : t);
+            fov = fov_spline_point(t);
+        }
         float tan_fov = tanf(to_radians(fov) / 2.0f);
         scaling = V3(tan_fov, tan_fov, 1.0f);
     }
@@ -301,8 +333,13 @@ int orc_scene_create(const trb_scene_desc* d, orc_scene** out) {
         const trb_camera& tc = d->cameras[c];
         Camera cam; cam.cam_world = load_xf(d, tc.spline_first, tc.n_splines);
         cam.shutter_size = tc.shutter_size; cam.active_at = tc.active_at;
-        if (tc.n_fov_ctrl > 0) { delete s; g_err = "animated fov unsupported"; return TRB_UNSUPPORTED; }
-        cam.init(tc.fov, d->film.width, d->film.height);
+        if (tc.n_fov_ctrl > 0) { /* Camera::animated_fov (camera.rs:95-125): starts from fovs[0] */
+            cam.fov_animated = true; cam.fov_degree = tc.fov_degree;
+            cam.fovs.assign(d->fov_floats + tc.fov_ctrl_first, d->fov_floats + tc.fov_ctrl_first + tc.n_fov_ctrl);
+            cam.fov_knots.assign(d->fov_floats + tc.fov_knot_first, d->fov_floats + tc.fov_knot_first + tc.n_fov_knots);
+            if (cam.fov_knots.size() != cam.fovs.size() + cam.fov_degree + 1) { delete s; g_err = "Invalid B-spline: knots.len() != control_points.len() + degree + 1"; return TRB_INVALID_ARG; }
+            cam.init(cam.fovs[0], d->film.width, d->film.height);
+        } else cam.init(tc.fov, d->film.width, d->film.height);
         s->cameras.push_back(cam);
     }
     if (s->cameras.empty()) { delete s; g_err = "A camera is required"; return TRB_INVALID_ARG; }

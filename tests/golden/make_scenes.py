@@ -88,8 +88,8 @@ def cube_obj():
 
 
 def tr15_like():
-    """C5-shaped input (BASELINE configs[4], the reference's tr15 scene): every feature tr15.json uses — B-spline keyframed
-    camera, keyframed groups with default degree 3 and repeated knots, keyframed objects inside keyframed groups, area
+    """C5-shaped input (BASELINE configs[4], the reference's tr15 scene): every feature tr15.json uses (plus an animated field
+    of view, scene.rs:286-304) — B-spline keyframed camera, keyframed groups with default degree 3 and repeated knots, keyframed objects inside keyframed groups, area
     lights on disks with keyframed emission whose 4th component ramps from 0, OBJ meshes, a MERL material — at a size the
     oracle renders in seconds. The models and the MERL table are stand-ins (the originals are not redistributable)."""
     tr = lambda t: {"type": "translate", "translation": t}
@@ -99,7 +99,7 @@ def tr15_like():
     rz = lambda r: {"type": "rotate_z", "rotation": r}
     cp = lambda *steps: {"transform": list(steps)}
     film = dict(FILM, width=1920, height=1080, samples=2048, frames=50, start_frame=0, end_frame=49, scene_time=25)
-    camera = {"fov": 40, "keyframes": {"control_points": [
+    camera = {"fov": [40, 40, 34, 44], "fov_knots": [0, 0, 0, 12, 25, 25, 25], "fov_spline_degree": 2, "keyframes": {"control_points": [
         cp(rx(15), tr([0, 12, -46])), cp(rx(15), tr([0, 12, -46])), cp(rx(9), tr([0, 14, -50])), cp(rx(9), tr([0, 14, -50])),
         cp(rx(8), ry(25), tr([-19, 14, -40])), cp(rx(8), ry(35), tr([-13, 14, -42])), cp(rx(8), ry(45), tr([-3, 16, -44]))],
         "knots": [0, 0, 0, 0, 6, 12, 18, 25, 25, 25, 25]}}

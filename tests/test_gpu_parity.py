@@ -55,7 +55,7 @@ SCENES = {
 def test_animated_scene_gpu_vs_oracle():
     """keyframed instances (one- and two-level stacks), keyframed camera, moving lights with keyframed
     emission — transforms recomposed per ray on the device (receiver.rs:30, emitter.rs:122,170,176,197, camera.rs:156)."""
-    desc = SB.scene_animated(64, 64, 8, frames=4, scene_time=1.0).finish()
+    desc = SB.scene_animated(64, 64, 8, frames=4, scene_time=1.0, animated_fov=True).finish()  # + CameraFov::Animated (camera.rs:134-141)
     g, o = api.Scene(desc), api.OracleScene(desc)
     kw = dict(sample_first=0, sample_count=4, seed=21)
     rng = np.random.default_rng(5)

@@ -218,3 +218,26 @@ def test_tr15_like_json_through_the_loader(trb):
     o.update_frame(20, 10.0, 10.5); y2 = o.transform(0)[0][1, 3]
     assert y0 == y1 == 12.0 and y2 == 10.0
     trb.trb_desc_free(d)
+
+
+def test_animated_fov_is_sampled_once_per_frame_at_the_clamped_midpoint():
+    """camera.rs:134-141: fov = spline.point(clamp((start + end) / 2, knot domain)); scaling = tan(fov / 2)."""
+    b = one_instance_scene([trs()], frames=10, scene_time=10.0)
+    b.cameras = []
+    b.add_camera([trs(t=(0, 0, -20))], fov=[20.0, 60.0], fov_knots=[2.0, 2.0, 6.0, 6.0], fov_degree=1, shutter_size=1.0)
+    o = api.OracleScene(b.finish())
+
+    def half_width(start, end):
+        o.update_frame(0, start, end)
+        rays, xy = o.camera_rays(seed=1)
+        # the image-space x of a sample maps linearly to d.x / d.z = tan(fov/2) * aspect * ndc: recover tan(fov/2) from one sample
+        k = int(np.argmax(xy[:, 0]))
+        d = rays["d"][k]
+        ndc = (xy[k, 0] / 16.0) * 2.0 - 1.0
+        return abs(d[0] / d[2]) / abs(ndc)
+
+    t20, t40, t60 = (math.tan(math.radians(f) / 2) for f in (20.0, 40.0, 60.0))
+    assert abs(half_width(0.0, 1.0) - t20) < 1e-4      # mid 0.5 clamps to the domain start (2.0) -> 20 degrees
+    assert abs(half_width(3.0, 5.0) - t40) < 1e-4      # mid 4.0 -> halfway -> 40 degrees
+    assert abs(half_width(3.9, 4.1) - t40) < 1e-4      # only the midpoint matters, not the shutter interval
+    assert abs(half_width(8.0, 9.0) - t60) < 1e-4      # clamps to the domain end

@@ -68,6 +68,28 @@ TRB_HD inline trb_keyframe spline_point(const trb_spline& sp, const trb_keyframe
     return tmp[0];
 }
 
+// BSpline<f32>::point (the camera's animated field of view, camera.rs:136-139): Interpolate for f32 is a * (1 - t) + b * t
+inline float spline_point_f32(uint32_t deg, const float* ctrl, const float* kn, uint32_t n, float t) {
+    uint32_t ub = n;
+    for (uint32_t i = 0; i < n; ++i) if (kn[i] > t) { ub = i; break; }
+    uint32_t i0;
+    if (ub == n) i0 = n - deg - 1;
+    else if (ub == 0) i0 = deg;
+    else if (ub >= n - deg - 1) i0 = n - deg - 1;
+    else i0 = ub;
+    float tmp[kMaxSplineDegree + 1];
+    for (uint32_t j = 0; j <= deg; ++j) tmp[j] = ctrl[j + i0 - deg - 1];
+    for (uint32_t lvl = 0; lvl < deg; ++lvl) {
+        const uint32_t k = lvl + 1;
+        for (uint32_t j = 0; j < deg - lvl; ++j) {
+            const uint32_t i = j + k + i0 - deg;
+            const float alpha = (t - kn[i - 1]) / (kn[i + deg - k] - kn[i - 1]);
+            tmp[j] = tmp[j] * (1.0f - alpha) + tmp[j + 1] * alpha;
+        }
+    }
+    return tmp[0];
+}
+
 TRB_HD inline Xf animated_xf(const trb_spline* splines, uint32_t first, uint32_t count, const trb_keyframe* kfs, const float* knots, float time) {
     Xf acc = xf_identity();
     for (uint32_t s = first; s < first + count; ++s) {

@@ -162,6 +162,7 @@ struct trb_scene {
     std::vector<trb_keyframe> keyframes;
     std::vector<float> knots;
     std::vector<trb_color_key> color_keys;
+    std::vector<float> fov_floats;
     std::vector<trb_material> materials;
     std::vector<HostMesh> meshes;
     uint32_t spp_pow2 = 1;
@@ -260,7 +261,11 @@ trb_status validate(const trb_scene_desc* d) {
     if (!light) return fail(TRB_INVALID_ARG, "At least one light is required"); // multithreaded.rs:39
     for (uint32_t i = 0; i < d->n_cameras; ++i) {
         const trb_camera& c = d->cameras[i];
-        if (c.n_fov_ctrl) return fail(TRB_UNSUPPORTED, "animated fov is not implemented (DESIGN.md: next)");
+        if (c.n_fov_ctrl) { // CameraFov::Animated (camera.rs:95-125)
+            if (c.fov_ctrl_first + c.n_fov_ctrl > d->n_fov_floats || c.fov_knot_first + c.n_fov_knots > d->n_fov_floats) return fail(TRB_INVALID_ARG, "fov spline out of bounds");
+            if (c.n_fov_knots != c.n_fov_ctrl + c.fov_degree + 1) return fail(TRB_INVALID_ARG, "Invalid B-spline: knots.len() != control_points.len() + degree + 1");
+            if (c.fov_degree > (uint32_t)trbh::kMaxSplineDegree) return fail(TRB_UNSUPPORTED, "B-spline degree above 5");
+        }
         if (c.spline_first + c.n_splines > d->n_splines) return fail(TRB_INVALID_ARG, "camera spline range out of bounds");
     }
     for (uint32_t i = 0; i < d->n_materials; ++i) {
@@ -473,6 +478,7 @@ trb_status trb_scene_create(const trb_scene_desc* d, int device, trb_scene** out
     s->keyframes.assign(d->keyframes, d->keyframes + d->n_keyframes);
     s->knots.assign(d->knots, d->knots + d->n_knots);
     s->color_keys.assign(d->color_keys, d->color_keys + d->n_color_keys);
+    if (d->n_fov_floats) s->fov_floats.assign(d->fov_floats, d->fov_floats + d->n_fov_floats);
     s->materials.assign(d->materials, d->materials + d->n_materials);
 
     // meshes: BVH<Triangle> with max_geom 16 (mesh.rs:44), then leaf-ordered triangle records
@@ -632,7 +638,15 @@ trb_status trb_scene_update_frame(trb_scene* s, uint32_t frame, float start, flo
     s->shutter_open = start;                                  // camera.rs:127-129
     s->shutter_close = start + c.shutter_size * (end - start);
     Mat4 px_to_cam; float scaling[3];
-    camera_setup(c.fov, s->film.width, s->film.height, px_to_cam, scaling);
+    float fov = c.fov;
+    if (c.n_fov_ctrl) { // sampled once per frame at the clamped mid-frame time (camera.rs:134-141)
+        const float* kn = s->fov_floats.data() + c.fov_knot_first;
+        const float lo = kn[c.fov_degree], hi = kn[c.n_fov_knots - 1 - c.fov_degree];
+        float t = (start + end) / 2.0f;
+        t = t < lo ? lo : (t > hi ? hi : t);
+        fov = trbh::spline_point_f32(c.fov_degree, s->fov_floats.data() + c.fov_ctrl_first, kn, c.n_fov_knots, t);
+    }
+    camera_setup(fov, s->film.width, s->film.height, px_to_cam, scaling);
     // cam_world.transform(frame_time): a keyframed camera is evaluated per ray on the device (camera.rs:156)
     const bool cam_static = trbh::xf_is_static(s->splines.data(), c.spline_first, c.n_splines);
     const Xf cam_world = trbh::animated_xf(s->splines.data(), c.spline_first, c.n_splines, s->keyframes.data(), s->knots.data(), s->shutter_open);

@@ -58,6 +58,7 @@ class SceneBuilder:
         self.integrator = (0, min_depth, max_depth)
         self.keyframes, self.knots, self.splines = [], [], []
         self.instances, self.color_keys, self.meshes, self.materials, self.merl, self.cameras = [], [], [], [], [], []
+        self.fov_floats = []
         self._keep = []
 
     # -- transforms ---------------------------------------------------------------------
@@ -125,9 +126,17 @@ class SceneBuilder:
     def point_light(self, xf, emission):
         return self.add_instance(F.INST_EMITTER_POINT, F.SHAPE_NONE, 0, xf, emission=emission)
 
-    def add_camera(self, xf, fov=30.0, shutter_size=0.5, active_at=0):
+    def add_camera(self, xf, fov=30.0, shutter_size=0.5, active_at=0, fov_knots=None, fov_degree=3):
+        """fov: degrees, or a list of B-spline control values with fov_knots / fov_degree (Camera::animated_fov, camera.rs:95-125)."""
         sf, ns = self._add_xf(xf)
-        self.cameras.append((sf, ns, float(fov), float(shutter_size), active_at))
+        if isinstance(fov, (list, tuple)):
+            knots = list(fov_knots) if fov_knots is not None else clamped_knots(len(fov), fov_degree)
+            assert len(knots) == len(fov) + fov_degree + 1
+            cf = len(self.fov_floats); self.fov_floats += [float(x) for x in fov]
+            kf = len(self.fov_floats); self.fov_floats += [float(x) for x in knots]
+            self.cameras.append((sf, ns, float(fov[0]), float(shutter_size), active_at, fov_degree, len(fov), cf, len(knots), kf))
+        else:
+            self.cameras.append((sf, ns, float(fov), float(shutter_size), active_at, 0, 0, 0, 0, 0))
 
     # -- finish ---------------------------------------------------------------------------
     def finish(self):
@@ -180,9 +189,11 @@ class SceneBuilder:
         d.merl_tables = mt; d.n_merl = len(self.merl)
 
         def cam(o, it):
-            o.spline_first, o.n_splines, o.fov, o.shutter_size, o.active_at = it
+            (o.spline_first, o.n_splines, o.fov, o.shutter_size, o.active_at, o.fov_degree, o.n_fov_ctrl, o.fov_ctrl_first, o.n_fov_knots,
+             o.fov_knot_first) = it
         d.cameras = arr(F.Camera, self.cameras, cam); d.n_cameras = len(self.cameras)
-        d.n_fov_floats = 0
+        ff = (F.f32 * max(1, len(self.fov_floats)))(*self.fov_floats); keep.append(ff)
+        d.fov_floats = ff; d.n_fov_floats = len(self.fov_floats)
         d._keep = keep
         return d
 
@@ -318,7 +329,7 @@ def scene_smallpt_like(width=512, height=512, spp=1024):
     return b
 
 
-def scene_animated(width=64, height=64, spp=8, frames=4, scene_time=1.0):
+def scene_animated(width=64, height=64, spp=8, frames=4, scene_time=1.0, animated_fov=False):
     """Small keyframed scene (the tr15 feature set): B-spline animated receivers (one- and two-level
     stacks), a moving area light with keyframed emission, a moving point light and a keyframed camera."""
     b = SceneBuilder(width, height, spp, 2, 6)
@@ -346,7 +357,7 @@ def scene_animated(width=64, height=64, spp=8, frames=4, scene_time=1.0):
     b.area_light(F.SHAPE_RECT, mats["white"], [trs(t=(0, 23.9, 8), q=quat_axis_angle((1, 0, 0), 90))], (1, 1, 1, 8), p0=6.0, p1=4.0)
     b.point_light([Anim([trs(t=(-10, 15, -12)), trs(t=(10, 18, -10))], degree=1)], [((1, 1, 1, 120), 0.2), ((1, 0.5, 0.5, 60), 0.8)])
     b.add_camera([Anim([trs(t=(-3, 12, -60)), trs(t=(0, 13, -58), q=quat_axis_angle((0, 1, 0), 3)), trs(t=(4, 12, -60), q=quat_axis_angle((0, 1, 0), -4))],
-                       degree=2)], fov=30.0, shutter_size=0.5)
+                       degree=2)], fov=[28.0, 34.0, 30.0, 26.0] if animated_fov else 30.0, fov_degree=2, shutter_size=0.5)
     return b
 
 
