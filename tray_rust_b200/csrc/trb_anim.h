@@ -90,12 +90,15 @@ inline float spline_point_f32(uint32_t deg, const float* ctrl, const float* kn, 
     return tmp[0];
 }
 
-TRB_HD inline Xf animated_xf(const trb_spline* splines, uint32_t first, uint32_t count, const trb_keyframe* kfs, const float* knots, float time) {
+// `level_xf` (optional): Keyframe::transform of every one-control-point level, computed once per scene with the same
+// operations (time-independent, so exact re-use): a keyframed stack usually mixes static and animated levels.
+TRB_HD inline Xf animated_xf(const trb_spline* splines, uint32_t first, uint32_t count, const trb_keyframe* kfs, const float* knots, float time,
+                             const Xf* level_xf = nullptr) {
     Xf acc = xf_identity();
     for (uint32_t s = first; s < first + count; ++s) {
         const trb_spline& sp = splines[s];
         Xf t;
-        if (sp.n_ctrl == 1) t = keyframe_xf(kfs[sp.ctrl_first]);
+        if (sp.n_ctrl == 1) t = level_xf ? level_xf[s] : keyframe_xf(kfs[sp.ctrl_first]);
         else {
             const float lo = knots[sp.knot_first + sp.degree], hi = knots[sp.knot_first + sp.n_knots - 1 - sp.degree];
             t = keyframe_xf(spline_point(sp, kfs, knots, clampf_hd(time, lo, hi)));

@@ -598,7 +598,12 @@ trb_status trb_scene_create(const trb_scene_desc* d, int device, trb_scene** out
         if (!s->keyframes.empty()) CU(s->arena.upload(s->keyframes.data(), s->keyframes.size(), &d_kf));
         if (!s->knots.empty()) CU(s->arena.upload(s->knots.data(), s->knots.size(), &d_kn));
         if (!s->color_keys.empty()) CU(s->arena.upload(s->color_keys.data(), s->color_keys.size(), &d_ck));
-        ds.splines = d_sp; ds.keyframes = d_kf; ds.knots = d_kn; ds.color_keys = d_ck; ds.has_anim = 0;
+        std::vector<Xf> level(s->splines.size(), xf_identity());
+        for (size_t k = 0; k < s->splines.size(); ++k)
+            if (s->splines[k].n_ctrl == 1) level[k] = keyframe_xf(s->keyframes[s->splines[k].ctrl_first]);
+        Xf* d_lv = nullptr;
+        if (!level.empty()) CU(s->arena.upload(level.data(), level.size(), &d_lv));
+        ds.splines = d_sp; ds.keyframes = d_kf; ds.knots = d_kn; ds.color_keys = d_ck; ds.level_xf = d_lv; ds.has_anim = 0;
     }
     // Scene::load_file builds the BVH<Instance> for [0, scene_time] (scene.rs:141); the first render rebuilds it
     *out = s.release();

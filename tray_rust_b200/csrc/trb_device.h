@@ -4,6 +4,7 @@
 #include <cstdint>
 #include <cuda_runtime.h>
 #include "../../include/trb.h"
+#include "trb_host.h" // trbh::Xf (host+device math shared with the per-frame host code)
 
 namespace trb {
 
@@ -128,6 +129,7 @@ struct DScene {
     const trb_keyframe* keyframes;
     const float* knots;
     const trb_color_key* color_keys;
+    const trbh::Xf* level_xf; // per spline: Keyframe::transform of a one-control-point level (else unused)
     uint32_t has_anim; // any instance / camera / emission depends on time
 };
 

@@ -202,7 +202,7 @@ __device__ __forceinline__ void load_xf(const float* __restrict__ src, float* ds
 // AnimatedTransform::transform(ray.time) of a keyframed instance: the reference recomposes it per ray per instance
 // (receiver.rs:30, emitter.rs:122,176,197); static instances use the matrices prepared by update_frame.
 __device__ __noinline__ void eval_anim_xf(const DScene& sc, uint32_t first, uint32_t n, float time, float* inv16, float* mat16) {
-    const trbh::Xf x = trbh::animated_xf(sc.splines, first, n, sc.keyframes, sc.knots, time);
+    const trbh::Xf x = trbh::animated_xf(sc.splines, first, n, sc.keyframes, sc.knots, time, sc.level_xf);
 #pragma unroll
     for (int i = 0; i < 16; ++i) { inv16[i] = x.inv.m[i]; if (mat16) mat16[i] = x.fwd.m[i]; }
 }
