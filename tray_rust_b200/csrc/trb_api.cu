@@ -4,6 +4,7 @@
 #include <cstdio>
 #include <cstdlib>
 #include <memory>
+#include <thread>
 #include "trb_host.h"
 #include "trb_kernels.cuh"
 
@@ -765,7 +766,16 @@ trb_status trb_render(trb_scene* s, const trb_render_cfg* cfg, float* film, trb_
     CU(cudaStreamSynchronize(0));
     r = check_error_flag(s);
     if (r != TRB_OK) return r;
-    for (size_t i = 0; i < npx * 4; ++i) film[i] += s->h_film_staging[i]; // additive, like film::Image::add_pixels (image.rs:21-33)
+    { // additive, like film::Image::add_pixels (image.rs:21-33); a 33 MB read-modify-write: split over a few host threads
+        const size_t n = npx * 4;
+        const unsigned nt = n >= (1u << 20) ? std::min(8u, std::max(1u, std::thread::hardware_concurrency())) : 1u;
+        const float* src = s->h_film_staging;
+        auto add = [film, src](size_t a, size_t b) { for (size_t i = a; i < b; ++i) film[i] += src[i]; };
+        std::vector<std::thread> th;
+        for (unsigned k = 1; k < nt; ++k) th.emplace_back(add, n * k / nt, n * (k + 1) / nt);
+        add(0, n / nt);
+        for (auto& t : th) t.join();
+    }
     if (stats) {
         trb::DStats h;
         CU(cudaMemcpy(&h, s->d_stats, sizeof h, cudaMemcpyDeviceToHost));

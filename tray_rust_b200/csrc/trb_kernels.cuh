@@ -425,23 +425,15 @@ __device__ __forceinline__ void trace_step(const DScene& sc, TraceState& t, cons
 // The same state machine cut into three kinds of micro-step so that a warp can run them in PHASES
 // (k_wf_trace, PHASED): per ray the sequence of operations — and therefore hits, t and the test
 // counters — is exactly trace_step's; only *when* a lane takes its next micro-step changes.
-//   class A  node work: one child-pair visit, or pop attempts            (~64 per ray on C4)
-//   class B  one triangle of a mesh leaf                                  (~4.5 per ray)
-//   class C  everything else: level root box, TLAS leaf, instance entry, mesh return (~6 per ray)
-// In the flat loop a warp executes A, B and C code every iteration with whatever lanes are in that
+//   node      one child-pair visit, or pop attempts                       (~64 per ray on C4)   step_nodes
+//   triangle  one triangle of a mesh leaf                                  (~4.5 per ray)        step_triangle
+//   other     level root box, TLAS leaf, instance entry, mesh return       (~6 per ray)          step_other
+// In the flat loop a warp executes all three kinds of code every iteration with whatever lanes are in that
 // state: ncu showed the triangle code running with 2.2 of 32 lanes and the pop loop with 4.
 // ------------------------------------------------------------------------------------------
 constexpr uint32_t ST_POP = 0xfffffffcu; // control: take the next reference off the stack
 constexpr int WF_BURST = 3;
 __device__ __forceinline__ bool trace_is_node(uint32_t cur) { return (cur & REF_TAG) == REF_INTERIOR || cur == ST_POP; }
-__device__ __forceinline__ int trace_class(const TraceState& t) {
-    const uint32_t cur = t.cur;
-    if (cur == ST_DONE) return 0;
-    const uint32_t tag = cur & REF_TAG;
-    if (tag == REF_INTERIOR || cur == ST_POP) return 1;
-    if (tag == REF_LEAF && t.level_inst != TRB_MISS) return 2;
-    return 3;
-}
 template <bool STATS, bool QUADS, class Stack>
 __device__ __forceinline__ void step_nodes(TraceState& t, const Stack& stack, Cnt& cnt, int* err) {
     uint32_t cur = t.cur;

@@ -17,5 +17,10 @@ def smoke():
     ig = gf[..., :3] / np.maximum(gf[..., 3:], 1e-6); io = of[..., :3] / np.maximum(of[..., 3:], 1e-6)
     rmse = float(np.sqrt(np.mean((ig - io) ** 2)))
     assert rmse < 1e-5, rmse
-    print("smoke ok: %d camera samples bit-exact vs oracle, film rmse %.2e, %d rays, kernel %.2f ms"
-          % (len(gs), rmse, st.rays_total(), st.kernel_ms))
+    # the keyframed kernel variants (per-ray AnimatedTransform evaluation) on one frame of a small animated scene
+    desc2 = SB.scene_animated(32, 32, 2, animated_fov=True).finish()
+    g2, o2 = api.Scene(desc2, 0), api.OracleScene(desc2)
+    g2.update_frame(1, 0.25, 0.5); o2.update_frame(1, 0.25, 0.5)
+    assert g2.render_samples(seed=5)[0].tobytes() == o2.render_samples(seed=5)[0].tobytes(), "keyframed scene differs from the oracle"
+    print("smoke ok: %d camera samples bit-exact vs oracle (+ %d of a keyframed scene), film rmse %.2e, %d rays, kernel %.2f ms"
+          % (len(gs), 32 * 32 * 2, rmse, st.rays_total(), st.kernel_ms))
