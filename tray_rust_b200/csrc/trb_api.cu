@@ -401,7 +401,9 @@ trb_status launch_wavefront(trb_scene* s, const trb::RenderParams& rp, uint32_t 
     if (mode == 0) {
         const int T = 9 + 2 * std::max(s->ds.fpw_x, s->ds.fpw_y);
         const unsigned film_grid = std::min<unsigned>(rp.n_blocks, (unsigned)s->sm_count * 8);
-        trb::k_wf_film<<<film_grid, trb::RENDER_THREADS, (size_t)T * T * sizeof(float4), st>>>(s->ds, rp, wf);
+        const bool film_v2 = getenv("TRB_FILM_V2") && atoi(getenv("TRB_FILM_V2")) != 0; // opt-in until measured (tools/film_check.py)
+        if (film_v2) trb::k_wf_film_v2<<<film_grid, trb::RENDER_THREADS, (size_t)4 * T * T * sizeof(float4), st>>>(s->ds, rp, wf);
+        else trb::k_wf_film<<<film_grid, trb::RENDER_THREADS, (size_t)T * T * sizeof(float4), st>>>(s->ds, rp, wf);
         g_launches++;
     }
     CU(cudaGetLastError());

@@ -1779,6 +1779,69 @@ __global__ void __launch_bounds__(RENDER_THREADS) k_wf_film(const __grid_constan
 }
 
 // LowDiscrepancy::get_samples + get_samples_1d + Camera::generate_ray only (parity of S2 / C)
+// k_wf_film without shared-memory atomics (opt-in: TRB_FILM_V2=1; validated by tools/film_check.py). Each of the CTA's
+// four warps splats into its OWN copy of the tile. Inside a warp the 32 lanes are 32 different pixels walking the footprint
+// in lockstep (same (dy, dx) offset at the same time, __syncwarp per offset), so their targets are always 32 different tile
+// pixels and a plain 16-byte read-modify-write is race-free; the four copies are summed at the flush. Same weights and
+// products as RenderTarget::write; only the order of the float additions differs (the film bar is an RMSE tolerance).
+__global__ void __launch_bounds__(RENDER_THREADS) k_wf_film_v2(const __grid_constant__ DScene sc, const __grid_constant__ RenderParams rp, const __grid_constant__ WfState wf) {
+    extern __shared__ float4 tiles[]; // 4 x T*T
+    __shared__ float s_table[256];
+    const int T = 9 + 2 * max(sc.fpw_x, sc.fpw_y);
+    for (int i = threadIdx.x; i < 256; i += RENDER_THREADS) s_table[i] = sc.filter_table[i];
+    const uint32_t pix = threadIdx.x & 63, lane_s = threadIdx.x >> 6;
+    float4* mine = tiles + (threadIdx.x >> 5) * (T * T);
+    const int ry = (int)ceilf(sc.filter_h / sc.filter_inv_h) + 1, rx = (int)ceilf(sc.filter_w / sc.filter_inv_w) + 1;
+    for (uint32_t item = blockIdx.x; item < rp.n_blocks; item += gridDim.x) {
+        __syncthreads();
+        for (int i = threadIdx.x; i < 4 * T * T; i += RENDER_THREADS) tiles[i] = make_float4(0.f, 0.f, 0.f, 0.f);
+        __syncthreads();
+        const uint2 blk = rp.blocks[item];
+        const uint32_t bx = blk.x * 8, by = blk.y * 8;
+        SampleId id; id.item = item; id.pix = pix; id.px = bx + (pix & 7); id.py = by + (pix >> 3); id.pixel = id.py * sc.width + id.px;
+        const PixelStreams ps = pixel_streams(rp.seed, id.pixel);
+        const int x_lo = max((int)bx - sc.fpw_x, 0), x_hi = min((int)bx + 8 + sc.fpw_x, (int)sc.width - 1);
+        const int y_lo = max((int)by - sc.fpw_y, 0), y_hi = min((int)by + 8 + sc.fpw_y, (int)sc.height - 1);
+        const int tx0 = (int)bx - sc.fpw_x, ty0 = (int)by - sc.fpw_y;
+        for (uint32_t s = lane_s; s < rp.sample_count; s += 2) { // uniform trip count inside a warp (one lane_s per warp)
+            id.si = rp.sample_first + s;
+            float sx, sy, tm;
+            sample_position(rp, ps, id, sx, sy, tm);
+            const float4 c4 = wf.rad[((size_t)item * 64 + pix) * rp.sample_count + s];
+            const float img_x = sx - 0.5f, img_y = sy - 0.5f;
+            for (int dy = -ry; dy <= ry + 1; ++dy) {
+                const int iy = (int)id.py + dy;
+                const float fy = fabsf((float)iy - img_y) * sc.filter_inv_h;
+                const bool vy = iy >= y_lo && iy <= y_hi && !(fy > sc.filter_h); // sic: normalised distance vs width (A7)
+                const uint32_t fyi = min(f2u(fy * 16.0f), 15u);
+                for (int dx = -rx; dx <= rx + 1; ++dx) {
+                    const int ix = (int)id.px + dx;
+                    const float fx = fabsf((float)ix - img_x) * sc.filter_inv_w;
+                    if (vy && ix >= x_lo && ix <= x_hi && !(fx > sc.filter_w)) {
+                        const uint32_t fxi = min(f2u(fx * 16.0f), 15u);
+                        const float wgt = s_table[fyi * 16 + fxi];
+                        float4* t = &mine[(iy - ty0) * T + (ix - tx0)];
+                        float4 a = *t;
+                        a.x += wgt * c4.x; a.y += wgt * c4.y; a.z += wgt * c4.z; a.w += wgt;
+                        *t = a;
+                    }
+                    __syncwarp(); // lockstep per offset: no lane starts (dy, dx + 1) before all finished (dy, dx)
+                }
+            }
+        }
+        __syncthreads();
+        for (int i = threadIdx.x; i < T * T; i += RENDER_THREADS) {
+            const int ix = tx0 + i % T, iy = ty0 + i / T;
+            if (ix < x_lo || ix > x_hi || iy < y_lo || iy > y_hi) continue;
+            const float4 a = tiles[i], b = tiles[T * T + i], c = tiles[2 * T * T + i], d = tiles[3 * T * T + i];
+            const float4 v = make_float4((a.x + b.x) + (c.x + d.x), (a.y + b.y) + (c.y + d.y), (a.z + b.z) + (c.z + d.z), (a.w + b.w) + (c.w + d.w));
+            if (v.w == 0.0f && v.x == 0.0f && v.y == 0.0f && v.z == 0.0f) continue;
+            float* dst = reinterpret_cast<float*>(rp.film + (size_t)iy * sc.width + ix);
+            atomicAdd(dst + 0, v.x); atomicAdd(dst + 1, v.y); atomicAdd(dst + 2, v.z); atomicAdd(dst + 3, v.w);
+        }
+    }
+}
+
 template <bool ANIM>
 __global__ void k_camera_rays(const __grid_constant__ DScene sc, const __grid_constant__ RenderParams rp, trb_ray* rays, float* xy) {
     const size_t n = (size_t)rp.n_blocks * 64 * rp.sample_count;
