@@ -401,7 +401,7 @@ trb_status launch_wavefront(trb_scene* s, const trb::RenderParams& rp, uint32_t 
     if (mode == 0) {
         const int T = 9 + 2 * std::max(s->ds.fpw_x, s->ds.fpw_y);
         const unsigned film_grid = std::min<unsigned>(rp.n_blocks, (unsigned)s->sm_count * 8);
-        const bool film_v2 = getenv("TRB_FILM_V2") && atoi(getenv("TRB_FILM_V2")) != 0; // opt-in until measured (tools/film_check.py)
+        const bool film_v2 = !(getenv("TRB_FILM_V2") && atoi(getenv("TRB_FILM_V2")) == 0); // TRB_FILM_V2=0: the shared-atomics kernel (profiles/r01_film_v2_check.json)
         if (film_v2) trb::k_wf_film_v2<<<film_grid, trb::RENDER_THREADS, (size_t)4 * T * T * sizeof(float4), st>>>(s->ds, rp, wf);
         else trb::k_wf_film<<<film_grid, trb::RENDER_THREADS, (size_t)T * T * sizeof(float4), st>>>(s->ds, rp, wf);
         g_launches++;
@@ -594,6 +594,8 @@ trb_status trb_scene_create(const trb_scene_desc* d, int device, trb_scene** out
     ds.filter_w = d->film.filter_w; ds.filter_h = d->film.filter_h;
     ds.filter_inv_w = 1.0f / d->film.filter_w; ds.filter_inv_h = 1.0f / d->film.filter_h;
     ds.fpw_x = (int)floorf(d->film.filter_w / 0.5f); ds.fpw_y = (int)floorf(d->film.filter_h / 0.5f); // render_target.rs:48-49
+    // the per-pixel test accepts |d| <= w / inv_w; the lock-block filter of render_target.rs:104-109 can only reject beyond fpw - 0.5
+    ds.film_block_filter = (d->film.filter_w / ds.filter_inv_w <= (float)ds.fpw_x && d->film.filter_h / ds.filter_inv_h <= (float)ds.fpw_y) ? 0u : 1u;
     ds.filter_table = d_table;
     { // animation tables (evaluated per ray for keyframed instances / camera / emission)
         trb_spline* d_sp = nullptr; trb_keyframe* d_kf = nullptr; float* d_kn = nullptr; trb_color_key* d_ck = nullptr;

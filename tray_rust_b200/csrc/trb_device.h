@@ -123,6 +123,7 @@ struct DScene {
     // film filter (render_target.rs:41-75)
     float filter_w, filter_h, filter_inv_w, filter_inv_h;
     int fpw_x, fpw_y;
+    uint32_t film_block_filter; // the 2x2 lock-block sample filter of RenderTarget::write can reject (wide filters only)
     const float* filter_table; // 256 floats
     // animation: the AnimatedTransform / AnimatedColor tables of the scene description, evaluated per ray
     const trb_spline* splines;

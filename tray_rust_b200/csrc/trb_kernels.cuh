@@ -1352,6 +1352,15 @@ __device__ __forceinline__ void flush_stats(DStats* st, const RayCounts& rc, con
 }
 
 // RenderTarget::write for one sample (render_target.rs:117-148) into the block's shared-memory tile
+// RenderTarget::write hands a sample to a 2x2 lock block only if it lies within filter_pixel_width of the block's write
+// range (render_target.rs:104-109) — on top of the per-pixel distance test. For the filters the reference's scenes use
+// (reach width/inv_width <= filter_pixel_width) this never rejects and DScene::film_block_filter is 0.
+__device__ __forceinline__ bool lock_block_takes(float s, int i, int lo, int hi, int fpw) {
+    const int b0 = (i >> 1) << 1; // lock_size = (2, 2)
+    const int w0 = max(lo, b0), w1 = min(hi + 1, b0 + 2);
+    return s >= (float)(w0 - fpw) && s < (float)(w1 + fpw);
+}
+
 __device__ __forceinline__ void splat_sample(const DScene& sc, float4* tile, const float* s_table, int T, int tx0, int ty0, int x_lo, int x_hi, int y_lo,
                                              int y_hi, uint32_t px, uint32_t py, float sx, float sy, f3 c) {
     const float img_x = sx - 0.5f, img_y = sy - 0.5f;
@@ -1362,10 +1371,12 @@ __device__ __forceinline__ void splat_sample(const DScene& sc, float4* tile, con
     for (int iy = iy0; iy <= iy1; ++iy) {
         const float fy = fabsf((float)iy - img_y) * sc.filter_inv_h;
         if (fy > sc.filter_h) continue; // sic: normalised distance vs width (A7)
+        if (sc.film_block_filter && !lock_block_takes(sy, iy, y_lo, y_hi, sc.fpw_y)) continue;
         const uint32_t fyi = min(f2u(fy * 16.0f), 15u);
         for (int ix = ix0; ix <= ix1; ++ix) {
             const float fx = fabsf((float)ix - img_x) * sc.filter_inv_w;
             if (fx > sc.filter_w) continue;
+            if (sc.film_block_filter && !lock_block_takes(sx, ix, x_lo, x_hi, sc.fpw_x)) continue;
             const uint32_t fxi = min(f2u(fx * 16.0f), 15u);
             const float wgt = s_table[fyi * 16 + fxi];
             float* t = reinterpret_cast<float*>(&tile[(iy - ty0) * T + (ix - tx0)]);
@@ -1812,12 +1823,13 @@ __global__ void __launch_bounds__(RENDER_THREADS) k_wf_film_v2(const __grid_cons
             for (int dy = -ry; dy <= ry + 1; ++dy) {
                 const int iy = (int)id.py + dy;
                 const float fy = fabsf((float)iy - img_y) * sc.filter_inv_h;
-                const bool vy = iy >= y_lo && iy <= y_hi && !(fy > sc.filter_h); // sic: normalised distance vs width (A7)
+                const bool vy = iy >= y_lo && iy <= y_hi && !(fy > sc.filter_h) && // sic: normalised distance vs width (A7)
+                                (!sc.film_block_filter || lock_block_takes(sy, iy, y_lo, y_hi, sc.fpw_y));
                 const uint32_t fyi = min(f2u(fy * 16.0f), 15u);
                 for (int dx = -rx; dx <= rx + 1; ++dx) {
                     const int ix = (int)id.px + dx;
                     const float fx = fabsf((float)ix - img_x) * sc.filter_inv_w;
-                    if (vy && ix >= x_lo && ix <= x_hi && !(fx > sc.filter_w)) {
+                    if (vy && ix >= x_lo && ix <= x_hi && !(fx > sc.filter_w) && (!sc.film_block_filter || lock_block_takes(sx, ix, x_lo, x_hi, sc.fpw_x))) {
                         const uint32_t fxi = min(f2u(fx * 16.0f), 15u);
                         const float wgt = s_table[fyi * 16 + fxi];
                         float4* t = &mine[(iy - ty0) * T + (ix - tx0)];
