@@ -214,7 +214,6 @@ def test_film_kernels_agree():
     assert np.allclose(f1, f2, rtol=1e-4, atol=1e-5) and np.allclose(f1[..., 3], f2[..., 3], rtol=1e-5, atol=1e-6)
 
 
-@pytest.mark.xfail(strict=False, reason="wide-filter lock-block rule (render_target.rs:104-109) added after the last GPU slot of round 1: not yet run on a GPU")
 def test_wide_gaussian_filter_film_vs_oracle():
     """A filter whose reach (width / inv_width = 9 px) exceeds filter_pixel_width (6): RenderTarget::write's per-2x2-block sample
     filter rejects contributions the per-pixel distance test would accept. No scene of the reference uses such a filter."""
