@@ -241,3 +241,33 @@ def test_animated_fov_is_sampled_once_per_frame_at_the_clamped_midpoint():
     assert abs(half_width(3.0, 5.0) - t40) < 1e-4      # mid 4.0 -> halfway -> 40 degrees
     assert abs(half_width(3.9, 4.1) - t40) < 1e-4      # only the midpoint matters, not the shutter interval
     assert abs(half_width(8.0, 9.0) - t60) < 1e-4      # clamps to the domain end
+
+
+def test_invalid_splines_are_rejected_like_bspline_new(trb):
+    """BSpline::new asserts knots.len() == control_points.len() + degree + 1 (bspline 0.2.2); the C ABI returns
+    TRB_INVALID_ARG with that message instead of aborting; degrees above the device evaluator's cap are TRB_UNSUPPORTED."""
+    import ctypes as C
+    m, inv = np.zeros(16, np.float32), np.zeros(16, np.float32)
+
+    def status(b):
+        d = b.finish()
+        rc = trb.trb_host_animated_transform(C.byref(d), 0, 1, 0.5, F.ptr(m), F.ptr(inv))
+        return rc, (trb.trb_last_error() or b"").decode()
+
+    ok = one_instance_scene([Anim([trs(), trs(t=(1, 0, 0))], degree=1)])
+    assert status(ok)[0] == F.TRB_OK
+    bad = one_instance_scene([Anim([trs(), trs(t=(1, 0, 0))], degree=1)])
+    bad.splines[0] = (1, 2, bad.splines[0][2], 3, bad.splines[0][4])          # 3 knots for 2 control points of degree 1
+    rc, msg = status(bad)
+    assert rc == F.TRB_INVALID_ARG and "knots.len() != control_points.len() + degree + 1" in msg
+    deep = one_instance_scene([Anim([trs(t=(k, 0, 0)) for k in range(8)], degree=6)])
+    rc, msg = status(deep)
+    assert rc == F.TRB_UNSUPPORTED and "degree" in msg
+    # the same rules for the camera's field-of-view spline
+    cam = one_instance_scene([trs()])
+    cam.cameras = []
+    cam.add_camera([trs(t=(0, 0, -20))], fov=[20.0, 60.0], fov_knots=[0.0, 0.0, 1.0, 1.0], fov_degree=1)
+    assert status(cam)[0] == F.TRB_OK
+    c = list(cam.cameras[0]); c[8] = 3; cam.cameras[0] = tuple(c)                # n_fov_knots 3 instead of 4
+    rc, msg = status(cam)
+    assert rc == F.TRB_INVALID_ARG and "knots.len()" in msg
