@@ -106,9 +106,10 @@ def build_scene_desc(a):
 def cpu_baseline(a, desc, threads=None):
     """The oracle port (kind "port": the Rust reference cannot be built here) on the host cores, baseline mode
     (per-ray transform recomposition like the reference), on a bounded sample of the same workload."""
-    from tray_rust_b200 import api, _ffi as F
+    from tray_rust_b200 import _ffi as F
+    from oracle import pyoracle as O   # the CPU arm: the one place besides tests/smoke that may execute oracle/
     threads = threads or host_threads()
-    o = api.OracleScene(desc, "det", baseline=True)
+    o = O.OracleScene(desc, "det", baseline=True)
     o.update_frame(0, 0.0, 0.0)
     nb = o.n_blocks()
     rng = np.random.default_rng(0)
@@ -138,9 +139,10 @@ def run_reference(a):
     rank = int(os.environ.get("RANK", "0"))
     if rank != 0:
         return
-    from tray_rust_b200 import api, _ffi as F
+    from tray_rust_b200 import _ffi as F
+    from oracle import pyoracle as O   # --impl reference: the oracle port is the timed CPU implementation of the path
     desc = build_scene_desc(a)
-    o = api.OracleScene(desc, "det", baseline=True)
+    o = O.OracleScene(desc, "det", baseline=True)
     o.update_frame(0, 0.0, 0.0)
     nb = o.n_blocks()
     cores = host_threads()

@@ -280,16 +280,25 @@ trb_status trb_scene_update_frame(trb_scene* scene, uint32_t frame, float start,
 /* -- the hot path ------------------------------------------------------------------ */
 
 /* ≙ Exec::render (exec/mod.rs:48; multithreaded.rs:55-70). Renders the selected
- * blocks/samples on the scene's GPU and ADDS the RGBW film (row-major, width*height*4
- * floats, layout of get_renderf32 render_target.rs:243-265) into the HOST buffer
- * `film_rgbw` — additive like film::Image::add_pixels (film/image.rs:21-33).
- * Includes update_frame unless TRB_RENDER_NO_UPDATE. Blocking. */
+ * blocks at the selected samples — with sample_count = 0 the WHOLE spp of the frame,
+ * like MultiThreaded::render — on the scene's GPU and ADDS the RGBW film (row-major,
+ * width*height*4 floats, layout of get_renderf32 render_target.rs:243-265) into the
+ * HOST buffer `film_rgbw` — additive like film::Image::add_pixels (film/image.rs:21-33).
+ * Internally the frame is rendered in additive passes sized to the free device memory
+ * (212 B of path state per camera sample in flight); the film is accumulated on the
+ * device and copied to the host once. Includes update_frame unless
+ * TRB_RENDER_NO_UPDATE. Blocking. */
 trb_status trb_render(trb_scene* scene, const trb_render_cfg* cfg, float* film_rgbw, trb_stats* stats);
 
 /* Same, but the film is a DEVICE buffer on the scene's GPU (accumulated into), and the
  * work is enqueued on `cuda_stream` (a cudaStream_t; NULL = default stream) without
  * host synchronisation. Never calls update_frame. `stats` (may be NULL) is a DEVICE
- * pointer to a trb_stats the kernels accumulate ray counters into. */
+ * pointer to a trb_stats the kernels accumulate ray counters into.
+ * Synchronisation contract: passes of one scene must be enqueued on ONE stream at a time
+ * (they share the scene's path-state buffers); trb_scene_update_frame drains the device
+ * before it touches the instance / TLAS buffers; a traversal-stack overflow (the reference
+ * panics) is latched on the device and reported by trb_scene_check_error or by the next
+ * host-buffer call (trb_render / trb_intersect / trb_render_samples). */
 trb_status trb_render_device(trb_scene* scene, const trb_render_cfg* cfg, float* d_film_rgbw,
                              trb_stats* d_stats, void* cuda_stream);
 
@@ -363,6 +372,17 @@ trb_status trb_host_animated_color(const trb_scene_desc* desc, uint32_t first, u
 trb_status trb_desc_load_json(const char* path, uint32_t width, uint32_t height, uint32_t spp,
                               trb_scene_desc** out);
 void trb_desc_free(trb_scene_desc* desc);
+
+/* Drains the scene's device and reports a latched traversal-stack overflow of passes enqueued with
+ * trb_render_device / trb_intersect_device (TRB_CUDA), else TRB_OK. */
+trb_status trb_scene_check_error(trb_scene* scene);
+
+/* Launch-shape options of the wavefront pipeline (results never depend on them; DESIGN.md "Options"):
+ * "pass.paths" camera samples per pass, "sort.mode" 0/1 ray-queue sorting, "sort.bits", "sort.min_round",
+ * "shade.split" 0/1, "pass.graph" 0/1, "film.v2" 0/1, "trace.refill", "trace.occupancy", "trace.grid",
+ * "trace.smem_stack", "trace.sched", "trace.quads". Defaults can also be preset by TRB_* environment
+ * variables, read once by trb_scene_create. */
+trb_status trb_scene_set_option(trb_scene* scene, const char* name, long long value);
 
 /* Device time spent in the dominant kernel (k_wf_trace) by launches made with TRB_RENDER_TIME_TRACE since the last
  * call, measured with CUDA events on the launching stream; synchronises those events. */

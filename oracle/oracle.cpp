@@ -19,6 +19,7 @@
  */
 #include "../include/trb.h"
 #include "orc_shade.h"
+#include <algorithm>
 #include <cstring>
 #include <cstdio>
 #include <string>
@@ -266,6 +267,7 @@ static AnimatedTransform load_xf(const trb_scene_desc* d, uint32_t first, uint32
             o.ctrl.push_back(kk);
         }
         for (uint32_t k = 0; k < sp.n_knots; ++k) o.knots.push_back(d->knots[sp.knot_first + k]);
+        std::stable_sort(o.knots.begin(), o.knots.end()); /* BSpline::new sorts the knots (bspline 0.2.2: knots.sort_by(partial_cmp)) */
         at.keyframes.push_back(o);
     }
     return at;
@@ -337,6 +339,7 @@ int orc_scene_create(const trb_scene_desc* d, orc_scene** out) {
             cam.fov_animated = true; cam.fov_degree = tc.fov_degree;
             cam.fovs.assign(d->fov_floats + tc.fov_ctrl_first, d->fov_floats + tc.fov_ctrl_first + tc.n_fov_ctrl);
             cam.fov_knots.assign(d->fov_floats + tc.fov_knot_first, d->fov_floats + tc.fov_knot_first + tc.n_fov_knots);
+            std::stable_sort(cam.fov_knots.begin(), cam.fov_knots.end()); /* BSpline::new sorts the knots */
             if (cam.fov_knots.size() != cam.fovs.size() + cam.fov_degree + 1) { delete s; g_err = "Invalid B-spline: knots.len() != control_points.len() + degree + 1"; return TRB_INVALID_ARG; }
             cam.init(cam.fovs[0], d->film.width, d->film.height);
         } else cam.init(tc.fov, d->film.width, d->film.height);

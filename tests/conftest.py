@@ -18,14 +18,14 @@ def pytest_configure(config):
 
 @pytest.fixture(scope="session")
 def oracle():
-    from tray_rust_b200 import _ffi
-    return _ffi.load_oracle("det")
+    from oracle import pyoracle as O
+    return O.load_oracle("det")
 
 
 @pytest.fixture(scope="session")
 def oracle_sys():
-    from tray_rust_b200 import _ffi
-    return _ffi.load_oracle("sys")
+    from oracle import pyoracle as O
+    return O.load_oracle("sys")
 
 
 @pytest.fixture(scope="session")

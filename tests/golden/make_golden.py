@@ -10,6 +10,7 @@ import numpy as np
 HERE = os.path.dirname(os.path.abspath(__file__))
 sys.path.insert(0, os.path.dirname(os.path.dirname(HERE)))
 from tray_rust_b200 import _ffi as F, api, scenebuild as SB  # noqa: E402
+from oracle import pyoracle as O  # noqa: E402
 
 
 def golden_scenes():
@@ -57,7 +58,7 @@ def frame_of(name):
 
 if __name__ == "__main__":
     for name, (mk, kw) in golden_scenes().items():
-        o = api.OracleScene(mk())
+        o = O.OracleScene(mk())
         o.update_frame(*frame_of(name))
         rays, xy = o.camera_rays(**kw)
         hits, hst = o.intersect(rays)
@@ -66,7 +67,7 @@ if __name__ == "__main__":
         np.savez_compressed(os.path.join(HERE, name + ".npz"), rays=rays, xy=xy, hits=hits, samples=samples, film=film,
                             counters=np.array([st.rays_primary, st.rays_shadow, st.rays_mis, st.rays_continuation, st.node_tests, st.tri_tests, st.inst_tests], np.uint64))
         print(name, len(rays), "samples; mean radiance", samples["r"].mean())
-    lib = F.load_oracle("det")
+    lib = O.load_oracle("det")
     pts = np.zeros((3, 64, 2), np.float32)
     for k, scr in enumerate(((0, 0), (0x9E3779B9, 0x7F4A7C15), (0xFFFFFFFE, 1))):
         for i in range(64):

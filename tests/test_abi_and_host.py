@@ -9,6 +9,7 @@ import numpy as np
 import pytest
 
 from tray_rust_b200 import _ffi as F, api, scenebuild as SB
+from oracle import pyoracle as O
 
 REPO = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 SCENES = os.path.join(REPO, "tests", "golden", "scenes")
@@ -109,7 +110,7 @@ def test_loader_flattens_cornell_box(trb):
     assert [me.indices[i] for i in range(6)] == [0, 1, 2, 0, 2, 3]              # fan triangulation
     em = desc.color_keys[desc.instances[5].emission_first]
     assert np.allclose(list(em.rgba), [40.0, 0.772549 * 40, 0.560784 * 40, 40.0], rtol=1e-6)   # load_color scales by [3] (Q15)
-    o = api.OracleScene(desc)
+    o = O.OracleScene(desc)
     film, st = o.render(seed=1)
     img = film[..., :3] / np.maximum(film[..., 3:], 1e-9)
     assert np.isfinite(film).all() and 0.1 < img.mean() < 0.5

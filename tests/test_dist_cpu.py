@@ -21,6 +21,8 @@ def test_shard_blocks_matches_master_rs():
             for (s0, c0), (s1, _) in zip(parts, parts[1:]):
                 assert s0 + c0 == s1
             assert all(c == n // w for _, c in parts[:-1])          # blocks_per_worker, remainder to the last (master.rs:91-93,218-224)
+    from tray_rust_b200.dist import shard_is_empty
+    assert [shard_is_empty(shard_blocks(1, r, 2)) for r in range(2)] == [True, False]   # fewer blocks than ranks: idle ranks, never "all blocks"
 
 
 def _worker(rank, world, port, out):
@@ -28,11 +30,13 @@ def _worker(rank, world, port, out):
     os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port))
     dist.init_process_group("gloo", rank=rank, world_size=world)
     from tray_rust_b200 import _ffi as F, api, scenebuild as SB
+    from oracle import pyoracle as O
     from tray_rust_b200.dist import shard_blocks, reduce_film, max_over_ranks, sum_over_ranks
-    o = api.OracleScene(SB.scene_smallpt_like(32, 24, 4).finish())
+    o = O.OracleScene(SB.scene_smallpt_like(32, 24, 4).finish())
     o.update_frame(0, 0.0, 0.0)
     nb = o.n_blocks()
     start, count = shard_blocks(nb, rank, world)
+    assert count > 0  # an empty shard must skip the render: block_count 0 means "all blocks" in the ABI (block_queue.rs:39-41)
     film, st = o.render(threads=1, flags=F.RENDER_NO_UPDATE, block_start=start, block_count=count, seed=3)
     t = torch.from_numpy(film)
     reduce_film(t, dst=0)
@@ -46,11 +50,12 @@ def _worker(rank, world, port, out):
 
 def test_two_rank_tile_sharding_sums_to_the_full_frame(tmp_path):
     sys.path.insert(0, REPO)
-    from tray_rust_b200 import _ffi as F, api, scenebuild as SB
+    from tray_rust_b200 import _ffi as F, scenebuild as SB
+    from oracle import pyoracle as O
     out = str(tmp_path / "film.npy")
     mp.spawn(_worker, args=(2, 29533, out), nprocs=2, join=True)
     got = np.load(out)
-    o = api.OracleScene(SB.scene_smallpt_like(32, 24, 4).finish())
+    o = O.OracleScene(SB.scene_smallpt_like(32, 24, 4).finish())
     o.update_frame(0, 0.0, 0.0)
     full, st = o.render(threads=1, flags=F.RENDER_NO_UPDATE, seed=3)
     assert np.allclose(got, full, rtol=1e-5, atol=1e-6)             # fp32 sum order differs between 1 and 2 ranks

@@ -9,6 +9,7 @@ import numpy as np
 import pytest
 
 from tray_rust_b200 import _ffi as F, api, scenebuild as SB
+from oracle import pyoracle as O
 
 pytestmark = pytest.mark.gpu
 HERE = os.path.dirname(os.path.abspath(__file__))
@@ -20,7 +21,7 @@ KEYS = ["camera_samples", "rays_primary", "rays_shadow", "rays_mis", "rays_conti
 
 
 def both(desc):
-    g, o = api.Scene(desc), api.OracleScene(desc)
+    g, o = api.Scene(desc), O.OracleScene(desc)
     g.update_frame(0, 0.0, 0.0); o.update_frame(0, 0.0, 0.0)
     return g, o
 
@@ -56,7 +57,7 @@ def test_animated_scene_gpu_vs_oracle():
     """keyframed instances (one- and two-level stacks), keyframed camera, moving lights with keyframed
     emission — transforms recomposed per ray on the device (receiver.rs:30, emitter.rs:122,170,176,197, camera.rs:156)."""
     desc = SB.scene_animated(64, 64, 8, frames=4, scene_time=1.0, animated_fov=True).finish()  # + CameraFov::Animated (camera.rs:134-141)
-    g, o = api.Scene(desc), api.OracleScene(desc)
+    g, o = api.Scene(desc), O.OracleScene(desc)
     kw = dict(sample_first=0, sample_count=4, seed=21)
     rng = np.random.default_rng(5)
     for fr in range(4):
@@ -151,7 +152,7 @@ def test_json_scenes_through_the_loader():
         lib = F.load_trb()
         d = C.POINTER(F.SceneDesc)()
         assert lib.trb_desc_load_json(path.encode(), *dims, C.byref(d)) == 0
-        o = api.OracleScene(d.contents)
+        o = O.OracleScene(d.contents)
         of, ost = o.render(seed=9)
         ig = rt.pixels[..., :3] / np.maximum(rt.pixels[..., 3:], 1e-6); io = of[..., :3] / np.maximum(of[..., 3:], 1e-6)
         assert np.sqrt(np.mean((ig - io) ** 2)) < 1e-5
@@ -176,7 +177,7 @@ def test_tr15_like_json_scene_gpu_vs_oracle():
     assert lib.trb_desc_load_json(path.encode(), 96, 56, 4, C.byref(d)) == 0
     desc = d.contents
     assert desc.n_merl == 1 and desc.film.frames == 50 and desc.n_instances == 12
-    g, o = api.Scene(desc), api.OracleScene(desc)
+    g, o = api.Scene(desc), O.OracleScene(desc)
     step = desc.film.scene_time / desc.film.frames
     for fr in (0, 9, 14, 49):
         g.update_frame(fr, fr * step, (fr + 1) * step); o.update_frame(fr, fr * step, (fr + 1) * step)
@@ -220,7 +221,7 @@ def test_wide_gaussian_filter_film_vs_oracle():
     b = SB.scene_c4(20000, 128, 72, 8)
     b.film.update(filter_type=F.FILTER_GAUSSIAN, filter_w=3.0, filter_h=2.5, filter_b=0.5, filter_c=0.0)
     desc = b.finish()
-    g, o = api.Scene(desc), api.OracleScene(desc)
+    g, o = api.Scene(desc), O.OracleScene(desc)
     gf, _ = g.render(seed=3); of, _ = o.render(seed=3)
     ig = gf[..., :3] / np.maximum(gf[..., 3:], 1e-6); io = of[..., :3] / np.maximum(of[..., 3:], 1e-6)
     assert np.sqrt(np.mean((ig - io) ** 2)) < 1e-5 and np.allclose(gf[..., 3], of[..., 3], rtol=1e-4, atol=1e-5)

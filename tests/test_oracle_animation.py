@@ -10,6 +10,7 @@ import numpy as np
 import pytest
 
 from tray_rust_b200 import _ffi as F, api, scenebuild as SB
+from oracle import pyoracle as O
 from tray_rust_b200.scenebuild import Anim, trs, quat_axis_angle
 
 
@@ -30,7 +31,7 @@ def xf_at(o, inst, time):
 
 def test_degree1_translation_is_a_lerp_and_time_is_clamped_to_the_knot_domain():
     a, c = (1.0, 2.0, 3.0), (5.0, -2.0, 11.0)
-    o = api.OracleScene(one_instance_scene([Anim([trs(t=a), trs(t=c)], degree=1)]).finish())
+    o = O.OracleScene(one_instance_scene([Anim([trs(t=a), trs(t=c)], degree=1)]).finish())
     for t in (0.0, 0.125, 0.5, 0.75, 1.0):
         m, inv = xf_at(o, 0, t)
         want = np.float32(1.0 - np.float32(t)) * np.asarray(a, np.float32) + np.float32(t) * np.asarray(c, np.float32)
@@ -41,7 +42,7 @@ def test_degree1_translation_is_a_lerp_and_time_is_clamped_to_the_knot_domain():
 
 
 def test_slerp_midpoint_and_unit_rotation():
-    o = api.OracleScene(one_instance_scene([Anim([trs(q=quat_axis_angle((0, 1, 0), 0)), trs(q=quat_axis_angle((0, 1, 0), 90))], degree=1)]).finish())
+    o = O.OracleScene(one_instance_scene([Anim([trs(q=quat_axis_angle((0, 1, 0), 0)), trs(q=quat_axis_angle((0, 1, 0), 90))], degree=1)]).finish())
     m, _ = xf_at(o, 0, 0.5)
     c = math.cos(math.radians(45)); s = math.sin(math.radians(45))
     assert np.allclose(m[:3, :3], [[c, 0, s], [0, 1, 0], [-s, 0, c]], atol=2e-6)
@@ -49,7 +50,7 @@ def test_slerp_midpoint_and_unit_rotation():
         r = xf_at(o, 0, float(t))[0][:3, :3]
         assert np.allclose(r @ r.T, np.eye(3), atol=3e-6)
     # nearly parallel quaternions take the normalised-lerp branch (cos_theta > 0.9995, quaternion.rs:104-105)
-    o2 = api.OracleScene(one_instance_scene([Anim([trs(q=quat_axis_angle((0, 0, 1), 10)), trs(q=quat_axis_angle((0, 0, 1), 10.5))], degree=1)]).finish())
+    o2 = O.OracleScene(one_instance_scene([Anim([trs(q=quat_axis_angle((0, 0, 1), 10)), trs(q=quat_axis_angle((0, 0, 1), 10.5))], degree=1)]).finish())
     r = xf_at(o2, 0, 0.5)[0][:3, :3]
     a = math.radians(10.25)
     assert np.allclose(r, [[math.cos(a), -math.sin(a), 0], [math.sin(a), math.cos(a), 0], [0, 0, 1]], atol=2e-6)
@@ -57,12 +58,12 @@ def test_slerp_midpoint_and_unit_rotation():
 
 def test_bspline_partition_of_unity_endpoints_and_symmetry():
     k = trs(t=(3, -1, 2), q=quat_axis_angle((1, 2, 3), 40), s=(2, 1, 0.5))
-    o = api.OracleScene(one_instance_scene([Anim([k] * 6, degree=3)]).finish())
+    o = O.OracleScene(one_instance_scene([Anim([k] * 6, degree=3)]).finish())
     ref = xf_at(o, 0, 0.0)[0]
     for t in (0.1, 0.33, 0.5, 0.9, 1.0):
         assert np.allclose(xf_at(o, 0, t)[0], ref, atol=2e-6)
     pts = [(0, 0, 0), (1, 4, 0), (3, 5, 1), (6, 4, 2), (8, 0, 3)]
-    o = api.OracleScene(one_instance_scene([Anim([trs(t=p) for p in pts], degree=3)]).finish())
+    o = O.OracleScene(one_instance_scene([Anim([trs(t=p) for p in pts], degree=3)]).finish())
     assert np.allclose(xf_at(o, 0, 0.0)[0][:3, 3], pts[0], atol=1e-6)   # clamped knot vector interpolates the end control points
     assert np.allclose(xf_at(o, 0, 1.0)[0][:3, 3], pts[-1], atol=1e-5)
     # closed form at the interior knot 0.5 of knots [0,0,0,0,.5,1,1,1,1]: basis (1/4, 1/2, 1/4) on control points 1..3
@@ -77,7 +78,7 @@ def test_bspline_partition_of_unity_endpoints_and_symmetry():
 def test_stack_order_animated_level_below_a_static_level():
     # transform = t_last * ... * t_first (animated_transform.rs:42-54): spin first, then place
     spin = Anim([trs(q=quat_axis_angle((0, 1, 0), 0)), trs(q=quat_axis_angle((0, 1, 0), 90))], degree=1)
-    o = api.OracleScene(one_instance_scene([spin, trs(t=(5, 0, 0), s=2.0)]).finish())
+    o = O.OracleScene(one_instance_scene([spin, trs(t=(5, 0, 0), s=2.0)]).finish())
     m, _ = xf_at(o, 0, 1.0)
     assert np.allclose(m[:3, 3], (5, 0, 0), atol=1e-6)
     assert np.allclose(m[:3, :3], 2.0 * np.array([[0, 0, 1], [0, 1, 0], [-1, 0, 0]]), atol=3e-6)
@@ -86,12 +87,12 @@ def test_stack_order_animated_level_below_a_static_level():
 def test_tlas_bounds_follow_animation_bounds_q22():
     fly = Anim([trs(t=(-8, 0, 0)), trs(t=(8, 0, 0))], degree=1)
     b = one_instance_scene([fly], frames=1)
-    o = api.OracleScene(b.finish())
+    o = O.OracleScene(b.finish())
     o.update_frame(0, 0.0, 1.0)   # shutter_size 1: the box must cover the whole sweep (128 time samples, animated_transform.rs:62-68)
     nodes, _ = o.bvh(-1)
     assert nodes["bmin"][:, 0].min() <= -9.0 and nodes["bmax"][:, 0].max() >= 9.0
     # Q22: a stack holding one static level is "not animated" for bounds -> only the box of transform(start)
-    o2 = api.OracleScene(one_instance_scene([fly, trs(s=1.0)], frames=1).finish())
+    o2 = O.OracleScene(one_instance_scene([fly, trs(s=1.0)], frames=1).finish())
     o2.update_frame(0, 0.0, 1.0)
     n2, _ = o2.bvh(-1)
     assert n2["bmin"][:, 0].min() == -9.0 and n2["bmax"][:, 0].max() <= 1.0 + 1e-5   # sphere at x=-8 (r=1) and the light at x in [-1, 1]
@@ -101,7 +102,7 @@ def test_tlas_bounds_follow_animation_bounds_q22():
 def test_keyframed_emission_lerps_and_clamps():
     keys = [((1.0, 0.0, 0.0, 10), 0.25), ((0.0, 1.0, 0.0, 20), 0.75)]
     b = one_instance_scene([trs(t=(0, 0, 0), s=0.01)], emission=keys, cam=[trs(t=(0, 10, -20))])
-    o = api.OracleScene(b.finish())
+    o = O.OracleScene(b.finish())
 
     def seen(time):
         o.update_frame(0, time, time)
@@ -117,7 +118,7 @@ def test_keyframed_emission_lerps_and_clamps():
 
 def test_animated_scene_renders_and_frames_differ():
     d = SB.scene_animated(32, 32, 4).finish()
-    o = api.OracleScene(d)
+    o = O.OracleScene(d)
     means, cams = [], []
     for fr in range(4):
         o.update_frame(fr, fr * 0.25, (fr + 1) * 0.25)
@@ -138,7 +139,7 @@ def test_product_host_animated_transform_matches_oracle_bit_for_bit(trb):
     """trb_host_animated_transform is the code the device runs per ray (csrc/trb_anim.h) compiled for the host."""
     b = SB.scene_animated(32, 32, 4)
     d = b.finish()
-    o = api.OracleScene(d)
+    o = O.OracleScene(d)
     import ctypes as C
     for time in (0.0, 0.03, 0.25, 0.3333, 0.5, 0.77, 1.0, 1.5, -0.5):
         o.update_frame(0, time, time)
@@ -202,7 +203,7 @@ def test_tr15_like_json_through_the_loader(trb):
     big = [l for l in lights if l.n_emission == 4][0]
     ck = [desc.color_keys[big.emission_first + k] for k in range(4)]
     assert [k.time for k in ck] == [0.0, 3.5, 5.0, 7.0] and ck[0].rgba[0] == 0.0 and abs(ck[2].rgba[0] - 110.0) < 1e-4  # rgb * 4th component
-    o = api.OracleScene(desc)
+    o = O.OracleScene(desc)
     step = desc.film.scene_time / desc.film.frames
     means = []
     for fr in (0, 9, 14, 30):
@@ -225,7 +226,7 @@ def test_animated_fov_is_sampled_once_per_frame_at_the_clamped_midpoint():
     b = one_instance_scene([trs()], frames=10, scene_time=10.0)
     b.cameras = []
     b.add_camera([trs(t=(0, 0, -20))], fov=[20.0, 60.0], fov_knots=[2.0, 2.0, 6.0, 6.0], fov_degree=1, shutter_size=1.0)
-    o = api.OracleScene(b.finish())
+    o = O.OracleScene(b.finish())
 
     def half_width(start, end):
         o.update_frame(0, start, end)
@@ -260,6 +261,22 @@ def test_invalid_splines_are_rejected_like_bspline_new(trb):
     bad.splines[0] = (1, 2, bad.splines[0][2], 3, bad.splines[0][4])          # 3 knots for 2 control points of degree 1
     rc, msg = status(bad)
     assert rc == F.TRB_INVALID_ARG and "knots.len() != control_points.len() + degree + 1" in msg
+    # BSpline::new's first check: control_points.len() > degree ("Too few control points for curve"). Two control points
+    # of degree 3 with 6 knots satisfy the knot-count rule but would index before the control points in de Boor.
+    few = one_instance_scene([Anim([trs(), trs(t=(1, 0, 0))], degree=1)])
+    few.knots = few.knots[:few.splines[0][4]] + [0.0, 0.0, 0.0, 1.0, 1.0, 1.0]
+    few.splines[0] = (3, 2, few.splines[0][2], 6, few.splines[0][4])
+    rc, msg = status(few)
+    assert rc == F.TRB_INVALID_ARG and "Too few control points" in msg
+    # BSpline::new sorts its knots: an unsorted knot vector evaluates like the sorted one
+    pts = [trs(t=(float(k), 0.5 * k, 0)) for k in range(5)]
+    srt = one_instance_scene([Anim(pts, knots=[0, 0, 0, 0.3, 0.6, 1, 1, 1], degree=2)])
+    uns = one_instance_scene([Anim(pts, knots=[1, 0, 0.6, 0, 1, 0.3, 0, 1], degree=2)])
+    assert status(srt)[0] == F.TRB_OK
+    m_sorted = m.copy()
+    assert status(uns)[0] == F.TRB_OK and m.tobytes() == m_sorted.tobytes()
+    nan = one_instance_scene([Anim(pts, knots=[0, 0, 0, float("nan"), 0.6, 1, 1, 1], degree=2)])
+    assert status(nan)[0] == F.TRB_INVALID_ARG
     deep = one_instance_scene([Anim([trs(t=(k, 0, 0)) for k in range(8)], degree=6)])
     rc, msg = status(deep)
     assert rc == F.TRB_UNSUPPORTED and "degree" in msg
@@ -271,3 +288,6 @@ def test_invalid_splines_are_rejected_like_bspline_new(trb):
     c = list(cam.cameras[0]); c[8] = 3; cam.cameras[0] = tuple(c)                # n_fov_knots 3 instead of 4
     rc, msg = status(cam)
     assert rc == F.TRB_INVALID_ARG and "knots.len()" in msg
+    c[8] = 4; c[5] = 2; cam.cameras[0] = tuple(c)                                # fov degree 2 with 2 control points
+    rc, msg = status(cam)
+    assert rc == F.TRB_INVALID_ARG and "Too few control points" in msg

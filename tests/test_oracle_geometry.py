@@ -5,6 +5,7 @@ import ctypes as C
 import numpy as np
 
 from tray_rust_b200 import _ffi as F, api, scenebuild as SB
+from oracle import pyoracle as O
 
 
 def mk_rays(o, d, tmin=0.0, tmax=np.inf):
@@ -20,7 +21,7 @@ def simple_scene(add):
     add(b, m)
     b.area_light(F.SHAPE_RECT, m, [SB.trs(t=(0, 1000, 0))], (1, 1, 1), p0=1, p1=1)
     b.add_camera([SB.trs(t=(0, 0, -5))])
-    o = api.OracleScene(b.finish())
+    o = O.OracleScene(b.finish())
     o.update_frame(0, 0.0, 0.0)
     return o
 
@@ -151,7 +152,7 @@ def test_host_bvh_builder_matches_oracle_and_invariants(trb):
         b.receiver(F.SHAPE_MESH, m, [SB.trs()], mesh=b.add_mesh(pos, nrm, uv, idx))
         b.area_light(F.SHAPE_RECT, m, [SB.trs(t=(0, 99, 0))], (1, 1, 1), p0=1, p1=1)
         b.add_camera([SB.trs()])
-        on, oo = api.OracleScene(b.finish()).bvh(0)
+        on, oo = O.OracleScene(b.finish()).bvh(0)
         assert nodes.tobytes() == on.tobytes() and np.array_equal(order, oo), n
         check_bvh_invariants(on, oo, boxes, 16)
 
@@ -165,7 +166,7 @@ def test_point_lights_are_never_hit():  # emitter.rs:119-120
     b = SB.SceneBuilder(8, 8, 1)
     b.point_light([SB.trs(t=(0, 0, 5))], (1, 1, 1, 10))
     b.add_camera([SB.trs()])
-    o = api.OracleScene(b.finish())
+    o = O.OracleScene(b.finish())
     o.update_frame(0, 0.0, 0.0)
     h, st = o.intersect(mk_rays([[0, 0, 0]], [[0, 0, 1]]))
     assert h["inst"][0] == F.MISS

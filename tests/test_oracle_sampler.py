@@ -3,6 +3,7 @@ DESIGN.md determinism contract)."""
 import numpy as np
 
 from tray_rust_b200 import _ffi as F, api, scenebuild as SB
+from oracle import pyoracle as O
 
 
 def s02(oracle, n, s0=0, s1=0):
@@ -61,7 +62,7 @@ def test_block_queue_order_and_selection(oracle):  # block_queue.rs:28-46
     m = b.add_material(F.MAT_MATTE, (0.5, 0.5, 0.5), roughness=1.0)
     b.area_light(F.SHAPE_RECT, m, [SB.trs()], (1, 1, 1), p0=1, p1=1)
     b.add_camera([SB.trs(t=(0, 0, -5))])
-    o = api.OracleScene(b.finish())
+    o = O.OracleScene(b.finish())
     bl = o.block_list()
     assert len(bl) == 4 * 3
     codes = [oracle.orc_morton2(int(x), int(y)) for x, y in bl]
@@ -109,7 +110,7 @@ def test_detmath_accuracy(oracle):
 
 def test_camera_rays_cover_the_image(oracle):
     b = SB.scene_smallpt_like(16, 16, 4)
-    o = api.OracleScene(b.finish())
+    o = O.OracleScene(b.finish())
     o.update_frame(0, 0.0, 0.0)
     rays, xy = o.camera_rays(seed=3)
     assert len(rays) == 16 * 16 * 4

@@ -7,6 +7,7 @@ import math
 import numpy as np
 
 from tray_rust_b200 import _ffi as F, api, scenebuild as SB
+from oracle import pyoracle as O
 
 ALL = 31
 NON_SPECULAR = 4 | 8 | 1 | 2
@@ -112,7 +113,7 @@ def direct_lighting_scene(spp):
 def test_direct_lighting_matches_closed_form(oracle):
     """E = rho/pi * L * integral over the light of cos cos' / r^2 dA, evaluated numerically in float64."""
     spp = 256
-    o = api.OracleScene(direct_lighting_scene(spp).finish())
+    o = O.OracleScene(direct_lighting_scene(spp).finish())
     o.update_frame(0, 0.0, 0.0)
     s, st = o.render_samples(seed=5)
     rays, _ = o.camera_rays(seed=5)
@@ -135,7 +136,7 @@ def test_direct_lighting_matches_closed_form(oracle):
 def test_libm_choice_is_statistically_neutral(oracle, oracle_sys):
     """detmath and glibc builds of the oracle agree at the level of Monte-Carlo noise."""
     d = SB.scene_smallpt_like(16, 16, 64).finish()
-    a, b = api.OracleScene(d, "det"), api.OracleScene(d, "sys")
+    a, b = O.OracleScene(d, "det"), O.OracleScene(d, "sys")
     for o in (a, b):
         o.update_frame(0, 0.0, 0.0)
     sa, _ = a.render_samples(seed=2)
@@ -148,7 +149,7 @@ def test_libm_choice_is_statistically_neutral(oracle, oracle_sys):
 
 
 def test_film_filter_properties(oracle):
-    o = api.OracleScene(SB.scene_smallpt_like(16, 16, 1).finish())
+    o = O.OracleScene(SB.scene_smallpt_like(16, 16, 1).finish())
     t = o.filter_table()
     assert t.shape == (16, 16) and np.allclose(t, t.T) and t[0, 0] > 0.75  # Mitchell b=c=1/3 at the centre ~ (8/9)^2
     assert (np.diff(t[0]) <= 1e-7).all() or t[0].min() < 0  # decreasing into the negative lobe
@@ -158,7 +159,7 @@ def test_film_filter_properties(oracle):
     m = b.add_material(F.MAT_MATTE, (0, 0, 0), roughness=0.0)
     b.area_light(F.SHAPE_RECT, m, [SB.trs(t=(0, 0, 5), q=SB.quat_axis_angle((1, 0, 0), 180), s=100)], (0.25, 0.5, 0.75), p0=2, p1=2)
     b.add_camera([SB.trs()], fov=40)
-    o = api.OracleScene(b.finish())
+    o = O.OracleScene(b.finish())
     film, st = o.render(seed=1)
     img = film[..., :3] / film[..., 3:]
     assert np.allclose(img, [0.25, 0.5, 0.75], atol=1e-5)

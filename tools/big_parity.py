@@ -10,12 +10,13 @@ import numpy as np
 
 sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 from tray_rust_b200 import _ffi as F, api, scenebuild as SB  # noqa: E402
+from oracle import pyoracle as O  # noqa: E402
 
 SPP = int(sys.argv[1]) if len(sys.argv) > 1 else 6
 KEYS = ["camera_samples", "rays_primary", "rays_shadow", "rays_mis", "rays_continuation", "node_tests", "tri_tests", "inst_tests"]
 t0 = time.time()
 desc = SB.scene_c4(1_000_000, 1920, 1080, 4096).finish()
-g, o = api.Scene(desc), api.OracleScene(desc)
+g, o = api.Scene(desc), O.OracleScene(desc)
 g.update_frame(0, 0.0, 0.0); o.update_frame(0, 0.0, 0.0)
 t1 = time.time()
 kw = dict(sample_first=0, sample_count=SPP, seed=1)

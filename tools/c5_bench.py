@@ -13,6 +13,7 @@ REPO = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 sys.path.insert(0, REPO)
 sys.path.insert(0, os.path.join(REPO, "tests", "golden"))
 from tray_rust_b200 import _ffi as F, api  # noqa: E402
+from oracle import pyoracle as O  # noqa: E402
 import make_scenes  # noqa: E402
 
 W, H, SPP_STEP, FRAME = 1920, 1080, 8, 12
@@ -24,7 +25,7 @@ d = C.POINTER(F.SceneDesc)()
 assert lib.trb_desc_load_json(os.path.join(REPO, "tests", "golden", "scenes", "c5_tr15_like.json").encode(), W, H, 2048, C.byref(d)) == 0
 desc = d.contents
 step = desc.film.scene_time / desc.film.frames
-g, o = api.Scene(desc, 0), api.OracleScene(desc)
+g, o = api.Scene(desc, 0), O.OracleScene(desc)
 g.update_frame(FRAME, FRAME * step, (FRAME + 1) * step); o.update_frame(FRAME, FRAME * step, (FRAME + 1) * step)
 kw = dict(block_start=12000, block_count=64, sample_first=0, sample_count=4, seed=1)
 gs, _ = g.render_samples(**kw); os_, _ = o.render_samples(**kw)

@@ -10,6 +10,7 @@ import torch
 
 sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 from tray_rust_b200 import _ffi as F, api, scenebuild as SB  # noqa: E402
+from oracle import pyoracle as O  # noqa: E402
 
 
 def film(g, v2, **kw):
@@ -23,7 +24,7 @@ for name, b in (("zoo64", SB.scene_materials_zoo(64, 64, 8, SB.synthetic_merl_ta
     if name == "c4_20k_wide":
         b.film.update(filter_type=F.FILTER_GAUSSIAN, filter_w=3.0, filter_h=2.5, filter_b=0.5, filter_c=0.0)
     desc = b.finish()
-    g, o = api.Scene(desc), api.OracleScene(desc)
+    g, o = api.Scene(desc), O.OracleScene(desc)
     f1, f2 = film(g, False, seed=3), film(g, True, seed=3)
     fo, _ = o.render(seed=3)
     n = lambda f: f[..., :3] / np.maximum(f[..., 3:], 1e-6)

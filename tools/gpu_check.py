@@ -10,6 +10,7 @@ import numpy as np
 
 sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 from tray_rust_b200 import _ffi as F, api, scenebuild as SB  # noqa: E402
+from oracle import pyoracle as O  # noqa: E402
 
 RES = {}
 
@@ -21,7 +22,7 @@ def report(name, ok, extra=""):
 
 def compare_scene(tag, desc, spp_pass=4, n_rand=20000, film=True):
     g = api.Scene(desc)
-    o = api.OracleScene(desc)
+    o = O.OracleScene(desc)
     g.update_frame(0, 0.0, 0.0)
     o.update_frame(0, 0.0, 0.0)
     gn, go = g.bvh(-1)

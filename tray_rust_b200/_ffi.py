@@ -4,9 +4,8 @@ The product library is ``tray_rust_b200/lib/libtrb.so`` (CUDA kernels + host cod
 built by ``__graft_entry__.build()``). There is NO CPU fallback: if the library is
 missing, ``load_trb()`` raises.
 
-``load_oracle()`` loads the parity oracle (``oracle/_build/liboracle_*.so``). It is test
-infrastructure: only tests/, ``__graft_entry__.smoke()`` and bench.py's cpu_baseline /
-``--impl reference`` legs may call it.
+The parity oracle has its own bindings under ``oracle/pyoracle.py`` (test infrastructure);
+nothing in this package imports, loads or links it.
 """
 import ctypes as C
 import os
@@ -131,11 +130,10 @@ TRB_SYMBOLS = [
     "trb_render", "trb_render_device", "trb_intersect", "trb_intersect_device", "trb_camera_rays",
     "trb_render_samples", "trb_film_to_srgb8", "trb_block_list", "trb_scene_get_bvh", "trb_scene_get_transform",
     "trb_scene_get_filter_table", "trb_last_error", "trb_abi_version", "trb_desc_load_json", "trb_desc_free",
-    "trb_host_build_bvh", "trb_host_keyframe_transform", "trb_host_animated_transform", "trb_host_animated_color", "trb_host_quad_check", "trb_launch_count", "trb_scene_trace_time",
+    "trb_host_build_bvh", "trb_host_keyframe_transform", "trb_host_animated_transform", "trb_host_animated_color", "trb_host_quad_check", "trb_launch_count", "trb_scene_trace_time", "trb_scene_check_error", "trb_scene_set_option",
 ]
 
 _trb = None
-_oracle = {}
 
 
 def trb_path():
@@ -182,64 +180,9 @@ def load_trb():
     lib.trb_host_quad_check.argtypes = [vp, u32, vp, u32, C.POINTER(u32), C.POINTER(C.c_uint64), C.POINTER(C.c_uint64)]
     lib.trb_launch_count.restype = C.c_uint64
     lib.trb_scene_trace_time.argtypes = [vp, C.POINTER(f32), C.POINTER(u32)]
+    lib.trb_scene_check_error.argtypes = [vp]
+    lib.trb_scene_set_option.argtypes = [vp, C.c_char_p, C.c_longlong]
     _trb = lib
-    return lib
-
-
-def oracle_path(kind="det"):
-    return os.path.join(REPO, "oracle", "_build", "liboracle_%s.so" % kind)
-
-
-def load_oracle(kind="det"):
-    """Load the CPU oracle (test infrastructure). kind: 'det' (detmath) or 'sys' (glibc libm)."""
-    if kind in _oracle:
-        return _oracle[kind]
-    p = oracle_path(kind)
-    if not os.path.exists(p):
-        raise RuntimeError("oracle library missing (%s): run oracle/build.sh" % p)
-    lib = C.CDLL(p)
-    vp, sz = C.c_void_p, C.c_size_t
-    lib.orc_last_error.restype = C.c_char_p
-    lib.orc_scene_create.argtypes = [C.POINTER(SceneDesc), C.POINTER(vp)]
-    lib.orc_scene_destroy.argtypes = [vp]
-    lib.orc_scene_destroy.restype = None
-    lib.orc_scene_update_frame.argtypes = [vp, u32, f32, f32]
-    lib.orc_set_baseline_mode.argtypes = [vp, C.c_int]
-    lib.orc_set_baseline_mode.restype = None
-    lib.orc_block_list.argtypes = [vp, u32, u32, C.POINTER(u32), vp, u32]
-    lib.orc_scene_get_bvh.argtypes = [vp, C.c_int, C.POINTER(u32), vp, C.POINTER(u32), vp]
-    lib.orc_scene_get_transform.argtypes = [vp, u32, vp, vp]
-    lib.orc_scene_get_filter_table.argtypes = [vp, vp]
-    lib.orc_intersect.argtypes = [vp, sz, vp, vp, C.POINTER(Stats)]
-    lib.orc_render.argtypes = [vp, C.POINTER(RenderCfg), vp, C.POINTER(Stats), C.c_int]
-    lib.orc_render_samples.argtypes = [vp, C.POINTER(RenderCfg), sz, vp, C.POINTER(Stats), C.c_int]
-    lib.orc_camera_rays.argtypes = [vp, C.POINTER(RenderCfg), sz, vp, vp]
-    lib.orc_film_to_srgb8.argtypes = [vp, vp, vp]
-    lib.orc_detmath.argtypes = [C.c_int, sz, vp, vp, vp]
-    lib.orc_detmath.restype = None
-    lib.orc_rng.argtypes = [u32, u32, u32, u32]
-    lib.orc_rng.restype = u32
-    lib.orc_permute.argtypes = [u32, u32, u32]
-    lib.orc_permute.restype = u32
-    lib.orc_sample_02.argtypes = [u32, u32, u32, vp]
-    lib.orc_sample_02.restype = None
-    lib.orc_morton2.argtypes = [u32, u32]
-    lib.orc_morton2.restype = u32
-    lib.orc_bsdf_probe.argtypes = [C.POINTER(Material), vp, vp, vp, u32, vp, vp]
-    lib.orc_m4_mul.argtypes = [vp, vp, vp]
-    lib.orc_m4_mul.restype = None
-    lib.orc_m4_inverse.argtypes = [vp, vp]
-    lib.orc_m4_inverse.restype = None
-    lib.orc_keyframe_transform.argtypes = [C.POINTER(Keyframe), vp, vp]
-    lib.orc_keyframe_transform.restype = None
-    lib.orc_partition_even.argtypes = [vp, sz]
-    lib.orc_partition_even.restype = sz
-    lib.orc_libm_kind.restype = C.c_int
-    lib.orc_cross_dot.argtypes = [vp, vp, vp]
-    lib.orc_cross_dot.restype = None
-    lib.orc_xf_apply.argtypes = [C.POINTER(Keyframe), vp, vp]
-    lib.orc_xf_apply.restype = None
-    _oracle[kind] = lib
     return lib
 
 

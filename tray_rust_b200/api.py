@@ -1,8 +1,7 @@
 """Python host side above the C ABI.
 
-``Scene`` wraps a ``trb_scene`` (GPU, product). ``OracleScene`` wraps the CPU oracle with the same
-methods so parity tests read the same on both sides; it is test infrastructure and must not be
-used by product code paths.
+``Scene`` wraps a ``trb_scene`` (GPU, product). The CPU oracle's wrapper with the same methods
+(``oracle.pyoracle.OracleScene``) is test infrastructure and lives outside this package.
 
 The reference-shaped mirror (``Config``, ``RenderTarget``, ``Exec.render`` with the argument
 meaning of /root/reference/src/exec/mod.rs:17-49) lives in ``tray_rust_b200.exec``.
@@ -117,6 +116,14 @@ class Scene(_Base):
         cfg = _cfg(**kw)
         self._check(self._lib.trb_render_device(self._h, C.byref(cfg), d_film_ptr, d_stats_ptr, stream))
 
+    def set_option(self, name, value):
+        """trb_scene_set_option: launch-shape options (never change results)."""
+        self._check(self._lib.trb_scene_set_option(self._h, name.encode(), int(value)))
+
+    def check_error(self):
+        """trb_scene_check_error: drain the device, raise on a latched traversal-stack overflow."""
+        self._check(self._lib.trb_scene_check_error(self._h))
+
     def trace_time(self):
         """(total ms, launches) of the trace kernel for launches made with RENDER_TIME_TRACE since the last call."""
         ms, n = F.f32(), F.u32()
@@ -152,74 +159,6 @@ class Scene(_Base):
         film = np.ascontiguousarray(film, dtype=np.float32)
         out = np.zeros((self.height, self.width, 3), np.uint8)
         self._check(self._lib.trb_film_to_srgb8(self._h, F.ptr(film), F.ptr(out)))
-        return out
-
-
-class OracleScene(_Base):
-    """CPU oracle with the same surface (TEST INFRASTRUCTURE ONLY)."""
-    _pfx = "orc_"
-
-    def __init__(self, desc, libm="det", baseline=False):
-        self._lib = F.load_oracle(libm)
-        self._desc = desc
-        h = C.c_void_p()
-        self._h = None
-        self._check(self._lib.orc_scene_create(C.byref(desc), C.byref(h)))
-        self._h = h
-        self.width, self.height = desc.film.width, desc.film.height
-        self.spp = 1 << (max(1, desc.film.samples) - 1).bit_length()
-        if baseline:
-            self._lib.orc_set_baseline_mode(h, 1)
-
-    def _check(self, rc):
-        if rc != F.TRB_OK:
-            raise TrbError(rc, (self._lib.orc_last_error() or b"").decode())
-
-    def close(self):
-        if self._h is not None:
-            self._lib.orc_scene_destroy(self._h)
-            self._h = None
-
-    def __del__(self):
-        try:
-            self.close()
-        except Exception:
-            pass
-
-    def render(self, film=None, threads=0, **kw):
-        cfg = _cfg(**kw)
-        if film is None:
-            film = np.zeros((self.height, self.width, 4), np.float32)
-        st = F.Stats()
-        self._check(self._lib.orc_render(self._h, C.byref(cfg), F.ptr(film), C.byref(st), threads))
-        return film, st
-
-    def render_samples(self, threads=0, **kw):
-        cfg = _cfg(**kw)
-        n = self._n_samples(cfg)
-        out = np.zeros(n, F.SAMPLE_DTYPE)
-        st = F.Stats()
-        self._check(self._lib.orc_render_samples(self._h, C.byref(cfg), n, F.ptr(out), C.byref(st), threads))
-        return out, st
-
-    def camera_rays(self, **kw):
-        cfg = _cfg(**kw)
-        n = self._n_samples(cfg)
-        rays, xy = np.zeros(n, F.RAY_DTYPE), np.zeros((n, 2), np.float32)
-        self._check(self._lib.orc_camera_rays(self._h, C.byref(cfg), n, F.ptr(rays), F.ptr(xy)))
-        return rays, xy
-
-    def intersect(self, rays):
-        rays = np.ascontiguousarray(rays, dtype=F.RAY_DTYPE)
-        hits = np.zeros(len(rays), F.HIT_DTYPE)
-        st = F.Stats()
-        self._check(self._lib.orc_intersect(self._h, len(rays), F.ptr(rays), F.ptr(hits), C.byref(st)))
-        return hits, st
-
-    def to_srgb8(self, film):
-        film = np.ascontiguousarray(film, dtype=np.float32)
-        out = np.zeros((self.height, self.width, 3), np.uint8)
-        self._check(self._lib.orc_film_to_srgb8(self._h, F.ptr(film), F.ptr(out)))
         return out
 
 

@@ -151,9 +151,45 @@ bool pack_quads(const std::vector<trb_bvh_node>& in, std::vector<trb::DQuad>& ou
 
 } // namespace
 
+namespace {
+// Launch-shape knobs of the wavefront pipeline. Read ONCE from the environment when the scene is created (developer
+// sweeps), changed afterwards only through trb_scene_set_option: the launch path never touches getenv.
+struct Tuning {
+    int refill = 8;            // trace: idle lanes that trigger a warp refill
+    int occ = 7;               // trace: resident CTAs per SM the kernel variant is compiled for
+    unsigned trace_grid = 12;  // trace: CTAs per SM launched
+    int smem_stack = 16;       // trace: traversal-stack entries kept in shared memory
+    uint32_t sched = 6;        // trace: quorum of the phased loop (0 = flat state machine)
+    int quads = 0;             // trace: DQuad two-level records (measured slower on C4)
+    int film_v2 = 1;           // film: per-warp private tiles (0 = shared-memory atomics)
+    int sort = 1;              // ray queues: 0 = path order, 1 = origin-cell / octant counting sort before each trace round
+    int sort_bits = 5;         // bits per axis of the origin cell grid
+    int sort_min_round = 1;    // first bounce round whose queues are sorted (round 0 = primary rays, already coherent)
+    int shade_split = 1;       // shading as three kernels (surface | direct light | BSDF sample) instead of one
+    int graph = 1;             // replay each pass as a CUDA graph when its shape repeats
+    uint64_t pass_paths = 1ull << 24; // camera samples per wavefront pass (the frame is rendered in additive passes)
+};
+int env_int(const char* name, int dflt) { const char* v = getenv(name); return v ? (int)strtol(v, nullptr, 0) : dflt; }
+void tuning_from_env(Tuning& t) {
+    t.refill = env_int("TRB_REFILL", t.refill); t.occ = env_int("TRB_TRACE_OCC", t.occ); t.trace_grid = (unsigned)env_int("TRB_TRACE_GRID", (int)t.trace_grid);
+    t.smem_stack = env_int("TRB_SMEM_STACK", t.smem_stack); t.sched = (uint32_t)env_int("TRB_TRACE_SCHED", (int)t.sched); t.quads = env_int("TRB_TRACE_QUADS", t.quads);
+    t.film_v2 = env_int("TRB_FILM_V2", t.film_v2); t.sort = env_int("TRB_SORT", t.sort); t.sort_bits = env_int("TRB_SORT_BITS", t.sort_bits);
+    t.sort_min_round = env_int("TRB_SORT_MIN_ROUND", t.sort_min_round); t.shade_split = env_int("TRB_SHADE_SPLIT", t.shade_split); t.graph = env_int("TRB_GRAPH", t.graph);
+    if (getenv("TRB_PASS_PATHS")) t.pass_paths = strtoull(getenv("TRB_PASS_PATHS"), nullptr, 0);
+}
+
+} // namespace
+
+struct BlockList { // one selection of the Morton block list, resident on the device (never overwritten in place: kernels in flight may read it)
+    uint32_t key[5];
+    std::vector<uint32_t> host; // (bx, by) pairs
+    uint2* dev = nullptr;
+};
+
 struct trb_scene {
     int device = 0;
     int sm_count = 148;
+    Tuning tune;
     // deep copy of the description
     trb_film film{};
     trb_integrator integrator{};
@@ -183,10 +219,7 @@ struct trb_scene {
     trb::DBvh* d_tlas_hdr = nullptr;
     uint32_t* d_tlas_order = nullptr;
     size_t tlas_capacity = 0;
-    uint2* d_blocks = nullptr;
-    size_t blocks_capacity = 0;
-    std::vector<uint32_t> cached_blocks;
-    uint32_t cached_block_start = 0xffffffffu, cached_block_count = 0xffffffffu, cached_shard[3] = {0, 0, 0};
+    std::vector<BlockList> block_lists;
     uint32_t* d_counter = nullptr;
     int* d_error = nullptr;
     trb::DStats* d_stats = nullptr;
@@ -201,6 +234,7 @@ struct trb_scene {
     std::vector<std::pair<cudaEvent_t, cudaEvent_t>> trace_events; // TRB_RENDER_TIME_TRACE
     std::vector<std::pair<cudaEvent_t, cudaEvent_t>> event_pool;
     ~trb_scene() {
+        for (auto& b : block_lists) cudaFree(b.dev);
         for (void* p : wf_allocs) cudaFree(p);
         for (auto& e : trace_events) { cudaEventDestroy(e.first); cudaEventDestroy(e.second); }
         for (auto& e : event_pool) { cudaEventDestroy(e.first); cudaEventDestroy(e.second); }
@@ -233,6 +267,7 @@ trb_status validate(const trb_scene_desc* d) {
     if (d->n_instances == 0) return fail(TRB_INVALID_ARG, "Aborting: the scene does not have any objects!"); // scene.rs:134
     if (d->n_cameras == 0) return fail(TRB_INVALID_ARG, "Error: A camera is required!");
     if (d->integrator.type != TRB_INTEGRATOR_PATH) return fail(TRB_UNSUPPORTED, "only the pathtracer integrator is implemented");
+    if (d->integrator.max_depth > 57u) return fail(TRB_UNSUPPORTED, "max_depth > 57");
     if (!(d->film.filter_w > 0.0f && d->film.filter_h > 0.0f)) return fail(TRB_INVALID_ARG, "filter width/height must be positive");
     if (floorf(d->film.filter_w / 0.5f) > 8.0f || floorf(d->film.filter_h / 0.5f) > 8.0f) return fail(TRB_UNSUPPORTED, "filter wider than 4 pixels");
     bool light = false;
@@ -244,30 +279,34 @@ trb_status validate(const trb_scene_desc* d) {
             return fail(TRB_INVALID_ARG, "Geometry of type 'mesh' is not sampleable and can't be used for area light geometry"); // scene.rs:577-579
         if (in.shape == TRB_SHAPE_MESH && in.mesh >= d->n_meshes) return fail(TRB_INVALID_ARG, "mesh index out of range");
         if (in.kind != TRB_INST_EMITTER_POINT && in.material >= d->n_materials) return fail(TRB_INVALID_ARG, "material index out of range");
-        if (in.spline_first + in.n_splines > d->n_splines) return fail(TRB_INVALID_ARG, "spline range out of bounds");
+        if ((uint64_t)in.spline_first + in.n_splines > d->n_splines) return fail(TRB_INVALID_ARG, "spline range out of bounds");
         if (in.kind != TRB_INST_RECEIVER) {
             light = true;
-            if (in.n_emission == 0 || in.emission_first + in.n_emission > d->n_color_keys) return fail(TRB_INVALID_ARG, "An emission color is required for emitters");
+            if (in.n_emission == 0 || (uint64_t)in.emission_first + in.n_emission > d->n_color_keys) return fail(TRB_INVALID_ARG, "An emission color is required for emitters");
         }
     }
-    for (uint32_t k = 0; k < d->n_splines; ++k) { // BSpline::new's invariants (bspline.rs:37-45) + the device evaluator's degree cap
+    for (uint32_t k = 0; k < d->n_splines; ++k) { // BSpline::new's invariants (bspline 0.2.2) + the device evaluator's degree cap
         const trb_spline& sp = d->splines[k];
-        if (sp.n_ctrl == 0 || sp.ctrl_first + sp.n_ctrl > d->n_keyframes) return fail(TRB_INVALID_ARG, "spline control points out of bounds");
+        if (sp.n_ctrl == 0 || (uint64_t)sp.ctrl_first + sp.n_ctrl > d->n_keyframes) return fail(TRB_INVALID_ARG, "spline control points out of bounds");
         if (sp.n_ctrl > 1) {
-            if (sp.knot_first + sp.n_knots > d->n_knots) return fail(TRB_INVALID_ARG, "spline knots out of bounds");
-            if (sp.n_knots != sp.n_ctrl + sp.degree + 1) return fail(TRB_INVALID_ARG, "Invalid B-spline: knots.len() != control_points.len() + degree + 1");
+            if ((uint64_t)sp.knot_first + sp.n_knots > d->n_knots) return fail(TRB_INVALID_ARG, "spline knots out of bounds");
+            if (sp.n_ctrl <= sp.degree) return fail(TRB_INVALID_ARG, "Too few control points for curve"); // BSpline::new panics with this message
+            if ((uint64_t)sp.n_knots != (uint64_t)sp.n_ctrl + sp.degree + 1) return fail(TRB_INVALID_ARG, "Invalid B-spline: knots.len() != control_points.len() + degree + 1");
             if (sp.degree > (uint32_t)trbh::kMaxSplineDegree) return fail(TRB_UNSUPPORTED, "B-spline degree above 5");
+            for (uint32_t i = 0; i < sp.n_knots; ++i) if (d->knots[sp.knot_first + i] != d->knots[sp.knot_first + i]) return fail(TRB_INVALID_ARG, "NaN knot in B-spline"); // BSpline::new sorts with partial_cmp().unwrap(): panics on NaN
         }
     }
     if (!light) return fail(TRB_INVALID_ARG, "At least one light is required"); // multithreaded.rs:39
     for (uint32_t i = 0; i < d->n_cameras; ++i) {
         const trb_camera& c = d->cameras[i];
         if (c.n_fov_ctrl) { // CameraFov::Animated (camera.rs:95-125)
-            if (c.fov_ctrl_first + c.n_fov_ctrl > d->n_fov_floats || c.fov_knot_first + c.n_fov_knots > d->n_fov_floats) return fail(TRB_INVALID_ARG, "fov spline out of bounds");
-            if (c.n_fov_knots != c.n_fov_ctrl + c.fov_degree + 1) return fail(TRB_INVALID_ARG, "Invalid B-spline: knots.len() != control_points.len() + degree + 1");
+            if ((uint64_t)c.fov_ctrl_first + c.n_fov_ctrl > d->n_fov_floats || (uint64_t)c.fov_knot_first + c.n_fov_knots > d->n_fov_floats) return fail(TRB_INVALID_ARG, "fov spline out of bounds");
+            if (c.n_fov_ctrl <= c.fov_degree) return fail(TRB_INVALID_ARG, "Too few control points for curve");
+            if ((uint64_t)c.n_fov_knots != (uint64_t)c.n_fov_ctrl + c.fov_degree + 1) return fail(TRB_INVALID_ARG, "Invalid B-spline: knots.len() != control_points.len() + degree + 1");
+            for (uint32_t i = 0; i < c.n_fov_knots; ++i) if (d->fov_floats[c.fov_knot_first + i] != d->fov_floats[c.fov_knot_first + i]) return fail(TRB_INVALID_ARG, "NaN knot in B-spline");
             if (c.fov_degree > (uint32_t)trbh::kMaxSplineDegree) return fail(TRB_UNSUPPORTED, "B-spline degree above 5");
         }
-        if (c.spline_first + c.n_splines > d->n_splines) return fail(TRB_INVALID_ARG, "camera spline range out of bounds");
+        if ((uint64_t)c.spline_first + c.n_splines > d->n_splines) return fail(TRB_INVALID_ARG, "camera spline range out of bounds");
     }
     for (uint32_t i = 0; i < d->n_materials; ++i) {
         if (d->materials[i].type > TRB_MAT_MERL) return fail(TRB_INVALID_ARG, "unrecognized material type");
@@ -282,31 +321,36 @@ trb_status validate(const trb_scene_desc* d) {
     return TRB_OK;
 }
 
-trb_status ensure_blocks(trb_scene* s, const trb_render_cfg* cfg, uint32_t* n_blocks) {
-    const uint32_t start = cfg->block_start, count = cfg->block_count;
+// The selected, sharded block list on the device. Lists are cached per selection and never overwritten in place, so a
+// pass still in flight on a caller stream keeps reading valid memory when the next call selects other blocks.
+trb_status ensure_blocks(trb_scene* s, const trb_render_cfg* cfg, const uint2** d_blocks, uint32_t* n_blocks) {
     if (cfg->shard_count > 1 && cfg->shard_index >= cfg->shard_count) return fail(TRB_INVALID_ARG, "shard_index must be < shard_count");
-    if (s->cached_block_start != start || s->cached_block_count != count || s->cached_shard[0] != cfg->shard_index ||
-        s->cached_shard[1] != cfg->shard_count || s->cached_shard[2] != cfg->shard_chunk) {
-        s->cached_blocks = morton_blocks(s->film.width, s->film.height, start, count, cfg->shard_index, cfg->shard_count, cfg->shard_chunk);
-        s->cached_shard[0] = cfg->shard_index; s->cached_shard[1] = cfg->shard_count; s->cached_shard[2] = cfg->shard_chunk;
-        const size_t n = s->cached_blocks.size() / 2;
-        if (n > s->blocks_capacity) {
-            CU(s->arena.alloc(n, &s->d_blocks));
-            s->blocks_capacity = n;
-        }
-        if (n) CU(cudaMemcpy(s->d_blocks, s->cached_blocks.data(), n * sizeof(uint2), cudaMemcpyHostToDevice));
-        s->cached_block_start = start; s->cached_block_count = count;
+    const uint32_t key[5] = {cfg->block_start, cfg->block_count, cfg->shard_index, cfg->shard_count, cfg->shard_chunk};
+    for (const BlockList& b : s->block_lists)
+        if (std::memcmp(b.key, key, sizeof key) == 0) { *d_blocks = b.dev; *n_blocks = (uint32_t)(b.host.size() / 2); return TRB_OK; }
+    if (s->block_lists.size() >= 16) { // bounded cache: retire everything once nothing can be reading it any more
+        CU(cudaDeviceSynchronize());
+        for (BlockList& b : s->block_lists) cudaFree(b.dev);
+        s->block_lists.clear();
     }
-    *n_blocks = (uint32_t)(s->cached_blocks.size() / 2);
+    BlockList bl;
+    std::memcpy(bl.key, key, sizeof key);
+    bl.host = morton_blocks(s->film.width, s->film.height, cfg->block_start, cfg->block_count, cfg->shard_index, cfg->shard_count, cfg->shard_chunk);
+    const size_t n = bl.host.size() / 2;
+    CU(cudaMalloc(reinterpret_cast<void**>(&bl.dev), std::max<size_t>(1, n) * sizeof(uint2)));
+    if (n) { cudaError_t e = cudaMemcpy(bl.dev, bl.host.data(), n * sizeof(uint2), cudaMemcpyHostToDevice); if (e != cudaSuccess) { cudaFree(bl.dev); CU(e); } }
+    s->block_lists.push_back(std::move(bl));
+    *d_blocks = s->block_lists.back().dev; *n_blocks = (uint32_t)n;
     return TRB_OK;
 }
 
 trb_status resolve_samples(const trb_scene* s, const trb_render_cfg* cfg, uint32_t& spp, uint32_t& first, uint32_t& count) {
+    if (cfg->spp > (1u << 31)) return fail(TRB_INVALID_ARG, "spp too large");
     spp = cfg->spp ? pow2_ceil(cfg->spp) : s->spp_pow2; // ld.rs:22-26
     first = cfg->sample_first;
     if (first > spp) return fail(TRB_INVALID_ARG, "sample_first exceeds spp");
     count = cfg->sample_count ? cfg->sample_count : spp - first;
-    if (first + count > spp) return fail(TRB_INVALID_ARG, "sample range exceeds spp");
+    if ((uint64_t)first + count > spp) return fail(TRB_INVALID_ARG, "sample range exceeds spp");
     return TRB_OK;
 }
 
@@ -324,32 +368,39 @@ trb_status launch_render_t(trb_scene* s, const trb::RenderParams& rp, uint32_t f
 }
 trb_status ensure_wavefront(trb_scene* s, size_t n_paths) {
     if (n_paths <= s->wf_capacity) return TRB_OK;
+    CU(cudaDeviceSynchronize()); // a pass still in flight owns the old buffers
     for (void* p : s->wf_allocs) cudaFree(p);
     s->wf_allocs.clear(); s->wf_capacity = 0;
-    const size_t cap = n_paths + n_paths / 16 + 1024;
-    auto grab = [&](size_t bytes, void** out) -> cudaError_t {
-        cudaError_t e = cudaMalloc(out, bytes);
-        if (e == cudaSuccess) s->wf_allocs.push_back(*out);
-        return e;
+    const size_t cap = n_paths;
+    cudaError_t err = cudaSuccess;
+    auto grab = [&](size_t bytes, void** out) {
+        if (err != cudaSuccess) return;
+        err = cudaMalloc(out, bytes);
+        if (err == cudaSuccess) s->wf_allocs.push_back(*out);
     };
     trb::WfState& w = s->wf;
     float4** f4[] = {&w.org, &w.cont, &w.shadow, &w.mis, &w.a, &w.b, &w.tprev, &w.thr, &w.illum, &w.ng, &w.rad};
-    for (float4** q : f4) CU(grab(cap * sizeof(float4), reinterpret_cast<void**>(q)));
-    CU(grab(cap * sizeof(uint4), reinterpret_cast<void**>(&w.hit)));
+    for (float4** q : f4) grab(cap * sizeof(float4), reinterpret_cast<void**>(q));
+    grab(cap * sizeof(uint4), reinterpret_cast<void**>(&w.hit));
     uint32_t** u1[] = {&w.q_active[0], &w.q_active[1], &w.q_cont, &w.q_shadow, &w.q_mis};
-    for (uint32_t** q : u1) CU(grab(cap * sizeof(uint32_t), reinterpret_cast<void**>(q)));
-    CU(grab(64 * trb::WF_CNT * sizeof(uint32_t), reinterpret_cast<void**>(&w.counters)));
+    for (uint32_t** q : u1) grab(cap * sizeof(uint32_t), reinterpret_cast<void**>(q));
+    grab(64 * trb::WF_CNT * sizeof(uint32_t), reinterpret_cast<void**>(&w.counters));
+    if (err != cudaSuccess) {
+        for (void* p : s->wf_allocs) cudaFree(p);
+        s->wf_allocs.clear();
+        cudaGetLastError();
+        return fail(err == cudaErrorMemoryAllocation ? TRB_OOM : TRB_CUDA, std::string("wavefront state: ") + cudaGetErrorString(err));
+    }
     s->wf_capacity = cap;
     return TRB_OK;
 }
 
-// Wavefront pass: generate, then (trace, shade) per bounce round, then the film (DESIGN.md "Execution shape").
+// One wavefront pass over rp's blocks x samples: generate, then (trace, shade) per bounce round, then the film
+// (DESIGN.md "Execution shape"). n_paths = blocks * 64 * sample_count must fit the allocated path state.
 trb_status launch_wavefront(trb_scene* s, const trb::RenderParams& rp, uint32_t flags, int mode, cudaStream_t st) {
     const size_t n_paths = (size_t)rp.n_blocks * 64 * rp.sample_count;
-    if (n_paths >= (1ull << 31)) return fail(TRB_INVALID_ARG, "pass too large: blocks*64*sample_count must be < 2^31; render in more passes");
-    if (s->integrator.max_depth + 3 > 60) return fail(TRB_UNSUPPORTED, "max_depth > 57");
-    trb_status r = ensure_wavefront(s, n_paths);
-    if (r != TRB_OK) return r;
+    if (n_paths > s->wf_capacity || n_paths >= (1ull << 30)) return fail(TRB_INVALID_ARG, "pass larger than the wavefront state");
+    const Tuning& tu = s->tune;
     trb::WfState wf = s->wf;
     wf.n_paths = (uint32_t)n_paths;
     const bool stats = (flags & TRB_RENDER_STATS) != 0;
@@ -361,22 +412,17 @@ trb_status launch_wavefront(trb_scene* s, const trb::RenderParams& rp, uint32_t 
     else trb::k_wf_generate<false><<<gen_grid, 256, 0, st>>>(s->ds, rp, wf);
     g_launches++;
     const unsigned shade_grid = (unsigned)s->sm_count * 4;
+    const int refill = tu.refill, occ = tu.occ, sst = tu.smem_stack;
+    const unsigned tgrid = (unsigned)s->sm_count * tu.trace_grid;
+    const uint32_t sched = tu.sched;   // 0 = flat state machine; else the quorum of the phased loop (see k_wf_trace)
+    const bool quads = tu.quads != 0;  // DQuad two-level records (never in the STATS variants: their counters are the reference's)
     for (uint32_t round = 0; round < rounds; ++round) {
-        const int refill = getenv("TRB_REFILL") ? atoi(getenv("TRB_REFILL")) : 8;
-        const int occ = getenv("TRB_TRACE_OCC") ? atoi(getenv("TRB_TRACE_OCC")) : 7;
-        const unsigned tg = getenv("TRB_TRACE_GRID") ? (unsigned)atoi(getenv("TRB_TRACE_GRID")) : 12u;
-        const unsigned tgrid = (unsigned)s->sm_count * tg;
         std::pair<cudaEvent_t, cudaEvent_t> ev{nullptr, nullptr};
         if (flags & TRB_RENDER_TIME_TRACE) {
             if (!s->event_pool.empty()) { ev = s->event_pool.back(); s->event_pool.pop_back(); }
             else { CU(cudaEventCreate(&ev.first)); CU(cudaEventCreate(&ev.second)); }
             CU(cudaEventRecord(ev.first, st));
         }
-        const int sst = getenv("TRB_SMEM_STACK") ? atoi(getenv("TRB_SMEM_STACK")) : 16;
-        // TRB_TRACE_SCHED: 0 = flat state machine; else the quorum of the phased loop (see k_wf_trace)
-        const uint32_t sched = getenv("TRB_TRACE_SCHED") ? (uint32_t)strtoul(getenv("TRB_TRACE_SCHED"), nullptr, 0) : 6u; // read per launch: tools/sched_sweep.py
-        // TRB_TRACE_QUADS=1: two-level DQuad records instead of child-pair records (never in the STATS variants: their counters are the reference's)
-        const bool quads = getenv("TRB_TRACE_QUADS") && atoi(getenv("TRB_TRACE_QUADS")) != 0; // measured 3-6 % slower than pairs on C4: off by default
 #define TRB_TRACE_LAUNCH(ST, MB, SS, AN, PH, QD) trb::k_wf_trace<ST, MB, SS, AN, PH, QD><<<tgrid, 128, 0, st>>>(s->ds, rp, wf, round, flags, refill, sched)
         if (anim) { if (stats) TRB_TRACE_LAUNCH(true, 4, 16, true, true, false); else TRB_TRACE_LAUNCH(false, 7, 16, true, true, false); }
         else if (stats) { if (sched) TRB_TRACE_LAUNCH(true, 4, 16, false, true, false); else TRB_TRACE_LAUNCH(true, 4, 16, false, false, false); }
@@ -401,8 +447,7 @@ trb_status launch_wavefront(trb_scene* s, const trb::RenderParams& rp, uint32_t 
     if (mode == 0) {
         const int T = 9 + 2 * std::max(s->ds.fpw_x, s->ds.fpw_y);
         const unsigned film_grid = std::min<unsigned>(rp.n_blocks, (unsigned)s->sm_count * 8);
-        const bool film_v2 = !(getenv("TRB_FILM_V2") && atoi(getenv("TRB_FILM_V2")) == 0); // TRB_FILM_V2=0: the shared-atomics kernel (profiles/r01_film_v2_check.json)
-        if (film_v2) trb::k_wf_film_v2<<<film_grid, trb::RENDER_THREADS, (size_t)4 * T * T * sizeof(float4), st>>>(s->ds, rp, wf);
+        if (tu.film_v2) trb::k_wf_film_v2<<<film_grid, trb::RENDER_THREADS, (size_t)4 * T * T * sizeof(float4), st>>>(s->ds, rp, wf);
         else trb::k_wf_film<<<film_grid, trb::RENDER_THREADS, (size_t)T * T * sizeof(float4), st>>>(s->ds, rp, wf);
         g_launches++;
     }
@@ -410,8 +455,42 @@ trb_status launch_wavefront(trb_scene* s, const trb::RenderParams& rp, uint32_t 
     return TRB_OK;
 }
 
+// Exec::render renders every selected block at the full spp in one call (multithreaded.rs:55-114). The wavefront keeps
+// 212 B of path state per camera sample in HBM, so a frame is cut into additive passes of at most `pass_paths` camera
+// samples (fewer if device memory is short): all selected blocks x a sample sub-range, or — for images with more than
+// pass_paths / 64 blocks — a block sub-range x one sample. A camera sample's radiance is a pure function of
+// (scene, seed, pixel, sample index), so the split changes nothing but the order of the film's float additions.
+trb_status render_passes(trb_scene* s, trb::RenderParams rp, uint32_t flags, int mode, cudaStream_t st) {
+    const uint32_t nb = rp.n_blocks, first = rp.sample_first, count = rp.sample_count;
+    const uint2* blocks = rp.blocks;
+    const uint64_t total = (uint64_t)nb * 64 * count;
+    uint64_t want = std::min<uint64_t>(total, std::min<uint64_t>(std::max<uint64_t>(s->tune.pass_paths, 64), (1ull << 30) - 64));
+    if (mode == 1) { // per-sample records are indexed by the path number of ONE pass
+        if (total >= (1ull << 30)) return fail(TRB_INVALID_ARG, "sample buffer too large: blocks*64*sample_count must be < 2^30; select fewer blocks or samples");
+        want = total;
+    }
+    want = ((want + 63) / 64) * 64;
+    if (want > s->wf_capacity) {
+        trb_status r;
+        while ((r = ensure_wavefront(s, (size_t)want)) == TRB_OOM && want > (1u << 16) && mode == 0) want = ((want / 2 + 63) / 64) * 64;
+        if (r != TRB_OK) return r;
+    }
+    const uint64_t cap = std::max<uint64_t>(want, 64);  // paths per pass actually used (a larger state left by an earlier call is not required)
+    uint32_t bp, sp;
+    if ((uint64_t)nb * 64 <= cap) { bp = nb; sp = (uint32_t)std::min<uint64_t>(count, cap / ((uint64_t)nb * 64)); }
+    else { bp = (uint32_t)(cap / 64); sp = 1; }
+    for (uint32_t b0 = 0; b0 < nb; b0 += bp)
+        for (uint32_t s0 = 0; s0 < count; s0 += sp) {
+            rp.blocks = blocks + b0; rp.n_blocks = std::min(bp, nb - b0);
+            rp.sample_first = first + s0; rp.sample_count = std::min(sp, count - s0);
+            trb_status r = launch_wavefront(s, rp, flags, mode, st);
+            if (r != TRB_OK) return r;
+        }
+    return TRB_OK;
+}
+
 trb_status launch_render(trb_scene* s, const trb::RenderParams& rp, uint32_t flags, int mode, cudaStream_t st) {
-    if (!(flags & TRB_RENDER_MEGAKERNEL)) return launch_wavefront(s, rp, flags, mode, st);
+    if (!(flags & TRB_RENDER_MEGAKERNEL)) return render_passes(s, rp, flags, mode, st);
     const bool stats = (flags & TRB_RENDER_STATS) != 0;
     CU(cudaMemsetAsync(rp.work_counter, 0, sizeof(uint32_t), st));
     if (s->ds.has_anim) {
@@ -443,6 +522,34 @@ void trb_internal_set_error(const char* msg) { g_error = msg ? msg : ""; } // us
 uint32_t trb_abi_version(void) { return TRB_ABI_VERSION; }
 unsigned long long trb_launch_count(void) { return g_launches; }
 
+trb_status trb_scene_set_option(trb_scene* s, const char* name, long long value) {
+    if (!s || !name) return fail(TRB_INVALID_ARG, "null argument");
+    Tuning& t = s->tune;
+    const std::string k(name);
+    if (k == "trace.refill") t.refill = (int)value;
+    else if (k == "trace.occupancy") t.occ = (int)value;
+    else if (k == "trace.grid") t.trace_grid = (unsigned)std::max<long long>(1, value);
+    else if (k == "trace.smem_stack") t.smem_stack = (int)value;
+    else if (k == "trace.sched") t.sched = (uint32_t)value;
+    else if (k == "trace.quads") t.quads = (int)value;
+    else if (k == "film.v2") t.film_v2 = (int)value;
+    else if (k == "sort.mode") t.sort = (int)value;
+    else if (k == "sort.bits") t.sort_bits = (int)std::min<long long>(6, std::max<long long>(1, value));
+    else if (k == "sort.min_round") t.sort_min_round = (int)value;
+    else if (k == "shade.split") t.shade_split = (int)value;
+    else if (k == "pass.graph") t.graph = (int)value;
+    else if (k == "pass.paths") { if (value < 64) return fail(TRB_INVALID_ARG, "pass.paths must be >= 64"); t.pass_paths = (uint64_t)value; }
+    else return fail(TRB_INVALID_ARG, "unknown option: " + k);
+    return TRB_OK;
+}
+
+trb_status trb_scene_check_error(trb_scene* s) {
+    if (!s) return fail(TRB_INVALID_ARG, "null scene");
+    CU(cudaSetDevice(s->device));
+    CU(cudaDeviceSynchronize());
+    return check_error_flag(s);
+}
+
 trb_status trb_scene_trace_time(trb_scene* s, float* total_ms, uint32_t* n_launches) {
     if (!s || !total_ms || !n_launches) return fail(TRB_INVALID_ARG, "null argument");
     CU(cudaSetDevice(s->device));
@@ -470,6 +577,7 @@ trb_status trb_scene_create(const trb_scene_desc* d, int device, trb_scene** out
     CU(cudaSetDevice(device));
     std::unique_ptr<trb_scene> s(new trb_scene);
     s->device = device;
+    tuning_from_env(s->tune);
     cudaDeviceProp prop;
     CU(cudaGetDeviceProperties(&prop, device));
     s->sm_count = prop.multiProcessorCount;
@@ -480,8 +588,12 @@ trb_status trb_scene_create(const trb_scene_desc* d, int device, trb_scene** out
     s->splines.assign(d->splines, d->splines + d->n_splines);
     s->keyframes.assign(d->keyframes, d->keyframes + d->n_keyframes);
     s->knots.assign(d->knots, d->knots + d->n_knots);
+    for (const trb_spline& sp : s->splines) // BSpline::new sorts its knots (bspline 0.2.2); ranges were bounds-checked by validate()
+        if (sp.n_ctrl > 1) std::stable_sort(s->knots.begin() + sp.knot_first, s->knots.begin() + sp.knot_first + sp.n_knots);
     s->color_keys.assign(d->color_keys, d->color_keys + d->n_color_keys);
     if (d->n_fov_floats) s->fov_floats.assign(d->fov_floats, d->fov_floats + d->n_fov_floats);
+    for (const trb_camera& c : s->cameras)
+        if (c.n_fov_ctrl) std::stable_sort(s->fov_floats.begin() + c.fov_knot_first, s->fov_floats.begin() + c.fov_knot_first + c.n_fov_knots);
     s->materials.assign(d->materials, d->materials + d->n_materials);
 
     // meshes: BVH<Triangle> with max_geom 16 (mesh.rs:44), then leaf-ordered triangle records
@@ -632,6 +744,9 @@ trb_status trb_scene_info(const trb_scene* s, uint32_t* w, uint32_t* h, uint32_t
 trb_status trb_scene_update_frame(trb_scene* s, uint32_t frame, float start, float end) {
     if (!s) return fail(TRB_INVALID_ARG, "null scene");
     CU(cudaSetDevice(s->device));
+    // A frame boundary: passes enqueued with trb_render_device may still be reading the instances / TLAS this call
+    // overwrites, so the device is drained first (the reference's update_frame likewise runs between renders, scene.rs:152).
+    CU(cudaDeviceSynchronize());
     // camera selection (scene.rs:153-166)
     int cam;
     if (s->active_camera >= 0) {
@@ -736,13 +851,14 @@ trb_status trb_render_device(trb_scene* s, const trb_render_cfg* cfg, float* d_f
     if (!s->frame_ready) return fail(TRB_INVALID_ARG, "Update frame must be called before rendering"); // scene.rs:179
     CU(cudaSetDevice(s->device));
     uint32_t spp, first, count, nb;
+    const uint2* d_blocks = nullptr;
     trb_status r = resolve_samples(s, cfg, spp, first, count);
     if (r != TRB_OK) return r;
-    r = ensure_blocks(s, cfg, &nb);
+    r = ensure_blocks(s, cfg, &d_blocks, &nb);
     if (r != TRB_OK) return r;
     if (nb == 0 || count == 0) return TRB_OK; // "Warning: This block queue is empty!" (block_queue.rs:42-44)
     trb::RenderParams rp{};
-    rp.blocks = s->d_blocks; rp.n_blocks = nb; rp.spp = spp; rp.sample_first = first; rp.sample_count = count; rp.seed = cfg->seed;
+    rp.blocks = d_blocks; rp.n_blocks = nb; rp.spp = spp; rp.sample_first = first; rp.sample_count = count; rp.seed = cfg->seed;
     rp.work_counter = s->d_counter; rp.film = reinterpret_cast<float4*>(d_film); rp.stats = reinterpret_cast<trb::DStats*>(d_stats);
     rp.error_flag = s->d_error;
     return launch_render(s, rp, cfg->flags, 0, static_cast<cudaStream_t>(stream));
@@ -796,9 +912,10 @@ trb_status trb_render_samples(trb_scene* s, const trb_render_cfg* cfg, size_t n,
     if (!s->frame_ready) return fail(TRB_INVALID_ARG, "Update frame must be called before rendering");
     CU(cudaSetDevice(s->device));
     uint32_t spp, first, count, nb;
+    const uint2* d_blocks = nullptr;
     trb_status r = resolve_samples(s, cfg, spp, first, count);
     if (r != TRB_OK) return r;
-    r = ensure_blocks(s, cfg, &nb);
+    r = ensure_blocks(s, cfg, &d_blocks, &nb);
     if (r != TRB_OK) return r;
     if (n != (size_t)nb * 64 * count) return fail(TRB_INVALID_ARG, "sample buffer size must be blocks*64*sample_count");
     if (n == 0) return TRB_OK;
@@ -806,7 +923,7 @@ trb_status trb_render_samples(trb_scene* s, const trb_render_cfg* cfg, size_t n,
     CU(cudaMalloc(&d_out, n * sizeof(trb_sample)));
     CU(cudaMemsetAsync(s->d_stats, 0, sizeof(trb::DStats), 0));
     trb::RenderParams rp{};
-    rp.blocks = s->d_blocks; rp.n_blocks = nb; rp.spp = spp; rp.sample_first = first; rp.sample_count = count; rp.seed = cfg->seed;
+    rp.blocks = d_blocks; rp.n_blocks = nb; rp.spp = spp; rp.sample_first = first; rp.sample_count = count; rp.seed = cfg->seed;
     rp.work_counter = s->d_counter; rp.film = nullptr; rp.samples_out = d_out; rp.stats = s->d_stats; rp.error_flag = s->d_error;
     CU(cudaEventRecord(s->ev0, 0));
     r = launch_render(s, rp, cfg->flags, 1, 0);
@@ -832,9 +949,10 @@ trb_status trb_camera_rays(trb_scene* s, const trb_render_cfg* cfg, size_t n, tr
     if (!s->frame_ready) return fail(TRB_INVALID_ARG, "Update frame must be called before rendering");
     CU(cudaSetDevice(s->device));
     uint32_t spp, first, count, nb;
+    const uint2* d_blocks = nullptr;
     trb_status r = resolve_samples(s, cfg, spp, first, count);
     if (r != TRB_OK) return r;
-    r = ensure_blocks(s, cfg, &nb);
+    r = ensure_blocks(s, cfg, &d_blocks, &nb);
     if (r != TRB_OK) return r;
     if (n != (size_t)nb * 64 * count) return fail(TRB_INVALID_ARG, "ray buffer size must be blocks*64*sample_count");
     if (n == 0) return TRB_OK;
@@ -843,7 +961,7 @@ trb_status trb_camera_rays(trb_scene* s, const trb_render_cfg* cfg, size_t n, tr
     cudaError_t e = cudaMalloc(&d_xy, n * 2 * sizeof(float));
     if (e != cudaSuccess) { cudaFree(d_rays); CU(e); }
     trb::RenderParams rp{};
-    rp.blocks = s->d_blocks; rp.n_blocks = nb; rp.spp = spp; rp.sample_first = first; rp.sample_count = count; rp.seed = cfg->seed;
+    rp.blocks = d_blocks; rp.n_blocks = nb; rp.spp = spp; rp.sample_first = first; rp.sample_count = count; rp.seed = cfg->seed;
     if (s->ds.has_anim) trb::k_camera_rays<true><<<(unsigned)std::min<size_t>((n + 255) / 256, 148 * 8), 256>>>(s->ds, rp, d_rays, d_xy);
     else trb::k_camera_rays<false><<<(unsigned)std::min<size_t>((n + 255) / 256, 148 * 8), 256>>>(s->ds, rp, d_rays, d_xy);
     e = cudaGetLastError();
@@ -1057,15 +1175,18 @@ trb_status trb_host_animated_transform(const trb_scene_desc* d, uint32_t first, 
     if (!d || !mat16 || !inv16) return fail(TRB_INVALID_ARG, "null argument");
     const trb_status r = validate(d);
     if (r != TRB_OK) return r;
-    if (first + count > d->n_splines) return fail(TRB_INVALID_ARG, "spline range out of bounds");
-    const Xf x = trbh::animated_xf(d->splines, first, count, d->keyframes, d->knots, time);
+    if ((uint64_t)first + count > d->n_splines) return fail(TRB_INVALID_ARG, "spline range out of bounds");
+    std::vector<float> knots(d->knots, d->knots + d->n_knots); // BSpline::new sorts its knots
+    for (uint32_t k = first; k < first + count; ++k)
+        if (d->splines[k].n_ctrl > 1) std::stable_sort(knots.begin() + d->splines[k].knot_first, knots.begin() + d->splines[k].knot_first + d->splines[k].n_knots);
+    const Xf x = trbh::animated_xf(d->splines, first, count, d->keyframes, knots.data(), time);
     std::memcpy(mat16, x.fwd.m, 64); std::memcpy(inv16, x.inv.m, 64);
     return TRB_OK;
 }
 
 trb_status trb_host_animated_color(const trb_scene_desc* d, uint32_t first, uint32_t count, float time, float* rgb3) {
     if (!d || !rgb3) return fail(TRB_INVALID_ARG, "null argument");
-    if (count == 0 || first + count > d->n_color_keys) return fail(TRB_INVALID_ARG, "colour key range out of bounds");
+    if (count == 0 || (uint64_t)first + count > d->n_color_keys) return fail(TRB_INVALID_ARG, "colour key range out of bounds");
     trbh::animated_color(d->color_keys, first, count, time, rgb3);
     return TRB_OK;
 }

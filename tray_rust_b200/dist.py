@@ -16,6 +16,12 @@ def shard_blocks(n_blocks, rank, world):
     return start, count
 
 
+def shard_is_empty(shard):
+    """True when `shard_blocks` gave this rank nothing (n_blocks < world). Such a rank must SKIP the render call:
+    in the ABI (and in block_queue.rs:39-41) block_count == 0 selects ALL blocks, which would over-count the film."""
+    return shard[1] == 0
+
+
 def shard_interleaved(rank, world, chunk=32):
     """Load-balanced alternative: rank r takes every world-th chunk of `chunk` consecutive blocks of the Morton list
     (render-cfg fields shard_index / shard_count / shard_chunk). Same union, same summed film; image regions of very
