@@ -152,6 +152,31 @@ def test_c5_tr15_like_1920x1080_one_call():
         lib.trb_desc_free(d)
 
 
+def test_c5_tr15_json_1920x1080_synthetic_assets_one_call():
+    """configs[4] as specified: the reference's scenes/tr15.json (59 instances, keyframed camera / groups / objects, 10 disk
+    lights with keyframed emission, 20 materials incl. 5 MERL tables) with synthetic stand-ins for its 13 OBJ and 5 MERL
+    assets (tests/golden/make_tr15.py). Frame 300 of 600 (mid-animation, lights on), whole frame in one call."""
+    import make_tr15
+    make_tr15.write_assets()
+    d, lib = load_json("c5_tr15.json", 1920, 1080, 4096)
+    try:
+        desc = d.contents
+        assert (desc.n_instances, desc.n_meshes, desc.n_materials, desc.n_merl, desc.film.frames) == (59, 25, 20, 5, 600)
+        g, o = api.Scene(desc), O.OracleScene(desc)
+        full, st = g.render(spp=2, seed=9, current_frame=300)
+        assert st.camera_samples == 1920 * 1080 * 2 and np.isfinite(full).all() and img(full).mean() > 0.005
+        step = desc.film.scene_time / desc.film.frames
+        nb = g.n_blocks()
+        for fr in (0, 300):
+            o.update_frame(fr, fr * step, (fr + 1) * step)
+            g.update_frame(fr, fr * step, (fr + 1) * step)
+            gn, go = g.bvh(-1); on, oo = o.bvh(-1)
+            assert gn.tobytes() == on.tobytes() and np.array_equal(go, oo)
+            check_ranges(g, o, [(8000, 64), (nb // 2 + 500, 96)], 2, 9, frame=fr)
+    finally:
+        lib.trb_desc_free(d)
+
+
 def test_total_rays_compared_with_the_oracle():
     """>= 1e8 rays compared bit for bit over C1 / C3 / C4 (runs last in this file)."""
     print("rays compared with the oracle in this file:", RAYS["total"])
