@@ -379,12 +379,20 @@ trb_status ensure_wavefront(trb_scene* s, size_t n_paths) {
         if (err == cudaSuccess) s->wf_allocs.push_back(*out);
     };
     trb::WfState& w = s->wf;
-    float4** f4[] = {&w.org, &w.cont, &w.shadow, &w.mis, &w.a, &w.b, &w.tprev, &w.thr, &w.illum, &w.ng, &w.rad};
+    float4** f4[] = {&w.org, &w.cont, &w.shadow, &w.mis, &w.a, &w.b, &w.tprev, &w.thr, &w.illum, &w.ng, &w.rad, &w.f_p, &w.f_n, &w.f_t, &w.f_b};
     for (float4** q : f4) grab(cap * sizeof(float4), reinterpret_cast<void**>(q));
     grab(cap * sizeof(uint4), reinterpret_cast<void**>(&w.hit));
-    uint32_t** u1[] = {&w.q_active[0], &w.q_active[1], &w.q_cont, &w.q_shadow, &w.q_mis};
+    uint32_t** u1[] = {&w.q_active[0], &w.q_active[1], &w.q_cont, &w.q_shadow, &w.q_mis, &w.q_mid};
     for (uint32_t** q : u1) grab(cap * sizeof(uint32_t), reinterpret_cast<void**>(q));
     grab(64 * trb::WF_CNT * sizeof(uint32_t), reinterpret_cast<void**>(&w.counters));
+    // ray sorting: up to three rays per path and round; bins for the finest grid the options allow
+    const size_t max_bins = (size_t)3 * (8u << (3 * trb::WF_SORT_MAX_BITS));
+    uint32_t** u3[] = {&w.q_sorted, &w.sort_key, &w.sort_rank};
+    for (uint32_t** q : u3) grab(3 * cap * sizeof(uint32_t), reinterpret_cast<void**>(q));
+    grab(max_bins * sizeof(uint32_t), reinterpret_cast<void**>(&w.sort_hist));
+    grab(max_bins * sizeof(uint32_t), reinterpret_cast<void**>(&w.sort_offs));
+    grab(64 * 8 * sizeof(uint32_t), reinterpret_cast<void**>(&w.bounds));
+    if (err == cudaSuccess) err = cudaMemset(w.sort_hist, 0, max_bins * sizeof(uint32_t)); // invariant: all zero between sorts (the scan clears what it reads)
     if (err != cudaSuccess) {
         for (void* p : s->wf_allocs) cudaFree(p);
         s->wf_allocs.clear();
@@ -417,13 +425,23 @@ trb_status launch_wavefront(trb_scene* s, const trb::RenderParams& rp, uint32_t 
     const uint32_t sched = tu.sched;   // 0 = flat state machine; else the quorum of the phased loop (see k_wf_trace)
     const bool quads = tu.quads != 0;  // DQuad two-level records (never in the STATS variants: their counters are the reference's)
     for (uint32_t round = 0; round < rounds; ++round) {
+        const uint32_t* q_sorted = nullptr;
+        if (tu.sort && (int)round >= tu.sort_min_round) { // counting sort of this round's rays by (type, octant, origin cell): DESIGN.md "Ray sorting"
+            const uint32_t bits = (uint32_t)std::min(trb::WF_SORT_MAX_BITS, std::max(1, tu.sort_bits));
+            const unsigned sgrid = (unsigned)s->sm_count * 8;
+            trb::k_wf_sort_count<<<sgrid, 256, 0, st>>>(wf, round, bits, tu.sort == 2 ? 1u : 0u);
+            trb::k_wf_sort_scan<<<1, 1024, 0, st>>>(wf, 3u * (8u << (3u * bits)));
+            trb::k_wf_sort_scatter<<<sgrid, 256, 0, st>>>(wf, round);
+            g_launches += 3;
+            q_sorted = wf.q_sorted;
+        }
         std::pair<cudaEvent_t, cudaEvent_t> ev{nullptr, nullptr};
         if (flags & TRB_RENDER_TIME_TRACE) {
             if (!s->event_pool.empty()) { ev = s->event_pool.back(); s->event_pool.pop_back(); }
             else { CU(cudaEventCreate(&ev.first)); CU(cudaEventCreate(&ev.second)); }
             CU(cudaEventRecord(ev.first, st));
         }
-#define TRB_TRACE_LAUNCH(ST, MB, SS, AN, PH, QD) trb::k_wf_trace<ST, MB, SS, AN, PH, QD><<<tgrid, 128, 0, st>>>(s->ds, rp, wf, round, flags, refill, sched)
+#define TRB_TRACE_LAUNCH(ST, MB, SS, AN, PH, QD) trb::k_wf_trace<ST, MB, SS, AN, PH, QD><<<tgrid, 128, 0, st>>>(s->ds, rp, wf, round, flags, refill, sched, q_sorted)
         if (anim) { if (stats) TRB_TRACE_LAUNCH(true, 4, 16, true, true, false); else TRB_TRACE_LAUNCH(false, 7, 16, true, true, false); }
         else if (stats) { if (sched) TRB_TRACE_LAUNCH(true, 4, 16, false, true, false); else TRB_TRACE_LAUNCH(true, 4, 16, false, false, false); }
         else if (sched == 0) { if (occ >= 8) TRB_TRACE_LAUNCH(false, 8, 16, false, false, false); else if (occ >= 7) TRB_TRACE_LAUNCH(false, 7, 16, false, false, false); else TRB_TRACE_LAUNCH(false, 6, 16, false, false, false); }
@@ -436,6 +454,24 @@ trb_status launch_wavefront(trb_scene* s, const trb::RenderParams& rp, uint32_t 
         else TRB_TRACE_LAUNCH(false, 7, 20, false, true, false);
 #undef TRB_TRACE_LAUNCH
         if (ev.first) { CU(cudaEventRecord(ev.second, st)); s->trace_events.push_back(ev); }
+        if (tu.shade_split) { // three kernels with fewer live values each (DESIGN.md "Split shading"); same device functions, same results
+            if (anim) {
+                if (mode == 0) trb::k_wf_shade_a<0, true, 3><<<shade_grid, 128, 0, st>>>(s->ds, rp, wf, round);
+                else trb::k_wf_shade_a<1, true, 3><<<shade_grid, 128, 0, st>>>(s->ds, rp, wf, round);
+                trb::k_wf_shade_b<true, 3><<<shade_grid, 128, 0, st>>>(s->ds, rp, wf, round);
+                if (mode == 0) trb::k_wf_shade_c<0, true, 4><<<shade_grid, 128, 0, st>>>(s->ds, rp, wf, round);
+                else trb::k_wf_shade_c<1, true, 4><<<shade_grid, 128, 0, st>>>(s->ds, rp, wf, round);
+            } else {
+                const unsigned ga = (unsigned)s->sm_count * 6, gb = (unsigned)s->sm_count * 5, gc = (unsigned)s->sm_count * 6;
+                if (mode == 0) trb::k_wf_shade_a<0, false, 6><<<ga, 128, 0, st>>>(s->ds, rp, wf, round);
+                else trb::k_wf_shade_a<1, false, 6><<<ga, 128, 0, st>>>(s->ds, rp, wf, round);
+                trb::k_wf_shade_b<false, 5><<<gb, 128, 0, st>>>(s->ds, rp, wf, round);
+                if (mode == 0) trb::k_wf_shade_c<0, false, 6><<<gc, 128, 0, st>>>(s->ds, rp, wf, round);
+                else trb::k_wf_shade_c<1, false, 6><<<gc, 128, 0, st>>>(s->ds, rp, wf, round);
+            }
+            g_launches += 4;
+            continue;
+        }
         // (occupancy 5 / 6 variants of the shade kernel were measured 1-2 % slower: spills outweigh the extra warps)
         if (anim) {
             if (mode == 0) trb::k_wf_shade<0, true, 3><<<shade_grid, 128, 0, st>>>(s->ds, rp, wf, round);

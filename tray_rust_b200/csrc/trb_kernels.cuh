@@ -1212,9 +1212,13 @@ struct BounceOut {
     f3 org;              // bsdf.p
     bool specular, terminate; // terminate: no continuation ray (black f / pdf 0 / RR / max depth)
 };
+// The three independent parts of a bounce (shared by the fused and the split shade kernels, so both run the same operations):
+//   bounce_emission  path.rs:71-76   emitted light seen directly / through specular bounces (Q1: the FIRST hit's normal)
+//   bounce_direct    path.rs:78-80   sample_one_light -> estimate_direct's set-up (integrator/mod.rs:106-169)
+//   bounce_scatter   path.rs:82-111  BSDF sample for the next direction, throughput, Russian roulette
 template <bool ANIM>
-__device__ __forceinline__ void shade_bounce(const DScene& sc, const Surf& s, uint32_t hit_inst, f3 ray_d, f3 first_ng, uint32_t bounce, bool prev_specular,
-                                             uint32_t hsample, f3 throughput_in, float time, f3& illum, BounceOut& o) {
+__device__ __forceinline__ void bounce_emission(const DScene& sc, uint32_t hit_inst, f3 ray_d, f3 first_ng, uint32_t bounce, bool prev_specular, f3 throughput_in,
+                                                float time, f3& illum) {
     const DInstance& in = sc.instances[hit_inst];
     if (bounce == 0 || prev_specular) {
         if (__ldg(&in.kind) != TRB_INST_RECEIVER) {
@@ -1226,22 +1230,24 @@ __device__ __forceinline__ void shade_bounce(const DScene& sc, const Surf& s, ui
             }
         }
     }
-    Mat m;
-    load_mat(sc.materials[__ldg(&in.material)], m);
-    Frame fr;
-    make_frame(s, fr);
-    const f3 wo = -ray_d;
+}
+template <bool ANIM>
+__device__ __forceinline__ void bounce_direct(const DScene& sc, const Mat& m, const Frame& fr, f3 wo, uint32_t bounce, uint32_t hsample, float time, DirectSetup& ds,
+                                              uint32_t& light) {
     PathRng rng; rng.h = hsample; rng.len = sc.max_depth + 1;
-    float l0, l1, b0, b1, q0, q1;
+    float l0, l1, b0, b1;
     rng.two_d(bounce, S_L0, S_L1, S_L_PERM, l0, l1);
     rng.two_d(bounce, S_B0, S_B1, S_B_PERM, b0, b1);
     const float lc = rng.one_d(bounce, S_LC, S_LC_PERM), bc = rng.one_d(bounce, S_BC, S_BC_PERM);
     uint32_t l = f2u(lc * (float)sc.n_lights); // sample_one_light (integrator/mod.rs:108-110), no xN (Q2)
     if (l > sc.n_lights - 1) l = sc.n_lights - 1;
-    o.light = __ldg(&sc.lights[l]);
-    direct_setup<ANIM>(sc, m, fr, wo, o.light, l0, l1, b0, b1, bc, time, o.ds);
-    o.t_before = throughput_in;
-    o.org = fr.p;
+    light = __ldg(&sc.lights[l]);
+    direct_setup<ANIM>(sc, m, fr, wo, light, l0, l1, b0, b1, bc, time, ds);
+}
+struct ScatterOut { f3 throughput, next_d; bool specular, terminate; };
+__device__ __forceinline__ void bounce_scatter(const DScene& sc, const Mat& m, const Frame& fr, f3 wo, uint32_t bounce, uint32_t hsample, f3 throughput_in, ScatterOut& o) {
+    PathRng rng; rng.h = hsample; rng.len = sc.max_depth + 1;
+    float q0, q1;
     rng.two_d(bounce, S_P0, S_P1, S_P_PERM, q0, q1);
     const float qc = rng.one_d(bounce, S_PC, S_PC_PERM);
     f3 f, wi; float pdf; uint32_t sampled;
@@ -1260,6 +1266,22 @@ __device__ __forceinline__ void shade_bounce(const DScene& sc, const Surf& s, ui
     if (bounce == sc.max_depth) return;
     o.next_d = unit(wi); // ray.child(&bsdf.p, &w_i.normalized()), min_t = 0.001
     o.terminate = false;
+}
+template <bool ANIM>
+__device__ __forceinline__ void shade_bounce(const DScene& sc, const Surf& s, uint32_t hit_inst, f3 ray_d, f3 first_ng, uint32_t bounce, bool prev_specular,
+                                             uint32_t hsample, f3 throughput_in, float time, f3& illum, BounceOut& o) {
+    bounce_emission<ANIM>(sc, hit_inst, ray_d, first_ng, bounce, prev_specular, throughput_in, time, illum);
+    Mat m;
+    load_mat(sc.materials[__ldg(&sc.instances[hit_inst].material)], m);
+    Frame fr;
+    make_frame(s, fr);
+    const f3 wo = -ray_d;
+    bounce_direct<ANIM>(sc, m, fr, wo, bounce, hsample, time, o.ds, o.light);
+    o.t_before = throughput_in;
+    o.org = fr.p;
+    ScatterOut so;
+    bounce_scatter(sc, m, fr, wo, bounce, hsample, throughput_in, so);
+    o.throughput = so.throughput; o.next_d = so.next_d; o.specular = so.specular; o.terminate = so.terminate;
 }
 
 // ------------------------------------------------------------------------------------------
@@ -1488,8 +1510,24 @@ struct WfState {
     uint32_t* q_cont; uint32_t* q_shadow; uint32_t* q_mis;
     uint32_t* counters; // per round: WF_CNT words
     uint32_t n_paths;
+    // ray-queue sorting (DESIGN.md "Ray sorting"): a counting sort of each round's rays by (octant, origin cell)
+    uint32_t* q_sorted;  // the round's rays in sorted order: type << 30 | path   (type 0 continuation, 1 shadow, 2 MIS)
+    uint32_t* sort_key;  // per queued ray: its bin
+    uint32_t* sort_rank; // per queued ray: its arrival rank inside the bin
+    uint32_t* sort_hist; // bins: counts (all zero between uses)
+    uint32_t* sort_offs; // bins: exclusive prefix sums
+    // split shading (k_wf_shade_a -> _b -> _c): the shading frame of the vertex (bsdf.rs:38-44) and the paths that reached it this round
+    float4* f_p;         // (frame origin p, hit instance)
+    float4* f_n;         // shading normal
+    float4* f_t;         // tangent
+    float4* f_b;         // bitangent
+    uint32_t* q_mid;     // paths to shade this round (survived resolve / termination / miss)
+    uint32_t* bounds;    // per round 8 words: min xyz, pad, max xyz, pad of the ray origins queued for that round (order-preserving uint encoding)
 };
-enum { WF_N_ACTIVE = 0, WF_N_CONT = 1, WF_N_SHADOW = 2, WF_N_MIS = 3, WF_TRACE_HEAD = 4, WF_SHADE_HEAD = 5, WF_CNT = 8 };
+constexpr uint32_t WF_PATH_MASK = 0x3fffffffu;
+constexpr int WF_SORT_MAX_BITS = 6; // origin grid up to 64^3 cells x 8 octants x 3 ray types = 6.3 M bins
+enum { WF_N_ACTIVE = 0, WF_N_CONT = 1, WF_N_SHADOW = 2, WF_N_MIS = 3, WF_TRACE_HEAD = 4, WF_SHADE_HEAD = 5, WF_N_MID = 6, WF_SHADE_B_HEAD = 7, WF_SHADE_C_HEAD = 8,
+       WF_CNT = 12 };
 enum { WF_F_SPECULAR = 1u, WF_F_TERMINATE = 2u, WF_F_SHADOW = 4u, WF_F_MIS = 8u };
 
 // sample index p -> block item, pixel, sample (the canonical order of trb_camera_rays / trb_render_samples)
@@ -1521,6 +1559,94 @@ __device__ __forceinline__ void wf_push(uint32_t* q, uint32_t* counter, bool wan
     if (want) q[base + __popc(mask & ((1u << lane) - 1u))] = value;
 }
 
+// order-preserving float <-> uint (for atomicMin / atomicMax over floats of either sign)
+__device__ __forceinline__ uint32_t f_ordered(float f) { const uint32_t u = __float_as_uint(f); return (u & 0x80000000u) ? ~u : (u | 0x80000000u); }
+__device__ __forceinline__ float f_unordered(uint32_t u) { return __uint_as_float((u & 0x80000000u) ? (u & 0x7fffffffu) : ~u); }
+// Bounding box of the ray origins a shade round queues, for the next round's sort grid: warp min/max, one atomic per warp and word.
+__device__ __forceinline__ void wf_bounds_add(uint32_t* b, bool have, f3 o) {
+    float lx = have ? o.x : finf(), ly = have ? o.y : finf(), lz = have ? o.z : finf();
+    float hx = have ? o.x : -finf(), hy = have ? o.y : -finf(), hz = have ? o.z : -finf();
+    if (__ballot_sync(0xffffffffu, have) == 0) return;
+#pragma unroll
+    for (int s = 16; s > 0; s >>= 1) {
+        lx = fminf(lx, __shfl_xor_sync(0xffffffffu, lx, s)); ly = fminf(ly, __shfl_xor_sync(0xffffffffu, ly, s)); lz = fminf(lz, __shfl_xor_sync(0xffffffffu, lz, s));
+        hx = fmaxf(hx, __shfl_xor_sync(0xffffffffu, hx, s)); hy = fmaxf(hy, __shfl_xor_sync(0xffffffffu, hy, s)); hz = fmaxf(hz, __shfl_xor_sync(0xffffffffu, hz, s));
+    }
+    if ((threadIdx.x & 31) == 0) {
+        atomicMin(b + 0, f_ordered(lx)); atomicMin(b + 1, f_ordered(ly)); atomicMin(b + 2, f_ordered(lz));
+        atomicMax(b + 4, f_ordered(hx)); atomicMax(b + 5, f_ordered(hy)); atomicMax(b + 6, f_ordered(hz));
+    }
+}
+
+// ------------------------------------------------------------------------------------------
+// Ray sorting. Bounce rays leave the shade kernel in path order, i.e. incoherent: neighbouring lanes of a trace warp
+// start in different parts of the scene and head in different directions, so every lane fetches its own BVH records
+// (ncu: one 32-byte sector per lane per load, the L1TEX data pipe is the trace kernel's limiter). Before each trace round
+// the round's rays (continuation | shadow | MIS, kept in that order) are counting-sorted by
+//     key = ray type, direction octant, Morton code of the origin's cell in a 2^bits grid over the origins' bounding box
+// so that a warp's 32 rays share the traversal order (octant) and most of the path from the root to their leaf region:
+// lanes then hit the same 128-byte lines. The order of rays never affects a result (each ray writes its own path's
+// record), so parity is untouched.   count: key + arrival rank (one atomic per ray)  ->  scan: bin offsets  ->  scatter.
+// ------------------------------------------------------------------------------------------
+__device__ __forceinline__ uint32_t spread3(uint32_t x) { // 10 bits -> every third bit
+    x &= 0x3ffu; x = (x | (x << 16)) & 0x030000ffu; x = (x | (x << 8)) & 0x0300f00fu; x = (x | (x << 4)) & 0x030c30c3u; x = (x | (x << 2)) & 0x09249249u;
+    return x;
+}
+struct RayRef { uint32_t type, p; };
+__device__ __forceinline__ RayRef wf_ray_ref(const WfState& wf, uint32_t i, uint32_t n_cont, uint32_t n_shadow) {
+    RayRef r;
+    if (i < n_cont) { r.type = 0; r.p = wf.q_cont[i]; }
+    else if (i < n_cont + n_shadow) { r.type = 1; r.p = wf.q_shadow[i - n_cont]; }
+    else { r.type = 2; r.p = wf.q_mis[i - n_cont - n_shadow]; }
+    return r;
+}
+__global__ void __launch_bounds__(256) k_wf_sort_count(const __grid_constant__ WfState wf, uint32_t round, uint32_t bits, uint32_t cell_major) {
+    const uint32_t* cnt_r = wf.counters + round * WF_CNT;
+    const uint32_t n_cont = cnt_r[WF_N_CONT], n_shadow = cnt_r[WF_N_SHADOW], total = n_cont + n_shadow + cnt_r[WF_N_MIS];
+    const uint32_t* b = wf.bounds + round * 8;
+    const f3 lo = mk(f_unordered(b[0]), f_unordered(b[1]), f_unordered(b[2])), hi = mk(f_unordered(b[4]), f_unordered(b[5]), f_unordered(b[6]));
+    const float cells = (float)(1u << bits);
+    const float sx = hi.x > lo.x ? cells / (hi.x - lo.x) : 0.0f, sy = hi.y > lo.y ? cells / (hi.y - lo.y) : 0.0f, sz = hi.z > lo.z ? cells / (hi.z - lo.z) : 0.0f;
+    const uint32_t cmax = (1u << bits) - 1u, nb = 8u << (3u * bits);
+    for (uint32_t i = blockIdx.x * blockDim.x + threadIdx.x; i < total; i += gridDim.x * blockDim.x) {
+        const RayRef r = wf_ray_ref(wf, i, n_cont, n_shadow);
+        const float4 o4 = wf.org[r.p];
+        const float4 d4 = r.type == 0 ? wf.cont[r.p] : (r.type == 1 ? wf.shadow[r.p] : wf.mis[r.p]);
+        const uint32_t cx = min(cmax, __float2uint_rz(fmaxf(0.0f, (o4.x - lo.x) * sx))), cy = min(cmax, __float2uint_rz(fmaxf(0.0f, (o4.y - lo.y) * sy))),
+                       cz = min(cmax, __float2uint_rz(fmaxf(0.0f, (o4.z - lo.z) * sz)));
+        const uint32_t m = spread3(cx) | (spread3(cy) << 1) | (spread3(cz) << 2);
+        const uint32_t oct = (d4.x < 0.0f ? 1u : 0u) | (d4.y < 0.0f ? 2u : 0u) | (d4.z < 0.0f ? 4u : 0u);
+        const uint32_t key = r.type * nb + (cell_major ? ((m << 3) | oct) : ((oct << (3u * bits)) | m));
+        wf.sort_key[i] = key;
+        wf.sort_rank[i] = atomicAdd(&wf.sort_hist[key], 1u);
+    }
+}
+// Exclusive prefix sum over the 3 * 8 * 8^bits bins, one CTA; leaves the histogram zeroed for the next round.
+__global__ void __launch_bounds__(1024) k_wf_sort_scan(const __grid_constant__ WfState wf, uint32_t n_bins) {
+    __shared__ uint32_t part[1024];
+    const uint32_t chunk = (n_bins + 1023u) / 1024u, b0 = min(n_bins, threadIdx.x * chunk), b1 = min(n_bins, b0 + chunk);
+    uint32_t sum = 0;
+    for (uint32_t k = b0; k < b1; ++k) sum += wf.sort_hist[k];
+    part[threadIdx.x] = sum;
+    __syncthreads();
+    for (uint32_t s = 1; s < 1024; s <<= 1) { // Hillis-Steele inclusive scan of the 1024 partial sums
+        const uint32_t v = threadIdx.x >= s ? part[threadIdx.x - s] : 0u;
+        __syncthreads();
+        part[threadIdx.x] += v;
+        __syncthreads();
+    }
+    uint32_t run = part[threadIdx.x] - sum;
+    for (uint32_t k = b0; k < b1; ++k) { const uint32_t c = wf.sort_hist[k]; wf.sort_offs[k] = run; wf.sort_hist[k] = 0u; run += c; }
+}
+__global__ void __launch_bounds__(256) k_wf_sort_scatter(const __grid_constant__ WfState wf, uint32_t round) {
+    const uint32_t* cnt_r = wf.counters + round * WF_CNT;
+    const uint32_t n_cont = cnt_r[WF_N_CONT], n_shadow = cnt_r[WF_N_SHADOW], total = n_cont + n_shadow + cnt_r[WF_N_MIS];
+    for (uint32_t i = blockIdx.x * blockDim.x + threadIdx.x; i < total; i += gridDim.x * blockDim.x) {
+        const RayRef r = wf_ray_ref(wf, i, n_cont, n_shadow);
+        wf.q_sorted[wf.sort_offs[wf.sort_key[i]] + wf.sort_rank[i]] = (r.type << 30) | r.p;
+    }
+}
+
 template <bool ANIM>
 __global__ void __launch_bounds__(256) k_wf_generate(const __grid_constant__ DScene sc, const __grid_constant__ RenderParams rp, const __grid_constant__ WfState wf) {
     const uint32_t n = wf.n_paths;
@@ -1541,6 +1667,10 @@ __global__ void __launch_bounds__(256) k_wf_generate(const __grid_constant__ DSc
         wf.counters[WF_N_ACTIVE] = n; wf.counters[WF_N_CONT] = n;
         if (rp.stats) { atomicAdd(&rp.stats->camera_samples, (unsigned long long)n); }
     }
+    if (blockIdx.x == 0 && threadIdx.x < 64) { // empty origin boxes for every round's sort grid
+        uint32_t* b = wf.bounds + threadIdx.x * 8;
+        b[0] = b[1] = b[2] = b[3] = 0xffffffffu; b[4] = b[5] = b[6] = b[7] = 0u;
+    }
 }
 
 // Trace round r: the rays queued by shade round r-1 (round 0: the primary rays). Persistent warps: a lane
@@ -1554,7 +1684,7 @@ __global__ void __launch_bounds__(256) k_wf_generate(const __grid_constant__ DSc
 // ballots are paid once per burst.
 template <bool STATS, int MINB, int SMEM_STACK, bool ANIM, bool PHASED, bool QUADS>
 __global__ void __launch_bounds__(128, MINB) k_wf_trace(const __grid_constant__ DScene sc, const __grid_constant__ RenderParams rp, const __grid_constant__ WfState wf,
-                                                         uint32_t round, uint32_t flags, int WF_REFILL_IDLE, uint32_t sched) {
+                                                         uint32_t round, uint32_t flags, int WF_REFILL_IDLE, uint32_t sched, const uint32_t* __restrict__ q_sorted) {
     uint32_t* cnt_r = wf.counters + round * WF_CNT;
     const uint32_t n_cont = cnt_r[WF_N_CONT], n_shadow = cnt_r[WF_N_SHADOW], n_mis = cnt_r[WF_N_MIS];
     const uint32_t total = n_cont + n_shadow + n_mis;
@@ -1597,7 +1727,8 @@ __global__ void __launch_bounds__(128, MINB) k_wf_trace(const __grid_constant__ 
             else if (!have) {
                 const uint32_t i = base + __popc(idle & lt_mask);
                 if (i < total) {
-                    if (i < n_cont) { type = 0; p = wf.q_cont[i]; }
+                    if (q_sorted) { const uint32_t e = __ldg(&q_sorted[i]); type = (int)(e >> 30); p = e & WF_PATH_MASK; } // sorted by (type, octant, origin cell)
+                    else if (i < n_cont) { type = 0; p = wf.q_cont[i]; }
                     else if (i < n_cont + n_shadow) { type = 1; p = wf.q_shadow[i - n_cont]; }
                     else { type = 2; p = wf.q_mis[i - n_cont - n_shadow]; }
                     const float4 o4 = __ldcs(&wf.org[p]);
@@ -1678,6 +1809,7 @@ __global__ void __launch_bounds__(128, MINB) k_wf_shade(const __grid_constant__ 
         const bool valid = i < n;
         uint32_t p = 0;
         bool push_cont = false, push_shadow = false, push_mis = false, push_active = false;
+        f3 new_org = splat(0.0f);
         if (valid) {
             p = round == 0 ? i : act[i];
             const float4 o4 = wf.org[p];
@@ -1720,6 +1852,7 @@ __global__ void __launch_bounds__(128, MINB) k_wf_shade(const __grid_constant__ 
                     push_cont = !o.terminate; push_shadow = o.ds.has_shadow; push_mis = o.ds.has_mis;
                     push_active = push_cont || push_shadow || push_mis;
                     if (push_active) {
+                        new_org = o.org;
                         wf.org[p] = make_float4(o.org.x, o.org.y, o.org.z, __uint_as_float(nf));
                         if (push_cont) wf.cont[p] = make_float4(o.next_d.x, o.next_d.y, o.next_d.z, finf());
                         if (push_shadow) wf.shadow[p] = make_float4(o.ds.shadow_d.x, o.ds.shadow_d.y, o.ds.shadow_d.z, 0.0f);
@@ -1749,6 +1882,187 @@ __global__ void __launch_bounds__(128, MINB) k_wf_shade(const __grid_constant__ 
         wf_push(wf.q_shadow, &cnt_n[WF_N_SHADOW], push_shadow, p);
         wf_push(wf.q_mis, &cnt_n[WF_N_MIS], push_mis, p);
         wf_push(act_next, &cnt_n[WF_N_ACTIVE], push_active, p);
+        wf_bounds_add(wf.bounds + (round + 1) * 8, push_active, new_org);
+    }
+}
+
+// ------------------------------------------------------------------------------------------
+// Split shading: the same bounce as k_wf_shade in three kernels, so that each part keeps fewer values live (the fused
+// kernel needs 128 registers: 4 CTAs per SM, 25 % of the warp slots) and its code stays resident in the instruction cache.
+//   k_wf_shade_a  fold the previous bounce's shadow / MIS results into the radiance (direct_resolve), end terminated or
+//                 escaped paths, else build the vertex: surface_at, emission (Q1), shading frame -> f_p/f_n/f_t/f_b, q_mid
+//   k_wf_shade_b  direct lighting set-up of the vertex: light choice, direct_setup -> A, B, shadow and MIS rays
+//   k_wf_shade_c  BSDF sample, throughput, Russian roulette -> continuation ray; decides whether the path goes on
+// Every value is computed by the same device functions in the same order as in the fused kernel: bit-identical results.
+// ------------------------------------------------------------------------------------------
+__device__ __forceinline__ void finish_sample(const DScene& sc, const RenderParams& rp, const WfState& wf, uint32_t p, f3 illum, int mode) {
+    const f3 c = mk(clampf(illum.x, 0.0f, 1.0f), clampf(illum.y, 0.0f, 1.0f), clampf(illum.z, 0.0f, 1.0f)); // multithreaded.rs:99 (Q12)
+    if (mode == 0) wf.rad[p] = make_float4(c.x, c.y, c.z, 1.0f);
+    else {
+        const SampleId id = sample_id(sc, rp, p);
+        const PixelStreams ps = pixel_streams(rp.seed, id.pixel);
+        float sx, sy, tm;
+        sample_position(rp, ps, id, sx, sy, tm);
+        trb_sample* out = reinterpret_cast<trb_sample*>(rp.samples_out) + p;
+        out->x = sx; out->y = sy; out->r = c.x; out->g = c.y; out->b = c.z;
+    }
+}
+__device__ __forceinline__ void load_frame(const WfState& wf, uint32_t p, Frame& fr, uint32_t& inst) {
+    const float4 a = wf.f_p[p], n = wf.f_n[p], t = wf.f_t[p], b = wf.f_b[p];
+    fr.p = mk(a.x, a.y, a.z); inst = __float_as_uint(a.w);
+    fr.n = mk(n.x, n.y, n.z); fr.tan = mk(t.x, t.y, t.z); fr.bitan = mk(b.x, b.y, b.z);
+}
+
+template <int MODE, bool ANIM, int MINB>
+__global__ void __launch_bounds__(128, MINB) k_wf_shade_a(const __grid_constant__ DScene sc, const __grid_constant__ RenderParams rp, const __grid_constant__ WfState wf,
+                                                     uint32_t round) {
+    uint32_t* cnt_r = wf.counters + round * WF_CNT;
+    const uint32_t n = cnt_r[WF_N_ACTIVE];
+    const uint32_t* __restrict__ act = wf.q_active[round & 1];
+    const int lane = threadIdx.x & 31;
+    for (;;) {
+        uint32_t base = 0;
+        if (lane == 0) base = atomicAdd(&cnt_r[WF_SHADE_HEAD], 32u);
+        base = __shfl_sync(0xffffffffu, base, 0);
+        if (base >= n) break;
+        const uint32_t i = base + lane;
+        uint32_t p = 0;
+        bool push_mid = false;
+        if (i < n) {
+            p = round == 0 ? i : act[i];
+            const float4 o4 = wf.org[p];
+            const uint32_t fl = __float_as_uint(o4.w);
+            const f3 org = mk(o4.x, o4.y, o4.z);
+            const float4 il4 = wf.illum[p];
+            f3 illum = mk(il4.x, il4.y, il4.z);
+            bool done = false;
+            const float4 th4 = wf.thr[p];
+            const float time = th4.w;
+            if (round > 0) { // fold in the direct light of the previous bounce (estimate_direct's two ray results)
+                const float4 a4 = wf.a[p], b4 = wf.b[p], t4 = wf.tprev[p];
+                bool occluded = false, mis_ok = false;
+                if (fl & WF_F_SHADOW) occluded = __float_as_uint(wf.shadow[p].w) != 0u;
+                if (fl & WF_F_MIS) {
+                    const float4 m4 = wf.mis[p];
+                    mis_ok = mis_sees_light<ANIM>(sc, org, mk(m4.x, m4.y, m4.z), __float_as_uint(b4.w), __float_as_uint(a4.w), m4.w, time);
+                }
+                illum = illum + mk(t4.x, t4.y, t4.z) * direct_resolve(mk(a4.x, a4.y, a4.z), mk(b4.x, b4.y, b4.z), occluded, mis_ok);
+                done = (fl & WF_F_TERMINATE) != 0;
+            }
+            if (!done) {
+                const float4 c4 = wf.cont[p];
+                const uint4 h4 = wf.hit[p];
+                if (h4.x == TRB_MISS) done = true; // primary miss: black sample (multithreaded.rs:101-102); later: `None => break`
+                else {
+                    Ray ray; ray.o = org; ray.d = mk(c4.x, c4.y, c4.z); ray.tmin = 0.0f; ray.tmax = c4.w;
+                    HitRec h; h.t = c4.w; h.inst = h4.x; h.prim = h4.y; h.b1 = __uint_as_float(h4.z); h.b2 = __uint_as_float(h4.w);
+                    Surf s;
+                    surface_at<ANIM>(sc, ray, h, s, time);
+                    f3 first_ng;
+                    if (round == 0) { first_ng = s.ng; wf.ng[p] = make_float4(s.ng.x, s.ng.y, s.ng.z, 0.0f); }
+                    else { const float4 n4 = wf.ng[p]; first_ng = mk(n4.x, n4.y, n4.z); }
+                    bounce_emission<ANIM>(sc, h.inst, ray.d, first_ng, round, (fl & WF_F_SPECULAR) != 0, mk(th4.x, th4.y, th4.z), time, illum);
+                    Frame fr;
+                    make_frame(s, fr);
+                    wf.f_p[p] = make_float4(fr.p.x, fr.p.y, fr.p.z, __uint_as_float(h.inst));
+                    wf.f_n[p] = make_float4(fr.n.x, fr.n.y, fr.n.z, 0.0f);
+                    wf.f_t[p] = make_float4(fr.tan.x, fr.tan.y, fr.tan.z, 0.0f);
+                    wf.f_b[p] = make_float4(fr.bitan.x, fr.bitan.y, fr.bitan.z, 0.0f);
+                    wf.illum[p] = make_float4(illum.x, illum.y, illum.z, 0.0f);
+                    push_mid = true;
+                }
+            }
+            if (done) finish_sample(sc, rp, wf, p, illum, MODE);
+        }
+        wf_push(wf.q_mid, &cnt_r[WF_N_MID], push_mid, p);
+    }
+}
+
+template <bool ANIM, int MINB>
+__global__ void __launch_bounds__(128, MINB) k_wf_shade_b(const __grid_constant__ DScene sc, const __grid_constant__ RenderParams rp, const __grid_constant__ WfState wf,
+                                                     uint32_t round) {
+    uint32_t* cnt_r = wf.counters + round * WF_CNT;
+    uint32_t* cnt_n = wf.counters + (round + 1) * WF_CNT;
+    const uint32_t n = cnt_r[WF_N_MID];
+    const int lane = threadIdx.x & 31;
+    for (;;) {
+        uint32_t base = 0;
+        if (lane == 0) base = atomicAdd(&cnt_r[WF_SHADE_B_HEAD], 32u);
+        base = __shfl_sync(0xffffffffu, base, 0);
+        if (base >= n) break;
+        const uint32_t i = base + lane;
+        uint32_t p = 0;
+        bool push_shadow = false, push_mis = false;
+        if (i < n) {
+            p = wf.q_mid[i];
+            Frame fr; uint32_t inst;
+            load_frame(wf, p, fr, inst);
+            const float4 c4 = wf.cont[p], th4 = wf.thr[p];
+            const f3 wo = -mk(c4.x, c4.y, c4.z);
+            Mat m;
+            load_mat(sc.materials[__ldg(&sc.instances[inst].material)], m);
+            const SampleId id = sample_id(sc, rp, p);
+            const uint32_t hs = rng_absorb(rng_absorb(rng_seed(rp.seed), id.pixel), id.si);
+            DirectSetup ds; uint32_t light;
+            bounce_direct<ANIM>(sc, m, fr, wo, round, hs, th4.w, ds, light);
+            push_shadow = ds.has_shadow; push_mis = ds.has_mis;
+            wf.org[p] = make_float4(fr.p.x, fr.p.y, fr.p.z, __uint_as_float((push_shadow ? WF_F_SHADOW : 0u) | (push_mis ? WF_F_MIS : 0u)));
+            if (push_shadow) wf.shadow[p] = make_float4(ds.shadow_d.x, ds.shadow_d.y, ds.shadow_d.z, 0.0f);
+            if (push_mis) wf.mis[p] = make_float4(ds.mis_d.x, ds.mis_d.y, ds.mis_d.z, finf());
+            wf.a[p] = make_float4(ds.a.x, ds.a.y, ds.a.z, __uint_as_float(TRB_MISS));
+            wf.b[p] = make_float4(ds.b.x, ds.b.y, ds.b.z, __uint_as_float(light));
+            wf.tprev[p] = make_float4(th4.x, th4.y, th4.z, 0.0f); // path_throughput multiplying this bounce's direct light
+        }
+        wf_push(wf.q_shadow, &cnt_n[WF_N_SHADOW], push_shadow, p);
+        wf_push(wf.q_mis, &cnt_n[WF_N_MIS], push_mis, p);
+    }
+}
+
+template <int MODE, bool ANIM, int MINB>
+__global__ void __launch_bounds__(128, MINB) k_wf_shade_c(const __grid_constant__ DScene sc, const __grid_constant__ RenderParams rp, const __grid_constant__ WfState wf,
+                                                     uint32_t round) {
+    uint32_t* cnt_r = wf.counters + round * WF_CNT;
+    uint32_t* cnt_n = wf.counters + (round + 1) * WF_CNT;
+    const uint32_t n = cnt_r[WF_N_MID];
+    uint32_t* act_next = wf.q_active[(round + 1) & 1];
+    const int lane = threadIdx.x & 31;
+    for (;;) {
+        uint32_t base = 0;
+        if (lane == 0) base = atomicAdd(&cnt_r[WF_SHADE_C_HEAD], 32u);
+        base = __shfl_sync(0xffffffffu, base, 0);
+        if (base >= n) break;
+        const uint32_t i = base + lane;
+        uint32_t p = 0;
+        bool push_cont = false, push_active = false;
+        f3 new_org = splat(0.0f);
+        if (i < n) {
+            p = wf.q_mid[i];
+            Frame fr; uint32_t inst;
+            load_frame(wf, p, fr, inst);
+            const float4 c4 = wf.cont[p], th4 = wf.thr[p];
+            const f3 wo = -mk(c4.x, c4.y, c4.z);
+            Mat m;
+            load_mat(sc.materials[__ldg(&sc.instances[inst].material)], m);
+            const SampleId id = sample_id(sc, rp, p);
+            const uint32_t hs = rng_absorb(rng_absorb(rng_seed(rp.seed), id.pixel), id.si);
+            ScatterOut so;
+            bounce_scatter(sc, m, fr, wo, round, hs, mk(th4.x, th4.y, th4.z), so);
+            const uint32_t fb = __float_as_uint(wf.org[p].w); // WF_F_SHADOW | WF_F_MIS from k_wf_shade_b
+            push_cont = !so.terminate;
+            push_active = push_cont || (fb & (WF_F_SHADOW | WF_F_MIS)) != 0u;
+            if (push_active) {
+                new_org = fr.p;
+                wf.org[p] = make_float4(fr.p.x, fr.p.y, fr.p.z, __uint_as_float(fb | (so.specular ? WF_F_SPECULAR : 0u) | (so.terminate ? WF_F_TERMINATE : 0u)));
+                if (push_cont) wf.cont[p] = make_float4(so.next_d.x, so.next_d.y, so.next_d.z, finf());
+                wf.thr[p] = make_float4(so.throughput.x, so.throughput.y, so.throughput.z, th4.w);
+            } else { // nothing pending: the direct light of this bounce is zero, the path ends here
+                const float4 il4 = wf.illum[p];
+                finish_sample(sc, rp, wf, p, mk(il4.x, il4.y, il4.z), MODE);
+            }
+        }
+        wf_push(wf.q_cont, &cnt_n[WF_N_CONT], push_cont, p);
+        wf_push(act_next, &cnt_n[WF_N_ACTIVE], push_active, p);
+        wf_bounds_add(wf.bounds + (round + 1) * 8, push_active, new_org);
     }
 }
 
