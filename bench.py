@@ -8,15 +8,18 @@ Workload (BASELINE.json configs[3]): synthetic 1M-triangle rando
 1920x1080, one 4096-spp frame rendered in additive passes. One STEP = one pass of `--spp-per-step` samples per pixel
 per GPU over the frame, tile-sharded across ranks exactly like the reference's master/worker mode
 (tray_rust_b200.dist.shard_blocks == master.rs:88-120): at N GPUs a step renders N*spp_per_step samples per pixel,
-each rank its own contiguous range of the Morton block list, followed by one SUM-reduce of the RGBW film (NCCL).
-Per-GPU work is therefore constant in N: "scaling": "weak".
+each rank its own interleaved share of the Morton block list; the per-rank films stay on the GPUs over the passes of
+the frame and are SUM-reduced ONCE (ncclReduce called by libtrb itself, trb_comm_reduce_film) — the timed region of K
+steps ends with that one reduce. Per-GPU work is therefore constant in N: "scaling": "weak".
 
 `value`  : rays/s of the whole job with the scene resident in HBM and the film left on the device.
 `e2e`    : the same metric through the reference-facing call trb_render (== Exec::render): per step it runs
            Scene::update_frame (TLAS rebuild + upload), the kernels, and copies the film back to host memory.
 `roofline`: dominant kernel's algorithmic bytes (48 B/ray + 32 B/node test + 48 B/triangle test + 64 B/instance test,
            SURVEY §8d; counted by the kernel's own test counters in an untimed replay of the same passes) over its
-           measured duration, against the measured HBM peak in MEASURED_PEAKS.json.
+           measured duration, against the measured HBM peak in MEASURED_PEAKS.json — AND, because the BVH is L2-resident,
+           what ncu measured for the same launches (profiles/traffic.json): real DRAM bytes (`traffic`, `dram_gbs`,
+           `dram_frac`), L2 sector traffic (`l2_gbs`) and the unit that actually limits the kernel (`limiter`).
 """
 import argparse
 import json
@@ -98,80 +101,107 @@ def host_threads():
         return os.cpu_count() or 1
 
 
+def host_info():
+    """What the CPU arm ran on: logical CPUs, affinity mask size, physical cores and the model name (from /proc/cpuinfo)."""
+    info = {"nproc": os.cpu_count(), "affinity": host_threads(), "physical_cores": None, "model": None}
+    try:
+        cores, phys, core = set(), None, None
+        for line in open("/proc/cpuinfo"):
+            if line.startswith("model name") and info["model"] is None:
+                info["model"] = line.split(":", 1)[1].strip()
+            elif line.startswith("physical id"):
+                phys = line.split(":")[1].strip()
+            elif line.startswith("core id"):
+                core = line.split(":")[1].strip()
+            elif not line.strip():
+                if phys is not None and core is not None:
+                    cores.add((phys, core))
+                phys = core = None
+        info["physical_cores"] = len(cores) or None
+    except Exception:
+        pass
+    return info
+
+
 def build_scene_desc(a):
     from tray_rust_b200 import scenebuild as SB
     return SB.scene_c4(a.tris, a.width, a.height, a.spp).finish()
 
 
-def cpu_baseline(a, desc, threads=None):
-    """The oracle port (kind "port": the Rust reference cannot be built here) on the host cores, baseline mode
-    (per-ray transform recomposition like the reference), on a bounded sample of the same workload."""
+def pin_openmp():
+    """Pin the CPU arm's OpenMP threads (must happen before libgomp starts): one thread per core, neighbours close."""
+    os.environ.setdefault("OMP_PROC_BIND", "close")
+    os.environ.setdefault("OMP_PLACES", "cores")
+
+
+def cpu_arm(a, desc, seconds, reps):
+    """The timed CPU implementation of the path: the oracle port (the Rust reference cannot be built here: no cargo/rustc),
+    baseline mode (per-ray transform recomposition like the reference), built -O3 -march=x86-64-v3 against glibc's libm
+    (oracle/_build/liboracle_fast.so; the detmath build is the parity checker, not the timed arm). Single-thread rate on a
+    small sample, then `reps` all-core repetitions of a bounded sample of the same workload; min / median / max reported so
+    that a noisy or oversubscribed box is visible in the line."""
     from tray_rust_b200 import _ffi as F
+    pin_openmp()
     from oracle import pyoracle as O   # the CPU arm: the one place besides tests/smoke that may execute oracle/
-    threads = threads or host_threads()
-    o = O.OracleScene(desc, "det", baseline=True)
+    threads = host_threads()
+    o = O.OracleScene(desc, "fast", baseline=True)
     o.update_frame(0, 0.0, 0.0)
     nb = o.n_blocks()
-    rng = np.random.default_rng(0)
-    probe_start = int(rng.integers(0, max(1, nb - 64)))
+    mid = nb // 2
+    kw = dict(flags=F.RENDER_NO_UPDATE, sample_first=0, sample_count=1, seed=a.seed)
     t0 = time.time()
-    _, st = o.render(threads=threads, flags=F.RENDER_NO_UPDATE, block_start=probe_start, block_count=64, sample_first=0, sample_count=1, seed=a.seed)
-    dt = max(time.time() - t0, 1e-3)
-    rate = st.rays_total() / dt
-    # choose a contiguous Morton range in the middle of the image sized for ~cpu_seconds
-    want_rays = rate * a.cpu_seconds
-    per_block = st.rays_total() / 64.0
-    count = int(min(nb, max(64, want_rays / per_block)))
-    start = max(0, nb // 2 - count // 2)
+    _, st = o.render(threads=1, block_start=mid, block_count=16, **kw)          # probe: single thread, 16 blocks
+    dt = max(time.time() - t0, 1e-4)
+    n1 = int(min(nb // 4, max(16, 16 * 2.5 / dt)))                               # ~2.5 s single-thread sample
     t0 = time.time()
-    _, st = o.render(threads=threads, flags=F.RENDER_NO_UPDATE, block_start=start, block_count=count, sample_first=0, sample_count=1, seed=a.seed)
-    dt = time.time() - t0
-    cores = threads
-    out = {"value": st.rays_total() / dt / 1e6, "unit": "Mrays/s", "cores": cores, "kind": "port",
-           "sample": "%d of %d Morton blocks (8x8 px) x 1 spp of the same C4 scene, %.1f s wall, oracle baseline mode, %d threads" % (count, nb, dt, cores),
-           "samples_per_s": st.camera_samples / dt}
+    _, st1 = o.render(threads=1, block_start=mid - n1 // 2, block_count=n1, **kw)
+    dt1 = time.time() - t0
+    single = st1.rays_total() / dt1 / 1e6
+    per_block = st1.rays_total() / n1
+    count = int(min(nb, max(64 * threads, single * 1e6 * threads * 0.5 * seconds / reps / per_block)))   # assume ~50 % parallel efficiency for sizing
+    start = max(0, mid - count // 2)
+    vals, rays, samples, wall = [], 0, 0, 0.0
+    for r in range(reps):
+        t0 = time.time()
+        _, stn = o.render(threads=threads, block_start=start, block_count=count, flags=F.RENDER_NO_UPDATE, sample_first=r, sample_count=1, seed=a.seed)
+        dt = time.time() - t0
+        vals.append(stn.rays_total() / dt / 1e6); rays += stn.rays_total(); samples += stn.camera_samples; wall += dt
     o.close()
-    return out
+    vals_sorted = sorted(vals)
+    return {"value": float(np.median(vals)), "unit": "Mrays/s", "cores": threads, "kind": "port",
+            "sample": "%d repetitions of %d of %d Morton blocks (8x8 px) x 1 spp of the same C4 scene, %.1f s wall in total; oracle port, baseline mode, "
+                      "-O3 -march=x86-64-v3 + glibc libm, %d OpenMP threads pinned (OMP_PROC_BIND=%s)" % (reps, count, nb, wall, threads, os.environ.get("OMP_PROC_BIND")),
+            "all_core": {"min": vals_sorted[0], "median": float(np.median(vals)), "max": vals_sorted[-1], "reps": vals},
+            "single_thread": {"value": single, "sample": "%d blocks x 1 spp, %.1f s" % (n1, dt1)},
+            "parallel_speedup": float(np.median(vals)) / single if single > 0 else None,
+            "host": host_info(), "samples_per_s": samples / wall, "rays": rays, "wall_s": wall}
 
 
 def run_reference(a):
-    """--impl reference: the CPU implementation of the path (oracle port) with all host threads, bounded steps."""
+    """--impl reference: the CPU implementation of the path (oracle port, see cpu_arm) with all host threads; each step is one
+    repetition of a bounded sample of the workload."""
     rank = int(os.environ.get("RANK", "0"))
     if rank != 0:
         return
-    from tray_rust_b200 import _ffi as F
-    from oracle import pyoracle as O   # --impl reference: the oracle port is the timed CPU implementation of the path
     desc = build_scene_desc(a)
-    o = O.OracleScene(desc, "det", baseline=True)
-    o.update_frame(0, 0.0, 0.0)
-    nb = o.n_blocks()
-    cores = host_threads()
-    count = min(nb, 75 * cores)  # bounded sample per step, a few seconds of CPU work on every core
-    start = nb // 2 - count // 2
-    times, rays, samples = [], 0, 0
-    for it in range(a.warmup + a.steps):
-        t0 = time.time()
-        _, st = o.render(threads=cores, flags=F.RENDER_NO_UPDATE, block_start=start, block_count=count, sample_first=it, sample_count=1, seed=a.seed)
-        dt = time.time() - t0
-        if it >= a.warmup:
-            times.append(dt); rays += st.rays_total(); samples += st.camera_samples
-    total = sum(times)
-    v = rays / total / 1e6
+    reps = a.warmup + a.steps
+    c = cpu_arm(a, desc, seconds=4.0 * reps, reps=reps)
+    vals = c["all_core"]["reps"][a.warmup:]
+    v = float(np.mean(vals))
+    c = dict(c, value=v)
     line = {"impl": "reference", "metric": METRIC, "value": v, "unit": "Mrays/s", "n_gpus": a.gpus, "steps": a.steps, "warmup": a.warmup,
-            "ms_per_step": 1e3 * total / a.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+            "ms_per_step": 1e3 * c["wall_s"] / reps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
             "config": {"workload": WORKLOAD, "tris": a.tris, "width": a.width, "height": a.height, "spp": a.spp},
-            "samples_per_s": samples / total,
-            "cpu_baseline": {"value": v, "unit": "Mrays/s", "cores": cores, "kind": "port",
-                             "sample": "each step = %d of %d Morton blocks x 1 spp of the C4 scene (oracle port, baseline mode, %d threads); the Rust reference cannot be built here (no cargo/rustc)" % (count, nb, cores)},
+            "samples_per_s": c["samples_per_s"], "cpu_baseline": c,
             "e2e": {"value": v, "unit": "Mrays/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}
-    print(json.dumps(line))
+    print(json.dumps(line, default=float))
 
 
 def run_ours(a):
     import torch
     import torch.distributed as dist
     from tray_rust_b200 import api, _ffi as F
-    from tray_rust_b200.dist import shard_interleaved, reduce_film, max_over_ranks, sum_over_ranks
+    from tray_rust_b200.dist import shard_interleaved, max_over_ranks, sum_over_ranks
 
     world = int(os.environ.get("WORLD_SIZE", "1"))
     rank = int(os.environ.get("RANK", "0"))
@@ -184,9 +214,14 @@ def run_ours(a):
     sys.stdout.flush()
     json_out = os.fdopen(os.dup(1), "w")
     os.dup2(2, 1)
+    comm = None
     if world > 1:
-        dist.init_process_group("nccl", device_id=dev)
+        dist.init_process_group("nccl", device_id=dev)   # plumbing only: barriers, max-over-ranks, shipping the NCCL unique id
     lib = F.load_trb()
+    if world > 1:   # the data-path collective is the library's own: ncclReduce of the film from libtrb (trb_comm_*)
+        uid = torch.tensor(list(api.Comm.unique_id()) if rank == 0 else [0] * 128, dtype=torch.uint8, device=dev)
+        dist.broadcast(uid, 0)
+        comm = api.Comm(bytes(uid.cpu().tolist()), world, rank, local)
 
     desc = build_scene_desc(a)
     t0 = time.time()
@@ -209,11 +244,12 @@ def run_ours(a):
         flush.fill_(i & 0xFF)                                         # L2 flush between timed iterations
         g.render_device(film.data_ptr(), st.data_ptr(), stream, spp=a.spp, sample_first=i * spp_step, sample_count=spp_step,
                         block_start=bstart, block_count=bcount, seed=a.seed, **shard, flags=flags)
-        if world > 1:
-            reduce_film(film, dst=0)
 
     for i in range(a.warmup):
         step(i)
+    if comm:
+        comm.reduce_film(film.data_ptr(), film.numel(), 0, stream)     # warm the communicator
+        film.zero_()                                                    # the timed passes accumulate one frame's film from zero on every rank
     torch.cuda.synchronize()
     if world > 1:
         dist.barrier()
@@ -234,8 +270,8 @@ def run_ours(a):
         g.render_device(film.data_ptr(), stats.data_ptr(), stream, spp=a.spp, sample_first=i * spp_step, sample_count=spp_step,
                         block_start=bstart, block_count=bcount, seed=a.seed, **shard)
         kev[k][1].record()
-        if world > 1:
-            reduce_film(film, dst=0)
+    if comm:
+        comm.reduce_film(film.data_ptr(), film.numel(), 0, stream)     # ONE film reduce for the passes of the frame (design: once per frame)
     e_end.record()
     torch.cuda.synchronize()
     if world > 1:
@@ -309,30 +345,24 @@ def run_ours(a):
             t_e += time.perf_counter() - t0
             rays_e += s_e.rays_total()
         api_name = "trb_render (Exec::render): update_frame + kernels + film D2H"
-    else:
-        pinned = torch.empty((a.height, a.width, 4), dtype=torch.float32, pin_memory=True) if rank == 0 else None
-        estats = torch.zeros(10, dtype=torch.int64, device=dev)
+    else:   # one trb_render_sharded per step on every rank: update_frame, this rank's shard, ONE ncclReduce, root's film D2H + host add
+        hfilm = np.zeros((a.height, a.width, 4), np.float32) if rank == 0 else None
+        comm.render_sharded(g, hfilm, 0, spp=a.spp, sample_first=0, sample_count=spp_step, seed=a.seed, shard_chunk=32)   # warm
         dist.barrier(); torch.cuda.synchronize()
-        t0 = time.perf_counter()
+        rays_rank, t0 = 0, time.perf_counter()
         for k in range(e2e_steps):
-            film.zero_()
-            g.update_frame(0, 0.0, 0.0)
-            g.render_device(film.data_ptr(), estats.data_ptr(), stream, spp=a.spp, sample_first=(a.warmup + k) * spp_step, sample_count=spp_step,
-                            block_start=bstart, block_count=bcount, seed=a.seed, **shard)
-            reduce_film(film, dst=0)
-            if rank == 0:
-                pinned.copy_(film, non_blocking=True)
-            torch.cuda.synchronize()
+            _, s_e = comm.render_sharded(g, hfilm, 0, spp=a.spp, sample_first=(a.warmup + k) * spp_step, sample_count=spp_step, seed=a.seed, shard_chunk=32)
+            rays_rank += s_e.rays_total()
         dist.barrier()
         t_e = max_over_ranks(time.perf_counter() - t0, dev)
-        rays_e = sum(sum_over_ranks(estats.cpu().numpy()[1:5].tolist(), dev))
-        api_name = "per rank: trb_scene_update_frame + trb_render_device on its tile shard, NCCL film reduce, rank-0 film D2H"
+        rays_e = sum(sum_over_ranks([rays_rank], dev))
+        api_name = "trb_render_sharded on every rank (Exec::render of the distributed mode): update_frame + its tile shard + one ncclReduce of the film + root film D2H"
     e2e = {"value": rays_e / t_e / 1e6, "unit": "Mrays/s", "h2d_bytes_per_step": int(h2d), "d2h_bytes_per_step": int(a.width * a.height * 16 + 80),
            "ms_per_step": 1e3 * t_e / e2e_steps, "steps": e2e_steps, "api": api_name}
 
     cpu = None
     if rank == 0 and world == 1 and not a.no_cpu_baseline:
-        cpu = cpu_baseline(a, desc)
+        cpu = cpu_arm(a, desc, seconds=a.cpu_seconds, reps=3)
 
     if rank == 0:
         peaks = {}
@@ -345,23 +375,32 @@ def run_ours(a):
         trace_launches = max(1, trace_launches)
         bytes_per_launch = bytes_total / trace_launches
         achieved = bytes_total / (trace_ms * 1e-3) / 1e9        # == bytes per launch / average launch duration
-        traffic = None
+        # what ncu measured for the trace launches of one step of this same command (tools/traffic_from_ncu.py -> profiles/traffic.json)
+        prof = {}
         try:
-            traffic = json.load(open(os.path.join(REPO, "profiles", "traffic.json"))).get("dram_bytes_per_launch")
+            prof = json.load(open(os.path.join(REPO, "profiles", "traffic.json")))
         except Exception:
             pass
+        traffic = prof.get("dram_bytes_per_launch")
+        launch_s = trace_ms / trace_launches * 1e-3
+        dram_gbs = traffic / launch_s / 1e9 if traffic else None
+        l2_gbs = prof["l2_bytes_per_launch"] / launch_s / 1e9 if prof.get("l2_bytes_per_launch") else None
         line = {
             "metric": METRIC, "value": rays_all / (total_ms * 1e-3) / 1e6, "unit": "Mrays/s", "n_gpus": world, "steps": a.steps, "warmup": a.warmup,
             "ms_per_step": total_ms / a.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
             "config": {"workload": WORKLOAD, "tris": a.tris, "width": a.width, "height": a.height, "spp": a.spp, "spp_per_step": spp_step,
-                       "blocks_per_rank": nb // world, "parallelism": "tile-sharded x%d (interleaved 32-block chunks of the Morton block list) + film SUM-reduce" % world,
+                       "blocks_per_rank": nb // world, "parallelism": "tile-sharded x%d (interleaved 32-block chunks of the Morton block list) + ONE film SUM-reduce (ncclReduce from libtrb) at the end of the timed passes" % world,
                        "l2": "256 MiB buffer written between timed steps (L2 flush)", "scene_create_s": round(create_s, 2)},
             "samples_per_s": tot[0] / (total_ms * 1e-3),
             "rays": {"primary": tot[1], "shadow": tot[2], "mis": tot[3], "continuation": tot[4],
                      "primary_plus_shadow_mrays_s": (tot[1] + tot[2]) / (total_ms * 1e-3) / 1e6},
             "roofline": {"bound": "hbm", "kernel": "k_wf_trace", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
                          "peak_source": "MEASURED_PEAKS.json hbm_gbs (measured)" if peaks else "fallback 6650 GB/s",
-                         "traffic": traffic, "algorithmic_bytes_per_launch": bytes_per_launch, "launches": trace_launches,
+                         "traffic": traffic, "dram_gbs": dram_gbs, "dram_frac": dram_gbs / peak if dram_gbs else None,
+                         "l2_gbs": l2_gbs, "l1tex_data_pipe_pct": prof.get("l1tex_data_pipe_pct"), "limiter": prof.get("limiter"),
+                         "note": "frac = ALGORITHMIC bytes (SURVEY 8d definition, reference data structure) over time vs the HBM peak; the ~90 MB BVH is L2-resident, so the "
+                                 "HBM bandwidth ncu measures for the same launches is dram_gbs (dram_frac of peak) and the kernel's limiter is the L1TEX data pipe",
+                         "algorithmic_bytes_per_launch": bytes_per_launch, "launches": trace_launches,
                          "avg_launch_ms": trace_ms / trace_launches, "trace_ms_per_step": trace_ms / a.steps,
                          "step_kernels_ms": avg_kernel_ms,
                          "per_ray": {"node_tests": cs[5] / max(1, rank_rays), "tri_tests": cs[6] / max(1, rank_rays), "inst_tests": cs[7] / max(1, rank_rays)}},

@@ -26,7 +26,7 @@
 extern "C" {
 #endif
 
-#define TRB_ABI_VERSION 2u
+#define TRB_ABI_VERSION 3u
 
 typedef enum trb_status {
     TRB_OK = 0,
@@ -35,7 +35,8 @@ typedef enum trb_status {
     TRB_OOM = 3,
     TRB_UNSUPPORTED = 4, /* valid in the reference, not in this build */
     TRB_IO = 5,
-    TRB_NO_DEVICE = 6    /* no CUDA device: this library has no CPU fallback */
+    TRB_NO_DEVICE = 6,   /* no CUDA device: this library has no CPU fallback */
+    TRB_NCCL = 7         /* an NCCL call failed, or libnccl.so.2 could not be loaded */
 } trb_status;
 
 /* ---------------------------------------------------------------------------------
@@ -301,6 +302,49 @@ trb_status trb_render(trb_scene* scene, const trb_render_cfg* cfg, float* film_r
  * host-buffer call (trb_render / trb_intersect / trb_render_samples). */
 trb_status trb_render_device(trb_scene* scene, const trb_render_cfg* cfg, float* d_film_rgbw,
                              trb_stats* d_stats, void* cuda_stream);
+
+/* -- multi-GPU: tile sharding + ONE film SUM-reduce per frame -------------
+ *
+ * The reference's distributed mode gives worker r of W the blocks [r*floor(B/W), ...) of the Morton block list
+ * (exec/distrib/master.rs:88-93,218-224), every worker renders its blocks at full spp with the scene replicated
+ * (worker.rs:37-89), and the master adds the workers' films (film/image.rs:21-50, master.rs:124-163). Here the
+ * exchange is one ncclReduce(SUM, fp32) of the RGBW film over NVLink at frame end. libnccl.so.2 is resolved at run
+ * time (the copy already loaded in the process, else the system one): a single-GPU user never needs it.
+ *
+ * Two shapes:
+ *   one process per GPU  trb_nccl_unique_id (rank 0; ship the 128 bytes to the other ranks by any means)
+ *                        -> trb_comm_create on every rank -> trb_render_sharded per frame
+ *   one process, n GPUs  trb_group_create / trb_group_load_json -> trb_group_render per frame
+ */
+#define TRB_NCCL_UNIQUE_ID_BYTES 128
+typedef struct trb_comm trb_comm;
+typedef struct trb_group trb_group;
+
+trb_status trb_nccl_unique_id(void* id128);
+/* ncclCommInitRank on `device`: collective over the n_ranks processes. */
+trb_status trb_comm_create(const void* id128, int n_ranks, int rank, int device, trb_comm** out);
+void trb_comm_destroy(trb_comm* comm);
+trb_status trb_comm_info(const trb_comm* comm, int* n_ranks, int* rank);
+/* SUM-reduce `n_floats` of a DEVICE film into rank `root`'s buffer (in place), enqueued on cuda_stream. */
+trb_status trb_comm_reduce_film(trb_comm* comm, float* d_film_rgbw, size_t n_floats, int root, void* cuda_stream);
+
+/* ≙ Exec::render of one rank of the distributed mode + the master's film sum: renders this rank's share of the
+ * selected blocks (interleaved chunks of cfg->shard_chunk blocks, default 32, rank = shard index; cfg->shard_count
+ * == 0xffffffff selects the reference's contiguous ranges instead), all samples, film kept on the device, then ONE
+ * reduce to `root`; on the root the summed film is ADDED into the host buffer `film_rgbw` (ignored elsewhere, may
+ * be NULL). `stats` receives this rank's counters. Blocking. */
+trb_status trb_render_sharded(trb_scene* scene, trb_comm* comm, const trb_render_cfg* cfg, int root, float* film_rgbw,
+                              trb_stats* stats);
+
+/* One process driving n GPUs: a scene replica per device (trb_scene_create on each) plus communicators from
+ * ncclCommInitAll. trb_group_render ≙ Exec::render on all of them: tile-sharded, one reduce to devices[0], film
+ * ADDED into the host buffer; `stats` is the sum over the devices. */
+trb_status trb_group_create(const trb_scene_desc* desc, const int* devices, int n_devices, trb_group** out);
+trb_status trb_group_load_json(const char* path, uint32_t width, uint32_t height, uint32_t spp, const int* devices,
+                               int n_devices, trb_group** out);
+trb_status trb_group_render(trb_group* group, const trb_render_cfg* cfg, float* film_rgbw, trb_stats* stats);
+trb_scene* trb_group_scene(trb_group* group, int index); /* borrowed: replica `index` (film_to_srgb8, info, options) */
+void trb_group_destroy(trb_group* group);
 
 /* ≙ Scene::intersect (scene.rs:148-150) for a batch of rays: closest hit through the
  * two-level BVH in the reference's traversal order. Host buffers. */

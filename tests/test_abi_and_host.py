@@ -155,3 +155,68 @@ def test_cpp_host_mirror_compiles_and_reports_no_device(tmp_path):
         assert r.returncode == 0 and "rendering took" in r.stdout
     else:
         assert r.returncode == 1 and "status" in r.stderr
+
+
+def _build_abi_check(tmp_path):
+    import subprocess
+    exe = str(tmp_path / "abi_check")
+    lib = os.path.join(REPO, "tray_rust_b200", "lib")
+    subprocess.run(["gcc", "-std=c11", "-Wall", "-Werror", "-I" + os.path.join(REPO, "include"), os.path.join(REPO, "tests", "c", "abi_check.c"),
+                    "-L" + lib, "-ltrb", "-Wl,-rpath," + lib, "-o", exe], check=True)
+    return exe
+
+
+CTYPES_OF = {"trb_keyframe": F.Keyframe, "trb_spline": F.Spline, "trb_color_key": F.ColorKey, "trb_instance": F.Instance, "trb_mesh": F.Mesh,
+             "trb_material": F.Material, "trb_camera": F.Camera, "trb_film": F.Film, "trb_integrator": F.Integrator, "trb_scene_desc": F.SceneDesc,
+             "trb_render_cfg": F.RenderCfg, "trb_stats": F.Stats, "trb_ray": F.Ray, "trb_hit": F.Hit, "trb_sample": F.Sample, "trb_bvh_node": F.BvhNode}
+
+
+def test_plain_c_caller_layout_matches_ctypes_and_the_documented_rust_binding(tmp_path):
+    """A C11 translation unit including only include/trb.h: its _Static_asserts pin ABI v3; every sizeof / offsetof it prints
+    must equal the ctypes mirror, and the #[repr(C)] structs INTEGRATION.md documents for the Rust side must list the same
+    fields in the same order (round 1 shipped a Rust TrbRenderCfg three fields short)."""
+    import subprocess
+    out = subprocess.run([_build_abi_check(tmp_path), "layout"], capture_output=True, text=True, check=True).stdout
+    sizes, offsets = {}, {}
+    for line in out.splitlines():
+        a, b, *c = line.split()
+        if b == "sizeof":
+            sizes[a] = int(c[0])
+        elif "." in a:
+            offsets.setdefault(a.split(".")[0], []).append((a.split(".")[1], int(b)))
+    assert "abi_version %d" % F.TRB_ABI_VERSION in out
+    assert set(sizes) == set(CTYPES_OF)
+    for name, ct in CTYPES_OF.items():
+        assert C.sizeof(ct) == sizes[name], name
+        assert [(f, getattr(ct, f).offset) for f, _ in ct._fields_] == offsets[name], name
+    # the Rust declarations in INTEGRATION.md: same field names, same order, matching scalar widths
+    doc = open(os.path.join(REPO, "INTEGRATION.md")).read()
+    width = {"u32": 4, "f32": 4, "u64": 8}
+    for rust, cname in (("TrbRenderCfg", "trb_render_cfg"), ("TrbStats", "trb_stats")):
+        m = re.search(r"pub struct %s \{(.*?)\}" % rust, doc, re.S)
+        assert m, rust
+        fields = [(n.strip(), t.strip()) for n, t in re.findall(r"(\w+)\s*:\s*(\w+)", m.group(1))]
+        assert [n for n, _ in fields] == [f for f, _ in offsets[cname]], rust
+        off = 0
+        for (n, t), (_, o) in zip(fields, offsets[cname]):
+            off = (off + width[t] - 1) // width[t] * width[t]
+            assert off == o, (rust, n)
+            off += width[t]
+        assert (off + 7) // 8 * 8 == sizes[cname] or off == sizes[cname], rust
+
+
+def test_plain_c_caller_reports_no_device_without_a_gpu(tmp_path):
+    import subprocess, torch
+    if torch.cuda.is_available():
+        pytest.skip("GPU present: covered by test_plain_c_caller_renders_through_the_documented_sequence")
+    r = subprocess.run([_build_abi_check(tmp_path), "render", os.path.join(SCENES, "c1_cornell_box.json"), "32", "32", "2"], capture_output=True, text=True)
+    assert r.returncode == 3 and "no CPU fallback" in r.stdout
+
+
+@pytest.mark.gpu
+def test_plain_c_caller_renders_through_the_documented_sequence(tmp_path):
+    """INTEGRATION.md's call sequence from C: trb_scene_load_json -> trb_render (whole frame, one call) -> trb_film_to_srgb8."""
+    import subprocess
+    r = subprocess.run([_build_abi_check(tmp_path), "render", os.path.join(SCENES, "c1_cornell_box.json"), "400", "400", "64"], capture_output=True, text=True)
+    assert r.returncode == 0, r.stdout + r.stderr
+    assert "camera_samples %d" % (400 * 400 * 64) in r.stdout

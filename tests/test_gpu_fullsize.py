@@ -58,7 +58,11 @@ def check_ranges(g, o, ranges, spp, seed, frame=0, counters=True):
         assert gst2.rays_total() == ost.rays_total()
         gf, _ = g.render(flags=F.RENDER_NO_UPDATE, **kw)
         of, _ = o.render(flags=F.RENDER_NO_UPDATE, **kw)
-        assert rmse(gf, of) < 1e-5 and np.allclose(gf, of, rtol=2e-4, atol=2e-5)
+        # a block range's film has rim pixels whose weight sum is ~0 (Mitchell's negative lobes): compare the raw RGBW sums,
+        # tolerance relative to the largest sum (float addition order differs), and rgb / weight only where the weight is solid
+        assert np.allclose(gf, of, rtol=2e-4, atol=2e-5 * max(1.0, float(np.abs(of).max())))
+        solid = of[..., 3] > 0.25 * float(of[..., 3].max())
+        assert float(np.sqrt(np.mean((img(gf)[solid] - img(of)[solid]) ** 2))) < 1e-5
         RAYS["total"] += ost.rays_total()
 
 

@@ -18,7 +18,8 @@ stats = torch.zeros(10, dtype=torch.int64, device=dev)
 flush = torch.empty(256 << 20, dtype=torch.uint8, device=dev)
 g = api.Scene(SB.scene_c4(1_000_000, W, H, 4096).finish(), 0)
 g.update_frame(0, 0.0, 0.0)
-DEFAULTS = {"sort.mode": 0, "sort.bits": 5, "sort.min_round": 1, "shade.split": 0, "pass.graph": 0, "trace.refill": 8, "trace.sched": 6}
+DEFAULTS = {"sort.mode": 0, "sort.bits": 5, "sort.min_round": 1, "shade.split": 0, "pass.graph": 0, "trace.refill": 8, "trace.sched": 6, "trace.mis_bounded": 0,
+            "trace.occupancy": 7, "trace.grid": 12}
 ref = None
 
 
@@ -53,15 +54,22 @@ def measure(name, **opts):
                       "other_ms_per_step": (ms - tms) / STEPS, "bit_exact_vs_first": same}), flush=True)
 
 
-measure("round-1 build (no sort, fused shade)")
-measure("split shade", shade_split=1)
-for bits in (4, 5, 6):
-    measure("sort octant-major bits=%d" % bits, sort_mode=1, sort_bits=bits)
-measure("sort cell-major bits=5", sort_mode=2, sort_bits=5)
-measure("sort octant-major bits=5 from round 2", sort_mode=1, sort_bits=5, sort_min_round=2)
-measure("sort octant-major bits=5 + split", sort_mode=1, sort_bits=5, shade_split=1)
-measure("sort octant-major bits=6 + split", sort_mode=1, sort_bits=6, shade_split=1)
-measure("sort bits=5 + split, refill 4", sort_mode=1, sort_bits=5, shade_split=1, trace_refill=4)
-measure("sort bits=5 + split, refill 16", sort_mode=1, sort_bits=5, shade_split=1, trace_refill=16)
-measure("sort bits=5 + split, sched 4", sort_mode=1, sort_bits=5, shade_split=1, trace_sched=4)
-measure("sort bits=5 + split, sched 10", sort_mode=1, sort_bits=5, shade_split=1, trace_sched=10)
+VARIANTS = os.environ.get("SWEEP", "mis").split(",")
+measure("round-1 configuration (MIS closest-hit, no sort, fused shade)")
+if "mis" in VARIANTS:
+    measure("MIS rays as bounded occlusion queries", trace_mis_bounded=1)
+    measure("bounded MIS + split shade", trace_mis_bounded=1, shade_split=1)
+    for refill in (4, 12, 16):
+        measure("bounded MIS, refill %d" % refill, trace_mis_bounded=1, trace_refill=refill)
+    for sched in (3, 10):
+        measure("bounded MIS, sched %d" % sched, trace_mis_bounded=1, trace_sched=sched)
+    measure("bounded MIS, occupancy 8", trace_mis_bounded=1, trace_occupancy=8)
+    measure("bounded MIS, grid 16", trace_mis_bounded=1, trace_grid=16)
+    measure("bounded MIS + sort octant-major bits=4", trace_mis_bounded=1, sort_mode=1, sort_bits=4)
+if "sort" in VARIANTS:
+    measure("split shade", shade_split=1)
+    for bits in (4, 5, 6):
+        measure("sort octant-major bits=%d" % bits, sort_mode=1, sort_bits=bits)
+    measure("sort cell-major bits=5", sort_mode=2, sort_bits=5)
+    measure("sort octant-major bits=5 from round 2", sort_mode=1, sort_bits=5, sort_min_round=2)
+    measure("sort octant-major bits=5 + split", sort_mode=1, sort_bits=5, shade_split=1)

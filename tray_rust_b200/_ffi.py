@@ -13,8 +13,8 @@ import os
 _HERE = os.path.dirname(os.path.abspath(__file__))
 REPO = os.path.dirname(_HERE)
 
-TRB_ABI_VERSION = 2
-TRB_OK, TRB_INVALID_ARG, TRB_CUDA, TRB_OOM, TRB_UNSUPPORTED, TRB_IO, TRB_NO_DEVICE = range(7)
+TRB_ABI_VERSION = 3
+TRB_OK, TRB_INVALID_ARG, TRB_CUDA, TRB_OOM, TRB_UNSUPPORTED, TRB_IO, TRB_NO_DEVICE, TRB_NCCL = range(8)
 INST_RECEIVER, INST_EMITTER_AREA, INST_EMITTER_POINT = 0, 1, 2
 SHAPE_NONE, SHAPE_SPHERE, SHAPE_DISK, SHAPE_RECT, SHAPE_MESH = 0, 1, 2, 3, 4
 MAT_MATTE, MAT_PLASTIC, MAT_METAL, MAT_SPECULAR_METAL, MAT_GLASS, MAT_ROUGH_GLASS, MAT_MERL = range(7)
@@ -131,6 +131,8 @@ TRB_SYMBOLS = [
     "trb_render_samples", "trb_film_to_srgb8", "trb_block_list", "trb_scene_get_bvh", "trb_scene_get_transform",
     "trb_scene_get_filter_table", "trb_last_error", "trb_abi_version", "trb_desc_load_json", "trb_desc_free",
     "trb_host_build_bvh", "trb_host_keyframe_transform", "trb_host_animated_transform", "trb_host_animated_color", "trb_host_quad_check", "trb_launch_count", "trb_scene_trace_time", "trb_scene_check_error", "trb_scene_set_option",
+    "trb_nccl_unique_id", "trb_comm_create", "trb_comm_destroy", "trb_comm_info", "trb_comm_reduce_film", "trb_render_sharded",
+    "trb_group_create", "trb_group_load_json", "trb_group_render", "trb_group_scene", "trb_group_destroy",
 ]
 
 _trb = None
@@ -182,6 +184,20 @@ def load_trb():
     lib.trb_scene_trace_time.argtypes = [vp, C.POINTER(f32), C.POINTER(u32)]
     lib.trb_scene_check_error.argtypes = [vp]
     lib.trb_scene_set_option.argtypes = [vp, C.c_char_p, C.c_longlong]
+    lib.trb_nccl_unique_id.argtypes = [vp]
+    lib.trb_comm_create.argtypes = [vp, C.c_int, C.c_int, C.c_int, C.POINTER(vp)]
+    lib.trb_comm_destroy.argtypes = [vp]
+    lib.trb_comm_destroy.restype = None
+    lib.trb_comm_info.argtypes = [vp, C.POINTER(C.c_int), C.POINTER(C.c_int)]
+    lib.trb_comm_reduce_film.argtypes = [vp, vp, sz, C.c_int, vp]
+    lib.trb_render_sharded.argtypes = [vp, vp, C.POINTER(RenderCfg), C.c_int, vp, C.POINTER(Stats)]
+    lib.trb_group_create.argtypes = [C.POINTER(SceneDesc), C.POINTER(C.c_int), C.c_int, C.POINTER(vp)]
+    lib.trb_group_load_json.argtypes = [C.c_char_p, u32, u32, u32, C.POINTER(C.c_int), C.c_int, C.POINTER(vp)]
+    lib.trb_group_render.argtypes = [vp, C.POINTER(RenderCfg), vp, C.POINTER(Stats)]
+    lib.trb_group_scene.argtypes = [vp, C.c_int]
+    lib.trb_group_scene.restype = vp
+    lib.trb_group_destroy.argtypes = [vp]
+    lib.trb_group_destroy.restype = None
     _trb = lib
     return lib
 

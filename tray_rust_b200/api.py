@@ -162,6 +162,95 @@ class Scene(_Base):
         return out
 
 
+class Comm:
+    """One rank of a multi-GPU job (one process per GPU): NCCL communicator owned by libtrb (trb_comm_*). The 128-byte
+    unique id is created by rank 0 with ``Comm.unique_id()`` and shipped to the other ranks by any transport."""
+
+    def __init__(self, uid, n_ranks, rank, device):
+        self._lib = F.load_trb()
+        h = C.c_void_p()
+        self._h = None
+        buf = (C.c_char * 128).from_buffer_copy(bytes(uid))
+        rc = self._lib.trb_comm_create(buf, n_ranks, rank, device, C.byref(h))
+        if rc != F.TRB_OK:
+            raise TrbError(rc, (self._lib.trb_last_error() or b"").decode())
+        self._h, self.n_ranks, self.rank, self.device = h, n_ranks, rank, device
+
+    @staticmethod
+    def unique_id():
+        lib = F.load_trb()
+        buf = (C.c_char * 128)()
+        rc = lib.trb_nccl_unique_id(buf)
+        if rc != F.TRB_OK:
+            raise TrbError(rc, (lib.trb_last_error() or b"").decode())
+        return bytes(buf)
+
+    def _check(self, rc):
+        if rc != F.TRB_OK:
+            raise TrbError(rc, (self._lib.trb_last_error() or b"").decode())
+
+    def reduce_film(self, d_film_ptr, n_floats, root=0, stream=None):
+        """SUM-reduce a device film to `root` (in place), enqueued on `stream` (trb_comm_reduce_film: ncclReduce)."""
+        self._check(self._lib.trb_comm_reduce_film(self._h, d_film_ptr, n_floats, root, stream))
+
+    def render_sharded(self, scene, film=None, root=0, **kw):
+        """trb_render_sharded: this rank's tile shard at full spp, ONE film reduce, root adds into its host film."""
+        cfg = _cfg(**kw)
+        if film is None and self.rank == root:
+            film = np.zeros((scene.height, scene.width, 4), np.float32)
+        st = F.Stats()
+        self._check(self._lib.trb_render_sharded(scene._h, self._h, C.byref(cfg), root, F.ptr(film) if film is not None else None, C.byref(st)))
+        return film, st
+
+    def close(self):
+        if self._h is not None:
+            self._lib.trb_comm_destroy(self._h)
+            self._h = None
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+
+class Group:
+    """One process driving several GPUs (trb_group_*): a scene replica per device, tile-sharded render, one film reduce."""
+
+    def __init__(self, desc, devices):
+        self._lib = F.load_trb()
+        self._desc = desc
+        devs = (C.c_int * len(devices))(*devices)
+        h = C.c_void_p()
+        self._h = None
+        rc = self._lib.trb_group_create(C.byref(desc), devs, len(devices), C.byref(h))
+        if rc != F.TRB_OK:
+            raise TrbError(rc, (self._lib.trb_last_error() or b"").decode())
+        self._h, self.devices = h, list(devices)
+        self.width, self.height = desc.film.width, desc.film.height
+
+    def render(self, film=None, **kw):
+        cfg = _cfg(**kw)
+        if film is None:
+            film = np.zeros((self.height, self.width, 4), np.float32)
+        st = F.Stats()
+        rc = self._lib.trb_group_render(self._h, C.byref(cfg), F.ptr(film), C.byref(st))
+        if rc != F.TRB_OK:
+            raise TrbError(rc, (self._lib.trb_last_error() or b"").decode())
+        return film, st
+
+    def close(self):
+        if self._h is not None:
+            self._lib.trb_group_destroy(self._h)
+            self._h = None
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+
 def bits(a):
     """uint32 view of a float32 array (bit-exact comparisons)."""
     return np.ascontiguousarray(a, dtype=np.float32).view(np.uint32)

@@ -1,6 +1,8 @@
 // trb_api.cu — the C ABI of include/trb.h: scene upload, per-frame update and kernel launches.
 // Everything that touches device memory lives here; there is no CPU rendering path in this library.
 #include <chrono>
+#include <dlfcn.h>
+#include <nccl.h>
 #include <cstdio>
 #include <cstdlib>
 #include <memory>
@@ -162,10 +164,11 @@ struct Tuning {
     uint32_t sched = 6;        // trace: quorum of the phased loop (0 = flat state machine)
     int quads = 0;             // trace: DQuad two-level records (measured slower on C4)
     int film_v2 = 1;           // film: per-warp private tiles (0 = shared-memory atomics)
-    int sort = 1;              // ray queues: 0 = path order, 1 = origin-cell / octant counting sort before each trace round
+    int sort = 0;              // ray queues: 0 = path order; 1 / 2 = counting sort by (octant, origin cell) / (cell, octant) before each trace round (measured: -1.5 % trace time, +10 % step time on C4)
     int sort_bits = 5;         // bits per axis of the origin cell grid
     int sort_min_round = 1;    // first bounce round whose queues are sorted (round 0 = primary rays, already coherent)
-    int shade_split = 1;       // shading as three kernels (surface | direct light | BSDF sample) instead of one
+    int mis_bounded = 1;       // trace: MIS rays as occlusion queries bounded by the sampled light's own intersection (0 = closest-hit like the reference)
+    int shade_split = 0;       // shading as three kernels (surface | direct light | BSDF sample) instead of one (measured equal on C4)
     int graph = 1;             // replay each pass as a CUDA graph when its shape repeats
     uint64_t pass_paths = 1ull << 24; // camera samples per wavefront pass (the frame is rendered in additive passes)
 };
@@ -174,7 +177,7 @@ void tuning_from_env(Tuning& t) {
     t.refill = env_int("TRB_REFILL", t.refill); t.occ = env_int("TRB_TRACE_OCC", t.occ); t.trace_grid = (unsigned)env_int("TRB_TRACE_GRID", (int)t.trace_grid);
     t.smem_stack = env_int("TRB_SMEM_STACK", t.smem_stack); t.sched = (uint32_t)env_int("TRB_TRACE_SCHED", (int)t.sched); t.quads = env_int("TRB_TRACE_QUADS", t.quads);
     t.film_v2 = env_int("TRB_FILM_V2", t.film_v2); t.sort = env_int("TRB_SORT", t.sort); t.sort_bits = env_int("TRB_SORT_BITS", t.sort_bits);
-    t.sort_min_round = env_int("TRB_SORT_MIN_ROUND", t.sort_min_round); t.shade_split = env_int("TRB_SHADE_SPLIT", t.shade_split); t.graph = env_int("TRB_GRAPH", t.graph);
+    t.sort_min_round = env_int("TRB_SORT_MIN_ROUND", t.sort_min_round); t.mis_bounded = env_int("TRB_MIS_BOUNDED", t.mis_bounded); t.shade_split = env_int("TRB_SHADE_SPLIT", t.shade_split); t.graph = env_int("TRB_GRAPH", t.graph);
     if (getenv("TRB_PASS_PATHS")) t.pass_paths = strtoull(getenv("TRB_PASS_PATHS"), nullptr, 0);
 }
 
@@ -424,6 +427,8 @@ trb_status launch_wavefront(trb_scene* s, const trb::RenderParams& rp, uint32_t 
     const unsigned tgrid = (unsigned)s->sm_count * tu.trace_grid;
     const uint32_t sched = tu.sched;   // 0 = flat state machine; else the quorum of the phased loop (see k_wf_trace)
     const bool quads = tu.quads != 0;  // DQuad two-level records (never in the STATS variants: their counters are the reference's)
+    // bit 8: MIS rays as bounded occlusion queries — not when the caller asked for the reference's traversal work (test counters, closest-hit shadows)
+    const uint32_t tflags = (flags & 0xffu) | ((tu.mis_bounded && !(flags & (TRB_RENDER_STATS | TRB_RENDER_REFERENCE_SHADOW))) ? 0x100u : 0u);
     for (uint32_t round = 0; round < rounds; ++round) {
         const uint32_t* q_sorted = nullptr;
         if (tu.sort && (int)round >= tu.sort_min_round) { // counting sort of this round's rays by (type, octant, origin cell): DESIGN.md "Ray sorting"
@@ -441,7 +446,7 @@ trb_status launch_wavefront(trb_scene* s, const trb::RenderParams& rp, uint32_t 
             else { CU(cudaEventCreate(&ev.first)); CU(cudaEventCreate(&ev.second)); }
             CU(cudaEventRecord(ev.first, st));
         }
-#define TRB_TRACE_LAUNCH(ST, MB, SS, AN, PH, QD) trb::k_wf_trace<ST, MB, SS, AN, PH, QD><<<tgrid, 128, 0, st>>>(s->ds, rp, wf, round, flags, refill, sched, q_sorted)
+#define TRB_TRACE_LAUNCH(ST, MB, SS, AN, PH, QD) trb::k_wf_trace<ST, MB, SS, AN, PH, QD><<<tgrid, 128, 0, st>>>(s->ds, rp, wf, round, tflags, refill, sched, q_sorted)
         if (anim) { if (stats) TRB_TRACE_LAUNCH(true, 4, 16, true, true, false); else TRB_TRACE_LAUNCH(false, 7, 16, true, true, false); }
         else if (stats) { if (sched) TRB_TRACE_LAUNCH(true, 4, 16, false, true, false); else TRB_TRACE_LAUNCH(true, 4, 16, false, false, false); }
         else if (sched == 0) { if (occ >= 8) TRB_TRACE_LAUNCH(false, 8, 16, false, false, false); else if (occ >= 7) TRB_TRACE_LAUNCH(false, 7, 16, false, false, false); else TRB_TRACE_LAUNCH(false, 6, 16, false, false, false); }
@@ -573,6 +578,7 @@ trb_status trb_scene_set_option(trb_scene* s, const char* name, long long value)
     else if (k == "sort.bits") t.sort_bits = (int)std::min<long long>(6, std::max<long long>(1, value));
     else if (k == "sort.min_round") t.sort_min_round = (int)value;
     else if (k == "shade.split") t.shade_split = (int)value;
+    else if (k == "trace.mis_bounded") t.mis_bounded = (int)value;
     else if (k == "pass.graph") t.graph = (int)value;
     else if (k == "pass.paths") { if (value < 64) return fail(TRB_INVALID_ARG, "pass.paths must be >= 64"); t.pass_paths = (uint64_t)value; }
     else return fail(TRB_INVALID_ARG, "unknown option: " + k);
@@ -1224,6 +1230,283 @@ trb_status trb_host_animated_color(const trb_scene_desc* d, uint32_t first, uint
     if (!d || !rgb3) return fail(TRB_INVALID_ARG, "null argument");
     if (count == 0 || (uint64_t)first + count > d->n_color_keys) return fail(TRB_INVALID_ARG, "colour key range out of bounds");
     trbh::animated_color(d->color_keys, first, count, time, rgb3);
+    return TRB_OK;
+}
+
+
+// ---------------------------------------------------------------------------------------------------------------
+// Multi-GPU: tile sharding + one film SUM-reduce per frame with NCCL called directly (no torch).
+// libnccl is resolved at run time so that the single-GPU library has no link-time dependency on it.
+// ---------------------------------------------------------------------------------------------------------------
+} // extern "C"
+
+namespace {
+struct NcclApi {
+    void* lib = nullptr;
+    ncclResult_t (*GetUniqueId)(ncclUniqueId*) = nullptr;
+    ncclResult_t (*CommInitRank)(ncclComm_t*, int, ncclUniqueId, int) = nullptr;
+    ncclResult_t (*CommInitAll)(ncclComm_t*, int, const int*) = nullptr;
+    ncclResult_t (*CommDestroy)(ncclComm_t) = nullptr;
+    ncclResult_t (*Reduce)(const void*, void*, size_t, ncclDataType_t, ncclRedOp_t, int, ncclComm_t, cudaStream_t) = nullptr;
+    ncclResult_t (*GroupStart)() = nullptr;
+    ncclResult_t (*GroupEnd)() = nullptr;
+    const char* (*GetErrorString)(ncclResult_t) = nullptr;
+};
+NcclApi g_nccl;
+trb_status nccl_load() {
+    if (g_nccl.lib) return TRB_OK;
+    void* h = dlopen("libnccl.so.2", RTLD_NOW | RTLD_NOLOAD); // the copy the process already uses (e.g. PyTorch's)
+    if (!h) h = dlopen("libnccl.so.2", RTLD_NOW | RTLD_GLOBAL);
+    if (!h) h = dlopen("libnccl.so", RTLD_NOW | RTLD_GLOBAL);
+    if (!h) return fail(TRB_NCCL, std::string("cannot load libnccl.so.2: ") + (dlerror() ? dlerror() : "not found"));
+    NcclApi a; a.lib = h;
+#define TRB_SYM(field, name) a.field = reinterpret_cast<decltype(a.field)>(dlsym(h, name)); if (!a.field) return fail(TRB_NCCL, "libnccl lacks " name)
+    TRB_SYM(GetUniqueId, "ncclGetUniqueId"); TRB_SYM(CommInitRank, "ncclCommInitRank"); TRB_SYM(CommInitAll, "ncclCommInitAll");
+    TRB_SYM(CommDestroy, "ncclCommDestroy"); TRB_SYM(Reduce, "ncclReduce"); TRB_SYM(GroupStart, "ncclGroupStart"); TRB_SYM(GroupEnd, "ncclGroupEnd");
+    TRB_SYM(GetErrorString, "ncclGetErrorString");
+#undef TRB_SYM
+    g_nccl = a;
+    return TRB_OK;
+}
+#define NC(call)                                                                                                   \
+    do {                                                                                                           \
+        ncclResult_t r_ = (call);                                                                                  \
+        if (r_ != ncclSuccess) return fail(TRB_NCCL, std::string(#call) + ": " + g_nccl.GetErrorString(r_));       \
+    } while (0)
+} // namespace
+
+struct trb_comm { ncclComm_t comm = nullptr; int n_ranks = 1, rank = 0, device = 0; };
+struct trb_group { std::vector<trb_scene*> scenes; std::vector<ncclComm_t> comms; std::vector<int> devices; };
+
+namespace {
+// this rank's shard of the selected block list inside cfg (interleaved chunks unless the caller asked for the reference's contiguous ranges)
+trb_status shard_cfg(const trb_scene* s, const trb_render_cfg* in, int rank, int n_ranks, trb_render_cfg* out, bool* empty) {
+    *out = *in; *empty = false;
+    if (n_ranks <= 1) { out->shard_index = out->shard_count = out->shard_chunk = 0; return TRB_OK; }
+    if (in->shard_count == 0xffffffffu) { // exec/distrib/master.rs:91-93,218-224: floor(B / W) blocks each, the remainder to the last worker
+        const uint32_t all = (s->film.width / 8) * (s->film.height / 8);
+        const uint32_t sel0 = in->block_count ? std::min(in->block_start, all) : 0u;
+        const uint32_t sel = in->block_count ? (uint32_t)std::min<uint64_t>(all - sel0, in->block_count) : all;
+        const uint32_t per = sel / (uint32_t)n_ranks, start = sel0 + (uint32_t)rank * per;
+        const uint32_t count = rank == n_ranks - 1 ? sel0 + sel - start : per;
+        out->block_start = start; out->block_count = count; out->shard_index = out->shard_count = out->shard_chunk = 0;
+        *empty = count == 0; // block_count 0 would mean "all blocks" (block_queue.rs:39-41): an idle rank must not render
+        return TRB_OK;
+    }
+    out->shard_index = (uint32_t)rank; out->shard_count = (uint32_t)n_ranks; out->shard_chunk = in->shard_chunk ? in->shard_chunk : 32u;
+    return TRB_OK;
+}
+// Exec::render on one replica with the film left on the device: update_frame, clear, all passes of this shard.
+trb_status render_to_device_film(trb_scene* s, const trb_render_cfg* cfg, bool empty, cudaStream_t st) {
+    CU(cudaSetDevice(s->device));
+    if (!(cfg->flags & TRB_RENDER_NO_UPDATE)) {
+        const float step = s->film.scene_time / (float)s->film.frames;
+        trb_status r = trb_scene_update_frame(s, cfg->current_frame, (float)cfg->current_frame * step, ((float)cfg->current_frame + 1.0f) * step);
+        if (r != TRB_OK) return r;
+    }
+    const size_t npx = (size_t)s->film.width * s->film.height;
+    CU(cudaMemsetAsync(s->d_film, 0, npx * sizeof(float4), st));
+    CU(cudaMemsetAsync(s->d_stats, 0, sizeof(trb::DStats), st));
+    if (empty) return TRB_OK;
+    return trb_render_device(s, cfg, reinterpret_cast<float*>(s->d_film), reinterpret_cast<trb_stats*>(s->d_stats), st);
+}
+trb_status film_to_host_add(trb_scene* s, float* film, cudaStream_t st) { // additive, like film::Image::add_pixels (image.rs:21-33)
+    const size_t npx = (size_t)s->film.width * s->film.height;
+    CU(cudaMemcpyAsync(s->h_film_staging, s->d_film, npx * sizeof(float4), cudaMemcpyDeviceToHost, st));
+    CU(cudaStreamSynchronize(st));
+    const float* src = s->h_film_staging;
+    const size_t n = npx * 4;
+    const unsigned nt = n >= (1u << 20) ? std::min(8u, std::max(1u, std::thread::hardware_concurrency())) : 1u;
+    auto add = [film, src](size_t a, size_t b) { for (size_t i = a; i < b; ++i) film[i] += src[i]; };
+    std::vector<std::thread> th;
+    for (unsigned k = 1; k < nt; ++k) th.emplace_back(add, n * k / nt, n * (k + 1) / nt);
+    add(0, n / nt);
+    for (auto& t : th) t.join();
+    return TRB_OK;
+}
+trb_status stats_to_host(trb_scene* s, trb_stats* stats, bool accumulate) {
+    trb::DStats h;
+    CU(cudaSetDevice(s->device));
+    CU(cudaMemcpy(&h, s->d_stats, sizeof h, cudaMemcpyDeviceToHost));
+    trb_stats one; std::memset(&one, 0, sizeof one);
+    stats_out(h, &one);
+    if (!accumulate) { *stats = one; return TRB_OK; }
+    stats->camera_samples += one.camera_samples; stats->rays_primary += one.rays_primary; stats->rays_shadow += one.rays_shadow; stats->rays_mis += one.rays_mis;
+    stats->rays_continuation += one.rays_continuation; stats->node_tests += one.node_tests; stats->tri_tests += one.tri_tests; stats->inst_tests += one.inst_tests;
+    return TRB_OK;
+}
+} // namespace
+
+extern "C" {
+
+trb_status trb_nccl_unique_id(void* id128) {
+    if (!id128) return fail(TRB_INVALID_ARG, "null argument");
+    trb_status r = nccl_load();
+    if (r != TRB_OK) return r;
+    ncclUniqueId id;
+    NC(g_nccl.GetUniqueId(&id));
+    static_assert(sizeof(ncclUniqueId) == TRB_NCCL_UNIQUE_ID_BYTES, "ncclUniqueId size");
+    std::memcpy(id128, &id, sizeof id);
+    return TRB_OK;
+}
+
+trb_status trb_comm_create(const void* id128, int n_ranks, int rank, int device, trb_comm** out) {
+    if (!id128 || !out || n_ranks < 1 || rank < 0 || rank >= n_ranks) return fail(TRB_INVALID_ARG, "bad communicator arguments");
+    *out = nullptr;
+    trb_status r = nccl_load();
+    if (r != TRB_OK) return r;
+    int ndev = 0;
+    if (cudaGetDeviceCount(&ndev) != cudaSuccess || ndev == 0) return fail(TRB_NO_DEVICE, "no CUDA device: tray_rust_b200 has no CPU fallback");
+    if (device < 0 || device >= ndev) return fail(TRB_INVALID_ARG, "device ordinal out of range");
+    CU(cudaSetDevice(device));
+    ncclUniqueId id;
+    std::memcpy(&id, id128, sizeof id);
+    std::unique_ptr<trb_comm> c(new trb_comm);
+    c->n_ranks = n_ranks; c->rank = rank; c->device = device;
+    NC(g_nccl.CommInitRank(&c->comm, n_ranks, id, rank));
+    *out = c.release();
+    return TRB_OK;
+}
+
+void trb_comm_destroy(trb_comm* c) {
+    if (!c) return;
+    if (c->comm && g_nccl.CommDestroy) { cudaSetDevice(c->device); g_nccl.CommDestroy(c->comm); }
+    delete c;
+}
+
+trb_status trb_comm_info(const trb_comm* c, int* n_ranks, int* rank) {
+    if (!c) return fail(TRB_INVALID_ARG, "null communicator");
+    if (n_ranks) *n_ranks = c->n_ranks;
+    if (rank) *rank = c->rank;
+    return TRB_OK;
+}
+
+trb_status trb_comm_reduce_film(trb_comm* c, float* d_film, size_t n, int root, void* stream) {
+    if (!c || !d_film || root < 0 || root >= c->n_ranks) return fail(TRB_INVALID_ARG, "bad reduce arguments");
+    if (c->n_ranks == 1) return TRB_OK;
+    CU(cudaSetDevice(c->device));
+    NC(g_nccl.Reduce(d_film, d_film, n, ncclFloat, ncclSum, root, c->comm, static_cast<cudaStream_t>(stream)));
+    return TRB_OK;
+}
+
+trb_status trb_render_sharded(trb_scene* s, trb_comm* c, const trb_render_cfg* cfg, int root, float* film, trb_stats* stats) {
+    if (!s || !c || !cfg || root < 0 || root >= c->n_ranks) return fail(TRB_INVALID_ARG, "null or bad argument");
+    if (c->rank == root && !film) return fail(TRB_INVALID_ARG, "the root rank needs a film buffer");
+    if (c->device != s->device) return fail(TRB_INVALID_ARG, "scene and communicator live on different devices");
+    trb_render_cfg mine; bool empty;
+    trb_status r = shard_cfg(s, cfg, c->rank, c->n_ranks, &mine, &empty);
+    if (r != TRB_OK) return r;
+    auto t0 = std::chrono::steady_clock::now();
+    CU(cudaSetDevice(s->device));
+    CU(cudaEventRecord(s->ev0, 0));
+    r = render_to_device_film(s, &mine, empty, nullptr);
+    if (r != TRB_OK) return r;
+    CU(cudaEventRecord(s->ev1, 0));
+    r = trb_comm_reduce_film(c, reinterpret_cast<float*>(s->d_film), (size_t)s->film.width * s->film.height * 4, root, nullptr); // ONE reduce per frame
+    if (r != TRB_OK) return r;
+    if (c->rank == root) { r = film_to_host_add(s, film, nullptr); if (r != TRB_OK) return r; }
+    else CU(cudaStreamSynchronize(nullptr));
+    r = check_error_flag(s);
+    if (r != TRB_OK) return r;
+    if (stats) {
+        r = stats_to_host(s, stats, false);
+        if (r != TRB_OK) return r;
+        CU(cudaEventElapsedTime(&stats->kernel_ms, s->ev0, s->ev1));
+        stats->update_ms = std::chrono::duration<float, std::milli>(std::chrono::steady_clock::now() - t0).count() - stats->kernel_ms;
+    }
+    return TRB_OK;
+}
+
+trb_status trb_group_create(const trb_scene_desc* desc, const int* devices, int n, trb_group** out) {
+    if (!out || !devices || n < 1) return fail(TRB_INVALID_ARG, "bad group arguments");
+    *out = nullptr;
+    for (int i = 0; i < n; ++i) for (int j = 0; j < i; ++j) if (devices[i] == devices[j]) return fail(TRB_INVALID_ARG, "duplicate device in group");
+    std::unique_ptr<trb_group> g(new trb_group);
+    g->devices.assign(devices, devices + n);
+    auto cleanup = [&]() { for (trb_scene* s : g->scenes) trb_scene_destroy(s); g->scenes.clear(); };
+    // replicas are built concurrently (the per-mesh SAH build is host work)
+    std::vector<trb_scene*> scenes(n, nullptr);
+    std::vector<trb_status> rc(n, TRB_OK);
+    std::vector<std::string> msg(n);
+    std::vector<std::thread> th;
+    for (int i = 0; i < n; ++i) th.emplace_back([&, i]() { rc[i] = trb_scene_create(desc, devices[i], &scenes[i]); if (rc[i] != TRB_OK) msg[i] = trb_last_error(); });
+    for (auto& t : th) t.join();
+    g->scenes = scenes;
+    for (int i = 0; i < n; ++i) if (rc[i] != TRB_OK) { g->scenes.erase(std::remove(g->scenes.begin(), g->scenes.end(), nullptr), g->scenes.end()); cleanup(); return fail(rc[i], msg[i]); }
+    if (n > 1) {
+        trb_status r = nccl_load();
+        if (r != TRB_OK) { cleanup(); return r; }
+        g->comms.resize(n);
+        ncclResult_t e = g_nccl.CommInitAll(g->comms.data(), n, devices);
+        if (e != ncclSuccess) { cleanup(); return fail(TRB_NCCL, std::string("ncclCommInitAll: ") + g_nccl.GetErrorString(e)); }
+    }
+    *out = g.release();
+    return TRB_OK;
+}
+
+trb_status trb_group_load_json(const char* path, uint32_t w, uint32_t h, uint32_t spp, const int* devices, int n, trb_group** out) {
+    trb_scene_desc* d = nullptr;
+    trb_status r = trb_desc_load_json(path, w, h, spp, &d);
+    if (r != TRB_OK) return r;
+    r = trb_group_create(d, devices, n, out);
+    const std::string keep = g_error;
+    trb_desc_free(d);
+    g_error = keep;
+    return r;
+}
+
+trb_scene* trb_group_scene(trb_group* g, int i) { return (g && i >= 0 && i < (int)g->scenes.size()) ? g->scenes[i] : nullptr; }
+
+void trb_group_destroy(trb_group* g) {
+    if (!g) return;
+    for (size_t i = 0; i < g->comms.size(); ++i) if (g->comms[i]) { cudaSetDevice(g->devices[i]); g_nccl.CommDestroy(g->comms[i]); }
+    for (trb_scene* s : g->scenes) trb_scene_destroy(s);
+    delete g;
+}
+
+trb_status trb_group_render(trb_group* g, const trb_render_cfg* cfg, float* film, trb_stats* stats) {
+    if (!g || !cfg || !film) return fail(TRB_INVALID_ARG, "null argument");
+    const int n = (int)g->scenes.size();
+    if (n == 1) return trb_render(g->scenes[0], cfg, film, stats);
+    auto t0 = std::chrono::steady_clock::now();
+    // enqueue every replica's shard (update_frame is host work per replica; the kernels of all devices then run concurrently)
+    std::vector<trb_status> rc(n, TRB_OK);
+    std::vector<std::string> msg(n);
+    std::vector<std::thread> th;
+    for (int i = 0; i < n; ++i) th.emplace_back([&, i]() {
+        trb_render_cfg mine; bool empty;
+        rc[i] = shard_cfg(g->scenes[i], cfg, i, n, &mine, &empty);
+        if (rc[i] == TRB_OK) { cudaSetDevice(g->scenes[i]->device); cudaEventRecord(g->scenes[i]->ev0, 0); rc[i] = render_to_device_film(g->scenes[i], &mine, empty, nullptr); cudaEventRecord(g->scenes[i]->ev1, 0); }
+        if (rc[i] != TRB_OK) msg[i] = trb_last_error();
+    });
+    for (auto& t : th) t.join();
+    for (int i = 0; i < n; ++i) if (rc[i] != TRB_OK) return fail(rc[i], msg[i]);
+    const size_t nfl = (size_t)g->scenes[0]->film.width * g->scenes[0]->film.height * 4;
+    NC(g_nccl.GroupStart()); // ONE reduce per frame, root = devices[0]
+    for (int i = 0; i < n; ++i) {
+        CU(cudaSetDevice(g->scenes[i]->device));
+        NC(g_nccl.Reduce(g->scenes[i]->d_film, g->scenes[i]->d_film, nfl, ncclFloat, ncclSum, 0, g->comms[i], nullptr));
+    }
+    NC(g_nccl.GroupEnd());
+    CU(cudaSetDevice(g->scenes[0]->device));
+    trb_status r = film_to_host_add(g->scenes[0], film, nullptr);
+    if (r != TRB_OK) return r;
+    float kernel_ms = 0.f;
+    if (stats) std::memset(stats, 0, sizeof *stats);
+    for (int i = 0; i < n; ++i) {
+        CU(cudaSetDevice(g->scenes[i]->device));
+        CU(cudaDeviceSynchronize());
+        r = check_error_flag(g->scenes[i]);
+        if (r != TRB_OK) return r;
+        if (stats) {
+            r = stats_to_host(g->scenes[i], stats, true);
+            if (r != TRB_OK) return r;
+            float ms = 0.f;
+            CU(cudaEventElapsedTime(&ms, g->scenes[i]->ev0, g->scenes[i]->ev1));
+            kernel_ms = std::max(kernel_ms, ms);
+        }
+    }
+    if (stats) { stats->kernel_ms = kernel_ms; stats->update_ms = std::chrono::duration<float, std::milli>(std::chrono::steady_clock::now() - t0).count() - kernel_ms; }
     return TRB_OK;
 }
 

@@ -259,6 +259,7 @@ struct TraceState {
     bool quads_ok;        // the kernel variant may use DQuad records at all
     const DTri* tris;
     uint32_t level_inst;  // instance whose mesh is being traversed, TRB_MISS at the top level
+    uint32_t skip_inst;   // instance the traversal ignores (bounded MIS query: the sampled light itself), TRB_MISS: none
     float tmin, tmax;
     float time;           // ray.time (only read for keyframed instances)
     int sp;
@@ -281,7 +282,7 @@ __device__ __forceinline__ void trace_init(const DScene& sc, TraceState& t, cons
     t.o = t.wo; t.d = t.wd; t.inv = t.winv;
     t.neg = neg_mask(t.d);
     trace_level(t, sc.tlas, sc.tlas_pairs, sc.tlas_quads);
-    t.tris = nullptr; t.level_inst = TRB_MISS;
+    t.tris = nullptr; t.level_inst = TRB_MISS; t.skip_inst = TRB_MISS;
     t.tmin = ray.tmin; t.tmax = ray.tmax;
     t.sp = 0; t.cur = ST_ROOT; t.found = false; t.any_hit = any_hit;
     t.h_inst = TRB_MISS; t.h_prim = 0; t.h_b1 = 0.0f; t.h_b2 = 0.0f;
@@ -541,7 +542,7 @@ __device__ __forceinline__ void step_other(const DScene& sc, TraceState& t, cons
         const DInstance& in = sc.instances[ii];
         if (STATS) cnt.inst++;
         const uint32_t kind = __ldg(&in.kind), shape = __ldg(&in.shape);
-        if (kind != TRB_INST_EMITTER_POINT) {
+        if (kind != TRB_INST_EMITTER_POINT && ii != t.skip_inst) {
             float m[16];
             instance_inv<ANIM>(sc, in, t.time, m);
             const f3 lo_ = xf_point(m, t.wo), ld_ = xf_vector(m, t.wd);
@@ -1110,13 +1111,14 @@ struct RayCounts { uint32_t primary, shadow, mis, cont; };
 struct DirectSetup {
     f3 a, b;             // contributions enabled by the shadow / MIS ray
     f3 shadow_d, mis_d;  // shadow segment p -> light sample (t in [0.001, 0.999]); MIS direction (t in [0.001, inf))
+    float mis_t;         // where the MIS ray meets the sampled light's own shape (Emitter::intersect's t), < 0: it cannot hit it
     bool has_shadow, has_mis;
 };
 
 template <bool ANIM>
 __device__ __noinline__ void direct_setup(const DScene& sc, const Mat& m, const Frame& fr, f3 wo, uint32_t li, float l0, float l1, float b0, float b1,
                                           float bc, float time, DirectSetup& ds) {
-    ds.a = splat(0.0f); ds.b = splat(0.0f); ds.shadow_d = splat(0.0f); ds.mis_d = splat(0.0f); ds.has_shadow = false; ds.has_mis = false;
+    ds.a = splat(0.0f); ds.b = splat(0.0f); ds.shadow_d = splat(0.0f); ds.mis_d = splat(0.0f); ds.has_shadow = false; ds.has_mis = false; ds.mis_t = -1.0f;
     const DInstance& light = sc.instances[li];
     const uint32_t kind = __ldg(&light.kind), shape = __ldg(&light.shape);
     const float p0 = __ldg(&light.p0), p1 = __ldg(&light.p1);
@@ -1175,6 +1177,17 @@ __device__ __noinline__ void direct_setup(const DScene& sc, const Mat& m, const 
             if (go) {
                 ds.has_mis = true; ds.mis_d = wi2; // Ray::segment(p, w_i, 0.001, inf)
                 ds.b = f * emission * fabsf(dot3(wi2, fr.n)) * w / pdf_bsdf; // used iff the ray hits this light from its front
+                // The only thing the integrator asks of this ray is "is its closest hit the sampled light?" (integrator/mod.rs:156-162).
+                // The light's own intersection is known here: the very expressions Emitter::intersect evaluates when the traversal
+                // reaches the light (emitter.rs:118-137: inv_mul_ray with the unnormalised direction, then the shape test on
+                // [0.001, inf)), so the trace kernel can answer with an occlusion query bounded by it (k_wf_trace, MIS_BOUNDED).
+                const f3 ol = xf_point(linv, p), dl = xf_vector(linv, wi2);
+                float tl = finf();
+                bool hl;
+                if (shape == TRB_SHAPE_SPHERE) hl = sphere_t(p0, ol, dl, 0.001f, tl);
+                else if (shape == TRB_SHAPE_DISK) hl = disk_t(p0, p1, ol, dl, 0.001f, tl);
+                else hl = rect_t(p0, p1, ol, dl, 0.001f, tl);
+                ds.mis_t = hl ? tl : -1.0f;
             }
         }
     }
@@ -1700,21 +1713,41 @@ __global__ void __launch_bounds__(128, MINB) k_wf_trace(const __grid_constant__ 
     bool have = false, exhausted = false;
     uint32_t p = 0;
     int type = 0;
+    // MIS rays as bounded occlusion queries (flags bit 8; never with the STATS / reference-shadow variants, whose counters are
+    // the reference's): mis_li = the sampled light (TRB_MISS: this lane's ray is an ordinary query), mis_tl = its distance.
+    const bool mis_bounded = PHASED && !STATS && (flags & 0x100u) != 0;
+    uint32_t mis_li = TRB_MISS;
+    float mis_tl = 0.0f;
     for (;;) {
         // ---- retire finished rays ----
         if (have && t.cur == ST_DONE) {
+            bool retry = false;
             if (type == 0) {
                 __stcs(&wf.cont[p], make_float4(t.wd.x, t.wd.y, t.wd.z, t.tmax));
                 __stcs(&wf.hit[p], make_uint4(t.found ? t.h_inst : TRB_MISS, t.h_prim, __float_as_uint(t.h_b1), __float_as_uint(t.h_b2)));
             } else if (type == 1) {
                 __stcs(&wf.shadow[p], make_float4(t.wd.x, t.wd.y, t.wd.z, __uint_as_float(t.found ? 1u : 0u)));
-            } else {
+            } else if (mis_li == TRB_MISS) { // MIS ray as a closest-hit query, like the reference (integrator/mod.rs:156)
                 __stcs(&wf.mis[p], make_float4(t.wd.x, t.wd.y, t.wd.z, t.tmax));
                 float4 a4 = __ldcs(&wf.a[p]);
                 a4.w = __uint_as_float(t.found ? t.h_inst : TRB_MISS);
                 __stcs(&wf.a[p], a4);
+            } else if (t.found && t.tmax == mis_tl) {
+                // Bounded query, and something else was accepted at EXACTLY the light's distance: which of the two the reference keeps
+                // depends on its traversal order ("last accepted wins", Q9), so this ray is traced again as the reference does.
+                Ray ray; ray.o = t.wo; ray.d = t.wd; ray.tmin = 0.001f; ray.tmax = finf();
+                trace_init(sc, t, ray, false, t.time, QUADS && PHASED);
+                if (PHASED) { stack.put(0, (unsigned long long)ST_DONE); t.sp = 1; }
+                mis_li = TRB_MISS;
+                retry = true;
+            } else {
+                // Bounded query: the light is the closest hit iff its own shape is hit (mis_tl >= 0) and nothing else is accepted on
+                // [0.001, mis_tl]. wf.mis[p].w already holds mis_tl, the t the traversal would have accepted the light with.
+                float4 a4 = __ldcs(&wf.a[p]);
+                a4.w = __uint_as_float((mis_tl >= 0.0f && !t.found) ? mis_li : TRB_MISS);
+                __stcs(&wf.a[p], a4);
             }
-            have = false;
+            have = retry;
         }
         // ---- refill idle lanes ----
         const unsigned idle = __ballot_sync(0xffffffffu, !have);
@@ -1736,8 +1769,17 @@ __global__ void __launch_bounds__(128, MINB) k_wf_trace(const __grid_constant__ 
                     Ray ray; ray.o = mk(o4.x, o4.y, o4.z); ray.d = mk(d4.x, d4.y, d4.z);
                     ray.tmin = (type == 0 && round == 0) ? 0.0f : 0.001f;
                     ray.tmax = type == 1 ? 0.999f : finf();
-                    trace_init(sc, t, ray, type == 1 && shadow_any, ANIM ? __ldg(&wf.thr[p].w) : 0.0f, QUADS && PHASED);
+                    bool any = type == 1 && shadow_any;
+                    mis_li = TRB_MISS;
+                    if (mis_bounded && type == 2) { // "is the closest hit the sampled light?" == "is anything but that light accepted before it?"
+                        mis_tl = d4.w;
+                        mis_li = __float_as_uint(__ldcs(&wf.b[p]).w);
+                        if (mis_tl >= 0.0f) { ray.tmax = mis_tl; any = true; }
+                    }
+                    trace_init(sc, t, ray, any, ANIM ? __ldg(&wf.thr[p].w) : 0.0f, QUADS && PHASED);
+                    t.skip_inst = mis_li;
                     if (PHASED) { stack.put(0, (unsigned long long)ST_DONE); t.sp = 1; } // bottom sentinel: popping it ends the ray
+                    if (mis_li != TRB_MISS && mis_tl < 0.0f) t.cur = ST_DONE;            // the ray misses the light's shape: nothing to trace
                     have = true;
                 }
             }
@@ -1856,7 +1898,7 @@ __global__ void __launch_bounds__(128, MINB) k_wf_shade(const __grid_constant__ 
                         wf.org[p] = make_float4(o.org.x, o.org.y, o.org.z, __uint_as_float(nf));
                         if (push_cont) wf.cont[p] = make_float4(o.next_d.x, o.next_d.y, o.next_d.z, finf());
                         if (push_shadow) wf.shadow[p] = make_float4(o.ds.shadow_d.x, o.ds.shadow_d.y, o.ds.shadow_d.z, 0.0f);
-                        if (push_mis) wf.mis[p] = make_float4(o.ds.mis_d.x, o.ds.mis_d.y, o.ds.mis_d.z, finf());
+                        if (push_mis) wf.mis[p] = make_float4(o.ds.mis_d.x, o.ds.mis_d.y, o.ds.mis_d.z, o.ds.mis_t);
                         wf.a[p] = make_float4(o.ds.a.x, o.ds.a.y, o.ds.a.z, __uint_as_float(TRB_MISS));
                         wf.b[p] = make_float4(o.ds.b.x, o.ds.b.y, o.ds.b.z, __uint_as_float(o.light));
                         wf.tprev[p] = make_float4(o.t_before.x, o.t_before.y, o.t_before.z, 0.0f);
@@ -2008,7 +2050,7 @@ __global__ void __launch_bounds__(128, MINB) k_wf_shade_b(const __grid_constant_
             push_shadow = ds.has_shadow; push_mis = ds.has_mis;
             wf.org[p] = make_float4(fr.p.x, fr.p.y, fr.p.z, __uint_as_float((push_shadow ? WF_F_SHADOW : 0u) | (push_mis ? WF_F_MIS : 0u)));
             if (push_shadow) wf.shadow[p] = make_float4(ds.shadow_d.x, ds.shadow_d.y, ds.shadow_d.z, 0.0f);
-            if (push_mis) wf.mis[p] = make_float4(ds.mis_d.x, ds.mis_d.y, ds.mis_d.z, finf());
+            if (push_mis) wf.mis[p] = make_float4(ds.mis_d.x, ds.mis_d.y, ds.mis_d.z, ds.mis_t);
             wf.a[p] = make_float4(ds.a.x, ds.a.y, ds.a.z, __uint_as_float(TRB_MISS));
             wf.b[p] = make_float4(ds.b.x, ds.b.y, ds.b.z, __uint_as_float(light));
             wf.tprev[p] = make_float4(th4.x, th4.y, th4.z, 0.0f); // path_throughput multiplying this bounce's direct light
