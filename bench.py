@@ -103,7 +103,12 @@ def host_threads():
 
 def host_info():
     """What the CPU arm ran on: logical CPUs, affinity mask size, physical cores and the model name (from /proc/cpuinfo)."""
-    info = {"nproc": os.cpu_count(), "affinity": host_threads(), "physical_cores": None, "model": None}
+    info = {"nproc": os.cpu_count(), "affinity": host_threads(), "physical_cores": None, "model": None, "cgroup_cpu_quota_cores": None}
+    try:   # a container CPU quota caps the all-core rate whatever nproc says
+        q, per = open("/sys/fs/cgroup/cpu.max").read().split()
+        info["cgroup_cpu_quota_cores"] = None if q == "max" else float(q) / float(per)
+    except Exception:
+        pass
     try:
         cores, phys, core = set(), None, None
         for line in open("/proc/cpuinfo"):

@@ -153,10 +153,15 @@ typedef struct trb_film {
     float filter_b, filter_c; /* Mitchell-Netravali b,c; Gaussian: filter_b = alpha */
 } trb_film;
 
-enum { TRB_INTEGRATOR_PATH = 0 };
+enum {
+    TRB_INTEGRATOR_PATH = 0,          /* integrator/path.rs:35-43: min_depth, max_depth */
+    TRB_INTEGRATOR_WHITTED = 1,       /* integrator/whitted.rs:29-38: max_depth = recursion limit (the JSON loader reads it from
+                                         "min_depth", like scene.rs:305-309); min_depth unused */
+    TRB_INTEGRATOR_NORMALS_DEBUG = 2  /* integrator/normals_debug.rs:25-36: (shading normal + 1) / 2 */
+};
 typedef struct trb_integrator {
     uint32_t type;
-    uint32_t min_depth, max_depth; /* integrator/path.rs:35-43 */
+    uint32_t min_depth, max_depth;
 } trb_integrator;
 
 typedef struct trb_scene_desc {

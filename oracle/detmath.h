@@ -202,7 +202,12 @@ enum {
     DM_S_LC = 9, DM_S_LC_PERM = 10,
     DM_S_BC = 11, DM_S_BC_PERM = 12,
     DM_S_PC = 13, DM_S_PC_PERM = 14,
-    DM_S_RR = 32
+    DM_S_RR = 32,
+    /* Whitted (integrator/whitted.rs, integrator/mod.rs:41-103): every illumination / specular_reflection / specular_transmission call
+     * asks the sampler for fresh 1-element arrays (a new random scramble each, ld.rs:55-63). Node n of the recursion tree (root 1,
+     * reflection child 2n, transmission child 2n+1) draws dimension DM_S_WHITTED + 8n + slot:
+     *   0,1 light sample_2d   2,3 reflection sample_2d   4 reflection sample_1d   5,6 transmission sample_2d   7 transmission sample_1d */
+    DM_S_WHITTED = 4096
 };
 
 #endif

@@ -292,7 +292,7 @@ int orc_scene_create(const trb_scene_desc* d, orc_scene** out) {
     if (!d || !out || d->abi_version != TRB_ABI_VERSION) { g_err = "bad desc"; return TRB_INVALID_ARG; }
     if (d->film.width % 8 || d->film.height % 8 || d->film.width == 0 || d->film.height == 0) { g_err = "image not divisible into 8x8 blocks"; return TRB_INVALID_ARG; }
     if (d->n_instances == 0) { g_err = "the scene does not have any objects"; return TRB_INVALID_ARG; }
-    if (d->integrator.type != TRB_INTEGRATOR_PATH) { g_err = "integrator unsupported"; return TRB_UNSUPPORTED; }
+    if (d->integrator.type > TRB_INTEGRATOR_NORMALS_DEBUG) { g_err = "Unrecognized integrator type"; return TRB_INVALID_ARG; }
     orc_scene* s = new orc_scene;
     s->film = d->film;
     s->spp_pow2 = next_pow2(std::max(1u, d->film.samples));
@@ -347,7 +347,7 @@ int orc_scene_create(const trb_scene_desc* d, orc_scene** out) {
     }
     if (s->cameras.empty()) { delete s; g_err = "A camera is required"; return TRB_INVALID_ARG; }
     s->shade.geom = &s->geom;
-    s->shade.min_depth = d->integrator.min_depth; s->shade.max_depth = d->integrator.max_depth;
+    s->shade.min_depth = d->integrator.min_depth; s->shade.max_depth = d->integrator.max_depth; s->shade.integrator = d->integrator.type;
     /* Scene::load_file builds the TLAS for [0, scene_time] (scene.rs:141); update_frame rebuilds it */
     s->geom.rebuild(0.0f, d->film.scene_time);
     *out = s;

@@ -424,6 +424,7 @@ struct SceneShade {
     std::vector<Material> materials;
     std::vector<uint32_t> lights; /* instance indices of emitters in object order (Q20) */
     uint32_t min_depth = 0, max_depth = 0;
+    uint32_t integrator = TRB_INTEGRATOR_PATH; /* Whitted: max_depth is its recursion limit (scene.rs:305-309 reads it from "min_depth") */
 
     /* Emitter::radiance (emitter.rs:140-142) */
     Col radiance(const Instance& e, V3 w, V3 n, float time) const {
@@ -509,8 +510,67 @@ struct SceneShade {
         return direct_light;
     }
 
+    /* NormalsDebug::illumination (integrator/normals_debug.rs:28-36) */
+    Col normals_debug(const Hit& hit) const {
+        BSDF bsdf;
+        materials[geom->instances[hit.inst].material].bsdf(hit.dg, bsdf);
+        return (Col(bsdf.n.x, bsdf.n.y, bsdf.n.z) + Col(1.0f)) / 2.0f;
+    }
+    /* One 1-element sampler array: get_samples_2d / get_samples_1d with a fresh scramble and index 0 (ld.rs:55-64, 91-119) */
+    static void whitted_2d(const PathSamples& ps, uint32_t node, uint32_t slot, float& x, float& y) {
+        x = van_der_corput(0, dm_scramble(ps.draw(DM_S_WHITTED + 8 * node + slot)));
+        y = sobol(0, dm_scramble(ps.draw(DM_S_WHITTED + 8 * node + slot + 1)));
+    }
+    static float whitted_1d(const PathSamples& ps, uint32_t node, uint32_t slot) { return van_der_corput(0, dm_scramble(ps.draw(DM_S_WHITTED + 8 * node + slot))); }
+    /* Integrator::specular_reflection / specular_transmission (integrator/mod.rs:41-103); `flags` = {Specular, Reflection | Transmission} */
+    Col whitted_specular(const Ray& ray, uint32_t depth, const BSDF& bsdf, uint32_t flags, uint32_t child, uint32_t slot, uint32_t node, const PathSamples& ps,
+                         Counters& cnt) const {
+        V3 w_o = -ray.d;
+        float u0, u1;
+        whitted_2d(ps, node, slot, u0, u1);
+        float uc = whitted_1d(ps, node, slot + 2);
+        Col f; V3 w_i; float pdf; uint32_t sampled;
+        bsdf.sample(w_o, flags, u0, u1, uc, f, w_i, pdf, sampled);
+        Col out(0.0f);
+        if (pdf > 0.0f && !f.is_black() && fabsf(dot(w_i, bsdf.n)) != 0.0f) {
+            Ray r2(bsdf.p, w_i, ray.time); /* ray.child(&bsdf.p, &w_i): direction as sampled */
+            r2.min_t = 0.001f;
+            Hit h;
+            cnt.rays[3]++;
+            if (geom->intersect(r2, h, cnt)) {
+                Col li = whitted(r2, depth + 1, h, child, ps, cnt);
+                out = f * li * fabsf(dot(w_i, bsdf.n)) / pdf;
+            }
+        }
+        return out;
+    }
+    /* Whitted::illumination (integrator/whitted.rs:41-70) */
+    Col whitted(const Ray& ray, uint32_t depth, const Hit& hit, uint32_t node, const PathSamples& ps, Counters& cnt) const {
+        const Instance& inst = geom->instances[hit.inst];
+        BSDF bsdf;
+        materials[inst.material].bsdf(hit.dg, bsdf);
+        V3 w_o = -ray.d;
+        float u0, u1;
+        whitted_2d(ps, node, 0, u0, u1);
+        Col illum(0.0f);
+        if (depth == 0 && inst.is_emitter()) illum = illum + radiance(inst, -ray.d, hit.dg.ng, ray.time);
+        for (uint32_t li : lights) {
+            Col lrad; V3 w_i; float pdf; Ray occl;
+            sample_incident(li, hit.dg.p, u0, u1, ray.time, lrad, w_i, pdf, occl);
+            Col f = bsdf.eval(w_o, w_i, BX_ALL);
+            if (!lrad.is_black() && !f.is_black() && !occluded(occl, cnt)) illum = illum + f * lrad * fabsf(dot(w_i, bsdf.n)) / pdf;
+        }
+        if (depth < max_depth) {
+            illum = illum + whitted_specular(ray, depth, bsdf, BX_SPECULAR | BX_REFLECTION, 2 * node, 2, node, ps, cnt);
+            illum = illum + whitted_specular(ray, depth, bsdf, BX_SPECULAR | BX_TRANSMISSION, 2 * node + 1, 5, node, ps, cnt);
+        }
+        return illum;
+    }
+
     /* Path::illumination (integrator/path.rs:45-119) */
     Col illumination(const Ray& r, const Hit& hit, const PathSamples& ps, Counters& cnt) const {
+        if (integrator == TRB_INTEGRATOR_NORMALS_DEBUG) return normals_debug(hit);
+        if (integrator == TRB_INTEGRATOR_WHITTED) return whitted(r, 0, hit, 1, ps, cnt);
         Col illum(0.0f), path_throughput(1.0f);
         bool specular_bounce = false;
         Hit current_hit = hit;

@@ -58,7 +58,10 @@ def test_reference_panics_become_status_codes(trb):
     b = base(); b.cameras = []
     assert _create(trb, b.finish())[0] == F.TRB_INVALID_ARG
     b = base(); b.integrator = (7, 1, 2)
-    assert _create(trb, b.finish())[0] == F.TRB_UNSUPPORTED
+    rc, msg = _create(trb, b.finish())
+    assert rc == F.TRB_INVALID_ARG and "Unrecognized integrator type" in msg          # scene.rs:313
+    b = base(); b.integrator = (F.INTEGRATOR_WHITTED, 0, 40)
+    assert _create(trb, b.finish())[0] == F.TRB_UNSUPPORTED                            # deeper than the device recursion stack provided for
     d = base().finish(); d.abi_version = 99
     assert _create(trb, d)[0] == F.TRB_INVALID_ARG
     b = base(); b.instances[5] = b.instances[5][:5] + (99,) + b.instances[5][6:]      # material out of range

@@ -167,3 +167,80 @@ def test_film_filter_properties(oracle):
     srgb = o.to_srgb8(film)
     exp = [int((1.055 * c ** (1 / 2.4) - 0.055) * 255.0) for c in (0.25, 0.5, 0.75)]
     assert np.abs(srgb.reshape(-1, 3).astype(int) - exp).max() <= 1
+
+
+# ---- the reference's other integrators -------------------------------------------------
+
+def test_normals_debug_is_half_the_shading_normal_plus_half(oracle):
+    """NormalsDebug::illumination = (bsdf.n + 1) / 2 (integrator/normals_debug.rs:28-36): a sphere seen head-on."""
+    b = SB.SceneBuilder(8, 8, 4)
+    b.integrator = (F.INTEGRATOR_NORMALS_DEBUG, 0, 0)
+    white = b.add_material(F.MAT_MATTE, (0.8, 0.8, 0.8), roughness=0.0)
+    b.receiver(F.SHAPE_SPHERE, white, [SB.trs(s=2.0)], p0=1.0)
+    b.point_light([SB.trs(t=(0, 10, 0))], (1, 1, 1, 10))
+    b.add_camera([SB.trs(t=(0, 0, -10))], fov=1.0)      # a needle of rays at the sphere's near pole: n = (0, 0, -1)
+    o = O.OracleScene(b.finish())
+    o.update_frame(0, 0.0, 0.0)
+    s, st = o.render_samples(seed=2)
+    assert np.allclose(s["r"], 0.5, atol=0.02) and np.allclose(s["g"], 0.5, atol=0.02) and np.allclose(s["b"], 0.0, atol=1e-3) and abs(float(s["r"].mean()) - 0.5) < 2e-3
+    assert st.rays_shadow == 0 and st.rays_continuation == 0 and st.rays_primary == len(s)
+
+
+def whitted_floor_scene(mat, depth, spp=16, light_height=4.0):
+    b = SB.SceneBuilder(8, 8, spp)
+    b.integrator = (F.INTEGRATOR_WHITTED, 0, depth)
+    m = b.add_material(*mat[0], **mat[1])
+    b.receiver(F.SHAPE_RECT, m, [SB.trs(q=SB.quat_axis_angle((1, 0, 0), -90), s=50)], p0=2, p1=2)        # floor y = 0, normal +y
+    b.point_light([SB.trs(t=(0, light_height, 0))], (1, 1, 1, 8))
+    b.add_camera([SB.trs(t=(0, 3, -6), q=SB.quat_axis_angle((1, 0, 0), 26.565))], fov=2.0)             # looks at the origin
+    return b
+
+
+def test_whitted_direct_term_matches_closed_form(oracle):
+    """Whitted on a Lambertian floor under a point light: L = rho/pi * I / d^2 * cos(theta) exactly (whitted.rs:56-62, emitter.rs:169-174),
+    one shadow ray per light and camera sample, no specular recursion."""
+    o = O.OracleScene(whitted_floor_scene(((F.MAT_MATTE, (0.6, 0.6, 0.6)), dict(roughness=0.0)), 5).finish())
+    o.update_frame(0, 0.0, 0.0)
+    s, st = o.render_samples(seed=4)
+    rays, _ = o.camera_rays(seed=4)
+    hits, _ = o.intersect(rays)
+    p = rays["o"] + rays["d"] * hits["t"][:, None]
+    d2 = p[:, 0] ** 2 + (4.0 - p[:, 1]) ** 2 + p[:, 2] ** 2
+    expect = 0.6 / math.pi * 8.0 / d2 * (4.0 / np.sqrt(d2))
+    assert np.allclose(s["r"], expect, rtol=2e-4)
+    assert st.rays_shadow == len(s) and st.rays_continuation == 0
+
+
+def test_whitted_mirror_recursion_and_depth_limit(oracle):
+    """A specular-metal floor under a point light and a Lambertian ceiling: the reflection ray (integrator/mod.rs:41-71) carries the
+    ceiling's direct light back, weighted by the Fresnel reflectance; max_depth 0 cuts the recursion (whitted.rs:63-66)."""
+    def build(depth):
+        b = whitted_floor_scene(((F.MAT_SPECULAR_METAL, (0.2, 0.9, 1.1), (3.9, 2.4, 2.2)), {}), depth)
+        grey = b.add_material(F.MAT_MATTE, (0.5, 0.5, 0.5), roughness=0.0)
+        b.receiver(F.SHAPE_RECT, grey, [SB.trs(t=(0, 9, 0), q=SB.quat_axis_angle((1, 0, 0), 90), s=50)], p0=2, p1=2)   # ceiling y = 9, normal -y
+        return b
+    o0, o3 = O.OracleScene(build(0).finish()), O.OracleScene(build(3).finish())
+    o0.update_frame(0, 0.0, 0.0); o3.update_frame(0, 0.0, 0.0)
+    s0, st0 = o0.render_samples(seed=4)
+    s3, st3 = o3.render_samples(seed=4)
+    assert st0.rays_continuation == 0 and np.all(s0["r"] == 0.0)                  # a mirror has no non-specular response to the light sample
+    assert st3.rays_continuation >= len(s3)                                        # at least the first reflection ray per sample
+    assert (s3["r"] > 0).all() and (s3["r"] < 0.5 / math.pi * 8.0 / 25.0 * 1.01).all()   # <= the ceiling's own direct light (rho/pi * I / d^2, d >= 5)
+
+
+def test_whitted_glass_branches_into_reflection_and_transmission(oracle):
+    """Glass has both specular lobes: every visit spawns a reflection AND a transmission ray (a binary recursion tree)."""
+    b = SB.SceneBuilder(8, 8, 4)
+    b.integrator = (F.INTEGRATOR_WHITTED, 0, 2)
+    glass = b.add_material(F.MAT_GLASS, (1, 1, 1), (1, 1, 1), eta=1.5)
+    grey = b.add_material(F.MAT_MATTE, (0.5, 0.5, 0.5), roughness=0.0)
+    b.receiver(F.SHAPE_SPHERE, glass, [SB.trs(s=2.0)], p0=1.0)
+    b.receiver(F.SHAPE_SPHERE, grey, [SB.trs(s=60.0)], p0=1.0)                    # an enclosing diffuse shell: every ray lands somewhere
+    b.point_light([SB.trs(t=(0, 10, -10))], (1, 1, 1, 200))
+    b.add_camera([SB.trs(t=(0, 0, -10))], fov=8.0)
+    o = O.OracleScene(b.finish())
+    o.update_frame(0, 0.0, 0.0)
+    s, st = o.render_samples(seed=3)
+    n = len(s)
+    assert st.rays_continuation > 3 * n                                             # depth 0: 2 rays, depth 1: up to 4 more
+    assert st.rays_continuation <= (2 + 4) * n and np.isfinite(s["r"]).all() and (s["r"] > 0).mean() > 0.9

@@ -19,6 +19,7 @@ INST_RECEIVER, INST_EMITTER_AREA, INST_EMITTER_POINT = 0, 1, 2
 SHAPE_NONE, SHAPE_SPHERE, SHAPE_DISK, SHAPE_RECT, SHAPE_MESH = 0, 1, 2, 3, 4
 MAT_MATTE, MAT_PLASTIC, MAT_METAL, MAT_SPECULAR_METAL, MAT_GLASS, MAT_ROUGH_GLASS, MAT_MERL = range(7)
 FILTER_MITCHELL_NETRAVALI, FILTER_GAUSSIAN = 0, 1
+INTEGRATOR_PATH, INTEGRATOR_WHITTED, INTEGRATOR_NORMALS_DEBUG = 0, 1, 2
 RENDER_STATS, RENDER_NO_UPDATE, RENDER_REFERENCE_SHADOW, RENDER_MEGAKERNEL, RENDER_TIME_TRACE = 1, 2, 4, 8, 16
 MISS = 0xFFFFFFFF
 BVH_LEAF = 0x80000000

@@ -167,7 +167,6 @@ struct Tuning {
     int sort = 0;              // ray queues: 0 = path order; 1 / 2 = counting sort by (octant, origin cell) / (cell, octant) before each trace round (measured: -1.5 % trace time, +10 % step time on C4)
     int sort_bits = 5;         // bits per axis of the origin cell grid
     int sort_min_round = 1;    // first bounce round whose queues are sorted (round 0 = primary rays, already coherent)
-    int mis_bounded = 1;       // trace: MIS rays as occlusion queries bounded by the sampled light's own intersection (0 = closest-hit like the reference)
     int shade_split = 0;       // shading as three kernels (surface | direct light | BSDF sample) instead of one (measured equal on C4)
     int graph = 1;             // replay each pass as a CUDA graph when its shape repeats
     uint64_t pass_paths = 1ull << 24; // camera samples per wavefront pass (the frame is rendered in additive passes)
@@ -177,7 +176,7 @@ void tuning_from_env(Tuning& t) {
     t.refill = env_int("TRB_REFILL", t.refill); t.occ = env_int("TRB_TRACE_OCC", t.occ); t.trace_grid = (unsigned)env_int("TRB_TRACE_GRID", (int)t.trace_grid);
     t.smem_stack = env_int("TRB_SMEM_STACK", t.smem_stack); t.sched = (uint32_t)env_int("TRB_TRACE_SCHED", (int)t.sched); t.quads = env_int("TRB_TRACE_QUADS", t.quads);
     t.film_v2 = env_int("TRB_FILM_V2", t.film_v2); t.sort = env_int("TRB_SORT", t.sort); t.sort_bits = env_int("TRB_SORT_BITS", t.sort_bits);
-    t.sort_min_round = env_int("TRB_SORT_MIN_ROUND", t.sort_min_round); t.mis_bounded = env_int("TRB_MIS_BOUNDED", t.mis_bounded); t.shade_split = env_int("TRB_SHADE_SPLIT", t.shade_split); t.graph = env_int("TRB_GRAPH", t.graph);
+    t.sort_min_round = env_int("TRB_SORT_MIN_ROUND", t.sort_min_round); t.shade_split = env_int("TRB_SHADE_SPLIT", t.shade_split); t.graph = env_int("TRB_GRAPH", t.graph);
     if (getenv("TRB_PASS_PATHS")) t.pass_paths = strtoull(getenv("TRB_PASS_PATHS"), nullptr, 0);
 }
 
@@ -269,8 +268,9 @@ trb_status validate(const trb_scene_desc* d) {
     if (d->film.frames == 0) return fail(TRB_INVALID_ARG, "film.frames must be >= 1");
     if (d->n_instances == 0) return fail(TRB_INVALID_ARG, "Aborting: the scene does not have any objects!"); // scene.rs:134
     if (d->n_cameras == 0) return fail(TRB_INVALID_ARG, "Error: A camera is required!");
-    if (d->integrator.type != TRB_INTEGRATOR_PATH) return fail(TRB_UNSUPPORTED, "only the pathtracer integrator is implemented");
-    if (d->integrator.max_depth > 57u) return fail(TRB_UNSUPPORTED, "max_depth > 57");
+    if (d->integrator.type > TRB_INTEGRATOR_NORMALS_DEBUG) return fail(TRB_INVALID_ARG, "Unrecognized integrator type"); // scene.rs:313
+    if (d->integrator.type == TRB_INTEGRATOR_PATH && d->integrator.max_depth > 57u) return fail(TRB_UNSUPPORTED, "max_depth > 57");
+    if (d->integrator.type == TRB_INTEGRATOR_WHITTED && d->integrator.max_depth > 24u) return fail(TRB_UNSUPPORTED, "whitted max_depth > 24 (device recursion stack)");
     if (!(d->film.filter_w > 0.0f && d->film.filter_h > 0.0f)) return fail(TRB_INVALID_ARG, "filter width/height must be positive");
     if (floorf(d->film.filter_w / 0.5f) > 8.0f || floorf(d->film.filter_h / 0.5f) > 8.0f) return fail(TRB_UNSUPPORTED, "filter wider than 4 pixels");
     bool light = false;
@@ -414,6 +414,24 @@ trb_status launch_wavefront(trb_scene* s, const trb::RenderParams& rp, uint32_t 
     const Tuning& tu = s->tune;
     trb::WfState wf = s->wf;
     wf.n_paths = (uint32_t)n_paths;
+    if (s->integrator.type != TRB_INTEGRATOR_PATH) { // Whitted / NormalsDebug: one thread per camera sample, then the same film kernel
+        const unsigned grid = (unsigned)std::min<size_t>((n_paths + 127) / 128, (size_t)s->sm_count * 8);
+        const bool anim = s->ds.has_anim != 0;
+        if (anim) { if (mode == 0) trb::k_simple_integrator<0, true><<<grid, 128, 0, st>>>(s->ds, rp, wf.rad, wf.n_paths, s->integrator.type, flags);
+                    else trb::k_simple_integrator<1, true><<<grid, 128, 0, st>>>(s->ds, rp, wf.rad, wf.n_paths, s->integrator.type, flags); }
+        else if (mode == 0) trb::k_simple_integrator<0, false><<<grid, 128, 0, st>>>(s->ds, rp, wf.rad, wf.n_paths, s->integrator.type, flags);
+        else trb::k_simple_integrator<1, false><<<grid, 128, 0, st>>>(s->ds, rp, wf.rad, wf.n_paths, s->integrator.type, flags);
+        g_launches++;
+        if (mode == 0) {
+            const int T = 9 + 2 * std::max(s->ds.fpw_x, s->ds.fpw_y);
+            const unsigned film_grid = std::min<unsigned>(rp.n_blocks, (unsigned)s->sm_count * 8);
+            if (tu.film_v2) trb::k_wf_film_v2<<<film_grid, trb::RENDER_THREADS, (size_t)4 * T * T * sizeof(float4), st>>>(s->ds, rp, wf);
+            else trb::k_wf_film<<<film_grid, trb::RENDER_THREADS, (size_t)T * T * sizeof(float4), st>>>(s->ds, rp, wf);
+            g_launches++;
+        }
+        CU(cudaGetLastError());
+        return TRB_OK;
+    }
     const bool stats = (flags & TRB_RENDER_STATS) != 0;
     const uint32_t rounds = s->integrator.max_depth + 2; // bounces 0..max_depth, plus the round that only resolves
     CU(cudaMemsetAsync(wf.counters, 0, 64 * trb::WF_CNT * sizeof(uint32_t), st));
@@ -427,8 +445,7 @@ trb_status launch_wavefront(trb_scene* s, const trb::RenderParams& rp, uint32_t 
     const unsigned tgrid = (unsigned)s->sm_count * tu.trace_grid;
     const uint32_t sched = tu.sched;   // 0 = flat state machine; else the quorum of the phased loop (see k_wf_trace)
     const bool quads = tu.quads != 0;  // DQuad two-level records (never in the STATS variants: their counters are the reference's)
-    // bit 8: MIS rays as bounded occlusion queries — not when the caller asked for the reference's traversal work (test counters, closest-hit shadows)
-    const uint32_t tflags = (flags & 0xffu) | ((tu.mis_bounded && !(flags & (TRB_RENDER_STATS | TRB_RENDER_REFERENCE_SHADOW))) ? 0x100u : 0u);
+    const uint32_t tflags = flags;
     for (uint32_t round = 0; round < rounds; ++round) {
         const uint32_t* q_sorted = nullptr;
         if (tu.sort && (int)round >= tu.sort_min_round) { // counting sort of this round's rays by (type, octant, origin cell): DESIGN.md "Ray sorting"
@@ -531,7 +548,7 @@ trb_status render_passes(trb_scene* s, trb::RenderParams rp, uint32_t flags, int
 }
 
 trb_status launch_render(trb_scene* s, const trb::RenderParams& rp, uint32_t flags, int mode, cudaStream_t st) {
-    if (!(flags & TRB_RENDER_MEGAKERNEL)) return render_passes(s, rp, flags, mode, st);
+    if (!(flags & TRB_RENDER_MEGAKERNEL) || s->integrator.type != TRB_INTEGRATOR_PATH) return render_passes(s, rp, flags, mode, st);
     const bool stats = (flags & TRB_RENDER_STATS) != 0;
     CU(cudaMemsetAsync(rp.work_counter, 0, sizeof(uint32_t), st));
     if (s->ds.has_anim) {
@@ -578,7 +595,6 @@ trb_status trb_scene_set_option(trb_scene* s, const char* name, long long value)
     else if (k == "sort.bits") t.sort_bits = (int)std::min<long long>(6, std::max<long long>(1, value));
     else if (k == "sort.min_round") t.sort_min_round = (int)value;
     else if (k == "shade.split") t.shade_split = (int)value;
-    else if (k == "trace.mis_bounded") t.mis_bounded = (int)value;
     else if (k == "pass.graph") t.graph = (int)value;
     else if (k == "pass.paths") { if (value < 64) return fail(TRB_INVALID_ARG, "pass.paths must be >= 64"); t.pass_paths = (uint64_t)value; }
     else return fail(TRB_INVALID_ARG, "unknown option: " + k);
@@ -620,6 +636,12 @@ trb_status trb_scene_create(const trb_scene_desc* d, int device, trb_scene** out
     std::unique_ptr<trb_scene> s(new trb_scene);
     s->device = device;
     tuning_from_env(s->tune);
+    if (d->integrator.type == TRB_INTEGRATOR_WHITTED) { // the reference's recursion is kept as device recursion: one frame per ray depth
+        size_t have = 0;
+        CU(cudaDeviceGetLimit(&have, cudaLimitStackSize));
+        const size_t need = 4096 + (size_t)2048 * (d->integrator.max_depth + 2);
+        if (have < need) CU(cudaDeviceSetLimit(cudaLimitStackSize, need));
+    }
     cudaDeviceProp prop;
     CU(cudaGetDeviceProperties(&prop, device));
     s->sm_count = prop.multiProcessorCount;

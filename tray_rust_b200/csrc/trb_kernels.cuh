@@ -259,7 +259,6 @@ struct TraceState {
     bool quads_ok;        // the kernel variant may use DQuad records at all
     const DTri* tris;
     uint32_t level_inst;  // instance whose mesh is being traversed, TRB_MISS at the top level
-    uint32_t skip_inst;   // instance the traversal ignores (bounded MIS query: the sampled light itself), TRB_MISS: none
     float tmin, tmax;
     float time;           // ray.time (only read for keyframed instances)
     int sp;
@@ -282,7 +281,7 @@ __device__ __forceinline__ void trace_init(const DScene& sc, TraceState& t, cons
     t.o = t.wo; t.d = t.wd; t.inv = t.winv;
     t.neg = neg_mask(t.d);
     trace_level(t, sc.tlas, sc.tlas_pairs, sc.tlas_quads);
-    t.tris = nullptr; t.level_inst = TRB_MISS; t.skip_inst = TRB_MISS;
+    t.tris = nullptr; t.level_inst = TRB_MISS;
     t.tmin = ray.tmin; t.tmax = ray.tmax;
     t.sp = 0; t.cur = ST_ROOT; t.found = false; t.any_hit = any_hit;
     t.h_inst = TRB_MISS; t.h_prim = 0; t.h_b1 = 0.0f; t.h_b2 = 0.0f;
@@ -542,7 +541,7 @@ __device__ __forceinline__ void step_other(const DScene& sc, TraceState& t, cons
         const DInstance& in = sc.instances[ii];
         if (STATS) cnt.inst++;
         const uint32_t kind = __ldg(&in.kind), shape = __ldg(&in.shape);
-        if (kind != TRB_INST_EMITTER_POINT && ii != t.skip_inst) {
+        if (kind != TRB_INST_EMITTER_POINT) {
             float m[16];
             instance_inv<ANIM>(sc, in, t.time, m);
             const f3 lo_ = xf_point(m, t.wo), ld_ = xf_vector(m, t.wd);
@@ -1111,14 +1110,13 @@ struct RayCounts { uint32_t primary, shadow, mis, cont; };
 struct DirectSetup {
     f3 a, b;             // contributions enabled by the shadow / MIS ray
     f3 shadow_d, mis_d;  // shadow segment p -> light sample (t in [0.001, 0.999]); MIS direction (t in [0.001, inf))
-    float mis_t;         // where the MIS ray meets the sampled light's own shape (Emitter::intersect's t), < 0: it cannot hit it
     bool has_shadow, has_mis;
 };
 
 template <bool ANIM>
 __device__ __noinline__ void direct_setup(const DScene& sc, const Mat& m, const Frame& fr, f3 wo, uint32_t li, float l0, float l1, float b0, float b1,
                                           float bc, float time, DirectSetup& ds) {
-    ds.a = splat(0.0f); ds.b = splat(0.0f); ds.shadow_d = splat(0.0f); ds.mis_d = splat(0.0f); ds.has_shadow = false; ds.has_mis = false; ds.mis_t = -1.0f;
+    ds.a = splat(0.0f); ds.b = splat(0.0f); ds.shadow_d = splat(0.0f); ds.mis_d = splat(0.0f); ds.has_shadow = false; ds.has_mis = false;
     const DInstance& light = sc.instances[li];
     const uint32_t kind = __ldg(&light.kind), shape = __ldg(&light.shape);
     const float p0 = __ldg(&light.p0), p1 = __ldg(&light.p1);
@@ -1177,17 +1175,6 @@ __device__ __noinline__ void direct_setup(const DScene& sc, const Mat& m, const 
             if (go) {
                 ds.has_mis = true; ds.mis_d = wi2; // Ray::segment(p, w_i, 0.001, inf)
                 ds.b = f * emission * fabsf(dot3(wi2, fr.n)) * w / pdf_bsdf; // used iff the ray hits this light from its front
-                // The only thing the integrator asks of this ray is "is its closest hit the sampled light?" (integrator/mod.rs:156-162).
-                // The light's own intersection is known here: the very expressions Emitter::intersect evaluates when the traversal
-                // reaches the light (emitter.rs:118-137: inv_mul_ray with the unnormalised direction, then the shape test on
-                // [0.001, inf)), so the trace kernel can answer with an occlusion query bounded by it (k_wf_trace, MIS_BOUNDED).
-                const f3 ol = xf_point(linv, p), dl = xf_vector(linv, wi2);
-                float tl = finf();
-                bool hl;
-                if (shape == TRB_SHAPE_SPHERE) hl = sphere_t(p0, ol, dl, 0.001f, tl);
-                else if (shape == TRB_SHAPE_DISK) hl = disk_t(p0, p1, ol, dl, 0.001f, tl);
-                else hl = rect_t(p0, p1, ol, dl, 0.001f, tl);
-                ds.mis_t = hl ? tl : -1.0f;
             }
         }
     }
@@ -1713,41 +1700,21 @@ __global__ void __launch_bounds__(128, MINB) k_wf_trace(const __grid_constant__ 
     bool have = false, exhausted = false;
     uint32_t p = 0;
     int type = 0;
-    // MIS rays as bounded occlusion queries (flags bit 8; never with the STATS / reference-shadow variants, whose counters are
-    // the reference's): mis_li = the sampled light (TRB_MISS: this lane's ray is an ordinary query), mis_tl = its distance.
-    const bool mis_bounded = PHASED && !STATS && (flags & 0x100u) != 0;
-    uint32_t mis_li = TRB_MISS;
-    float mis_tl = 0.0f;
     for (;;) {
         // ---- retire finished rays ----
         if (have && t.cur == ST_DONE) {
-            bool retry = false;
             if (type == 0) {
                 __stcs(&wf.cont[p], make_float4(t.wd.x, t.wd.y, t.wd.z, t.tmax));
                 __stcs(&wf.hit[p], make_uint4(t.found ? t.h_inst : TRB_MISS, t.h_prim, __float_as_uint(t.h_b1), __float_as_uint(t.h_b2)));
             } else if (type == 1) {
                 __stcs(&wf.shadow[p], make_float4(t.wd.x, t.wd.y, t.wd.z, __uint_as_float(t.found ? 1u : 0u)));
-            } else if (mis_li == TRB_MISS) { // MIS ray as a closest-hit query, like the reference (integrator/mod.rs:156)
+            } else {
                 __stcs(&wf.mis[p], make_float4(t.wd.x, t.wd.y, t.wd.z, t.tmax));
                 float4 a4 = __ldcs(&wf.a[p]);
                 a4.w = __uint_as_float(t.found ? t.h_inst : TRB_MISS);
                 __stcs(&wf.a[p], a4);
-            } else if (t.found && t.tmax == mis_tl) {
-                // Bounded query, and something else was accepted at EXACTLY the light's distance: which of the two the reference keeps
-                // depends on its traversal order ("last accepted wins", Q9), so this ray is traced again as the reference does.
-                Ray ray; ray.o = t.wo; ray.d = t.wd; ray.tmin = 0.001f; ray.tmax = finf();
-                trace_init(sc, t, ray, false, t.time, QUADS && PHASED);
-                if (PHASED) { stack.put(0, (unsigned long long)ST_DONE); t.sp = 1; }
-                mis_li = TRB_MISS;
-                retry = true;
-            } else {
-                // Bounded query: the light is the closest hit iff its own shape is hit (mis_tl >= 0) and nothing else is accepted on
-                // [0.001, mis_tl]. wf.mis[p].w already holds mis_tl, the t the traversal would have accepted the light with.
-                float4 a4 = __ldcs(&wf.a[p]);
-                a4.w = __uint_as_float((mis_tl >= 0.0f && !t.found) ? mis_li : TRB_MISS);
-                __stcs(&wf.a[p], a4);
             }
-            have = retry;
+            have = false;
         }
         // ---- refill idle lanes ----
         const unsigned idle = __ballot_sync(0xffffffffu, !have);
@@ -1769,17 +1736,8 @@ __global__ void __launch_bounds__(128, MINB) k_wf_trace(const __grid_constant__ 
                     Ray ray; ray.o = mk(o4.x, o4.y, o4.z); ray.d = mk(d4.x, d4.y, d4.z);
                     ray.tmin = (type == 0 && round == 0) ? 0.0f : 0.001f;
                     ray.tmax = type == 1 ? 0.999f : finf();
-                    bool any = type == 1 && shadow_any;
-                    mis_li = TRB_MISS;
-                    if (mis_bounded && type == 2) { // "is the closest hit the sampled light?" == "is anything but that light accepted before it?"
-                        mis_tl = d4.w;
-                        mis_li = __float_as_uint(__ldcs(&wf.b[p]).w);
-                        if (mis_tl >= 0.0f) { ray.tmax = mis_tl; any = true; }
-                    }
-                    trace_init(sc, t, ray, any, ANIM ? __ldg(&wf.thr[p].w) : 0.0f, QUADS && PHASED);
-                    t.skip_inst = mis_li;
+                    trace_init(sc, t, ray, type == 1 && shadow_any, ANIM ? __ldg(&wf.thr[p].w) : 0.0f, QUADS && PHASED);
                     if (PHASED) { stack.put(0, (unsigned long long)ST_DONE); t.sp = 1; } // bottom sentinel: popping it ends the ray
-                    if (mis_li != TRB_MISS && mis_tl < 0.0f) t.cur = ST_DONE;            // the ray misses the light's shape: nothing to trace
                     have = true;
                 }
             }
@@ -1898,7 +1856,7 @@ __global__ void __launch_bounds__(128, MINB) k_wf_shade(const __grid_constant__ 
                         wf.org[p] = make_float4(o.org.x, o.org.y, o.org.z, __uint_as_float(nf));
                         if (push_cont) wf.cont[p] = make_float4(o.next_d.x, o.next_d.y, o.next_d.z, finf());
                         if (push_shadow) wf.shadow[p] = make_float4(o.ds.shadow_d.x, o.ds.shadow_d.y, o.ds.shadow_d.z, 0.0f);
-                        if (push_mis) wf.mis[p] = make_float4(o.ds.mis_d.x, o.ds.mis_d.y, o.ds.mis_d.z, o.ds.mis_t);
+                        if (push_mis) wf.mis[p] = make_float4(o.ds.mis_d.x, o.ds.mis_d.y, o.ds.mis_d.z, finf());
                         wf.a[p] = make_float4(o.ds.a.x, o.ds.a.y, o.ds.a.z, __uint_as_float(TRB_MISS));
                         wf.b[p] = make_float4(o.ds.b.x, o.ds.b.y, o.ds.b.z, __uint_as_float(o.light));
                         wf.tprev[p] = make_float4(o.t_before.x, o.t_before.y, o.t_before.z, 0.0f);
@@ -1926,6 +1884,138 @@ __global__ void __launch_bounds__(128, MINB) k_wf_shade(const __grid_constant__ 
         wf_push(act_next, &cnt_n[WF_N_ACTIVE], push_active, p);
         wf_bounds_add(wf.bounds + (round + 1) * 8, push_active, new_org);
     }
+}
+
+// ------------------------------------------------------------------------------------------
+// The two other integrators of the reference: Whitted (integrator/whitted.rs:41-70 with
+// Integrator::specular_reflection / specular_transmission, integrator/mod.rs:41-103) and NormalsDebug
+// (integrator/normals_debug.rs:28-36). Not the performance path: one thread per camera sample, the recursion of the
+// reference kept as a recursion (post-order float sums must associate exactly like the Rust code), rays traced inline.
+// Sampler: every call of the reference asks for fresh 1-element arrays; node n of the recursion tree (root 1, reflection
+// child 2n, transmission child 2n + 1) draws dimension S_WHITTED + 8n + slot of the camera sample's stream (detmath contract).
+// ------------------------------------------------------------------------------------------
+constexpr uint32_t S_WHITTED = 4096;
+__device__ __forceinline__ void whitted_2d(uint32_t hs, uint32_t node, uint32_t slot, float& x, float& y) {
+    x = ld_vdc(0, scramble_of(rng_absorb(hs, S_WHITTED + 8 * node + slot)));
+    y = ld_sobol(0, scramble_of(rng_absorb(hs, S_WHITTED + 8 * node + slot + 1)));
+}
+__device__ __forceinline__ float whitted_1d(uint32_t hs, uint32_t node, uint32_t slot) { return ld_vdc(0, scramble_of(rng_absorb(hs, S_WHITTED + 8 * node + slot))); }
+
+// Light::sample_incident of Emitter (emitter.rs:160-190): radiance arriving at p, direction, pdf and the occlusion segment
+template <bool ANIM>
+__device__ __noinline__ void light_sample_incident(const DScene& sc, uint32_t li, f3 p, float u0, float u1, float time, f3& lrad, f3& wi, float& pdf, f3& seg) {
+    const DInstance& light = sc.instances[li];
+    const uint32_t kind = __ldg(&light.kind), shape = __ldg(&light.shape);
+    const float p0 = __ldg(&light.p0), p1 = __ldg(&light.p1);
+    f3 emission;
+    emission_at<ANIM>(sc, light, time, emission.x, emission.y, emission.z);
+    float linv[16], lmat[16];
+    instance_inv_mat<ANIM>(sc, light, time, linv, lmat);
+    if (kind == TRB_INST_EMITTER_POINT) { // emitter.rs:169-174
+        const f3 pos = xf_point(lmat, splat(0.0f));
+        wi = unit(pos - p);
+        lrad = emission / len2(pos - p);
+        pdf = 1.0f;
+        seg = pos - p;
+        return;
+    }
+    const f3 pl = xf_point(linv, p); // emitter.rs:175-185 (object-space pdf and direction, Q5)
+    f3 ps, nl;
+    shape_sample(shape, p0, p1, pl, u0, u1, ps, nl);
+    const f3 wil = unit(ps - pl);
+    pdf = shape_pdf(shape, p0, p1, pl, wil);
+    lrad = dot3(-wil, nl) > 0.0f ? emission : splat(0.0f);
+    const f3 pw = xf_point(lmat, ps);
+    wi = xf_vector(lmat, wil);
+    seg = pw - p;
+}
+
+template <bool ANIM>
+__device__ f3 whitted_illum(const DScene& sc, const Ray& ray, uint32_t depth, const HitRec& hit, uint32_t node, uint32_t hs, float time, bool ref_shadow,
+                            RayCounts& rc, Cnt& cnt, int* err) {
+    Surf s;
+    surface_at<ANIM>(sc, ray, hit, s, time);
+    const DInstance& in = sc.instances[hit.inst];
+    Mat m;
+    load_mat(sc.materials[__ldg(&in.material)], m);
+    Frame fr;
+    make_frame(s, fr);
+    const f3 wo = -ray.d;
+    float u0, u1;
+    whitted_2d(hs, node, 0, u0, u1);
+    f3 illum = splat(0.0f);
+    if (depth == 0 && __ldg(&in.kind) != TRB_INST_RECEIVER) { // whitted.rs:49-54
+        if (dot3(-ray.d, s.ng) > 0.0f) { f3 le; emission_at<ANIM>(sc, in, time, le.x, le.y, le.z); illum = illum + le; }
+        else illum = illum + splat(0.0f);
+    }
+    for (uint32_t k = 0; k < sc.n_lights; ++k) { // whitted.rs:56-62: every light, the same 2-D sample
+        f3 lrad, wi, seg; float pdf;
+        light_sample_incident<ANIM>(sc, __ldg(&sc.lights[k]), s.p, u0, u1, time, lrad, wi, pdf, seg);
+        const f3 f = bsdf_eval(sc, m, fr, wo, wi, BX_ALL);
+        if (!black(lrad) && !black(f)) {
+            Ray sr; sr.o = s.p; sr.d = seg; sr.tmin = 0.001f; sr.tmax = 0.999f;
+            HitRec sh;
+            rc.shadow++;
+            if (!scene_trace<true, ANIM>(sc, sr, sh, !ref_shadow, cnt, err, time)) illum = illum + f * lrad * fabsf(dot3(wi, fr.n)) / pdf;
+        }
+    }
+    if (depth < sc.max_depth) {
+#pragma unroll 1
+        for (int which = 0; which < 2; ++which) { // specular_reflection, then specular_transmission (integrator/mod.rs:41-103)
+            const uint32_t flags = BX_SPECULAR | (which == 0 ? BX_REFLECTION : BX_TRANSMISSION), slot = which == 0 ? 2u : 5u;
+            float v0, v1;
+            whitted_2d(hs, node, slot, v0, v1);
+            const float vc = whitted_1d(hs, node, slot + 2);
+            f3 f, wi; float pdf; uint32_t sampled;
+            bsdf_sample(sc, m, fr, wo, flags, v0, v1, vc, f, wi, pdf, sampled);
+            f3 out = splat(0.0f);
+            if (pdf > 0.0f && !black(f) && fabsf(dot3(wi, fr.n)) != 0.0f) {
+                Ray r2; r2.o = fr.p; r2.d = wi; r2.tmin = 0.001f; r2.tmax = finf();
+                HitRec h2;
+                rc.cont++;
+                if (scene_trace<true, ANIM>(sc, r2, h2, false, cnt, err, time)) {
+                    const f3 li = whitted_illum<ANIM>(sc, r2, depth + 1, h2, 2 * node + (uint32_t)which, hs, time, ref_shadow, rc, cnt, err);
+                    out = f * li * fabsf(dot3(wi, fr.n)) / pdf;
+                }
+            }
+            illum = illum + out;
+        }
+    }
+    return illum;
+}
+
+// One camera sample per thread for the Whitted / NormalsDebug integrators; radiance to wf.rad (MODE 0, then the film kernel) or to trb_sample records (MODE 1).
+template <int MODE, bool ANIM>
+__global__ void __launch_bounds__(128) k_simple_integrator(const __grid_constant__ DScene sc, const __grid_constant__ RenderParams rp, float4* rad, uint32_t n_paths,
+                                                           uint32_t integrator, uint32_t flags) {
+    RayCounts rc = {0, 0, 0, 0};
+    Cnt cnt = {0, 0, 0};
+    uint32_t mine = 0;
+    for (uint32_t p = blockIdx.x * blockDim.x + threadIdx.x; p < n_paths; p += gridDim.x * blockDim.x) {
+        const SampleId id = sample_id(sc, rp, p);
+        const PixelStreams ps = pixel_streams(rp.seed, id.pixel);
+        const uint32_t hpix = ps.hpix;
+        float sx, sy, tm;
+        sample_position(rp, ps, id, sx, sy, tm);
+        Ray ray;
+        const float time = camera_ray<ANIM>(sc, sx, sy, tm, ray);
+        mine++; rc.primary++;
+        HitRec hit;
+        f3 c = splat(0.0f);
+        if (scene_trace<true, ANIM>(sc, ray, hit, false, cnt, rp.error_flag, time)) {
+            if (integrator == TRB_INTEGRATOR_NORMALS_DEBUG) { // (bsdf.n + 1) / 2
+                Surf s;
+                surface_at<ANIM>(sc, ray, hit, s, time);
+                Frame fr;
+                make_frame(s, fr);
+                c = (fr.n + splat(1.0f)) / 2.0f;
+            } else c = whitted_illum<ANIM>(sc, ray, 0, hit, 1, rng_absorb(hpix, id.si), time, (flags & 4u) != 0, rc, cnt, rp.error_flag);
+        }
+        c = mk(clampf(c.x, 0.0f, 1.0f), clampf(c.y, 0.0f, 1.0f), clampf(c.z, 0.0f, 1.0f)); // multithreaded.rs:99 (Q12)
+        if (MODE == 0) rad[p] = make_float4(c.x, c.y, c.z, 1.0f);
+        else { trb_sample* out = reinterpret_cast<trb_sample*>(rp.samples_out) + p; out->x = sx; out->y = sy; out->r = c.x; out->g = c.y; out->b = c.z; }
+    }
+    if (rp.stats) flush_stats(rp.stats, rc, cnt, mine, true);
 }
 
 // ------------------------------------------------------------------------------------------
@@ -2050,7 +2140,7 @@ __global__ void __launch_bounds__(128, MINB) k_wf_shade_b(const __grid_constant_
             push_shadow = ds.has_shadow; push_mis = ds.has_mis;
             wf.org[p] = make_float4(fr.p.x, fr.p.y, fr.p.z, __uint_as_float((push_shadow ? WF_F_SHADOW : 0u) | (push_mis ? WF_F_MIS : 0u)));
             if (push_shadow) wf.shadow[p] = make_float4(ds.shadow_d.x, ds.shadow_d.y, ds.shadow_d.z, 0.0f);
-            if (push_mis) wf.mis[p] = make_float4(ds.mis_d.x, ds.mis_d.y, ds.mis_d.z, ds.mis_t);
+            if (push_mis) wf.mis[p] = make_float4(ds.mis_d.x, ds.mis_d.y, ds.mis_d.z, finf());
             wf.a[p] = make_float4(ds.a.x, ds.a.y, ds.a.z, __uint_as_float(TRB_MISS));
             wf.b[p] = make_float4(ds.b.x, ds.b.y, ds.b.z, __uint_as_float(light));
             wf.tprev[p] = make_float4(th4.x, th4.y, th4.z, 0.0f); // path_throughput multiplying this bounce's direct light

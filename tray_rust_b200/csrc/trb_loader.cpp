@@ -632,7 +632,14 @@ DescOwner* load_scene(const char* path, uint32_t w, uint32_t h, uint32_t spp) {
         o->desc.integrator.type = TRB_INTEGRATOR_PATH;
         o->desc.integrator.min_depth = (uint32_t)integ.expect("min_depth", "The integrator must specify the minimum ray depth").u64("min_depth must be a number");
         o->desc.integrator.max_depth = (uint32_t)integ.expect("max_depth", "The integrator must specify the maximum ray depth").u64("max_depth must be a number");
-    } else if (ity == "whitted" || ity == "normals_debug") die(TRB_UNSUPPORTED, "integrator '" + ity + "' is not implemented (DESIGN.md: next, row N4)");
+    } else if (ity == "whitted") { // scene.rs:305-309: Whitted::new(min_depth) — the recursion limit is read from the key "min_depth" (sic)
+        o->desc.integrator.type = TRB_INTEGRATOR_WHITTED;
+        o->desc.integrator.min_depth = 0;
+        o->desc.integrator.max_depth = (uint32_t)integ.expect("min_depth", "The integrator must specify the minimum ray depth").u64("min_depth must be a number");
+    } else if (ity == "normals_debug") { // scene.rs:310-311
+        o->desc.integrator.type = TRB_INTEGRATOR_NORMALS_DEBUG;
+        o->desc.integrator.min_depth = o->desc.integrator.max_depth = 0;
+    }
     else die(TRB_INVALID_ARG, "Unrecognized integrator type '" + ity + "'");
 
     if (root.get("textures")) die(TRB_UNSUPPORTED, "image textures are not implemented (DESIGN.md: next, row N3)");
