@@ -167,6 +167,7 @@ struct Tuning {
     int sort = 0;              // ray queues: 0 = path order; 1 / 2 = counting sort by (octant, origin cell) / (cell, octant) before each trace round (measured: -1.5 % trace time, +10 % step time on C4)
     int sort_bits = 5;         // bits per axis of the origin cell grid
     int sort_min_round = 1;    // first bounce round whose queues are sorted (round 0 = primary rays, already coherent)
+    int anim_table = 1;        // keyframed scenes: evaluate each keyframed instance's transform once per path (0 = per ray per instance, like the reference)
     int shade_split = 0;       // shading as three kernels (surface | direct light | BSDF sample) instead of one (measured equal on C4)
     int graph = 1;             // replay each pass as a CUDA graph when its shape repeats
     uint64_t pass_paths = 1ull << 24; // camera samples per wavefront pass (the frame is rendered in additive passes)
@@ -176,7 +177,7 @@ void tuning_from_env(Tuning& t) {
     t.refill = env_int("TRB_REFILL", t.refill); t.occ = env_int("TRB_TRACE_OCC", t.occ); t.trace_grid = (unsigned)env_int("TRB_TRACE_GRID", (int)t.trace_grid);
     t.smem_stack = env_int("TRB_SMEM_STACK", t.smem_stack); t.sched = (uint32_t)env_int("TRB_TRACE_SCHED", (int)t.sched); t.quads = env_int("TRB_TRACE_QUADS", t.quads);
     t.film_v2 = env_int("TRB_FILM_V2", t.film_v2); t.sort = env_int("TRB_SORT", t.sort); t.sort_bits = env_int("TRB_SORT_BITS", t.sort_bits);
-    t.sort_min_round = env_int("TRB_SORT_MIN_ROUND", t.sort_min_round); t.shade_split = env_int("TRB_SHADE_SPLIT", t.shade_split); t.graph = env_int("TRB_GRAPH", t.graph);
+    t.sort_min_round = env_int("TRB_SORT_MIN_ROUND", t.sort_min_round); t.shade_split = env_int("TRB_SHADE_SPLIT", t.shade_split); t.anim_table = env_int("TRB_ANIM_TABLE", t.anim_table); t.graph = env_int("TRB_GRAPH", t.graph);
     if (getenv("TRB_PASS_PATHS")) t.pass_paths = strtoull(getenv("TRB_PASS_PATHS"), nullptr, 0);
 }
 
@@ -205,6 +206,8 @@ struct trb_scene {
     std::vector<trb_material> materials;
     std::vector<HostMesh> meshes;
     uint32_t spp_pow2 = 1;
+    uint32_t n_anim = 0;                 // instances whose transform stack is keyframed (evaluated per path into WfState::xf_tab)
+    uint32_t* d_anim_instances = nullptr;
     // per-frame host state
     int active_camera = -1;
     float shutter_open = 0, shutter_close = 0;
@@ -395,6 +398,8 @@ trb_status ensure_wavefront(trb_scene* s, size_t n_paths) {
     grab(max_bins * sizeof(uint32_t), reinterpret_cast<void**>(&w.sort_hist));
     grab(max_bins * sizeof(uint32_t), reinterpret_cast<void**>(&w.sort_offs));
     grab(64 * 8 * sizeof(uint32_t), reinterpret_cast<void**>(&w.bounds));
+    w.xf_tab = nullptr; w.n_anim = s->n_anim;
+    if (s->n_anim) grab(cap * (size_t)s->n_anim * 32 * sizeof(float), reinterpret_cast<void**>(&w.xf_tab)); // per-path keyframed transforms (128 B per path and keyframed instance)
     if (err == cudaSuccess) err = cudaMemset(w.sort_hist, 0, max_bins * sizeof(uint32_t)); // invariant: all zero between sorts (the scan clears what it reads)
     if (err != cudaSuccess) {
         for (void* p : s->wf_allocs) cudaFree(p);
@@ -440,6 +445,11 @@ trb_status launch_wavefront(trb_scene* s, const trb::RenderParams& rp, uint32_t 
     if (anim) trb::k_wf_generate<true><<<gen_grid, 256, 0, st>>>(s->ds, rp, wf);
     else trb::k_wf_generate<false><<<gen_grid, 256, 0, st>>>(s->ds, rp, wf);
     g_launches++;
+    if (anim && wf.xf_tab && s->tune.anim_table) { // AnimatedTransform::transform(ray.time) once per (path, keyframed instance)
+        const size_t items = n_paths * wf.n_anim;
+        trb::k_wf_anim_table<<<(unsigned)std::min<size_t>((items + 127) / 128, (size_t)s->sm_count * 16), 128, 0, st>>>(s->ds, wf);
+        g_launches++;
+    } else wf.xf_tab = nullptr;
     const unsigned shade_grid = (unsigned)s->sm_count * 4;
     const int refill = tu.refill, occ = tu.occ, sst = tu.smem_stack;
     const unsigned tgrid = (unsigned)s->sm_count * tu.trace_grid;
@@ -595,6 +605,7 @@ trb_status trb_scene_set_option(trb_scene* s, const char* name, long long value)
     else if (k == "sort.bits") t.sort_bits = (int)std::min<long long>(6, std::max<long long>(1, value));
     else if (k == "sort.min_round") t.sort_min_round = (int)value;
     else if (k == "shade.split") t.shade_split = (int)value;
+    else if (k == "anim.table") t.anim_table = (int)value;
     else if (k == "pass.graph") t.graph = (int)value;
     else if (k == "pass.paths") { if (value < 64) return fail(TRB_INVALID_ARG, "pass.paths must be >= 64"); t.pass_paths = (uint64_t)value; }
     else return fail(TRB_INVALID_ARG, "unknown option: " + k);
@@ -753,6 +764,8 @@ trb_status trb_scene_create(const trb_scene_desc* d, int device, trb_scene** out
     CU(s->arena.upload(s->table, 256, &d_table));
 
     CU(s->arena.alloc(d->n_instances, &s->d_instances));
+    CU(s->arena.alloc(d->n_instances, &s->d_anim_instances));
+    for (const trb_instance& in : s->instances) if (!trbh::xf_is_static(s->splines.data(), in.spline_first, in.n_splines)) s->n_anim++;
     CU(s->arena.alloc(1, &s->d_counter));
     CU(s->arena.alloc(1, &s->d_error));
     CU(cudaMemset(s->d_error, 0, sizeof(int)));
@@ -851,6 +864,7 @@ trb_status trb_scene_update_frame(trb_scene* s, uint32_t frame, float start, flo
     s->world.resize(n);
     std::vector<Box3> bounds(n);
     std::vector<trb::DInstance> di(n);
+    std::vector<uint32_t> anim_list;
     for (size_t i = 0; i < n; ++i) {
         const trb_instance& in = s->instances[i];
         // world[i] = transform(shutter_open): exact for static instances; keyframed ones are re-evaluated per ray on the device
@@ -875,6 +889,7 @@ trb_status trb_scene_update_frame(trb_scene* s, uint32_t frame, float start, flo
         o.kind = in.kind; o.shape = in.shape; o.p0 = in.p0; o.p1 = in.p1; o.mesh = in.mesh; o.material = in.material;
         if (!trbh::xf_is_static(s->splines.data(), in.spline_first, in.n_splines)) {
             o.flags |= trb::DI_ANIM_XF; o.spline_first = in.spline_first; o.n_splines = in.n_splines; any_anim = true;
+            o.anim_slot = (uint32_t)anim_list.size(); anim_list.push_back((uint32_t)i);
         }
         if (in.kind != TRB_INST_RECEIVER) {
             for (int k = 0; k < 3; ++k) o.emission[k] = s->color_keys[in.emission_first].rgba[k];
@@ -901,6 +916,8 @@ trb_status trb_scene_update_frame(trb_scene* s, uint32_t frame, float start, flo
     if (!pn.empty()) CU(cudaMemcpy(s->d_tlas, pn.data(), pn.size() * sizeof(trb::DPair), cudaMemcpyHostToDevice));
     CU(cudaMemcpy(s->d_tlas_order, s->tlas_order.data(), n * sizeof(uint32_t), cudaMemcpyHostToDevice));
     CU(cudaMemcpy(s->d_instances, di.data(), n * sizeof(trb::DInstance), cudaMemcpyHostToDevice));
+    if (!anim_list.empty()) CU(cudaMemcpy(s->d_anim_instances, anim_list.data(), anim_list.size() * sizeof(uint32_t), cudaMemcpyHostToDevice));
+    s->ds.anim_instances = s->d_anim_instances; s->ds.n_anim_instances = (uint32_t)anim_list.size();
     if (!qn.empty()) CU(cudaMemcpy(s->d_tlas_quads, qn.data(), qn.size() * sizeof(trb::DQuad), cudaMemcpyHostToDevice));
     hdr.pairs = s->d_tlas; hdr.quads = s->d_tlas_quads;
     if (!s->d_tlas_hdr) CU(s->arena.alloc(1, &s->d_tlas_hdr));

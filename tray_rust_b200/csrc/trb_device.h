@@ -78,7 +78,8 @@ struct alignas(16) DInstance { // 176 B: the two matrices are read as 16-byte ve
     uint32_t flags;          // DI_ANIM_XF: transform depends on ray time; DI_ANIM_EMISSION: keyframed emission
     uint32_t spline_first, n_splines;     // AnimatedTransform (into DScene::splines) when DI_ANIM_XF
     uint32_t emission_first, n_emission;  // colour keys (into DScene::color_keys) when DI_ANIM_EMISSION
-    uint32_t pad[2];
+    uint32_t anim_slot;      // index among the keyframed instances (DScene::anim_instances) when DI_ANIM_XF
+    uint32_t pad;
 };
 constexpr uint32_t DI_ANIM_XF = 1u, DI_ANIM_EMISSION = 2u;
 static_assert(sizeof(DInstance) == 192, "DInstance must stay 16-byte sized");
@@ -132,6 +133,8 @@ struct DScene {
     const trb_color_key* color_keys;
     const trbh::Xf* level_xf; // per spline: Keyframe::transform of a one-control-point level (else unused)
     uint32_t has_anim; // any instance / camera / emission depends on time
+    const uint32_t* anim_instances; // instance indices with DI_ANIM_XF, in instance order
+    uint32_t n_anim_instances;
 };
 
 struct RenderParams {

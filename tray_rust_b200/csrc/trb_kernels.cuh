@@ -206,15 +206,28 @@ __device__ __noinline__ void eval_anim_xf(const DScene& sc, uint32_t first, uint
 #pragma unroll
     for (int i = 0; i < 16; ++i) { inv16[i] = x.inv.m[i]; if (mat16) mat16[i] = x.fwd.m[i]; }
 }
-template <bool ANIM>
-__device__ __forceinline__ void instance_inv(const DScene& sc, const DInstance& in, float time, float* inv16) {
-    if (ANIM && (__ldg(&in.flags) & DI_ANIM_XF)) eval_anim_xf(sc, __ldg(&in.spline_first), __ldg(&in.n_splines), time, inv16, nullptr);
-    else load_xf(in.inv, inv16);
+// Keyframed instances in the wavefront pipeline: AnimatedTransform::transform(time) depends only on (instance, ray.time) and every ray
+// of a path carries the camera ray's time, so k_wf_anim_table evaluates it ONCE per (path, keyframed instance) with the very same
+// function (bit-identical) into a per-path row: entry `anim_slot` = 16 floats inverse + 16 floats forward. `row` == nullptr
+// (megakernel, trb_intersect, Whitted): evaluate in place, per ray per instance, like the reference.
+__device__ __forceinline__ void load_row(const float* __restrict__ src, float* dst) { // plain loads: the table is written by an earlier kernel of the same pass
+    const float4* s4 = reinterpret_cast<const float4*>(src);
+#pragma unroll
+    for (int i = 0; i < 4; ++i) { const float4 v = s4[i]; dst[4 * i] = v.x; dst[4 * i + 1] = v.y; dst[4 * i + 2] = v.z; dst[4 * i + 3] = v.w; }
 }
 template <bool ANIM>
-__device__ __forceinline__ void instance_inv_mat(const DScene& sc, const DInstance& in, float time, float* inv16, float* mat16) {
-    if (ANIM && (__ldg(&in.flags) & DI_ANIM_XF)) eval_anim_xf(sc, __ldg(&in.spline_first), __ldg(&in.n_splines), time, inv16, mat16);
-    else { load_xf(in.inv, inv16); load_xf(in.mat, mat16); }
+__device__ __forceinline__ void instance_inv(const DScene& sc, const DInstance& in, float time, float* inv16, const float* row = nullptr) {
+    if (ANIM && (__ldg(&in.flags) & DI_ANIM_XF)) {
+        if (row) load_row(row + 32 * __ldg(&in.anim_slot), inv16);
+        else eval_anim_xf(sc, __ldg(&in.spline_first), __ldg(&in.n_splines), time, inv16, nullptr);
+    } else load_xf(in.inv, inv16);
+}
+template <bool ANIM>
+__device__ __forceinline__ void instance_inv_mat(const DScene& sc, const DInstance& in, float time, float* inv16, float* mat16, const float* row = nullptr) {
+    if (ANIM && (__ldg(&in.flags) & DI_ANIM_XF)) {
+        if (row) { const float* e = row + 32 * __ldg(&in.anim_slot); load_row(e, inv16); load_row(e + 16, mat16); }
+        else eval_anim_xf(sc, __ldg(&in.spline_first), __ldg(&in.n_splines), time, inv16, mat16);
+    } else { load_xf(in.inv, inv16); load_xf(in.mat, mat16); }
 }
 // AnimatedColor::color(time) of an emitter (animated_color.rs:52-78)
 template <bool ANIM>
@@ -261,6 +274,7 @@ struct TraceState {
     uint32_t level_inst;  // instance whose mesh is being traversed, TRB_MISS at the top level
     float tmin, tmax;
     float time;           // ray.time (only read for keyframed instances)
+    const float* xf_row;  // this path's row of evaluated keyframed transforms (wavefront), nullptr: evaluate per instance test
     int sp;
     uint32_t cur;
     bool found, any_hit;
@@ -275,7 +289,7 @@ __device__ __forceinline__ void trace_level(TraceState& t, const DBvh* bvh, cons
     t.pairs = t.quad ? reinterpret_cast<const DPair*>(quads) : pairs;
 }
 __device__ __forceinline__ void trace_init(const DScene& sc, TraceState& t, const Ray& ray, bool any_hit, float time, bool quads_ok = false) {
-    t.time = time; t.quads_ok = quads_ok;
+    t.time = time; t.quads_ok = quads_ok; t.xf_row = nullptr;
     t.wo = ray.o; t.wd = ray.d;
     t.winv = mk(1.0f / ray.d.x, 1.0f / ray.d.y, 1.0f / ray.d.z);
     t.o = t.wo; t.d = t.wd; t.inv = t.winv;
@@ -390,7 +404,7 @@ __device__ __forceinline__ void trace_step(const DScene& sc, TraceState& t, cons
         bool enter = false;
         if (kind != TRB_INST_EMITTER_POINT) { // point lights never intersect (emitter.rs:119-120)
             float m[16];
-            instance_inv<ANIM>(sc, in, t.time, m);
+            instance_inv<ANIM>(sc, in, t.time, m, t.xf_row);
             const f3 lo_ = xf_point(m, t.wo), ld_ = xf_vector(m, t.wd); // inv_mul_ray: direction not renormalised
             if (shape == TRB_SHAPE_MESH) {
                 const DMesh& me = sc.meshes[__ldg(&in.mesh)];
@@ -543,7 +557,7 @@ __device__ __forceinline__ void step_other(const DScene& sc, TraceState& t, cons
         const uint32_t kind = __ldg(&in.kind), shape = __ldg(&in.shape);
         if (kind != TRB_INST_EMITTER_POINT) {
             float m[16];
-            instance_inv<ANIM>(sc, in, t.time, m);
+            instance_inv<ANIM>(sc, in, t.time, m, t.xf_row);
             const f3 lo_ = xf_point(m, t.wo), ld_ = xf_vector(m, t.wd);
             if (shape == TRB_SHAPE_MESH) {
                 const DMesh& me = sc.meshes[__ldg(&in.mesh)];
@@ -592,10 +606,10 @@ __device__ __noinline__ bool scene_trace(const DScene& sc, Ray& ray, HitRec& hit
 struct Surf { f3 p, n, ng, dp_du; };
 
 template <bool ANIM>
-__device__ __forceinline__ void surface_at(const DScene& sc, const Ray& ray, const HitRec& hit, Surf& s, float time) {
+__device__ __forceinline__ void surface_at(const DScene& sc, const Ray& ray, const HitRec& hit, Surf& s, float time, const float* xf_row = nullptr) {
     const DInstance& in = sc.instances[hit.inst];
     float m[16], w[16];
-    instance_inv_mat<ANIM>(sc, in, time, m, w);
+    instance_inv_mat<ANIM>(sc, in, time, m, w, xf_row);
     const f3 o = xf_point(m, ray.o), d = xf_vector(m, ray.d);
     const f3 p = o + d * hit.t; // ray.at(t) of the local ray
     const uint32_t shape = __ldg(&in.shape);
@@ -1115,7 +1129,7 @@ struct DirectSetup {
 
 template <bool ANIM>
 __device__ __noinline__ void direct_setup(const DScene& sc, const Mat& m, const Frame& fr, f3 wo, uint32_t li, float l0, float l1, float b0, float b1,
-                                          float bc, float time, DirectSetup& ds) {
+                                          float bc, float time, DirectSetup& ds, const float* xf_row = nullptr) {
     ds.a = splat(0.0f); ds.b = splat(0.0f); ds.shadow_d = splat(0.0f); ds.mis_d = splat(0.0f); ds.has_shadow = false; ds.has_mis = false;
     const DInstance& light = sc.instances[li];
     const uint32_t kind = __ldg(&light.kind), shape = __ldg(&light.shape);
@@ -1124,7 +1138,7 @@ __device__ __noinline__ void direct_setup(const DScene& sc, const Mat& m, const 
     emission_at<ANIM>(sc, light, time, emission.x, emission.y, emission.z); // self.emission.color(time)
     const bool delta = kind == TRB_INST_EMITTER_POINT;
     float linv[16], lmat[16];
-    instance_inv_mat<ANIM>(sc, light, time, linv, lmat); // self.transform.transform(time)
+    instance_inv_mat<ANIM>(sc, light, time, linv, lmat, xf_row); // self.transform.transform(time)
     const f3 p = fr.p;
     // --- light.sample_incident(&bsdf.p, ...) ---
     f3 lrad, wi, seg;
@@ -1181,7 +1195,7 @@ __device__ __noinline__ void direct_setup(const DScene& sc, const Mat& m, const 
 }
 // Does the MIS ray's hit see the light's emitting side? e.radiance(&-w_i, &h.dg.p, &h.dg.ng) (integrator/mod.rs:156-162)
 template <bool ANIM>
-__device__ __forceinline__ bool mis_sees_light(const DScene& sc, f3 org, f3 mis_d, uint32_t li, uint32_t hit_inst, float hit_t, float time) {
+__device__ __forceinline__ bool mis_sees_light(const DScene& sc, f3 org, f3 mis_d, uint32_t li, uint32_t hit_inst, float hit_t, float time, const float* xf_row = nullptr) {
     if (hit_inst != li) return false;
     const DInstance& light = sc.instances[li];
     f3 le;
@@ -1190,7 +1204,7 @@ __device__ __forceinline__ bool mis_sees_light(const DScene& sc, f3 org, f3 mis_
     Ray mr; mr.o = org; mr.d = mis_d; mr.tmin = 0.001f; mr.tmax = hit_t;
     HitRec mh; mh.t = hit_t; mh.inst = hit_inst; mh.prim = 0; mh.b1 = 0.0f; mh.b2 = 0.0f; // area lights are analytic shapes
     Surf s;
-    surface_at<ANIM>(sc, mr, mh, s, time);
+    surface_at<ANIM>(sc, mr, mh, s, time, xf_row);
     return dot3(-mis_d, s.ng) > 0.0f;
 }
 __device__ __forceinline__ f3 direct_resolve(f3 a, f3 b, bool occluded, bool mis_ok) {
@@ -1233,7 +1247,7 @@ __device__ __forceinline__ void bounce_emission(const DScene& sc, uint32_t hit_i
 }
 template <bool ANIM>
 __device__ __forceinline__ void bounce_direct(const DScene& sc, const Mat& m, const Frame& fr, f3 wo, uint32_t bounce, uint32_t hsample, float time, DirectSetup& ds,
-                                              uint32_t& light) {
+                                              uint32_t& light, const float* xf_row = nullptr) {
     PathRng rng; rng.h = hsample; rng.len = sc.max_depth + 1;
     float l0, l1, b0, b1;
     rng.two_d(bounce, S_L0, S_L1, S_L_PERM, l0, l1);
@@ -1242,7 +1256,7 @@ __device__ __forceinline__ void bounce_direct(const DScene& sc, const Mat& m, co
     uint32_t l = f2u(lc * (float)sc.n_lights); // sample_one_light (integrator/mod.rs:108-110), no xN (Q2)
     if (l > sc.n_lights - 1) l = sc.n_lights - 1;
     light = __ldg(&sc.lights[l]);
-    direct_setup<ANIM>(sc, m, fr, wo, light, l0, l1, b0, b1, bc, time, ds);
+    direct_setup<ANIM>(sc, m, fr, wo, light, l0, l1, b0, b1, bc, time, ds, xf_row);
 }
 struct ScatterOut { f3 throughput, next_d; bool specular, terminate; };
 __device__ __forceinline__ void bounce_scatter(const DScene& sc, const Mat& m, const Frame& fr, f3 wo, uint32_t bounce, uint32_t hsample, f3 throughput_in, ScatterOut& o) {
@@ -1269,14 +1283,14 @@ __device__ __forceinline__ void bounce_scatter(const DScene& sc, const Mat& m, c
 }
 template <bool ANIM>
 __device__ __forceinline__ void shade_bounce(const DScene& sc, const Surf& s, uint32_t hit_inst, f3 ray_d, f3 first_ng, uint32_t bounce, bool prev_specular,
-                                             uint32_t hsample, f3 throughput_in, float time, f3& illum, BounceOut& o) {
+                                             uint32_t hsample, f3 throughput_in, float time, f3& illum, BounceOut& o, const float* xf_row = nullptr) {
     bounce_emission<ANIM>(sc, hit_inst, ray_d, first_ng, bounce, prev_specular, throughput_in, time, illum);
     Mat m;
     load_mat(sc.materials[__ldg(&sc.instances[hit_inst].material)], m);
     Frame fr;
     make_frame(s, fr);
     const f3 wo = -ray_d;
-    bounce_direct<ANIM>(sc, m, fr, wo, bounce, hsample, time, o.ds, o.light);
+    bounce_direct<ANIM>(sc, m, fr, wo, bounce, hsample, time, o.ds, o.light, xf_row);
     o.t_before = throughput_in;
     o.org = fr.p;
     ScatterOut so;
@@ -1522,6 +1536,9 @@ struct WfState {
     float4* f_t;         // tangent
     float4* f_b;         // bitangent
     uint32_t* q_mid;     // paths to shade this round (survived resolve / termination / miss)
+    // keyframed scenes: per path, the evaluated transforms of every keyframed instance (32 floats each: inverse, forward); nullptr: none
+    float* xf_tab;
+    uint32_t n_anim;
     uint32_t* bounds;    // per round 8 words: min xyz, pad, max xyz, pad of the ray origins queued for that round (order-preserving uint encoding)
 };
 constexpr uint32_t WF_PATH_MASK = 0x3fffffffu;
@@ -1557,6 +1574,26 @@ __device__ __forceinline__ void wf_push(uint32_t* q, uint32_t* counter, bool wan
     if (lane == leader) base = atomicAdd(counter, (uint32_t)__popc(mask));
     base = __shfl_sync(0xffffffffu, base, leader);
     if (want) q[base + __popc(mask & ((1u << lane) - 1u))] = value;
+}
+
+template <bool ANIM>
+__device__ __forceinline__ const float* wf_xf_row(const WfState& wf, uint32_t p) {
+    return (ANIM && wf.xf_tab) ? wf.xf_tab + (size_t)p * wf.n_anim * 32 : nullptr;
+}
+// AnimatedTransform::transform(ray.time) once per (path, keyframed instance) — see instance_inv(). One thread per table entry.
+__global__ void __launch_bounds__(128) k_wf_anim_table(const __grid_constant__ DScene sc, const __grid_constant__ WfState wf) {
+    const size_t n = (size_t)wf.n_paths * wf.n_anim;
+    for (size_t i = blockIdx.x * (size_t)blockDim.x + threadIdx.x; i < n; i += (size_t)gridDim.x * blockDim.x) {
+        const uint32_t p = (uint32_t)(i / wf.n_anim), k = (uint32_t)(i % wf.n_anim);
+        const DInstance& in = sc.instances[__ldg(&sc.anim_instances[k])];
+        float inv[16], mat[16];
+        eval_anim_xf(sc, __ldg(&in.spline_first), __ldg(&in.n_splines), wf.thr[p].w, inv, mat);
+        float4* dst = reinterpret_cast<float4*>(wf.xf_tab + i * 32);
+#pragma unroll
+        for (int q = 0; q < 4; ++q) dst[q] = make_float4(inv[4 * q], inv[4 * q + 1], inv[4 * q + 2], inv[4 * q + 3]);
+#pragma unroll
+        for (int q = 0; q < 4; ++q) dst[4 + q] = make_float4(mat[4 * q], mat[4 * q + 1], mat[4 * q + 2], mat[4 * q + 3]);
+    }
 }
 
 // order-preserving float <-> uint (for atomicMin / atomicMax over floats of either sign)
@@ -1737,6 +1774,7 @@ __global__ void __launch_bounds__(128, MINB) k_wf_trace(const __grid_constant__ 
                     ray.tmin = (type == 0 && round == 0) ? 0.0f : 0.001f;
                     ray.tmax = type == 1 ? 0.999f : finf();
                     trace_init(sc, t, ray, type == 1 && shadow_any, ANIM ? __ldg(&wf.thr[p].w) : 0.0f, QUADS && PHASED);
+                    t.xf_row = wf_xf_row<ANIM>(wf, p);
                     if (PHASED) { stack.put(0, (unsigned long long)ST_DONE); t.sp = 1; } // bottom sentinel: popping it ends the ray
                     have = true;
                 }
@@ -1820,13 +1858,14 @@ __global__ void __launch_bounds__(128, MINB) k_wf_shade(const __grid_constant__ 
             bool done = false;
             const float4 th4 = wf.thr[p];
             const float time = th4.w;
+            const float* xf_row = wf_xf_row<ANIM>(wf, p);
             if (round > 0) { // fold in the direct light of the previous bounce (estimate_direct's two ray results)
                 const float4 a4 = wf.a[p], b4 = wf.b[p], t4 = wf.tprev[p];
                 bool occluded = false, mis_ok = false;
                 if (fl & WF_F_SHADOW) occluded = __float_as_uint(wf.shadow[p].w) != 0u;
                 if (fl & WF_F_MIS) {
                     const float4 m4 = wf.mis[p];
-                    mis_ok = mis_sees_light<ANIM>(sc, org, mk(m4.x, m4.y, m4.z), __float_as_uint(b4.w), __float_as_uint(a4.w), m4.w, time);
+                    mis_ok = mis_sees_light<ANIM>(sc, org, mk(m4.x, m4.y, m4.z), __float_as_uint(b4.w), __float_as_uint(a4.w), m4.w, time, xf_row);
                 }
                 illum = illum + mk(t4.x, t4.y, t4.z) * direct_resolve(mk(a4.x, a4.y, a4.z), mk(b4.x, b4.y, b4.z), occluded, mis_ok);
                 done = (fl & WF_F_TERMINATE) != 0;
@@ -1839,14 +1878,14 @@ __global__ void __launch_bounds__(128, MINB) k_wf_shade(const __grid_constant__ 
                     Ray ray; ray.o = org; ray.d = mk(c4.x, c4.y, c4.z); ray.tmin = 0.0f; ray.tmax = c4.w;
                     HitRec h; h.t = c4.w; h.inst = h4.x; h.prim = h4.y; h.b1 = __uint_as_float(h4.z); h.b2 = __uint_as_float(h4.w);
                     Surf s;
-                    surface_at<ANIM>(sc, ray, h, s, time);
+                    surface_at<ANIM>(sc, ray, h, s, time, xf_row);
                     f3 first_ng;
                     if (round == 0) { first_ng = s.ng; wf.ng[p] = make_float4(s.ng.x, s.ng.y, s.ng.z, 0.0f); }
                     else { const float4 n4 = wf.ng[p]; first_ng = mk(n4.x, n4.y, n4.z); }
                     const SampleId id = sample_id(sc, rp, p);
                     const uint32_t hs = rng_absorb(rng_absorb(rng_seed(rp.seed), id.pixel), id.si);
                     BounceOut o;
-                    shade_bounce<ANIM>(sc, s, h.inst, ray.d, first_ng, round, (fl & WF_F_SPECULAR) != 0, hs, mk(th4.x, th4.y, th4.z), time, illum, o);
+                    shade_bounce<ANIM>(sc, s, h.inst, ray.d, first_ng, round, (fl & WF_F_SPECULAR) != 0, hs, mk(th4.x, th4.y, th4.z), time, illum, o, xf_row);
                     const uint32_t nf = (o.specular ? WF_F_SPECULAR : 0u) | (o.terminate ? WF_F_TERMINATE : 0u) | (o.ds.has_shadow ? WF_F_SHADOW : 0u) |
                                         (o.ds.has_mis ? WF_F_MIS : 0u);
                     push_cont = !o.terminate; push_shadow = o.ds.has_shadow; push_mis = o.ds.has_mis;
@@ -2070,13 +2109,14 @@ __global__ void __launch_bounds__(128, MINB) k_wf_shade_a(const __grid_constant_
             bool done = false;
             const float4 th4 = wf.thr[p];
             const float time = th4.w;
+            const float* xf_row = wf_xf_row<ANIM>(wf, p);
             if (round > 0) { // fold in the direct light of the previous bounce (estimate_direct's two ray results)
                 const float4 a4 = wf.a[p], b4 = wf.b[p], t4 = wf.tprev[p];
                 bool occluded = false, mis_ok = false;
                 if (fl & WF_F_SHADOW) occluded = __float_as_uint(wf.shadow[p].w) != 0u;
                 if (fl & WF_F_MIS) {
                     const float4 m4 = wf.mis[p];
-                    mis_ok = mis_sees_light<ANIM>(sc, org, mk(m4.x, m4.y, m4.z), __float_as_uint(b4.w), __float_as_uint(a4.w), m4.w, time);
+                    mis_ok = mis_sees_light<ANIM>(sc, org, mk(m4.x, m4.y, m4.z), __float_as_uint(b4.w), __float_as_uint(a4.w), m4.w, time, xf_row);
                 }
                 illum = illum + mk(t4.x, t4.y, t4.z) * direct_resolve(mk(a4.x, a4.y, a4.z), mk(b4.x, b4.y, b4.z), occluded, mis_ok);
                 done = (fl & WF_F_TERMINATE) != 0;
@@ -2089,7 +2129,7 @@ __global__ void __launch_bounds__(128, MINB) k_wf_shade_a(const __grid_constant_
                     Ray ray; ray.o = org; ray.d = mk(c4.x, c4.y, c4.z); ray.tmin = 0.0f; ray.tmax = c4.w;
                     HitRec h; h.t = c4.w; h.inst = h4.x; h.prim = h4.y; h.b1 = __uint_as_float(h4.z); h.b2 = __uint_as_float(h4.w);
                     Surf s;
-                    surface_at<ANIM>(sc, ray, h, s, time);
+                    surface_at<ANIM>(sc, ray, h, s, time, xf_row);
                     f3 first_ng;
                     if (round == 0) { first_ng = s.ng; wf.ng[p] = make_float4(s.ng.x, s.ng.y, s.ng.z, 0.0f); }
                     else { const float4 n4 = wf.ng[p]; first_ng = mk(n4.x, n4.y, n4.z); }
@@ -2136,7 +2176,7 @@ __global__ void __launch_bounds__(128, MINB) k_wf_shade_b(const __grid_constant_
             const SampleId id = sample_id(sc, rp, p);
             const uint32_t hs = rng_absorb(rng_absorb(rng_seed(rp.seed), id.pixel), id.si);
             DirectSetup ds; uint32_t light;
-            bounce_direct<ANIM>(sc, m, fr, wo, round, hs, th4.w, ds, light);
+            bounce_direct<ANIM>(sc, m, fr, wo, round, hs, th4.w, ds, light, wf_xf_row<ANIM>(wf, p));
             push_shadow = ds.has_shadow; push_mis = ds.has_mis;
             wf.org[p] = make_float4(fr.p.x, fr.p.y, fr.p.z, __uint_as_float((push_shadow ? WF_F_SHADOW : 0u) | (push_mis ? WF_F_MIS : 0u)));
             if (push_shadow) wf.shadow[p] = make_float4(ds.shadow_d.x, ds.shadow_d.y, ds.shadow_d.z, 0.0f);
