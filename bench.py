@@ -23,6 +23,7 @@ steps ends with that one reduce. Per-GPU work is therefore constant in N: "scali
 """
 import argparse
 import json
+import math
 import os
 import subprocess
 import sys
@@ -146,9 +147,12 @@ def cpu_arm(a, desc, seconds, reps):
     small sample, then `reps` all-core repetitions of a bounded sample of the same workload; min / median / max reported so
     that a noisy or oversubscribed box is visible in the line."""
     from tray_rust_b200 import _ffi as F
+    host = host_info()                 # before OpenMP pins this thread
     pin_openmp()
     from oracle import pyoracle as O   # the CPU arm: the one place besides tests/smoke that may execute oracle/
     threads = host_threads()
+    if host.get("cgroup_cpu_quota_cores"):   # a container quota below the visible CPUs: more threads than that only adds throttling
+        threads = max(1, min(threads, int(math.ceil(host["cgroup_cpu_quota_cores"]))))
     o = O.OracleScene(desc, "fast", baseline=True)
     o.update_frame(0, 0.0, 0.0)
     nb = o.n_blocks()
@@ -179,7 +183,7 @@ def cpu_arm(a, desc, seconds, reps):
             "all_core": {"min": vals_sorted[0], "median": float(np.median(vals)), "max": vals_sorted[-1], "reps": vals},
             "single_thread": {"value": single, "sample": "%d blocks x 1 spp, %.1f s" % (n1, dt1)},
             "parallel_speedup": float(np.median(vals)) / single if single > 0 else None,
-            "host": host_info(), "samples_per_s": samples / wall, "rays": rays, "wall_s": wall}
+            "host": host, "samples_per_s": samples / wall, "rays": rays, "wall_s": wall}
 
 
 def run_reference(a):

@@ -131,125 +131,147 @@ inline Box3 arvo_bounds(const Mat4& m, const Box3& b) {
 }
 
 // ---------------------------------------------------------------------------------------------
-// SAH BVH2 in the reference's exact topology and order. Emits the flattened pre-order array directly
-// (the reference builds a pointer tree and flattens it depth-first; both visit nodes in the same order).
+// SAH BVH2 in the reference's exact topology and order (bvh.rs:139-267, partition.rs:9-38), emitting the flattened
+// pre-order array directly (the reference builds a pointer tree and flattens it depth-first; both visit nodes in the same
+// order). ONE implementation for the host (per-mesh BLAS at load time, TLAS when the device path is off) and the device
+// (TLAS per update_frame, k_tlas_build): iterative with an explicit task stack — device recursion would need a stack
+// reservation for every resident thread — on caller-provided arrays.
 // ---------------------------------------------------------------------------------------------
-struct BvhBuilder {
+TRB_HD inline Box3 box_empty_hd() { Box3 b; for (int i = 0; i < 3; ++i) { b.lo[i] = INFINITY; b.hi[i] = -INFINITY; } return b; }
+TRB_HD inline void box_grow_hd(Box3& b, const Box3& o) { for (int i = 0; i < 3; ++i) { b.lo[i] = fminf(b.lo[i], o.lo[i]); b.hi[i] = fmaxf(b.hi[i], o.hi[i]); } }
+TRB_HD inline float box_area_hd(const Box3& b) { // bbox.rs:66-69
+    const float dx = b.hi[0] - b.lo[0], dy = b.hi[1] - b.lo[1], dz = b.hi[2] - b.lo[2];
+    return 2.0f * (dx * dy + dx * dz + dy * dz);
+}
+TRB_HD inline uint32_t sat_u32_hd(float f) { if (!(f > 0.0f)) return 0; if (f >= 4294967296.0f) return 0xffffffffu; return (uint32_t)f; }
+
+struct BvhBuildArrays {
+    const Box3* boxes; uint32_t n; uint32_t max_geom;
+    float* cx; float* cy; float* cz;   // scratch [n]: centroids = lo*0.5 + hi*0.5 (bbox.rs:58-61 via linalg::lerp)
+    uint32_t* idx;                     // scratch [n]
+    uint32_t* task;                    // scratch [3 * n]: pending right subtrees (begin, end, parent)
+    trb_bvh_node* nodes;               // out [2 * n]
+    uint32_t* order;                   // out [n]: ordered_geom
+    uint32_t n_nodes, n_order;
+};
+
+TRB_HD inline void bvh_build_arrays(BvhBuildArrays& B) {
+    const Box3* boxes = B.boxes;
+    uint32_t* idx = B.idx;
+    for (uint32_t i = 0; i < B.n; ++i) {
+        B.cx[i] = boxes[i].lo[0] * (1.0f - 0.5f) + boxes[i].hi[0] * 0.5f;
+        B.cy[i] = boxes[i].lo[1] * (1.0f - 0.5f) + boxes[i].hi[1] * 0.5f;
+        B.cz[i] = boxes[i].lo[2] * (1.0f - 0.5f) + boxes[i].hi[2] * 0.5f;
+        idx[i] = i;
+    }
+    B.n_nodes = 0; B.n_order = 0;
+    uint32_t n_task = 0;
+    uint32_t begin = 0, end = B.n, parent = 0xffffffffu; // the range being emitted; parent != ~0: this node is that interior's second child
+    for (;;) {
+        // ---- BVH::build (bvh.rs:139-232) over idx[begin, end): emit one node, descend into its first child or pop a pending second child
+        const uint32_t n = end - begin;
+        const uint32_t me = B.n_nodes++;
+        if (parent != 0xffffffffu) B.nodes[parent].a = me; // second_child index (bvh.rs:259-262)
+        Box3 bounds = box_empty_hd();
+        for (uint32_t i = begin; i < end; ++i) box_grow_hd(bounds, boxes[idx[i]]);
+        bool is_leaf = false;
+        int axis = 0;
+        uint32_t mid = begin + n / 2;
+        if (n == 1) is_leaf = true;
+        else {
+            Box3 cb = box_empty_hd();
+            for (uint32_t i = begin; i < end; ++i) {
+                const uint32_t g = idx[i];
+                cb.lo[0] = fminf(cb.lo[0], B.cx[g]); cb.hi[0] = fmaxf(cb.hi[0], B.cx[g]);
+                cb.lo[1] = fminf(cb.lo[1], B.cy[g]); cb.hi[1] = fmaxf(cb.hi[1], B.cy[g]);
+                cb.lo[2] = fminf(cb.lo[2], B.cz[g]); cb.hi[2] = fmaxf(cb.hi[2], B.cz[g]);
+            }
+            { // bbox.rs:47-56 max_extent
+                const float dx = cb.hi[0] - cb.lo[0], dy = cb.hi[1] - cb.lo[1], dz = cb.hi[2] - cb.lo[2];
+                axis = (dx > dy && dx > dz) ? 0 : (dy > dz ? 1 : 2);
+            }
+            const float* cen = axis == 0 ? B.cx : (axis == 1 ? B.cy : B.cz);
+            if (fabsf(cb.hi[axis] - cb.lo[axis]) < kEps) { // coincident centroids (bvh.rs:156-166)
+                if (n < B.max_geom) is_leaf = true;
+            } else if (n < 5) { // stable sort by centroid, median split (bvh.rs:169-178); insertion sort == stable
+                for (uint32_t i = begin + 1; i < end; ++i) {
+                    const uint32_t g = idx[i];
+                    const float key = cen[g];
+                    uint32_t j = i;
+                    while (j > begin && cen[idx[j - 1]] > key) { idx[j] = idx[j - 1]; --j; }
+                    idx[j] = g;
+                }
+            } else {
+                const float cmin = cb.lo[axis], cmax = cb.hi[axis];
+                uint32_t count[12];
+                Box3 bb[12];
+                for (int k = 0; k < 12; ++k) { count[k] = 0; bb[k] = box_empty_hd(); }
+                for (uint32_t i = begin; i < end; ++i) {
+                    uint32_t k = sat_u32_hd((cen[idx[i]] - cmin) / (cmax - cmin) * 12.0f);
+                    if (k >= 12) k = 11;
+                    count[k]++;
+                    box_grow_hd(bb[k], boxes[idx[i]]);
+                }
+                float best_cost = INFINITY; int best = 0;
+                const float total_area = box_area_hd(bounds);
+                for (int sp = 0; sp < 11; ++sp) { // cost of splitting after bucket sp (bvh.rs:191-206)
+                    Box3 lb = box_empty_hd(), rb = box_empty_hd();
+                    uint32_t lc = 0, rc = 0;
+                    for (int k = 0; k <= sp; ++k) { box_grow_hd(lb, bb[k]); lc += count[k]; }
+                    for (int k = sp + 1; k < 12; ++k) { box_grow_hd(rb, bb[k]); rc += count[k]; }
+                    const float cost = 0.125f + ((float)lc * box_area_hd(lb) + (float)rc * box_area_hd(rb)) / total_area;
+                    if (cost < best_cost) { best_cost = cost; best = sp; }
+                }
+                if (n > B.max_geom || best_cost < (float)n) {
+                    // partition.rs:9-38: two-ended, swaps the first "false" from the front with the first "true" from the back
+                    uint32_t lo = begin, hi = end, split = begin;
+                    for (;;) {
+                        long f = -1, bk = -1;
+                        while (lo < hi) { const uint32_t p = lo++; uint32_t k = sat_u32_hd((cen[idx[p]] - cmin) / (cmax - cmin) * 12.0f); if (k >= 12) k = 11; if (k > (uint32_t)best) { f = p; break; } split++; }
+                        while (lo < hi) { const uint32_t p = --hi; uint32_t k = sat_u32_hd((cen[idx[p]] - cmin) / (cmax - cmin) * 12.0f); if (k >= 12) k = 11; if (k <= (uint32_t)best) { bk = p; break; } }
+                        if (f < 0 || bk < 0) break;
+                        const uint32_t tmp = idx[f]; idx[f] = idx[bk]; idx[bk] = tmp;
+                        split++;
+                    }
+                    mid = split;
+                } else is_leaf = true;
+            }
+        }
+        trb_bvh_node& nd = B.nodes[me];
+        for (int i = 0; i < 3; ++i) { nd.bmin[i] = bounds.lo[i]; nd.bmax[i] = bounds.hi[i]; }
+        if (is_leaf) {
+            nd.a = B.n_order; nd.b = TRB_BVH_LEAF | n;
+            for (uint32_t i = begin; i < end; ++i) B.order[B.n_order++] = idx[i];
+            if (n_task == 0) break;
+            n_task--;
+            begin = B.task[3 * n_task]; end = B.task[3 * n_task + 1]; parent = B.task[3 * n_task + 2];
+        } else {
+            nd.a = 0; nd.b = (uint32_t)axis;
+            B.task[3 * n_task] = mid; B.task[3 * n_task + 1] = end; B.task[3 * n_task + 2] = me; n_task++; // second child later
+            end = mid; parent = 0xffffffffu;                                                                 // first child = next node (bvh.rs:255)
+        }
+    }
+    // BuildNode::interior: an interior node's bounds are the union of its children's (bvh.rs:358-362); children follow their parent
+    for (uint32_t i = B.n_nodes; i-- > 0;) {
+        trb_bvh_node& nd = B.nodes[i];
+        if (nd.b & TRB_BVH_LEAF) continue;
+        const trb_bvh_node& l = B.nodes[i + 1];
+        const trb_bvh_node& r = B.nodes[nd.a];
+        for (int k = 0; k < 3; ++k) { nd.bmin[k] = fminf(l.bmin[k], r.bmin[k]); nd.bmax[k] = fmaxf(l.bmax[k], r.bmax[k]); }
+    }
+}
+
+struct BvhBuilder { // host convenience over bvh_build_arrays
     std::vector<trb_bvh_node> nodes;
     std::vector<uint32_t> order; // ordered_geom
-    const Box3* boxes = nullptr;
-    std::vector<float> cx, cy, cz; // centroids = lo*0.5 + hi*0.5 (bbox.rs:58-61 via linalg::lerp)
-    std::vector<uint32_t> idx;
-    uint32_t max_geom = 4;
-
-    float centroid(uint32_t g, int axis) const { return axis == 0 ? cx[g] : (axis == 1 ? cy[g] : cz[g]); }
-
-    void build(const std::vector<Box3>& b, uint32_t max_geom_) {
-        boxes = b.data(); max_geom = max_geom_;
+    void build(const std::vector<Box3>& b, uint32_t max_geom) {
         const size_t n = b.size();
-        cx.resize(n); cy.resize(n); cz.resize(n); idx.resize(n);
-        for (size_t i = 0; i < n; ++i) {
-            cx[i] = b[i].lo[0] * (1.0f - 0.5f) + b[i].hi[0] * 0.5f;
-            cy[i] = b[i].lo[1] * (1.0f - 0.5f) + b[i].hi[1] * 0.5f;
-            cz[i] = b[i].lo[2] * (1.0f - 0.5f) + b[i].hi[2] * 0.5f;
-            idx[i] = (uint32_t)i;
-        }
-        nodes.clear(); order.clear();
-        nodes.reserve(2 * n); order.reserve(n);
-        emit(0, (uint32_t)n);
-    }
-
-  private:
-    void set_bounds(uint32_t node, const Box3& b) {
-        for (int i = 0; i < 3; ++i) { nodes[node].bmin[i] = b.lo[i]; nodes[node].bmax[i] = b.hi[i]; }
-    }
-    uint32_t leaf(uint32_t begin, uint32_t end, const Box3& bounds) {
-        const uint32_t me = (uint32_t)nodes.size();
-        nodes.push_back(trb_bvh_node{});
-        set_bounds(me, bounds);
-        nodes[me].a = (uint32_t)order.size();
-        nodes[me].b = TRB_BVH_LEAF | (end - begin);
-        for (uint32_t i = begin; i < end; ++i) order.push_back(idx[i]);
-        return me;
-    }
-    uint32_t interior(uint32_t begin, uint32_t mid, uint32_t end, int axis) {
-        const uint32_t me = (uint32_t)nodes.size();
-        nodes.push_back(trb_bvh_node{});
-        const uint32_t l = emit(begin, mid);
-        const uint32_t r = emit(mid, end);
-        Box3 u; // BuildNode::interior: union of the children (bvh.rs:358-362)
-        for (int i = 0; i < 3; ++i) { u.lo[i] = fminf(nodes[l].bmin[i], nodes[r].bmin[i]); u.hi[i] = fmaxf(nodes[l].bmax[i], nodes[r].bmax[i]); }
-        set_bounds(me, u);
-        nodes[me].a = r;
-        nodes[me].b = (uint32_t)axis;
-        return me;
-    }
-    static uint32_t sat_u32(float f) { if (!(f > 0.0f)) return 0; if (f >= 4294967296.0f) return 0xffffffffu; return (uint32_t)f; }
-
-    // BVH::build (bvh.rs:139-232) over idx[begin, end)
-    uint32_t emit(uint32_t begin, uint32_t end) {
-        const uint32_t n = end - begin;
-        Box3 bounds = box_empty();
-        for (uint32_t i = begin; i < end; ++i) box_grow(bounds, boxes[idx[i]]);
-        if (n == 1) return leaf(begin, end, bounds);
-        Box3 cb = box_empty();
-        for (uint32_t i = begin; i < end; ++i) { const float c[3] = {cx[idx[i]], cy[idx[i]], cz[idx[i]]}; box_grow_pt(cb, c); }
-        const int axis = box_longest_axis(cb);
-        uint32_t mid = begin + n / 2;
-        if (fabsf(cb.hi[axis] - cb.lo[axis]) < kEps) { // coincident centroids (bvh.rs:156-166)
-            if (n < max_geom) return leaf(begin, end, bounds);
-            return interior(begin, mid, end, axis);
-        }
-        if (n < 5) { // stable sort by centroid, median split (bvh.rs:169-178)
-            for (uint32_t i = begin + 1; i < end; ++i) { // insertion sort == stable
-                const uint32_t g = idx[i];
-                const float key = centroid(g, axis);
-                uint32_t j = i;
-                while (j > begin && centroid(idx[j - 1], axis) > key) { idx[j] = idx[j - 1]; --j; }
-                idx[j] = g;
-            }
-        } else {
-            const float cmin = cb.lo[axis], cmax = cb.hi[axis];
-            auto bucket = [&](uint32_t g) -> uint32_t {
-                const uint32_t b = sat_u32((centroid(g, axis) - cmin) / (cmax - cmin) * 12.0f);
-                return b == 12 ? 11 : b;
-            };
-            uint32_t count[12] = {0};
-            Box3 bb[12];
-            for (int k = 0; k < 12; ++k) bb[k] = box_empty();
-            for (uint32_t i = begin; i < end; ++i) {
-                uint32_t k = bucket(idx[i]);
-                if (k > 11) k = 11;
-                count[k]++;
-                box_grow(bb[k], boxes[idx[i]]);
-            }
-            float best_cost = INFINITY; int best = 0;
-            const float total_area = box_area(bounds);
-            for (int s = 0; s < 11; ++s) { // cost of splitting after bucket s (bvh.rs:191-206)
-                Box3 lb = box_empty(), rb = box_empty();
-                uint32_t lc = 0, rc = 0;
-                for (int k = 0; k <= s; ++k) { box_grow(lb, bb[k]); lc += count[k]; }
-                for (int k = s + 1; k < 12; ++k) { box_grow(rb, bb[k]); rc += count[k]; }
-                const float cost = 0.125f + ((float)lc * box_area(lb) + (float)rc * box_area(rb)) / total_area;
-                if (cost < best_cost) { best_cost = cost; best = s; }
-            }
-            if (n > max_geom || best_cost < (float)n) {
-                // partition.rs:9-38: two-ended, swaps the first "false" from the front with the first "true" from the back
-                uint32_t lo = begin, hi = end, split = begin;
-                for (;;) {
-                    long f = -1, bk = -1;
-                    while (lo < hi) { const uint32_t p = lo++; if (bucket(idx[p]) > (uint32_t)best) { f = p; break; } split++; }
-                    while (lo < hi) { const uint32_t p = --hi; if (bucket(idx[p]) <= (uint32_t)best) { bk = p; break; } }
-                    if (f < 0 || bk < 0) break;
-                    std::swap(idx[f], idx[bk]);
-                    split++;
-                }
-                mid = split;
-            } else {
-                return leaf(begin, end, bounds);
-            }
-        }
-        return interior(begin, mid, end, axis);
+        std::vector<float> cx(n), cy(n), cz(n);
+        std::vector<uint32_t> idx(n), task(3 * n + 3);
+        nodes.assign(2 * n, trb_bvh_node{}); order.assign(n, 0u);
+        BvhBuildArrays B{b.data(), (uint32_t)n, max_geom, cx.data(), cy.data(), cz.data(), idx.data(), task.data(), nodes.data(), order.data(), 0, 0};
+        bvh_build_arrays(B);
+        nodes.resize(B.n_nodes); order.resize(B.n_order);
     }
 };
 
