@@ -328,3 +328,33 @@ def test_whitted_json_scene_through_the_loader(tmp_path):
         assert ost.rays_continuation > 0       # the metal and glass spheres recurse
     finally:
         lib.trb_desc_free(dp)
+
+
+def test_update_frame_on_device_matches_the_host_path_and_the_oracle():
+    """SURVEY 8(f) N1: Scene::update_frame on the device (k_frame_instances + k_tlas_build: instance transforms at shutter-open,
+    animation bounds over the shutter, the reference's SAH build with max_geom 4 and the traversal records) against the same
+    work done by the host code (option "frame.device" = 0) and by the oracle, frame by frame of a keyframed scene."""
+    desc = SB.scene_animated(48, 48, 4, frames=6, scene_time=1.5, animated_fov=True).finish()
+    g, o = api.Scene(desc), O.OracleScene(desc)
+    step = 1.5 / 6
+    for fr in range(6):
+        o.update_frame(fr, fr * step, (fr + 1) * step)
+        on, oo = o.bvh(-1)
+        per_path = {}
+        for dev in (1, 0):
+            g.set_option("frame.device", dev)
+            g.update_frame(fr, fr * step, (fr + 1) * step)
+            gn, go = g.bvh(-1)
+            assert gn.tobytes() == on.tobytes() and np.array_equal(go, oo), (fr, dev)
+            for i in range(desc.n_instances):
+                gm, gi = g.transform(i); om, oi = o.transform(i)
+                assert gm.tobytes() == om.tobytes() and gi.tobytes() == oi.tobytes(), (fr, dev, i)
+            per_path[dev] = g.render_samples(seed=6)[0]
+        assert per_path[0].tobytes() == per_path[1].tobytes() == o.render_samples(seed=6)[0].tobytes()
+    g.set_option("frame.device", 1)
+    # the per-path transform table against per-ray evaluation
+    g.update_frame(2, 2 * step, 3 * step)
+    a = g.render_samples(seed=8)[0]
+    g.set_option("anim.table", 0)
+    b = g.render_samples(seed=8)[0]
+    assert a.tobytes() == b.tobytes()

@@ -109,13 +109,13 @@ TRB_HD inline Xf animated_xf(const trb_spline* splines, uint32_t first, uint32_t
 }
 
 // AnimatedTransform::is_animated (animated_transform.rs:73-75): true only if EVERY stacked spline has > 1 control point (Q22)
-inline bool xf_is_animated(const trb_spline* splines, uint32_t first, uint32_t count) {
+TRB_HD inline bool xf_is_animated(const trb_spline* splines, uint32_t first, uint32_t count) {
     if (count == 0) return true;
     bool b = true;
     for (uint32_t s = first; s < first + count; ++s) b = b && splines[s].n_ctrl > 1;
     return b;
 }
-inline bool xf_is_static(const trb_spline* splines, uint32_t first, uint32_t count) {
+TRB_HD inline bool xf_is_static(const trb_spline* splines, uint32_t first, uint32_t count) {
     for (uint32_t s = first; s < first + count; ++s) if (splines[s].n_ctrl != 1) return false;
     return true;
 }

@@ -167,6 +167,7 @@ struct Tuning {
     int sort = 0;              // ray queues: 0 = path order; 1 / 2 = counting sort by (octant, origin cell) / (cell, octant) before each trace round (measured: -1.5 % trace time, +10 % step time on C4)
     int sort_bits = 5;         // bits per axis of the origin cell grid
     int sort_min_round = 1;    // first bounce round whose queues are sorted (round 0 = primary rays, already coherent)
+    int frame_device = 1;      // Scene::update_frame on the device (instance transforms, animation bounds, TLAS SAH build); 0 = on the host
     int anim_table = 1;        // keyframed scenes: evaluate each keyframed instance's transform once per path (0 = per ray per instance, like the reference)
     int shade_split = 0;       // shading as three kernels (surface | direct light | BSDF sample) instead of one (measured equal on C4)
     int graph = 1;             // replay each pass as a CUDA graph when its shape repeats
@@ -177,7 +178,7 @@ void tuning_from_env(Tuning& t) {
     t.refill = env_int("TRB_REFILL", t.refill); t.occ = env_int("TRB_TRACE_OCC", t.occ); t.trace_grid = (unsigned)env_int("TRB_TRACE_GRID", (int)t.trace_grid);
     t.smem_stack = env_int("TRB_SMEM_STACK", t.smem_stack); t.sched = (uint32_t)env_int("TRB_TRACE_SCHED", (int)t.sched); t.quads = env_int("TRB_TRACE_QUADS", t.quads);
     t.film_v2 = env_int("TRB_FILM_V2", t.film_v2); t.sort = env_int("TRB_SORT", t.sort); t.sort_bits = env_int("TRB_SORT_BITS", t.sort_bits);
-    t.sort_min_round = env_int("TRB_SORT_MIN_ROUND", t.sort_min_round); t.shade_split = env_int("TRB_SHADE_SPLIT", t.shade_split); t.anim_table = env_int("TRB_ANIM_TABLE", t.anim_table); t.graph = env_int("TRB_GRAPH", t.graph);
+    t.sort_min_round = env_int("TRB_SORT_MIN_ROUND", t.sort_min_round); t.shade_split = env_int("TRB_SHADE_SPLIT", t.shade_split); t.anim_table = env_int("TRB_ANIM_TABLE", t.anim_table); t.frame_device = env_int("TRB_FRAME_DEVICE", t.frame_device); t.graph = env_int("TRB_GRAPH", t.graph);
     if (getenv("TRB_PASS_PATHS")) t.pass_paths = strtoull(getenv("TRB_PASS_PATHS"), nullptr, 0);
 }
 
@@ -224,6 +225,14 @@ struct trb_scene {
     trb::DBvh* d_tlas_hdr = nullptr;
     uint32_t* d_tlas_order = nullptr;
     size_t tlas_capacity = 0;
+    // device-side update_frame (k_frame_instances / k_tlas_build): reference-order nodes, instance bounds, builder scratch
+    trb_bvh_node* d_tlas_nodes = nullptr;
+    float* d_bounds = nullptr;           // n x Box3 (6 floats)
+    float* d_build_f = nullptr;
+    uint32_t* d_build_u = nullptr;
+    uint32_t* d_build_counts = nullptr;
+    uint32_t tlas_n_nodes = 0;
+    bool instances_static_uploaded = false, host_frame_stale = false;
     std::vector<BlockList> block_lists;
     uint32_t* d_counter = nullptr;
     int* d_error = nullptr;
@@ -606,6 +615,7 @@ trb_status trb_scene_set_option(trb_scene* s, const char* name, long long value)
     else if (k == "sort.min_round") t.sort_min_round = (int)value;
     else if (k == "shade.split") t.shade_split = (int)value;
     else if (k == "anim.table") t.anim_table = (int)value;
+    else if (k == "frame.device") t.frame_device = (int)value;
     else if (k == "pass.graph") t.graph = (int)value;
     else if (k == "pass.paths") { if (value < 64) return fail(TRB_INVALID_ARG, "pass.paths must be >= 64"); t.pass_paths = (uint64_t)value; }
     else return fail(TRB_INVALID_ARG, "unknown option: " + k);
@@ -861,13 +871,69 @@ trb_status trb_scene_update_frame(trb_scene* s, uint32_t frame, float start, flo
 
     // instance transforms + bounds, then BVH<Instance>::rebuild(shutter_open, shutter_close) (scene.rs:175, bvh.rs:61-78)
     const size_t n = s->instances.size();
-    s->world.resize(n);
-    std::vector<Box3> bounds(n);
+    // static part of the device instance records (everything but the matrices); keyframed / animated flags are scene properties
     std::vector<trb::DInstance> di(n);
     std::vector<uint32_t> anim_list;
     for (size_t i = 0; i < n; ++i) {
         const trb_instance& in = s->instances[i];
-        // world[i] = transform(shutter_open): exact for static instances; keyframed ones are re-evaluated per ray on the device
+        trb::DInstance& o = di[i];
+        std::memset(&o, 0, sizeof o);
+        o.kind = in.kind; o.shape = in.shape; o.p0 = in.p0; o.p1 = in.p1; o.mesh = in.mesh; o.material = in.material;
+        o.xf_first = in.spline_first; o.xf_count = in.n_splines;
+        if (!trbh::xf_is_static(s->splines.data(), in.spline_first, in.n_splines)) {
+            o.flags |= trb::DI_ANIM_XF; o.spline_first = in.spline_first; o.n_splines = in.n_splines; any_anim = true;
+            o.anim_slot = (uint32_t)anim_list.size(); anim_list.push_back((uint32_t)i);
+        }
+        if (in.kind != TRB_INST_RECEIVER) {
+            for (int k = 0; k < 3; ++k) o.emission[k] = s->color_keys[in.emission_first].rgba[k];
+            if (in.n_emission > 1) { o.flags |= trb::DI_ANIM_EMISSION; o.emission_first = in.emission_first; o.n_emission = in.n_emission; any_anim = true; }
+        }
+    }
+    s->ds.has_anim = any_anim ? 1u : 0u;
+    if (n + 1 > s->tlas_capacity) { // a tree over n instances has < n interior records and < 2n nodes
+        CU(s->arena.alloc(n + 1, &s->d_tlas_quads));
+        CU(s->arena.alloc(n + 1, &s->d_tlas));
+        CU(s->arena.alloc(n, &s->d_tlas_order));
+        CU(s->arena.alloc(2 * n + 2, &s->d_tlas_nodes));
+        CU(s->arena.alloc(6 * n, &s->d_bounds));
+        CU(s->arena.alloc(3 * n, &s->d_build_f));
+        CU(s->arena.alloc(7 * n + 8, &s->d_build_u));
+        CU(s->arena.alloc(4, &s->d_build_counts));
+        s->tlas_capacity = n + 1;
+    }
+    if (!s->d_tlas_hdr) CU(s->arena.alloc(1, &s->d_tlas_hdr));
+    if (!anim_list.empty()) CU(cudaMemcpy(s->d_anim_instances, anim_list.data(), anim_list.size() * sizeof(uint32_t), cudaMemcpyHostToDevice));
+    s->ds.anim_instances = s->d_anim_instances; s->ds.n_anim_instances = (uint32_t)anim_list.size();
+    s->ds.tlas = s->d_tlas_hdr; s->ds.tlas_pairs = s->d_tlas; s->ds.tlas_quads = s->d_tlas_quads; s->ds.tlas_order = s->d_tlas_order;
+
+    if (s->tune.frame_device && !s->tune.quads) {
+        // ---- device path: transforms, animation bounds, SAH build and record packing all on the GPU (k_frame_instances, k_tlas_build)
+        if (!s->instances_static_uploaded) { CU(cudaMemcpy(s->d_instances, di.data(), n * sizeof(trb::DInstance), cudaMemcpyHostToDevice)); s->instances_static_uploaded = true; }
+        trb::FrameBuild fb{};
+        fb.instances = s->d_instances; fb.bounds = reinterpret_cast<trbh::Box3*>(s->d_bounds); fb.n = (uint32_t)n;
+        fb.shutter_open = s->shutter_open; fb.shutter_close = s->shutter_close;
+        fb.cx = s->d_build_f; fb.cy = s->d_build_f + n; fb.cz = s->d_build_f + 2 * n;
+        fb.idx = s->d_build_u; fb.task = s->d_build_u + n; fb.rec_of = s->d_build_u + 4 * n + 4;
+        fb.nodes = s->d_tlas_nodes; fb.order = s->d_tlas_order; fb.counts = s->d_build_counts; fb.pairs = s->d_tlas; fb.hdr = s->d_tlas_hdr;
+        trb::k_frame_instances<<<(unsigned)((n + 63) / 64), 64>>>(s->ds, fb);
+        trb::k_tlas_build<<<1, 1>>>(fb);
+        g_launches += 2;
+        CU(cudaGetLastError());
+        uint32_t counts[3] = {0, 0, 0};
+        CU(cudaMemcpy(counts, s->d_build_counts, sizeof counts, cudaMemcpyDeviceToHost)); // also the frame's only synchronisation point
+        if (!counts[2]) return fail(TRB_UNSUPPORTED, "too many instances for the leaf encoding");
+        s->tlas_n_nodes = counts[0];
+        s->host_frame_stale = true; // world transforms / TLAS nodes are fetched from the device when a getter asks for them
+        s->frame_ready = true;
+        return TRB_OK;
+    }
+
+    // ---- host path (kept for the DQuad experiment and as an independent check of the device path)
+    s->world.resize(n);
+    std::vector<Box3> bounds(n);
+    for (size_t i = 0; i < n; ++i) {
+        const trb_instance& in = s->instances[i];
+        // world[i] = transform(shutter_open): exact for static instances; keyframed ones are re-evaluated per ray / per path on the device
         s->world[i] = trbh::animated_xf(s->splines.data(), in.spline_first, in.n_splines, s->keyframes.data(), s->knots.data(), s->shutter_open);
         const Box3 local = shape_bounds(*s, in);
         if (!trbh::xf_is_animated(s->splines.data(), in.spline_first, in.n_splines)) { // animation_bounds (animated_transform.rs:57-70, Q22)
@@ -882,24 +948,13 @@ trb_status trb_scene_update_frame(trb_scene* s, uint32_t frame, float start, flo
             }
             bounds[i] = acc;
         }
-        trb::DInstance& o = di[i];
-        std::memset(&o, 0, sizeof o);
-        std::memcpy(o.inv, s->world[i].inv.m, 64);
-        std::memcpy(o.mat, s->world[i].fwd.m, 64);
-        o.kind = in.kind; o.shape = in.shape; o.p0 = in.p0; o.p1 = in.p1; o.mesh = in.mesh; o.material = in.material;
-        if (!trbh::xf_is_static(s->splines.data(), in.spline_first, in.n_splines)) {
-            o.flags |= trb::DI_ANIM_XF; o.spline_first = in.spline_first; o.n_splines = in.n_splines; any_anim = true;
-            o.anim_slot = (uint32_t)anim_list.size(); anim_list.push_back((uint32_t)i);
-        }
-        if (in.kind != TRB_INST_RECEIVER) {
-            for (int k = 0; k < 3; ++k) o.emission[k] = s->color_keys[in.emission_first].rgba[k];
-            if (in.n_emission > 1) { o.flags |= trb::DI_ANIM_EMISSION; o.emission_first = in.emission_first; o.n_emission = in.n_emission; any_anim = true; }
-        }
+        std::memcpy(di[i].inv, s->world[i].inv.m, 64);
+        std::memcpy(di[i].mat, s->world[i].fwd.m, 64);
     }
-    s->ds.has_anim = any_anim ? 1u : 0u;
     BvhBuilder bb;
     bb.build(bounds, 4);
     s->tlas_nodes = bb.nodes; s->tlas_order = bb.order;
+    s->host_frame_stale = false; s->instances_static_uploaded = false;
     std::vector<trb::DPair> pn;
     trb::DBvh hdr{};
     if (!pack_pairs(s->tlas_nodes, pn, hdr)) return fail(TRB_UNSUPPORTED, "too many instances for the leaf encoding");
@@ -907,22 +962,12 @@ trb_status trb_scene_update_frame(trb_scene* s, uint32_t frame, float start, flo
     uint32_t qroot = 0;
     if (!pack_quads(s->tlas_nodes, qn, qroot)) return fail(TRB_UNSUPPORTED, "too many instances for the leaf encoding");
     hdr.root_hi.w = bits_f(qroot);
-    if (pn.size() + 1 > s->tlas_capacity) {
-        CU(s->arena.alloc(pn.size() + 1, &s->d_tlas_quads)); // a tree has fewer quad records than pair records
-        CU(s->arena.alloc(pn.size() + 1, &s->d_tlas));
-        CU(s->arena.alloc(n, &s->d_tlas_order));
-        s->tlas_capacity = pn.size() + 1;
-    }
     if (!pn.empty()) CU(cudaMemcpy(s->d_tlas, pn.data(), pn.size() * sizeof(trb::DPair), cudaMemcpyHostToDevice));
     CU(cudaMemcpy(s->d_tlas_order, s->tlas_order.data(), n * sizeof(uint32_t), cudaMemcpyHostToDevice));
     CU(cudaMemcpy(s->d_instances, di.data(), n * sizeof(trb::DInstance), cudaMemcpyHostToDevice));
-    if (!anim_list.empty()) CU(cudaMemcpy(s->d_anim_instances, anim_list.data(), anim_list.size() * sizeof(uint32_t), cudaMemcpyHostToDevice));
-    s->ds.anim_instances = s->d_anim_instances; s->ds.n_anim_instances = (uint32_t)anim_list.size();
     if (!qn.empty()) CU(cudaMemcpy(s->d_tlas_quads, qn.data(), qn.size() * sizeof(trb::DQuad), cudaMemcpyHostToDevice));
     hdr.pairs = s->d_tlas; hdr.quads = s->d_tlas_quads;
-    if (!s->d_tlas_hdr) CU(s->arena.alloc(1, &s->d_tlas_hdr));
     CU(cudaMemcpy(s->d_tlas_hdr, &hdr, sizeof hdr, cudaMemcpyHostToDevice));
-    s->ds.tlas = s->d_tlas_hdr; s->ds.tlas_pairs = s->d_tlas; s->ds.tlas_quads = s->d_tlas_quads; s->ds.tlas_order = s->d_tlas_order;
     s->frame_ready = true;
     return TRB_OK;
 }
@@ -1128,7 +1173,17 @@ trb_status trb_block_list(const trb_scene* s, uint32_t start, uint32_t count, ui
 trb_status trb_scene_get_bvh(const trb_scene* s, int which, uint32_t* n_nodes, trb_bvh_node* nodes, uint32_t* n_ordered, uint32_t* ordered) {
     if (!s || !n_nodes || !n_ordered) return fail(TRB_INVALID_ARG, "null argument");
     const std::vector<trb_bvh_node>* nn; const std::vector<uint32_t>* oo;
-    if (which < 0) { if (!s->frame_ready) return fail(TRB_INVALID_ARG, "update_frame first"); nn = &s->tlas_nodes; oo = &s->tlas_order; }
+    std::vector<trb_bvh_node> dev_nodes; std::vector<uint32_t> dev_order;
+    if (which < 0) {
+        if (!s->frame_ready) return fail(TRB_INVALID_ARG, "update_frame first");
+        if (s->host_frame_stale) { // the frame was prepared on the device: read its TLAS back
+            CU(cudaSetDevice(s->device));
+            dev_nodes.resize(s->tlas_n_nodes); dev_order.resize(s->instances.size());
+            CU(cudaMemcpy(dev_nodes.data(), s->d_tlas_nodes, dev_nodes.size() * sizeof(trb_bvh_node), cudaMemcpyDeviceToHost));
+            CU(cudaMemcpy(dev_order.data(), s->d_tlas_order, dev_order.size() * sizeof(uint32_t), cudaMemcpyDeviceToHost));
+            nn = &dev_nodes; oo = &dev_order;
+        } else { nn = &s->tlas_nodes; oo = &s->tlas_order; }
+    }
     else { if ((size_t)which >= s->meshes.size()) return fail(TRB_INVALID_ARG, "mesh index out of range"); nn = &s->meshes[which].nodes; oo = &s->meshes[which].order; }
     *n_nodes = (uint32_t)nn->size(); *n_ordered = (uint32_t)oo->size();
     if (nodes) std::memcpy(nodes, nn->data(), nn->size() * sizeof(trb_bvh_node));
@@ -1137,7 +1192,14 @@ trb_status trb_scene_get_bvh(const trb_scene* s, int which, uint32_t* n_nodes, t
 }
 
 trb_status trb_scene_get_transform(const trb_scene* s, uint32_t inst, float* mat16, float* inv16) {
-    if (!s || !s->frame_ready || inst >= s->world.size()) return fail(TRB_INVALID_ARG, "bad instance / update_frame first");
+    if (!s || !s->frame_ready || inst >= s->instances.size()) return fail(TRB_INVALID_ARG, "bad instance / update_frame first");
+    if (s->host_frame_stale) { // prepared on the device
+        trb::DInstance di;
+        CU(cudaSetDevice(s->device));
+        CU(cudaMemcpy(&di, s->d_instances + inst, sizeof di, cudaMemcpyDeviceToHost));
+        std::memcpy(mat16, di.mat, 64); std::memcpy(inv16, di.inv, 64);
+        return TRB_OK;
+    }
     std::memcpy(mat16, s->world[inst].fwd.m, 64); std::memcpy(inv16, s->world[inst].inv.m, 64);
     return TRB_OK;
 }

@@ -68,7 +68,7 @@ struct DMesh {
 
 // geometry::Instance with its world transform at the current frame (static instances: recomposed
 // once per update_frame instead of once per ray — bit-identical, DESIGN.md "X1").
-struct alignas(16) DInstance { // 176 B: the two matrices are read as 16-byte vectors
+struct alignas(16) DInstance { // 208 B: the two matrices are read as 16-byte vectors
     float inv[16];  // world -> object, row-major 4x4 (last row kept: transform.rs:150-162 divides by w)
     float mat[16];  // object -> world
     uint32_t kind, shape;
@@ -80,9 +80,11 @@ struct alignas(16) DInstance { // 176 B: the two matrices are read as 16-byte ve
     uint32_t emission_first, n_emission;  // colour keys (into DScene::color_keys) when DI_ANIM_EMISSION
     uint32_t anim_slot;      // index among the keyframed instances (DScene::anim_instances) when DI_ANIM_XF
     uint32_t pad;
+    uint32_t xf_first, xf_count;  // the instance's whole transform stack (every level), for the per-frame device update
+    uint32_t pad2[2];
 };
 constexpr uint32_t DI_ANIM_XF = 1u, DI_ANIM_EMISSION = 2u;
-static_assert(sizeof(DInstance) == 192, "DInstance must stay 16-byte sized");
+static_assert(sizeof(DInstance) == 208, "DInstance must stay 16-byte sized");
 
 struct DMaterial {
     uint32_t type;

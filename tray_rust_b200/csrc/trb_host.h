@@ -119,7 +119,7 @@ inline int box_longest_axis(const Box3& b) { // bbox.rs:47-56
     return dy > dz ? 1 : 2;
 }
 // Transform * BBox (Arvo), transform.rs:256-281
-inline Box3 arvo_bounds(const Mat4& m, const Box3& b) {
+TRB_HD inline Box3 arvo_bounds(const Mat4& m, const Box3& b) {
     Box3 o;
     for (int i = 0; i < 3; ++i) o.lo[i] = o.hi[i] = m.m[4 * i + 3];
     for (int i = 0; i < 3; ++i)

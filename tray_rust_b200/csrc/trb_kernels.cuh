@@ -2379,6 +2379,90 @@ __global__ void __launch_bounds__(128) k_intersect(const __grid_constant__ DScen
     if (stats) flush_stats(stats, rc, cnt, 0, STATS);
 }
 
+// ------------------------------------------------------------------------------------------
+// Scene::update_frame on the device (scene.rs:152-176, bvh.rs:61-78): per instance the world transform at the
+// shutter-open time and its bounds over the shutter interval (animation_bounds, animated_transform.rs:57-70: 128 time
+// samples when every stacked level is keyframed, one box otherwise — Q22), then BVH<Instance>::rebuild with the reference's
+// SAH builder (the same bvh_build_arrays the host runs, one thread: a TLAS has tens of instances) and the child-pair
+// records the trace kernel walks. Nothing is uploaded per frame but the camera block inside the kernel parameters.
+// ------------------------------------------------------------------------------------------
+struct FrameBuild {
+    DInstance* instances;          // in/out: static fields set at scene creation; inv / mat written here
+    trbh::Box3* bounds;            // out [n]
+    uint32_t n;
+    float shutter_open, shutter_close;
+    // TLAS build
+    float* cx; float* cy; float* cz; uint32_t* idx; uint32_t* task; uint32_t* rec_of; // scratch
+    trb_bvh_node* nodes; uint32_t* order; uint32_t* counts; // out: reference-order nodes, ordered_geom, {n_nodes, n_order, pack ok}
+    DPair* pairs; DBvh* hdr;                                // out: traversal records + header
+};
+__device__ __forceinline__ trbh::Box3 shape_bounds_dev(const DScene& sc, const DInstance& in) {
+    trbh::Box3 b;
+    const float p0 = in.p0, p1 = in.p1;
+    switch (in.shape) {
+        case TRB_SHAPE_SPHERE: for (int i = 0; i < 3; ++i) { b.lo[i] = -p0; b.hi[i] = p0; } break;                               // sphere.rs:84-88
+        case TRB_SHAPE_DISK: b.lo[0] = b.lo[1] = -p0; b.hi[0] = b.hi[1] = p0; b.lo[2] = -0.1f; b.hi[2] = 0.1f; break;            // disk.rs:79-81
+        case TRB_SHAPE_RECT: { const float hw = p0 / 2.0f, hh = p1 / 2.0f; b.lo[0] = -hw; b.lo[1] = -hh; b.hi[0] = hw; b.hi[1] = hh; b.lo[2] = b.hi[2] = 0.0f; break; } // rectangle.rs:67-71
+        case TRB_SHAPE_MESH: { const DBvh& h = sc.meshes[in.mesh].bvh; b.lo[0] = h.root_lo.x; b.lo[1] = h.root_lo.y; b.lo[2] = h.root_lo.z; b.hi[0] = h.root_hi.x; b.hi[1] = h.root_hi.y; b.hi[2] = h.root_hi.z; break; } // mesh.rs:87-90
+        default: for (int i = 0; i < 3; ++i) b.lo[i] = b.hi[i] = 0.0f;                                                          // point light (emitter.rs:152)
+    }
+    return b;
+}
+__global__ void __launch_bounds__(64) k_frame_instances(const __grid_constant__ DScene sc, const __grid_constant__ FrameBuild fb) {
+    const uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= fb.n) return;
+    DInstance& in = fb.instances[i];
+    const uint32_t first = in.xf_first, cnt = in.xf_count;
+    const trbh::Xf w = trbh::animated_xf(sc.splines, first, cnt, sc.keyframes, sc.knots, fb.shutter_open, sc.level_xf);
+#pragma unroll
+    for (int k = 0; k < 16; ++k) { in.inv[k] = w.inv.m[k]; in.mat[k] = w.fwd.m[k]; }
+    const trbh::Box3 local = shape_bounds_dev(sc, in);
+    trbh::Box3 acc;
+    if (!trbh::xf_is_animated(sc.splines, first, cnt)) acc = trbh::arvo_bounds(w.fwd, local);
+    else {
+        acc = trbh::box_empty_hd();
+        for (int k = 0; k < 128; ++k) {
+            const float u = (float)k / 127.0f;
+            const float time = fb.shutter_open * (1.0f - u) + fb.shutter_close * u; // linalg::lerp
+            const trbh::Xf x = trbh::animated_xf(sc.splines, first, cnt, sc.keyframes, sc.knots, time, sc.level_xf);
+            trbh::box_grow_hd(acc, trbh::arvo_bounds(x.fwd, local));
+        }
+    }
+    fb.bounds[i] = acc;
+}
+__global__ void k_tlas_build(const __grid_constant__ FrameBuild fb) {
+    if (blockIdx.x != 0 || threadIdx.x != 0) return;
+    trbh::BvhBuildArrays B{fb.bounds, fb.n, 4u, fb.cx, fb.cy, fb.cz, fb.idx, fb.task, fb.nodes, fb.order, 0u, 0u}; // max_geom 4 (scene.rs:141)
+    trbh::bvh_build_arrays(B);
+    // child-pair records (trb_device.h DPair): pure re-layout of the reference-order tree
+    const trb_bvh_node* in = fb.nodes;
+    uint32_t n_rec = 0;
+    bool ok = true;
+    for (uint32_t i = 0; i < B.n_nodes; ++i) if (!(in[i].b & TRB_BVH_LEAF)) fb.rec_of[i] = n_rec++;
+    auto ref_of = [&](uint32_t i) -> uint32_t {
+        if (in[i].b & TRB_BVH_LEAF) {
+            const uint32_t cnt = in[i].b & ~TRB_BVH_LEAF, first = in[i].a;
+            if (cnt > 31 || first >= (1u << 25)) ok = false;
+            return REF_LEAF | (cnt << 25) | first;
+        }
+        return REF_INTERIOR | fb.rec_of[i];
+    };
+    for (uint32_t i = 0; i < B.n_nodes; ++i) {
+        if (in[i].b & TRB_BVH_LEAF) continue;
+        const trb_bvh_node& l = in[i + 1];
+        const trb_bvh_node& r = in[in[i].a];
+        DPair& p = fb.pairs[fb.rec_of[i]];
+        p.l_lo = make_float4(l.bmin[0], l.bmin[1], l.bmin[2], __uint_as_float(ref_of(i + 1)));
+        p.l_hi = make_float4(l.bmax[0], l.bmax[1], l.bmax[2], __uint_as_float(ref_of(in[i].a)));
+        p.r_lo = make_float4(r.bmin[0], r.bmin[1], r.bmin[2], __uint_as_float(in[i].b));
+        p.r_hi = make_float4(r.bmax[0], r.bmax[1], r.bmax[2], 0.f);
+    }
+    fb.hdr->pairs = fb.pairs;
+    fb.hdr->root_lo = make_float4(in[0].bmin[0], in[0].bmin[1], in[0].bmin[2], __uint_as_float(ref_of(0)));
+    fb.hdr->root_hi = make_float4(in[0].bmax[0], in[0].bmax[1], in[0].bmax[2], 0.f);
+    fb.counts[0] = B.n_nodes; fb.counts[1] = B.n_order; fb.counts[2] = ok ? 1u : 0u;
+}
+
 // RenderTarget::get_render (render_target.rs:185-210) + Colorf::to_srgb (color.rs:59-72)
 __global__ void k_srgb8(size_t n, const float4* __restrict__ film, uint8_t* __restrict__ rgb8) {
     for (size_t i = blockIdx.x * (size_t)blockDim.x + threadIdx.x; i < n; i += (size_t)gridDim.x * blockDim.x) {
