@@ -374,6 +374,10 @@ trb_status trb_render_samples(trb_scene* scene, const trb_render_cfg* cfg, size_
  * (c*255) as u8; pixels with weight <= 0 stay 0. Host buffers; runs on the scene's GPU. */
 trb_status trb_film_to_srgb8(trb_scene* scene, const float* film_rgbw, uint8_t* rgb8);
 
+/* ≙ image::save_buffer(path, &img, w, h, image::RGB(8)) for the frames written by main.rs:95-103 and by the distributed
+ * master (exec/distrib/master.rs:137-142): an 8-bit RGB PNG (stored deflate blocks; host only, no device needed). */
+trb_status trb_write_png(const char* path, const uint8_t* rgb8, uint32_t width, uint32_t height);
+
 /* -- introspection for parity tests ------------------------------------------------ */
 
 /* The Morton-sorted 8x8 block list (block_queue.rs:28-46) after select_blocks: pairs (bx,by). */

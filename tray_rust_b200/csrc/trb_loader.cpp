@@ -702,3 +702,58 @@ trb_status trb_scene_load_json(const char* path, uint32_t w, uint32_t h, uint32_
 }
 
 } // extern "C"
+
+
+// ------------------------------------------------------------------------------------------------------------
+// PNG output (the output half): what `image::save_buffer(path, &img, w, h, image::RGB(8))` does for the frames
+// of main.rs:95-103 / master.rs:137-142 — 8-bit RGB, no interlace, filter type 0 on every scanline. The zlib stream uses
+// stored (uncompressed) deflate blocks: any PNG reader accepts it, and the library needs no compression dependency.
+// ------------------------------------------------------------------------------------------------------------
+namespace {
+uint32_t png_crc(const uint8_t* p, size_t n, uint32_t crc) {
+    static uint32_t table[256];
+    static bool init = false;
+    if (!init) { for (uint32_t i = 0; i < 256; ++i) { uint32_t c = i; for (int k = 0; k < 8; ++k) c = (c & 1) ? 0xedb88320u ^ (c >> 1) : c >> 1; table[i] = c; } init = true; }
+    for (size_t i = 0; i < n; ++i) crc = table[(crc ^ p[i]) & 0xff] ^ (crc >> 8);
+    return crc;
+}
+void png_be32(std::vector<uint8_t>& b, uint32_t v) { b.push_back(v >> 24); b.push_back(v >> 16); b.push_back(v >> 8); b.push_back(v); }
+void png_chunk(std::vector<uint8_t>& out, const char* type, const std::vector<uint8_t>& data) {
+    png_be32(out, (uint32_t)data.size());
+    const size_t o = out.size();
+    out.insert(out.end(), type, type + 4);
+    out.insert(out.end(), data.begin(), data.end());
+    png_be32(out, png_crc(&out[o], out.size() - o, 0xffffffffu) ^ 0xffffffffu);
+}
+} // namespace
+
+extern "C" trb_status trb_write_png(const char* path, const uint8_t* rgb8, uint32_t width, uint32_t height) {
+    if (!path || !rgb8 || width == 0 || height == 0) { trb_internal_set_error("null argument"); return TRB_INVALID_ARG; }
+    std::vector<uint8_t> raw; // scanlines, each prefixed with filter type 0
+    raw.reserve((size_t)height * (3 * (size_t)width + 1));
+    for (uint32_t y = 0; y < height; ++y) { raw.push_back(0); raw.insert(raw.end(), rgb8 + (size_t)y * width * 3, rgb8 + (size_t)(y + 1) * width * 3); }
+    std::vector<uint8_t> z = {0x78, 0x01}; // zlib header, then stored deflate blocks of <= 65535 bytes
+    uint32_t a = 1, b = 0;                 // Adler-32 of the raw data
+    for (size_t o = 0; o < raw.size();) {
+        const size_t n = std::min<size_t>(65535, raw.size() - o);
+        z.push_back(o + n == raw.size() ? 1 : 0);
+        z.push_back(n & 0xff); z.push_back(n >> 8); z.push_back(~n & 0xff); z.push_back((~n >> 8) & 0xff);
+        z.insert(z.end(), raw.begin() + o, raw.begin() + o + n);
+        for (size_t i = o; i < o + n; ++i) { a = (a + raw[i]) % 65521u; b = (b + a) % 65521u; }
+        o += n;
+    }
+    png_be32(z, (b << 16) | a);
+    std::vector<uint8_t> out = {0x89, 'P', 'N', 'G', 0x0d, 0x0a, 0x1a, 0x0a};
+    std::vector<uint8_t> ihdr;
+    png_be32(ihdr, width); png_be32(ihdr, height);
+    ihdr.push_back(8); ihdr.push_back(2); ihdr.push_back(0); ihdr.push_back(0); ihdr.push_back(0); // 8 bits, colour type 2 (RGB), deflate, adaptive filtering, no interlace
+    png_chunk(out, "IHDR", ihdr);
+    png_chunk(out, "IDAT", z);
+    png_chunk(out, "IEND", {});
+    FILE* f = std::fopen(path, "wb");
+    if (!f) { trb_internal_set_error((std::string("cannot open ") + path).c_str()); return TRB_IO; }
+    const bool ok = std::fwrite(out.data(), 1, out.size(), f) == out.size();
+    std::fclose(f);
+    if (!ok) { trb_internal_set_error("short write"); return TRB_IO; }
+    return TRB_OK;
+}
