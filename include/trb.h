@@ -26,7 +26,7 @@
 extern "C" {
 #endif
 
-#define TRB_ABI_VERSION 3u
+#define TRB_ABI_VERSION 4u
 
 typedef enum trb_status {
     TRB_OK = 0,
@@ -109,7 +109,21 @@ typedef struct trb_mesh {
     const uint32_t* indices;
 } trb_mesh;
 
-enum { /* material types (src/material/), constant textures only (texture/mod.rs) */
+/* texture::Image / texture::AnimatedImage (src/texture/image.rs:36-48, animated_image.rs): what scene.rs:317-394 builds for
+ * "image", "animated_image" and "movie" textures. A frame is RGBA8 with the semantics of image::DynamicImage::get_pixel
+ * (grey -> (l, l, l, 255), RGB -> alpha 255), row-major from the top; one frame = Image, two or more = AnimatedImage whose
+ * frames carry their keyframe times in the order given. */
+typedef struct trb_image {
+    uint32_t width, height;
+    const uint8_t* rgba8; /* width * height * 4 bytes */
+    float time;
+    uint32_t pad;
+} trb_image;
+typedef struct trb_texture {
+    uint32_t first_image, n_images; /* images[first_image .. first_image + n_images) */
+} trb_texture;
+
+enum { /* material types (src/material/); every colour / scalar parameter is a constant or a texture (texture/mod.rs) */
     TRB_MAT_MATTE = 0,          /* c0 = diffuse, roughness (degrees; 0 => Lambertian) */
     TRB_MAT_PLASTIC = 1,        /* c0 = diffuse, c1 = gloss, roughness                */
     TRB_MAT_METAL = 2,          /* c0 = refractive_index, c1 = absorption_coefficient, roughness */
@@ -125,6 +139,10 @@ typedef struct trb_material {
     float roughness;
     float eta;
     uint32_t merl;
+    /* LoadedTextures::find_color / find_scalar (scene.rs:45-87): a parameter given as a texture NAME in the JSON is sampled at the
+     * hit's (u, v, time) in Material::bsdf. tex[k] = 1 + index into trb_scene_desc.textures, 0 = the constant above;
+     * k: 0 = c0, 1 = c1 (sample_color), 2 = roughness, 3 = eta (sample_f32). */
+    uint32_t tex[4];
 } trb_material;
 
 #define TRB_MERL_N_THETA_H 90u
@@ -178,6 +196,8 @@ typedef struct trb_scene_desc {
     uint32_t n_materials; const trb_material* materials;
     uint32_t n_merl;      const float* const* merl_tables; /* each TRB_MERL_TABLE_FLOATS floats */
     uint32_t n_fov_floats; const float* fov_floats;
+    uint32_t n_textures;  const trb_texture* textures;
+    uint32_t n_images;    const trb_image* images;
 } trb_scene_desc;
 
 /* ---------------------------------------------------------------------------------

@@ -215,6 +215,7 @@ struct orc_scene {
     SceneShade shade;
     std::vector<Mesh*> meshes;
     std::vector<std::vector<float>> merl;
+    TextureSet textures;
     std::vector<Camera> cameras;
     int active_camera = -1;
     RenderTarget rt;
@@ -315,7 +316,24 @@ int orc_scene_create(const trb_scene_desc* d, orc_scene** out) {
         Material mat; mat.type = tm.type; mat.c0 = Col(tm.c0[0], tm.c0[1], tm.c0[2]); mat.c1 = Col(tm.c1[0], tm.c1[1], tm.c1[2]);
         mat.roughness = tm.roughness; mat.eta = tm.eta;
         if (tm.type == TRB_MAT_MERL) mat.merl = s->merl[tm.merl].data();
+        for (int k = 0; k < 4; ++k) {
+            mat.tex[k] = tm.tex[k];
+            if (tm.tex[k] > d->n_textures) { delete s; g_err = "texture index out of range"; return TRB_INVALID_ARG; }
+        }
+        mat.textures = &s->textures;
         s->shade.materials.push_back(mat);
+    }
+    for (uint32_t t = 0; t < d->n_textures; ++t) {
+        const trb_texture& tt = d->textures[t];
+        if (tt.n_images == 0 || (uint64_t)tt.first_image + tt.n_images > d->n_images) { delete s; g_err = "texture image range out of bounds"; return TRB_INVALID_ARG; }
+        s->textures.tex.push_back(tt);
+    }
+    for (uint32_t i = 0; i < d->n_images; ++i) {
+        const trb_image& ti = d->images[i];
+        if (ti.width == 0 || ti.height == 0 || !ti.rgba8) { delete s; g_err = "empty image"; return TRB_INVALID_ARG; }
+        TexImage im; im.w = ti.width; im.h = ti.height; im.time = ti.time;
+        im.px.assign(ti.rgba8, ti.rgba8 + (size_t)ti.width * ti.height * 4);
+        s->textures.img.push_back(std::move(im));
     }
     for (uint32_t i = 0; i < d->n_instances; ++i) {
         const trb_instance& ti = d->instances[i];

@@ -319,14 +319,89 @@ struct BSDF {
     }
 };
 
+/* ---- textures (texture/mod.rs:21-41 bilinear_interpolate, image.rs:14-48, animated_image.rs:18-60) ------------------ */
+struct TexImage { uint32_t w = 0, h = 0; std::vector<uint8_t> px; float time = 0.0f; };
+struct TextureSet {
+    std::vector<trb_texture> tex;
+    std::vector<TexImage> img;
+    static uint32_t clampu(uint32_t x, uint32_t hi) { return x > hi ? hi : x; }
+    static float get_float(const TexImage& im, uint32_t x, uint32_t y) { /* Image::get_float: channel 0 */
+        x = clampu(x, im.w - 1); y = clampu(y, im.h - 1);
+        return (float)im.px[4 * ((size_t)y * im.w + x)] / 255.0f;
+    }
+    static Col get_color(const TexImage& im, uint32_t x, uint32_t y) { /* Image::get_color (alpha is carried by Colorf but never read by a BxDF) */
+        x = clampu(x, im.w - 1); y = clampu(y, im.h - 1);
+        const uint8_t* p = &im.px[4 * ((size_t)y * im.w + x)];
+        return Col((float)p[0] / 255.0f, (float)p[1] / 255.0f, (float)p[2] / 255.0f);
+    }
+    static float image_f32(const TexImage& im, float u, float v) { /* Image::sample_f32 */
+        float x = u * (float)im.w, y = v * (float)im.h;
+        uint32_t x0 = f2u(x), y0 = f2u(y);
+        float s00 = get_float(im, x0, y0), s10 = get_float(im, x0 + 1, y0), s01 = get_float(im, x0, y0 + 1), s11 = get_float(im, x0 + 1, y0 + 1);
+        float sx = x - (float)x0, sy = y - (float)y0;
+        return s00 * (1.0f - sx) * (1.0f - sy) + s10 * sx * (1.0f - sy) + s01 * (1.0f - sx) * sy + s11 * sx * sy;
+    }
+    static Col image_color(const TexImage& im, float u, float v) { /* Image::sample_color */
+        float x = u * (float)im.w, y = v * (float)im.h;
+        uint32_t x0 = f2u(x), y0 = f2u(y);
+        Col s00 = get_color(im, x0, y0), s10 = get_color(im, x0 + 1, y0), s01 = get_color(im, x0, y0 + 1), s11 = get_color(im, x0 + 1, y0 + 1);
+        float sx = x - (float)x0, sy = y - (float)y0;
+        return s00 * (1.0f - sx) * (1.0f - sy) + s10 * sx * (1.0f - sy) + s01 * (1.0f - sx) * sy + s11 * sx * sy;
+    }
+    /* AnimatedImage::active_keyframes (animated_image.rs:23-37): binary search over the keyframe times */
+    void active(const trb_texture& t, float time, uint32_t& lo, int& hi) const {
+        uint32_t a = 0, b = t.n_images; /* first index whose time is not < `time` */
+        while (a < b) { uint32_t m = (a + b) / 2; if (img[t.first_image + m].time < time) a = m + 1; else b = m; }
+        if (a < t.n_images && img[t.first_image + a].time == time) { lo = a; hi = -1; }
+        else if (a == t.n_images) { lo = a - 1; hi = -1; }
+        else if (a == 0) { lo = 0; hi = -1; }
+        else { lo = a - 1; hi = (int)a; }
+    }
+    float sample_f32(uint32_t ti, float u, float v, float time) const {
+        const trb_texture& t = tex[ti];
+        if (t.n_images == 1) return image_f32(img[t.first_image], u, v);
+        uint32_t lo; int hi;
+        active(t, time, lo, hi);
+        const TexImage& a = img[t.first_image + lo];
+        if (hi < 0) return image_f32(a, u, v);
+        const TexImage& b = img[t.first_image + hi];
+        float x = (time - a.time) / (b.time - a.time);
+        return image_f32(a, u, v) * (1.0f - x) + image_f32(b, u, v) * x; /* linalg::lerp */
+    }
+    Col sample_color(uint32_t ti, float u, float v, float time) const {
+        const trb_texture& t = tex[ti];
+        if (t.n_images == 1) return image_color(img[t.first_image], u, v);
+        uint32_t lo; int hi;
+        active(t, time, lo, hi);
+        const TexImage& a = img[t.first_image + lo];
+        if (hi < 0) return image_color(a, u, v);
+        const TexImage& b = img[t.first_image + hi];
+        float x = (time - a.time) / (b.time - a.time);
+        return image_color(a, u, v) * (1.0f - x) + image_color(b, u, v) * x;
+    }
+};
+
 struct Material {
     uint32_t type = 0;
     Col c0, c1;
     float roughness = 0, eta = 1;
     const float* merl = nullptr;
+    uint32_t tex[4] = {0, 0, 0, 0};      /* 1 + texture index bound to c0 / c1 / roughness / eta, 0 = constant */
+    const TextureSet* textures = nullptr;
 
-    /* Material::bsdf (material/{matte:52,plastic:59,metal:56,specular_metal:49,glass:51,rough_glass:57,merl:88}.rs) */
+    /* Material::bsdf (material/{matte:52,plastic:59,metal:56,specular_metal:49,glass:51,rough_glass:57,merl:88}.rs): every parameter is
+     * texture.sample_color / sample_f32(hit.dg.u, hit.dg.v, hit.dg.time); constants return themselves */
     void bsdf(const DG& dg, BSDF& out) const {
+        if (tex[0] | tex[1] | tex[2] | tex[3]) {
+            Material m = *this;
+            m.tex[0] = m.tex[1] = m.tex[2] = m.tex[3] = 0;
+            if (tex[0]) m.c0 = textures->sample_color(tex[0] - 1, dg.u, dg.v, dg.time);
+            if (tex[1]) m.c1 = textures->sample_color(tex[1] - 1, dg.u, dg.v, dg.time);
+            if (tex[2]) m.roughness = textures->sample_f32(tex[2] - 1, dg.u, dg.v, dg.time);
+            if (tex[3]) m.eta = textures->sample_f32(tex[3] - 1, dg.u, dg.v, dg.time);
+            m.bsdf(dg, out);
+            return;
+        }
         out.n_lobes = 0; out.eta = 1.0f;
         auto push = [&](const Lobe& l) { out.lobes[out.n_lobes++] = l; };
         switch (type) {

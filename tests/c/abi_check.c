@@ -2,7 +2,7 @@
  *
  *   abi_check layout                  prints sizeof / offsetof of every ABI struct as "struct.field offset" lines; the Python test
  *                                     compares them with the ctypes mirrors (tray_rust_b200/_ffi.py) and with the Rust #[repr(C)]
- *                                     declarations documented in INTEGRATION.md. The _Static_asserts pin ABI v3's layout.
+ *                                     declarations documented in INTEGRATION.md. The _Static_asserts pin ABI v4's layout.
  *   abi_check render scene.json w h spp   the documented call sequence of INTEGRATION.md from C: trb_scene_load_json ->
  *                                     trb_render (sample_count = 0: the whole frame in one call) -> trb_film_to_srgb8.
  * What the reference does at this boundary: Exec::render(&mut Scene, &mut RenderTarget, &Config)
@@ -13,13 +13,14 @@
 #include <string.h>
 #include "trb.h"
 
-_Static_assert(TRB_ABI_VERSION == 3u, "layout below is ABI v3");
+_Static_assert(TRB_ABI_VERSION == 4u, "layout below is ABI v4");
 _Static_assert(sizeof(trb_keyframe) == 40, "trb_keyframe");
 _Static_assert(sizeof(trb_spline) == 20, "trb_spline");
 _Static_assert(sizeof(trb_color_key) == 20, "trb_color_key");
 _Static_assert(sizeof(trb_instance) == 40, "trb_instance");
 _Static_assert(sizeof(trb_mesh) == 40 && offsetof(trb_mesh, positions) == 8, "trb_mesh");
-_Static_assert(sizeof(trb_material) == 40, "trb_material");
+_Static_assert(sizeof(trb_material) == 56 && offsetof(trb_material, tex) == 40, "trb_material");
+_Static_assert(sizeof(trb_image) == 24 && offsetof(trb_image, rgba8) == 8 && sizeof(trb_texture) == 8, "trb_image / trb_texture");
 _Static_assert(sizeof(trb_camera) == 40, "trb_camera");
 _Static_assert(sizeof(trb_film) == 48, "trb_film");
 _Static_assert(sizeof(trb_integrator) == 12, "trb_integrator");
@@ -27,7 +28,7 @@ _Static_assert(sizeof(trb_render_cfg) == 44 && offsetof(trb_render_cfg, shard_in
 _Static_assert(sizeof(trb_stats) == 72 && offsetof(trb_stats, kernel_ms) == 64, "trb_stats: 8 x u64 + 2 x f32");
 _Static_assert(sizeof(trb_ray) == 32 && sizeof(trb_hit) == 16 && sizeof(trb_sample) == 20 && sizeof(trb_bvh_node) == 32, "ray / hit / sample / node records");
 _Static_assert(offsetof(trb_scene_desc, film) == 4 && offsetof(trb_scene_desc, integrator) == 52 && offsetof(trb_scene_desc, n_cameras) == 64 &&
-               offsetof(trb_scene_desc, cameras) == 72 && sizeof(trb_scene_desc) == 224, "trb_scene_desc");
+               offsetof(trb_scene_desc, cameras) == 72 && sizeof(trb_scene_desc) == 256, "trb_scene_desc");
 
 #define S(T) printf(#T " sizeof %zu\n", sizeof(T))
 #define F(T, f) printf(#T "." #f " %zu\n", offsetof(T, f))
@@ -39,7 +40,9 @@ static int layout(void) {
     S(trb_instance); F(trb_instance, kind); F(trb_instance, shape); F(trb_instance, p0); F(trb_instance, p1); F(trb_instance, mesh); F(trb_instance, material);
     F(trb_instance, spline_first); F(trb_instance, n_splines); F(trb_instance, emission_first); F(trb_instance, n_emission);
     S(trb_mesh); F(trb_mesh, n_verts); F(trb_mesh, n_tris); F(trb_mesh, positions); F(trb_mesh, normals); F(trb_mesh, texcoords); F(trb_mesh, indices);
-    S(trb_material); F(trb_material, type); F(trb_material, c0); F(trb_material, c1); F(trb_material, roughness); F(trb_material, eta); F(trb_material, merl);
+    S(trb_material); F(trb_material, type); F(trb_material, c0); F(trb_material, c1); F(trb_material, roughness); F(trb_material, eta); F(trb_material, merl); F(trb_material, tex);
+    S(trb_image); F(trb_image, width); F(trb_image, height); F(trb_image, rgba8); F(trb_image, time); F(trb_image, pad);
+    S(trb_texture); F(trb_texture, first_image); F(trb_texture, n_images);
     S(trb_camera); F(trb_camera, spline_first); F(trb_camera, n_splines); F(trb_camera, fov); F(trb_camera, shutter_size); F(trb_camera, active_at);
     F(trb_camera, fov_degree); F(trb_camera, n_fov_ctrl); F(trb_camera, fov_ctrl_first); F(trb_camera, n_fov_knots); F(trb_camera, fov_knot_first);
     S(trb_film); F(trb_film, width); F(trb_film, height); F(trb_film, samples); F(trb_film, frames); F(trb_film, start_frame); F(trb_film, end_frame);
@@ -50,6 +53,7 @@ static int layout(void) {
     F(trb_scene_desc, splines); F(trb_scene_desc, n_keyframes); F(trb_scene_desc, keyframes); F(trb_scene_desc, n_knots); F(trb_scene_desc, knots);
     F(trb_scene_desc, n_color_keys); F(trb_scene_desc, color_keys); F(trb_scene_desc, n_meshes); F(trb_scene_desc, meshes); F(trb_scene_desc, n_materials);
     F(trb_scene_desc, materials); F(trb_scene_desc, n_merl); F(trb_scene_desc, merl_tables); F(trb_scene_desc, n_fov_floats); F(trb_scene_desc, fov_floats);
+    F(trb_scene_desc, n_textures); F(trb_scene_desc, textures); F(trb_scene_desc, n_images); F(trb_scene_desc, images);
     S(trb_render_cfg); F(trb_render_cfg, spp); F(trb_render_cfg, sample_first); F(trb_render_cfg, sample_count); F(trb_render_cfg, block_start);
     F(trb_render_cfg, block_count); F(trb_render_cfg, current_frame); F(trb_render_cfg, seed); F(trb_render_cfg, flags); F(trb_render_cfg, shard_index);
     F(trb_render_cfg, shard_count); F(trb_render_cfg, shard_chunk);

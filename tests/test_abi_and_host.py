@@ -27,7 +27,7 @@ def test_library_exports_every_declared_symbol(trb):
 
 def test_struct_layouts_match_the_header():
     assert C.sizeof(F.Ray) == 32 and C.sizeof(F.Hit) == 16 and C.sizeof(F.Sample) == 20 and C.sizeof(F.BvhNode) == 32
-    assert C.sizeof(F.Keyframe) == 40 and C.sizeof(F.Instance) == 40 and C.sizeof(F.Material) == 40
+    assert C.sizeof(F.Keyframe) == 40 and C.sizeof(F.Instance) == 40 and C.sizeof(F.Material) == 56
     assert F.RAY_DTYPE.itemsize == 32 and F.HIT_DTYPE.itemsize == 16 and F.SAMPLE_DTYPE.itemsize == 20 and F.NODE_DTYPE.itemsize == 32
     assert C.sizeof(F.Stats) == 8 * 8 + 8
 
@@ -170,12 +170,12 @@ def _build_abi_check(tmp_path):
 
 
 CTYPES_OF = {"trb_keyframe": F.Keyframe, "trb_spline": F.Spline, "trb_color_key": F.ColorKey, "trb_instance": F.Instance, "trb_mesh": F.Mesh,
-             "trb_material": F.Material, "trb_camera": F.Camera, "trb_film": F.Film, "trb_integrator": F.Integrator, "trb_scene_desc": F.SceneDesc,
+             "trb_material": F.Material, "trb_image": F.Image, "trb_texture": F.Texture, "trb_camera": F.Camera, "trb_film": F.Film, "trb_integrator": F.Integrator, "trb_scene_desc": F.SceneDesc,
              "trb_render_cfg": F.RenderCfg, "trb_stats": F.Stats, "trb_ray": F.Ray, "trb_hit": F.Hit, "trb_sample": F.Sample, "trb_bvh_node": F.BvhNode}
 
 
 def test_plain_c_caller_layout_matches_ctypes_and_the_documented_rust_binding(tmp_path):
-    """A C11 translation unit including only include/trb.h: its _Static_asserts pin ABI v3; every sizeof / offsetof it prints
+    """A C11 translation unit including only include/trb.h: its _Static_asserts pin ABI v4; every sizeof / offsetof it prints
     must equal the ctypes mirror, and the #[repr(C)] structs INTEGRATION.md documents for the Rust side must list the same
     fields in the same order (round 1 shipped a Rust TrbRenderCfg three fields short)."""
     import subprocess

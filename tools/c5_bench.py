@@ -26,7 +26,8 @@ dev = torch.device("cuda:0")
 film = torch.zeros(H, W, 4, dtype=torch.float32, device=dev)
 stats = torch.zeros(10, dtype=torch.int64, device=dev)
 
-for name, frame in (("c5_tr15.json", 300), ("c5_tr15_like.json", 12)):
+QUICK = "--quick" in sys.argv   # one scene, table on only (for ncu launch lists)
+for name, frame in ((("c5_tr15.json", 300),) if QUICK else (("c5_tr15.json", 300), ("c5_tr15_like.json", 12))):
     d = C.POINTER(F.SceneDesc)()
     assert lib.trb_desc_load_json(os.path.join(SCENES, name).encode(), W, H, 2048, C.byref(d)) == 0, lib.trb_last_error()
     desc = d.contents
@@ -35,8 +36,8 @@ for name, frame in (("c5_tr15.json", 300), ("c5_tr15_like.json", 12)):
     g.update_frame(frame, frame * step, (frame + 1) * step); o.update_frame(frame, frame * step, (frame + 1) * step)
     kw = dict(block_start=12000, block_count=48, sample_first=0, sample_count=2, seed=1)
     os_, _ = o.render_samples(**kw)
-    for table in (1, 0):
-        g.set_option("anim.table", table)
+    for table, split, occ in (((1, 0, 4),) if QUICK else ((1, 0, 4), (1, 0, 3), (1, 1, 4), (0, 0, 4))):
+        g.set_option("anim.table", table); g.set_option("shade.split", split); g.set_option("shade.anim_occupancy", occ)
         parity = g.render_samples(**kw)[0].tobytes() == os_.tobytes()
         g.render_device(film.data_ptr(), stats.data_ptr(), None, spp=2048, sample_first=0, sample_count=SPP_STEP, seed=1)
         torch.cuda.synchronize(); stats.zero_()
@@ -48,7 +49,7 @@ for name, frame in (("c5_tr15.json", 300), ("c5_tr15_like.json", 12)):
         ms = e0.elapsed_time(e1)
         s = stats.cpu().numpy()
         print(json.dumps({"workload": "%s 1920x1080 frame %d (%d instances, %d meshes, %d MERL tables), 2 passes x %d spp" % (name, frame, desc.n_instances, desc.n_meshes, desc.n_merl, SPP_STEP),
-                          "per_path_transform_table": bool(table), "bit_exact_vs_oracle_on_48_blocks": bool(parity), "mrays_s": float(s[1:5].sum()) / ms / 1e3,
+                          "per_path_transform_table": bool(table), "split_shade": bool(split), "shade_ctas_per_sm": occ, "bit_exact_vs_oracle_on_48_blocks": bool(parity), "mrays_s": float(s[1:5].sum()) / ms / 1e3,
                           "msamples_s": float(s[0]) / ms / 1e3, "ms_per_pass": ms / 2,
                           "rays": {"primary": int(s[1]), "shadow": int(s[2]), "mis": int(s[3]), "continuation": int(s[4])}}), flush=True)
     g.close(); o.close()

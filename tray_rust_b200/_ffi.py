@@ -13,7 +13,7 @@ import os
 _HERE = os.path.dirname(os.path.abspath(__file__))
 REPO = os.path.dirname(_HERE)
 
-TRB_ABI_VERSION = 3
+TRB_ABI_VERSION = 4
 TRB_OK, TRB_INVALID_ARG, TRB_CUDA, TRB_OOM, TRB_UNSUPPORTED, TRB_IO, TRB_NO_DEVICE, TRB_NCCL = range(8)
 INST_RECEIVER, INST_EMITTER_AREA, INST_EMITTER_POINT = 0, 1, 2
 SHAPE_NONE, SHAPE_SPHERE, SHAPE_DISK, SHAPE_RECT, SHAPE_MESH = 0, 1, 2, 3, 4
@@ -50,8 +50,16 @@ class Mesh(C.Structure):
                 ("texcoords", C.POINTER(f32)), ("indices", C.POINTER(u32))]
 
 
+class Image(C.Structure):
+    _fields_ = [("width", u32), ("height", u32), ("rgba8", C.POINTER(C.c_uint8)), ("time", f32), ("pad", u32)]
+
+
+class Texture(C.Structure):
+    _fields_ = [("first_image", u32), ("n_images", u32)]
+
+
 class Material(C.Structure):
-    _fields_ = [("type", u32), ("c0", f32 * 3), ("c1", f32 * 3), ("roughness", f32), ("eta", f32), ("merl", u32)]
+    _fields_ = [("type", u32), ("c0", f32 * 3), ("c1", f32 * 3), ("roughness", f32), ("eta", f32), ("merl", u32), ("tex", u32 * 4)]
 
 
 class Camera(C.Structure):
@@ -81,7 +89,9 @@ class SceneDesc(C.Structure):
                 ("n_meshes", u32), ("meshes", C.POINTER(Mesh)),
                 ("n_materials", u32), ("materials", C.POINTER(Material)),
                 ("n_merl", u32), ("merl_tables", C.POINTER(C.POINTER(f32))),
-                ("n_fov_floats", u32), ("fov_floats", C.POINTER(f32))]
+                ("n_fov_floats", u32), ("fov_floats", C.POINTER(f32)),
+                ("n_textures", u32), ("textures", C.POINTER(Texture)),
+                ("n_images", u32), ("images", C.POINTER(Image))]
 
 
 class RenderCfg(C.Structure):

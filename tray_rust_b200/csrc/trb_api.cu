@@ -167,6 +167,7 @@ struct Tuning {
     int sort = 0;              // ray queues: 0 = path order; 1 / 2 = counting sort by (octant, origin cell) / (cell, octant) before each trace round (measured: -1.5 % trace time, +10 % step time on C4)
     int sort_bits = 5;         // bits per axis of the origin cell grid
     int sort_min_round = 1;    // first bounce round whose queues are sorted (round 0 = primary rays, already coherent)
+    int shade_anim_occ = 4;    // keyframed shade kernel variant: resident CTAs per SM it is compiled for (3 or 4)
     int frame_device = 1;      // Scene::update_frame on the device (instance transforms, animation bounds, TLAS SAH build); 0 = on the host
     int anim_table = 1;        // keyframed scenes: evaluate each keyframed instance's transform once per path (0 = per ray per instance, like the reference)
     int shade_split = 0;       // shading as three kernels (surface | direct light | BSDF sample) instead of one (measured equal on C4)
@@ -326,7 +327,16 @@ trb_status validate(const trb_scene_desc* d) {
     for (uint32_t i = 0; i < d->n_materials; ++i) {
         if (d->materials[i].type > TRB_MAT_MERL) return fail(TRB_INVALID_ARG, "unrecognized material type");
         if (d->materials[i].type == TRB_MAT_MERL && d->materials[i].merl >= d->n_merl) return fail(TRB_INVALID_ARG, "merl table index out of range");
+        for (int k = 0; k < 4; ++k) if (d->materials[i].tex[k] > d->n_textures) return fail(TRB_INVALID_ARG, "texture index out of range");
     }
+    uint64_t texels = 0;
+    for (uint32_t i = 0; i < d->n_textures; ++i)
+        if (d->textures[i].n_images == 0 || (uint64_t)d->textures[i].first_image + d->textures[i].n_images > d->n_images) return fail(TRB_INVALID_ARG, "texture image range out of bounds");
+    for (uint32_t i = 0; i < d->n_images; ++i) {
+        if (d->images[i].width == 0 || d->images[i].height == 0 || !d->images[i].rgba8) return fail(TRB_INVALID_ARG, "empty image");
+        texels += (uint64_t)d->images[i].width * d->images[i].height;
+    }
+    if (texels >= (1ull << 32)) return fail(TRB_UNSUPPORTED, "more than 2^32 texels of image textures");
     for (uint32_t i = 0; i < d->n_meshes; ++i) {
         const trb_mesh& m = d->meshes[i];
         if (m.n_tris == 0 || m.n_verts == 0) return fail(TRB_INVALID_ARG, "empty mesh");
@@ -514,9 +524,10 @@ trb_status launch_wavefront(trb_scene* s, const trb::RenderParams& rp, uint32_t 
             continue;
         }
         // (occupancy 5 / 6 variants of the shade kernel were measured 1-2 % slower: spills outweigh the extra warps)
-        if (anim) {
-            if (mode == 0) trb::k_wf_shade<0, true, 3><<<shade_grid, 128, 0, st>>>(s->ds, rp, wf, round);
-            else trb::k_wf_shade<1, true, 3><<<shade_grid, 128, 0, st>>>(s->ds, rp, wf, round);
+        if (anim) { // keyframed variant: 168 registers at 3 CTAs per SM, or capped to 128 (some spills) at 4
+            if (mode != 0) trb::k_wf_shade<1, true, 3><<<shade_grid, 128, 0, st>>>(s->ds, rp, wf, round);
+            else if (tu.shade_anim_occ >= 4) trb::k_wf_shade<0, true, 4><<<shade_grid, 128, 0, st>>>(s->ds, rp, wf, round);
+            else trb::k_wf_shade<0, true, 3><<<shade_grid, 128, 0, st>>>(s->ds, rp, wf, round);
         } else if (mode == 0) trb::k_wf_shade<0, false, 4><<<shade_grid, 128, 0, st>>>(s->ds, rp, wf, round);
         else trb::k_wf_shade<1, false, 4><<<shade_grid, 128, 0, st>>>(s->ds, rp, wf, round);
         g_launches += 2;
@@ -616,6 +627,7 @@ trb_status trb_scene_set_option(trb_scene* s, const char* name, long long value)
     else if (k == "shade.split") t.shade_split = (int)value;
     else if (k == "anim.table") t.anim_table = (int)value;
     else if (k == "frame.device") t.frame_device = (int)value;
+    else if (k == "shade.anim_occupancy") t.shade_anim_occ = (int)value;
     else if (k == "pass.graph") t.graph = (int)value;
     else if (k == "pass.paths") { if (value < 64) return fail(TRB_INVALID_ARG, "pass.paths must be >= 64"); t.pass_paths = (uint64_t)value; }
     else return fail(TRB_INVALID_ARG, "unknown option: " + k);
@@ -756,6 +768,7 @@ trb_status trb_scene_create(const trb_scene_desc* d, int device, trb_scene** out
         o.on_a = 1.0f - 0.5f * sigma / (sigma + 0.33f);
         o.on_b = 0.45f * sigma / (sigma + 0.09f);
         o.merl_off = m.type == TRB_MAT_MERL ? m.merl * TRB_MERL_TABLE_FLOATS : 0;
+        for (int k = 0; k < 4; ++k) o.tex[k] = m.tex[k];
     }
     trb::DMaterial* d_mats;
     CU(s->arena.upload(dmats.data(), dmats.size(), &d_mats));
@@ -764,6 +777,24 @@ trb_status trb_scene_create(const trb_scene_desc* d, int device, trb_scene** out
     for (uint32_t i = 0; i < d->n_merl; ++i)
         CU(cudaMemcpy(d_merl + (size_t)i * TRB_MERL_TABLE_FLOATS, d->merl_tables[i], sizeof(float) * TRB_MERL_TABLE_FLOATS, cudaMemcpyHostToDevice));
 
+    { // image textures: every frame's RGBA8 texels in one array (texture/image.rs)
+        std::vector<trb::DImage> dimg(d->n_images);
+        std::vector<trb::DTexture> dtex(d->n_textures);
+        std::vector<uchar4> tx;
+        for (uint32_t i = 0; i < d->n_images; ++i) {
+            const trb_image& im = d->images[i];
+            dimg[i].width = im.width; dimg[i].height = im.height; dimg[i].offset = (uint32_t)tx.size(); dimg[i].time = im.time;
+            const size_t n = (size_t)im.width * im.height;
+            tx.resize(tx.size() + n);
+            std::memcpy(tx.data() + dimg[i].offset, im.rgba8, n * 4);
+        }
+        for (uint32_t i = 0; i < d->n_textures; ++i) { dtex[i].first_image = d->textures[i].first_image; dtex[i].n_images = d->textures[i].n_images; }
+        trb::DImage* d_img = nullptr; trb::DTexture* d_tex = nullptr; uchar4* d_tx = nullptr;
+        CU(s->arena.upload(dimg.data(), dimg.size(), &d_img));
+        CU(s->arena.upload(dtex.data(), dtex.size(), &d_tex));
+        CU(s->arena.upload(tx.data(), tx.size(), &d_tx));
+        s->ds.images = d_img; s->ds.textures = d_tex; s->ds.texels = d_tx; s->ds.n_textures = d->n_textures;
+    }
     std::vector<uint32_t> lights;
     for (uint32_t i = 0; i < d->n_instances; ++i) if (d->instances[i].kind != TRB_INST_RECEIVER) lights.push_back(i); // multithreaded.rs:33-38
     uint32_t* d_lights;

@@ -95,7 +95,12 @@ struct DMaterial {
     float on_a, on_b; // OrenNayar::new (oren_nayar.rs:26-34)
     uint32_t merl_off; // float offset into merl
     uint32_t pad;
+    uint32_t tex[4];   // 1 + texture index bound to c0 / c1 / roughness / eta (0 = the constant), LoadedTextures::find_color / find_scalar
 };
+
+// texture::Image / AnimatedImage frames (src/texture/image.rs, animated_image.rs): RGBA8 texels of all images in one array
+struct DImage { uint32_t width, height, offset; float time; }; // offset: first texel in DScene::texels
+struct DTexture { uint32_t first_image, n_images; };
 
 struct DCamera {
     float px_to_cam[16]; // proj_div_inv * raster_screen (camera.rs:152)
@@ -137,6 +142,11 @@ struct DScene {
     uint32_t has_anim; // any instance / camera / emission depends on time
     const uint32_t* anim_instances; // instance indices with DI_ANIM_XF, in instance order
     uint32_t n_anim_instances;
+    // image textures: sampled in Material::bsdf at the hit's (u, v, time)
+    const DTexture* textures;
+    const DImage* images;
+    const uchar4* texels;
+    uint32_t n_textures;
 };
 
 struct RenderParams {

@@ -603,7 +603,7 @@ __device__ __noinline__ bool scene_trace(const DScene& sc, Ray& ray, HitRec& hit
 // DifferentialGeometry of the final hit, transformed to world space (receiver.rs:36-41). Only the
 // members the integrator reads: p, n, ng, dp_du (u, v feed constant textures only; dp_dv only feeds n).
 // ------------------------------------------------------------------------------------------
-struct Surf { f3 p, n, ng, dp_du; };
+struct Surf { f3 p, n, ng, dp_du; float u, v; }; // u, v: only filled when the scene has image textures (DScene::n_textures)
 
 template <bool ANIM>
 __device__ __forceinline__ void surface_at(const DScene& sc, const Ray& ray, const HitRec& hit, Surf& s, float time, const float* xf_row = nullptr) {
@@ -630,6 +630,7 @@ __device__ __forceinline__ void surface_at(const DScene& sc, const Ray& ray, con
         ng = n;                                      // with_normal: n == ng
         const float tax = __ldg(T + 2 * ia), tay = __ldg(T + 2 * ia + 1), tbx = __ldg(T + 2 * ib), tby = __ldg(T + 2 * ib + 1);
         const float tcx = __ldg(T + 2 * ic), tcy = __ldg(T + 2 * ic + 1);
+        s.u = b0 * tax + b1 * tbx + b2 * tcx; s.v = b0 * tay + b1 * tby + b2 * tcy;        // texcoord = bary-lerp (mesh.rs:178)
         const float du0 = tax - tcx, du1 = tbx - tcx, dv0 = tay - tcy, dv1 = tby - tcy; // mesh.rs:182-184
         const float det = du0 * dv1 - dv0 * du1;
         if (det == 0.0f) {
@@ -643,6 +644,12 @@ __device__ __forceinline__ void surface_at(const DScene& sc, const Ray& ray, con
     } else if (shape == TRB_SHAPE_SPHERE) {
         n = unit(p); ng = n;                                            // sphere.rs:58, with_normal
         dp_du = mk(-TRB_PI * 2.0f * p.y, TRB_PI * 2.0f * p.x, 0.0f);    // sphere.rs:75
+        if (sc.n_textures) { // sphere.rs:59-73
+            const float radius = __ldg(&in.p0);
+            const float theta = dacos(clampf(p.z / radius, -1.0f, 1.0f));
+            const float uu = datan2(p.x, p.y) / (2.0f * TRB_PI);
+            s.u = uu < 0.0f ? uu + 1.0f : uu; s.v = theta / TRB_PI;
+        }
     } else if (shape == TRB_SHAPE_DISK) {
         const float radius = __ldg(&in.p0), inner = __ldg(&in.p1);
         const float hr = sqrtf(p.x * p.x + p.y * p.y);
@@ -650,12 +657,18 @@ __device__ __forceinline__ void surface_at(const DScene& sc, const Ray& ray, con
         const f3 dp_dv = ((inner - radius) / hr) * mk(p.x, p.y, 0.0f);  // disk.rs:72
         n = unit(cross3(dp_du, dp_dv));                                  // DifferentialGeometry::new
         ng = unit(mk(0.0f, 0.0f, 1.0f));
+        if (sc.n_textures) { // disk.rs:60-70
+            float phi = datan2(p.y, p.x);
+            if (phi < 0.0f) phi += TRB_PI * 2.0f;
+            s.u = phi / (2.0f * TRB_PI); s.v = 1.0f - (hr - inner) / (radius - inner);
+        }
     } else {
         const float hw = __ldg(&in.p0) / 2.0f, hh = __ldg(&in.p1) / 2.0f;
         dp_du = mk(hw * 2.0f, 0.0f, 0.0f);                               // rectangle.rs:57-58
         const f3 dp_dv = mk(0.0f, hh * 2.0f, 0.0f);
         n = unit(cross3(dp_du, dp_dv));
         ng = unit(mk(0.0f, 0.0f, 1.0f));
+        s.u = (p.x + hw) / (2.0f * hw); s.v = (p.y + hh) / (2.0f * hh);  // rectangle.rs:54-55
     }
     s.p = xf_point(w, p);
     s.n = xf_normal_t(m, n);
@@ -706,6 +719,78 @@ __device__ __forceinline__ void load_mat(const DMaterial& m, Mat& o) {
     o.c1 = mk(__ldg(&m.c1[0]), __ldg(&m.c1[1]), __ldg(&m.c1[2]));
     o.roughness = __ldg(&m.roughness); o.width = __ldg(&m.width); o.eta = __ldg(&m.eta);
     o.on_a = __ldg(&m.on_a); o.on_b = __ldg(&m.on_b); o.merl_off = __ldg(&m.merl_off);
+}
+// ---- image textures (texture/mod.rs:21-41 bilinear_interpolate, image.rs:14-48, animated_image.rs:18-60) ----
+__device__ __forceinline__ f3 tex_texel(const DScene& sc, const DImage& im, uint32_t x, uint32_t y) { // Image::get_color: clamp to the last texel, c / 255
+    x = min(x, im.width - 1u); y = min(y, im.height - 1u);
+    const uchar4 t = __ldg(&sc.texels[im.offset + y * im.width + x]);
+    return mk((float)t.x / 255.0f, (float)t.y / 255.0f, (float)t.z / 255.0f);
+}
+__device__ f3 tex_image_color(const DScene& sc, const DImage& im, float u, float v) { // Image::sample_color
+    const float x = u * (float)im.width, y = v * (float)im.height;
+    const uint32_t x0 = f2u(x), y0 = f2u(y);
+    const f3 s00 = tex_texel(sc, im, x0, y0), s10 = tex_texel(sc, im, x0 + 1u, y0), s01 = tex_texel(sc, im, x0, y0 + 1u), s11 = tex_texel(sc, im, x0 + 1u, y0 + 1u);
+    const float sx = x - (float)x0, sy = y - (float)y0;
+    return s00 * (1.0f - sx) * (1.0f - sy) + s10 * sx * (1.0f - sy) + s01 * (1.0f - sx) * sy + s11 * sx * sy;
+}
+__device__ float tex_image_f32(const DScene& sc, const DImage& im, float u, float v) { // Image::sample_f32: channel 0
+    const float x = u * (float)im.width, y = v * (float)im.height;
+    const uint32_t x0 = f2u(x), y0 = f2u(y);
+    const float s00 = tex_texel(sc, im, x0, y0).x, s10 = tex_texel(sc, im, x0 + 1u, y0).x, s01 = tex_texel(sc, im, x0, y0 + 1u).x, s11 = tex_texel(sc, im, x0 + 1u, y0 + 1u).x;
+    const float sx = x - (float)x0, sy = y - (float)y0;
+    return s00 * (1.0f - sx) * (1.0f - sy) + s10 * sx * (1.0f - sy) + s01 * (1.0f - sx) * sy + s11 * sx * sy;
+}
+// AnimatedImage::active_keyframes (animated_image.rs:23-37): lo and, between two keyframes, hi (else -1)
+__device__ __forceinline__ void tex_active(const DScene& sc, const DTexture& t, float time, uint32_t& lo, int& hi) {
+    uint32_t a = 0, b = t.n_images;
+    while (a < b) { const uint32_t m = (a + b) / 2; if (__ldg(&sc.images[t.first_image + m].time) < time) a = m + 1; else b = m; }
+    if (a < t.n_images && __ldg(&sc.images[t.first_image + a].time) == time) { lo = a; hi = -1; }
+    else if (a == t.n_images) { lo = a - 1; hi = -1; }
+    else if (a == 0) { lo = 0; hi = -1; }
+    else { lo = a - 1; hi = (int)a; }
+}
+__device__ f3 tex_sample_color(const DScene& sc, uint32_t ti, float u, float v, float time) {
+    const DTexture t = sc.textures[ti];
+    if (t.n_images == 1) return tex_image_color(sc, sc.images[t.first_image], u, v);
+    uint32_t lo; int hi;
+    tex_active(sc, t, time, lo, hi);
+    const DImage a = sc.images[t.first_image + lo];
+    if (hi < 0) return tex_image_color(sc, a, u, v);
+    const DImage b = sc.images[t.first_image + hi];
+    const float x = (time - a.time) / (b.time - a.time);
+    return tex_image_color(sc, a, u, v) * (1.0f - x) + tex_image_color(sc, b, u, v) * x; // linalg::lerp
+}
+__device__ float tex_sample_f32(const DScene& sc, uint32_t ti, float u, float v, float time) {
+    const DTexture t = sc.textures[ti];
+    if (t.n_images == 1) return tex_image_f32(sc, sc.images[t.first_image], u, v);
+    uint32_t lo; int hi;
+    tex_active(sc, t, time, lo, hi);
+    const DImage a = sc.images[t.first_image + lo];
+    if (hi < 0) return tex_image_f32(sc, a, u, v);
+    const DImage b = sc.images[t.first_image + hi];
+    const float x = (time - a.time) / (b.time - a.time);
+    return tex_image_f32(sc, a, u, v) * (1.0f - x) + tex_image_f32(sc, b, u, v) * x;
+}
+// Material::bsdf's texture lookups: every parameter = texture.sample_*(hit.dg.u, hit.dg.v, hit.dg.time) (material/*.rs). Scenes without
+// image textures (n_textures == 0: a uniform branch) read the constants prepared at scene creation.
+__device__ __noinline__ void apply_textures(const DScene& sc, const DMaterial& dm, float u, float v, float time, Mat& o) {
+    const uint32_t t0 = __ldg(&dm.tex[0]), t1 = __ldg(&dm.tex[1]), t2 = __ldg(&dm.tex[2]), t3 = __ldg(&dm.tex[3]);
+    if (t0) o.c0 = tex_sample_color(sc, t0 - 1, u, v, time);
+    if (t1) o.c1 = tex_sample_color(sc, t1 - 1, u, v, time);
+    if (t3) o.eta = tex_sample_f32(sc, t3 - 1, u, v, time);
+    if (t2) {
+        o.roughness = tex_sample_f32(sc, t2 - 1, u, v, time);
+        o.width = fmaxf(o.roughness, 0.000001f);              // Beckmann::new (beckmann.rs:19-22)
+        float sigma = TRB_PI / 180.0f * o.roughness;          // OrenNayar::new (oren_nayar.rs:26-34), roughness in degrees
+        sigma *= sigma;
+        o.on_a = 1.0f - 0.5f * sigma / (sigma + 0.33f);
+        o.on_b = 0.45f * sigma / (sigma + 0.09f);
+    }
+}
+__device__ __forceinline__ void load_mat_at(const DScene& sc, uint32_t material, float u, float v, float time, Mat& o) {
+    const DMaterial& dm = sc.materials[material];
+    load_mat(dm, o);
+    if (sc.n_textures) apply_textures(sc, dm, u, v, time, o);
 }
 // The lobes Material::bsdf allocates, in allocation order (material/{matte:52,plastic:59,metal:56,
 // specular_metal:49,glass:51,rough_glass:57,merl:88}.rs). Returns false when lobe `i` does not exist.
@@ -1286,7 +1371,7 @@ __device__ __forceinline__ void shade_bounce(const DScene& sc, const Surf& s, ui
                                              uint32_t hsample, f3 throughput_in, float time, f3& illum, BounceOut& o, const float* xf_row = nullptr) {
     bounce_emission<ANIM>(sc, hit_inst, ray_d, first_ng, bounce, prev_specular, throughput_in, time, illum);
     Mat m;
-    load_mat(sc.materials[__ldg(&sc.instances[hit_inst].material)], m);
+    load_mat_at(sc, __ldg(&sc.instances[hit_inst].material), s.u, s.v, time, m);
     Frame fr;
     make_frame(s, fr);
     const f3 wo = -ray_d;
@@ -1976,7 +2061,7 @@ __device__ f3 whitted_illum(const DScene& sc, const Ray& ray, uint32_t depth, co
     surface_at<ANIM>(sc, ray, hit, s, time);
     const DInstance& in = sc.instances[hit.inst];
     Mat m;
-    load_mat(sc.materials[__ldg(&in.material)], m);
+    load_mat_at(sc, __ldg(&in.material), s.u, s.v, time, m);
     Frame fr;
     make_frame(s, fr);
     const f3 wo = -ray.d;
@@ -2078,9 +2163,9 @@ __device__ __forceinline__ void finish_sample(const DScene& sc, const RenderPara
         out->x = sx; out->y = sy; out->r = c.x; out->g = c.y; out->b = c.z;
     }
 }
-__device__ __forceinline__ void load_frame(const WfState& wf, uint32_t p, Frame& fr, uint32_t& inst) {
+__device__ __forceinline__ void load_frame(const WfState& wf, uint32_t p, Frame& fr, uint32_t& inst, float& u, float& v) {
     const float4 a = wf.f_p[p], n = wf.f_n[p], t = wf.f_t[p], b = wf.f_b[p];
-    fr.p = mk(a.x, a.y, a.z); inst = __float_as_uint(a.w);
+    fr.p = mk(a.x, a.y, a.z); inst = __float_as_uint(a.w); u = n.w; v = t.w;
     fr.n = mk(n.x, n.y, n.z); fr.tan = mk(t.x, t.y, t.z); fr.bitan = mk(b.x, b.y, b.z);
 }
 
@@ -2137,8 +2222,8 @@ __global__ void __launch_bounds__(128, MINB) k_wf_shade_a(const __grid_constant_
                     Frame fr;
                     make_frame(s, fr);
                     wf.f_p[p] = make_float4(fr.p.x, fr.p.y, fr.p.z, __uint_as_float(h.inst));
-                    wf.f_n[p] = make_float4(fr.n.x, fr.n.y, fr.n.z, 0.0f);
-                    wf.f_t[p] = make_float4(fr.tan.x, fr.tan.y, fr.tan.z, 0.0f);
+                    wf.f_n[p] = make_float4(fr.n.x, fr.n.y, fr.n.z, s.u); // .w: the hit's (u, v) for image textures
+                    wf.f_t[p] = make_float4(fr.tan.x, fr.tan.y, fr.tan.z, s.v);
                     wf.f_b[p] = make_float4(fr.bitan.x, fr.bitan.y, fr.bitan.z, 0.0f);
                     wf.illum[p] = make_float4(illum.x, illum.y, illum.z, 0.0f);
                     push_mid = true;
@@ -2167,12 +2252,12 @@ __global__ void __launch_bounds__(128, MINB) k_wf_shade_b(const __grid_constant_
         bool push_shadow = false, push_mis = false;
         if (i < n) {
             p = wf.q_mid[i];
-            Frame fr; uint32_t inst;
-            load_frame(wf, p, fr, inst);
+            Frame fr; uint32_t inst; float tu, tv;
+            load_frame(wf, p, fr, inst, tu, tv);
             const float4 c4 = wf.cont[p], th4 = wf.thr[p];
             const f3 wo = -mk(c4.x, c4.y, c4.z);
             Mat m;
-            load_mat(sc.materials[__ldg(&sc.instances[inst].material)], m);
+            load_mat_at(sc, __ldg(&sc.instances[inst].material), tu, tv, th4.w, m);
             const SampleId id = sample_id(sc, rp, p);
             const uint32_t hs = rng_absorb(rng_absorb(rng_seed(rp.seed), id.pixel), id.si);
             DirectSetup ds; uint32_t light;
@@ -2209,12 +2294,12 @@ __global__ void __launch_bounds__(128, MINB) k_wf_shade_c(const __grid_constant_
         f3 new_org = splat(0.0f);
         if (i < n) {
             p = wf.q_mid[i];
-            Frame fr; uint32_t inst;
-            load_frame(wf, p, fr, inst);
+            Frame fr; uint32_t inst; float tu, tv;
+            load_frame(wf, p, fr, inst, tu, tv);
             const float4 c4 = wf.cont[p], th4 = wf.thr[p];
             const f3 wo = -mk(c4.x, c4.y, c4.z);
             Mat m;
-            load_mat(sc.materials[__ldg(&sc.instances[inst].material)], m);
+            load_mat_at(sc, __ldg(&sc.instances[inst].material), tu, tv, th4.w, m);
             const SampleId id = sample_id(sc, rp, p);
             const uint32_t hs = rng_absorb(rng_absorb(rng_seed(rp.seed), id.pixel), id.si);
             ScatterOut so;

@@ -8,7 +8,9 @@
 #include <cmath>
 #include <cstdio>
 #include <cstring>
+#include <cstdlib>
 #include <fstream>
+#include <iterator>
 #include <map>
 #include <memory>
 #include <sstream>
@@ -366,6 +368,10 @@ struct DescOwner {
     std::vector<std::vector<float>> merl;
     std::vector<const float*> merl_ptrs;
     std::vector<float> fov_floats;
+    std::vector<trb_texture> textures;
+    std::vector<trb_image> images;
+    std::vector<std::vector<uint8_t>> image_data;
+    std::map<std::string, uint32_t> texture_names;
     std::map<std::string, uint32_t> material_names;
     std::map<std::string, std::map<std::string, uint32_t>> mesh_cache; // file -> model -> mesh index
     std::string dir;
@@ -403,13 +409,209 @@ std::pair<uint32_t, uint32_t> add_xf(DescOwner& o, const JVal& obj, const char* 
     return {first, (uint32_t)o.splines.size() - first};
 }
 
-void color_tex(const JVal& e, float out[3], const char* what) { // LoadedTextures::find_color (scene.rs:27-42), constants only
-    if (e.kind == JVal::Str) die(TRB_UNSUPPORTED, std::string("named (image) textures are not implemented: ") + what);
+// ---- image textures (scene.rs:317-394 load_textures; image::open) -------------------------------------------------------
+// PNG decoding (what `image::open` does for the formats this build reads): 8-bit grey / grey+alpha / RGB / palette / RGBA,
+// non-interlaced, expanded to RGBA8 like DynamicImage::get_pixel (grey -> l,l,l,255; RGB -> alpha 255). Own inflate (RFC 1951).
+struct BitReader {
+    const uint8_t* p; size_t n, pos = 0; uint32_t bitbuf = 0; int bitcnt = 0;
+    uint32_t bits(int k) { while (bitcnt < k) { if (pos >= n) die(TRB_IO, "truncated deflate stream"); bitbuf |= (uint32_t)p[pos++] << bitcnt; bitcnt += 8; } const uint32_t v = bitbuf & ((1u << k) - 1u); bitbuf >>= k; bitcnt -= k; return v; }
+};
+struct Huffman {
+    uint16_t count[16] = {0}, symbol[320] = {0};
+    void build(const uint8_t* len, int n) {
+        for (int i = 0; i < 16; ++i) count[i] = 0;
+        for (int i = 0; i < n; ++i) count[len[i]]++;
+        count[0] = 0;
+        uint16_t offs[16]; offs[1] = 0;
+        for (int i = 1; i < 15; ++i) offs[i + 1] = offs[i] + count[i];
+        for (int i = 0; i < n; ++i) if (len[i]) symbol[offs[len[i]]++] = (uint16_t)i;
+    }
+    int decode(BitReader& br) const {
+        int code = 0, first = 0, index = 0;
+        for (int len = 1; len <= 15; ++len) {
+            code |= (int)br.bits(1);
+            const int c = count[len];
+            if (code - c < first) return symbol[index + (code - first)];
+            index += c; first += c; first <<= 1; code <<= 1;
+        }
+        die(TRB_IO, "bad Huffman code in deflate stream");
+        return -1;
+    }
+};
+std::vector<uint8_t> inflate_zlib(const uint8_t* data, size_t n) {
+    if (n < 6) die(TRB_IO, "truncated zlib stream");
+    BitReader br{data + 2, n - 2};
+    std::vector<uint8_t> out;
+    static const uint16_t lbase[29] = {3,4,5,6,7,8,9,10,11,13,15,17,19,23,27,31,35,43,51,59,67,83,99,115,131,163,195,227,258};
+    static const uint16_t lext[29] = {0,0,0,0,0,0,0,0,1,1,1,1,2,2,2,2,3,3,3,3,4,4,4,4,5,5,5,5,0};
+    static const uint16_t dbase[30] = {1,2,3,4,5,7,9,13,17,25,33,49,65,97,129,193,257,385,513,769,1025,1537,2049,3073,4097,6145,8193,12289,16385,24577};
+    static const uint16_t dext[30] = {0,0,0,0,1,1,2,2,3,3,4,4,5,5,6,6,7,7,8,8,9,9,10,10,11,11,12,12,13,13};
+    for (bool last = false; !last;) {
+        last = br.bits(1) != 0;
+        const uint32_t type = br.bits(2);
+        if (type == 0) { // stored
+            br.bitbuf = 0; br.bitcnt = 0;
+            if (br.pos + 4 > br.n) die(TRB_IO, "truncated deflate stream");
+            const uint32_t len = br.p[br.pos] | (br.p[br.pos + 1] << 8);
+            br.pos += 4;
+            if (br.pos + len > br.n) die(TRB_IO, "truncated deflate stream");
+            out.insert(out.end(), br.p + br.pos, br.p + br.pos + len);
+            br.pos += len;
+            continue;
+        }
+        if (type == 3) die(TRB_IO, "bad deflate block type");
+        Huffman lit, dist;
+        uint8_t lens[320];
+        if (type == 1) {
+            for (int i = 0; i < 144; ++i) lens[i] = 8; for (int i = 144; i < 256; ++i) lens[i] = 9; for (int i = 256; i < 280; ++i) lens[i] = 7; for (int i = 280; i < 288; ++i) lens[i] = 8;
+            lit.build(lens, 288);
+            for (int i = 0; i < 30; ++i) lens[i] = 5;
+            dist.build(lens, 30);
+        } else {
+            const int nlen = (int)br.bits(5) + 257, ndist = (int)br.bits(5) + 1, ncode = (int)br.bits(4) + 4;
+            static const uint8_t order[19] = {16,17,18,0,8,7,9,6,10,5,11,4,12,3,13,2,14,1,15};
+            uint8_t cl[19] = {0};
+            for (int i = 0; i < ncode; ++i) cl[order[i]] = (uint8_t)br.bits(3);
+            Huffman lc; lc.build(cl, 19);
+            for (int i = 0; i < nlen + ndist;) {
+                const int sym = lc.decode(br);
+                if (sym < 16) lens[i++] = (uint8_t)sym;
+                else {
+                    int rep; uint8_t v = 0;
+                    if (sym == 16) { if (i == 0) die(TRB_IO, "bad deflate lengths"); v = lens[i - 1]; rep = 3 + (int)br.bits(2); }
+                    else if (sym == 17) rep = 3 + (int)br.bits(3);
+                    else rep = 11 + (int)br.bits(7);
+                    if (i + rep > nlen + ndist) die(TRB_IO, "bad deflate lengths");
+                    while (rep--) lens[i++] = v;
+                }
+            }
+            lit.build(lens, nlen); dist.build(lens + nlen, ndist);
+        }
+        for (;;) {
+            const int sym = lit.decode(br);
+            if (sym < 256) out.push_back((uint8_t)sym);
+            else if (sym == 256) break;
+            else {
+                if (sym > 285) die(TRB_IO, "bad deflate symbol");
+                const uint32_t len = lbase[sym - 257] + br.bits(lext[sym - 257]);
+                const int ds = dist.decode(br);
+                if (ds > 29) die(TRB_IO, "bad deflate distance");
+                const uint32_t d = dbase[ds] + br.bits(dext[ds]);
+                if (d > out.size()) die(TRB_IO, "deflate distance too far back");
+                for (uint32_t k = 0; k < len; ++k) out.push_back(out[out.size() - d]);
+            }
+        }
+    }
+    return out;
+}
+void load_png(const std::string& path, uint32_t& w, uint32_t& h, std::vector<uint8_t>& rgba) {
+    std::ifstream f(path, std::ios::binary);
+    if (!f) die(TRB_IO, "Failed to load image file " + path);
+    std::vector<uint8_t> raw((std::istreambuf_iterator<char>(f)), std::istreambuf_iterator<char>());
+    static const uint8_t sig[8] = {0x89, 'P', 'N', 'G', 0x0d, 0x0a, 0x1a, 0x0a};
+    if (raw.size() < 8 || std::memcmp(raw.data(), sig, 8) != 0) die(TRB_UNSUPPORTED, "only PNG image textures are read by this build: " + path);
+    auto be32 = [&](size_t o) { return ((uint32_t)raw[o] << 24) | ((uint32_t)raw[o + 1] << 16) | ((uint32_t)raw[o + 2] << 8) | raw[o + 3]; };
+    uint32_t depth = 0, ctype = 0, interlace = 0;
+    std::vector<uint8_t> idat, plte, trns;
+    w = h = 0;
+    for (size_t o = 8; o + 12 <= raw.size();) {
+        const uint32_t n = be32(o);
+        if (o + 12 + (size_t)n > raw.size()) die(TRB_IO, "truncated PNG " + path);
+        const std::string ty(reinterpret_cast<const char*>(&raw[o + 4]), 4);
+        const uint8_t* d = &raw[o + 8];
+        if (ty == "IHDR") { if (n < 13) die(TRB_IO, "bad IHDR"); w = be32(o + 8); h = be32(o + 12); depth = d[8]; ctype = d[9]; interlace = d[12]; }
+        else if (ty == "PLTE") plte.assign(d, d + n);
+        else if (ty == "tRNS") trns.assign(d, d + n);
+        else if (ty == "IDAT") idat.insert(idat.end(), d, d + n);
+        else if (ty == "IEND") break;
+        o += 12 + (size_t)n;
+    }
+    if (w == 0 || h == 0 || w > 32768 || h > 32768) die(TRB_IO, "bad PNG dimensions in " + path);
+    if (depth != 8 || interlace != 0) die(TRB_UNSUPPORTED, "only 8-bit non-interlaced PNG textures are read by this build: " + path);
+    const int ch = ctype == 0 ? 1 : ctype == 2 ? 3 : ctype == 3 ? 1 : ctype == 4 ? 2 : ctype == 6 ? 4 : 0;
+    if (!ch) die(TRB_IO, "bad PNG colour type in " + path);
+    const std::vector<uint8_t> data = inflate_zlib(idat.data(), idat.size());
+    const size_t stride = (size_t)w * ch;
+    if (data.size() < (stride + 1) * h) die(TRB_IO, "truncated PNG image data in " + path);
+    std::vector<uint8_t> img(stride * h);
+    for (uint32_t y = 0; y < h; ++y) { // undo the scanline filters (PNG spec 9.2)
+        const uint8_t ft = data[(stride + 1) * y];
+        const uint8_t* in = &data[(stride + 1) * y + 1];
+        uint8_t* cur = &img[stride * y];
+        const uint8_t* up = y ? &img[stride * (y - 1)] : nullptr;
+        for (size_t x = 0; x < stride; ++x) {
+            const int a = x >= (size_t)ch ? cur[x - ch] : 0, b = up ? up[x] : 0, c = (up && x >= (size_t)ch) ? up[x - ch] : 0;
+            int v = in[x];
+            if (ft == 1) v += a;
+            else if (ft == 2) v += b;
+            else if (ft == 3) v += (a + b) >> 1;
+            else if (ft == 4) { const int pp = a + b - c, pa = std::abs(pp - a), pb = std::abs(pp - b), pc = std::abs(pp - c); v += (pa <= pb && pa <= pc) ? a : (pb <= pc ? b : c); }
+            else if (ft != 0) die(TRB_IO, "bad PNG filter type in " + path);
+            cur[x] = (uint8_t)v;
+        }
+    }
+    rgba.resize((size_t)w * h * 4);
+    for (size_t i = 0; i < (size_t)w * h; ++i) {
+        uint8_t* o = &rgba[4 * i];
+        const uint8_t* p = &img[i * ch];
+        if (ctype == 0) { o[0] = o[1] = o[2] = p[0]; o[3] = 255; }
+        else if (ctype == 2) { o[0] = p[0]; o[1] = p[1]; o[2] = p[2]; o[3] = 255; }
+        else if (ctype == 3) { const size_t k = p[0]; if (3 * k + 2 >= plte.size()) die(TRB_IO, "PNG palette index out of range in " + path); o[0] = plte[3 * k]; o[1] = plte[3 * k + 1]; o[2] = plte[3 * k + 2]; o[3] = k < trns.size() ? trns[k] : 255; }
+        else if (ctype == 4) { o[0] = o[1] = o[2] = p[0]; o[3] = p[1]; }
+        else { o[0] = p[0]; o[1] = p[1]; o[2] = p[2]; o[3] = p[3]; }
+    }
+}
+uint32_t add_image(DescOwner& o, const std::string& file, float time) {
+    trb_image im{};
+    std::vector<uint8_t> px;
+    load_png(join(o.dir, file), im.width, im.height, px);
+    im.time = time;
+    o.image_data.push_back(std::move(px));
+    o.images.push_back(im); // rgba8 pointers are set once every image is loaded (vectors may still move)
+    return (uint32_t)o.images.size() - 1;
+}
+void load_textures(DescOwner& o, const JVal& e) { // scene.rs:317-394
+    for (const JVal& t : e.a("The 'textures' must be an array of textures to load")) {
+        const std::string& name = t.expect("name", "Error loading texture: A name is required").s("name must be a string");
+        const std::string& ty = t.expect("type", "A texture type is required").s("Texture type must be a string");
+        if (o.texture_names.count(name)) die(TRB_INVALID_ARG, "Error loading texture '" + name + "': name conflicts with an existing entry");
+        trb_texture tex{};
+        tex.first_image = (uint32_t)o.images.size();
+        if (ty == "image") add_image(o, t.expect("file", "Image textures must specify an image file").s("Image file name must be a string"), 0.0f);
+        else if (ty == "animated_image") {
+            const auto& frames = t.expect("keyframes", "animated_image requires keyframes").a("animated_image keyframes must be an array");
+            if (frames.size() < 2) die(TRB_INVALID_ARG, "animated_image must have at least 2 frames");
+            for (const JVal& f : frames)
+                add_image(o, f.expect("file", "Image textures must specify an image file").s("Image file name must be a string"),
+                          (float)f.expect("time", "animated_image keyframe requires time").f64("animated_image keyframe time must be a number"));
+        } else if (ty == "movie") { // keyframes generated from a file name pattern and a frame rate
+            const std::string& prefix = t.expect("file_prefix", "A file_prefix for movie is required").s("file_prefix for movie must be a string");
+            const std::string& suffix = t.expect("file_suffix", "A file_suffix for movie is required").s("file_suffix for movie must be a string");
+            const uint64_t total = t.expect("frames", "# of frames for movie texture is required").u64("frames for movie texture must be an int");
+            const uint64_t rate = t.expect("framerate", "A framerate for movie is required").u64("framerate for movie must be an int");
+            if (total < 2) die(TRB_INVALID_ARG, "animated_image must have at least 2 frames"); // AnimatedImage::new asserts frames.len() >= 2
+            for (uint64_t fr = 0; fr < total; ++fr) {
+                char num[32]; std::snprintf(num, sizeof num, "%05llu", (unsigned long long)fr);
+                add_image(o, prefix + num + suffix, (float)fr / (float)rate);
+            }
+        } else die(TRB_INVALID_ARG, "Unrecognized texture type '" + ty + "' for texture '" + name + "'");
+        tex.n_images = (uint32_t)o.images.size() - tex.first_image;
+        o.texture_names[name] = (uint32_t)o.textures.size();
+        o.textures.push_back(tex);
+    }
+}
+uint32_t named_texture(DescOwner& o, const JVal& e, const char* what) { // a string value names a loaded texture (find_color / find_scalar return None otherwise)
+    auto it = o.texture_names.find(e.s(what));
+    if (it == o.texture_names.end()) die(TRB_INVALID_ARG, std::string("Invalid texture name specified for ") + what);
+    return it->second + 1;
+}
+void color_tex(DescOwner& o, const JVal& e, float out[3], uint32_t& tex, const char* what) { // LoadedTextures::find_color (scene.rs:45-69)
+    if (e.kind == JVal::Str) { tex = named_texture(o, e, what); return; }
     float c[4]; load_color(e, c, what);
     out[0] = c[0]; out[1] = c[1]; out[2] = c[2];
 }
-float scalar_tex(const JVal& e, const char* what) { // find_scalar (scene.rs:43-54)
-    if (e.kind == JVal::Str) die(TRB_UNSUPPORTED, std::string("named (image) textures are not implemented: ") + what);
+float scalar_tex(DescOwner& o, const JVal& e, uint32_t& tex, const char* what) { // find_scalar (scene.rs:70-87)
+    if (e.kind == JVal::Str) { tex = named_texture(o, e, what); return 0.0f; }
     return (float)e.f64(what);
 }
 
@@ -422,28 +624,28 @@ void load_materials(DescOwner& o, const JVal& e) { // scene.rs:433-541
         t.eta = 1.0f;
         if (ty == "glass" || ty == "rough_glass") {
             t.type = ty == "glass" ? TRB_MAT_GLASS : TRB_MAT_ROUGH_GLASS;
-            color_tex(m.expect("reflect", "reflect color/texture name is required for glass"), t.c0, "reflect");
-            color_tex(m.expect("transmit", "transmit color/texture name is required for glass"), t.c1, "transmit");
-            t.eta = scalar_tex(m.expect("eta", "eta color/texture name is required for glass"), "eta");
-            if (ty == "rough_glass") t.roughness = scalar_tex(m.expect("roughness", "roughness is required for rough glass"), "roughness");
+            color_tex(o, m.expect("reflect", "reflect color/texture name is required for glass"), t.c0, t.tex[0], "reflect");
+            color_tex(o, m.expect("transmit", "transmit color/texture name is required for glass"), t.c1, t.tex[1], "transmit");
+            t.eta = scalar_tex(o, m.expect("eta", "eta color/texture name is required for glass"), t.tex[3], "eta");
+            if (ty == "rough_glass") t.roughness = scalar_tex(o, m.expect("roughness", "roughness is required for rough glass"), t.tex[2], "roughness");
         } else if (ty == "matte") {
             t.type = TRB_MAT_MATTE;
-            color_tex(m.expect("diffuse", "diffuse color/texture name is required for matte"), t.c0, "diffuse");
-            t.roughness = scalar_tex(m.expect("roughness", "roughness color/texture is required for matte"), "roughness");
+            color_tex(o, m.expect("diffuse", "diffuse color/texture name is required for matte"), t.c0, t.tex[0], "diffuse");
+            t.roughness = scalar_tex(o, m.expect("roughness", "roughness color/texture is required for matte"), t.tex[2], "roughness");
         } else if (ty == "merl") {
             t.type = TRB_MAT_MERL;
             t.merl = (uint32_t)o.merl.size();
             o.merl.push_back(load_merl(join(o.dir, m.expect("file", "A filename containing the MERL material data is required").s("The MERL file must be a string"))));
         } else if (ty == "metal" || ty == "specular_metal") {
             t.type = ty == "metal" ? TRB_MAT_METAL : TRB_MAT_SPECULAR_METAL;
-            color_tex(m.expect("refractive_index", "refractive_index color/texture name is required for metal"), t.c0, "refractive_index");
-            color_tex(m.expect("absorption_coefficient", "absorption_coefficient color/texture name is required for metal"), t.c1, "absorption_coefficient");
-            if (ty == "metal") t.roughness = scalar_tex(m.expect("roughness", "roughness color/texture is required for metal"), "roughness");
+            color_tex(o, m.expect("refractive_index", "refractive_index color/texture name is required for metal"), t.c0, t.tex[0], "refractive_index");
+            color_tex(o, m.expect("absorption_coefficient", "absorption_coefficient color/texture name is required for metal"), t.c1, t.tex[1], "absorption_coefficient");
+            if (ty == "metal") t.roughness = scalar_tex(o, m.expect("roughness", "roughness color/texture is required for metal"), t.tex[2], "roughness");
         } else if (ty == "plastic") {
             t.type = TRB_MAT_PLASTIC;
-            color_tex(m.expect("diffuse", "diffuse color/texture name is required for plastic"), t.c0, "diffuse");
-            color_tex(m.expect("gloss", "gloss color/texture name is required for plastic"), t.c1, "gloss");
-            t.roughness = scalar_tex(m.expect("roughness", "roughness color/texture is required for plastic"), "roughness");
+            color_tex(o, m.expect("diffuse", "diffuse color/texture name is required for plastic"), t.c0, t.tex[0], "diffuse");
+            color_tex(o, m.expect("gloss", "gloss color/texture name is required for plastic"), t.c1, t.tex[1], "gloss");
+            t.roughness = scalar_tex(o, m.expect("roughness", "roughness color/texture is required for plastic"), t.tex[2], "roughness");
         } else die(TRB_INVALID_ARG, "Error parsing material '" + name + "': unrecognized type '" + ty + "'");
         o.material_names[name] = (uint32_t)o.materials.size();
         o.materials.push_back(t);
@@ -642,7 +844,7 @@ DescOwner* load_scene(const char* path, uint32_t w, uint32_t h, uint32_t spp) {
     }
     else die(TRB_INVALID_ARG, "Unrecognized integrator type '" + ity + "'");
 
-    if (root.get("textures")) die(TRB_UNSUPPORTED, "image textures are not implemented (DESIGN.md: next, row N3)");
+    if (const JVal* tx = root.get("textures")) load_textures(*o, *tx); // scene.rs:118-121: loaded before the materials that name them
     load_materials(*o, root.expect("materials", "An array of materials is required"));
     std::vector<PendingInstance> pend;
     load_objects(*o, root.expect("objects", "The scene must specify a list of objects"), pend);
@@ -666,6 +868,9 @@ DescOwner* load_scene(const char* path, uint32_t w, uint32_t h, uint32_t spp) {
     d.n_materials = (uint32_t)o->materials.size(); d.materials = o->materials.data();
     d.n_merl = (uint32_t)o->merl.size(); d.merl_tables = o->merl_ptrs.data();
     d.n_fov_floats = (uint32_t)o->fov_floats.size(); d.fov_floats = o->fov_floats.data();
+    for (size_t i = 0; i < o->images.size(); ++i) o->images[i].rgba8 = o->image_data[i].data();
+    d.n_textures = (uint32_t)o->textures.size(); d.textures = o->textures.data();
+    d.n_images = (uint32_t)o->images.size(); d.images = o->images.data();
     return o.release();
 }
 

@@ -59,6 +59,7 @@ class SceneBuilder:
         self.keyframes, self.knots, self.splines = [], [], []
         self.instances, self.color_keys, self.meshes, self.materials, self.merl, self.cameras = [], [], [], [], [], []
         self.fov_floats = []
+        self.textures, self.images = [], []
         self._keep = []
 
     # -- transforms ---------------------------------------------------------------------
@@ -78,8 +79,21 @@ class SceneBuilder:
             self.knots += [0.0, 1.0]  # AnimatedTransform::unanimated (animated_transform.rs:34-37)
         return first, len(levels)
 
-    def add_material(self, mtype, c0=(0, 0, 0), c1=(0, 0, 0), roughness=0.0, eta=1.0, merl=0):
-        self.materials.append((mtype, tuple(c0), tuple(c1), float(roughness), float(eta), merl))
+    def add_texture(self, frames):
+        """texture::Image (one frame) or texture::AnimatedImage (>= 2 frames): frames = [(H x W x 4 uint8 array, time), ...] or a single
+        array. Returns the value to pass as tex_c0 / tex_c1 / tex_roughness / tex_eta of add_material (index + 1)."""
+        if isinstance(frames, np.ndarray):
+            frames = [(frames, 0.0)]
+        first = len(self.images)
+        for px, t in frames:
+            px = np.ascontiguousarray(px, np.uint8)
+            assert px.ndim == 3 and px.shape[2] == 4
+            self.images.append((px, float(t)))
+        self.textures.append((first, len(frames)))
+        return len(self.textures)
+
+    def add_material(self, mtype, c0=(0, 0, 0), c1=(0, 0, 0), roughness=0.0, eta=1.0, merl=0, tex_c0=0, tex_c1=0, tex_roughness=0, tex_eta=0):
+        self.materials.append((mtype, tuple(c0), tuple(c1), float(roughness), float(eta), merl, (tex_c0, tex_c1, tex_roughness, tex_eta)))
         return len(self.materials) - 1
 
     def add_merl_table(self, table):
@@ -181,6 +195,7 @@ class SceneBuilder:
 
         def mat(o, it):
             o.type = it[0]; o.c0[:] = it[1]; o.c1[:] = it[2]; o.roughness = it[3]; o.eta = it[4]; o.merl = it[5]
+            o.tex[:] = it[6] if len(it) > 6 else (0, 0, 0, 0)
         d.materials = arr(F.Material, self.materials, mat); d.n_materials = len(self.materials)
         mt = (C.POINTER(F.f32) * max(1, len(self.merl)))()
         for i, t in enumerate(self.merl):
@@ -194,6 +209,17 @@ class SceneBuilder:
         d.cameras = arr(F.Camera, self.cameras, cam); d.n_cameras = len(self.cameras)
         ff = (F.f32 * max(1, len(self.fov_floats)))(*self.fov_floats); keep.append(ff)
         d.fov_floats = ff; d.n_fov_floats = len(self.fov_floats)
+
+        def tex(o, it):
+            o.first_image, o.n_images = it
+        d.textures = arr(F.Texture, self.textures, tex); d.n_textures = len(self.textures)
+
+        def image(o, it):
+            px, t = it
+            o.height, o.width = px.shape[0], px.shape[1]
+            o.rgba8 = px.ctypes.data_as(C.POINTER(C.c_uint8)); o.time = t
+        d.images = arr(F.Image, self.images, image); d.n_images = len(self.images)
+        keep.append(self.images)
         d._keep = keep
         return d
 
