@@ -452,7 +452,7 @@ trb_status trb_scene_check_error(trb_scene* scene);
 
 /* Launch-shape options of the wavefront pipeline (results never depend on them; DESIGN.md "Options"):
  * "pass.paths" camera samples per pass, "sort.mode" 0/1 ray-queue sorting, "sort.bits", "sort.min_round",
- * "shade.split" 0/1, "anim.table" 0/1, "pass.graph" 0/1, "film.v2" 0/1, "trace.refill", "trace.occupancy", "trace.grid",
+ * "shade.split" 0/1, "anim.table" 0/1, "frame.device" 0/1, "shade.anim_occupancy" 3/4, "film.v2" 0/1, "trace.refill", "trace.occupancy", "trace.grid",
  * "trace.smem_stack", "trace.sched", "trace.quads". Defaults can also be preset by TRB_* environment
  * variables, read once by trb_scene_create. */
 trb_status trb_scene_set_option(trb_scene* scene, const char* name, long long value);

@@ -1,5 +1,5 @@
 """Developer tool (GPU box): A/B the round-2 launch options on the bench workload (C4, 1920x1080, 8 spp per step) in ONE
-process: ray-queue sorting (mode / grid bits / first round), split shading, pass graphs. Prints one JSON line per variant
+process: ray-queue sorting (mode / grid bits / first round), split shading. Prints one JSON line per variant
 with the step time, the trace-kernel share and a bit-exactness check of the per-sample radiance against the first variant.
    gpurun -- 'python tools/r02_sweep.py > gpurun_out/r02_sweep.log'"""
 import json
@@ -18,7 +18,7 @@ stats = torch.zeros(10, dtype=torch.int64, device=dev)
 flush = torch.empty(256 << 20, dtype=torch.uint8, device=dev)
 g = api.Scene(SB.scene_c4(1_000_000, W, H, 4096).finish(), 0)
 g.update_frame(0, 0.0, 0.0)
-DEFAULTS = {"sort.mode": 0, "sort.bits": 5, "sort.min_round": 1, "shade.split": 0, "pass.graph": 0, "trace.refill": 8, "trace.sched": 6, "trace.mis_bounded": 0,
+DEFAULTS = {"sort.mode": 0, "sort.bits": 5, "sort.min_round": 1, "shade.split": 0, "trace.refill": 8, "trace.sched": 6,
             "trace.occupancy": 7, "trace.grid": 12}
 ref = None
 
@@ -54,18 +54,11 @@ def measure(name, **opts):
                       "other_ms_per_step": (ms - tms) / STEPS, "bit_exact_vs_first": same}), flush=True)
 
 
-VARIANTS = os.environ.get("SWEEP", "mis").split(",")
-measure("round-1 configuration (MIS closest-hit, no sort, fused shade)")
-if "mis" in VARIANTS:
-    measure("MIS rays as bounded occlusion queries", trace_mis_bounded=1)
-    measure("bounded MIS + split shade", trace_mis_bounded=1, shade_split=1)
-    for refill in (4, 12, 16):
-        measure("bounded MIS, refill %d" % refill, trace_mis_bounded=1, trace_refill=refill)
-    for sched in (3, 10):
-        measure("bounded MIS, sched %d" % sched, trace_mis_bounded=1, trace_sched=sched)
-    measure("bounded MIS, occupancy 8", trace_mis_bounded=1, trace_occupancy=8)
-    measure("bounded MIS, grid 16", trace_mis_bounded=1, trace_grid=16)
-    measure("bounded MIS + sort octant-major bits=4", trace_mis_bounded=1, sort_mode=1, sort_bits=4)
+VARIANTS = os.environ.get("SWEEP", "shade").split(",")
+measure("default configuration")
+if "shade" in VARIANTS:
+    measure("split shade", shade_split=1)
+    measure("trace refill 12", trace_refill=12)
 if "sort" in VARIANTS:
     measure("split shade", shade_split=1)
     for bits in (4, 5, 6):

@@ -170,8 +170,9 @@ struct Tuning {
     int shade_anim_occ = 4;    // keyframed shade kernel variant: resident CTAs per SM it is compiled for (3 or 4)
     int frame_device = 1;      // Scene::update_frame on the device (instance transforms, animation bounds, TLAS SAH build); 0 = on the host
     int anim_table = 1;        // keyframed scenes: evaluate each keyframed instance's transform once per path (0 = per ray per instance, like the reference)
-    int shade_split = 0;       // shading as three kernels (surface | direct light | BSDF sample) instead of one (measured equal on C4)
-    int graph = 1;             // replay each pass as a CUDA graph when its shape repeats
+    int shade_split = -1;      // shading as three kernels (surface | direct light | BSDF sample) instead of one: 1 / 0, -1 = per scene — split
+                               // when the scene mixes material kinds or uses MERL (tr15: 274 -> 337 Mrays/s, tr15-like 388 -> 577), fused for
+                               // one-material scenes like C4 (134.4 vs 134.9 ms per step)
     uint64_t pass_paths = 1ull << 24; // camera samples per wavefront pass (the frame is rendered in additive passes)
 };
 int env_int(const char* name, int dflt) { const char* v = getenv(name); return v ? (int)strtol(v, nullptr, 0) : dflt; }
@@ -179,7 +180,7 @@ void tuning_from_env(Tuning& t) {
     t.refill = env_int("TRB_REFILL", t.refill); t.occ = env_int("TRB_TRACE_OCC", t.occ); t.trace_grid = (unsigned)env_int("TRB_TRACE_GRID", (int)t.trace_grid);
     t.smem_stack = env_int("TRB_SMEM_STACK", t.smem_stack); t.sched = (uint32_t)env_int("TRB_TRACE_SCHED", (int)t.sched); t.quads = env_int("TRB_TRACE_QUADS", t.quads);
     t.film_v2 = env_int("TRB_FILM_V2", t.film_v2); t.sort = env_int("TRB_SORT", t.sort); t.sort_bits = env_int("TRB_SORT_BITS", t.sort_bits);
-    t.sort_min_round = env_int("TRB_SORT_MIN_ROUND", t.sort_min_round); t.shade_split = env_int("TRB_SHADE_SPLIT", t.shade_split); t.anim_table = env_int("TRB_ANIM_TABLE", t.anim_table); t.frame_device = env_int("TRB_FRAME_DEVICE", t.frame_device); t.graph = env_int("TRB_GRAPH", t.graph);
+    t.sort_min_round = env_int("TRB_SORT_MIN_ROUND", t.sort_min_round); t.shade_split = env_int("TRB_SHADE_SPLIT", t.shade_split); t.anim_table = env_int("TRB_ANIM_TABLE", t.anim_table); t.frame_device = env_int("TRB_FRAME_DEVICE", t.frame_device);
     if (getenv("TRB_PASS_PATHS")) t.pass_paths = strtoull(getenv("TRB_PASS_PATHS"), nullptr, 0);
 }
 
@@ -209,6 +210,7 @@ struct trb_scene {
     std::vector<HostMesh> meshes;
     uint32_t spp_pow2 = 1;
     uint32_t n_anim = 0;                 // instances whose transform stack is keyframed (evaluated per path into WfState::xf_tab)
+    bool mixed_materials = false;        // receivers use >= 3 material kinds or a MERL table: the split shade kernels win (Tuning::shade_split = -1)
     uint32_t* d_anim_instances = nullptr;
     // per-frame host state
     int active_camera = -1;
@@ -407,7 +409,7 @@ trb_status ensure_wavefront(trb_scene* s, size_t n_paths) {
     float4** f4[] = {&w.org, &w.cont, &w.shadow, &w.mis, &w.a, &w.b, &w.tprev, &w.thr, &w.illum, &w.ng, &w.rad, &w.f_p, &w.f_n, &w.f_t, &w.f_b};
     for (float4** q : f4) grab(cap * sizeof(float4), reinterpret_cast<void**>(q));
     grab(cap * sizeof(uint4), reinterpret_cast<void**>(&w.hit));
-    uint32_t** u1[] = {&w.q_active[0], &w.q_active[1], &w.q_cont, &w.q_shadow, &w.q_mis, &w.q_mid};
+    uint32_t** u1[] = {&w.q_active[0], &w.q_active[1], &w.q_ending[0], &w.q_ending[1], &w.q_cont, &w.q_shadow, &w.q_mis, &w.q_mid};
     for (uint32_t** q : u1) grab(cap * sizeof(uint32_t), reinterpret_cast<void**>(q));
     grab(64 * trb::WF_CNT * sizeof(uint32_t), reinterpret_cast<void**>(&w.counters));
     // ray sorting: up to three rays per path and round; bins for the finest grid the options allow
@@ -505,7 +507,7 @@ trb_status launch_wavefront(trb_scene* s, const trb::RenderParams& rp, uint32_t 
         else TRB_TRACE_LAUNCH(false, 7, 20, false, true, false);
 #undef TRB_TRACE_LAUNCH
         if (ev.first) { CU(cudaEventRecord(ev.second, st)); s->trace_events.push_back(ev); }
-        if (tu.shade_split) { // three kernels with fewer live values each (DESIGN.md "Split shading"); same device functions, same results
+        if (tu.shade_split > 0 || (tu.shade_split < 0 && s->mixed_materials)) { // three kernels with fewer live values each (DESIGN.md "Split shading"); same device functions, same results
             if (anim) {
                 if (mode == 0) trb::k_wf_shade_a<0, true, 3><<<shade_grid, 128, 0, st>>>(s->ds, rp, wf, round);
                 else trb::k_wf_shade_a<1, true, 3><<<shade_grid, 128, 0, st>>>(s->ds, rp, wf, round);
@@ -628,7 +630,6 @@ trb_status trb_scene_set_option(trb_scene* s, const char* name, long long value)
     else if (k == "anim.table") t.anim_table = (int)value;
     else if (k == "frame.device") t.frame_device = (int)value;
     else if (k == "shade.anim_occupancy") t.shade_anim_occ = (int)value;
-    else if (k == "pass.graph") t.graph = (int)value;
     else if (k == "pass.paths") { if (value < 64) return fail(TRB_INVALID_ARG, "pass.paths must be >= 64"); t.pass_paths = (uint64_t)value; }
     else return fail(TRB_INVALID_ARG, "unknown option: " + k);
     return TRB_OK;
@@ -807,6 +808,11 @@ trb_status trb_scene_create(const trb_scene_desc* d, int device, trb_scene** out
     CU(s->arena.alloc(d->n_instances, &s->d_instances));
     CU(s->arena.alloc(d->n_instances, &s->d_anim_instances));
     for (const trb_instance& in : s->instances) if (!trbh::xf_is_static(s->splines.data(), in.spline_first, in.n_splines)) s->n_anim++;
+    {
+        uint32_t kinds = 0;
+        for (const trb_instance& in : s->instances) if (in.kind == TRB_INST_RECEIVER) kinds |= 1u << s->materials[in.material].type;
+        s->mixed_materials = __builtin_popcount(kinds) >= 3 || (kinds & (1u << TRB_MAT_MERL)) != 0;
+    }
     CU(s->arena.alloc(1, &s->d_counter));
     CU(s->arena.alloc(1, &s->d_error));
     CU(cudaMemset(s->d_error, 0, sizeof(int)));

@@ -1606,6 +1606,7 @@ struct WfState {
     float4* ng;      // first hit's geometric normal (Q1)
     float4* rad;     // finished, clamped radiance per sample (film mode)
     uint32_t* q_active[2];
+    uint32_t* q_ending[2]; // paths that have stopped scattering but still wait for their last shadow / MIS results (fused shade kernel)
     uint32_t* q_cont; uint32_t* q_shadow; uint32_t* q_mis;
     uint32_t* counters; // per round: WF_CNT words
     uint32_t n_paths;
@@ -1629,7 +1630,7 @@ struct WfState {
 constexpr uint32_t WF_PATH_MASK = 0x3fffffffu;
 constexpr int WF_SORT_MAX_BITS = 6; // origin grid up to 64^3 cells x 8 octants x 3 ray types = 6.3 M bins
 enum { WF_N_ACTIVE = 0, WF_N_CONT = 1, WF_N_SHADOW = 2, WF_N_MIS = 3, WF_TRACE_HEAD = 4, WF_SHADE_HEAD = 5, WF_N_MID = 6, WF_SHADE_B_HEAD = 7, WF_SHADE_C_HEAD = 8,
-       WF_CNT = 12 };
+       WF_N_ENDING = 9, WF_ENDING_HEAD = 10, WF_CNT = 12 };
 enum { WF_F_SPECULAR = 1u, WF_F_TERMINATE = 2u, WF_F_SHADOW = 4u, WF_F_MIS = 8u };
 
 // sample index p -> block item, pixel, sample (the canonical order of trb_camera_rays / trb_render_samples)
@@ -1913,6 +1914,19 @@ __global__ void __launch_bounds__(128, MINB) k_wf_trace(const __grid_constant__ 
     }
 }
 
+// per-sample clamp (multithreaded.rs:99, Q12) and hand-over to the film (MODE 0) or the parity records (MODE 1)
+__device__ __forceinline__ void finish_sample(const DScene& sc, const RenderParams& rp, const WfState& wf, uint32_t p, f3 illum, int mode) {
+    const f3 c = mk(clampf(illum.x, 0.0f, 1.0f), clampf(illum.y, 0.0f, 1.0f), clampf(illum.z, 0.0f, 1.0f)); // multithreaded.rs:99 (Q12)
+    if (mode == 0) wf.rad[p] = make_float4(c.x, c.y, c.z, 1.0f);
+    else {
+        const SampleId id = sample_id(sc, rp, p);
+        const PixelStreams ps = pixel_streams(rp.seed, id.pixel);
+        float sx, sy, tm;
+        sample_position(rp, ps, id, sx, sy, tm);
+        trb_sample* out = reinterpret_cast<trb_sample*>(rp.samples_out) + p;
+        out->x = sx; out->y = sy; out->r = c.x; out->g = c.y; out->b = c.z;
+    }
+}
 // Shade round r (== bounce r of every live path). MODE 0: finished samples go to wf.rad; MODE 1: to trb_sample records.
 template <int MODE, bool ANIM, int MINB>
 __global__ void __launch_bounds__(128, MINB) k_wf_shade(const __grid_constant__ DScene sc, const __grid_constant__ RenderParams rp, const __grid_constant__ WfState wf,
@@ -1922,7 +1936,37 @@ __global__ void __launch_bounds__(128, MINB) k_wf_shade(const __grid_constant__ 
     const uint32_t n = cnt_r[WF_N_ACTIVE];
     const uint32_t* __restrict__ act = wf.q_active[round & 1];
     uint32_t* act_next = wf.q_active[(round + 1) & 1];
+    uint32_t* ending_next = wf.q_ending[(round + 1) & 1];
     const int lane = threadIdx.x & 31;
+    // Paths whose last bounce ended them (black BSDF sample, Russian roulette, max depth) only have the direct light of that bounce
+    // left to fold in. They come in their own list so that the warps doing the expensive shading below are not one third empty:
+    // this loop is a few loads and one direct_resolve per path.
+    if (round > 0) {
+        const uint32_t n_end = cnt_r[WF_N_ENDING];
+        const uint32_t* __restrict__ ending = wf.q_ending[round & 1];
+        for (;;) {
+            uint32_t base = 0;
+            if (lane == 0) base = atomicAdd(&cnt_r[WF_ENDING_HEAD], 32u);
+            base = __shfl_sync(0xffffffffu, base, 0);
+            if (base >= n_end) break;
+            const uint32_t i = base + lane;
+            if (i < n_end) {
+                const uint32_t p = ending[i];
+                const float4 o4 = wf.org[p];
+                const uint32_t fl = __float_as_uint(o4.w);
+                const float4 il4 = wf.illum[p];
+                const float4 a4 = wf.a[p], b4 = wf.b[p], t4 = wf.tprev[p];
+                bool occluded = false, mis_ok = false;
+                if (fl & WF_F_SHADOW) occluded = __float_as_uint(wf.shadow[p].w) != 0u;
+                if (fl & WF_F_MIS) {
+                    const float4 m4 = wf.mis[p];
+                    mis_ok = mis_sees_light<ANIM>(sc, mk(o4.x, o4.y, o4.z), mk(m4.x, m4.y, m4.z), __float_as_uint(b4.w), __float_as_uint(a4.w), m4.w, wf.thr[p].w, wf_xf_row<ANIM>(wf, p));
+                }
+                const f3 illum = mk(il4.x, il4.y, il4.z) + mk(t4.x, t4.y, t4.z) * direct_resolve(mk(a4.x, a4.y, a4.z), mk(b4.x, b4.y, b4.z), occluded, mis_ok);
+                finish_sample(sc, rp, wf, p, illum, MODE);
+            }
+        }
+    }
     for (;;) {
         uint32_t base = 0;
         if (lane == 0) base = atomicAdd(&cnt_r[WF_SHADE_HEAD], 32u);
@@ -1931,7 +1975,7 @@ __global__ void __launch_bounds__(128, MINB) k_wf_shade(const __grid_constant__ 
         const uint32_t i = base + lane;
         const bool valid = i < n;
         uint32_t p = 0;
-        bool push_cont = false, push_shadow = false, push_mis = false, push_active = false;
+        bool push_cont = false, push_shadow = false, push_mis = false, push_active = false, push_ending = false;
         f3 new_org = splat(0.0f);
         if (valid) {
             p = round == 0 ? i : act[i];
@@ -1975,6 +2019,7 @@ __global__ void __launch_bounds__(128, MINB) k_wf_shade(const __grid_constant__ 
                                         (o.ds.has_mis ? WF_F_MIS : 0u);
                     push_cont = !o.terminate; push_shadow = o.ds.has_shadow; push_mis = o.ds.has_mis;
                     push_active = push_cont || push_shadow || push_mis;
+                    push_ending = push_active && o.terminate; // nothing left to shade: next round only resolves its shadow / MIS rays
                     if (push_active) {
                         new_org = o.org;
                         wf.org[p] = make_float4(o.org.x, o.org.y, o.org.z, __uint_as_float(nf));
@@ -2005,7 +2050,8 @@ __global__ void __launch_bounds__(128, MINB) k_wf_shade(const __grid_constant__ 
         wf_push(wf.q_cont, &cnt_n[WF_N_CONT], push_cont, p);
         wf_push(wf.q_shadow, &cnt_n[WF_N_SHADOW], push_shadow, p);
         wf_push(wf.q_mis, &cnt_n[WF_N_MIS], push_mis, p);
-        wf_push(act_next, &cnt_n[WF_N_ACTIVE], push_active, p);
+        wf_push(act_next, &cnt_n[WF_N_ACTIVE], push_active && !push_ending, p);
+        wf_push(ending_next, &cnt_n[WF_N_ENDING], push_ending, p);
         wf_bounds_add(wf.bounds + (round + 1) * 8, push_active, new_org);
     }
 }
@@ -2151,18 +2197,6 @@ __global__ void __launch_bounds__(128) k_simple_integrator(const __grid_constant
 //   k_wf_shade_c  BSDF sample, throughput, Russian roulette -> continuation ray; decides whether the path goes on
 // Every value is computed by the same device functions in the same order as in the fused kernel: bit-identical results.
 // ------------------------------------------------------------------------------------------
-__device__ __forceinline__ void finish_sample(const DScene& sc, const RenderParams& rp, const WfState& wf, uint32_t p, f3 illum, int mode) {
-    const f3 c = mk(clampf(illum.x, 0.0f, 1.0f), clampf(illum.y, 0.0f, 1.0f), clampf(illum.z, 0.0f, 1.0f)); // multithreaded.rs:99 (Q12)
-    if (mode == 0) wf.rad[p] = make_float4(c.x, c.y, c.z, 1.0f);
-    else {
-        const SampleId id = sample_id(sc, rp, p);
-        const PixelStreams ps = pixel_streams(rp.seed, id.pixel);
-        float sx, sy, tm;
-        sample_position(rp, ps, id, sx, sy, tm);
-        trb_sample* out = reinterpret_cast<trb_sample*>(rp.samples_out) + p;
-        out->x = sx; out->y = sy; out->r = c.x; out->g = c.y; out->b = c.z;
-    }
-}
 __device__ __forceinline__ void load_frame(const WfState& wf, uint32_t p, Frame& fr, uint32_t& inst, float& u, float& v) {
     const float4 a = wf.f_p[p], n = wf.f_n[p], t = wf.f_t[p], b = wf.f_b[p];
     fr.p = mk(a.x, a.y, a.z); inst = __float_as_uint(a.w); u = n.w; v = t.w;
