@@ -18,6 +18,8 @@ ncu --metrics gpu__time_duration.sum --clock-control none -c 400 --csv --log-fil
 for k in trace shade film_v2; do
   ncu --set full --import-source on --clock-control none -k regex:k_wf_$k -s 1 -c 1 -f -o ${P}_prof_$k python bench.py --steps 1 --warmup 1 --no-cpu-baseline > /dev/null 2>&1
   python tools/ncu_summary.py ${P}_prof_$k.ncu-rep > ${P}_ncu_k_wf_$k.txt 2>&1
+  ncu -i ${P}_prof_$k.ncu-rep --page source --csv > ${P}_source_k_wf_$k.csv 2> /dev/null
+  rm -f ${P}_prof_$k.ncu-rep   # gpurun merges at most 64 MiB back: keep the summaries and the per-instruction table, not the report
 done
 for t in memcheck racecheck; do
   timeout 900 compute-sanitizer --tool $t python tools/sanitize.py > ${P}_sanitizer_$t.log 2>&1
