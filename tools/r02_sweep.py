@@ -19,7 +19,7 @@ flush = torch.empty(256 << 20, dtype=torch.uint8, device=dev)
 g = api.Scene(SB.scene_c4(1_000_000, W, H, 4096).finish(), 0)
 g.update_frame(0, 0.0, 0.0)
 DEFAULTS = {"sort.mode": 0, "sort.bits": 5, "sort.min_round": 1, "shade.split": 0, "trace.refill": 8, "trace.sched": 6,
-            "trace.occupancy": 7, "trace.grid": 12}
+            "trace.occupancy": 7, "trace.grid": 12, "trace.pipe": 0}
 ref = None
 
 
@@ -66,3 +66,13 @@ if "sort" in VARIANTS:
     measure("sort cell-major bits=5", sort_mode=2, sort_bits=5)
     measure("sort octant-major bits=5 from round 2", sort_mode=1, sort_bits=5, sort_min_round=2)
     measure("sort octant-major bits=5 + split", sort_mode=1, sort_bits=5, shade_split=1)
+if "pipe" in VARIANTS:  # trace.pipe: bit 0 = box_hit_finite, 32 = RayHome + fused non-node chains; 34-37 = 33 at 8/8/9/9 CTAs per SM with 16/12/12/8 stack entries in shared memory
+    for pipe in (33, 36):
+        measure("trace.pipe=%d" % pipe, trace_pipe=pipe)
+    for grid in (9, 18, 27):
+        measure("trace.pipe=36 grid=%d" % grid, trace_pipe=36, trace_grid=grid)
+    for sched in (4, 8, 10):
+        measure("trace.pipe=36 grid=18 sched=%d" % sched, trace_pipe=36, trace_grid=18, trace_sched=sched)
+    for refill in (4, 12, 16):
+        measure("trace.pipe=36 grid=18 refill=%d" % refill, trace_pipe=36, trace_grid=18, trace_refill=refill)
+    measure("default again")

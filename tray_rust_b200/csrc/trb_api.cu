@@ -158,11 +158,10 @@ namespace {
 // sweeps), changed afterwards only through trb_scene_set_option: the launch path never touches getenv.
 struct Tuning {
     int refill = 8;            // trace: idle lanes that trigger a warp refill
-    int occ = 7;               // trace: resident CTAs per SM the kernel variant is compiled for
-    unsigned trace_grid = 12;  // trace: CTAs per SM launched
-    int smem_stack = 16;       // trace: traversal-stack entries kept in shared memory
+    unsigned trace_grid = 0;   // trace: CTAs per SM launched (0 = twice what the chosen variant keeps resident)
     uint32_t sched = 6;        // trace: quorum of the phased loop (0 = flat state machine)
     int quads = 0;             // trace: DQuad two-level records (measured slower on C4)
+    int pipe = 36;             // trace: kernel variant. 0 = round-1 kernel; 1 = + box_hit_finite; 33 = + RayHome + fused non-node chains at 7 CTAs per SM; 34 / 35 / 36 / 37 = the same at 8 / 8 / 9 / 9 CTAs with 16 / 12 / 12 / 8 stack entries in shared memory
     int film_v2 = 1;           // film: per-warp private tiles (0 = shared-memory atomics)
     int sort = 0;              // ray queues: 0 = path order; 1 / 2 = counting sort by (octant, origin cell) / (cell, octant) before each trace round (measured: -1.5 % trace time, +10 % step time on C4)
     int sort_bits = 5;         // bits per axis of the origin cell grid
@@ -177,8 +176,8 @@ struct Tuning {
 };
 int env_int(const char* name, int dflt) { const char* v = getenv(name); return v ? (int)strtol(v, nullptr, 0) : dflt; }
 void tuning_from_env(Tuning& t) {
-    t.refill = env_int("TRB_REFILL", t.refill); t.occ = env_int("TRB_TRACE_OCC", t.occ); t.trace_grid = (unsigned)env_int("TRB_TRACE_GRID", (int)t.trace_grid);
-    t.smem_stack = env_int("TRB_SMEM_STACK", t.smem_stack); t.sched = (uint32_t)env_int("TRB_TRACE_SCHED", (int)t.sched); t.quads = env_int("TRB_TRACE_QUADS", t.quads);
+    t.refill = env_int("TRB_REFILL", t.refill); t.trace_grid = (unsigned)env_int("TRB_TRACE_GRID", (int)t.trace_grid);
+    t.sched = (uint32_t)env_int("TRB_TRACE_SCHED", (int)t.sched); t.quads = env_int("TRB_TRACE_QUADS", t.quads); t.pipe = env_int("TRB_TRACE_PIPE", t.pipe);
     t.film_v2 = env_int("TRB_FILM_V2", t.film_v2); t.sort = env_int("TRB_SORT", t.sort); t.sort_bits = env_int("TRB_SORT_BITS", t.sort_bits);
     t.sort_min_round = env_int("TRB_SORT_MIN_ROUND", t.sort_min_round); t.shade_split = env_int("TRB_SHADE_SPLIT", t.shade_split); t.anim_table = env_int("TRB_ANIM_TABLE", t.anim_table); t.frame_device = env_int("TRB_FRAME_DEVICE", t.frame_device);
     if (getenv("TRB_PASS_PATHS")) t.pass_paths = strtoull(getenv("TRB_PASS_PATHS"), nullptr, 0);
@@ -472,8 +471,10 @@ trb_status launch_wavefront(trb_scene* s, const trb::RenderParams& rp, uint32_t 
         g_launches++;
     } else wf.xf_tab = nullptr;
     const unsigned shade_grid = (unsigned)s->sm_count * 4;
-    const int refill = tu.refill, occ = tu.occ, sst = tu.smem_stack;
-    const unsigned tgrid = (unsigned)s->sm_count * tu.trace_grid;
+    const int refill = tu.refill;
+    // persistent CTAs: two rounds of what is resident per SM (9 for the default variant, 7 keyframed, 4 with counters) unless set
+    const unsigned resident = (flags & TRB_RENDER_STATS) ? 4u : (s->ds.has_anim || tu.pipe == 0 || tu.pipe == 1 || tu.pipe == 33 ? 7u : (tu.pipe == 34 || tu.pipe == 35 ? 8u : 9u));
+    const unsigned tgrid = (unsigned)s->sm_count * (tu.trace_grid ? tu.trace_grid : 2u * resident);
     const uint32_t sched = tu.sched;   // 0 = flat state machine; else the quorum of the phased loop (see k_wf_trace)
     const bool quads = tu.quads != 0;  // DQuad two-level records (never in the STATS variants: their counters are the reference's)
     const uint32_t tflags = flags;
@@ -494,17 +495,28 @@ trb_status launch_wavefront(trb_scene* s, const trb::RenderParams& rp, uint32_t 
             else { CU(cudaEventCreate(&ev.first)); CU(cudaEventCreate(&ev.second)); }
             CU(cudaEventRecord(ev.first, st));
         }
-#define TRB_TRACE_LAUNCH(ST, MB, SS, AN, PH, QD) trb::k_wf_trace<ST, MB, SS, AN, PH, QD><<<tgrid, 128, 0, st>>>(s->ds, rp, wf, round, tflags, refill, sched, q_sorted)
-        if (anim) { if (stats) TRB_TRACE_LAUNCH(true, 4, 16, true, true, false); else TRB_TRACE_LAUNCH(false, 7, 16, true, true, false); }
-        else if (stats) { if (sched) TRB_TRACE_LAUNCH(true, 4, 16, false, true, false); else TRB_TRACE_LAUNCH(true, 4, 16, false, false, false); }
-        else if (sched == 0) { if (occ >= 8) TRB_TRACE_LAUNCH(false, 8, 16, false, false, false); else if (occ >= 7) TRB_TRACE_LAUNCH(false, 7, 16, false, false, false); else TRB_TRACE_LAUNCH(false, 6, 16, false, false, false); }
-        else if (quads) TRB_TRACE_LAUNCH(false, 7, 16, false, true, true);
-        else if (occ >= 8) TRB_TRACE_LAUNCH(false, 8, 16, false, true, false);
-        else if (occ <= 6) TRB_TRACE_LAUNCH(false, 6, 16, false, true, false);
-        else if (sst <= 8) TRB_TRACE_LAUNCH(false, 7, 8, false, true, false);
-        else if (sst <= 12) TRB_TRACE_LAUNCH(false, 7, 12, false, true, false);
-        else if (sst <= 16) TRB_TRACE_LAUNCH(false, 7, 16, false, true, false);
-        else TRB_TRACE_LAUNCH(false, 7, 20, false, true, false);
+#define TRB_TRACE_LAUNCH(ST, MB, SS, AN, PH, QD, PIPE) trb::k_wf_trace<ST, MB, SS, AN, PH, QD, PIPE><<<tgrid, 128, 0, st>>>(s->ds, rp, wf, round, tflags, refill, sched, q_sorted)
+        // PIPE 33 = box_hit_finite + RayHome + fused non-node chains (trb_kernels.cuh); tu.pipe picks the variant and how many
+        // CTAs per SM it is compiled for: 36 (default) = 9 CTAs / 12 stack entries in shared memory. The STATS and keyframed
+        // variants run the same code at their own occupancy, so the parity tests' counters cover it.
+        const bool v2 = tu.pipe != 0;
+        if (anim) {
+            if (stats) { if (v2) TRB_TRACE_LAUNCH(true, 4, 16, true, true, false, 33); else TRB_TRACE_LAUNCH(true, 4, 16, true, true, false, 0); }
+            else if (v2) TRB_TRACE_LAUNCH(false, 7, 16, true, true, false, 33); else TRB_TRACE_LAUNCH(false, 7, 16, true, true, false, 0);
+        } else if (stats) {
+            if (sched == 0) TRB_TRACE_LAUNCH(true, 4, 16, false, false, false, 0);
+            else if (v2) TRB_TRACE_LAUNCH(true, 4, 16, false, true, false, 33); else TRB_TRACE_LAUNCH(true, 4, 16, false, true, false, 0);
+        } else if (sched == 0) TRB_TRACE_LAUNCH(false, 7, 16, false, false, false, 0); // flat state machine (no phases)
+        else if (quads) TRB_TRACE_LAUNCH(false, 7, 16, false, true, true, 0);
+        else switch (tu.pipe) {
+            case 0: TRB_TRACE_LAUNCH(false, 7, 16, false, true, false, 0); break;  // round-1 kernel
+            case 1: TRB_TRACE_LAUNCH(false, 7, 16, false, true, false, 1); break;  // + box_hit_finite only
+            case 33: TRB_TRACE_LAUNCH(false, 7, 16, false, true, false, 33); break;
+            case 34: TRB_TRACE_LAUNCH(false, 8, 16, false, true, false, 33); break;
+            case 35: TRB_TRACE_LAUNCH(false, 8, 12, false, true, false, 33); break;
+            case 37: TRB_TRACE_LAUNCH(false, 9, 8, false, true, false, 33); break;
+            default: TRB_TRACE_LAUNCH(false, 9, 12, false, true, false, 33); break; // 36
+        }
 #undef TRB_TRACE_LAUNCH
         if (ev.first) { CU(cudaEventRecord(ev.second, st)); s->trace_events.push_back(ev); }
         if (tu.shade_split > 0 || (tu.shade_split < 0 && s->mixed_materials)) { // three kernels with fewer live values each (DESIGN.md "Split shading"); same device functions, same results
@@ -617,11 +629,11 @@ trb_status trb_scene_set_option(trb_scene* s, const char* name, long long value)
     Tuning& t = s->tune;
     const std::string k(name);
     if (k == "trace.refill") t.refill = (int)value;
-    else if (k == "trace.occupancy") t.occ = (int)value;
-    else if (k == "trace.grid") t.trace_grid = (unsigned)std::max<long long>(1, value);
-    else if (k == "trace.smem_stack") t.smem_stack = (int)value;
+    else if (k == "trace.occupancy" || k == "trace.smem_stack") {} // round-1 knobs: the variant (trace.pipe) now fixes both
+    else if (k == "trace.grid") t.trace_grid = (unsigned)std::max<long long>(0, value);
     else if (k == "trace.sched") t.sched = (uint32_t)value;
     else if (k == "trace.quads") t.quads = (int)value;
+    else if (k == "trace.pipe") t.pipe = (int)value;
     else if (k == "film.v2") t.film_v2 = (int)value;
     else if (k == "sort.mode") t.sort = (int)value;
     else if (k == "sort.bits") t.sort_bits = (int)std::min<long long>(6, std::max<long long>(1, value));

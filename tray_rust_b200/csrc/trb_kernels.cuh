@@ -260,6 +260,16 @@ constexpr uint32_t ST_RETURN = 0xfffffffeu; // leave the mesh: restore the world
 constexpr uint32_t ST_DONE = 0xffffffffu;
 constexpr int STACK_DEPTH = 96;
 
+// Where the wavefront trace kernel keeps the parts of a ray's state that are touched once or twice per ray, instead of in
+// registers for the ray's whole life (13 registers -> one more resident CTA per SM): the world-space ray is re-read from the
+// path state when a mesh is left (1/d recomputed by the same three IEEE divisions), and an accepted hit is written to the
+// path's hit record at once (a later, nearer hit overwrites it; same thread, program order).
+struct RayHome {
+    const float4* org; const float4* dir; // this ray's origin / direction entries of the path state
+    uint4* hit;                           // type 0 (continuation / primary): (inst, prim, b1, b2)
+    float* a_w;                           // type 2 (MIS): the hit instance goes to wf.a[p].w
+    int type;
+};
 // The traversal as an explicit state machine so that a warp can keep all lanes busy: scene_trace()
 // runs it to completion for one ray; the wavefront trace kernel refills finished lanes with new rays.
 struct TraceState {
@@ -270,6 +280,7 @@ struct TraceState {
     const DPair* pairs;   // current level's records, kept in registers: no pointer chase per step (DQuad records when `quad`)
     bool quad;            // this level is traversed through the DQuad records (finite 1/d only, see trb_device.h)
     bool quads_ok;        // the kernel variant may use DQuad records at all
+    bool exact_box;       // the current level's ray has a zero, NaN or infinite component: literal box_hit (see box_hit_finite)
     const DTri* tris;
     uint32_t level_inst;  // instance whose mesh is being traversed, TRB_MISS at the top level
     float tmin, tmax;
@@ -285,6 +296,7 @@ __device__ __forceinline__ uint32_t neg_mask(f3 d) { return (d.x < 0.0f ? 1u : 0
 __device__ __forceinline__ bool finite3(f3 v) { return fabsf(v.x) < finf() && fabsf(v.y) < finf() && fabsf(v.z) < finf(); }
 __device__ __forceinline__ void trace_level(TraceState& t, const DBvh* bvh, const DPair* pairs, const DQuad* quads) {
     t.bvh = bvh;
+    t.exact_box = !(finite3(t.o) && finite3(t.d) && finite3(t.inv));
     t.quad = t.quads_ok && finite3(t.inv);
     t.pairs = t.quad ? reinterpret_cast<const DPair*>(quads) : pairs;
 }
@@ -503,8 +515,78 @@ __device__ __forceinline__ void step_nodes(TraceState& t, const Stack& stack, Cn
     }
     t.cur = cur;
 }
-template <bool STATS>
-__device__ __forceinline__ void step_triangle(TraceState& t, Cnt& cnt) {
+// BBox::fast_intersect for a ray whose origin, direction and 1/direction are all finite (TraceState::exact_box == false):
+// then none of the six slab distances is NaN ((plane - o) is finite or ±inf, 1/d is finite and non-zero), near <= far on
+// every axis (lo <= hi, near/far chosen by the sign of d, IEEE rounding is monotone), and the reference's sequence
+//   reject if a > B || b > A;  m = max(a, b), M = min(A, B);  reject if m > C || c > M;  m = max(m, c), M = min(M, C)
+// accepts exactly when max(a, b, c) <= min(A, B, C) — nine pairwise conditions of which the reference tests six and the
+// other three (a <= A, b <= B, c <= C) hold by construction — with the same final tmin (up to the sign of a zero, which
+// no compare sees). 23 instructions (6 select, 6 sub, 6 mul, 2 FMNMX3, 3 compares) instead of 33. Rays with a zero, NaN
+// or infinite component keep the literal box_hit.
+__device__ __forceinline__ bool box_hit_finite(const float4 lo, const float4 hi, f3 o, f3 inv, bool nx, bool ny, bool nz, float tmin_r, float tmax_r, float& t_entry) {
+    const float ax = ((nx ? hi.x : lo.x) - o.x) * inv.x, bx = ((nx ? lo.x : hi.x) - o.x) * inv.x;
+    const float ay = ((ny ? hi.y : lo.y) - o.y) * inv.y, by = ((ny ? lo.y : hi.y) - o.y) * inv.y;
+    const float az = ((nz ? hi.z : lo.z) - o.z) * inv.z, bz = ((nz ? lo.z : hi.z) - o.z) * inv.z;
+    const float m = fmaxf(fmaxf(ax, ay), az), M = fminf(fminf(bx, by), bz);
+    t_entry = m;
+    return m <= M && m < tmax_r && M > tmin_r;
+}
+// step_nodes for pair records with box_hit_finite for the lanes whose ray is all-finite (operations per ray, hits, t and
+// counters unchanged). What else was tried on this micro-step in round 2 and measured slower on C4, per-sample radiance
+// bit-identical (profiles/r02_c10_sweep_*.log): issuing the next record's load as soon as a lane knows its next node
+// (+12 %: lanes on different paths of the divergent push / pop code write the same registers and the warp-wide scoreboard
+// serialises the loads), the same through one convergent load point after the first pop attempt (+15 %),
+// prefetch.global.L1 of the near child / both children / the next node (+15 % / +60 % / +14 %: the instruction is ten times
+// slower than a load on this part, tools/micro/pair_fetch.cu), four 128-bit loads instead of two 256-bit loads (+12 %).
+template <bool STATS, bool FAST, class Stack>
+__device__ __forceinline__ void step_nodes2(TraceState& t, const Stack& stack, Cnt& cnt, int* err) {
+    uint32_t cur = t.cur;
+    if (cur != ST_POP) {
+        const DPair* __restrict__ rec = t.pairs + cur;
+        float4 l_lo, l_hi, r_lo, r_hi;
+        ldg256(&rec->l_lo, l_lo, l_hi);
+        ldg256(&rec->r_lo, r_lo, r_hi);
+        if (STATS) cnt.node += 2;
+        const uint32_t axis = __float_as_uint(r_lo.w);
+        const bool neg = ((t.neg >> axis) & 1u) != 0; // near child = second_child iff d[axis] < 0 (bvh.rs:111-117)
+        const uint32_t ref_l = __float_as_uint(l_lo.w), ref_r = __float_as_uint(l_hi.w);
+        const bool nx = (t.neg & 1u) != 0, ny = (t.neg & 2u) != 0, nz = (t.neg & 4u) != 0;
+        float tl, tr;
+        bool hl, hr;
+        if (FAST && !t.exact_box) {
+            hl = box_hit_finite(l_lo, l_hi, t.o, t.inv, nx, ny, nz, t.tmin, t.tmax, tl);
+            hr = box_hit_finite(r_lo, r_hi, t.o, t.inv, nx, ny, nz, t.tmin, t.tmax, tr);
+        } else {
+            hl = box_hit(l_lo, l_hi, t.o, t.inv, nx, ny, nz, t.tmin, t.tmax, tl);
+            hr = box_hit(r_lo, r_hi, t.o, t.inv, nx, ny, nz, t.tmin, t.tmax, tr);
+        }
+        const bool both = hl && hr;
+        cur = both ? (neg ? ref_r : ref_l) : (hl ? ref_l : (hr ? ref_r : ST_POP));
+        if (both) {
+            if (t.sp >= STACK_DEPTH - 6) { *err = 1; t.sp = 0; cur = ST_DONE; }
+            else stack.put(t.sp++, ((unsigned long long)__float_as_uint(neg ? tl : tr) << 32) | (neg ? ref_l : ref_r));
+        }
+    }
+#pragma unroll
+    for (int k = 0; k < 2; ++k) { // bounded pops (see step_nodes); entry 0 of the stack is the ST_DONE sentinel
+        if (cur == ST_POP) {
+            const unsigned long long e = stack.get(--t.sp);
+            const uint32_t ref = (uint32_t)e;
+            if ((ref & ST_INSTANCE) || __uint_as_float((uint32_t)(e >> 32)) < t.tmax) cur = ref;
+        }
+    }
+    t.cur = cur;
+}
+template <bool HOME>
+__device__ __forceinline__ void accept_hit(TraceState& t, const RayHome* home, uint32_t inst, uint32_t prim, float b1, float b2) {
+    if (HOME) {
+        if (home->type == 0) __stcs(home->hit, make_uint4(inst, prim, __float_as_uint(b1), __float_as_uint(b2)));
+        else if (home->type == 2) __stcs(home->a_w, __uint_as_float(inst));
+    } else { t.h_prim = prim; t.h_b1 = b1; t.h_b2 = b2; t.h_inst = inst; }
+    t.found = true;
+}
+template <bool STATS, bool HOME = false>
+__device__ __forceinline__ void step_triangle(TraceState& t, Cnt& cnt, const RayHome* home = nullptr) {
     const uint32_t cur = t.cur;
     const uint32_t a = cur & 0x01ffffffu, n = (cur >> 25) & 31u;
     uint32_t next = n > 1 ? (REF_LEAF | ((n - 1) << 25) | (a + 1)) : ST_POP;
@@ -526,31 +608,46 @@ __device__ __forceinline__ void step_triangle(TraceState& t, Cnt& cnt) {
         const bool ok = dd != 0.0f && !(b1 < 0.0f || b1 > 1.0f) && !(b2 < 0.0f || b1 + b2 > 1.0f) && !(tt < t.tmin || tt > t.tmax);
         if (ok) {
             t.tmax = tt;
-            t.h_prim = __float_as_uint(v0.w); t.h_b1 = b1; t.h_b2 = b2; t.h_inst = t.level_inst;
-            t.found = true;
+            accept_hit<HOME>(t, home, t.level_inst, __float_as_uint(v0.w), b1, b2);
             if (t.any_hit) { t.sp = 0; next = ST_DONE; } // occlusion only: any accepted hit answers the query
         }
     }
     t.cur = next;
 }
-template <bool STATS, bool ANIM, class Stack>
-__device__ __forceinline__ void step_other(const DScene& sc, TraceState& t, const Stack& stack, Cnt& cnt) {
-    const uint32_t cur = t.cur;
+// HOME also FUSES the chains of non-node micro-steps every ray goes through (each one otherwise costs the lane a whole
+// scheduling cycle of the phased loop): a TLAS leaf pushes all but its first instance and tests that one at once; entering a
+// mesh tests the mesh's root box at once with the transformed ray (a miss leaves the traversal state untouched — what
+// enter + root miss + pop RETURN + restore amounts to). Operations per ray, their order and the counters are unchanged.
+template <bool STATS, bool ANIM, bool HOME = false, class Stack>
+__device__ __forceinline__ void step_other(const DScene& sc, TraceState& t, const Stack& stack, Cnt& cnt, const RayHome* home = nullptr) {
+    uint32_t cur = t.cur;
     uint32_t next = ST_POP;
+    bool inst_now = false;
     if ((cur & REF_TAG) == REF_LEAF) { // TLAS leaf: its instances pop in the reference's order (bvh.rs:95-98)
         const uint32_t a = cur & 0x01ffffffu, n = (cur >> 25) & 31u;
-        for (uint32_t k = a + n; k-- > a;) stack.put(t.sp++, ST_INSTANCE | k);
+        if (HOME) {
+            for (uint32_t k = a + n; k-- > a + 1;) stack.put(t.sp++, ST_INSTANCE | k);
+            cur = ST_INSTANCE | a; inst_now = n != 0;
+        } else
+            for (uint32_t k = a + n; k-- > a;) stack.put(t.sp++, ST_INSTANCE | k);
     } else if (cur == ST_ROOT) {
-        const float4 lo = __ldg(&t.bvh->root_lo), hi = __ldg(&t.bvh->root_hi);
+        const DBvh* bvh = t.bvh;
+        if (HOME) bvh = t.level_inst == TRB_MISS ? sc.tlas : &sc.meshes[__ldg(&sc.instances[t.level_inst].mesh)].bvh; // (fused paths never get here for a mesh)
+        const float4 lo = __ldg(&bvh->root_lo), hi = __ldg(&bvh->root_hi);
         if (STATS) cnt.node++;
         float te;
         if (box_hit(lo, hi, t.o, t.inv, (t.neg & 1u) != 0, (t.neg & 2u) != 0, (t.neg & 4u) != 0, t.tmin, t.tmax, te)) next = __float_as_uint(t.quad ? hi.w : lo.w);
     } else if (cur == ST_RETURN) {
-        t.o = t.wo; t.d = t.wd; t.inv = t.winv;
+        if (HOME) { // the world ray, as trace_init made it
+            const float4 o4 = __ldcs(home->org), d4 = __ldcs(home->dir);
+            t.o = mk(o4.x, o4.y, o4.z); t.d = mk(d4.x, d4.y, d4.z);
+            t.inv = mk(1.0f / t.d.x, 1.0f / t.d.y, 1.0f / t.d.z);
+        } else { t.o = t.wo; t.d = t.wd; t.inv = t.winv; }
         t.neg = neg_mask(t.d);
         trace_level(t, sc.tlas, sc.tlas_pairs, sc.tlas_quads);
         t.level_inst = TRB_MISS;
-    } else { // Instance::intersect for one entry of a TLAS leaf
+    } else inst_now = true;
+    if (inst_now) { // Instance::intersect for one entry of a TLAS leaf
         const uint32_t ii = __ldg(&sc.tlas_order[cur & ~REF_TAG]);
         const DInstance& in = sc.instances[ii];
         if (STATS) cnt.inst++;
@@ -558,16 +655,26 @@ __device__ __forceinline__ void step_other(const DScene& sc, TraceState& t, cons
         if (kind != TRB_INST_EMITTER_POINT) {
             float m[16];
             instance_inv<ANIM>(sc, in, t.time, m, t.xf_row);
-            const f3 lo_ = xf_point(m, t.wo), ld_ = xf_vector(m, t.wd);
+            const f3 lo_ = xf_point(m, HOME ? t.o : t.wo), ld_ = xf_vector(m, HOME ? t.d : t.wd); // at the top level the current ray IS the world ray
             if (shape == TRB_SHAPE_MESH) {
                 const DMesh& me = sc.meshes[__ldg(&in.mesh)];
-                t.o = lo_; t.d = ld_;
-                t.inv = mk(1.0f / ld_.x, 1.0f / ld_.y, 1.0f / ld_.z);
-                t.neg = neg_mask(ld_);
-                trace_level(t, &me.bvh, me.bvh.pairs, me.bvh.quads);
-                t.tris = me.tris; t.level_inst = ii;
-                stack.put(t.sp++, ST_RETURN);
+                const f3 inv_ = mk(1.0f / ld_.x, 1.0f / ld_.y, 1.0f / ld_.z);
+                const uint32_t neg_ = neg_mask(ld_);
+                bool enter = true;
                 next = ST_ROOT;
+                if (HOME) { // BVH<Triangle>::intersect starts by testing its root box: do it now
+                    const float4 lo = __ldg(&me.bvh.root_lo), hi = __ldg(&me.bvh.root_hi);
+                    if (STATS) cnt.node++;
+                    float te;
+                    enter = box_hit(lo, hi, lo_, inv_, (neg_ & 1u) != 0, (neg_ & 2u) != 0, (neg_ & 4u) != 0, t.tmin, t.tmax, te);
+                    next = enter ? __float_as_uint(lo.w) : ST_POP;
+                }
+                if (enter) {
+                    t.o = lo_; t.d = ld_; t.inv = inv_; t.neg = neg_;
+                    trace_level(t, &me.bvh, me.bvh.pairs, me.bvh.quads);
+                    t.tris = me.tris; t.level_inst = ii;
+                    stack.put(t.sp++, ST_RETURN);
+                }
             } else {
                 const float p0 = __ldg(&in.p0), p1 = __ldg(&in.p1);
                 float tt = t.tmax;
@@ -577,8 +684,7 @@ __device__ __forceinline__ void step_other(const DScene& sc, TraceState& t, cons
                 else h = rect_t(p0, p1, lo_, ld_, t.tmin, tt);
                 if (h) {
                     t.tmax = tt;
-                    t.h_inst = ii; t.h_prim = 0; t.h_b1 = 0.0f; t.h_b2 = 0.0f;
-                    t.found = true;
+                    accept_hit<HOME>(t, home, ii, 0u, 0.0f, 0.0f);
                     if (t.any_hit) { t.sp = 0; next = ST_DONE; }
                 }
             }
@@ -1805,9 +1911,10 @@ __global__ void __launch_bounds__(256) k_wf_generate(const __grid_constant__ DSc
 // return) that runs only once enough lanes are waiting for one (or no lane has node work left), so triangle tests and
 // instance entries execute with several lanes instead of the two that happen to be there, and the scheduling
 // ballots are paid once per burst.
-template <bool STATS, int MINB, int SMEM_STACK, bool ANIM, bool PHASED, bool QUADS>
+template <bool STATS, int MINB, int SMEM_STACK, bool ANIM, bool PHASED, bool QUADS, int PIPE = 0>
 __global__ void __launch_bounds__(128, MINB) k_wf_trace(const __grid_constant__ DScene sc, const __grid_constant__ RenderParams rp, const __grid_constant__ WfState wf,
                                                          uint32_t round, uint32_t flags, int WF_REFILL_IDLE, uint32_t sched, const uint32_t* __restrict__ q_sorted) {
+    constexpr bool HOME = PHASED && (PIPE & 32) != 0; // RayHome: world ray and hit record live in the path state, not in registers
     uint32_t* cnt_r = wf.counters + round * WF_CNT;
     const uint32_t n_cont = cnt_r[WF_N_CONT], n_shadow = cnt_r[WF_N_SHADOW], n_mis = cnt_r[WF_N_MIS];
     const uint32_t total = n_cont + n_shadow + n_mis;
@@ -1825,7 +1932,17 @@ __global__ void __launch_bounds__(128, MINB) k_wf_trace(const __grid_constant__ 
     int type = 0;
     for (;;) {
         // ---- retire finished rays ----
-        if (have && t.cur == ST_DONE) {
+        if (HOME && have && t.cur == ST_DONE) { // the direction entries stay as they are: only the result words are written
+            if (type == 0) {
+                __stcs(&wf.cont[p].w, t.tmax);
+                if (!t.found) __stcs(&wf.hit[p], make_uint4(TRB_MISS, 0u, 0u, 0u));
+            } else if (type == 1) __stcs(&wf.shadow[p].w, __uint_as_float(t.found ? 1u : 0u));
+            else {
+                __stcs(&wf.mis[p].w, t.tmax);
+                if (!t.found) __stcs(&wf.a[p].w, __uint_as_float(TRB_MISS));
+            }
+            have = false;
+        } else if (have && t.cur == ST_DONE) {
             if (type == 0) {
                 __stcs(&wf.cont[p], make_float4(t.wd.x, t.wd.y, t.wd.z, t.tmax));
                 __stcs(&wf.hit[p], make_uint4(t.found ? t.h_inst : TRB_MISS, t.h_prim, __float_as_uint(t.h_b1), __float_as_uint(t.h_b2)));
@@ -1862,6 +1979,12 @@ __global__ void __launch_bounds__(128, MINB) k_wf_trace(const __grid_constant__ 
                     trace_init(sc, t, ray, type == 1 && shadow_any, ANIM ? __ldg(&wf.thr[p].w) : 0.0f, QUADS && PHASED);
                     t.xf_row = wf_xf_row<ANIM>(wf, p);
                     if (PHASED) { stack.put(0, (unsigned long long)ST_DONE); t.sp = 1; } // bottom sentinel: popping it ends the ray
+                    if (HOME) { // the TLAS root box is every ray's first test: do it here, with all refilled lanes, instead of as a non-node micro-step
+                        const float4 lo = __ldg(&sc.tlas->root_lo), hi = __ldg(&sc.tlas->root_hi);
+                        if (STATS) cnt.node++;
+                        float te;
+                        t.cur = box_hit(lo, hi, t.o, t.inv, (t.neg & 1u) != 0, (t.neg & 2u) != 0, (t.neg & 4u) != 0, t.tmin, t.tmax, te) ? __float_as_uint(lo.w) : ST_POP;
+                    }
                     have = true;
                 }
             }
@@ -1876,15 +1999,19 @@ __global__ void __launch_bounds__(128, MINB) k_wf_trace(const __grid_constant__ 
             for (;;) {
 #pragma unroll
                 for (int k = 0; k < WF_BURST; ++k)
-                    if (trace_is_node(t.cur)) step_nodes<STATS, QUADS>(t, stack, cnt, rp.error_flag);
+                    if (trace_is_node(t.cur)) {
+                        if (PIPE != 0 && !QUADS) step_nodes2<STATS, (PIPE & 1) != 0>(t, stack, cnt, rp.error_flag);
+                        else step_nodes<STATS, QUADS>(t, stack, cnt, rp.error_flag);
+                    }
                 const bool is_a = trace_is_node(t.cur), is_o = !is_a && t.cur != ST_DONE;
                 const unsigned m_a = __ballot_sync(0xffffffffu, is_a), m_o = __ballot_sync(0xffffffffu, is_o);
                 if ((m_a | m_o) == 0) break;
                 if (!exhausted && 32 - __popc(m_a | m_o) >= WF_REFILL_IDLE) break;
                 if (m_o != 0 && (m_a == 0 || __popc(m_o) >= thr_o)) {
                     if (is_o) {
-                        if ((t.cur & REF_TAG) == REF_LEAF && t.level_inst != TRB_MISS) step_triangle<STATS>(t, cnt);
-                        else step_other<STATS, ANIM>(sc, t, stack, cnt);
+                        const RayHome home{&wf.org[p], type == 0 ? &wf.cont[p] : (type == 1 ? &wf.shadow[p] : &wf.mis[p]), &wf.hit[p], &wf.a[p].w, type};
+                        if ((t.cur & REF_TAG) == REF_LEAF && t.level_inst != TRB_MISS) step_triangle<STATS, HOME>(t, cnt, &home);
+                        else step_other<STATS, ANIM, HOME>(sc, t, stack, cnt, &home);
                     }
                 }
             }
