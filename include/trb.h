@@ -432,6 +432,13 @@ trb_status trb_host_keyframe_transform(const trb_keyframe* kf, float* mat16, flo
 trb_status trb_host_quad_check(const trb_bvh_node* nodes, uint32_t n_nodes, const trb_ray* rays, uint32_t n_rays,
                                uint32_t* mismatches, uint64_t* leaf_visits, uint64_t* quad_visits);
 
+/* Device self-check of the trace kernel's short box test (csrc/trb_kernels.cuh box_hit_finite, used for rays whose origin,
+ * direction and 1/direction are all finite) against the literal transcription of BBox::fast_intersect (bbox.rs:75-104) on
+ * n_cases generated boxes and rays built from awkward values (signed zeros, denormals, huge / tiny magnitudes, origins on box
+ * planes, flat boxes). out[0] = cases with an all-finite ray, out[1] = hits among them, out[2] = MISMATCHES (must be 0),
+ * out[3] = cases that take the literal path. Needs a GPU (TRB_NO_DEVICE otherwise). */
+trb_status trb_selftest_box(uint32_t n_cases, uint32_t seed, uint64_t out[4]);
+
 /* AnimatedTransform::transform(time) (animated_transform.rs:40-56) of the transform stack
  * desc->splines[first .. first+count): the same code the device runs per ray for keyframed
  * instances, compiled for the host. AnimatedColor::color(time) (animated_color.rs:52-78) of

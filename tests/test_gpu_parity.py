@@ -246,6 +246,28 @@ def test_edge_cases():
         fresh.render_samples()                                                             # update_frame not called (scene.rs:179)
 
 
+def test_box_hit_finite_selftest_and_forced_literal_path():
+    """The trace kernel's 23-instruction box test (all-finite rays) against the literal transcription of BBox::fast_intersect:
+    generated awkward cases on the device, then a whole render with every ray forced onto the literal path."""
+    trb = F.load_trb()
+    out = (C.c_uint64 * 4)()
+    assert trb.trb_selftest_box(1 << 22, 7, out) == F.TRB_OK, trb.trb_last_error()
+    finite, hits, bad, literal = [int(x) for x in out]
+    assert bad == 0 and finite > 1 << 20 and hits > 1 << 14 and literal > 1 << 16, (finite, hits, bad, literal)
+    desc = SB.scene_c4(20000, 128, 72, 8).finish()
+    g, o = both(desc)
+    kw = dict(block_start=0, block_count=40, sample_first=0, sample_count=4, seed=9)
+    ref, st_o = o.render_samples(**kw)
+    for exact in (0, 1):
+        g.set_option("trace.exact_box", exact)
+        s, _ = g.render_samples(**kw)                                   # the 9-CTA variant
+        s2, st = g.render_samples(flags=F.RENDER_STATS | F.RENDER_REFERENCE_SHADOW, **kw)   # the variant with counters, closest-hit shadow rays
+        assert s.tobytes() == ref.tobytes() and s2.tobytes() == ref.tobytes()
+        assert all(getattr(st, k) == getattr(st_o, k) for k in KEYS)
+    g.set_option("trace.pipe", 0)                                       # round-1 kernel: same results
+    assert g.render_samples(**kw)[0].tobytes() == ref.tobytes()
+
+
 def test_full_size_properties_c4():
     """BASELINE-size workload (1M triangles, 1920x1080): size-independent properties instead of an oracle run."""
     g = api.Scene(SB.scene_c4(1_000_000, 1920, 1080, 4096).finish())

@@ -18,8 +18,8 @@ stats = torch.zeros(10, dtype=torch.int64, device=dev)
 flush = torch.empty(256 << 20, dtype=torch.uint8, device=dev)
 g = api.Scene(SB.scene_c4(1_000_000, W, H, 4096).finish(), 0)
 g.update_frame(0, 0.0, 0.0)
-DEFAULTS = {"sort.mode": 0, "sort.bits": 5, "sort.min_round": 1, "shade.split": 0, "trace.refill": 8, "trace.sched": 6,
-            "trace.occupancy": 7, "trace.grid": 12, "trace.pipe": 0}
+DEFAULTS = {"sort.mode": 0, "sort.bits": 5, "sort.min_round": 1, "shade.split": 0, "trace.refill": 8, "trace.sched": 6, "trace.grid": 0,
+            "trace.pipe": 36}
 ref = None
 
 

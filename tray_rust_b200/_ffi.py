@@ -141,7 +141,7 @@ TRB_SYMBOLS = [
     "trb_render", "trb_render_device", "trb_intersect", "trb_intersect_device", "trb_camera_rays",
     "trb_render_samples", "trb_film_to_srgb8", "trb_block_list", "trb_scene_get_bvh", "trb_scene_get_transform",
     "trb_scene_get_filter_table", "trb_last_error", "trb_abi_version", "trb_desc_load_json", "trb_desc_free",
-    "trb_host_build_bvh", "trb_host_keyframe_transform", "trb_host_animated_transform", "trb_host_animated_color", "trb_host_quad_check", "trb_launch_count", "trb_scene_trace_time", "trb_scene_check_error", "trb_scene_set_option", "trb_write_png",
+    "trb_host_build_bvh", "trb_host_keyframe_transform", "trb_host_animated_transform", "trb_host_animated_color", "trb_host_quad_check", "trb_selftest_box", "trb_launch_count", "trb_scene_trace_time", "trb_scene_check_error", "trb_scene_set_option", "trb_write_png",
     "trb_nccl_unique_id", "trb_comm_create", "trb_comm_destroy", "trb_comm_info", "trb_comm_reduce_film", "trb_render_sharded",
     "trb_group_create", "trb_group_load_json", "trb_group_render", "trb_group_scene", "trb_group_destroy",
 ]
@@ -191,6 +191,7 @@ def load_trb():
     lib.trb_host_animated_transform.argtypes = [C.POINTER(SceneDesc), u32, u32, f32, vp, vp]
     lib.trb_host_animated_color.argtypes = [C.POINTER(SceneDesc), u32, u32, f32, vp]
     lib.trb_host_quad_check.argtypes = [vp, u32, vp, u32, C.POINTER(u32), C.POINTER(C.c_uint64), C.POINTER(C.c_uint64)]
+    lib.trb_selftest_box.argtypes = [u32, u32, C.POINTER(C.c_uint64)]
     lib.trb_launch_count.restype = C.c_uint64
     lib.trb_scene_trace_time.argtypes = [vp, C.POINTER(f32), C.POINTER(u32)]
     lib.trb_write_png.argtypes = [C.c_char_p, vp, u32, u32]

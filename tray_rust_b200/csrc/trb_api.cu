@@ -161,6 +161,7 @@ struct Tuning {
     unsigned trace_grid = 0;   // trace: CTAs per SM launched (0 = twice what the chosen variant keeps resident)
     uint32_t sched = 6;        // trace: quorum of the phased loop (0 = flat state machine)
     int quads = 0;             // trace: DQuad two-level records (measured slower on C4)
+    int exact_box = 0;         // trace: test option — every ray takes the literal BBox::fast_intersect transcription (box_hit) instead of box_hit_finite
     int pipe = 36;             // trace: kernel variant. 0 = round-1 kernel; 1 = + box_hit_finite; 33 = + RayHome + fused non-node chains at 7 CTAs per SM; 34 / 35 / 36 / 37 = the same at 8 / 8 / 9 / 9 CTAs with 16 / 12 / 12 / 8 stack entries in shared memory
     int film_v2 = 1;           // film: per-warp private tiles (0 = shared-memory atomics)
     int sort = 0;              // ray queues: 0 = path order; 1 / 2 = counting sort by (octant, origin cell) / (cell, octant) before each trace round (measured: -1.5 % trace time, +10 % step time on C4)
@@ -477,7 +478,7 @@ trb_status launch_wavefront(trb_scene* s, const trb::RenderParams& rp, uint32_t 
     const unsigned tgrid = (unsigned)s->sm_count * (tu.trace_grid ? tu.trace_grid : 2u * resident);
     const uint32_t sched = tu.sched;   // 0 = flat state machine; else the quorum of the phased loop (see k_wf_trace)
     const bool quads = tu.quads != 0;  // DQuad two-level records (never in the STATS variants: their counters are the reference's)
-    const uint32_t tflags = flags;
+    const uint32_t tflags = flags | (tu.exact_box ? trb::WF_TRACE_FORCE_EXACT_BOX : 0u);
     for (uint32_t round = 0; round < rounds; ++round) {
         const uint32_t* q_sorted = nullptr;
         if (tu.sort && (int)round >= tu.sort_min_round) { // counting sort of this round's rays by (type, octant, origin cell): DESIGN.md "Ray sorting"
@@ -634,6 +635,7 @@ trb_status trb_scene_set_option(trb_scene* s, const char* name, long long value)
     else if (k == "trace.sched") t.sched = (uint32_t)value;
     else if (k == "trace.quads") t.quads = (int)value;
     else if (k == "trace.pipe") t.pipe = (int)value;
+    else if (k == "trace.exact_box") t.exact_box = (int)value;
     else if (k == "film.v2") t.film_v2 = (int)value;
     else if (k == "sort.mode") t.sort = (int)value;
     else if (k == "sort.bits") t.sort_bits = (int)std::min<long long>(6, std::max<long long>(1, value));
@@ -1282,6 +1284,23 @@ trb_status trb_host_keyframe_transform(const trb_keyframe* kf, float* mat16, flo
 // (b) through the DQuad records with quad_visit — the function the trace kernel runs — and the two must visit the same
 // leaves in the same order with the same max_t history. Leaves "hit" pseudo-randomly (a hash of leaf and ray decides a
 // distance) so that max_t shrinks during the walk. Returns the number of rays whose walks differ.
+trb_status trb_selftest_box(uint32_t n_cases, uint32_t seed, uint64_t out[4]) {
+    if (!out || n_cases == 0) return fail(TRB_INVALID_ARG, "null argument");
+    int n_dev = 0;
+    if (cudaGetDeviceCount(&n_dev) != cudaSuccess || n_dev == 0) { cudaGetLastError(); return fail(TRB_NO_DEVICE, "no CUDA device"); }
+    unsigned long long* d = nullptr;
+    CU(cudaMalloc(&d, 4 * sizeof(unsigned long long)));
+    cudaMemset(d, 0, 4 * sizeof(unsigned long long));
+    trb::k_selftest_box<<<(n_cases + 255) / 256, 256>>>(n_cases, seed, d);
+    g_launches++;
+    unsigned long long h[4] = {0, 0, 0, 0};
+    const cudaError_t e = cudaMemcpy(h, d, sizeof h, cudaMemcpyDeviceToHost);
+    cudaFree(d);
+    if (e != cudaSuccess) return fail(TRB_CUDA, cudaGetErrorString(e));
+    for (int k = 0; k < 4; ++k) out[k] = h[k];
+    return TRB_OK;
+}
+
 trb_status trb_host_quad_check(const trb_bvh_node* nodes, uint32_t n_nodes, const trb_ray* rays, uint32_t n_rays, uint32_t* mismatches,
                                uint64_t* leaf_visits, uint64_t* quad_visits) {
     if (!nodes || !rays || !mismatches || n_nodes == 0) return fail(TRB_INVALID_ARG, "null argument");

@@ -31,15 +31,20 @@ __device__ __forceinline__ f3 splat(float v) { return mk(v, v, v); }
 __device__ __forceinline__ f3 operator+(f3 a, f3 b) { return mk(a.x + b.x, a.y + b.y, a.z + b.z); }
 __device__ __forceinline__ f3 operator-(f3 a, f3 b) { return mk(a.x - b.x, a.y - b.y, a.z - b.z); }
 __device__ __forceinline__ f3 operator*(f3 a, f3 b) { return mk(a.x * b.x, a.y * b.y, a.z * b.z); }
-__device__ __forceinline__ f3 operator/(f3 a, f3 b) { return mk(a.x / b.x, a.y / b.y, a.z / b.z); }
+// a / b and sqrtf(a) under a name (div.rn / sqrt.rn, inlined). Calling them out of line shrinks the fused shade kernel from 312 KB
+// to 249 KB (nvcc expands every division into ~15 instructions; 526 sites) but costs 6.5 ms per C4 step: measured and reverted
+// (profiles/r02_c13_shade_outlined_division.log).
+__device__ __forceinline__ float ieee_div(float a, float b) { return a / b; }
+__device__ __forceinline__ float ieee_sqrt(float a) { return sqrtf(a); }
+__device__ __forceinline__ f3 operator/(f3 a, f3 b) { return mk(ieee_div(a.x, b.x), ieee_div(a.y, b.y), ieee_div(a.z, b.z)); }
 __device__ __forceinline__ f3 operator*(f3 a, float s) { return mk(a.x * s, a.y * s, a.z * s); }
 __device__ __forceinline__ f3 operator*(float s, f3 a) { return mk(s * a.x, s * a.y, s * a.z); }
-__device__ __forceinline__ f3 operator/(f3 a, float s) { return mk(a.x / s, a.y / s, a.z / s); }
+__device__ __forceinline__ f3 operator/(f3 a, float s) { return mk(ieee_div(a.x, s), ieee_div(a.y, s), ieee_div(a.z, s)); }
 __device__ __forceinline__ f3 operator-(f3 a) { return mk(-a.x, -a.y, -a.z); }
 __device__ __forceinline__ float dot3(f3 a, f3 b) { return a.x * b.x + a.y * b.y + a.z * b.z; }
 __device__ __forceinline__ f3 cross3(f3 a, f3 b) { return mk(a.y * b.z - a.z * b.y, a.z * b.x - a.x * b.z, a.x * b.y - a.y * b.x); }
 __device__ __forceinline__ float len2(f3 a) { return a.x * a.x + a.y * a.y + a.z * a.z; }
-__device__ __forceinline__ f3 unit(f3 a) { float l = sqrtf(len2(a)); return mk(a.x / l, a.y / l, a.z / l); } // Vector::normalized: 3 divides
+__device__ __forceinline__ f3 unit(f3 a) { float l = ieee_sqrt(len2(a)); return mk(ieee_div(a.x, l), ieee_div(a.y, l), ieee_div(a.z, l)); } // Vector::normalized: 3 divides
 __device__ __forceinline__ bool black(f3 c) { return c.x == 0.0f && c.y == 0.0f && c.z == 0.0f; }
 __device__ __forceinline__ float clampf(float x, float lo, float hi) { return x < lo ? lo : (x > hi ? hi : x); }
 __device__ __forceinline__ float lerpf(float t, float a, float b) { return a * (1.0f - t) + b * t; }
@@ -281,6 +286,7 @@ struct TraceState {
     bool quad;            // this level is traversed through the DQuad records (finite 1/d only, see trb_device.h)
     bool quads_ok;        // the kernel variant may use DQuad records at all
     bool exact_box;       // the current level's ray has a zero, NaN or infinite component: literal box_hit (see box_hit_finite)
+    bool force_exact;     // test option "trace.exact_box": every ray takes the literal box_hit
     const DTri* tris;
     uint32_t level_inst;  // instance whose mesh is being traversed, TRB_MISS at the top level
     float tmin, tmax;
@@ -296,12 +302,12 @@ __device__ __forceinline__ uint32_t neg_mask(f3 d) { return (d.x < 0.0f ? 1u : 0
 __device__ __forceinline__ bool finite3(f3 v) { return fabsf(v.x) < finf() && fabsf(v.y) < finf() && fabsf(v.z) < finf(); }
 __device__ __forceinline__ void trace_level(TraceState& t, const DBvh* bvh, const DPair* pairs, const DQuad* quads) {
     t.bvh = bvh;
-    t.exact_box = !(finite3(t.o) && finite3(t.d) && finite3(t.inv));
+    t.exact_box = t.force_exact || !(finite3(t.o) && finite3(t.d) && finite3(t.inv));
     t.quad = t.quads_ok && finite3(t.inv);
     t.pairs = t.quad ? reinterpret_cast<const DPair*>(quads) : pairs;
 }
-__device__ __forceinline__ void trace_init(const DScene& sc, TraceState& t, const Ray& ray, bool any_hit, float time, bool quads_ok = false) {
-    t.time = time; t.quads_ok = quads_ok; t.xf_row = nullptr;
+__device__ __forceinline__ void trace_init(const DScene& sc, TraceState& t, const Ray& ray, bool any_hit, float time, bool quads_ok = false, bool force_exact = false) {
+    t.time = time; t.quads_ok = quads_ok; t.xf_row = nullptr; t.force_exact = force_exact;
     t.wo = ray.o; t.wd = ray.d;
     t.winv = mk(1.0f / ray.d.x, 1.0f / ray.d.y, 1.0f / ray.d.z);
     t.o = t.wo; t.d = t.wd; t.inv = t.winv;
@@ -458,6 +464,7 @@ __device__ __forceinline__ void trace_step(const DScene& sc, TraceState& t, cons
 // state: ncu showed the triangle code running with 2.2 of 32 lanes and the pop loop with 4.
 // ------------------------------------------------------------------------------------------
 constexpr uint32_t ST_POP = 0xfffffffcu; // control: take the next reference off the stack
+constexpr uint32_t WF_TRACE_FORCE_EXACT_BOX = 0x40000000u; // k_wf_trace flag (option "trace.exact_box"): see TraceState::force_exact
 constexpr int WF_BURST = 3;
 __device__ __forceinline__ bool trace_is_node(uint32_t cur) { return (cur & REF_TAG) == REF_INTERIOR || cur == ST_POP; }
 template <bool STATS, bool QUADS, class Stack>
@@ -530,6 +537,38 @@ __device__ __forceinline__ bool box_hit_finite(const float4 lo, const float4 hi,
     const float m = fmaxf(fmaxf(ax, ay), az), M = fminf(fminf(bx, by), bz);
     t_entry = m;
     return m <= M && m < tmax_r && M > tmin_r;
+}
+// Self-test (trb_selftest_box): box_hit_finite against the literal box_hit on generated boxes and rays whose components are
+// drawn from a table of awkward values (zeros of both signs, denormals, huge and tiny magnitudes, planes equal to the ray origin,
+// degenerate boxes) mixed with random ones. For every all-finite ray the hit flags must agree and, on a hit, the entry
+// distances must compare equal (a zero's sign may differ). out[0] = cases with an all-finite ray, out[1] = hits among
+// them, out[2] = mismatches, out[3] = cases that take the literal path (a zero / NaN / infinite component).
+__device__ __forceinline__ float selftest_value(uint32_t h) {
+    const float table[16] = {0.0f, -0.0f, 1.0f, -1.0f, 0.5f, -0.5f, 1e-30f, -1e-30f, 1e30f, -1e30f, 3.0e38f, -3.0e38f, 1e-40f, -1e-40f, 2.0f, 1.17549435e-38f};
+    if ((h & 3u) == 0) return table[(h >> 2) & 15u];
+    const float u = (float)(h >> 8) * (1.0f / 16777216.0f);
+    return (h & 4u) ? (u * 2.0f - 1.0f) * 30.0f : (u * 2.0f - 1.0f);
+}
+__global__ void k_selftest_box(uint32_t n, uint32_t seed, unsigned long long* out) {
+    const uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    uint32_t h = rng_absorb(rng_seed(seed), i);
+    float v[14];
+    for (int k = 0; k < 14; ++k) { h = mix32(h + 0x9e3779b9u); v[k] = selftest_value(h); }
+    const float4 lo = make_float4(fminf(v[0], v[3]), fminf(v[1], v[4]), fminf(v[2], v[5]), 0.0f), hi = make_float4(fmaxf(v[0], v[3]), fmaxf(v[1], v[4]), fmaxf(v[2], v[5]), 0.0f);
+    f3 o = mk(v[6], v[7], v[8]);
+    if ((h & 0x30u) == 0) o.x = lo.x;      // origin exactly on a plane
+    if ((h & 0xc0u) == 0) o.y = hi.y;
+    const f3 d = mk(v[9], v[10], v[11]);
+    const f3 inv = mk(1.0f / d.x, 1.0f / d.y, 1.0f / d.z);
+    const float tmin = (h & 0x100u) ? 0.0f : 0.001f, tmax = (h & 0x200u) ? finf() : fabsf(v[12]) * 40.0f;
+    const bool nx = d.x < 0.0f, ny = d.y < 0.0f, nz = d.z < 0.0f;
+    if (!(finite3(o) && finite3(d) && finite3(inv))) { atomicAdd(&out[3], 1ull); return; }
+    float ta = 0.0f, tb = 0.0f;
+    const bool a = box_hit(lo, hi, o, inv, nx, ny, nz, tmin, tmax, ta), b = box_hit_finite(lo, hi, o, inv, nx, ny, nz, tmin, tmax, tb);
+    atomicAdd(&out[0], 1ull);
+    if (a) atomicAdd(&out[1], 1ull);
+    if (a != b || (a && !(ta == tb))) atomicAdd(&out[2], 1ull);
 }
 // step_nodes for pair records with box_hit_finite for the lanes whose ray is all-finite (operations per ray, hits, t and
 // counters unchanged). What else was tried on this micro-step in round 2 and measured slower on C4, per-sample radiance
@@ -790,10 +829,10 @@ __device__ __forceinline__ void concentric_disk(float u0, float u1, float& ox, f
     if (s0 == 0.0f && s1 == 0.0f) { ox = s0; oy = s1; return; }
     float radius, theta;
     if (s0 >= -s1) {
-        if (s0 > s1) { radius = s0; theta = s1 > 0.0f ? s1 / s0 : 8.0f + s1 / s0; }
-        else { radius = s1; theta = 2.0f - s0 / s1; }
-    } else if (s0 <= s1) { radius = -s0; theta = 4.0f + s1 / s0; }
-    else { radius = -s1; theta = 6.0f - s0 / s1; }
+        if (s0 > s1) { radius = s0; theta = s1 > 0.0f ? ieee_div(s1, s0) : 8.0f + ieee_div(s1, s0); }
+        else { radius = s1; theta = 2.0f - ieee_div(s0, s1); }
+    } else if (s0 <= s1) { radius = -s0; theta = 4.0f + ieee_div(s1, s0); }
+    else { radius = -s1; theta = 6.0f - ieee_div(s0, s1); }
     theta = theta * TRB_PIO4;
     float sn, cs;
     dsincos(theta, sn, cs);
@@ -802,11 +841,11 @@ __device__ __forceinline__ void concentric_disk(float u0, float u1, float& ox, f
 __device__ __forceinline__ f3 cos_hemisphere(float u0, float u1) { // mc.rs:11-16
     float dx, dy;
     concentric_disk(u0, u1, dx, dy);
-    return mk(dx, dy, sqrtf(fmaxf(0.0f, 1.0f - dx * dx - dy * dy)));
+    return mk(dx, dy, ieee_sqrt(fmaxf(0.0f, 1.0f - dx * dx - dy * dy)));
 }
 __device__ __forceinline__ float power_heuristic(float pf, float pg) { // mc.rs:56-60 with n_f = n_g = 1
     float f = 1.0f * pf, g = 1.0f * pg;
-    return (f * f) / (f * f + g * g);
+    return ieee_div(f * f, f * f + g * g);
 }
 
 // ------------------------------------------------------------------------------------------
@@ -938,10 +977,10 @@ __device__ __forceinline__ bool type_matches(uint32_t type, uint32_t flags) { re
 
 // trig helpers (bxdf/mod.rs:125-166)
 __device__ __forceinline__ float sin2_theta(f3 v) { return fmaxf(0.0f, 1.0f - v.z * v.z); }
-__device__ __forceinline__ float sin_theta(f3 v) { return sqrtf(sin2_theta(v)); }
-__device__ __forceinline__ float tan_theta(f3 v) { float s2 = sin2_theta(v); return s2 <= 0.0f ? 0.0f : sqrtf(s2) / v.z; }
-__device__ __forceinline__ float cos_phi(f3 v) { float s = sin_theta(v); return s == 0.0f ? 1.0f : clampf(v.x / s, -1.0f, 1.0f); }
-__device__ __forceinline__ float sin_phi(f3 v) { float s = sin_theta(v); return s == 0.0f ? 0.0f : clampf(v.y / s, -1.0f, 1.0f); }
+__device__ __forceinline__ float sin_theta(f3 v) { return ieee_sqrt(sin2_theta(v)); }
+__device__ __forceinline__ float tan_theta(f3 v) { float s2 = sin2_theta(v); return s2 <= 0.0f ? 0.0f : ieee_div(ieee_sqrt(s2), v.z); }
+__device__ __forceinline__ float cos_phi(f3 v) { float s = sin_theta(v); return s == 0.0f ? 1.0f : clampf(ieee_div(v.x, s), -1.0f, 1.0f); }
+__device__ __forceinline__ float sin_phi(f3 v) { float s = sin_theta(v); return s == 0.0f ? 0.0f : clampf(ieee_div(v.y, s), -1.0f, 1.0f); }
 __device__ __forceinline__ bool same_hemi(f3 a, f3 b) { return a.z * b.z > 0.0f; }
 
 // fresnel.rs. Conductor for the metals, Dielectric(1, eta) for glass, Dielectric(1, 1.5) for plastic (Q16).
@@ -961,38 +1000,38 @@ __device__ __forceinline__ f3 fresnel(const Mat& m, float cos_i) {
     dielectric_etas(m, eta_i, eta_t);
     const float ci = clampf(cos_i, -1.0f, 1.0f); // fresnel.rs:48-66
     const float ei = ci > 0.0f ? eta_i : eta_t, et = ci > 0.0f ? eta_t : eta_i;
-    const float sin_t = ei / et * sqrtf(fmaxf(0.0f, 1.0f - ci * ci));
+    const float sin_t = ieee_div(ei, et) * ieee_sqrt(fmaxf(0.0f, 1.0f - ci * ci));
     if (sin_t >= 1.0f) return splat(1.0f);
-    const float ct = sqrtf(fmaxf(0.0f, 1.0f - sin_t * sin_t));
+    const float ct = ieee_sqrt(fmaxf(0.0f, 1.0f - sin_t * sin_t));
     const float aci = fabsf(ci);
-    const float r_par = (et * aci - ei * ct) / (et * aci + ei * ct); // fresnel.rs:10-14
-    const float r_perp = (ei * aci - et * ct) / (ei * aci + et * ct);
+    const float r_par = ieee_div(et * aci - ei * ct, et * aci + ei * ct); // fresnel.rs:10-14
+    const float r_perp = ieee_div(ei * aci - et * ct, ei * aci + et * ct);
     return splat(0.5f * (r_par * r_par + r_perp * r_perp));
 }
 // microfacet/beckmann.rs
 __device__ __forceinline__ float beck_d(float width, f3 wh) { // :26-35
     const float c2 = wh.z * wh.z;
-    const float tan_sqr = sin2_theta(wh) / c2;
+    const float tan_sqr = ieee_div(sin2_theta(wh), c2);
     if (isinf(tan_sqr)) return 0.0f;
     const float c4 = c2 * c2;
     const float w2 = width * width;
-    return dexp(-tan_sqr / w2) / (TRB_PI * w2 * c4);
+    return ieee_div(dexp(ieee_div(-tan_sqr, w2)), TRB_PI * w2 * c4);
 }
 __device__ __forceinline__ f3 beck_sample(float width, float u0, float u1) { // :36-46
     float ls = dlog(1.0f - u0);
     if (isinf(ls)) ls = 0.0f;
     const float tan2 = -(width * width) * ls;
     const float phi = 2.0f * TRB_PI * u1;
-    const float ct = 1.0f / sqrtf(1.0f + tan2);
-    const float st = sqrtf(fmaxf(0.0f, 1.0f - ct * ct));
+    const float ct = ieee_div(1.0f, ieee_sqrt(1.0f + tan2));
+    const float st = ieee_sqrt(fmaxf(0.0f, 1.0f - ct * ct));
     float sn, cs;
     dsincos(phi, sn, cs);
     return mk(st * cs, st * sn, ct); // linalg::spherical_dir
 }
 __device__ __forceinline__ float beck_pdf(float width, f3 wh) { return fabsf(wh.z) * beck_d(width, wh); }
 __device__ __forceinline__ float beck_g1(float width, f3 v) { // :56-64
-    const float a = 1.0f / (width * fabsf(tan_theta(v)));
-    if (a < 1.6f) { const float a2 = a * a; return (3.535f * a + 2.181f * a2) / (1.0f + 2.276f * a + 2.577f * a2); }
+    const float a = ieee_div(1.0f, width * fabsf(tan_theta(v)));
+    if (a < 1.6f) { const float a2 = a * a; return ieee_div(3.535f * a + 2.181f * a2, 1.0f + 2.276f * a + 2.577f * a2); }
     return 1.0f;
 }
 __device__ __forceinline__ bool refract3(f3 w, f3 n, float eta, f3& out) { // linalg/mod.rs:117-127
@@ -1000,7 +1039,7 @@ __device__ __forceinline__ bool refract3(f3 w, f3 n, float eta, f3& out) { // li
     const float s1 = fmaxf(0.0f, 1.0f - c1 * c1);
     const float s2 = eta * eta * s1;
     if (s2 >= 1.0f) return false;
-    const float c2 = sqrtf(1.0f - s2);
+    const float c2 = ieee_sqrt(1.0f - s2);
     out = eta * -w + (eta * c1 - c2) * n;
     return true;
 }
@@ -1014,7 +1053,7 @@ __device__ __forceinline__ float mt_jacobian(f3 wo, f3 wi, f3 wh, float e0, floa
     const float ih = dot3(wi, wh), oh = dot3(wo, wh);
     const float s = e1 * ih + e0 * oh;
     const float denom = s * s;
-    if (denom != 0.0f) return fabsf(e0 * e0 * fabsf(oh) / denom);
+    if (denom != 0.0f) return fabsf(ieee_div(e0 * e0 * fabsf(oh), denom));
     return 0.0f;
 }
 __device__ __forceinline__ f3 mt_half(f3 wo, f3 wi, float e0, float e1) { return unit(-e1 * wi - e0 * wo); } // :50-52
@@ -1037,7 +1076,7 @@ __device__ __noinline__ f3 merl_eval(const float* __restrict__ table, f3 wo, f3 
     float phi_d = datan2(wd.y, wd.x);
     if (phi_d < 0.0f) phi_d = phi_d + TRB_PI * 2.0f;
     if (phi_d > TRB_PI) phi_d = phi_d - TRB_PI;
-    const uint32_t ih = merl_index(sqrtf(fmaxf(0.0f, 2.0f * theta_h / TRB_PI)), 1.0f, TRB_MERL_N_THETA_H);
+    const uint32_t ih = merl_index(ieee_sqrt(fmaxf(0.0f, 2.0f * theta_h / TRB_PI)), 1.0f, TRB_MERL_N_THETA_H);
     const uint32_t id = merl_index(theta_d, TRB_PI / 2.0f, TRB_MERL_N_THETA_D);
     const uint32_t ip = merl_index(phi_d, TRB_PI, TRB_MERL_N_PHI_D);
     const uint32_t i = ip + TRB_MERL_N_PHI_D * (id + ih * TRB_MERL_N_THETA_D);
@@ -1052,8 +1091,8 @@ __device__ f3 lobe_eval(const DScene& sc, const Mat& m, int kind, f3 col, f3 wo,
             float max_cos = 0.0f;
             if (si > 1e-4f && so > 1e-4f) max_cos = fmaxf(0.0f, cos_phi(wi) * cos_phi(wo) + sin_phi(wi) * sin_phi(wo));
             float sin_alpha, tan_beta;
-            if (fabsf(wi.z) > fabsf(wo.z)) { sin_alpha = so; tan_beta = si / fabsf(wi.z); }
-            else { sin_alpha = si; tan_beta = so / fabsf(wo.z); }
+            if (fabsf(wi.z) > fabsf(wo.z)) { sin_alpha = so; tan_beta = ieee_div(si, fabsf(wi.z)); }
+            else { sin_alpha = si; tan_beta = ieee_div(so, fabsf(wo.z)); }
             return col * TRB_INV_PI * (m.on_a + m.on_b * max_cos * sin_alpha * tan_beta);
         }
         case LK_TS: { // torrance_sparrow.rs:40-56
@@ -1078,7 +1117,7 @@ __device__ f3 lobe_eval(const DScene& sc, const Mat& m, int kind, f3 col, f3 wo,
             const float g = beck_g1(m.width, wi) * beck_g1(m.width, wo);
             const float ih = dot3(wi, wh);
             const float jac = mt_jacobian(wo, wi, wh, e0, e1);
-            return col * (fabsf(ih) / (fabsf(wi.z) * fabsf(wo.z))) * (f * g * d) * jac;
+            return col * ieee_div(fabsf(ih), fabsf(wi.z) * fabsf(wo.z)) * (f * g * d) * jac;
         }
         case LK_MERL: return merl_eval(sc.merl + m.merl_off, wo, wi);
         default: return splat(0.0f); // specular lobes (specular_reflection.rs:38, specular_transmission.rs:38)
@@ -1089,7 +1128,7 @@ __device__ float lobe_pdf(const Mat& m, int kind, f3 wo, f3 wi) {
         case LK_TS: { // torrance_sparrow.rs:73-81
             if (!same_hemi(wo, wi)) return 0.0f;
             const f3 wh = unit(wo + wi);
-            const float jac = 1.0f / (4.0f * fabsf(dot3(wo, wh)));
+            const float jac = ieee_div(1.0f, 4.0f * fabsf(dot3(wo, wh)));
             return beck_pdf(m.width, wh) * jac;
         }
         case LK_MT: { // microfacet_transmission.rs:100-108
@@ -1186,7 +1225,7 @@ __device__ __noinline__ float bsdf_pdf(const Mat& m, const Frame& fr, f3 wo_w, f
         int kind; uint32_t type; f3 col;
         if (lobe_of(m, i, kind, type, col) && type_matches(type, flags)) { pdf = pdf + lobe_pdf(m, kind, wo, wi); n++; }
     }
-    return n > 0 ? pdf / (float)n : 0.0f;
+    return n > 0 ? ieee_div(pdf, (float)n) : 0.0f;
 }
 __device__ __noinline__ void bsdf_sample(const DScene& sc, const Mat& m, const Frame& fr, f3 wo_w, uint32_t flags, float u0, float u1, float uc,
                                          f3& f, f3& wi_w, float& pdf, uint32_t& sampled) { // bsdf.rs:85-112
@@ -1222,7 +1261,7 @@ __device__ __forceinline__ float shape_area(uint32_t shape, float p0, float p1) 
 __device__ __forceinline__ void shape_sample_uniform(uint32_t shape, float p0, float p1, float u0, float u1, f3& p, f3& n) {
     if (shape == TRB_SHAPE_SPHERE) { // sphere.rs:92-95, mc::uniform_sample_sphere
         const float z = 1.0f - 2.0f * u0;
-        const float r = sqrtf(fmaxf(0.0f, 1.0f - z * z));
+        const float r = ieee_sqrt(fmaxf(0.0f, 1.0f - z * z));
         const float phi = TRB_PI * 2.0f * u1;
         float sn, cs;
         dsincos(phi, sn, cs);
@@ -1243,9 +1282,9 @@ __device__ void shape_sample(uint32_t shape, float p0, float p1, f3 pt, float u0
     const f3 wz = unit(splat(0.0f) - pt);
     f3 wx, wy;
     coord_system(wz, wx, wy);
-    const float ctm = sqrtf(fmaxf(0.0f, 1.0f - p0 * p0 / dist_sqr));
+    const float ctm = ieee_sqrt(fmaxf(0.0f, 1.0f - ieee_div(p0 * p0, dist_sqr)));
     const float ct = lerpf(u0, ctm, 1.0f); // mc::uniform_sample_cone_frame (mc.rs:77-83)
-    const float st = sqrtf(1.0f - ct * ct);
+    const float st = ieee_sqrt(1.0f - ct * ct);
     const float phi = u1 * TRB_PI * 2.0f;
     float sn, cs;
     dsincos(phi, sn, cs);
@@ -1259,9 +1298,9 @@ __device__ void shape_sample(uint32_t shape, float p0, float p1, f3 pt, float u0
 __device__ float shape_pdf(uint32_t shape, float p0, float p1, f3 pt, f3 wi) {
     if (shape == TRB_SHAPE_SPHERE) { // sphere.rs:131-140
         const float dist_sqr = len2(pt - splat(0.0f));
-        if (dist_sqr - p0 * p0 < 0.0001f) return 1.0f / shape_area(shape, p0, p1);
-        const float ctm = sqrtf(fmaxf(0.0f, 1.0f - p0 * p0 / dist_sqr));
-        return 1.0f / (TRB_PI * 2.0f * (1.0f - ctm)); // mc::uniform_cone_pdf
+        if (dist_sqr - p0 * p0 < 0.0001f) return ieee_div(1.0f, shape_area(shape, p0, p1));
+        const float ctm = ieee_sqrt(fmaxf(0.0f, 1.0f - ieee_div(p0 * p0, dist_sqr)));
+        return ieee_div(1.0f, TRB_PI * 2.0f * (1.0f - ctm)); // mc::uniform_cone_pdf
     }
     // disk.rs:97-110 / rectangle.rs:91-104: re-intersect from pt along wi on [0.001, inf)
     float tmax = finf();
@@ -1270,7 +1309,7 @@ __device__ float shape_pdf(uint32_t shape, float p0, float p1, f3 pt, f3 wi) {
     const f3 ph = pt + wi * tmax;
     f3 n; // d.n of DifferentialGeometry::new = normalize(cross(dp_du, dp_dv))
     if (shape == TRB_SHAPE_DISK) {
-        const float hr = sqrtf(ph.x * ph.x + ph.y * ph.y);
+        const float hr = ieee_sqrt(ph.x * ph.x + ph.y * ph.y);
         const f3 dp_du = mk(-TRB_PI * 2.0f * ph.y, TRB_PI * 2.0f * ph.x, 0.0f);
         const f3 dp_dv = ((p1 - p0) / hr) * mk(ph.x, ph.y, 0.0f);
         n = unit(cross3(dp_du, dp_dv));
@@ -1279,7 +1318,7 @@ __device__ float shape_pdf(uint32_t shape, float p0, float p1, f3 pt, f3 wi) {
         n = unit(cross3(mk(hw * 2.0f, 0.0f, 0.0f), mk(0.0f, hh * 2.0f, 0.0f)));
     }
     const f3 w = -wi;
-    const float pdf = len2(pt - ph) / (fabsf(dot3(n, w)) * shape_area(shape, p0, p1));
+    const float pdf = ieee_div(len2(pt - ph), fabsf(dot3(n, w)) * shape_area(shape, p0, p1));
     return isfinite(pdf) ? pdf : 0.0f;
 }
 
@@ -1976,7 +2015,7 @@ __global__ void __launch_bounds__(128, MINB) k_wf_trace(const __grid_constant__ 
                     Ray ray; ray.o = mk(o4.x, o4.y, o4.z); ray.d = mk(d4.x, d4.y, d4.z);
                     ray.tmin = (type == 0 && round == 0) ? 0.0f : 0.001f;
                     ray.tmax = type == 1 ? 0.999f : finf();
-                    trace_init(sc, t, ray, type == 1 && shadow_any, ANIM ? __ldg(&wf.thr[p].w) : 0.0f, QUADS && PHASED);
+                    trace_init(sc, t, ray, type == 1 && shadow_any, ANIM ? __ldg(&wf.thr[p].w) : 0.0f, QUADS && PHASED, (flags & WF_TRACE_FORCE_EXACT_BOX) != 0);
                     t.xf_row = wf_xf_row<ANIM>(wf, p);
                     if (PHASED) { stack.put(0, (unsigned long long)ST_DONE); t.sp = 1; } // bottom sentinel: popping it ends the ray
                     if (HOME) { // the TLAS root box is every ray's first test: do it here, with all refilled lanes, instead of as a non-node micro-step
