@@ -66,13 +66,7 @@ if "sort" in VARIANTS:
     measure("sort cell-major bits=5", sort_mode=2, sort_bits=5)
     measure("sort octant-major bits=5 from round 2", sort_mode=1, sort_bits=5, sort_min_round=2)
     measure("sort octant-major bits=5 + split", sort_mode=1, sort_bits=5, shade_split=1)
-if "pipe" in VARIANTS:  # trace.pipe: bit 0 = box_hit_finite, 32 = RayHome + fused non-node chains; 34-37 = 33 at 8/8/9/9 CTAs per SM with 16/12/12/8 stack entries in shared memory
-    for pipe in (33, 36):
+if "pipe" in VARIANTS:  # trace.pipe: kernel variant (trb_api.cu Tuning::pipe)
+    for pipe in (38, 39, 36):
         measure("trace.pipe=%d" % pipe, trace_pipe=pipe)
-    for grid in (9, 18, 27):
-        measure("trace.pipe=36 grid=%d" % grid, trace_pipe=36, trace_grid=grid)
-    for sched in (4, 8, 10):
-        measure("trace.pipe=36 grid=18 sched=%d" % sched, trace_pipe=36, trace_grid=18, trace_sched=sched)
-    for refill in (4, 12, 16):
-        measure("trace.pipe=36 grid=18 refill=%d" % refill, trace_pipe=36, trace_grid=18, trace_refill=refill)
     measure("default again")

@@ -577,6 +577,7 @@ __global__ void k_selftest_box(uint32_t n, uint32_t seed, unsigned long long* ou
 // serialises the loads), the same through one convergent load point after the first pop attempt (+15 %),
 // prefetch.global.L1 of the near child / both children / the next node (+15 % / +60 % / +14 %: the instruction is ten times
 // slower than a load on this part, tools/micro/pair_fetch.cu), four 128-bit loads instead of two 256-bit loads (+12 %).
+// The L1 data pipe is not the limiter although ncu shows it at 80-91 %: one more (hitting) 256-bit load per visit costs 2 %.
 template <bool STATS, bool FAST, class Stack>
 __device__ __forceinline__ void step_nodes2(TraceState& t, const Stack& stack, Cnt& cnt, int* err) {
     uint32_t cur = t.cur;
