@@ -376,7 +376,7 @@ def test_update_frame_on_device_matches_the_host_path_and_the_oracle():
     g.set_option("frame.device", 1)
     # the per-path transform table against per-ray evaluation
     g.update_frame(2, 2 * step, 3 * step)
-    a = g.render_samples(seed=8)[0]
-    g.set_option("anim.table", 0)
-    b = g.render_samples(seed=8)[0]
-    assert a.tobytes() == b.tobytes()
+    a = g.render_samples(seed=8)[0]                   # default: each distinct keyframed spline once per path, then the stacks
+    for mode in (1, 0):                               # one thread per (path, instance) evaluates the whole stack; per ray per instance
+        g.set_option("anim.table", mode)
+        assert g.render_samples(seed=8)[0].tobytes() == a.tobytes(), mode

@@ -124,9 +124,11 @@ TRB_HD inline bool xf_is_static(const trb_spline* splines, uint32_t first, uint3
 TRB_HD inline void animated_color(const trb_color_key* keys, uint32_t first, uint32_t n, float time, float out[3]) {
     if (n == 0) { out[0] = out[1] = out[2] = 0.0f; return; }
     if (n == 1) { for (int i = 0; i < 3; ++i) out[i] = keys[first].rgba[i]; return; }
-    int fi = -1, si = -1;
+    // first = last key of the leading run with key.time < time (take_while().last()), second = first key with !(key.time < time)
+    // (find()): the run ends exactly where the second begins, so one scan gives both
+    int fi = -1;
     for (uint32_t k = 0; k < n; ++k) { if (keys[first + k].time < time) fi = (int)k; else break; }
-    for (uint32_t k = 0; k < n; ++k) { if (!(keys[first + k].time < time)) { si = (int)k; break; } }
+    const int si = fi + 1 < (int)n ? fi + 1 : -1;
     if (fi < 0) { for (int i = 0; i < 3; ++i) out[i] = keys[first].rgba[i]; return; }
     if (si < 0) { for (int i = 0; i < 3; ++i) out[i] = keys[first + n - 1].rgba[i]; return; }
     const trb_color_key& a = keys[first + fi];

@@ -169,7 +169,7 @@ struct Tuning {
     int sort_min_round = 1;    // first bounce round whose queues are sorted (round 0 = primary rays, already coherent)
     int shade_anim_occ = 4;    // keyframed shade kernel variant: resident CTAs per SM it is compiled for (3 or 4)
     int frame_device = 1;      // Scene::update_frame on the device (instance transforms, animation bounds, TLAS SAH build); 0 = on the host
-    int anim_table = 1;        // keyframed scenes: evaluate each keyframed instance's transform once per path (0 = per ray per instance, like the reference)
+    int anim_table = 2;        // keyframed scenes: evaluate each keyframed instance's transform once per path (0 = per ray per instance, like the reference; 1 = one thread per (path, instance) evaluates the whole stack; 2 = each distinct keyframed spline once per path, then the stacks)
     int shade_split = -1;      // shading as three kernels (surface | direct light | BSDF sample) instead of one: 1 / 0, -1 = per scene — split
                                // when the scene mixes material kinds or uses MERL (tr15: 274 -> 337 Mrays/s, tr15-like 388 -> 577), fused for
                                // one-material scenes like C4 (134.4 vs 134.9 ms per step)
@@ -468,13 +468,20 @@ trb_status launch_wavefront(trb_scene* s, const trb::RenderParams& rp, uint32_t 
     g_launches++;
     if (anim && wf.xf_tab && s->tune.anim_table) { // AnimatedTransform::transform(ray.time) once per (path, keyframed instance)
         const size_t items = n_paths * wf.n_anim;
-        trb::k_wf_anim_table<<<(unsigned)std::min<size_t>((items + 127) / 128, (size_t)s->sm_count * 16), 128, 0, st>>>(s->ds, wf);
+        const uint32_t nu = s->ds.n_uniq_splines;
+        if (s->tune.anim_table >= 2 && nu > 0 && nu <= 256) { // each distinct keyframed spline once per path, in shared memory; then the stacks
+            const uint32_t per_iter = std::max(1u, std::min(32u, 128u / nu));
+            const size_t smem = (size_t)per_iter * nu * 32 * sizeof(float);
+            const unsigned grid = (unsigned)std::min<size_t>((n_paths + per_iter - 1) / per_iter, (size_t)s->sm_count * 16);
+            trb::k_wf_anim_table2<<<grid, 128, smem, st>>>(s->ds, wf, per_iter);
+        } else
+            trb::k_wf_anim_table<<<(unsigned)std::min<size_t>((items + 127) / 128, (size_t)s->sm_count * 16), 128, 0, st>>>(s->ds, wf);
         g_launches++;
     } else wf.xf_tab = nullptr;
     const unsigned shade_grid = (unsigned)s->sm_count * 4;
     const int refill = tu.refill;
     // persistent CTAs: two rounds of what is resident per SM (9 for the default variant, 7 keyframed, 4 with counters) unless set
-    const unsigned resident = (flags & TRB_RENDER_STATS) ? 4u : (s->ds.has_anim || tu.pipe == 0 || tu.pipe == 1 || tu.pipe == 33 ? 7u : (tu.pipe == 34 || tu.pipe == 35 ? 8u : 9u));
+    const unsigned resident = (flags & TRB_RENDER_STATS) ? 4u : (tu.pipe == 0 || tu.pipe == 1 || tu.pipe == 33 ? 7u : (tu.pipe == 34 || tu.pipe == 35 || s->ds.has_anim ? 8u : 9u));
     const unsigned tgrid = (unsigned)s->sm_count * (tu.trace_grid ? tu.trace_grid : 2u * resident);
     const uint32_t sched = tu.sched;   // 0 = flat state machine; else the quorum of the phased loop (see k_wf_trace)
     const bool quads = tu.quads != 0;  // DQuad two-level records (never in the STATS variants: their counters are the reference's)
@@ -503,7 +510,10 @@ trb_status launch_wavefront(trb_scene* s, const trb::RenderParams& rp, uint32_t 
         const bool v2 = tu.pipe != 0;
         if (anim) {
             if (stats) { if (v2) TRB_TRACE_LAUNCH(true, 4, 16, true, true, false, 33); else TRB_TRACE_LAUNCH(true, 4, 16, true, true, false, 0); }
-            else if (v2) TRB_TRACE_LAUNCH(false, 7, 16, true, true, false, 33); else TRB_TRACE_LAUNCH(false, 7, 16, true, true, false, 0);
+            else if (!v2) TRB_TRACE_LAUNCH(false, 7, 16, true, true, false, 0);
+            else if (tu.pipe == 33) TRB_TRACE_LAUNCH(false, 7, 16, true, true, false, 33);
+            else if (tu.pipe == 37) TRB_TRACE_LAUNCH(false, 9, 12, true, true, false, 33);
+            else TRB_TRACE_LAUNCH(false, 8, 12, true, true, false, 33); // keyframed default: 8 CTAs per SM (353 vs 352 / 346 Mrays/s at 7 / 9 on tr15.json)
         } else if (stats) {
             if (sched == 0) TRB_TRACE_LAUNCH(true, 4, 16, false, false, false, 0);
             else if (v2) TRB_TRACE_LAUNCH(true, 4, 16, false, true, false, 33); else TRB_TRACE_LAUNCH(true, 4, 16, false, true, false, 0);
@@ -858,6 +868,23 @@ trb_status trb_scene_create(const trb_scene_desc* d, int device, trb_scene** out
             if (s->splines[k].n_ctrl == 1) level[k] = keyframe_xf(s->keyframes[s->splines[k].ctrl_first]);
         Xf* d_lv = nullptr;
         if (!level.empty()) CU(s->arena.upload(level.data(), level.size(), &d_lv));
+        // distinct keyframed splines by content (degree, knots, control keyframes compared bit for bit)
+        std::vector<uint32_t> uniq_of(s->splines.size(), 0xffffffffu), uniq_list;
+        auto same = [&](const trb_spline& a, const trb_spline& b) {
+            return a.degree == b.degree && a.n_ctrl == b.n_ctrl && a.n_knots == b.n_knots &&
+                   memcmp(&s->keyframes[a.ctrl_first], &s->keyframes[b.ctrl_first], a.n_ctrl * sizeof(trb_keyframe)) == 0 &&
+                   memcmp(&s->knots[a.knot_first], &s->knots[b.knot_first], a.n_knots * sizeof(float)) == 0;
+        };
+        for (size_t k = 0; k < s->splines.size(); ++k) {
+            if (s->splines[k].n_ctrl <= 1) continue;
+            for (size_t u = 0; u < uniq_list.size() && uniq_of[k] == 0xffffffffu; ++u)
+                if (same(s->splines[k], s->splines[uniq_list[u]])) uniq_of[k] = (uint32_t)u;
+            if (uniq_of[k] == 0xffffffffu) { uniq_of[k] = (uint32_t)uniq_list.size(); uniq_list.push_back((uint32_t)k); }
+        }
+        uint32_t* d_uo = nullptr; uint32_t* d_ul = nullptr;
+        if (!uniq_of.empty()) CU(s->arena.upload(uniq_of.data(), uniq_of.size(), &d_uo));
+        if (!uniq_list.empty()) CU(s->arena.upload(uniq_list.data(), uniq_list.size(), &d_ul));
+        ds.spline_uniq = d_uo; ds.uniq_splines = d_ul; ds.n_uniq_splines = (uint32_t)uniq_list.size();
         ds.splines = d_sp; ds.keyframes = d_kf; ds.knots = d_kn; ds.color_keys = d_ck; ds.level_xf = d_lv; ds.has_anim = 0;
     }
     // Scene::load_file builds the BVH<Instance> for [0, scene_time] (scene.rs:141); the first render rebuilds it

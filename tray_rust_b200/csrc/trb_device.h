@@ -139,6 +139,12 @@ struct DScene {
     const float* knots;
     const trb_color_key* color_keys;
     const trbh::Xf* level_xf; // per spline: Keyframe::transform of a one-control-point level (else unused)
+    // distinct keyframed splines (by content): instances of one keyframed group carry copies of the group's spline, and
+    // Keyframe::transform(BSpline::point(time)) of a spline is a pure function of (its content, time) — evaluated once per path and
+    // distinct spline (k_wf_anim_table)
+    const uint32_t* spline_uniq;  // per spline: index into uniq_splines, 0xffffffff for one-control-point levels
+    const uint32_t* uniq_splines; // per distinct keyframed spline: a representative index into `splines`
+    uint32_t n_uniq_splines;
     uint32_t has_anim; // any instance / camera / emission depends on time
     const uint32_t* anim_instances; // instance indices with DI_ANIM_XF, in instance order
     uint32_t n_anim_instances;

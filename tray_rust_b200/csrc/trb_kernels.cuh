@@ -1828,6 +1828,53 @@ __global__ void __launch_bounds__(128) k_wf_anim_table(const __grid_constant__ D
     }
 }
 
+// The same table with each DISTINCT keyframed spline evaluated once per path: the instances of a keyframed group carry copies of
+// the group's spline (tr15.json: 28 keyframed instances, 8 distinct splines), and a level's transform
+// Keyframe::transform(BSpline::point(clamp(time))) depends only on (the spline's content, time). Phase 1: one thread per
+// (path, distinct spline) -> shared memory; phase 2: one thread per (path, keyframed instance) composes its stack in the
+// reference's order from those and the precomputed one-control-point levels — the operations of trbh::animated_xf, so the rows
+// are bit-identical to k_wf_anim_table's.
+__global__ void __launch_bounds__(128) k_wf_anim_table2(const __grid_constant__ DScene sc, const __grid_constant__ WfState wf, uint32_t per_iter) {
+    extern __shared__ float s_lvl[]; // [path of this iteration][distinct spline][fwd 16 | inv 16]
+    const uint32_t nu = sc.n_uniq_splines;
+    for (uint32_t p0 = blockIdx.x * per_iter; p0 < wf.n_paths; p0 += gridDim.x * per_iter) {
+        const uint32_t np = min(per_iter, wf.n_paths - p0);
+        for (uint32_t i = threadIdx.x; i < np * nu; i += blockDim.x) {
+            const uint32_t lp = i / nu, u = i % nu;
+            const trb_spline& sp = sc.splines[__ldg(&sc.uniq_splines[u])];
+            const float time = wf.thr[p0 + lp].w;
+            const float lo = sc.knots[sp.knot_first + sp.degree], hi = sc.knots[sp.knot_first + sp.n_knots - 1 - sp.degree];
+            const trbh::Xf t = trbh::keyframe_xf(trbh::spline_point(sp, sc.keyframes, sc.knots, trbh::clampf_hd(time, lo, hi)));
+            float* dst = s_lvl + (size_t)i * 32;
+#pragma unroll
+            for (int q = 0; q < 16; ++q) { dst[q] = t.fwd.m[q]; dst[16 + q] = t.inv.m[q]; }
+        }
+        __syncthreads();
+        for (uint32_t i = threadIdx.x; i < np * wf.n_anim; i += blockDim.x) {
+            const uint32_t lp = i / wf.n_anim, k = i % wf.n_anim;
+            const DInstance& in = sc.instances[__ldg(&sc.anim_instances[k])];
+            const uint32_t first = __ldg(&in.spline_first), count = __ldg(&in.n_splines);
+            trbh::Xf acc = trbh::xf_identity();
+            for (uint32_t s = first; s < first + count; ++s) {
+                trbh::Xf t;
+                if (sc.splines[s].n_ctrl == 1) t = sc.level_xf[s];
+                else {
+                    const float* src = s_lvl + ((size_t)lp * nu + __ldg(&sc.spline_uniq[s])) * 32;
+#pragma unroll
+                    for (int q = 0; q < 16; ++q) { t.fwd.m[q] = src[q]; t.inv.m[q] = src[16 + q]; }
+                }
+                acc = trbh::xf_compose(t, acc);
+            }
+            float4* dst = reinterpret_cast<float4*>(wf.xf_tab + ((size_t)(p0 + lp) * wf.n_anim + k) * 32);
+#pragma unroll
+            for (int q = 0; q < 4; ++q) dst[q] = make_float4(acc.inv.m[4 * q], acc.inv.m[4 * q + 1], acc.inv.m[4 * q + 2], acc.inv.m[4 * q + 3]);
+#pragma unroll
+            for (int q = 0; q < 4; ++q) dst[4 + q] = make_float4(acc.fwd.m[4 * q], acc.fwd.m[4 * q + 1], acc.fwd.m[4 * q + 2], acc.fwd.m[4 * q + 3]);
+        }
+        __syncthreads();
+    }
+}
+
 // order-preserving float <-> uint (for atomicMin / atomicMax over floats of either sign)
 __device__ __forceinline__ uint32_t f_ordered(float f) { const uint32_t u = __float_as_uint(f); return (u & 0x80000000u) ? ~u : (u | 0x80000000u); }
 __device__ __forceinline__ float f_unordered(uint32_t u) { return __uint_as_float((u & 0x80000000u) ? (u & 0x7fffffffu) : ~u); }
