@@ -36,8 +36,8 @@ for name, frame in ((("c5_tr15.json", 300),) if QUICK else (("c5_tr15.json", 300
     g.update_frame(frame, frame * step, (frame + 1) * step); o.update_frame(frame, frame * step, (frame + 1) * step)
     kw = dict(block_start=12000, block_count=48, sample_first=0, sample_count=2, seed=1)
     os_, _ = o.render_samples(**kw)
-    for table, split, occ, pipe in (((1, -1, 4, 34), (2, -1, 4, 34)) if QUICK else ((2, 0, 4, 34), (2, 1, 4, 34), (1, 1, 4, 34), (2, 1, 4, 0), (0, 0, 4, 34))):
-        g.set_option("anim.table", table); g.set_option("shade.split", split); g.set_option("shade.anim_occupancy", occ); g.set_option("trace.pipe", pipe)
+    for table, split, occ, pipe, msort in (((2, -1, 4, 34, 0), (2, -1, 4, 34, 1)) if QUICK else ((2, 0, 4, 34, 1), (2, 1, 4, 34, 1), (2, 1, 4, 34, 0), (1, 1, 4, 34, 1), (2, 1, 4, 0, 1), (0, 0, 4, 34, 1))):
+        g.set_option("anim.table", table); g.set_option("shade.split", split); g.set_option("shade.anim_occupancy", occ); g.set_option("trace.pipe", pipe); g.set_option("shade.sort", msort)
         parity = g.render_samples(**kw)[0].tobytes() == os_.tobytes()
         g.render_device(film.data_ptr(), stats.data_ptr(), None, spp=2048, sample_first=0, sample_count=SPP_STEP, seed=1)
         torch.cuda.synchronize(); stats.zero_()
@@ -49,7 +49,7 @@ for name, frame in ((("c5_tr15.json", 300),) if QUICK else (("c5_tr15.json", 300
         ms = e0.elapsed_time(e1)
         s = stats.cpu().numpy()
         print(json.dumps({"workload": "%s 1920x1080 frame %d (%d instances, %d meshes, %d MERL tables), 2 passes x %d spp" % (name, frame, desc.n_instances, desc.n_meshes, desc.n_merl, SPP_STEP),
-                          "per_path_transform_table": table, "split_shade": split, "trace_variant": pipe, "shade_ctas_per_sm": occ, "bit_exact_vs_oracle_on_48_blocks": bool(parity), "mrays_s": float(s[1:5].sum()) / ms / 1e3,
+                          "per_path_transform_table": table, "split_shade": split, "trace_variant": pipe, "material_buckets": bool(msort), "shade_ctas_per_sm": occ, "bit_exact_vs_oracle_on_48_blocks": bool(parity), "mrays_s": float(s[1:5].sum()) / ms / 1e3,
                           "msamples_s": float(s[0]) / ms / 1e3, "ms_per_pass": ms / 2,
                           "rays": {"primary": int(s[1]), "shadow": int(s[2]), "mis": int(s[3]), "continuation": int(s[4])}}), flush=True)
     g.close(); o.close()

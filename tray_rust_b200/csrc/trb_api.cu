@@ -173,6 +173,7 @@ struct Tuning {
     int shade_split = -1;      // shading as three kernels (surface | direct light | BSDF sample) instead of one: 1 / 0, -1 = per scene — split
                                // when the scene mixes material kinds or uses MERL (tr15: 274 -> 337 Mrays/s, tr15-like 388 -> 577), fused for
                                // one-material scenes like C4 (134.4 vs 134.9 ms per step)
+    int shade_sort = 1;        // split shading: bucket the paths by material kind between k_wf_shade_a and _b / _c
     uint64_t pass_paths = 1ull << 24; // camera samples per wavefront pass (the frame is rendered in additive passes)
 };
 int env_int(const char* name, int dflt) { const char* v = getenv(name); return v ? (int)strtol(v, nullptr, 0) : dflt; }
@@ -409,8 +410,9 @@ trb_status ensure_wavefront(trb_scene* s, size_t n_paths) {
     float4** f4[] = {&w.org, &w.cont, &w.shadow, &w.mis, &w.a, &w.b, &w.tprev, &w.thr, &w.illum, &w.ng, &w.rad, &w.f_p, &w.f_n, &w.f_t, &w.f_b};
     for (float4** q : f4) grab(cap * sizeof(float4), reinterpret_cast<void**>(q));
     grab(cap * sizeof(uint4), reinterpret_cast<void**>(&w.hit));
-    uint32_t** u1[] = {&w.q_active[0], &w.q_active[1], &w.q_ending[0], &w.q_ending[1], &w.q_cont, &w.q_shadow, &w.q_mis, &w.q_mid};
+    uint32_t** u1[] = {&w.q_active[0], &w.q_active[1], &w.q_ending[0], &w.q_ending[1], &w.q_cont, &w.q_shadow, &w.q_mis};
     for (uint32_t** q : u1) grab(cap * sizeof(uint32_t), reinterpret_cast<void**>(q));
+    grab(cap * trb::WF_MID_BUCKETS * sizeof(uint32_t), reinterpret_cast<void**>(&w.q_mid)); // one list per material kind (split shading)
     grab(64 * trb::WF_CNT * sizeof(uint32_t), reinterpret_cast<void**>(&w.counters));
     // ray sorting: up to three rays per path and round; bins for the finest grid the options allow
     const size_t max_bins = (size_t)3 * (8u << (3 * trb::WF_SORT_MAX_BITS));
@@ -440,6 +442,7 @@ trb_status launch_wavefront(trb_scene* s, const trb::RenderParams& rp, uint32_t 
     const Tuning& tu = s->tune;
     trb::WfState wf = s->wf;
     wf.n_paths = (uint32_t)n_paths;
+    wf.mid_keyed = s->tune.shade_sort ? 1u : 0u;
     if (s->integrator.type != TRB_INTEGRATOR_PATH) { // Whitted / NormalsDebug: one thread per camera sample, then the same film kernel
         const unsigned grid = (unsigned)std::min<size_t>((n_paths + 127) / 128, (size_t)s->sm_count * 8);
         const bool anim = s->ds.has_anim != 0;
@@ -651,6 +654,7 @@ trb_status trb_scene_set_option(trb_scene* s, const char* name, long long value)
     else if (k == "sort.bits") t.sort_bits = (int)std::min<long long>(6, std::max<long long>(1, value));
     else if (k == "sort.min_round") t.sort_min_round = (int)value;
     else if (k == "shade.split") t.shade_split = (int)value;
+    else if (k == "shade.sort") t.shade_sort = (int)value;
     else if (k == "anim.table") t.anim_table = (int)value;
     else if (k == "frame.device") t.frame_device = (int)value;
     else if (k == "shade.anim_occupancy") t.shade_anim_occ = (int)value;

@@ -1767,7 +1767,10 @@ struct WfState {
     float4* f_n;         // shading normal
     float4* f_t;         // tangent
     float4* f_b;         // bitangent
-    uint32_t* q_mid;     // paths to shade this round (survived resolve / termination / miss)
+    uint32_t* q_mid;     // paths to shade this round (survived resolve / termination / miss): WF_MID_BUCKETS lists of n_paths entries, one per
+                         // material kind, so that k_wf_shade_b / _c run one material's code at a time (whole warps of one kind, and the
+                         // GPU's instruction caches hold one kind's code: the kernels are ~190 KB and waited 31 % of their time on instruction fetch)
+    uint32_t mid_keyed;  // 0: everything in bucket 0 (option shade.sort = 0)
     // keyframed scenes: per path, the evaluated transforms of every keyframed instance (32 floats each: inverse, forward); nullptr: none
     float* xf_tab;
     uint32_t n_anim;
@@ -1776,7 +1779,10 @@ struct WfState {
 constexpr uint32_t WF_PATH_MASK = 0x3fffffffu;
 constexpr int WF_SORT_MAX_BITS = 6; // origin grid up to 64^3 cells x 8 octants x 3 ray types = 6.3 M bins
 enum { WF_N_ACTIVE = 0, WF_N_CONT = 1, WF_N_SHADOW = 2, WF_N_MIS = 3, WF_TRACE_HEAD = 4, WF_SHADE_HEAD = 5, WF_N_MID = 6, WF_SHADE_B_HEAD = 7, WF_SHADE_C_HEAD = 8,
-       WF_N_ENDING = 9, WF_ENDING_HEAD = 10, WF_CNT = 12 };
+       WF_N_ENDING = 9, WF_ENDING_HEAD = 10,
+       // split shading with the paths bucketed by material kind (k_wf_shade_a fills, _b and _c drain bucket after bucket)
+       WF_MID_K = 12, WF_B_HEAD_K = 20, WF_C_HEAD_K = 28, WF_CNT = 36 };
+constexpr uint32_t WF_MID_BUCKETS = 8;
 enum { WF_F_SPECULAR = 1u, WF_F_TERMINATE = 2u, WF_F_SHADOW = 4u, WF_F_MIS = 8u };
 
 // sample index p -> block item, pixel, sample (the canonical order of trb_camera_rays / trb_render_samples)
@@ -1806,6 +1812,18 @@ __device__ __forceinline__ void wf_push(uint32_t* q, uint32_t* counter, bool wan
     if (lane == leader) base = atomicAdd(counter, (uint32_t)__popc(mask));
     base = __shfl_sync(0xffffffffu, base, leader);
     if (want) q[base + __popc(mask & ((1u << lane) - 1u))] = value;
+}
+
+// the same into one of several lists: lanes with equal keys are grouped (match.any), one atomic per group
+__device__ __forceinline__ void wf_push_keyed(uint32_t* q, uint32_t stride, uint32_t* counters, bool want, uint32_t key, uint32_t value) {
+    const unsigned mask = __ballot_sync(0xffffffffu, want);
+    if (mask == 0 || !want) return;
+    const unsigned peers = __match_any_sync(mask, key);
+    const int lane = threadIdx.x & 31, leader = __ffs(peers) - 1;
+    uint32_t base = 0;
+    if (lane == leader) base = atomicAdd(&counters[key], (uint32_t)__popc(peers));
+    base = __shfl_sync(peers, base, leader);
+    q[(size_t)key * stride + base + __popc(peers & ((1u << lane) - 1u))] = value;
 }
 
 template <bool ANIM>
@@ -2430,7 +2448,7 @@ __global__ void __launch_bounds__(128, MINB) k_wf_shade_a(const __grid_constant_
         base = __shfl_sync(0xffffffffu, base, 0);
         if (base >= n) break;
         const uint32_t i = base + lane;
-        uint32_t p = 0;
+        uint32_t p = 0, mid_key = 0;
         bool push_mid = false;
         if (i < n) {
             p = round == 0 ? i : act[i];
@@ -2475,11 +2493,12 @@ __global__ void __launch_bounds__(128, MINB) k_wf_shade_a(const __grid_constant_
                     wf.f_b[p] = make_float4(fr.bitan.x, fr.bitan.y, fr.bitan.z, 0.0f);
                     wf.illum[p] = make_float4(illum.x, illum.y, illum.z, 0.0f);
                     push_mid = true;
+                    if (wf.mid_keyed) mid_key = __ldg(&sc.materials[__ldg(&sc.instances[h.inst].material)].type) & (WF_MID_BUCKETS - 1u);
                 }
             }
             if (done) finish_sample(sc, rp, wf, p, illum, MODE);
         }
-        wf_push(wf.q_mid, &cnt_r[WF_N_MID], push_mid, p);
+        wf_push_keyed(wf.q_mid, wf.n_paths, &cnt_r[WF_MID_K], push_mid, mid_key, p);
     }
 }
 
@@ -2488,18 +2507,21 @@ __global__ void __launch_bounds__(128, MINB) k_wf_shade_b(const __grid_constant_
                                                      uint32_t round) {
     uint32_t* cnt_r = wf.counters + round * WF_CNT;
     uint32_t* cnt_n = wf.counters + (round + 1) * WF_CNT;
-    const uint32_t n = cnt_r[WF_N_MID];
     const int lane = threadIdx.x & 31;
+    for (uint32_t bucket = 0; bucket < WF_MID_BUCKETS; ++bucket) {
+    const uint32_t n = cnt_r[WF_MID_K + bucket];
+    const uint32_t* __restrict__ q_mid = wf.q_mid + (size_t)bucket * wf.n_paths;
     for (;;) {
+        if (n == 0) break;
         uint32_t base = 0;
-        if (lane == 0) base = atomicAdd(&cnt_r[WF_SHADE_B_HEAD], 32u);
+        if (lane == 0) base = atomicAdd(&cnt_r[WF_B_HEAD_K + bucket], 32u);
         base = __shfl_sync(0xffffffffu, base, 0);
         if (base >= n) break;
         const uint32_t i = base + lane;
         uint32_t p = 0;
         bool push_shadow = false, push_mis = false;
         if (i < n) {
-            p = wf.q_mid[i];
+            p = q_mid[i];
             Frame fr; uint32_t inst; float tu, tv;
             load_frame(wf, p, fr, inst, tu, tv);
             const float4 c4 = wf.cont[p], th4 = wf.thr[p];
@@ -2521,6 +2543,7 @@ __global__ void __launch_bounds__(128, MINB) k_wf_shade_b(const __grid_constant_
         wf_push(wf.q_shadow, &cnt_n[WF_N_SHADOW], push_shadow, p);
         wf_push(wf.q_mis, &cnt_n[WF_N_MIS], push_mis, p);
     }
+    }
 }
 
 template <int MODE, bool ANIM, int MINB>
@@ -2528,12 +2551,15 @@ __global__ void __launch_bounds__(128, MINB) k_wf_shade_c(const __grid_constant_
                                                      uint32_t round) {
     uint32_t* cnt_r = wf.counters + round * WF_CNT;
     uint32_t* cnt_n = wf.counters + (round + 1) * WF_CNT;
-    const uint32_t n = cnt_r[WF_N_MID];
     uint32_t* act_next = wf.q_active[(round + 1) & 1];
     const int lane = threadIdx.x & 31;
+    for (uint32_t bucket = 0; bucket < WF_MID_BUCKETS; ++bucket) {
+    const uint32_t n = cnt_r[WF_MID_K + bucket];
+    const uint32_t* __restrict__ q_mid = wf.q_mid + (size_t)bucket * wf.n_paths;
     for (;;) {
+        if (n == 0) break;
         uint32_t base = 0;
-        if (lane == 0) base = atomicAdd(&cnt_r[WF_SHADE_C_HEAD], 32u);
+        if (lane == 0) base = atomicAdd(&cnt_r[WF_C_HEAD_K + bucket], 32u);
         base = __shfl_sync(0xffffffffu, base, 0);
         if (base >= n) break;
         const uint32_t i = base + lane;
@@ -2541,7 +2567,7 @@ __global__ void __launch_bounds__(128, MINB) k_wf_shade_c(const __grid_constant_
         bool push_cont = false, push_active = false;
         f3 new_org = splat(0.0f);
         if (i < n) {
-            p = wf.q_mid[i];
+            p = q_mid[i];
             Frame fr; uint32_t inst; float tu, tv;
             load_frame(wf, p, fr, inst, tu, tv);
             const float4 c4 = wf.cont[p], th4 = wf.thr[p];
@@ -2568,6 +2594,7 @@ __global__ void __launch_bounds__(128, MINB) k_wf_shade_c(const __grid_constant_
         wf_push(wf.q_cont, &cnt_n[WF_N_CONT], push_cont, p);
         wf_push(act_next, &cnt_n[WF_N_ACTIVE], push_active, p);
         wf_bounds_add(wf.bounds + (round + 1) * 8, push_active, new_org);
+    }
     }
 }
 
