@@ -7,7 +7,7 @@ mkdir -p gpurun_out
 python -m pytest tests -m gpu -q > ${P}_pytest.log 2>&1
 tail -4 ${P}_pytest.log
 python -c "import __graft_entry__ as g; g.smoke()" > ${P}_smoke.log 2>&1
-python tools/r02_sweep.py > ${P}_sweep.log 2> ${P}_sweep.err
+SWEEP=final python tools/r02_sweep.py > ${P}_sweep.log 2> ${P}_sweep.err
 # what ncu measures for the trace launches of ONE bench step: DRAM bytes, L2 sectors, L1 global-load sectors, L1TEX data pipe, issue slots
 ncu --metrics dram__bytes_read.sum,dram__bytes_write.sum,lts__t_sectors.sum,l1tex__t_sectors_pipe_lsu_mem_global_op_ld.sum,l1tex__data_pipe_lsu_wavefronts.avg.pct_of_peak_sustained_elapsed,smsp__issue_active.avg.pct_of_peak_sustained_active,gpu__time_duration.sum \
     --clock-control none -k regex:k_wf_trace -c 10 --csv --log-file ${P}_trace_metrics.csv python bench.py --steps 1 --warmup 1 --no-cpu-baseline > /dev/null 2>&1
@@ -18,11 +18,12 @@ ncu --metrics gpu__time_duration.sum --clock-control none -c 400 --csv --log-fil
 for k in trace shade film_v2; do
   ncu --set full --import-source on --clock-control none -k regex:k_wf_$k -s 1 -c 1 -f -o ${P}_prof_$k python bench.py --steps 1 --warmup 1 --no-cpu-baseline > /dev/null 2>&1
   python tools/ncu_summary.py ${P}_prof_$k.ncu-rep > ${P}_ncu_k_wf_$k.txt 2>&1
-  ncu -i ${P}_prof_$k.ncu-rep --page source --csv > ${P}_source_k_wf_$k.csv 2> /dev/null
+  if [ $k = trace ]; then ncu -i ${P}_prof_$k.ncu-rep --page source --csv > ${P}_source_k_wf_$k.csv 2> /dev/null; fi
   rm -f ${P}_prof_$k.ncu-rep   # gpurun merges at most 64 MiB back: keep the summaries and the per-instruction table, not the report
 done
 for t in memcheck racecheck; do
   timeout 900 compute-sanitizer --tool $t python tools/sanitize.py > ${P}_sanitizer_$t.log 2>&1
 done
-python tools/c5_bench.py --quick > ${P}_c5.log 2> ${P}_c5.err
+python tools/c5_bench.py > ${P}_c5.log 2> ${P}_c5.err
+python tools/configs_bench.py > ${P}_configs.log 2> ${P}_configs.err
 ls -la gpurun_out | tail -25

@@ -70,3 +70,10 @@ if "pipe" in VARIANTS:  # trace.pipe: kernel variant (trb_api.cu Tuning::pipe)
     for pipe in (38, 39, 36):
         measure("trace.pipe=%d" % pipe, trace_pipe=pipe)
     measure("default again")
+if "final" in VARIANTS:  # the round's trace-kernel steps side by side, in one process
+    measure("trace.pipe=0 (round-1 kernel)", trace_pipe=0)
+    measure("trace.pipe=1 (+ box_hit_finite)", trace_pipe=1)
+    measure("trace.pipe=33 (+ RayHome + fused non-node chains, 7 CTAs per SM)", trace_pipe=33)
+    measure("trace.pipe=34 (8 CTAs per SM)", trace_pipe=34)
+    measure("trace.pipe=36 (9 CTAs per SM) = default", trace_pipe=36)
+    measure("split shade", shade_split=1)
