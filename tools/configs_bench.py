@@ -51,6 +51,7 @@ for name, mk, w, h, spp, spp_step, frame in CONFIGS:
     stats = torch.zeros(10, dtype=torch.int64, device=dev)
     for buckets in (1, 0):
         g.set_option("shade.sort", buckets)
+        if os.environ.get("SPLIT"): g.set_option("shade.split", int(os.environ["SPLIT"]))
         g.render_device(film.data_ptr(), stats.data_ptr(), None, spp=spp, sample_first=0, sample_count=spp_step, seed=1)
         torch.cuda.synchronize(); stats.zero_()
         e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
@@ -60,6 +61,6 @@ for name, mk, w, h, spp, spp_step, frame in CONFIGS:
         e1.record(); torch.cuda.synchronize()
         ms = e0.elapsed_time(e1)
         s = stats.cpu().numpy()
-        print(json.dumps({"config": name, "material_buckets": bool(buckets), "mrays_s": float(s[1:5].sum()) / ms / 1e3, "msamples_s": float(s[0]) / ms / 1e3,
+        print(json.dumps({"config": name, "material_buckets": bool(buckets), "shade_split_option": os.environ.get("SPLIT", "per scene"), "mrays_s": float(s[1:5].sum()) / ms / 1e3, "msamples_s": float(s[0]) / ms / 1e3,
                           "ms_per_pass": ms / 3, "spp_per_pass": spp_step, "instances": desc.n_instances, "meshes": desc.n_meshes}), flush=True)
     g.close()

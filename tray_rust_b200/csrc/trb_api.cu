@@ -211,7 +211,7 @@ struct trb_scene {
     std::vector<HostMesh> meshes;
     uint32_t spp_pow2 = 1;
     uint32_t n_anim = 0;                 // instances whose transform stack is keyframed (evaluated per path into WfState::xf_tab)
-    bool mixed_materials = false;        // receivers use >= 3 material kinds or a MERL table: the split shade kernels win (Tuning::shade_split = -1)
+    bool mixed_materials = false;        // the hittable instances use >= 2 material kinds or a MERL table: the split shade kernels with material buckets win (Tuning::shade_split = -1)
     uint32_t* d_anim_instances = nullptr;
     // per-frame host state
     int active_camera = -1;
@@ -838,8 +838,10 @@ trb_status trb_scene_create(const trb_scene_desc* d, int device, trb_scene** out
     for (const trb_instance& in : s->instances) if (!trbh::xf_is_static(s->splines.data(), in.spline_first, in.n_splines)) s->n_anim++;
     {
         uint32_t kinds = 0;
-        for (const trb_instance& in : s->instances) if (in.kind == TRB_INST_RECEIVER) kinds |= 1u << s->materials[in.material].type;
-        s->mixed_materials = __builtin_popcount(kinds) >= 3 || (kinds & (1u << TRB_MAT_MERL)) != 0;
+        for (const trb_instance& in : s->instances) if (in.kind != TRB_INST_EMITTER_POINT && in.material < s->materials.size()) kinds |= 1u << s->materials[in.material].type;
+        // two kinds are enough: with the material buckets the split kernels run one kind's code at a time, the fused kernel runs every
+        // kind a warp holds (C3, matte + plastic: 857 -> 2157 Mrays/s; cornell_box.json: 1099 -> 2087; profiles/r02_c25_split_two_kinds.log)
+        s->mixed_materials = __builtin_popcount(kinds) >= 2 || (kinds & (1u << TRB_MAT_MERL)) != 0;
     }
     CU(s->arena.alloc(1, &s->d_counter));
     CU(s->arena.alloc(1, &s->d_error));
