@@ -49,8 +49,8 @@ for name, mk, w, h, spp, spp_step, frame in CONFIGS:
     g.update_frame(frame, frame * step, (frame + 1) * step)
     film = torch.zeros(h, w, 4, dtype=torch.float32, device=dev)
     stats = torch.zeros(10, dtype=torch.int64, device=dev)
-    for buckets in (1, 0):
-        g.set_option("shade.sort", buckets)
+    for buckets, kind in ((1, 1), (1, 0), (0, 0)):
+        g.set_option("shade.sort", buckets); g.set_option("shade.kind", kind)
         if os.environ.get("SPLIT"): g.set_option("shade.split", int(os.environ["SPLIT"]))
         g.render_device(film.data_ptr(), stats.data_ptr(), None, spp=spp, sample_first=0, sample_count=spp_step, seed=1)
         torch.cuda.synchronize(); stats.zero_()
@@ -61,6 +61,6 @@ for name, mk, w, h, spp, spp_step, frame in CONFIGS:
         e1.record(); torch.cuda.synchronize()
         ms = e0.elapsed_time(e1)
         s = stats.cpu().numpy()
-        print(json.dumps({"config": name, "material_buckets": bool(buckets), "shade_split_option": os.environ.get("SPLIT", "per scene"), "mrays_s": float(s[1:5].sum()) / ms / 1e3, "msamples_s": float(s[0]) / ms / 1e3,
+        print(json.dumps({"config": name, "material_buckets": bool(buckets), "matte_instantiation": bool(kind), "shade_split_option": os.environ.get("SPLIT", "per scene"), "mrays_s": float(s[1:5].sum()) / ms / 1e3, "msamples_s": float(s[0]) / ms / 1e3,
                           "ms_per_pass": ms / 3, "spp_per_pass": spp_step, "instances": desc.n_instances, "meshes": desc.n_meshes}), flush=True)
     g.close()

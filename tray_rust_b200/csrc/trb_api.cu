@@ -174,6 +174,7 @@ struct Tuning {
                                // when the scene mixes material kinds or uses MERL (tr15: 274 -> 337 Mrays/s, tr15-like 388 -> 577), fused for
                                // one-material scenes like C4 (134.4 vs 134.9 ms per step)
     int shade_sort = 1;        // split shading: bucket the paths by material kind between k_wf_shade_a and _b / _c
+    int shade_kind = 1;        // split shading with buckets: the matte bucket goes through _b / _c instantiations compiled for matte alone
     uint64_t pass_paths = 1ull << 24; // camera samples per wavefront pass (the frame is rendered in additive passes)
 };
 int env_int(const char* name, int dflt) { const char* v = getenv(name); return v ? (int)strtol(v, nullptr, 0) : dflt; }
@@ -211,6 +212,7 @@ struct trb_scene {
     std::vector<HostMesh> meshes;
     uint32_t spp_pow2 = 1;
     uint32_t n_anim = 0;                 // instances whose transform stack is keyframed (evaluated per path into WfState::xf_tab)
+    uint32_t material_kinds = 0;         // bit k: some hittable instance's material is of kind k (TRB_MAT_*)
     bool mixed_materials = false;        // the hittable instances use >= 2 material kinds or a MERL table: the split shade kernels with material buckets win (Tuning::shade_split = -1)
     uint32_t* d_anim_instances = nullptr;
     // per-frame host state
@@ -533,20 +535,39 @@ trb_status launch_wavefront(trb_scene* s, const trb::RenderParams& rp, uint32_t 
         }
 #undef TRB_TRACE_LAUNCH
         if (ev.first) { CU(cudaEventRecord(ev.second, st)); s->trace_events.push_back(ev); }
-        if (tu.shade_split > 0 || (tu.shade_split < 0 && s->mixed_materials)) { // three kernels with fewer live values each (DESIGN.md "Split shading"); same device functions, same results
+        // per scene (shade_split < 0): split when the scene mixes material kinds, and also when it is all matte — the matte instantiations of
+        // _b / _c beat the fused kernel (C4: 1066 vs 1027 Mrays/s, profiles/r02_c26_matte_instantiation.log); other one-kind scenes stay fused
+        const bool split_auto = s->mixed_materials || (tu.shade_sort && tu.shade_kind && s->material_kinds == (1u << TRB_MAT_MATTE));
+        if (tu.shade_split > 0 || (tu.shade_split < 0 && split_auto)) { // three kernels with fewer live values each (DESIGN.md "Split shading"); same device functions, same results
+            // with the material buckets, _b and _c run once per kind that has an instantiation of its own (matte: the commonest), and once
+            // for the other kinds the scene uses
+            const uint32_t all = 0xffu, own = (tu.shade_sort && tu.shade_kind) ? (s->material_kinds & (1u << TRB_MAT_MATTE)) : 0u;
+            const uint32_t rest = tu.shade_sort ? (s->material_kinds & ~own) : all;
             if (anim) {
                 if (mode == 0) trb::k_wf_shade_a<0, true, 3><<<shade_grid, 128, 0, st>>>(s->ds, rp, wf, round);
                 else trb::k_wf_shade_a<1, true, 3><<<shade_grid, 128, 0, st>>>(s->ds, rp, wf, round);
-                trb::k_wf_shade_b<true, 3><<<shade_grid, 128, 0, st>>>(s->ds, rp, wf, round);
-                if (mode == 0) trb::k_wf_shade_c<0, true, 4><<<shade_grid, 128, 0, st>>>(s->ds, rp, wf, round);
-                else trb::k_wf_shade_c<1, true, 4><<<shade_grid, 128, 0, st>>>(s->ds, rp, wf, round);
+                if (own) trb::k_wf_shade_b<true, 4, TRB_MAT_MATTE><<<shade_grid, 128, 0, st>>>(s->ds, rp, wf, round, own);
+                if (rest) trb::k_wf_shade_b<true, 3><<<shade_grid, 128, 0, st>>>(s->ds, rp, wf, round, rest);
+                if (mode == 0) {
+                    if (own) trb::k_wf_shade_c<0, true, 6, TRB_MAT_MATTE><<<(unsigned)s->sm_count * 6, 128, 0, st>>>(s->ds, rp, wf, round, own);
+                    if (rest) trb::k_wf_shade_c<0, true, 4><<<shade_grid, 128, 0, st>>>(s->ds, rp, wf, round, rest);
+                } else {
+                    if (own) trb::k_wf_shade_c<1, true, 6, TRB_MAT_MATTE><<<(unsigned)s->sm_count * 6, 128, 0, st>>>(s->ds, rp, wf, round, own);
+                    if (rest) trb::k_wf_shade_c<1, true, 4><<<shade_grid, 128, 0, st>>>(s->ds, rp, wf, round, rest);
+                }
             } else {
                 const unsigned ga = (unsigned)s->sm_count * 6, gb = (unsigned)s->sm_count * 5, gc = (unsigned)s->sm_count * 6;
                 if (mode == 0) trb::k_wf_shade_a<0, false, 6><<<ga, 128, 0, st>>>(s->ds, rp, wf, round);
                 else trb::k_wf_shade_a<1, false, 6><<<ga, 128, 0, st>>>(s->ds, rp, wf, round);
-                trb::k_wf_shade_b<false, 5><<<gb, 128, 0, st>>>(s->ds, rp, wf, round);
-                if (mode == 0) trb::k_wf_shade_c<0, false, 6><<<gc, 128, 0, st>>>(s->ds, rp, wf, round);
-                else trb::k_wf_shade_c<1, false, 6><<<gc, 128, 0, st>>>(s->ds, rp, wf, round);
+                if (own) trb::k_wf_shade_b<false, 5, TRB_MAT_MATTE><<<gb, 128, 0, st>>>(s->ds, rp, wf, round, own);
+                if (rest) trb::k_wf_shade_b<false, 5><<<gb, 128, 0, st>>>(s->ds, rp, wf, round, rest);
+                if (mode == 0) {
+                    if (own) trb::k_wf_shade_c<0, false, 6, TRB_MAT_MATTE><<<gc, 128, 0, st>>>(s->ds, rp, wf, round, own);
+                    if (rest) trb::k_wf_shade_c<0, false, 6><<<gc, 128, 0, st>>>(s->ds, rp, wf, round, rest);
+                } else {
+                    if (own) trb::k_wf_shade_c<1, false, 6, TRB_MAT_MATTE><<<gc, 128, 0, st>>>(s->ds, rp, wf, round, own);
+                    if (rest) trb::k_wf_shade_c<1, false, 6><<<gc, 128, 0, st>>>(s->ds, rp, wf, round, rest);
+                }
             }
             g_launches += 4;
             continue;
@@ -655,6 +676,7 @@ trb_status trb_scene_set_option(trb_scene* s, const char* name, long long value)
     else if (k == "sort.min_round") t.sort_min_round = (int)value;
     else if (k == "shade.split") t.shade_split = (int)value;
     else if (k == "shade.sort") t.shade_sort = (int)value;
+    else if (k == "shade.kind") t.shade_kind = (int)value;
     else if (k == "anim.table") t.anim_table = (int)value;
     else if (k == "frame.device") t.frame_device = (int)value;
     else if (k == "shade.anim_occupancy") t.shade_anim_occ = (int)value;
@@ -842,6 +864,7 @@ trb_status trb_scene_create(const trb_scene_desc* d, int device, trb_scene** out
         // two kinds are enough: with the material buckets the split kernels run one kind's code at a time, the fused kernel runs every
         // kind a warp holds (C3, matte + plastic: 857 -> 2157 Mrays/s; cornell_box.json: 1099 -> 2087; profiles/r02_c25_split_two_kinds.log)
         s->mixed_materials = __builtin_popcount(kinds) >= 2 || (kinds & (1u << TRB_MAT_MERL)) != 0;
+        s->material_kinds = kinds;
     }
     CU(s->arena.alloc(1, &s->d_counter));
     CU(s->arena.alloc(1, &s->d_error));

@@ -855,10 +855,25 @@ __device__ __forceinline__ float power_heuristic(float pf, float pg) { // mc.rs:
 enum { BX_REFLECTION = 1, BX_TRANSMISSION = 2, BX_DIFFUSE = 4, BX_GLOSSY = 8, BX_SPECULAR = 16 }; // bxdf/mod.rs:37-41
 constexpr uint32_t BX_ALL = 31, BX_NON_SPECULAR = BX_DIFFUSE | BX_GLOSSY | BX_REFLECTION | BX_TRANSMISSION;
 enum { LK_LAMBERT, LK_OREN_NAYAR, LK_SPEC_REFL, LK_SPEC_TRANS, LK_TS, LK_MT, LK_MERL };
+// Compile-time material kind of the split shade kernels' per-bucket instantiations (KIND = a TRB_MAT_* value, -1 = any): with the
+// paths bucketed by kind, a kernel that only ever sees one kind is compiled with that kind's lobes alone (fewer live values,
+// a fraction of the code). Same functions, same arithmetic: which lobes a Material has is data the specialised code knows already.
+__host__ __device__ constexpr bool lk_in(int KIND, int lk) {
+    return KIND < 0 ? true
+         : KIND == TRB_MAT_MATTE ? (lk == LK_LAMBERT || lk == LK_OREN_NAYAR)
+         : KIND == TRB_MAT_PLASTIC ? (lk == LK_LAMBERT || lk == LK_TS)
+         : KIND == TRB_MAT_METAL ? lk == LK_TS
+         : KIND == TRB_MAT_SPECULAR_METAL ? lk == LK_SPEC_REFL
+         : KIND == TRB_MAT_GLASS ? (lk == LK_SPEC_REFL || lk == LK_SPEC_TRANS)
+         : KIND == TRB_MAT_ROUGH_GLASS ? (lk == LK_TS || lk == LK_MT)
+         : lk == LK_MERL;
+}
 
 struct Mat { // DMaterial in registers
     uint32_t type; f3 c0, c1; float roughness, width, eta, on_a, on_b; uint32_t merl_off;
 };
+template <int KIND>
+__device__ __forceinline__ Mat mat_of_kind(const Mat& m) { Mat o = m; if (KIND >= 0) o.type = (uint32_t)KIND; return o; }
 __device__ __forceinline__ void load_mat(const DMaterial& m, Mat& o) {
     o.type = __ldg(&m.type);
     o.c0 = mk(__ldg(&m.c0[0]), __ldg(&m.c0[1]), __ldg(&m.c0[2]));
@@ -1084,10 +1099,12 @@ __device__ __noinline__ f3 merl_eval(const float* __restrict__ table, f3 wo, f3 
     return mk(__ldg(table + 3 * i), __ldg(table + 3 * i + 1), __ldg(table + 3 * i + 2));
 }
 
-__device__ f3 lobe_eval(const DScene& sc, const Mat& m, int kind, f3 col, f3 wo, f3 wi) {
+template <int KIND = -1>
+__device__ f3 lobe_eval(const DScene& sc, const Mat& m_, int kind, f3 col, f3 wo, f3 wi) {
+    const Mat m = mat_of_kind<KIND>(m_);
     switch (kind) {
-        case LK_LAMBERT: return col * TRB_INV_PI; // lambertian.rs:32-34
-        case LK_OREN_NAYAR: { // oren_nayar.rs:43-61
+        case LK_LAMBERT: if (!lk_in(KIND, LK_LAMBERT)) break; return col * TRB_INV_PI; // lambertian.rs:32-34
+        case LK_OREN_NAYAR: if (!lk_in(KIND, LK_OREN_NAYAR)) break; { // oren_nayar.rs:43-61
             const float so = sin_theta(wo), si = sin_theta(wi);
             float max_cos = 0.0f;
             if (si > 1e-4f && so > 1e-4f) max_cos = fmaxf(0.0f, cos_phi(wi) * cos_phi(wo) + sin_phi(wi) * sin_phi(wo));
@@ -1096,7 +1113,7 @@ __device__ f3 lobe_eval(const DScene& sc, const Mat& m, int kind, f3 col, f3 wo,
             else { sin_alpha = si; tan_beta = ieee_div(so, fabsf(wo.z)); }
             return col * TRB_INV_PI * (m.on_a + m.on_b * max_cos * sin_alpha * tan_beta);
         }
-        case LK_TS: { // torrance_sparrow.rs:40-56
+        case LK_TS: if (!lk_in(KIND, LK_TS)) break; { // torrance_sparrow.rs:40-56
             const float cto = fabsf(wo.z), cti = fabsf(wi.z);
             if (cto == 0.0f || cti == 0.0f) return splat(0.0f);
             f3 wh = wi + wo;
@@ -1107,7 +1124,7 @@ __device__ f3 lobe_eval(const DScene& sc, const Mat& m, int kind, f3 col, f3 wo,
             const float g = beck_g1(m.width, wi) * beck_g1(m.width, wo);
             return col * f * d * g / (4.0f * cti * cto);
         }
-        case LK_MT: { // microfacet_transmission.rs:65-82
+        case LK_MT: if (!lk_in(KIND, LK_MT)) break; { // microfacet_transmission.rs:65-82
             if (same_hemi(wo, wi)) return splat(0.0f);
             if (wo.z == 0.0f || wi.z == 0.0f) return splat(0.0f);
             float e0, e1;
@@ -1120,38 +1137,43 @@ __device__ f3 lobe_eval(const DScene& sc, const Mat& m, int kind, f3 col, f3 wo,
             const float jac = mt_jacobian(wo, wi, wh, e0, e1);
             return col * ieee_div(fabsf(ih), fabsf(wi.z) * fabsf(wo.z)) * (f * g * d) * jac;
         }
-        case LK_MERL: return merl_eval(sc.merl + m.merl_off, wo, wi);
-        default: return splat(0.0f); // specular lobes (specular_reflection.rs:38, specular_transmission.rs:38)
+        case LK_MERL: if (!lk_in(KIND, LK_MERL)) break; return merl_eval(sc.merl + m.merl_off, wo, wi);
+        default: break; // specular lobes (specular_reflection.rs:38, specular_transmission.rs:38)
     }
+    return splat(0.0f);
 }
-__device__ float lobe_pdf(const Mat& m, int kind, f3 wo, f3 wi) {
+template <int KIND = -1>
+__device__ float lobe_pdf(const Mat& m_, int kind, f3 wo, f3 wi) {
+    const Mat m = mat_of_kind<KIND>(m_);
     switch (kind) {
-        case LK_TS: { // torrance_sparrow.rs:73-81
+        case LK_TS: if (!lk_in(KIND, LK_TS)) break; { // torrance_sparrow.rs:73-81
             if (!same_hemi(wo, wi)) return 0.0f;
             const f3 wh = unit(wo + wi);
             const float jac = ieee_div(1.0f, 4.0f * fabsf(dot3(wo, wh)));
             return beck_pdf(m.width, wh) * jac;
         }
-        case LK_MT: { // microfacet_transmission.rs:100-108
+        case LK_MT: if (!lk_in(KIND, LK_MT)) break; { // microfacet_transmission.rs:100-108
             if (same_hemi(wo, wi)) return 0.0f;
             float e0, e1;
             mt_etas(m, wo, e0, e1);
             const f3 wh = mt_half(wo, wi, e0, e1);
             return beck_pdf(m.width, wh) * mt_jacobian(wo, wi, wh, e0, e1);
         }
-        default: // BxDF::pdf default (bxdf/mod.rs:114-121)
-            return same_hemi(wo, wi) ? fabsf(wi.z) * TRB_INV_PI : 0.0f;
+        default: break;
     }
+    return same_hemi(wo, wi) ? fabsf(wi.z) * TRB_INV_PI : 0.0f; // BxDF::pdf default (bxdf/mod.rs:114-121)
 }
-__device__ void lobe_sample(const DScene& sc, const Mat& m, int kind, f3 col, f3 wo, float u0, float u1, f3& f, f3& wi, float& pdf) {
+template <int KIND = -1>
+__device__ void lobe_sample(const DScene& sc, const Mat& m_, int kind, f3 col, f3 wo, float u0, float u1, f3& f, f3& wi, float& pdf) {
+    const Mat m = mat_of_kind<KIND>(m_);
     switch (kind) {
-        case LK_SPEC_REFL: { // specular_reflection.rs:39-50
+        case LK_SPEC_REFL: if (!lk_in(KIND, LK_SPEC_REFL)) break; { // specular_reflection.rs:39-50
             wi = mk(-wo.x, -wo.y, wo.z);
             if (wi.z != 0.0f) { f = fresnel(m, wo.z) * col / fabsf(wi.z); pdf = 1.0f; }
             else { f = splat(0.0f); pdf = 0.0f; }
             return;
         }
-        case LK_SPEC_TRANS: { // specular_transmission.rs:39-56
+        case LK_SPEC_TRANS: if (!lk_in(KIND, LK_SPEC_TRANS)) break; { // specular_transmission.rs:39-56
             float eta_i, eta_t;
             dielectric_etas(m, eta_i, eta_t);
             const bool entering = wo.z > 0.0f;
@@ -1165,32 +1187,31 @@ __device__ void lobe_sample(const DScene& sc, const Mat& m, int kind, f3 col, f3
             } else { f = splat(0.0f); wi = splat(0.0f); pdf = 0.0f; }
             return;
         }
-        case LK_TS: { // torrance_sparrow.rs:57-72
+        case LK_TS: if (!lk_in(KIND, LK_TS)) break; { // torrance_sparrow.rs:57-72
             if (wo.z == 0.0f) { f = splat(0.0f); wi = splat(0.0f); pdf = 0.0f; return; }
             f3 wh = beck_sample(m.width, u0, u1);
             if (!same_hemi(wo, wh)) wh = -wh;
             wi = 2.0f * dot3(wo, wh) * wh - wo; // linalg::reflect
             if (!same_hemi(wo, wi)) { f = splat(0.0f); wi = splat(0.0f); pdf = 0.0f; }
-            else { f = lobe_eval(sc, m, kind, col, wo, wi); pdf = lobe_pdf(m, kind, wo, wi); }
+            else { f = lobe_eval<KIND>(sc, m, kind, col, wo, wi); pdf = lobe_pdf<KIND>(m, kind, wo, wi); }
             return;
         }
-        case LK_MT: { // microfacet_transmission.rs:83-99
+        case LK_MT: if (!lk_in(KIND, LK_MT)) break; { // microfacet_transmission.rs:83-99
             f3 wh = beck_sample(m.width, u0, u1);
             if (!same_hemi(wo, wh)) wh = -wh;
             float e0, e1;
             mt_etas(m, wo, e0, e1);
             f3 r;
-            if (refract3(wo, wh, e0 / e1, r) && !same_hemi(wo, r)) { wi = r; f = lobe_eval(sc, m, kind, col, wo, wi); pdf = lobe_pdf(m, kind, wo, wi); }
+            if (refract3(wo, wh, e0 / e1, r) && !same_hemi(wo, r)) { wi = r; f = lobe_eval<KIND>(sc, m, kind, col, wo, wi); pdf = lobe_pdf<KIND>(m, kind, wo, wi); }
             else { f = splat(0.0f); wi = splat(0.0f); pdf = 0.0f; }
             return;
         }
-        default: { // BxDF::sample default (bxdf/mod.rs:102-108): Lambertian, Oren-Nayar, Merl
-            wi = cos_hemisphere(u0, u1);
-            if (wo.z < 0.0f) wi.z *= -1.0f;
-            f = lobe_eval(sc, m, kind, col, wo, wi); pdf = lobe_pdf(m, kind, wo, wi);
-            return;
-        }
+        default: break;
     }
+    // BxDF::sample default (bxdf/mod.rs:102-108): Lambertian, Oren-Nayar, Merl
+    wi = cos_hemisphere(u0, u1);
+    if (wo.z < 0.0f) wi.z *= -1.0f;
+    f = lobe_eval<KIND>(sc, m, kind, col, wo, wi); pdf = lobe_pdf<KIND>(m, kind, wo, wi);
 }
 
 // bxdf::BSDF (bsdf.rs)
@@ -1207,29 +1228,35 @@ __device__ __forceinline__ f3 from_shading(const Frame& fr, f3 v) {
     return mk(fr.bitan.x * v.x + fr.tan.x * v.y + fr.n.x * v.z, fr.bitan.y * v.x + fr.tan.y * v.y + fr.n.y * v.z,
               fr.bitan.z * v.x + fr.tan.z * v.y + fr.n.z * v.z);
 }
-__device__ __noinline__ f3 bsdf_eval(const DScene& sc, const Mat& m, const Frame& fr, f3 wo_w, f3 wi_w, uint32_t flags) { // bsdf.rs:66-78
+template <int KIND = -1>
+__device__ __noinline__ f3 bsdf_eval(const DScene& sc, const Mat& m_, const Frame& fr, f3 wo_w, f3 wi_w, uint32_t flags) { // bsdf.rs:66-78
+    const Mat m = mat_of_kind<KIND>(m_);
     const f3 wo = unit(to_shading(fr, wo_w)), wi = unit(to_shading(fr, wi_w));
     if (wo.z * wi.z > 0.0f) flags &= ~(uint32_t)BX_TRANSMISSION; else flags &= ~(uint32_t)BX_REFLECTION;
     f3 acc = splat(0.0f);
 #pragma unroll 1
     for (int i = 0; i < 2; ++i) {
         int kind; uint32_t type; f3 col;
-        if (lobe_of(m, i, kind, type, col) && type_matches(type, flags)) acc = acc + lobe_eval(sc, m, kind, col, wo, wi);
+        if (lobe_of(m, i, kind, type, col) && type_matches(type, flags)) acc = acc + lobe_eval<KIND>(sc, m, kind, col, wo, wi);
     }
     return acc;
 }
-__device__ __noinline__ float bsdf_pdf(const Mat& m, const Frame& fr, f3 wo_w, f3 wi_w, uint32_t flags) { // bsdf.rs:114-125
+template <int KIND = -1>
+__device__ __noinline__ float bsdf_pdf(const Mat& m_, const Frame& fr, f3 wo_w, f3 wi_w, uint32_t flags) { // bsdf.rs:114-125
+    const Mat m = mat_of_kind<KIND>(m_);
     const f3 wo = unit(to_shading(fr, wo_w)), wi = unit(to_shading(fr, wi_w));
     float pdf = 0.0f; int n = 0;
 #pragma unroll 1
     for (int i = 0; i < 2; ++i) {
         int kind; uint32_t type; f3 col;
-        if (lobe_of(m, i, kind, type, col) && type_matches(type, flags)) { pdf = pdf + lobe_pdf(m, kind, wo, wi); n++; }
+        if (lobe_of(m, i, kind, type, col) && type_matches(type, flags)) { pdf = pdf + lobe_pdf<KIND>(m, kind, wo, wi); n++; }
     }
     return n > 0 ? ieee_div(pdf, (float)n) : 0.0f;
 }
-__device__ __noinline__ void bsdf_sample(const DScene& sc, const Mat& m, const Frame& fr, f3 wo_w, uint32_t flags, float u0, float u1, float uc,
+template <int KIND = -1>
+__device__ __noinline__ void bsdf_sample(const DScene& sc, const Mat& m_, const Frame& fr, f3 wo_w, uint32_t flags, float u0, float u1, float uc,
                                          f3& f, f3& wi_w, float& pdf, uint32_t& sampled) { // bsdf.rs:85-112
+    const Mat m = mat_of_kind<KIND>(m_);
     int n_matching = 0;
     for (int i = 0; i < 2; ++i) { int k; uint32_t t; f3 c; if (lobe_of(m, i, k, t, c) && type_matches(t, flags)) n_matching++; }
     if (n_matching == 0) { f = splat(0.0f); wi_w = splat(0.0f); pdf = 0.0f; sampled = 0; return; }
@@ -1242,12 +1269,12 @@ __device__ __noinline__ void bsdf_sample(const DScene& sc, const Mat& m, const F
     }
     const f3 wo = unit(to_shading(fr, wo_w));
     f3 wi;
-    lobe_sample(sc, m, kind, col, wo, u0, u1, f, wi, pdf);
+    lobe_sample<KIND>(sc, m, kind, col, wo, u0, u1, f, wi, pdf);
     if (len2(wi) == 0.0f) { f = splat(0.0f); wi_w = splat(0.0f); pdf = 0.0f; sampled = 0; return; }
     wi_w = unit(from_shading(fr, wi));
     const bool spec = (type & BX_SPECULAR) != 0;
-    if (!spec && n_matching > 1) pdf = bsdf_pdf(m, fr, wo_w, wi_w, flags);
-    if (!spec) f = bsdf_eval(sc, m, fr, wo_w, wi_w, flags);
+    if (!spec && n_matching > 1) pdf = bsdf_pdf<KIND>(m, fr, wo_w, wi_w, flags);
+    if (!spec) f = bsdf_eval<KIND>(sc, m, fr, wo_w, wi_w, flags);
     sampled = type;
 }
 
@@ -1358,7 +1385,7 @@ struct DirectSetup {
     bool has_shadow, has_mis;
 };
 
-template <bool ANIM>
+template <bool ANIM, int KIND = -1>
 __device__ __noinline__ void direct_setup(const DScene& sc, const Mat& m, const Frame& fr, f3 wo, uint32_t li, float l0, float l1, float b0, float b1,
                                           float bc, float time, DirectSetup& ds, const float* xf_row = nullptr) {
     ds.a = splat(0.0f); ds.b = splat(0.0f); ds.shadow_d = splat(0.0f); ds.mis_d = splat(0.0f); ds.has_shadow = false; ds.has_mis = false;
@@ -1394,11 +1421,11 @@ __device__ __noinline__ void direct_setup(const DScene& sc, const Mat& m, const 
     if (pdf_light > 0.0f && !black(lrad)) {
         ds.has_shadow = true; ds.shadow_d = seg; // OcclusionTester::test_points: Ray::segment(a, b - a, 0.001, 0.999)
         // evaluated only when unoccluded in the reference; a pure function of the same inputs, so hoisting it is exact
-        const f3 f = bsdf_eval(sc, m, fr, wo, wi, BX_NON_SPECULAR);
+        const f3 f = bsdf_eval<KIND>(sc, m, fr, wo, wi, BX_NON_SPECULAR);
         if (!black(f)) {
             if (delta) ds.a = f * lrad * fabsf(dot3(wi, fr.n)) / pdf_light;
             else {
-                const float pdf_bsdf = bsdf_pdf(m, fr, wo, wi, BX_NON_SPECULAR);
+                const float pdf_bsdf = bsdf_pdf<KIND>(m, fr, wo, wi, BX_NON_SPECULAR);
                 const float w = power_heuristic(pdf_light, pdf_bsdf);
                 ds.a = f * lrad * fabsf(dot3(wi, fr.n)) * w / pdf_light;
             }
@@ -1406,7 +1433,7 @@ __device__ __noinline__ void direct_setup(const DScene& sc, const Mat& m, const 
     }
     if (!delta) { // --- BSDF sampling ---
         f3 f, wi2; float pdf_bsdf; uint32_t sampled;
-        bsdf_sample(sc, m, fr, wo, BX_NON_SPECULAR, b0, b1, bc, f, wi2, pdf_bsdf, sampled);
+        bsdf_sample<KIND>(sc, m, fr, wo, BX_NON_SPECULAR, b0, b1, bc, f, wi2, pdf_bsdf, sampled);
         if (pdf_bsdf > 0.0f && !black(f)) {
             float w = 1.0f;
             bool go = true;
@@ -1476,7 +1503,7 @@ __device__ __forceinline__ void bounce_emission(const DScene& sc, uint32_t hit_i
         }
     }
 }
-template <bool ANIM>
+template <bool ANIM, int KIND = -1>
 __device__ __forceinline__ void bounce_direct(const DScene& sc, const Mat& m, const Frame& fr, f3 wo, uint32_t bounce, uint32_t hsample, float time, DirectSetup& ds,
                                               uint32_t& light, const float* xf_row = nullptr) {
     PathRng rng; rng.h = hsample; rng.len = sc.max_depth + 1;
@@ -1487,16 +1514,17 @@ __device__ __forceinline__ void bounce_direct(const DScene& sc, const Mat& m, co
     uint32_t l = f2u(lc * (float)sc.n_lights); // sample_one_light (integrator/mod.rs:108-110), no xN (Q2)
     if (l > sc.n_lights - 1) l = sc.n_lights - 1;
     light = __ldg(&sc.lights[l]);
-    direct_setup<ANIM>(sc, m, fr, wo, light, l0, l1, b0, b1, bc, time, ds, xf_row);
+    direct_setup<ANIM, KIND>(sc, m, fr, wo, light, l0, l1, b0, b1, bc, time, ds, xf_row);
 }
 struct ScatterOut { f3 throughput, next_d; bool specular, terminate; };
+template <int KIND = -1>
 __device__ __forceinline__ void bounce_scatter(const DScene& sc, const Mat& m, const Frame& fr, f3 wo, uint32_t bounce, uint32_t hsample, f3 throughput_in, ScatterOut& o) {
     PathRng rng; rng.h = hsample; rng.len = sc.max_depth + 1;
     float q0, q1;
     rng.two_d(bounce, S_P0, S_P1, S_P_PERM, q0, q1);
     const float qc = rng.one_d(bounce, S_PC, S_PC_PERM);
     f3 f, wi; float pdf; uint32_t sampled;
-    bsdf_sample(sc, m, fr, wo, BX_ALL, q0, q1, qc, f, wi, pdf, sampled);
+    bsdf_sample<KIND>(sc, m, fr, wo, BX_ALL, q0, q1, qc, f, wi, pdf, sampled);
     o.throughput = throughput_in; o.next_d = splat(0.0f); o.specular = false; o.terminate = true;
     if (black(f) || pdf == 0.0f) return;
     o.specular = (sampled & BX_SPECULAR) != 0;
@@ -2502,13 +2530,16 @@ __global__ void __launch_bounds__(128, MINB) k_wf_shade_a(const __grid_constant_
     }
 }
 
-template <bool ANIM, int MINB>
+// KIND >= 0: the instantiation compiled for that material kind alone; it drains that kind's bucket. KIND = -1: any kind; drains the
+// buckets of `bucket_mask` (the kinds the scene uses that have no instantiation of their own).
+template <bool ANIM, int MINB, int KIND = -1>
 __global__ void __launch_bounds__(128, MINB) k_wf_shade_b(const __grid_constant__ DScene sc, const __grid_constant__ RenderParams rp, const __grid_constant__ WfState wf,
-                                                     uint32_t round) {
+                                                     uint32_t round, uint32_t bucket_mask) {
     uint32_t* cnt_r = wf.counters + round * WF_CNT;
     uint32_t* cnt_n = wf.counters + (round + 1) * WF_CNT;
     const int lane = threadIdx.x & 31;
     for (uint32_t bucket = 0; bucket < WF_MID_BUCKETS; ++bucket) {
+    if (!((bucket_mask >> bucket) & 1u)) continue;
     const uint32_t n = cnt_r[WF_MID_K + bucket];
     const uint32_t* __restrict__ q_mid = wf.q_mid + (size_t)bucket * wf.n_paths;
     for (;;) {
@@ -2531,7 +2562,7 @@ __global__ void __launch_bounds__(128, MINB) k_wf_shade_b(const __grid_constant_
             const SampleId id = sample_id(sc, rp, p);
             const uint32_t hs = rng_absorb(rng_absorb(rng_seed(rp.seed), id.pixel), id.si);
             DirectSetup ds; uint32_t light;
-            bounce_direct<ANIM>(sc, m, fr, wo, round, hs, th4.w, ds, light, wf_xf_row<ANIM>(wf, p));
+            bounce_direct<ANIM, KIND>(sc, m, fr, wo, round, hs, th4.w, ds, light, wf_xf_row<ANIM>(wf, p));
             push_shadow = ds.has_shadow; push_mis = ds.has_mis;
             wf.org[p] = make_float4(fr.p.x, fr.p.y, fr.p.z, __uint_as_float((push_shadow ? WF_F_SHADOW : 0u) | (push_mis ? WF_F_MIS : 0u)));
             if (push_shadow) wf.shadow[p] = make_float4(ds.shadow_d.x, ds.shadow_d.y, ds.shadow_d.z, 0.0f);
@@ -2546,14 +2577,15 @@ __global__ void __launch_bounds__(128, MINB) k_wf_shade_b(const __grid_constant_
     }
 }
 
-template <int MODE, bool ANIM, int MINB>
+template <int MODE, bool ANIM, int MINB, int KIND = -1>
 __global__ void __launch_bounds__(128, MINB) k_wf_shade_c(const __grid_constant__ DScene sc, const __grid_constant__ RenderParams rp, const __grid_constant__ WfState wf,
-                                                     uint32_t round) {
+                                                     uint32_t round, uint32_t bucket_mask) {
     uint32_t* cnt_r = wf.counters + round * WF_CNT;
     uint32_t* cnt_n = wf.counters + (round + 1) * WF_CNT;
     uint32_t* act_next = wf.q_active[(round + 1) & 1];
     const int lane = threadIdx.x & 31;
     for (uint32_t bucket = 0; bucket < WF_MID_BUCKETS; ++bucket) {
+    if (!((bucket_mask >> bucket) & 1u)) continue;
     const uint32_t n = cnt_r[WF_MID_K + bucket];
     const uint32_t* __restrict__ q_mid = wf.q_mid + (size_t)bucket * wf.n_paths;
     for (;;) {
@@ -2577,7 +2609,7 @@ __global__ void __launch_bounds__(128, MINB) k_wf_shade_c(const __grid_constant_
             const SampleId id = sample_id(sc, rp, p);
             const uint32_t hs = rng_absorb(rng_absorb(rng_seed(rp.seed), id.pixel), id.si);
             ScatterOut so;
-            bounce_scatter(sc, m, fr, wo, round, hs, mk(th4.x, th4.y, th4.z), so);
+            bounce_scatter<KIND>(sc, m, fr, wo, round, hs, mk(th4.x, th4.y, th4.z), so);
             const uint32_t fb = __float_as_uint(wf.org[p].w); // WF_F_SHADOW | WF_F_MIS from k_wf_shade_b
             push_cont = !so.terminate;
             push_active = push_cont || (fb & (WF_F_SHADOW | WF_F_MIS)) != 0u;
