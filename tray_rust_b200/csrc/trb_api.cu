@@ -212,6 +212,7 @@ struct trb_scene {
     std::vector<HostMesh> meshes;
     uint32_t spp_pow2 = 1;
     uint32_t n_anim = 0;                 // instances whose transform stack is keyframed (evaluated per path into WfState::xf_tab)
+    bool frame_set = false; uint32_t last_frame = 0; float last_start = 0, last_end = 0; // the arguments of the last update_frame (re-run when an option changes what it builds)
     uint32_t material_kinds = 0;         // bit k: some hittable instance's material is of kind k (TRB_MAT_*)
     bool mixed_materials = false;        // the hittable instances use >= 2 material kinds or a MERL table: the split shade kernels with material buckets win (Tuning::shade_split = -1)
     uint32_t* d_anim_instances = nullptr;
@@ -667,7 +668,12 @@ trb_status trb_scene_set_option(trb_scene* s, const char* name, long long value)
     else if (k == "trace.occupancy" || k == "trace.smem_stack") {} // round-1 knobs: the variant (trace.pipe) now fixes both
     else if (k == "trace.grid") t.trace_grid = (unsigned)std::max<long long>(0, value);
     else if (k == "trace.sched") t.sched = (uint32_t)value;
-    else if (k == "trace.quads") t.quads = (int)value;
+    else if (k == "trace.quads" || k == "frame.device") { // both decide what update_frame builds (the DQuad TLAS records exist on the host path only): rebuild the current frame
+        int& field = k == "trace.quads" ? t.quads : t.frame_device;
+        const bool changed = (field != 0) != (value != 0);
+        field = (int)value;
+        if (changed && s->frame_set) return trb_scene_update_frame(s, s->last_frame, s->last_start, s->last_end);
+    }
     else if (k == "trace.pipe") t.pipe = (int)value;
     else if (k == "trace.exact_box") t.exact_box = (int)value;
     else if (k == "film.v2") t.film_v2 = (int)value;
@@ -678,7 +684,6 @@ trb_status trb_scene_set_option(trb_scene* s, const char* name, long long value)
     else if (k == "shade.sort") t.shade_sort = (int)value;
     else if (k == "shade.kind") t.shade_kind = (int)value;
     else if (k == "anim.table") t.anim_table = (int)value;
-    else if (k == "frame.device") t.frame_device = (int)value;
     else if (k == "shade.anim_occupancy") t.shade_anim_occ = (int)value;
     else if (k == "pass.paths") { if (value < 64) return fail(TRB_INVALID_ARG, "pass.paths must be >= 64"); t.pass_paths = (uint64_t)value; }
     else return fail(TRB_INVALID_ARG, "unknown option: " + k);
@@ -941,6 +946,7 @@ trb_status trb_scene_update_frame(trb_scene* s, uint32_t frame, float start, flo
     // A frame boundary: passes enqueued with trb_render_device may still be reading the instances / TLAS this call
     // overwrites, so the device is drained first (the reference's update_frame likewise runs between renders, scene.rs:152).
     CU(cudaDeviceSynchronize());
+    s->frame_set = true; s->last_frame = frame; s->last_start = start; s->last_end = end;
     // camera selection (scene.rs:153-166)
     int cam;
     if (s->active_camera >= 0) {
