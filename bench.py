@@ -19,7 +19,7 @@ steps ends with that one reduce. Per-GPU work is therefore constant in N: "scali
            SURVEY §8d; counted by the kernel's own test counters in an untimed replay of the same passes) over its
            measured duration, against the measured HBM peak in MEASURED_PEAKS.json — AND, because the BVH is L2-resident,
            what ncu measured for the same launches (profiles/traffic.json): real DRAM bytes (`traffic`, `dram_gbs`,
-           `dram_frac`), L2 sector traffic (`l2_gbs`) and the unit that actually limits the kernel (`limiter`).
+           `dram_frac`), L2 sector traffic (`l2_gbs`), the L1TEX data-pipe and issue-slot utilisation, and what limits the kernel (`limiter`).
 """
 import argparse
 import json
@@ -406,9 +406,12 @@ def run_ours(a):
             "roofline": {"bound": "hbm", "kernel": "k_wf_trace", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
                          "peak_source": "MEASURED_PEAKS.json hbm_gbs (measured)" if peaks else "fallback 6650 GB/s",
                          "traffic": traffic, "dram_gbs": dram_gbs, "dram_frac": dram_gbs / peak if dram_gbs else None,
-                         "l2_gbs": l2_gbs, "l1tex_data_pipe_pct": prof.get("l1tex_data_pipe_pct"), "limiter": prof.get("limiter"),
+                         "l2_gbs": l2_gbs, "l1tex_data_pipe_pct": prof.get("l1tex_data_pipe_pct"), "issue_active_pct": prof.get("issue_active_pct"),
+                         "limiter": "latency of dependent node fetches + SIMT divergence",
                          "note": "frac = ALGORITHMIC bytes (SURVEY 8d definition, reference data structure) over time vs the HBM peak; the ~90 MB BVH is L2-resident, so the "
-                                 "HBM bandwidth ncu measures for the same launches is dram_gbs (dram_frac of peak) and the kernel's limiter is the L1TEX data pipe",
+                                 "HBM bandwidth ncu measures for the same launches is dram_gbs (dram_frac of peak). The busiest unit ncu shows is the L1TEX data pipe "
+                                 "(l1tex_data_pipe_pct), but it is not the limiter: one more L1-hitting 256-bit load per node visit costs 2 % "
+                                 "(profiles/r02_c16_diag_extra_l1_load.log); 38 % of warp time waits on the fetch of the next node record, 15.7 of 32 lanes are active",
                          "algorithmic_bytes_per_launch": bytes_per_launch, "launches": trace_launches,
                          "avg_launch_ms": trace_ms / trace_launches, "trace_ms_per_step": trace_ms / a.steps,
                          "step_kernels_ms": avg_kernel_ms,
