@@ -457,11 +457,14 @@ void trb_desc_free(trb_scene_desc* desc);
  * trb_render_device / trb_intersect_device (TRB_CUDA), else TRB_OK. */
 trb_status trb_scene_check_error(trb_scene* scene);
 
-/* Launch-shape options of the wavefront pipeline (results never depend on them; DESIGN.md "Options"):
- * "pass.paths" camera samples per pass, "sort.mode" 0/1 ray-queue sorting, "sort.bits", "sort.min_round",
- * "shade.split" 0/1, "anim.table" 0/1, "frame.device" 0/1, "shade.anim_occupancy" 3/4, "film.v2" 0/1, "trace.refill", "trace.occupancy", "trace.grid",
- * "trace.smem_stack", "trace.sched", "trace.quads". Defaults can also be preset by TRB_* environment
- * variables, read once by trb_scene_create. */
+/* Launch-shape options of the wavefront pipeline (results never depend on them; DESIGN.md "Launch options"):
+ * "pass.paths" camera samples per pass; "trace.pipe" trace-kernel variant (36 = default: 9 CTAs per SM; 0 = the round-1 kernel),
+ * "trace.refill", "trace.grid", "trace.sched", "trace.quads", "trace.exact_box" (test: every ray takes the literal box test);
+ * "shade.split" -1 per scene / 0 fused / 1 split, "shade.sort" 0/1 material buckets between the split kernels, "shade.kind" 0/1 the
+ * matte instantiations of the split kernels, "shade.anim_occupancy" 3/4; "anim.table" 0/1/2, "frame.device" 0/1; "film.v2" 0/1;
+ * "sort.mode" 0/1/2 ray-queue sorting, "sort.bits", "sort.min_round". "trace.quads" and "frame.device" re-run update_frame for the
+ * current frame (they change what it builds). Defaults can also be preset by TRB_* environment variables, read once by
+ * trb_scene_create. */
 trb_status trb_scene_set_option(trb_scene* scene, const char* name, long long value);
 
 /* Device time spent in the dominant kernel (k_wf_trace) by launches made with TRB_RENDER_TIME_TRACE since the last
