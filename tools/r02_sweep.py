@@ -19,7 +19,7 @@ flush = torch.empty(256 << 20, dtype=torch.uint8, device=dev)
 g = api.Scene(SB.scene_c4(1_000_000, W, H, 4096).finish(), 0)
 g.update_frame(0, 0.0, 0.0)
 DEFAULTS = {"sort.mode": 0, "sort.bits": 5, "sort.min_round": 1, "shade.split": 0, "trace.refill": 8, "trace.sched": 6, "trace.grid": 0,
-            "trace.pipe": 36}
+            "trace.pipe": 36, "shade.kind": 1}
 ref = None
 
 
@@ -77,3 +77,7 @@ if "final" in VARIANTS:  # the round's trace-kernel steps side by side, in one p
     measure("trace.pipe=34 (8 CTAs per SM)", trace_pipe=34)
     measure("trace.pipe=36 (9 CTAs per SM) = default", trace_pipe=36)
     measure("split shade", shade_split=1)
+if "kind" in VARIANTS:  # the matte instantiations of the split shade kernels against the generic split kernels and the fused kernel (C4 is all matte)
+    measure("split + matte instantiations = per-scene default", shade_split=-1, shade_kind=1)
+    measure("split, generic kernels", shade_split=1, shade_kind=0)
+    measure("fused shade kernel", shade_split=0)

@@ -872,8 +872,6 @@ __host__ __device__ constexpr bool lk_in(int KIND, int lk) {
 struct Mat { // DMaterial in registers
     uint32_t type; f3 c0, c1; float roughness, width, eta, on_a, on_b; uint32_t merl_off;
 };
-template <int KIND>
-__device__ __forceinline__ Mat mat_of_kind(const Mat& m) { Mat o = m; if (KIND >= 0) o.type = (uint32_t)KIND; return o; }
 __device__ __forceinline__ void load_mat(const DMaterial& m, Mat& o) {
     o.type = __ldg(&m.type);
     o.c0 = mk(__ldg(&m.c0[0]), __ldg(&m.c0[1]), __ldg(&m.c0[2]));
@@ -955,8 +953,12 @@ __device__ __forceinline__ void load_mat_at(const DScene& sc, uint32_t material,
 }
 // The lobes Material::bsdf allocates, in allocation order (material/{matte:52,plastic:59,metal:56,
 // specular_metal:49,glass:51,rough_glass:57,merl:88}.rs). Returns false when lobe `i` does not exist.
+// Material kind: the template argument where the caller is an instantiation for one kind, else the material's own field
+template <int KIND>
+__device__ __forceinline__ uint32_t mat_kind(const Mat& m) { return KIND >= 0 ? (uint32_t)KIND : m.type; }
+template <int KIND = -1>
 __device__ __forceinline__ bool lobe_of(const Mat& m, int i, int& kind, uint32_t& type, f3& col) {
-    switch (m.type) {
+    switch (mat_kind<KIND>(m)) {
         case TRB_MAT_MATTE:
             if (i != 0) return false;
             kind = m.roughness == 0.0f ? LK_LAMBERT : LK_OREN_NAYAR; type = BX_DIFFUSE | BX_REFLECTION; col = m.c0; return true;
@@ -1000,9 +1002,11 @@ __device__ __forceinline__ float sin_phi(f3 v) { float s = sin_theta(v); return 
 __device__ __forceinline__ bool same_hemi(f3 a, f3 b) { return a.z * b.z > 0.0f; }
 
 // fresnel.rs. Conductor for the metals, Dielectric(1, eta) for glass, Dielectric(1, 1.5) for plastic (Q16).
-__device__ __forceinline__ void dielectric_etas(const Mat& m, float& ei, float& et) { ei = 1.0f; et = m.type == TRB_MAT_PLASTIC ? 1.5f : m.eta; }
+template <int KIND = -1>
+__device__ __forceinline__ void dielectric_etas(const Mat& m, float& ei, float& et) { ei = 1.0f; et = mat_kind<KIND>(m) == TRB_MAT_PLASTIC ? 1.5f : m.eta; }
+template <int KIND = -1>
 __device__ __forceinline__ f3 fresnel(const Mat& m, float cos_i) {
-    if (m.type == TRB_MAT_METAL || m.type == TRB_MAT_SPECULAR_METAL) { // fresnel.rs:19-28
+    if (mat_kind<KIND>(m) == TRB_MAT_METAL || mat_kind<KIND>(m) == TRB_MAT_SPECULAR_METAL) { // fresnel.rs:19-28
         const float c = fabsf(cos_i);
         const f3 eta = m.c0, k = m.c1, one = splat(1.0f);
         const f3 a = (eta * eta + k * k) * c * c;
@@ -1013,7 +1017,7 @@ __device__ __forceinline__ f3 fresnel(const Mat& m, float cos_i) {
         return (r_par + r_perp) * 0.5f;
     }
     float eta_i, eta_t;
-    dielectric_etas(m, eta_i, eta_t);
+    dielectric_etas<KIND>(m, eta_i, eta_t);
     const float ci = clampf(cos_i, -1.0f, 1.0f); // fresnel.rs:48-66
     const float ei = ci > 0.0f ? eta_i : eta_t, et = ci > 0.0f ? eta_t : eta_i;
     const float sin_t = ieee_div(ei, et) * ieee_sqrt(fmaxf(0.0f, 1.0f - ci * ci));
@@ -1060,9 +1064,10 @@ __device__ __forceinline__ bool refract3(f3 w, f3 n, float eta, f3& out) { // li
     return true;
 }
 // microfacet_transmission.rs helpers
+template <int KIND = -1>
 __device__ __forceinline__ void mt_etas(const Mat& m, f3 wo, float& e0, float& e1) { // :33-39
     float ei, et;
-    dielectric_etas(m, ei, et);
+    dielectric_etas<KIND>(m, ei, et);
     if (wo.z > 0.0f) { e0 = ei; e1 = et; } else { e0 = et; e1 = ei; }
 }
 __device__ __forceinline__ float mt_jacobian(f3 wo, f3 wi, f3 wh, float e0, float e1) { // :40-49
@@ -1100,8 +1105,7 @@ __device__ __noinline__ f3 merl_eval(const float* __restrict__ table, f3 wo, f3 
 }
 
 template <int KIND = -1>
-__device__ f3 lobe_eval(const DScene& sc, const Mat& m_, int kind, f3 col, f3 wo, f3 wi) {
-    const Mat m = mat_of_kind<KIND>(m_);
+__device__ f3 lobe_eval(const DScene& sc, const Mat& m, int kind, f3 col, f3 wo, f3 wi) {
     switch (kind) {
         case LK_LAMBERT: if (!lk_in(KIND, LK_LAMBERT)) break; return col * TRB_INV_PI; // lambertian.rs:32-34
         case LK_OREN_NAYAR: if (!lk_in(KIND, LK_OREN_NAYAR)) break; { // oren_nayar.rs:43-61
@@ -1120,7 +1124,7 @@ __device__ f3 lobe_eval(const DScene& sc, const Mat& m_, int kind, f3 col, f3 wo
             if (wh.x == 0.0f && wh.y == 0.0f && wh.z == 0.0f) return splat(0.0f);
             wh = unit(wh);
             const float d = beck_d(m.width, wh);
-            const f3 f = fresnel(m, dot3(wi, wh));
+            const f3 f = fresnel<KIND>(m, dot3(wi, wh));
             const float g = beck_g1(m.width, wi) * beck_g1(m.width, wo);
             return col * f * d * g / (4.0f * cti * cto);
         }
@@ -1128,10 +1132,10 @@ __device__ f3 lobe_eval(const DScene& sc, const Mat& m_, int kind, f3 col, f3 wo
             if (same_hemi(wo, wi)) return splat(0.0f);
             if (wo.z == 0.0f || wi.z == 0.0f) return splat(0.0f);
             float e0, e1;
-            mt_etas(m, wo, e0, e1);
+            mt_etas<KIND>(m, wo, e0, e1);
             const f3 wh = mt_half(wo, wi, e0, e1);
             const float d = beck_d(m.width, wh);
-            const f3 f = splat(1.0f) - fresnel(m, dot3(wi, wh));
+            const f3 f = splat(1.0f) - fresnel<KIND>(m, dot3(wi, wh));
             const float g = beck_g1(m.width, wi) * beck_g1(m.width, wo);
             const float ih = dot3(wi, wh);
             const float jac = mt_jacobian(wo, wi, wh, e0, e1);
@@ -1143,8 +1147,7 @@ __device__ f3 lobe_eval(const DScene& sc, const Mat& m_, int kind, f3 col, f3 wo
     return splat(0.0f);
 }
 template <int KIND = -1>
-__device__ float lobe_pdf(const Mat& m_, int kind, f3 wo, f3 wi) {
-    const Mat m = mat_of_kind<KIND>(m_);
+__device__ float lobe_pdf(const Mat& m, int kind, f3 wo, f3 wi) {
     switch (kind) {
         case LK_TS: if (!lk_in(KIND, LK_TS)) break; { // torrance_sparrow.rs:73-81
             if (!same_hemi(wo, wi)) return 0.0f;
@@ -1155,7 +1158,7 @@ __device__ float lobe_pdf(const Mat& m_, int kind, f3 wo, f3 wi) {
         case LK_MT: if (!lk_in(KIND, LK_MT)) break; { // microfacet_transmission.rs:100-108
             if (same_hemi(wo, wi)) return 0.0f;
             float e0, e1;
-            mt_etas(m, wo, e0, e1);
+            mt_etas<KIND>(m, wo, e0, e1);
             const f3 wh = mt_half(wo, wi, e0, e1);
             return beck_pdf(m.width, wh) * mt_jacobian(wo, wi, wh, e0, e1);
         }
@@ -1164,25 +1167,24 @@ __device__ float lobe_pdf(const Mat& m_, int kind, f3 wo, f3 wi) {
     return same_hemi(wo, wi) ? fabsf(wi.z) * TRB_INV_PI : 0.0f; // BxDF::pdf default (bxdf/mod.rs:114-121)
 }
 template <int KIND = -1>
-__device__ void lobe_sample(const DScene& sc, const Mat& m_, int kind, f3 col, f3 wo, float u0, float u1, f3& f, f3& wi, float& pdf) {
-    const Mat m = mat_of_kind<KIND>(m_);
+__device__ void lobe_sample(const DScene& sc, const Mat& m, int kind, f3 col, f3 wo, float u0, float u1, f3& f, f3& wi, float& pdf) {
     switch (kind) {
         case LK_SPEC_REFL: if (!lk_in(KIND, LK_SPEC_REFL)) break; { // specular_reflection.rs:39-50
             wi = mk(-wo.x, -wo.y, wo.z);
-            if (wi.z != 0.0f) { f = fresnel(m, wo.z) * col / fabsf(wi.z); pdf = 1.0f; }
+            if (wi.z != 0.0f) { f = fresnel<KIND>(m, wo.z) * col / fabsf(wi.z); pdf = 1.0f; }
             else { f = splat(0.0f); pdf = 0.0f; }
             return;
         }
         case LK_SPEC_TRANS: if (!lk_in(KIND, LK_SPEC_TRANS)) break; { // specular_transmission.rs:39-56
             float eta_i, eta_t;
-            dielectric_etas(m, eta_i, eta_t);
+            dielectric_etas<KIND>(m, eta_i, eta_t);
             const bool entering = wo.z > 0.0f;
             const float ei = entering ? eta_i : eta_t, et = entering ? eta_t : eta_i;
             const f3 n = entering ? mk(0.0f, 0.0f, 1.0f) : mk(0.0f, 0.0f, -1.0f);
             f3 r;
             if (refract3(wo, n, ei / et, r)) {
                 wi = r;
-                const f3 fr = splat(1.0f) - fresnel(m, wi.z);
+                const f3 fr = splat(1.0f) - fresnel<KIND>(m, wi.z);
                 f = fr * col / fabsf(wi.z); pdf = 1.0f;
             } else { f = splat(0.0f); wi = splat(0.0f); pdf = 0.0f; }
             return;
@@ -1200,7 +1202,7 @@ __device__ void lobe_sample(const DScene& sc, const Mat& m_, int kind, f3 col, f
             f3 wh = beck_sample(m.width, u0, u1);
             if (!same_hemi(wo, wh)) wh = -wh;
             float e0, e1;
-            mt_etas(m, wo, e0, e1);
+            mt_etas<KIND>(m, wo, e0, e1);
             f3 r;
             if (refract3(wo, wh, e0 / e1, r) && !same_hemi(wo, r)) { wi = r; f = lobe_eval<KIND>(sc, m, kind, col, wo, wi); pdf = lobe_pdf<KIND>(m, kind, wo, wi); }
             else { f = splat(0.0f); wi = splat(0.0f); pdf = 0.0f; }
@@ -1229,43 +1231,40 @@ __device__ __forceinline__ f3 from_shading(const Frame& fr, f3 v) {
               fr.bitan.z * v.x + fr.tan.z * v.y + fr.n.z * v.z);
 }
 template <int KIND = -1>
-__device__ __noinline__ f3 bsdf_eval(const DScene& sc, const Mat& m_, const Frame& fr, f3 wo_w, f3 wi_w, uint32_t flags) { // bsdf.rs:66-78
-    const Mat m = mat_of_kind<KIND>(m_);
+__device__ __noinline__ f3 bsdf_eval(const DScene& sc, const Mat& m, const Frame& fr, f3 wo_w, f3 wi_w, uint32_t flags) { // bsdf.rs:66-78
     const f3 wo = unit(to_shading(fr, wo_w)), wi = unit(to_shading(fr, wi_w));
     if (wo.z * wi.z > 0.0f) flags &= ~(uint32_t)BX_TRANSMISSION; else flags &= ~(uint32_t)BX_REFLECTION;
     f3 acc = splat(0.0f);
 #pragma unroll 1
     for (int i = 0; i < 2; ++i) {
         int kind; uint32_t type; f3 col;
-        if (lobe_of(m, i, kind, type, col) && type_matches(type, flags)) acc = acc + lobe_eval<KIND>(sc, m, kind, col, wo, wi);
+        if (lobe_of<KIND>(m, i, kind, type, col) && type_matches(type, flags)) acc = acc + lobe_eval<KIND>(sc, m, kind, col, wo, wi);
     }
     return acc;
 }
 template <int KIND = -1>
-__device__ __noinline__ float bsdf_pdf(const Mat& m_, const Frame& fr, f3 wo_w, f3 wi_w, uint32_t flags) { // bsdf.rs:114-125
-    const Mat m = mat_of_kind<KIND>(m_);
+__device__ __noinline__ float bsdf_pdf(const Mat& m, const Frame& fr, f3 wo_w, f3 wi_w, uint32_t flags) { // bsdf.rs:114-125
     const f3 wo = unit(to_shading(fr, wo_w)), wi = unit(to_shading(fr, wi_w));
     float pdf = 0.0f; int n = 0;
 #pragma unroll 1
     for (int i = 0; i < 2; ++i) {
         int kind; uint32_t type; f3 col;
-        if (lobe_of(m, i, kind, type, col) && type_matches(type, flags)) { pdf = pdf + lobe_pdf<KIND>(m, kind, wo, wi); n++; }
+        if (lobe_of<KIND>(m, i, kind, type, col) && type_matches(type, flags)) { pdf = pdf + lobe_pdf<KIND>(m, kind, wo, wi); n++; }
     }
     return n > 0 ? ieee_div(pdf, (float)n) : 0.0f;
 }
 template <int KIND = -1>
-__device__ __noinline__ void bsdf_sample(const DScene& sc, const Mat& m_, const Frame& fr, f3 wo_w, uint32_t flags, float u0, float u1, float uc,
+__device__ __noinline__ void bsdf_sample(const DScene& sc, const Mat& m, const Frame& fr, f3 wo_w, uint32_t flags, float u0, float u1, float uc,
                                          f3& f, f3& wi_w, float& pdf, uint32_t& sampled) { // bsdf.rs:85-112
-    const Mat m = mat_of_kind<KIND>(m_);
     int n_matching = 0;
-    for (int i = 0; i < 2; ++i) { int k; uint32_t t; f3 c; if (lobe_of(m, i, k, t, c) && type_matches(t, flags)) n_matching++; }
+    for (int i = 0; i < 2; ++i) { int k; uint32_t t; f3 c; if (lobe_of<KIND>(m, i, k, t, c) && type_matches(t, flags)) n_matching++; }
     if (n_matching == 0) { f = splat(0.0f); wi_w = splat(0.0f); pdf = 0.0f; sampled = 0; return; }
     uint32_t comp = f2u(uc * (float)n_matching);
     if (comp > (uint32_t)n_matching - 1) comp = n_matching - 1;
     int kind = 0; uint32_t type = 0; f3 col = splat(0.0f);
     for (int i = 0, k = 0; i < 2; ++i) {
         int kk; uint32_t tt; f3 cc;
-        if (lobe_of(m, i, kk, tt, cc) && type_matches(tt, flags)) { if ((uint32_t)k == comp) { kind = kk; type = tt; col = cc; break; } k++; }
+        if (lobe_of<KIND>(m, i, kk, tt, cc) && type_matches(tt, flags)) { if ((uint32_t)k == comp) { kind = kk; type = tt; col = cc; break; } k++; }
     }
     const f3 wo = unit(to_shading(fr, wo_w));
     f3 wi;
