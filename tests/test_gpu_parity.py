@@ -268,6 +268,19 @@ def test_box_hit_finite_selftest_and_forced_literal_path():
     assert g.render_samples(**kw)[0].tobytes() == ref.tobytes()
 
 
+def test_split_shade_buckets_and_kind_instantiations_agree():
+    """Split shading with / without the material buckets and the matte instantiations, and the fused kernel: one result."""
+    desc = SB.scene_materials_zoo(64, 64, 8, SB.synthetic_merl_table()).finish()
+    g, o = both(desc)
+    kw = dict(sample_first=0, sample_count=4, seed=11)
+    ref = o.render_samples(**kw)[0].tobytes()
+    for split, sort, kind in ((-1, 1, 1), (1, 1, 0), (1, 0, 0), (0, 1, 1)):
+        g.set_option("shade.split", split); g.set_option("shade.sort", sort); g.set_option("shade.kind", kind)
+        assert g.render_samples(**kw)[0].tobytes() == ref, (split, sort, kind)
+        film, st = g.render(**kw)
+        assert st.camera_samples == 64 * 64 * 4 and np.isfinite(film).all()
+
+
 def test_full_size_properties_c4():
     """BASELINE-size workload (1M triangles, 1920x1080): size-independent properties instead of an oracle run."""
     g = api.Scene(SB.scene_c4(1_000_000, 1920, 1080, 4096).finish())
