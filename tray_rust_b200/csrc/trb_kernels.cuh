@@ -2130,7 +2130,7 @@ __global__ void __launch_bounds__(128, MINB) k_wf_trace(const __grid_constant__ 
             const int thr_o = (int)(sched & 255u);
             for (;;) {
 #pragma unroll
-                for (int k = 0; k < WF_BURST; ++k)
+                for (int k = 0; k < WF_BURST; ++k) // (bursts of 4 and two triangles per triangle phase were measured on the v2 kernel: 87.6 / 87.3 vs 87.2 ms, profiles/r02_c28_tri2_burst4.log)
                     if (trace_is_node(t.cur)) {
                         if (PIPE != 0 && !QUADS) step_nodes2<STATS, (PIPE & 1) != 0>(t, stack, cnt, rp.error_flag);
                         else step_nodes<STATS, QUADS>(t, stack, cnt, rp.error_flag);
