@@ -572,7 +572,7 @@ __global__ void k_selftest_box(uint32_t n, uint32_t seed, unsigned long long* ou
 }
 // step_nodes for pair records with box_hit_finite for the lanes whose ray is all-finite (operations per ray, hits, t and
 // counters unchanged). What else was tried on this micro-step in round 2 and measured slower on C4, per-sample radiance
-// bit-identical (profiles/r02_c10_sweep_*.log): issuing the next record's load as soon as a lane knows its next node
+// bit-identical (profiles/r02_c10_sweep_fetch_experiments.log): issuing the next record's load as soon as a lane knows its next node
 // (+12 %: lanes on different paths of the divergent push / pop code write the same registers and the warp-wide scoreboard
 // serialises the loads), the same through one convergent load point after the first pop attempt (+15 %),
 // prefetch.global.L1 of the near child / both children / the next node (+15 % / +60 % / +14 %: the instruction is ten times
